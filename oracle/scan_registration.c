@@ -1,0 +1,302 @@
+/* TEST INFRASTRUCTURE -- CPU oracle (see vlo_oracle.h header comment; parity unpinned).
+ *
+ * Restates MultiScanRegistration::process + BasicScanRegistration::extractFeatures of the LOAM
+ * fork the reference depends on (knobs from
+ * gtsam_fusion/config/carla/loam_params.yaml:3,22-31).  Sequential, one ring / one sector at a
+ * time, exactly in upstream's evaluation order: this is the spec the CUDA kernels are held to.
+ */
+#include "vlo_oracle.h"
+#include "detmath.h"
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+
+#define ORC_PI 3.14159265358979323846
+
+void orc_default_config(orc_config *c)
+{
+    c->scan_period = 0.1f;
+    c->n_rings = 16; c->lower_deg = -15.0f; c->upper_deg = 15.0f;
+    c->feature_regions = 6;
+    c->curvature_region = 5;
+    c->max_corner_sharp = 2;
+    c->max_corner_less_sharp = 20;
+    c->max_surface_flat = 4;
+    c->surface_curvature_threshold = 0.1f;
+    c->less_flat_filter_size = 0.2f;
+    c->odom_max_iterations = 25;
+    c->odom_delta_t_abort = 0.05f;
+    c->odom_delta_r_abort = 0.05f;
+    c->odom_degen_eig = 30.0f;
+    c->map_max_iterations = 10;
+    c->map_delta_t_abort = 0.05f;
+    c->map_delta_r_abort = 0.05f;
+    c->map_degen_eig = 40.0f;
+    c->deskew = 1;
+    c->odom_forward_bound_quirk = 0;
+    c->dopt_rot_threshold = 11.5f;
+    c->dopt_trans_threshold = 28.9f;
+}
+
+/* MultiScanMapper::getRingForAngle: int(((angle*180/M_PI) - lower) * factor + 0.5) */
+static int ring_for_angle(const orc_config *c, float angle)
+{
+    float factor = (float)(c->n_rings - 1) / (c->upper_deg - c->lower_deg);
+    float a180 = angle * 180.0f;
+    double v = ((double)a180 / ORC_PI - (double)c->lower_deg) * (double)factor + 0.5;
+    return (int)v;
+}
+
+int orc_organise(const orc_config *c, const float *raw, int n, int stride,
+                 orc_pt *out, int *ring_start, int *src_index)
+{
+    const int R = c->n_rings;
+    for (int r = 0; r <= R; r++) ring_start[r] = 0;
+    if (n <= 0) return 0;
+    int *ring = (int *)malloc(sizeof(int) * (size_t)n);
+    float *inten = (float *)malloc(sizeof(float) * (size_t)n);
+
+    float startOri = -orc_atan2f(raw[1], raw[0]);
+    float endOri = -orc_atan2f(raw[(size_t)(n - 1) * stride + 1], raw[(size_t)(n - 1) * stride]) + 2.0f * (float)ORC_PI;
+    if ((double)(endOri - startOri) > 3 * ORC_PI) endOri = (float)((double)endOri - 2 * ORC_PI);
+    else if ((double)(endOri - startOri) < ORC_PI) endOri = (float)((double)endOri + 2 * ORC_PI);
+
+    int halfPassed = 0;
+    int *count = (int *)calloc((size_t)R, sizeof(int));
+    for (int i = 0; i < n; i++) {
+        const float *p = raw + (size_t)i * stride;
+        float x = p[1], y = p[2], z = p[0];          /* LOAM frame: x<-y, y<-z, z<-x */
+        ring[i] = -1;
+        if (!isfinite(x) || !isfinite(y) || !isfinite(z)) continue;
+        if ((x * x + y * y) + z * z < 0.0001f) continue;
+        float angle = orc_atanf(y / sqrtf(x * x + z * z));
+        int id = ring_for_angle(c, angle);
+        if (id >= R || id < 0) continue;
+        float ori = -orc_atan2f(x, z);
+        if (!halfPassed) {
+            if ((double)ori < (double)startOri - ORC_PI / 2) ori = (float)((double)ori + 2 * ORC_PI);
+            else if ((double)ori > (double)startOri + ORC_PI * 3 / 2) ori = (float)((double)ori - 2 * ORC_PI);
+            if ((double)(ori - startOri) > ORC_PI) halfPassed = 1;
+        } else {
+            ori = (float)((double)ori + 2 * ORC_PI);
+            if ((double)ori < (double)endOri - ORC_PI * 3 / 2) ori = (float)((double)ori + 2 * ORC_PI);
+            else if ((double)ori > (double)endOri + ORC_PI / 2) ori = (float)((double)ori - 2 * ORC_PI);
+        }
+        float relTime = c->scan_period * (ori - startOri) / (endOri - startOri);
+        ring[i] = id;
+        inten[i] = (float)id + relTime;
+        count[id]++;
+    }
+    for (int r = 0; r < R; r++) ring_start[r + 1] = ring_start[r] + count[r];
+    int *cursor = (int *)malloc(sizeof(int) * (size_t)R);
+    memcpy(cursor, ring_start, sizeof(int) * (size_t)R);
+    for (int i = 0; i < n; i++) {
+        if (ring[i] < 0) continue;
+        const float *p = raw + (size_t)i * stride;
+        int o = cursor[ring[i]]++;
+        out[o].x = p[1]; out[o].y = p[2]; out[o].z = p[0]; out[o].w = inten[i];
+        if (src_index) src_index[o] = i;
+    }
+    int total = ring_start[R];
+    free(ring); free(inten); free(count); free(cursor);
+    return total;
+}
+
+static inline float sqdiff(const orc_pt *a, const orc_pt *b)
+{
+    float dx = a->x - b->x, dy = a->y - b->y, dz = a->z - b->z;
+    return (dx * dx + dy * dy) + dz * dz;
+}
+static inline float sqdiff_w(const orc_pt *a, const orc_pt *b, float wb)
+{
+    float dx = a->x - b->x * wb, dy = a->y - b->y * wb, dz = a->z - b->z * wb;
+    return (dx * dx + dy * dy) + dz * dz;
+}
+static inline float sqnorm(const orc_pt *a) { return (a->x * a->x + a->y * a->y) + a->z * a->z; }
+
+/* BasicScanRegistration::markAsPicked */
+static void mark_as_picked(const orc_pt *cloud, uint8_t *picked, int K, int idx, int scan_start)
+{
+    int s = idx - scan_start;
+    picked[s] = 1;
+    for (int i = 1; i <= K; i++) {
+        if (sqdiff(&cloud[idx + i], &cloud[idx + i - 1]) > 0.05) break;   /* double literal upstream */
+        picked[s + i] = 1;
+    }
+    for (int i = 1; i <= K; i++) {
+        if (sqdiff(&cloud[idx - i], &cloud[idx - i + 1]) > 0.05) break;
+        picked[s - i] = 1;
+    }
+}
+
+/* PCL VoxelGrid<PointXYZI> (downsample_all_data) restated: voxel key from floor(p/leaf) relative
+ * to the cloud's min corner, output ordered by ascending voxel key, centroid = sequential float
+ * sum in input order / count.  (PCL sorts with std::sort, whose order inside one voxel is
+ * unspecified; frozen here as input order.) */
+typedef struct { long long key; int order; } vox_ent;
+static int vox_cmp(const void *a, const void *b)
+{
+    const vox_ent *x = (const vox_ent *)a, *y = (const vox_ent *)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return x->order - y->order;
+}
+static int voxel_downsample(const orc_pt *in, int n, float leaf, orc_pt *out)
+{
+    if (n == 0) return 0;
+    float inv = 1.0f / leaf;
+    float mn[3] = { in[0].x, in[0].y, in[0].z }, mx[3] = { in[0].x, in[0].y, in[0].z };
+    for (int i = 1; i < n; i++) {
+        if (in[i].x < mn[0]) mn[0] = in[i].x; if (in[i].x > mx[0]) mx[0] = in[i].x;
+        if (in[i].y < mn[1]) mn[1] = in[i].y; if (in[i].y > mx[1]) mx[1] = in[i].y;
+        if (in[i].z < mn[2]) mn[2] = in[i].z; if (in[i].z > mx[2]) mx[2] = in[i].z;
+    }
+    int minb[3], maxb[3];
+    for (int a = 0; a < 3; a++) { minb[a] = (int)floorf(mn[a] * inv); maxb[a] = (int)floorf(mx[a] * inv); }
+    long long d0 = maxb[0] - minb[0] + 1, d1 = maxb[1] - minb[1] + 1;
+    vox_ent *e = (vox_ent *)malloc(sizeof(vox_ent) * (size_t)n);
+    for (int i = 0; i < n; i++) {
+        long long i0 = (long long)((int)floorf(in[i].x * inv) - minb[0]);
+        long long i1 = (long long)((int)floorf(in[i].y * inv) - minb[1]);
+        long long i2 = (long long)((int)floorf(in[i].z * inv) - minb[2]);
+        e[i].key = i0 + i1 * d0 + i2 * d0 * d1;
+        e[i].order = i;
+    }
+    qsort(e, (size_t)n, sizeof(vox_ent), vox_cmp);
+    int m = 0;
+    for (int i = 0; i < n;) {
+        int j = i;
+        float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f;
+        while (j < n && e[j].key == e[i].key) {
+            const orc_pt *p = &in[e[j].order];
+            sx += p->x; sy += p->y; sz += p->z; sw += p->w;
+            j++;
+        }
+        float cnt = (float)(j - i);
+        out[m].x = sx / cnt; out[m].y = sy / cnt; out[m].z = sz / cnt; out[m].w = sw / cnt;
+        m++;
+        i = j;
+    }
+    free(e);
+    return m;
+}
+
+void orc_extract(const orc_config *c, const orc_pt *cloud, const int *ring_start,
+                 int8_t *label, float *curvature, uint8_t *picked_out,
+                 int *sharp_idx, int *less_sharp_idx, int *flat_idx,
+                 orc_pt *less_flat, int *lsharp_ring_start, int *lflat_ring_start,
+                 orc_feature_counts *counts)
+{
+    const int R = c->n_rings, K = c->curvature_region, NR = c->feature_regions;
+    const float thr = c->surface_curvature_threshold;
+    int total = ring_start[R];
+    memset(label, 0, (size_t)total);
+    memset(curvature, 0, sizeof(float) * (size_t)total);
+    if (picked_out) memset(picked_out, 0, (size_t)total);
+    int n_sharp = 0, n_ls = 0, n_flat = 0, n_lf = 0;
+    int max_ring = 0;
+    for (int r = 0; r < R; r++) { int s = ring_start[r + 1] - ring_start[r]; if (s > max_ring) max_ring = s; }
+    uint8_t *picked = (uint8_t *)malloc((size_t)max_ring + 16);
+    int *sortidx = (int *)malloc(sizeof(int) * ((size_t)max_ring + 1));
+    orc_pt *cand = (orc_pt *)malloc(sizeof(orc_pt) * ((size_t)max_ring + 1));
+
+    for (int r = 0; r < R; r++) {
+        lsharp_ring_start[r] = n_ls;
+        lflat_ring_start[r] = n_lf;
+        int start = ring_start[r], end = ring_start[r + 1] - 1;   /* inclusive, as _scanIndices */
+        if (ring_start[r + 1] - ring_start[r] <= 0) continue;
+        if (end <= start + 2 * K) continue;                       /* "skip empty scans" */
+        int scan_size = end - start + 1;
+        memset(picked, 0, (size_t)scan_size);
+        int n_cand = 0;
+
+        /* setScanBuffersFor: occlusion / parallel-beam rejection */
+        for (int i = start + K; i < end - K; i++) {
+            const orc_pt *prev = &cloud[i - 1], *pt = &cloud[i], *next = &cloud[i + 1];
+            float diffNext = sqdiff(next, pt);
+            if (diffNext > 0.1) {                 /* double literals upstream: compare in double */
+                float depth1 = sqrtf(sqnorm(pt));
+                float depth2 = sqrtf(sqnorm(next));
+                if (depth1 > depth2) {
+                    float wd = sqrtf(sqdiff_w(next, pt, depth2 / depth1)) / depth2;
+                    if (wd < 0.1) {
+                        for (int m = 0; m <= K; m++) picked[i - start - K + m] = 1;
+                        continue;
+                    }
+                } else {
+                    float wd = sqrtf(sqdiff_w(pt, next, depth1 / depth2)) / depth1;
+                    if (wd < 0.1) {
+                        for (int m = 0; m <= K; m++) picked[i - start + 1 + m] = 1;
+                    }
+                }
+            }
+            float diffPrev = sqdiff(pt, prev);
+            float dis = sqnorm(pt);
+            if (diffNext > 0.0002 * dis && diffPrev > 0.0002 * dis) picked[i - start] = 1;
+        }
+
+        for (int j = 0; j < NR; j++) {
+            int sp = ((start + K) * (NR - j) + (end - K) * j) / NR;
+            int ep = ((start + K) * (NR - 1 - j) + (end - K) * (j + 1)) / NR - 1;
+            if (ep <= sp) continue;
+            int region = ep - sp + 1;
+
+            /* setRegionBuffersFor: curvature + stable insertion sort ascending */
+            float w = (float)(-2 * K);
+            for (int i = sp; i <= ep; i++) {
+                float dx = w * cloud[i].x, dy = w * cloud[i].y, dz = w * cloud[i].z;
+                for (int m = 1; m <= K; m++) {
+                    dx += cloud[i + m].x + cloud[i - m].x;
+                    dy += cloud[i + m].y + cloud[i - m].y;
+                    dz += cloud[i + m].z + cloud[i - m].z;
+                }
+                curvature[i] = (dx * dx + dy * dy) + dz * dz;
+                sortidx[i - sp] = i;
+            }
+            for (int i = 1; i < region; i++) {
+                int v = sortidx[i];
+                float cv = curvature[v];
+                int j2 = i;
+                while (j2 >= 1 && cv < curvature[sortidx[j2 - 1]]) { sortidx[j2] = sortidx[j2 - 1]; j2--; }
+                sortidx[j2] = v;
+            }
+
+            /* corners: from the largest curvature down */
+            int largest = 0;
+            for (int k = region; k > 0 && largest < c->max_corner_less_sharp;) {
+                int idx = sortidx[--k];
+                if (picked[idx - start] == 0 && curvature[idx] > thr) {
+                    largest++;
+                    if (largest <= c->max_corner_sharp) {
+                        label[idx] = 2;
+                        sharp_idx[n_sharp++] = idx;
+                    } else {
+                        label[idx] = 1;
+                    }
+                    less_sharp_idx[n_ls++] = idx;
+                    mark_as_picked(cloud, picked, K, idx, start);
+                }
+            }
+            /* flats: from the smallest curvature up */
+            int smallest = 0;
+            for (int k = 0; k < region && smallest < c->max_surface_flat; k++) {
+                int idx = sortidx[k];
+                if (picked[idx - start] == 0 && curvature[idx] < thr) {
+                    smallest++;
+                    label[idx] = -1;
+                    flat_idx[n_flat++] = idx;
+                    mark_as_picked(cloud, picked, K, idx, start);
+                }
+            }
+            /* less flat candidates: everything not a corner */
+            for (int i = sp; i <= ep; i++)
+                if (label[i] <= 0) cand[n_cand++] = cloud[i];
+        }
+        n_lf += voxel_downsample(cand, n_cand, c->less_flat_filter_size, less_flat + n_lf);
+        if (picked_out) memcpy(picked_out + start, picked, (size_t)scan_size);
+    }
+    lsharp_ring_start[R] = n_ls;
+    lflat_ring_start[R] = n_lf;
+    /* rings skipped above still need monotone offsets */
+    counts->n_sharp = n_sharp; counts->n_less_sharp = n_ls; counts->n_flat = n_flat; counts->n_less_flat = n_lf;
+    free(picked); free(sortidx); free(cand);
+}
