@@ -8,9 +8,8 @@
  *
  * Frozen choices (upstream leaves them to Eigen / the compiler / the fork):
  *  R1  AtA / AtB summation order: terms indexed by query (sharp queries first, then flat; a
- *      rejected query contributes zeros); chunks of 256 queries; inside a chunk 8 groups of 32
- *      reduced by s[i] += s[i+stride], stride 16,8,4,2,1, the 8 group sums by stride 4,2,1;
- *      chunk sums accumulated sequentially.  float32 throughout, no contraction.
+ *      rejected query contributes zeros); three-level blocked summation (32 queries, 32 blocks,
+ *      then sequential), see orc_reduce_r1.  float32 throughout, no contraction.
  *  R2  P = sum over kept eigenvectors v v^T (== upstream matV^-1 matV2 for orthonormal V).
  *  R3  OptStatus.hessian = AtA of the LAST linearisation, native LOAM order (rx ry rz tx ty tz).
  *  R4  cov = sigma^2 (AtA)^-1, sigma^2 = sum (s d)^2 / (n - 6), float64.
@@ -157,23 +156,24 @@ void orc_odometry_associate(const orc_config *c, const float *T,
     orc_kdtree_free(kc); orc_kdtree_free(ks);
 }
 
-/* R1 reduction of terms[Q][NTERM] */
+/* R1 reduction of terms[Q][nterm]: three-level blocked summation, float32.
+ *   level 1: blocks of 32 consecutive queries, each summed sequentially from its first element;
+ *   level 2: blocks of 32 consecutive level-1 sums (1024 queries), summed sequentially;
+ *   level 3: level-2 sums added sequentially. */
 void orc_reduce_r1(const float *terms, int Q, int nterm, float *total)
 {
-    float s[256];
-    for (int e = 0; e < nterm; e++) total[e] = 0.0f;
-    for (int c0 = 0; c0 < Q; c0 += 256) {
-        for (int e = 0; e < nterm; e++) {
-            for (int i = 0; i < 256; i++) s[i] = (c0 + i < Q) ? terms[(size_t)(c0 + i) * nterm + e] : 0.0f;
-            for (int g = 0; g < 8; g++)
-                for (int stride = 16; stride >= 1; stride >>= 1)
-                    for (int i = 0; i < stride; i++) s[g * 32 + i] = s[g * 32 + i] + s[g * 32 + i + stride];
-            float gs[8];
-            for (int g = 0; g < 8; g++) gs[g] = s[g * 32];
-            for (int stride = 4; stride >= 1; stride >>= 1)
-                for (int i = 0; i < stride; i++) gs[i] = gs[i] + gs[i + stride];
-            total[e] = total[e] + gs[0];
+    for (int e = 0; e < nterm; e++) {
+        float l3 = 0.0f;
+        for (int c2 = 0; c2 < Q; c2 += 1024) {
+            float l2 = 0.0f;
+            for (int c1 = c2; c1 < Q && c1 < c2 + 1024; c1 += 32) {
+                float l1 = 0.0f;
+                for (int i = c1; i < Q && i < c1 + 32; i++) l1 = l1 + terms[(size_t)i * nterm + e];
+                l2 = l2 + l1;
+            }
+            l3 = l3 + l2;
         }
+        total[e] = l3;
     }
 }
 

@@ -129,54 +129,58 @@ static void mark_as_picked(const orc_pt *cloud, uint8_t *picked, int K, int idx,
     }
 }
 
-/* PCL VoxelGrid<PointXYZI> (downsample_all_data) restated: voxel key from floor(p/leaf) relative
- * to the cloud's min corner, output ordered by ascending voxel key, centroid = sequential float
- * sum in input order / count.  (PCL sorts with std::sort, whose order inside one voxel is
- * unspecified; frozen here as input order.) */
-typedef struct { long long key; int order; } vox_ent;
-static int vox_cmp(const void *a, const void *b)
-{
-    const vox_ent *x = (const vox_ent *)a, *y = (const vox_ent *)b;
-    if (x->key != y->key) return x->key < y->key ? -1 : 1;
-    return x->order - y->order;
-}
+/* pcl::VoxelGrid<PointXYZI> (leaf = lessFlatFilterSize, loam_params.yaml:31) restated: points are
+ * grouped by voxel (floor(p * 1/leaf) per axis) and each voxel emits the centroid of its members
+ * (all four fields).  Two things PCL leaves to std::sort / float summation order are FROZEN here so
+ * that a parallel implementation can be bit-exact:
+ *   V1  output order = order of first appearance of the voxel along the ring (PCL: ascending linear
+ *       voxel index, an artefact of its sort key);
+ *   V2  centroid = voxel origin + mean of the members' offsets, the offsets quantised to 2^-20 m and
+ *       summed as integers (order independent; <= 0.5 um from any float-order sum);
+ *       intensity likewise on its fractional part (rel-time), integer part = ring. */
+typedef struct { int ix, iy, iz; int first; int cnt; long long sx, sy, sz, sw; } vox_grp;
+#define VOX_Q 1048576.0f
 static int voxel_downsample(const orc_pt *in, int n, float leaf, orc_pt *out)
 {
     if (n == 0) return 0;
     float inv = 1.0f / leaf;
-    float mn[3] = { in[0].x, in[0].y, in[0].z }, mx[3] = { in[0].x, in[0].y, in[0].z };
-    for (int i = 1; i < n; i++) {
-        if (in[i].x < mn[0]) mn[0] = in[i].x; if (in[i].x > mx[0]) mx[0] = in[i].x;
-        if (in[i].y < mn[1]) mn[1] = in[i].y; if (in[i].y > mx[1]) mx[1] = in[i].y;
-        if (in[i].z < mn[2]) mn[2] = in[i].z; if (in[i].z > mx[2]) mx[2] = in[i].z;
-    }
-    int minb[3], maxb[3];
-    for (int a = 0; a < 3; a++) { minb[a] = (int)floorf(mn[a] * inv); maxb[a] = (int)floorf(mx[a] * inv); }
-    long long d0 = maxb[0] - minb[0] + 1, d1 = maxb[1] - minb[1] + 1;
-    vox_ent *e = (vox_ent *)malloc(sizeof(vox_ent) * (size_t)n);
-    for (int i = 0; i < n; i++) {
-        long long i0 = (long long)((int)floorf(in[i].x * inv) - minb[0]);
-        long long i1 = (long long)((int)floorf(in[i].y * inv) - minb[1]);
-        long long i2 = (long long)((int)floorf(in[i].z * inv) - minb[2]);
-        e[i].key = i0 + i1 * d0 + i2 * d0 * d1;
-        e[i].order = i;
-    }
-    qsort(e, (size_t)n, sizeof(vox_ent), vox_cmp);
+    int cap = 1; while (cap < 2 * n) cap <<= 1;
+    int *table = (int *)malloc(sizeof(int) * (size_t)cap);
+    for (int i = 0; i < cap; i++) table[i] = -1;
+    vox_grp *g = (vox_grp *)malloc(sizeof(vox_grp) * (size_t)n);
     int m = 0;
-    for (int i = 0; i < n;) {
-        int j = i;
-        float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f;
-        while (j < n && e[j].key == e[i].key) {
-            const orc_pt *p = &in[e[j].order];
-            sx += p->x; sy += p->y; sz += p->z; sw += p->w;
-            j++;
+    for (int i = 0; i < n; i++) {
+        int ix = (int)floorf(in[i].x * inv), iy = (int)floorf(in[i].y * inv), iz = (int)floorf(in[i].z * inv);
+        unsigned h = ((unsigned)ix * 73856093u) ^ ((unsigned)iy * 19349663u) ^ ((unsigned)iz * 83492791u);
+        int slot = (int)(h & (unsigned)(cap - 1));
+        int gi = -1;
+        while (table[slot] >= 0) {
+            vox_grp *c = &g[table[slot]];
+            if (c->ix == ix && c->iy == iy && c->iz == iz) { gi = table[slot]; break; }
+            slot = (slot + 1) & (cap - 1);
         }
-        float cnt = (float)(j - i);
-        out[m].x = sx / cnt; out[m].y = sy / cnt; out[m].z = sz / cnt; out[m].w = sw / cnt;
-        m++;
-        i = j;
+        if (gi < 0) {
+            gi = m++;
+            table[slot] = gi;
+            g[gi].ix = ix; g[gi].iy = iy; g[gi].iz = iz; g[gi].first = i; g[gi].cnt = 0;
+            g[gi].sx = g[gi].sy = g[gi].sz = g[gi].sw = 0;
+        }
+        float ox = (float)ix * leaf, oy = (float)iy * leaf, oz = (float)iz * leaf;
+        g[gi].sx += (long long)(int)rintf((in[i].x - ox) * VOX_Q);
+        g[gi].sy += (long long)(int)rintf((in[i].y - oy) * VOX_Q);
+        g[gi].sz += (long long)(int)rintf((in[i].z - oz) * VOX_Q);
+        g[gi].sw += (long long)(int)rintf((in[i].w - (float)(int)in[i].w) * VOX_Q);
+        g[gi].cnt++;
     }
-    free(e);
+    for (int k = 0; k < m; k++) {
+        double c = (double)g[k].cnt;
+        float ox = (float)g[k].ix * leaf, oy = (float)g[k].iy * leaf, oz = (float)g[k].iz * leaf;
+        out[k].x = ox + (float)(((double)g[k].sx / c) * (1.0 / 1048576.0));
+        out[k].y = oy + (float)(((double)g[k].sy / c) * (1.0 / 1048576.0));
+        out[k].z = oz + (float)(((double)g[k].sz / c) * (1.0 / 1048576.0));
+        out[k].w = (float)(int)in[g[k].first].w + (float)(((double)g[k].sw / c) * (1.0 / 1048576.0));
+    }
+    free(table); free(g);
     return m;
 }
 

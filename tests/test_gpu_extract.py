@@ -1,0 +1,93 @@
+"""Parity of K0 (organise) and K1 (feature extraction) with the oracle: bit-exact."""
+import numpy as np
+import pytest
+
+from tests import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfgs(orc, lidar, **kw):
+    from vil_sensor_fusion_b200 import api
+    ocfg = orc.default_config(lidar)
+    gcfg = api.default_config(lidar, **kw)
+    return ocfg, gcfg
+
+
+def _check_scan(orc, h, ocfg, scan_idx, raw):
+    cloud_o, rs_o, src_o = orc.organise(ocfg, raw)
+    cloud_g, rs_g, src_g = h.get_cloud(scan_idx)
+    assert cloud_g.shape == cloud_o.shape
+    np.testing.assert_array_equal(rs_g, rs_o)
+    np.testing.assert_array_equal(src_g, src_o)
+    np.testing.assert_array_equal(cloud_g.view(np.uint32), cloud_o.view(np.uint32))
+    fo = orc.extract(ocfg, cloud_o, rs_o)
+    fg = h.get_features(scan_idx)
+    np.testing.assert_array_equal(fg["curvature"].view(np.uint32), fo["curvature"].view(np.uint32))
+    np.testing.assert_array_equal(fg["picked"], fo["picked"])
+    np.testing.assert_array_equal(fg["label"], fo["label"])
+    for k in ("sharp_idx", "less_sharp_idx", "flat_idx", "less_sharp_ring_start", "less_flat_ring_start"):
+        np.testing.assert_array_equal(fg[k], fo[k], err_msg=k)
+    assert fg["less_flat"].shape == fo["less_flat"].shape
+    np.testing.assert_array_equal(fg["less_flat"].view(np.uint32), fo["less_flat"].view(np.uint32))
+    return fo
+
+
+def test_vlp16_batch_bit_exact(orc):
+    from vil_sensor_fusion_b200 import api
+    ocfg, gcfg = _cfgs(orc, "VLP-16", max_scans=4, max_points=32768)
+    raws = [scenes.vlp16_scan(0.0), scenes.vlp16_scan(0.1, noise=0.02, seed=1), scenes.ragged_scan(),
+            scenes.vlp16_scan(0.3, rolling=False)]
+    with api.Handle(gcfg) as h:
+        h.upload(raws)
+        h.organise()
+        h.extract()
+        for i, raw in enumerate(raws):
+            fo = _check_scan(orc, h, ocfg, i, raw)
+            assert len(fo["sharp_idx"]) > 20 and len(fo["flat_idx"]) > 100
+
+
+def test_hdl64_bit_exact(orc):
+    from vil_sensor_fusion_b200 import api
+    ocfg, gcfg = _cfgs(orc, "HDL-64E", max_scans=2, max_points=131072)
+    raws = [scenes.hdl64_scan(0.0), scenes.hdl64_scan(0.1, noise=0.02, seed=5)]
+    with api.Handle(gcfg) as h:
+        h.upload(raws)
+        h.organise()
+        h.extract()
+        for i, raw in enumerate(raws):
+            _check_scan(orc, h, ocfg, i, raw)
+
+
+def test_edge_cases(orc):
+    """empty scan, tiny scan (rings shorter than 2K+1), single ring, corridor with missing returns."""
+    from vil_sensor_fusion_b200 import api, synth
+    ocfg, gcfg = _cfgs(orc, "VLP-16", max_scans=4, max_points=32768)
+    full = scenes.vlp16_scan(0.0)
+    tiny = full[:100].copy()
+    empty = np.zeros((0, 4), np.float32)
+    corridor = synth.make_scan(synth.scene_corridor(), "VLP-16", pose=(np.eye(3), np.zeros(3)), rolling=False)
+    short_rings = scenes.vlp16_scan(0.0, n_az=40)      # 40 points per ring: sequential sector path
+    raws = [tiny, empty, corridor, short_rings]
+    with api.Handle(gcfg) as h:
+        h.upload(raws)
+        h.organise()
+        h.extract()
+        for i, raw in enumerate(raws):
+            if raw.shape[0] == 0:
+                c = h.counts()[i]
+                assert c["n_valid"] == 0 and c["n_sharp"] == 0 and c["n_less_flat"] == 0
+                continue
+            _check_scan(orc, h, ocfg, i, raw)
+
+
+def test_ring_capacity_error(orc):
+    from vil_sensor_fusion_b200 import api
+    gcfg = api.default_config("VLP-16", max_scans=1, max_points=32768, max_ring_points=1024)
+    with api.Handle(gcfg) as h:
+        h.upload([scenes.vlp16_scan(0.0)])
+        h.organise()
+        h.extract()
+        with pytest.raises(api.VloError) as e:
+            h.synchronize()
+        assert e.value.code == -3

@@ -1,0 +1,251 @@
+"""Python host side of the C-ABI (ctypes): the handle the package's tooling uses.
+
+Mirrors the reference-facing surface: scans in (PointCloud2 payloads as float32 arrays), per-scan
+odometry + OptStatus-like results out, `(6,6,T)` Hessian stacks for the analysis tooling
+(vil_fusion/python/make_prettier_graphs.py:411-474,547-576 in the reference).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import Config, FeatureCounts, Preint, Result
+
+LIDAR = {"VLP-16": (-15.0, 15.0, 16), "HDL-32": (-30.67, 10.67, 32), "HDL-64E": (-24.9, 2.0, 64)}
+
+RESULT_DTYPE = np.dtype([
+    ("transform", "f4", 6), ("hessian", "f4", (6, 6)), ("eig", "f4", 6), ("P", "f4", (6, 6)),
+    ("is_degenerate", "i4"), ("iterations", "i4"), ("n_corr_edge", "i4"), ("n_corr_plane", "i4"),
+    ("logdet_rot", "f4"), ("logdet_trans", "f4"), ("pass_dopt", "i4"), ("status", "i4"), ("cov", "f8", (6, 6)),
+])
+assert RESULT_DTYPE.itemsize == C.sizeof(Result)
+
+PREINT_DTYPE = np.dtype([
+    ("dR", "f8", (3, 3)), ("dP", "f8", 3), ("dV", "f8", 3), ("dR_dbg", "f8", (3, 3)), ("dP_dba", "f8", (3, 3)),
+    ("dP_dbg", "f8", (3, 3)), ("dV_dba", "f8", (3, 3)), ("dV_dbg", "f8", (3, 3)), ("cov", "f8", (15, 15)),
+    ("dt", "f8"), ("n_integrated", "i4"), ("_pad", "i4"),
+])
+assert PREINT_DTYPE.itemsize == C.sizeof(Preint)
+
+
+class VloError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("vlo error %d: %s" % (code, msg))
+        self.code = code
+
+
+def default_config(lidar: str = "VLP-16", **kw) -> Config:
+    lib = _lib.load()
+    c = Config()
+    lib.vlo_default_config(C.byref(c))
+    if lib.vlo_set_lidar(C.byref(c), lidar.encode()) != 0:
+        raise ValueError("unknown lidar preset %r" % lidar)
+    for k, v in kw.items():
+        if not hasattr(c, k):
+            raise AttributeError(k)
+        setattr(c, k, v)
+    return c
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Handle:
+    """One vlo_handle: one CUDA stream + all device memory for a batch of scans."""
+
+    def __init__(self, cfg: Config):
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        rc = self.lib.vlo_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            raise VloError(rc, {-4: "no usable CUDA device (there is no CPU fallback)", -1: "invalid config"}.get(rc, "vlo_create failed"))
+        self.n_scans = 0
+
+    def close(self):
+        if self._h:
+            self.lib.vlo_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc < 0:
+            raise VloError(rc, self.lib.vlo_last_error(self._h).decode())
+        return rc
+
+    # ---- scans
+    def upload(self, scans, stride: int | None = None):
+        """scans: list of float32 (n_i, stride) arrays (host) -> resident batch."""
+        if isinstance(scans, np.ndarray) and scans.ndim == 2:
+            scans = [scans]
+        scans = [np.ascontiguousarray(s, np.float32) for s in scans]
+        stride = stride or scans[0].shape[1]
+        offs = np.zeros(len(scans) + 1, np.int32)
+        offs[1:] = np.cumsum([s.shape[0] for s in scans])
+        raw = np.concatenate(scans, axis=0) if len(scans) > 1 else scans[0]
+        if raw.shape[0] == 0:
+            raw = np.zeros((1, stride), np.float32)
+        self._check(self.lib.vlo_scans_upload(self._h, _ptr(raw), _ptr(offs), len(scans), stride, 0))
+        self.n_scans = len(scans)
+
+    def upload_raw(self, raw_ptr, offsets: np.ndarray, stride: int, on_device: bool):
+        offsets = np.ascontiguousarray(offsets, np.int32)
+        self._check(self.lib.vlo_scans_upload(self._h, _ptr(raw_ptr), _ptr(offsets), len(offsets) - 1, stride, int(on_device)))
+        self.n_scans = len(offsets) - 1
+
+    def organise(self):
+        self._check(self.lib.vlo_scans_organise(self._h))
+
+    def extract(self):
+        self._check(self.lib.vlo_scans_extract(self._h))
+
+    def synchronize(self):
+        self._check(self.lib.vlo_synchronize(self._h))
+
+    def launch_count(self) -> int:
+        return int(self.lib.vlo_launch_count(self._h))
+
+    def counts(self):
+        arr = (FeatureCounts * self.n_scans)()
+        self._check(self.lib.vlo_scans_counts(self._h, arr))
+        return [dict(n_valid=a.n_valid, n_sharp=a.n_sharp, n_less_sharp=a.n_less_sharp, n_flat=a.n_flat,
+                     n_less_flat=a.n_less_flat) for a in arr]
+
+    def get_cloud(self, scan: int):
+        c = self.counts()[scan]
+        n = c["n_valid"]
+        cloud = np.zeros((max(n, 1), 4), np.float32)
+        rs = np.zeros(self.cfg.n_rings + 1, np.int32)
+        src = np.zeros(max(n, 1), np.int32)
+        self._check(self.lib.vlo_scan_get_cloud(self._h, scan, _ptr(cloud), _ptr(rs), _ptr(src)))
+        return cloud[:n], rs, src[:n]
+
+    def get_features(self, scan: int):
+        c = self.counts()[scan]
+        n = c["n_valid"]
+        label = np.zeros(max(n, 1), np.int8)
+        curv = np.zeros(max(n, 1), np.float32)
+        picked = np.zeros(max(n, 1), np.uint8)
+        sharp = np.zeros(max(c["n_sharp"], 1), np.int32)
+        lsharp = np.zeros(max(c["n_less_sharp"], 1), np.int32)
+        flat = np.zeros(max(c["n_flat"], 1), np.int32)
+        lflat = np.zeros((max(c["n_less_flat"], 1), 4), np.float32)
+        lsr = np.zeros(self.cfg.n_rings + 1, np.int32)
+        lfr = np.zeros(self.cfg.n_rings + 1, np.int32)
+        self._check(self.lib.vlo_scan_get_features(self._h, scan, _ptr(label), _ptr(curv), _ptr(picked), _ptr(sharp),
+                                                   _ptr(lsharp), _ptr(flat), _ptr(lflat), _ptr(lsr), _ptr(lfr)))
+        return dict(label=label[:n], curvature=curv[:n], picked=picked[:n], sharp_idx=sharp[:c["n_sharp"]],
+                    less_sharp_idx=lsharp[:c["n_less_sharp"]], flat_idx=flat[:c["n_flat"]],
+                    less_flat=lflat[:c["n_less_flat"]], less_sharp_ring_start=lsr, less_flat_ring_start=lfr)
+
+    # ---- scan-to-scan
+    def register_pairs(self, last, cur, seeds=None, last_transforms=None) -> np.ndarray:
+        last = np.ascontiguousarray(last, np.int32)
+        cur = np.ascontiguousarray(cur, np.int32)
+        n = len(last)
+        seeds = None if seeds is None else np.ascontiguousarray(seeds, np.float32).reshape(n, 6)
+        lt = None if last_transforms is None else np.ascontiguousarray(last_transforms, np.float32).reshape(n, 6)
+        out = np.zeros(n, RESULT_DTYPE)
+        self._check(self.lib.vlo_register_pairs(self._h, _ptr(last), _ptr(cur), n, _ptr(seeds), _ptr(lt), _ptr(out)))
+        return out
+
+    def pair_correspondences(self, pair: int, rnd: int, n_sharp: int, n_flat: int):
+        ci = np.zeros((max(n_sharp, 1), 2), np.int32)
+        si = np.zeros((max(n_flat, 1), 3), np.int32)
+        self._check(self.lib.vlo_pair_get_correspondences(self._h, pair, rnd, _ptr(ci), _ptr(si)))
+        return ci[:n_sharp], si[:n_flat]
+
+    # ---- scan-to-map
+    def map_build(self, corner_xyzi, surf_xyzi):
+        c = np.ascontiguousarray(corner_xyzi, np.float32)
+        s = np.ascontiguousarray(surf_xyzi, np.float32)
+        self._check(self.lib.vlo_map_build(self._h, _ptr(c), c.shape[0], _ptr(s), s.shape[0], 0))
+
+    def register_map(self, scans, seeds) -> np.ndarray:
+        scans = np.ascontiguousarray(scans, np.int32)
+        seeds = np.ascontiguousarray(seeds, np.float32).reshape(len(scans), 6)
+        out = np.zeros(len(scans), RESULT_DTYPE)
+        self._check(self.lib.vlo_register_map(self._h, _ptr(scans), len(scans), _ptr(seeds), _ptr(out)))
+        return out
+
+    def map_correspondences(self, slot: int, n_corner: int, n_surf: int):
+        ci = np.zeros((max(n_corner, 1), 5), np.int32)
+        si = np.zeros((max(n_surf, 1), 5), np.int32)
+        self._check(self.lib.vlo_map_get_correspondences(self._h, slot, _ptr(ci), _ptr(si)))
+        return ci[:n_corner], si[:n_surf]
+
+    def map_knn(self, which: int, queries, k: int):
+        q = np.ascontiguousarray(queries, np.float32)
+        idx = np.zeros((q.shape[0], k), np.int32)
+        d2 = np.zeros((q.shape[0], k), np.float32)
+        self._check(self.lib.vlo_map_knn(self._h, which, _ptr(q), q.shape[0], k, _ptr(idx), _ptr(d2)))
+        return idx, d2
+
+    # ---- online
+    def process_scan(self, raw: np.ndarray, stamp: float = 0.0, want_map: bool = False):
+        raw = np.ascontiguousarray(raw, np.float32)
+        odom = Result()
+        mapped = Result() if want_map else None
+        rc = self._check(self.lib.vlo_process_scan(self._h, _ptr(raw), raw.shape[0], raw.shape[1], stamp,
+                                                   C.byref(odom), C.byref(mapped) if want_map else None))
+        o = np.frombuffer(bytes(odom), RESULT_DTYPE)[0]
+        m = np.frombuffer(bytes(mapped), RESULT_DTYPE)[0] if want_map else None
+        return rc, o, m
+
+    # ---- IMU
+    def imu_preintegrate_batch(self, t, acc, gyro, t0, t1, bias=None) -> np.ndarray:
+        t = np.ascontiguousarray(t, np.float64)
+        acc = np.ascontiguousarray(acc, np.float64)
+        gyro = np.ascontiguousarray(gyro, np.float64)
+        t0 = np.ascontiguousarray(t0, np.float64)
+        t1 = np.ascontiguousarray(t1, np.float64)
+        bias = np.zeros(6) if bias is None else np.ascontiguousarray(bias, np.float64)
+        out = np.zeros(len(t0), PREINT_DTYPE)
+        self._check(self.lib.vlo_imu_preintegrate_batch(self._h, _ptr(t), _ptr(acc), _ptr(gyro), len(t), _ptr(t0),
+                                                        _ptr(t1), _ptr(bias), len(t0), _ptr(out)))
+        return out
+
+
+def pose_diff(before7, after7):
+    out = np.zeros(7)
+    _lib.load().vlo_pose_diff(_ptr(np.ascontiguousarray(before7, np.float64)),
+                              _ptr(np.ascontiguousarray(after7, np.float64)), _ptr(out))
+    return out
+
+
+def dopt_gate(hessian, rot_thr=11.5, trans_thr=28.9):
+    Hm = np.ascontiguousarray(hessian, np.float32)
+    lr, lt = C.c_float(), C.c_float()
+    ok = _lib.load().vlo_dopt_gate(_ptr(Hm), rot_thr, trans_thr, C.byref(lr), C.byref(lt))
+    return bool(ok), lr.value, lt.value
+
+
+def accumulate_pose(sum_in, transform, fudge=1.0):
+    out = np.zeros(6, np.float32)
+    _lib.load().vlo_accumulate_pose(_ptr(np.ascontiguousarray(sum_in, np.float32)),
+                                    _ptr(np.ascontiguousarray(transform, np.float32)), fudge, _ptr(out))
+    return out
+
+
+def hessian_stack(results: np.ndarray) -> np.ndarray:
+    """(6,6,T) float64 array in the layout `apply_degen_function` consumes
+    (vil_fusion/python/make_prettier_graphs.py:547-576)."""
+    return np.ascontiguousarray(np.transpose(results["hessian"].astype(np.float64), (1, 2, 0)))

@@ -1,0 +1,153 @@
+// Voxel-hash grids (K2): device-side layout and the exact, warp-cooperative nearest-neighbour
+// search shared by scan-to-scan association (k3) and scan-to-map (k5).  Replaces
+// pcl::KdTreeFLANN::nearestKSearch as used by the `loam` nodelets.
+//
+// Layout (all grids of a set are contiguous so they clear with two memsets):
+//   keys  [G][ts]   packed cell coordinates (3 x 21 bit, biased), ~0 = empty, open addressing
+//   cnt   [G][ts]   points per cell during the build (counted down to 0 by the scatter pass)
+//   start [G][ts+1] exclusive scan of cnt in slot order: cell s owns sorted[start[s] .. start[s+1])
+//   sorted[G][max]  xyz + tag; tag = (ring << 24) | dense index of the point in its ring-major cloud
+// Exactness contract: neighbours compare by (d2, tie) lexicographically with
+// d2 = ((dx*dx) + (dy*dy)) + (dz*dz) in float32 (no FMA); shells of cells are visited outwards and
+// the search stops only when the k-th best distance is strictly inside the visited cube (minus a
+// slack that covers the rounding of floor(p * inv_cell)), so storage order never matters.
+#pragma once
+#include "vlo_internal.cuh"
+
+#define GRID_EMPTY 0xFFFFFFFFFFFFFFFFull
+
+struct GridSet {
+    float cell, inv_cell;
+    int ts;              // table size (power of two)
+    int max_pts;
+    int G;
+    unsigned long long *keys;
+    int *cnt;
+    int *start;
+    float4 *sorted;
+};
+
+__device__ __forceinline__ unsigned long long grid_key(int ix, int iy, int iz)
+{
+    return ((unsigned long long)(unsigned)(ix + (1 << 20)) << 42) | ((unsigned long long)(unsigned)(iy + (1 << 20)) << 21)
+         | (unsigned long long)(unsigned)(iz + (1 << 20));
+}
+__device__ __forceinline__ unsigned grid_hash(int ix, int iy, int iz)
+{
+    return ((unsigned)ix * 73856093u) ^ ((unsigned)iy * 19349663u) ^ ((unsigned)iz * 83492791u);
+}
+
+// returns slot of the cell or -1
+__device__ __forceinline__ int grid_find(const GridSet &gs, int g, int ix, int iy, int iz)
+{
+    const unsigned long long *keys = gs.keys + (size_t)g * gs.ts;
+    unsigned long long key = grid_key(ix, iy, iz);
+    int slot = (int)(grid_hash(ix, iy, iz) & (unsigned)(gs.ts - 1));
+    while (true) {
+        unsigned long long k = keys[slot];
+        if (k == key) return slot;
+        if (k == GRID_EMPTY) return -1;
+        slot = (slot + 1) & (gs.ts - 1);
+    }
+}
+
+// Candidate filters -------------------------------------------------------------------------------
+struct FilterAll {          // plain k-NN, ties -> lowest dense index
+    __device__ __forceinline__ bool operator()(unsigned tag, unsigned &tie) const { tie = tag & 0xFFFFFFu; return true; }
+};
+// upstream's partner loops: forward indices first (ascending), then backward
+// (descending); `ring_lo..ring_hi` admissible rings, `skip_ring` excluded (or -1), `same_ring_only`.
+struct FilterPartner {
+    int ind;        // dense index of the nearest neighbour
+    int ring_lo, ring_hi, skip_ring;
+    int fwd_bound;  // forward candidates need dense index < fwd_bound
+    __device__ __forceinline__ bool operator()(unsigned tag, unsigned &tie) const
+    {
+        int ring = (int)(tag >> 24), idx = (int)(tag & 0xFFFFFFu);
+        if (ring < ring_lo || ring > ring_hi || ring == skip_ring || idx == ind) return false;
+        if (idx > ind) { if (idx >= fwd_bound) return false; tie = (unsigned)(idx - ind); }
+        else tie = 0x40000000u + (unsigned)(ind - idx);
+        return true;
+    }
+};
+
+// K-best list kept sorted ascending by (d2 bits, tie) in registers.  Entries whose tag is
+// GRID_NOTAG are placeholders carrying the admission threshold; they always sit behind real ones.
+#define GRID_NOTAG 0xFFFFFFFFu
+template <int K> struct TopK {
+    unsigned d[K]; unsigned t[K]; unsigned tag[K];
+    __device__ __forceinline__ void init(unsigned dthr, unsigned tthr) {
+        #pragma unroll
+        for (int i = 0; i < K; i++) { d[i] = dthr; t[i] = tthr; tag[i] = GRID_NOTAG; }
+    }
+    __device__ __forceinline__ void insert(unsigned dd, unsigned tt, unsigned tg) {
+        if (!(dd < d[K - 1] || (dd == d[K - 1] && tt < t[K - 1]))) return;
+        d[K - 1] = dd; t[K - 1] = tt; tag[K - 1] = tg;
+        #pragma unroll
+        for (int i = K - 1; i > 0; i--) {
+            if (d[i] < d[i - 1] || (d[i] == d[i - 1] && t[i] < t[i - 1])) {
+                unsigned a = d[i]; d[i] = d[i - 1]; d[i - 1] = a;
+                a = t[i]; t[i] = t[i - 1]; t[i - 1] = a;
+                a = tag[i]; tag[i] = tag[i - 1]; tag[i - 1] = a;
+            }
+        }
+    }
+    __device__ __forceinline__ void pop() {
+        #pragma unroll
+        for (int i = 0; i < K - 1; i++) { d[i] = d[i + 1]; t[i] = t[i + 1]; tag[i] = tag[i + 1]; }
+        d[K - 1] = 0xFFFFFFFFu; t[K - 1] = 0xFFFFFFFFu; tag[K - 1] = GRID_NOTAG;
+    }
+};
+
+// Warp-cooperative exact search.  All 32 lanes call it with the same query; on return every lane
+// holds the global K best in `best` (d = float bits of d2; tag == GRID_NOTAG means "none").
+// Candidates need d2 < dmax (strict) and must pass the filter.
+template <int K, typename Filter>
+__device__ void grid_search(const GridSet &gs, int g, float qx, float qy, float qz, float dmax,
+                            const Filter &flt, TopK<K> &best, int lane)
+{
+    const int *start = gs.start + (size_t)g * (gs.ts + 1);
+    const float4 *sorted = gs.sorted + (size_t)g * gs.max_pts;
+    const int cx = (int)floorf(qx * gs.inv_cell), cy = (int)floorf(qy * gs.inv_cell), cz = (int)floorf(qz * gs.inv_cell);
+    best.init(__float_as_uint(dmax), 0xFFFFFFFFu);
+    const float slack = 1e-3f * gs.cell;
+    for (int rho = 1; ; rho++) {
+        const int side = 2 * rho + 1, ncell = side * side * side;   // rho == 1 also covers the centre cell
+        TopK<K> loc;
+        if (lane == 0) loc = best; else loc.init(best.d[K - 1], best.t[K - 1]);
+        for (int c = lane; c < ncell; c += 32) {
+            int dx = c % side - rho, dy = (c / side) % side - rho, dz = c / (side * side) - rho;
+            if (rho > 1 && abs(dx) < rho && abs(dy) < rho && abs(dz) < rho) continue;   // interior: already visited
+            int slot = grid_find(gs, g, cx + dx, cy + dy, cz + dz);
+            if (slot < 0) continue;
+            int s0 = start[slot], s1 = start[slot + 1];
+            for (int k = s0; k < s1; k++) {
+                float4 p = sorted[k];
+                float ddx = p.x - qx, ddy = p.y - qy, ddz = p.z - qz;
+                float d2 = (ddx * ddx + ddy * ddy) + ddz * ddz;
+                unsigned tie, tag = __float_as_uint(p.w);
+                if (!(d2 < dmax) || !flt(tag, tie)) continue;
+                loc.insert(__float_as_uint(d2), tie, tag);
+            }
+        }
+        #pragma unroll
+        for (int i = 0; i < K; i++) {
+            bool valid = loc.tag[0] != GRID_NOTAG;
+            unsigned hd = valid ? loc.d[0] : 0xFFFFFFFFu;
+            unsigned m = __reduce_min_sync(0xffffffffu, hd);
+            if (m == 0xFFFFFFFFu) { best.d[i] = __float_as_uint(dmax); best.t[i] = 0xFFFFFFFFu; best.tag[i] = GRID_NOTAG; continue; }
+            unsigned ht = (valid && hd == m) ? loc.t[0] : 0xFFFFFFFFu;
+            unsigned mt = __reduce_min_sync(0xffffffffu, ht);
+            bool mine = valid && hd == m && loc.t[0] == mt;
+            int src = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
+            unsigned tg = __shfl_sync(0xffffffffu, loc.tag[0], src);
+            best.d[i] = m; best.t[i] = mt; best.tag[i] = tg;
+            if (lane == src) loc.pop();
+        }
+        // stop when the k-th best is strictly inside the visited cube, or nothing below dmax can remain
+        float bound = (float)rho * gs.cell - slack;
+        float b2 = bound * bound;
+        if (best.tag[K - 1] != GRID_NOTAG && __uint_as_float(best.d[K - 1]) < b2) break;
+        if (b2 >= dmax) break;
+    }
+}

@@ -1,0 +1,172 @@
+// K0  organise: raw PointCloud2 payload (AoS float32, ROS axes) -> ring-major float4 cloud in the
+// LOAM frame with intensity = ring + relTime.  Replaces MultiScanRegistration::process of the
+// `loam` nodelet the reference launches (gtsam_fusion/launch/loam.launch:33-38; knobs
+// loam_params.yaml:3,22).  SURVEY.md Appendix A.1 is the algorithm; the sequential `halfPassed`
+// flag becomes "index of the first valid point whose branch-A orientation passes pi" (a min
+// reduction) and the per-ring push_back becomes a stable 3-kernel counting sort by ring.
+#include "vlo_internal.cuh"
+
+#define K0_TILE 256
+
+struct K0Params {
+    const float *raw; const int *raw_offset; int stride;
+    int n_rings; float lower_deg, factor, scan_period;
+    int N;            // capacity per scan
+    int tiles;        // tiles per scan (capacity)
+};
+
+__device__ __forceinline__ int k0_ring(const K0Params &p, float x, float y, float z)
+{
+    if (!isfinite(x) || !isfinite(y) || !isfinite(z)) return -1;
+    if ((x * x + y * y) + z * z < 0.0001f) return -1;
+    float angle = vlo_atanf(y / sqrtf(x * x + z * z));
+    float a180 = angle * 180.0f;
+    double v = ((double)a180 / VLO_PI_D - (double)p.lower_deg) * (double)p.factor + 0.5;
+    int id = (int)v;
+    if (id >= p.n_rings || id < 0) return -1;
+    return id;
+}
+
+__global__ void k0_bounds(K0Params p, float *ori_bounds, int *first_half, int n_scans)
+{
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_scans) return;
+    int o0 = p.raw_offset[b], o1 = p.raw_offset[b + 1];
+    first_half[b] = 0x7fffffff;
+    if (o1 <= o0) { ori_bounds[2 * b] = 0.f; ori_bounds[2 * b + 1] = 0.f; return; }
+    const float *f = p.raw + (size_t)o0 * p.stride, *l = p.raw + (size_t)(o1 - 1) * p.stride;
+    float startOri = -vlo_atan2f(f[1], f[0]);
+    float endOri = -vlo_atan2f(l[1], l[0]) + 2.0f * (float)VLO_PI_D;
+    if ((double)(endOri - startOri) > 3 * VLO_PI_D) endOri = (float)((double)endOri - 2 * VLO_PI_D);
+    else if ((double)(endOri - startOri) < VLO_PI_D) endOri = (float)((double)endOri + 2 * VLO_PI_D);
+    ori_bounds[2 * b] = startOri; ori_bounds[2 * b + 1] = endOri;
+}
+
+// pass 1: per-tile ring histogram + first index passing the half-sweep test
+__global__ void __launch_bounds__(K0_TILE) k0_classify(K0Params p, const float *ori_bounds, int *first_half, int *tile_hist)
+{
+    __shared__ int hist[VLO_MAX_RINGS];
+    __shared__ int s_first;
+    int b = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+    int o0 = p.raw_offset[b], n = p.raw_offset[b + 1] - o0;
+    if (tile * K0_TILE >= n) {   // still must zero the histogram column for the scan kernel
+        if (tid < p.n_rings) tile_hist[((size_t)b * p.n_rings + tid) * p.tiles + tile] = 0;
+        return;
+    }
+    if (tid < p.n_rings) hist[tid] = 0;
+    if (tid == 0) s_first = 0x7fffffff;
+    __syncthreads();
+    int i = tile * K0_TILE + tid;
+    if (i < n) {
+        const float *q = p.raw + (size_t)(o0 + i) * p.stride;
+        float x = q[1], y = q[2], z = q[0];
+        int ring = k0_ring(p, x, y, z);
+        if (ring >= 0) {
+            atomicAdd(&hist[ring], 1);
+            float startOri = ori_bounds[2 * b];
+            float ori = -vlo_atan2f(x, z);
+            if ((double)ori < (double)startOri - VLO_PI_D / 2) ori = (float)((double)ori + 2 * VLO_PI_D);
+            else if ((double)ori > (double)startOri + VLO_PI_D * 3 / 2) ori = (float)((double)ori - 2 * VLO_PI_D);
+            if ((double)(ori - startOri) > VLO_PI_D) atomicMin(&s_first, i);
+        }
+    }
+    __syncthreads();
+    if (tid < p.n_rings) tile_hist[((size_t)b * p.n_rings + tid) * p.tiles + tile] = hist[tid];
+    if (tid == 0 && s_first != 0x7fffffff) atomicMin(&first_half[b], s_first);
+}
+
+// pass 2: per (scan, ring) exclusive scan over tiles; ring_start
+__global__ void __launch_bounds__(256) k0_scan(K0Params p, int *tile_hist, int *ring_start, int *counts)
+{
+    __shared__ int ring_total[VLO_MAX_RINGS];
+    int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    int n = p.raw_offset[b + 1] - p.raw_offset[b];
+    int tiles = (n + K0_TILE - 1) / K0_TILE;
+    for (int r = warp; r < p.n_rings; r += nw) {
+        int *row = tile_hist + ((size_t)b * p.n_rings + r) * p.tiles;
+        int carry = 0;
+        for (int t0 = 0; t0 < tiles; t0 += 32) {
+            int t = t0 + lane;
+            int v = (t < tiles) ? row[t] : 0;
+            int inc = v;
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+            if (t < tiles) row[t] = carry + inc - v;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) ring_total[r] = carry;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int r = 0; r < p.n_rings; r++) { ring_start[b * (VLO_MAX_RINGS + 1) + r] = acc; acc += ring_total[r]; }
+        for (int r = p.n_rings; r <= VLO_MAX_RINGS; r++) ring_start[b * (VLO_MAX_RINGS + 1) + r] = acc;
+        counts[b * 8 + 0] = acc;
+    }
+}
+
+// pass 3: stable scatter into ring-major order, rel-time with the final half-sweep rule
+__global__ void __launch_bounds__(K0_TILE) k0_scatter(K0Params p, const float *ori_bounds, const int *first_half,
+                                                       const int *tile_hist, const int *ring_start,
+                                                       float4 *cloud, int *src_index)
+{
+    __shared__ int warp_cnt[K0_TILE / 32][VLO_MAX_RINGS];
+    int b = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int o0 = p.raw_offset[b], n = p.raw_offset[b + 1] - o0;
+    if (tile * K0_TILE >= n) return;
+    for (int k = tid; k < (K0_TILE / 32) * VLO_MAX_RINGS; k += K0_TILE) (&warp_cnt[0][0])[k] = 0;
+    __syncthreads();
+    int i = tile * K0_TILE + tid;
+    int ring = -1; float x = 0.f, y = 0.f, z = 0.f;
+    if (i < n) {
+        const float *q = p.raw + (size_t)(o0 + i) * p.stride;
+        x = q[1]; y = q[2]; z = q[0];
+        ring = k0_ring(p, x, y, z);
+    }
+    unsigned mask = __match_any_sync(0xffffffffu, ring);
+    int rank = __popc(mask & ((1u << lane) - 1u));
+    if (ring >= 0 && rank == 0) warp_cnt[warp][ring] = __popc(mask);
+    __syncthreads();
+    if (tid < p.n_rings) {
+        int run = 0;
+        #pragma unroll
+        for (int w = 0; w < K0_TILE / 32; w++) { int v = warp_cnt[w][tid]; warp_cnt[w][tid] = run; run += v; }
+    }
+    __syncthreads();
+    if (ring < 0) return;
+    float startOri = ori_bounds[2 * b], endOri = ori_bounds[2 * b + 1];
+    float ori = -vlo_atan2f(x, z);
+    if (i <= first_half[b]) {
+        if ((double)ori < (double)startOri - VLO_PI_D / 2) ori = (float)((double)ori + 2 * VLO_PI_D);
+        else if ((double)ori > (double)startOri + VLO_PI_D * 3 / 2) ori = (float)((double)ori - 2 * VLO_PI_D);
+    } else {
+        ori = (float)((double)ori + 2 * VLO_PI_D);
+        if ((double)ori < (double)endOri - VLO_PI_D * 3 / 2) ori = (float)((double)ori + 2 * VLO_PI_D);
+        else if ((double)ori > (double)endOri + VLO_PI_D / 2) ori = (float)((double)ori - 2 * VLO_PI_D);
+    }
+    float relTime = p.scan_period * (ori - startOri) / (endOri - startOri);
+    int pos = ring_start[b * (VLO_MAX_RINGS + 1) + ring]
+            + tile_hist[((size_t)b * p.n_rings + ring) * p.tiles + tile] + warp_cnt[warp][ring] + rank;
+    cloud[(size_t)b * p.N + pos] = make_float4(x, y, z, (float)ring + relTime);
+    src_index[(size_t)b * p.N + pos] = i;
+}
+
+int vlo_launch_organise(vlo_handle *h)
+{
+    ScanBatchDev &sb = h->sb;
+    K0Params p;
+    p.raw = sb.raw; p.raw_offset = sb.raw_offset; p.stride = sb.stride;
+    p.n_rings = h->cfg.n_rings; p.lower_deg = h->cfg.lower_deg;
+    p.factor = (float)(h->cfg.n_rings - 1) / (h->cfg.upper_deg - h->cfg.lower_deg);
+    p.scan_period = h->cfg.scan_period; p.N = h->cfg.max_points; p.tiles = h->tiles_per_scan;
+    int B = sb.n_scans;
+    k0_bounds<<<(B + 127) / 128, 128, 0, h->stream>>>(p, sb.ori_bounds, sb.first_half, B);
+    dim3 grid(h->tiles_per_scan, B);
+    k0_classify<<<grid, K0_TILE, 0, h->stream>>>(p, sb.ori_bounds, sb.first_half, sb.tile_hist);
+    k0_scan<<<B, 256, 0, h->stream>>>(p, sb.tile_hist, sb.ring_start, sb.counts);
+    k0_scatter<<<grid, K0_TILE, 0, h->stream>>>(p, sb.ori_bounds, sb.first_half, sb.tile_hist, sb.ring_start,
+                                                sb.cloud, sb.src_index);
+    h->launches += 4;
+    VLO_CUDA(cudaGetLastError());
+    return VLO_OK;
+}

@@ -1,0 +1,453 @@
+// K1  feature extraction: one CTA per (ring, scan).  Replaces BasicScanRegistration::extractFeatures
+// of the `loam` nodelet (gtsam_fusion/launch/loam.launch:33-38; knobs loam_params.yaml:25-31);
+// SURVEY.md Appendix A.2-A.3 is the algorithm.  The ring is staged once in shared memory
+// (coalesced float4 loads -> SoA) and everything else happens on chip:
+//   B  occlusion / parallel-beam flags as a gather (window-OR) instead of upstream's scatter
+//   C  11-tap curvature in upstream's summation order
+//   D  greedy sector selection: no sort -- each pick is a warp arg-max / arg-min over the sector
+//      ((curvature, index) lexicographic == walking upstream's stable insertion sort), REDUX for
+//      the reduction, ballot for the +-K neighbour suppression.  Sectors run concurrently on
+//      separate warps; the only cross-sector dependency (suppression marks spilling into the next
+//      sector's first K points) is checked afterwards and the rare conflicting sector is redone.
+//   F  less-flat voxel filter: shared-memory hash on the voxel triple, integer (order-free) sums,
+//      output in order of first appearance (block scan of leader flags).
+#include "vlo_internal.cuh"
+
+#define K1_THREADS 256
+#define K1_EMPTY 0xFFFFFFFFFFFFFFFFull
+
+struct K1Params {
+    const float4 *cloud; const int *ring_start; int N; int n_rings;
+    int K, NR, max_sharp, max_lsharp, max_flat; float thr; float leaf;
+    int MR, HT;
+    int8_t *label; float *curvature; uint8_t *picked;
+    int *slot_sharp, *slot_lsharp, *slot_flat; uint8_t *slot_cnt;
+    float4 *lflat_slotted; int *lflat_cnt;
+    int *status_word;
+};
+
+struct K1Smem {
+    float *x, *y, *z, *w;
+    float *curv;            // later reused as int slot_of[]
+    uint8_t *flag;          // bit0 f1, bit1 f2, bit2 f3, bit3 gap(i,i+1) > 0.05, bit4 base picked
+    uint8_t *mark0, *mark1; // suppression marks written by even / odd sectors
+    int8_t *label;
+    unsigned long long *vkey;
+    int *vfirst, *vcnt, *vsx, *vsy, *vsz, *vsw;
+};
+
+__device__ __forceinline__ K1Smem k1_carve(unsigned char *base, int MR, int HT)
+{
+    K1Smem s;
+    s.vkey = (unsigned long long *)base; base += (size_t)HT * 8;
+    s.x = (float *)base; base += (size_t)MR * 4;
+    s.y = (float *)base; base += (size_t)MR * 4;
+    s.z = (float *)base; base += (size_t)MR * 4;
+    s.w = (float *)base; base += (size_t)MR * 4;
+    s.curv = (float *)base; base += (size_t)MR * 4;
+    s.vfirst = (int *)base; base += (size_t)HT * 4;
+    s.vcnt = (int *)base; base += (size_t)HT * 4;
+    s.vsx = (int *)base; base += (size_t)HT * 4;
+    s.vsy = (int *)base; base += (size_t)HT * 4;
+    s.vsz = (int *)base; base += (size_t)HT * 4;
+    s.vsw = (int *)base; base += (size_t)HT * 4;
+    s.flag = base; base += MR;
+    s.mark0 = base; base += MR;
+    s.mark1 = base; base += MR;
+    s.label = (int8_t *)base;
+    return s;
+}
+
+static size_t k1_smem_bytes(int MR, int HT) { return (size_t)HT * 8 + (size_t)MR * 20 + (size_t)HT * 24 + (size_t)MR * 4; }
+
+// one sector's greedy selection, executed by one full warp.
+// view_prev_lo..view_prev_hi: index range (ring-relative) where the previous sector's marks are visible.
+__device__ void k1_sector_greedy(const K1Params &p, const K1Smem &s, int lane, int sec, int sp, int ep, int start,
+                                 uint8_t *own, const uint8_t *prev, int view_prev_lo, int view_prev_hi, int b, int r)
+{
+    // sp, ep: ring-relative inclusive sector range; own: mark array this sector writes and sees
+    const int K = p.K;
+    size_t slot_base = ((size_t)(b * p.n_rings + r) * p.NR + sec);
+    int n_sharp = 0, n_ls = 0, n_flat = 0;
+    // ---- corners: largest (curvature, index) first
+    for (int pick = 0; pick < p.max_lsharp; pick++) {
+        unsigned best_c = 0u; int best_i = -1;
+        for (int i = sp + lane; i <= ep; i += 32) {
+            bool pk = (s.flag[i] & 16) || own[i] || (i >= view_prev_lo && i <= view_prev_hi && prev[i]);
+            float c = s.curv[i];
+            if (!pk && c > p.thr) {
+                unsigned cb = __float_as_uint(c);
+                if (cb > best_c || (cb == best_c && i > best_i)) { best_c = cb; best_i = i; }
+            }
+        }
+        unsigned m = __reduce_max_sync(0xffffffffu, best_c);
+        if (m == 0u) break;
+        int cand = (best_c == m) ? best_i : -1;
+        int idx = __reduce_max_sync(0xffffffffu, cand);
+        // label + slot
+        if (lane == 0) {
+            if (pick < p.max_sharp) { s.label[idx] = 2; p.slot_sharp[slot_base * p.max_sharp + n_sharp] = start + idx; }
+            else s.label[idx] = 1;
+            p.slot_lsharp[slot_base * p.max_lsharp + n_ls] = start + idx;
+        }
+        if (pick < p.max_sharp) n_sharp++;
+        n_ls++;
+        // markAsPicked
+        unsigned g = 1u;
+        if (lane < K) g = (s.flag[idx + lane] >> 3) & 1u;                 // gap(idx+lane, idx+lane+1)
+        else if (lane >= 16 && lane < 16 + K) g = (s.flag[idx - 1 - (lane - 16)] >> 3) & 1u;
+        unsigned bal = __ballot_sync(0xffffffffu, g);
+        int fcount = min(K, __ffs(bal & 0xffffu) - 1);
+        int bcount = min(K, __ffs(bal >> 16) - 1);
+        if (lane == 0) own[idx] = 1;
+        if (lane < fcount) own[idx + 1 + lane] = 1;
+        if (lane >= 16 && lane - 16 < bcount) own[idx - 1 - (lane - 16)] = 1;
+        __syncwarp();
+    }
+    // ---- flats: smallest (curvature, index) first
+    for (int pick = 0; pick < p.max_flat; pick++) {
+        unsigned best_c = 0xffffffffu; int best_i = 0x7fffffff;
+        for (int i = sp + lane; i <= ep; i += 32) {
+            bool pk = (s.flag[i] & 16) || own[i] || (i >= view_prev_lo && i <= view_prev_hi && prev[i]);
+            float c = s.curv[i];
+            if (!pk && c < p.thr) {
+                unsigned cb = __float_as_uint(c);
+                if (cb < best_c || (cb == best_c && i < best_i)) { best_c = cb; best_i = i; }
+            }
+        }
+        unsigned m = __reduce_min_sync(0xffffffffu, best_c);
+        if (m == 0xffffffffu) break;
+        int cand = (best_c == m) ? best_i : 0x7fffffff;
+        int idx = __reduce_min_sync(0xffffffffu, cand);
+        if (lane == 0) { s.label[idx] = -1; p.slot_flat[slot_base * p.max_flat + n_flat] = start + idx; }
+        n_flat++;
+        unsigned g = 1u;
+        if (lane < K) g = (s.flag[idx + lane] >> 3) & 1u;
+        else if (lane >= 16 && lane < 16 + K) g = (s.flag[idx - 1 - (lane - 16)] >> 3) & 1u;
+        unsigned bal = __ballot_sync(0xffffffffu, g);
+        int fcount = min(K, __ffs(bal & 0xffffu) - 1);
+        int bcount = min(K, __ffs(bal >> 16) - 1);
+        if (lane == 0) own[idx] = 1;
+        if (lane < fcount) own[idx + 1 + lane] = 1;
+        if (lane >= 16 && lane - 16 < bcount) own[idx - 1 - (lane - 16)] = 1;
+        __syncwarp();
+    }
+    if (lane == 0) {
+        uint8_t *c = p.slot_cnt + slot_base * 4;
+        c[0] = (uint8_t)n_sharp; c[1] = (uint8_t)n_ls; c[2] = (uint8_t)n_flat; c[3] = 0;
+    }
+}
+
+extern __shared__ __align__(16) unsigned char k1_smem_raw[];
+
+__global__ void __launch_bounds__(K1_THREADS) k1_extract(K1Params p)
+{
+    __shared__ int s_sp[VLO_MAX_REGIONS], s_ep[VLO_MAX_REGIONS];
+    __shared__ int s_warp_scan[K1_THREADS / 32];
+    __shared__ int s_seq;
+    const int r = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int start = p.ring_start[b * (VLO_MAX_RINGS + 1) + r];
+    const int n = p.ring_start[b * (VLO_MAX_RINGS + 1) + r + 1] - start;
+    const int K = p.K, NR = p.NR;
+    const size_t gbase = (size_t)b * p.N + start;
+    K1Smem s = k1_carve(k1_smem_raw, p.MR, p.HT);
+
+    // slot counters default to zero
+    if (tid < NR * 4) p.slot_cnt[((size_t)(b * p.n_rings + r) * NR) * 4 + tid] = 0;
+    if (tid == 0) p.lflat_cnt[b * p.n_rings + r] = 0;
+    if (n <= 0) return;
+    bool skip = (n <= 2 * K + 1) || (n > p.MR);
+    if (n > p.MR && tid == 0) atomicOr(p.status_word, 1);
+    if (skip) {
+        for (int i = tid; i < n; i += K1_THREADS) { p.label[gbase + i] = 0; p.curvature[gbase + i] = 0.f; p.picked[gbase + i] = 0; }
+        return;
+    }
+    // ---- A: stage ring
+    for (int i = tid; i < n; i += K1_THREADS) {
+        float4 v = p.cloud[gbase + i];
+        s.x[i] = v.x; s.y[i] = v.y; s.z[i] = v.z; s.w[i] = v.w;
+        s.label[i] = 0; s.mark0[i] = 0; s.mark1[i] = 0; s.curv[i] = 0.f;
+    }
+    if (tid < NR) {
+        int a = start + K, e = start + n - 1 - K;     // absolute, as upstream's integer arithmetic
+        int sp = (a * (NR - tid) + e * tid) / NR;
+        int ep = (a * (NR - 1 - tid) + e * (tid + 1)) / NR - 1;
+        s_sp[tid] = sp - start; s_ep[tid] = ep - start;
+    }
+    if (tid == 0) s_seq = 0;
+    __syncthreads();
+    // ---- B1: per-point flags
+    for (int i = tid; i < n; i += K1_THREADS) {
+        unsigned f = 0;
+        float px = s.x[i], py = s.y[i], pz = s.z[i];
+        float diffNext = 0.f;
+        if (i + 1 < n) {
+            diffNext = sqdiff3(s.x[i + 1], s.y[i + 1], s.z[i + 1], px, py, pz);
+            if ((double)diffNext > 0.05) f |= 8u;
+        }
+        if (i >= K && i < n - 1 - K) {
+            bool cont = false;
+            if ((double)diffNext > 0.1) {
+                float nx = s.x[i + 1], ny = s.y[i + 1], nz = s.z[i + 1];
+                float depth1 = sqrtf((px * px + py * py) + pz * pz);
+                float depth2 = sqrtf((nx * nx + ny * ny) + nz * nz);
+                if (depth1 > depth2) {
+                    float wq = depth2 / depth1;
+                    float wd = sqrtf(sqdiff3(nx, ny, nz, px * wq, py * wq, pz * wq)) / depth2;
+                    if ((double)wd < 0.1) { f |= 1u; cont = true; }
+                } else {
+                    float wq = depth1 / depth2;
+                    float wd = sqrtf(sqdiff3(px, py, pz, nx * wq, ny * wq, nz * wq)) / depth1;
+                    if ((double)wd < 0.1) f |= 2u;
+                }
+            }
+            if (!cont) {
+                float diffPrev = sqdiff3(px, py, pz, s.x[i - 1], s.y[i - 1], s.z[i - 1]);
+                float dis = (px * px + py * py) + pz * pz;
+                if ((double)diffNext > 0.0002 * (double)dis && (double)diffPrev > 0.0002 * (double)dis) f |= 4u;
+            }
+        }
+        s.flag[i] = (uint8_t)f;
+    }
+    __syncthreads();
+    // ---- B2: window-OR -> base picked (bit4);  C: curvature inside sector ranges
+    const int lo_all = s_sp[0], hi_all = s_ep[NR - 1];
+    for (int i = tid; i < n; i += K1_THREADS) {
+        unsigned pk = (s.flag[i] >> 2) & 1u;
+        for (int m = 0; m <= K; m++) {
+            int a = i + m; if (a < n) pk |= (s.flag[a] & 1u);
+            int c = i - 1 - m; if (c >= 0) pk |= ((s.flag[c] >> 1) & 1u);
+        }
+        float cv = 0.f;
+        if (i >= lo_all && i <= hi_all) {
+            bool in = false;
+            for (int j = 0; j < NR; j++) in |= (s_ep[j] > s_sp[j] && i >= s_sp[j] && i <= s_ep[j]);
+            if (in) {
+                float wgt = (float)(-2 * K);
+                float dx = wgt * s.x[i], dy = wgt * s.y[i], dz = wgt * s.z[i];
+                for (int m = 1; m <= K; m++) {
+                    dx += s.x[i + m] + s.x[i - m];
+                    dy += s.y[i + m] + s.y[i - m];
+                    dz += s.z[i + m] + s.z[i - m];
+                }
+                cv = (dx * dx + dy * dy) + dz * dz;
+            }
+        }
+        s.curv[i] = cv;
+        p.curvature[gbase + i] = cv;
+        s.mark1[i] = (uint8_t)pk;     // stash: flag bytes are still being read by other threads
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += K1_THREADS) { s.flag[i] = (uint8_t)(s.flag[i] | (s.mark1[i] << 4)); s.mark1[i] = 0; }
+    // decide concurrent vs sequential sector processing
+    if (tid == 0) {
+        int seq = 0;
+        for (int j = 0; j < NR; j++) if (s_ep[j] > s_sp[j] && s_ep[j] - s_sp[j] + 1 < 2 * K + 2) seq = 1;
+        if (NR > K1_THREADS / 32 || NR == 1) seq = 1;
+        s_seq = seq;
+    }
+    __syncthreads();
+    // ---- D: greedy selection
+    if (!s_seq) {
+        if (warp < NR && s_ep[warp] > s_sp[warp])
+            k1_sector_greedy(p, s, lane, warp, s_sp[warp], s_ep[warp], start,
+                             (warp & 1) ? s.mark1 : s.mark0, (warp & 1) ? s.mark0 : s.mark1, 1, 0, b, r);
+        __syncthreads();
+        if (warp == 0) {
+            for (int j = 1; j < NR; j++) {
+                if (!(s_ep[j] > s_sp[j])) continue;
+                const uint8_t *prev = (j & 1) ? s.mark0 : s.mark1;
+                uint8_t *own = (j & 1) ? s.mark1 : s.mark0;
+                int i = s_sp[j] + lane;
+                bool conflict = (lane < K) && (i <= s_ep[j]) && prev[i] && s.label[i] != 0;
+                if (__any_sync(0xffffffffu, conflict)) {
+                    for (int q = s_sp[j] - K + lane; q <= s_ep[j] + K; q += 32) if (q >= 0 && q < n) own[q] = 0;
+                    for (int q = s_sp[j] + lane; q <= s_ep[j]; q += 32) s.label[q] = 0;
+                    __syncwarp();
+                    k1_sector_greedy(p, s, lane, j, s_sp[j], s_ep[j], start, own, prev, s_sp[j], s_sp[j] + K - 1, b, r);
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == 0) {
+        // short rings: sectors strictly in order on one warp, a single mark array sees everything
+        for (int j = 0; j < NR; j++) {
+            if (!(s_ep[j] > s_sp[j])) continue;
+            k1_sector_greedy(p, s, lane, j, s_sp[j], s_ep[j], start, s.mark0, s.mark1, 1, 0, b, r);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    // ---- E: labels + picked mask out
+    for (int i = tid; i < n; i += K1_THREADS) {
+        p.label[gbase + i] = s.label[i];
+        p.picked[gbase + i] = (uint8_t)(((s.flag[i] >> 4) & 1u) | s.mark0[i] | s.mark1[i]);
+    }
+    // ---- F: less-flat voxel filter
+    int *slot_of = (int *)s.curv;
+    for (int k = tid; k < p.HT; k += K1_THREADS) {
+        s.vkey[k] = K1_EMPTY; s.vfirst[k] = 0x7fffffff; s.vcnt[k] = 0; s.vsx[k] = 0; s.vsy[k] = 0; s.vsz[k] = 0; s.vsw[k] = 0;
+    }
+    __syncthreads();
+    const float leaf = p.leaf, inv = 1.0f / p.leaf;
+    for (int i = tid; i < n; i += K1_THREADS) {
+        int so = -1;
+        bool in = false;
+        if (i >= lo_all && i <= hi_all)
+            for (int j = 0; j < NR; j++) in |= (s_ep[j] > s_sp[j] && i >= s_sp[j] && i <= s_ep[j]);
+        if (in && s.label[i] <= 0) {
+            float x = s.x[i], y = s.y[i], z = s.z[i], w = s.w[i];
+            int ix = (int)floorf(x * inv), iy = (int)floorf(y * inv), iz = (int)floorf(z * inv);
+            unsigned long long key = ((unsigned long long)(unsigned)(ix + (1 << 20)) << 42)
+                                   | ((unsigned long long)(unsigned)(iy + (1 << 20)) << 21)
+                                   | (unsigned long long)(unsigned)(iz + (1 << 20));
+            unsigned hsh = ((unsigned)ix * 73856093u) ^ ((unsigned)iy * 19349663u) ^ ((unsigned)iz * 83492791u);
+            int slot = (int)(hsh & (unsigned)(p.HT - 1));
+            while (true) {
+                unsigned long long old = atomicCAS(&s.vkey[slot], K1_EMPTY, key);
+                if (old == K1_EMPTY || old == key) break;
+                slot = (slot + 1) & (p.HT - 1);
+            }
+            float ox = (float)ix * leaf, oy = (float)iy * leaf, oz = (float)iz * leaf;
+            atomicMin(&s.vfirst[slot], i);
+            atomicAdd(&s.vcnt[slot], 1);
+            atomicAdd(&s.vsx[slot], (int)rintf((x - ox) * 1048576.0f));
+            atomicAdd(&s.vsy[slot], (int)rintf((y - oy) * 1048576.0f));
+            atomicAdd(&s.vsz[slot], (int)rintf((z - oz) * 1048576.0f));
+            atomicAdd(&s.vsw[slot], (int)rintf((w - (float)(int)w) * 1048576.0f));
+            so = slot;
+        }
+        slot_of[i] = so;
+    }
+    __syncthreads();
+    // leaders in index order: thread t owns the contiguous chunk [t*per, (t+1)*per)
+    const int per = (n + K1_THREADS - 1) / K1_THREADS;
+    int i0 = tid * per, i1 = min(n, i0 + per);
+    int cnt = 0;
+    for (int i = i0; i < i1; i++) { int so = slot_of[i]; if (so >= 0 && s.vfirst[so] == i) cnt++; }
+    int inc = cnt;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+    if (lane == 31) s_warp_scan[warp] = inc;
+    __syncthreads();
+    int woff = 0, total = 0;
+    for (int wv = 0; wv < K1_THREADS / 32; wv++) { int v = s_warp_scan[wv]; if (wv < warp) woff += v; total += v; }
+    int pos = woff + inc - cnt;
+    for (int i = i0; i < i1; i++) {
+        int so = slot_of[i];
+        if (so >= 0 && s.vfirst[so] == i) {
+            double c = (double)s.vcnt[so];
+            float x = s.x[i], y = s.y[i], z = s.z[i];
+            int ix = (int)floorf(x * inv), iy = (int)floorf(y * inv), iz = (int)floorf(z * inv);
+            float ox = (float)ix * leaf, oy = (float)iy * leaf, oz = (float)iz * leaf;
+            float4 o;
+            o.x = ox + (float)(((double)s.vsx[so] / c) * (1.0 / 1048576.0));
+            o.y = oy + (float)(((double)s.vsy[so] / c) * (1.0 / 1048576.0));
+            o.z = oz + (float)(((double)s.vsz[so] / c) * (1.0 / 1048576.0));
+            o.w = (float)(int)s.w[i] + (float)(((double)s.vsw[so] / c) * (1.0 / 1048576.0));
+            p.lflat_slotted[gbase + pos] = o;
+            pos++;
+        }
+    }
+    if (tid == 0) p.lflat_cnt[b * p.n_rings + r] = total;
+}
+
+// K1b  compaction: per scan, exclusive scans of the per-(ring, sector) counters -> dense index
+// lists + gathered feature points + per-ring offsets of the less-sharp / less-flat clouds.
+struct K1bParams {
+    const float4 *cloud; int N; int n_rings, NR, max_sharp, max_lsharp, max_flat;
+    const int *slot_sharp, *slot_lsharp, *slot_flat; const uint8_t *slot_cnt; const int *lflat_cnt;
+    int *counts; int *sharp_idx, *lsharp_idx, *flat_idx; float4 *sharp_pts, *lsharp_pts, *flat_pts;
+    int cap_sharp, cap_lsharp, cap_flat;
+    int *lsharp_ring_start, *lflat_ring_start;
+};
+
+__global__ void __launch_bounds__(256) k1b_compact(K1bParams p)
+{
+    __shared__ int off_sharp[VLO_MAX_RINGS * VLO_MAX_REGIONS + 1];
+    __shared__ int off_ls[VLO_MAX_RINGS * VLO_MAX_REGIONS + 1];
+    __shared__ int off_flat[VLO_MAX_RINGS * VLO_MAX_REGIONS + 1];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int nsec = p.n_rings * p.NR;
+    if (tid == 0) {
+        int a = 0, l = 0, f = 0;
+        for (int k = 0; k < nsec; k++) {
+            const uint8_t *c = p.slot_cnt + ((size_t)b * nsec + k) * 4;
+            off_sharp[k] = a; off_ls[k] = l; off_flat[k] = f;
+            a += c[0]; l += c[1]; f += c[2];
+        }
+        off_sharp[nsec] = a; off_ls[nsec] = l; off_flat[nsec] = f;
+        int lf = 0;
+        for (int r = 0; r < p.n_rings; r++) {
+            p.lsharp_ring_start[b * (VLO_MAX_RINGS + 1) + r] = off_ls[r * p.NR];
+            p.lflat_ring_start[b * (VLO_MAX_RINGS + 1) + r] = lf;
+            lf += p.lflat_cnt[b * p.n_rings + r];
+        }
+        for (int r = p.n_rings; r <= VLO_MAX_RINGS; r++) {
+            p.lsharp_ring_start[b * (VLO_MAX_RINGS + 1) + r] = l;
+            p.lflat_ring_start[b * (VLO_MAX_RINGS + 1) + r] = lf;
+        }
+        p.counts[b * 8 + 1] = a; p.counts[b * 8 + 2] = l; p.counts[b * 8 + 3] = f; p.counts[b * 8 + 4] = lf;
+    }
+    __syncthreads();
+    const float4 *cloud = p.cloud + (size_t)b * p.N;
+    const int maxq = max(p.max_lsharp, max(p.max_sharp, p.max_flat));
+    for (int k = tid; k < nsec * maxq; k += blockDim.x) {
+        int sec = k / maxq, q = k % maxq;
+        const uint8_t *c = p.slot_cnt + ((size_t)b * nsec + sec) * 4;
+        if (q < p.max_lsharp && q < c[1]) {
+            int idx = p.slot_lsharp[((size_t)b * nsec + sec) * p.max_lsharp + q];
+            int o = off_ls[sec] + q;
+            p.lsharp_idx[(size_t)b * p.cap_lsharp + o] = idx;
+            p.lsharp_pts[(size_t)b * p.cap_lsharp + o] = cloud[idx];
+        }
+        if (q < p.max_sharp && q < c[0]) {
+            int idx = p.slot_sharp[((size_t)b * nsec + sec) * p.max_sharp + q];
+            int o = off_sharp[sec] + q;
+            p.sharp_idx[(size_t)b * p.cap_sharp + o] = idx;
+            p.sharp_pts[(size_t)b * p.cap_sharp + o] = cloud[idx];
+        }
+        if (q < p.max_flat && q < c[2]) {
+            int idx = p.slot_flat[((size_t)b * nsec + sec) * p.max_flat + q];
+            int o = off_flat[sec] + q;
+            p.flat_idx[(size_t)b * p.cap_flat + o] = idx;
+            p.flat_pts[(size_t)b * p.cap_flat + o] = cloud[idx];
+        }
+    }
+}
+
+int vlo_launch_extract(vlo_handle *h)
+{
+    ScanBatchDev &sb = h->sb;
+    const vlo_config &c = h->cfg;
+    K1Params p;
+    p.cloud = sb.cloud; p.ring_start = sb.ring_start; p.N = c.max_points; p.n_rings = c.n_rings;
+    p.K = c.curvature_region; p.NR = c.feature_regions; p.max_sharp = c.max_corner_sharp;
+    p.max_lsharp = c.max_corner_less_sharp; p.max_flat = c.max_surface_flat;
+    p.thr = c.surface_curvature_threshold; p.leaf = c.less_flat_filter_size;
+    p.MR = c.max_ring_points; int HT = 1; while (HT < p.MR) HT <<= 1; p.HT = HT;
+    p.label = sb.label; p.curvature = sb.curvature; p.picked = sb.picked;
+    p.slot_sharp = sb.slot_sharp; p.slot_lsharp = sb.slot_lsharp; p.slot_flat = sb.slot_flat; p.slot_cnt = sb.slot_cnt;
+    p.lflat_slotted = sb.lflat_slotted; p.lflat_cnt = sb.lflat_cnt; p.status_word = h->status_word;
+    size_t smem = k1_smem_bytes(p.MR, p.HT);
+    static size_t configured = 0;
+    if (smem > configured) {
+        VLO_CUDA(cudaFuncSetAttribute(k1_extract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid(c.n_rings, sb.n_scans);
+    k1_extract<<<grid, K1_THREADS, smem, h->stream>>>(p);
+    K1bParams q;
+    q.cloud = sb.cloud; q.N = c.max_points; q.n_rings = c.n_rings; q.NR = c.feature_regions;
+    q.max_sharp = c.max_corner_sharp; q.max_lsharp = c.max_corner_less_sharp; q.max_flat = c.max_surface_flat;
+    q.slot_sharp = sb.slot_sharp; q.slot_lsharp = sb.slot_lsharp; q.slot_flat = sb.slot_flat; q.slot_cnt = sb.slot_cnt;
+    q.lflat_cnt = sb.lflat_cnt; q.counts = sb.counts;
+    q.sharp_idx = sb.sharp_idx; q.lsharp_idx = sb.lsharp_idx; q.flat_idx = sb.flat_idx;
+    q.sharp_pts = sb.sharp_pts; q.lsharp_pts = sb.lsharp_pts; q.flat_pts = sb.flat_pts;
+    q.cap_sharp = h->cap_sharp; q.cap_lsharp = h->cap_lsharp; q.cap_flat = h->cap_flat;
+    q.lsharp_ring_start = sb.lsharp_ring_start; q.lflat_ring_start = sb.lflat_ring_start;
+    k1b_compact<<<sb.n_scans, 256, 0, h->stream>>>(q);
+    h->launches += 2;
+    VLO_CUDA(cudaGetLastError());
+    return VLO_OK;
+}

@@ -1,0 +1,144 @@
+// K2  voxel-hash build (count -> scan -> scatter) for a set of grids, plus a k-NN service kernel.
+// See grid.cuh for the layout and the exactness contract.
+#include "grid.cuh"
+
+// point sources: ring-slotted clouds (ring r's live points at [ring_off[r], +ring_cnt[r]) of a
+// per-grid base array; dense index = dense_start[r] + offset) or plain dense arrays.
+struct GridSource {
+    const float4 *pts; size_t pts_stride;       // per grid
+    const int *ring_off; int ring_off_stride;   // [R+1] slot offsets (NULL -> dense source)
+    const int *ring_cnt; int ring_cnt_stride;   // [R]
+    const int *dense_start; int dense_start_stride; // [R+1]
+    const int *n_dense; int n_dense_stride; int n_dense_field;   // dense sources: point count per grid
+    int n_rings;
+    const int *grid_scan;                        // optional indirection: grid g reads scan grid_scan[g]
+};
+
+__device__ __forceinline__ bool grid_src_point(const GridSource &src, int g, int i, float4 &p, unsigned &tag)
+{
+    int b = src.grid_scan ? src.grid_scan[g] : g;
+    if (src.ring_off) {
+        const int *ro = src.ring_off + (size_t)b * src.ring_off_stride;
+        if (i >= ro[src.n_rings]) return false;
+        int lo = 0, hi = src.n_rings;            // ring r with ro[r] <= i < ro[r+1]
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (ro[mid] <= i) lo = mid; else hi = mid; }
+        int off = i - ro[lo];
+        if (off >= src.ring_cnt[(size_t)b * src.ring_cnt_stride + lo]) return false;
+        p = src.pts[(size_t)b * src.pts_stride + i];
+        int dense = src.dense_start[(size_t)b * src.dense_start_stride + lo] + off;
+        tag = ((unsigned)lo << 24) | (unsigned)dense;
+        return true;
+    }
+    int n = src.n_dense[(size_t)b * src.n_dense_stride + src.n_dense_field];
+    if (i >= n) return false;
+    p = src.pts[(size_t)b * src.pts_stride + i];
+    tag = ((unsigned)(int)p.w << 24) | (unsigned)i;
+    return true;
+}
+
+__global__ void __launch_bounds__(256) k2_count(GridSet gs, GridSource src, int n_slots)
+{
+    int g = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    float4 p; unsigned tag;
+    if (!grid_src_point(src, g, i, p, tag)) return;
+    int ix = (int)floorf(p.x * gs.inv_cell), iy = (int)floorf(p.y * gs.inv_cell), iz = (int)floorf(p.z * gs.inv_cell);
+    unsigned long long key = grid_key(ix, iy, iz);
+    unsigned long long *keys = gs.keys + (size_t)g * gs.ts;
+    int slot = (int)(grid_hash(ix, iy, iz) & (unsigned)(gs.ts - 1));
+    while (true) {
+        unsigned long long old = atomicCAS(&keys[slot], GRID_EMPTY, key);
+        if (old == GRID_EMPTY || old == key) break;
+        slot = (slot + 1) & (gs.ts - 1);
+    }
+    atomicAdd(&gs.cnt[(size_t)g * gs.ts + slot], 1);
+}
+
+__global__ void __launch_bounds__(1024) k2_scan(GridSet gs)
+{
+    __shared__ int warp_sum[32];
+    __shared__ int carry_s;
+    int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int *cnt = gs.cnt + (size_t)g * gs.ts;
+    int *start = gs.start + (size_t)g * (gs.ts + 1);
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < gs.ts; base += 1024) {
+        int v = cnt[base + tid];
+        int inc = v;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+        if (lane == 31) warp_sum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int w = warp_sum[lane], winc = w;
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, winc, d); if (lane >= d) winc += u; }
+            warp_sum[lane] = winc - w;
+        }
+        __syncthreads();
+        int carry = carry_s;
+        start[base + tid] = carry + warp_sum[warp] + inc - v;
+        __syncthreads();
+        if (tid == 1023) carry_s = carry + warp_sum[warp] + inc;
+        __syncthreads();
+    }
+    if (tid == 0) start[gs.ts] = carry_s;
+}
+
+__global__ void __launch_bounds__(256) k2_scatter(GridSet gs, GridSource src, int n_slots)
+{
+    int g = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    float4 p; unsigned tag;
+    if (!grid_src_point(src, g, i, p, tag)) return;
+    int ix = (int)floorf(p.x * gs.inv_cell), iy = (int)floorf(p.y * gs.inv_cell), iz = (int)floorf(p.z * gs.inv_cell);
+    int slot = grid_find(gs, g, ix, iy, iz);
+    int pos = gs.start[(size_t)g * (gs.ts + 1) + slot] + atomicSub(&gs.cnt[(size_t)g * gs.ts + slot], 1) - 1;
+    gs.sorted[(size_t)g * gs.max_pts + pos] = make_float4(p.x, p.y, p.z, __uint_as_float(tag));
+}
+
+int vlo_grid_build(vlo_handle *h, const GridSet &gs, const GridSource &src, int n_grids, int n_slots)
+{
+    if (n_grids <= 0) return VLO_OK;
+    VLO_CUDA(cudaMemsetAsync(gs.keys, 0xFF, sizeof(unsigned long long) * (size_t)n_grids * gs.ts, h->stream));
+    VLO_CUDA(cudaMemsetAsync(gs.cnt, 0, sizeof(int) * (size_t)n_grids * gs.ts, h->stream));
+    dim3 grid((n_slots + 255) / 256, n_grids);
+    k2_count<<<grid, 256, 0, h->stream>>>(gs, src, n_slots);
+    k2_scan<<<n_grids, 1024, 0, h->stream>>>(gs);
+    k2_scatter<<<grid, 256, 0, h->stream>>>(gs, src, n_slots);
+    h->launches += 3;
+    VLO_CUDA(cudaGetLastError());
+    return VLO_OK;
+}
+
+// k-NN service (parity tests / tooling): one warp per query
+template <int K>
+__global__ void __launch_bounds__(256) k2_knn(GridSet gs, int g, const float4 *q, int nq, float dmax, int *idx, float *d2)
+{
+    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= nq) return;
+    float4 p = q[w];
+    TopK<K> best;
+    grid_search<K>(gs, g, p.x, p.y, p.z, dmax, FilterAll(), best, lane);
+    if (lane == 0) {
+        #pragma unroll
+        for (int i = 0; i < K; i++) {
+            bool ok = best.tag[i] != GRID_NOTAG;
+            idx[(size_t)w * K + i] = ok ? (int)(best.tag[i] & 0xFFFFFFu) : -1;
+            d2[(size_t)w * K + i] = ok ? __uint_as_float(best.d[i]) : __int_as_float(0x7f800000);
+        }
+    }
+}
+
+int vlo_grid_knn(vlo_handle *h, const GridSet &gs, int g, const float4 *d_q, int nq, int k, float dmax, int *d_idx, float *d_d2)
+{
+    int blocks = (nq * 32 + 255) / 256;
+    if (nq <= 0) return VLO_OK;
+    if (k == 1) k2_knn<1><<<blocks, 256, 0, h->stream>>>(gs, g, d_q, nq, dmax, d_idx, d_d2);
+    else if (k == 5) k2_knn<5><<<blocks, 256, 0, h->stream>>>(gs, g, d_q, nq, dmax, d_idx, d_d2);
+    else { h->err = "k must be 1 or 5"; return VLO_ERR_INVALID_ARG; }
+    h->launches += 1;
+    VLO_CUDA(cudaGetLastError());
+    return VLO_OK;
+}

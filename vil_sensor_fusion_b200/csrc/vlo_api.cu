@@ -1,0 +1,287 @@
+// C-ABI of libvlo.so (include/vlo.h): handle lifecycle, uploads, stage launchers, copy-backs.
+// Host logic only; every computation on the hot path is a kernel in k*.cu.  No CPU fallback: with
+// no usable CUDA device vlo_create fails with VLO_ERR_NO_DEVICE.
+#include "vlo_internal.cuh"
+#include <cstring>
+#include <cstdlib>
+#include <cmath>
+#include <algorithm>
+
+static const char *kVersion = "vlo-b200 0.1 (sm_100a)";
+
+extern "C" const char *vlo_version(void) { return kVersion; }
+
+extern "C" void vlo_default_config(vlo_config *c)
+{
+    memset(c, 0, sizeof(*c));
+    c->max_scans = 2; c->max_points = 32768; c->max_ring_points = 2048; c->max_map_points = 0;
+    c->max_imu_factors = 0; c->max_imu_samples = 0; c->device = 0;
+    c->scan_period = 0.1f; c->n_rings = 16; c->lower_deg = -15.0f; c->upper_deg = 15.0f;
+    c->feature_regions = 6; c->curvature_region = 5; c->max_corner_sharp = 2; c->max_corner_less_sharp = 20;
+    c->max_surface_flat = 4; c->surface_curvature_threshold = 0.1f; c->less_flat_filter_size = 0.2f;
+    c->odom_max_iterations = 25; c->odom_delta_t_abort = 0.05f; c->odom_delta_r_abort = 0.05f; c->odom_degen_eig = 30.0f;
+    c->deskew = 1; c->odom_forward_bound_quirk = 0;
+    c->map_max_iterations = 10; c->map_delta_t_abort = 0.05f; c->map_delta_r_abort = 0.05f; c->map_degen_eig = 40.0f;
+    c->map_cell_size = 1.0f; c->odom_cell_size = 1.0f;
+    c->dopt_rot_threshold = 11.5f; c->dopt_trans_threshold = 28.9f;
+    c->cov_accel = 1e-6; c->cov_gyro = 1e-6; c->cov_integration = 1e-8; c->cov_bias_acc = 1e-4;
+    c->cov_bias_omega = 1e-6; c->cov_bias_acc_omega_int = 1e-4;
+}
+
+extern "C" int vlo_set_lidar(vlo_config *c, const char *name)
+{
+    if (!strcmp(name, "VLP-16")) { c->n_rings = 16; c->lower_deg = -15.0f; c->upper_deg = 15.0f; return VLO_OK; }
+    if (!strcmp(name, "HDL-32")) { c->n_rings = 32; c->lower_deg = -30.67f; c->upper_deg = 10.67f; return VLO_OK; }
+    if (!strcmp(name, "HDL-64E")) { c->n_rings = 64; c->lower_deg = -24.9f; c->upper_deg = 2.0f; return VLO_OK; }
+    return VLO_ERR_INVALID_ARG;
+}
+
+template <typename T> static cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)); }
+
+#define HALLOC(ptr, n) do { cudaError_t e_ = dalloc(&(ptr), (n)); if (e_ != cudaSuccess) { \
+    h->err = std::string("cudaMalloc " #ptr ": ") + cudaGetErrorString(e_); vlo_destroy(h); return VLO_ERR_CUDA; } } while (0)
+
+static int ensure_pinned(vlo_handle *h, size_t bytes)
+{
+    if (bytes <= h->pinned_bytes) return VLO_OK;
+    if (h->pinned) cudaFreeHost(h->pinned);
+    h->pinned = nullptr; h->pinned_bytes = 0;
+    VLO_CUDA(cudaMallocHost(&h->pinned, bytes));
+    h->pinned_bytes = bytes;
+    return VLO_OK;
+}
+
+static int alloc_grid(vlo_handle *h, VoxelGridDev &g, int max_pts, float cell)
+{
+    int ts = 256; while (ts < 2 * max_pts) ts <<= 1;
+    g.cell = cell; g.inv_cell = 1.0f / cell; g.table_size = ts; g.n_points = 0;
+    HALLOC(g.keys, (size_t)ts); HALLOC(g.cell_start, (size_t)ts); HALLOC(g.cell_count, (size_t)ts);
+    HALLOC(g.cell_cursor, (size_t)ts); HALLOC(g.sorted_pts, (size_t)max_pts);
+    return VLO_OK;
+}
+
+static void free_grid(VoxelGridDev &g)
+{
+    cudaFree(g.keys); cudaFree(g.cell_start); cudaFree(g.cell_count); cudaFree(g.cell_cursor); cudaFree(g.sorted_pts);
+    memset(&g, 0, sizeof(g));
+}
+
+extern "C" int vlo_create(const vlo_config *cfg, vlo_handle **out)
+{
+    if (!cfg || !out) return VLO_ERR_INVALID_ARG;
+    *out = nullptr;
+    const vlo_config &c = *cfg;
+    if (c.max_scans < 1 || c.max_points < 1 || c.n_rings < 1 || c.n_rings > VLO_MAX_RINGS ||
+        c.feature_regions < 1 || c.feature_regions > VLO_MAX_REGIONS || c.curvature_region < 1 || c.curvature_region > 15 ||
+        c.max_ring_points < 32 || c.max_ring_points > 4096 || c.max_corner_sharp < 0 || c.max_corner_less_sharp < c.max_corner_sharp ||
+        c.max_corner_less_sharp > 255 || c.max_surface_flat < 0 || c.max_surface_flat > 255 || !(c.upper_deg > c.lower_deg) ||
+        !(c.less_flat_filter_size > 0.f) || !(c.scan_period > 0.f))
+        return VLO_ERR_INVALID_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || c.device >= ndev) return VLO_ERR_NO_DEVICE;
+    if (cudaSetDevice(c.device) != cudaSuccess) return VLO_ERR_NO_DEVICE;
+    vlo_handle *h = new vlo_handle();
+    h->cfg = c; h->launches = 0; h->pinned = nullptr; h->pinned_bytes = 0;
+    memset(&h->sb, 0, sizeof(h->sb));
+    h->d_grid_corner = h->d_grid_surf = nullptr; h->d_map_grid = nullptr;
+    memset(h->map_grid, 0, sizeof(h->map_grid)); h->map_pts[0] = h->map_pts[1] = nullptr; h->map_n[0] = h->map_n[1] = 0;
+    h->status_word = nullptr; h->pair_T = h->pair_seed = nullptr; h->pair_last = h->pair_cur = h->pair_state = nullptr;
+    h->pair_cidx = h->pair_sidx = h->pair_trace = nullptr; h->pair_result = nullptr; h->tgt_corner = h->tgt_surf = nullptr;
+    h->map_partials = nullptr; h->map_idx5 = nullptr;
+    h->online_have_last = 0; h->online_slot = 0;
+    memset(h->online_T, 0, sizeof(h->online_T)); memset(h->online_sum, 0, sizeof(h->online_sum));
+    memset(h->online_map_T, 0, sizeof(h->online_map_T));
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return VLO_ERR_CUDA; }
+    const int B = c.max_scans, N = c.max_points, R = c.n_rings, NR = c.feature_regions;
+    h->tiles_per_scan = (N + 255) / 256;
+    h->cap_sharp = R * NR * std::max(c.max_corner_sharp, 1);
+    h->cap_lsharp = R * NR * std::max(c.max_corner_less_sharp, 1);
+    h->cap_flat = R * NR * std::max(c.max_surface_flat, 1);
+    ScanBatchDev &sb = h->sb;
+    HALLOC(h->status_word, 1);
+    cudaMemset(h->status_word, 0, sizeof(int));
+    HALLOC(sb.raw_owned, (size_t)B * N * 4);
+    HALLOC(sb.raw_offset, (size_t)B + 1);
+    HALLOC(sb.first_half, (size_t)B); HALLOC(sb.ori_bounds, (size_t)B * 2);
+    HALLOC(sb.tile_hist, (size_t)B * R * h->tiles_per_scan);
+    HALLOC(sb.cloud, (size_t)B * N); HALLOC(sb.ring_start, (size_t)B * (VLO_MAX_RINGS + 1)); HALLOC(sb.src_index, (size_t)B * N);
+    HALLOC(sb.label, (size_t)B * N); HALLOC(sb.curvature, (size_t)B * N); HALLOC(sb.picked, (size_t)B * N);
+    HALLOC(sb.slot_sharp, (size_t)B * h->cap_sharp); HALLOC(sb.slot_lsharp, (size_t)B * h->cap_lsharp);
+    HALLOC(sb.slot_flat, (size_t)B * h->cap_flat); HALLOC(sb.slot_cnt, (size_t)B * R * NR * 4);
+    HALLOC(sb.lflat_slotted, (size_t)B * N); HALLOC(sb.lflat_cnt, (size_t)B * R);
+    HALLOC(sb.counts, (size_t)B * 8);
+    HALLOC(sb.sharp_idx, (size_t)B * h->cap_sharp); HALLOC(sb.lsharp_idx, (size_t)B * h->cap_lsharp); HALLOC(sb.flat_idx, (size_t)B * h->cap_flat);
+    HALLOC(sb.sharp_pts, (size_t)B * h->cap_sharp); HALLOC(sb.lsharp_pts, (size_t)B * h->cap_lsharp); HALLOC(sb.flat_pts, (size_t)B * h->cap_flat);
+    HALLOC(sb.lflat_pts, (size_t)B * N);
+    HALLOC(sb.lsharp_ring_start, (size_t)B * (VLO_MAX_RINGS + 1)); HALLOC(sb.lflat_ring_start, (size_t)B * (VLO_MAX_RINGS + 1));
+    cudaMemset(sb.counts, 0, (size_t)B * 8 * sizeof(int));
+    // registration workspace: at most one pair per resident scan
+    h->max_pairs = B;
+    HALLOC(h->pair_T, (size_t)B * 6); HALLOC(h->pair_seed, (size_t)B * 6);
+    HALLOC(h->pair_last, (size_t)B); HALLOC(h->pair_cur, (size_t)B); HALLOC(h->pair_state, (size_t)B * 4);
+    HALLOC(h->pair_cidx, (size_t)B * h->cap_sharp * 2); HALLOC(h->pair_sidx, (size_t)B * h->cap_flat * 3);
+    HALLOC(h->pair_trace, (size_t)B * 5 * (h->cap_sharp * 2 + h->cap_flat * 3));
+    HALLOC(h->pair_result, (size_t)B);
+    HALLOC(h->tgt_corner, (size_t)B * h->cap_lsharp); HALLOC(h->tgt_surf, (size_t)B * N);
+    h->grid_corner.resize(B); h->grid_surf.resize(B);
+    for (int b = 0; b < B; b++) {
+        memset(&h->grid_corner[b], 0, sizeof(VoxelGridDev)); memset(&h->grid_surf[b], 0, sizeof(VoxelGridDev));
+    }
+    for (int b = 0; b < B; b++) {
+        int rc = alloc_grid(h, h->grid_corner[b], h->cap_lsharp, c.odom_cell_size); if (rc) return rc;
+        rc = alloc_grid(h, h->grid_surf[b], N, c.odom_cell_size); if (rc) return rc;
+    }
+    HALLOC(h->d_grid_corner, (size_t)B); HALLOC(h->d_grid_surf, (size_t)B);
+    cudaMemcpy(h->d_grid_corner, h->grid_corner.data(), sizeof(VoxelGridDev) * B, cudaMemcpyHostToDevice);
+    cudaMemcpy(h->d_grid_surf, h->grid_surf.data(), sizeof(VoxelGridDev) * B, cudaMemcpyHostToDevice);
+    if (c.max_map_points > 0) {
+        for (int w = 0; w < 2; w++) {
+            HALLOC(h->map_pts[w], (size_t)c.max_map_points);
+            int rc = alloc_grid(h, h->map_grid[w], c.max_map_points, c.map_cell_size); if (rc) return rc;
+        }
+        HALLOC(h->d_map_grid, 2);
+        int qcap = h->cap_lsharp + N;
+        HALLOC(h->map_partials, (size_t)B * ((qcap + 31) / 32 + 2) * VLO_NTERM);
+        HALLOC(h->map_idx5, (size_t)B * qcap * 5);
+    }
+    if (cudaDeviceSynchronize() != cudaSuccess) { h->err = "device sync after allocation failed"; vlo_destroy(h); return VLO_ERR_CUDA; }
+    *out = h;
+    return VLO_OK;
+}
+
+extern "C" void vlo_destroy(vlo_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    cudaStreamSynchronize(h->stream);
+    ScanBatchDev &sb = h->sb;
+    void *ptrs[] = { sb.raw_owned, sb.raw_offset, sb.first_half, sb.ori_bounds, sb.tile_hist, sb.cloud, sb.ring_start, sb.src_index,
+                     sb.label, sb.curvature, sb.picked, sb.slot_sharp, sb.slot_lsharp, sb.slot_flat, sb.slot_cnt, sb.lflat_slotted,
+                     sb.lflat_cnt, sb.counts, sb.sharp_idx, sb.lsharp_idx, sb.flat_idx, sb.sharp_pts, sb.lsharp_pts, sb.flat_pts,
+                     sb.lflat_pts, sb.lsharp_ring_start, sb.lflat_ring_start, h->status_word, h->pair_T, h->pair_seed, h->pair_last,
+                     h->pair_cur, h->pair_state, h->pair_cidx, h->pair_sidx, h->pair_trace, h->pair_result, h->tgt_corner, h->tgt_surf,
+                     h->d_grid_corner, h->d_grid_surf, h->d_map_grid, h->map_pts[0], h->map_pts[1], h->map_partials, h->map_idx5 };
+    for (void *p : ptrs) if (p) cudaFree(p);
+    for (auto &g : h->grid_corner) free_grid(g);
+    for (auto &g : h->grid_surf) free_grid(g);
+    free_grid(h->map_grid[0]); free_grid(h->map_grid[1]);
+    if (h->pinned) cudaFreeHost(h->pinned);
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" const char *vlo_last_error(const vlo_handle *h) { return h ? h->err.c_str() : "null handle"; }
+extern "C" long long vlo_launch_count(const vlo_handle *h) { return h ? h->launches : 0; }
+
+extern "C" int vlo_synchronize(vlo_handle *h)
+{
+    if (!h) return VLO_ERR_INVALID_ARG;
+    VLO_CUDA(cudaStreamSynchronize(h->stream));
+    int st = 0;
+    VLO_CUDA(cudaMemcpy(&st, h->status_word, sizeof(int), cudaMemcpyDeviceToHost));
+    if (st & 1) { h->err = "a ring holds more points than max_ring_points"; return VLO_ERR_CAPACITY; }
+    return VLO_OK;
+}
+
+extern "C" int vlo_scans_upload(vlo_handle *h, const float *raw, const int *offsets, int n_scans, int stride, int on_device)
+{
+    if (!h || !raw || !offsets || n_scans < 1 || stride < 3) return VLO_ERR_INVALID_ARG;
+    if (n_scans > h->cfg.max_scans) { h->err = "n_scans exceeds max_scans"; return VLO_ERR_CAPACITY; }
+    for (int s = 0; s < n_scans; s++) {
+        int n = offsets[s + 1] - offsets[s];
+        if (n < 0) return VLO_ERR_INVALID_ARG;
+        if (n > h->cfg.max_points) { h->err = "a scan exceeds max_points"; return VLO_ERR_CAPACITY; }
+    }
+    cudaSetDevice(h->cfg.device);
+    ScanBatchDev &sb = h->sb;
+    size_t total = (size_t)(offsets[n_scans] - offsets[0]);
+    int rc = ensure_pinned(h, sizeof(int) * (size_t)(h->cfg.max_scans + 1)); if (rc) return rc;
+    int *poff = (int *)h->pinned;
+    for (int s = 0; s <= n_scans; s++) poff[s] = offsets[s] - offsets[0];
+    VLO_CUDA(cudaMemcpyAsync(sb.raw_offset, poff, sizeof(int) * (size_t)(n_scans + 1), cudaMemcpyHostToDevice, h->stream));
+    if (on_device) {
+        sb.raw = raw + (size_t)offsets[0] * stride;
+    } else {
+        if (total * stride > (size_t)h->cfg.max_scans * h->cfg.max_points * 4) { h->err = "raw payload exceeds staging capacity (stride > 4?)"; return VLO_ERR_CAPACITY; }
+        VLO_CUDA(cudaMemcpyAsync(sb.raw_owned, raw + (size_t)offsets[0] * stride, total * stride * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        sb.raw = sb.raw_owned;
+    }
+    // the offsets staging buffer is reused by the next call: make the copy complete first
+    VLO_CUDA(cudaStreamSynchronize(h->stream));
+    sb.n_scans = n_scans; sb.stride = stride;
+    return VLO_OK;
+}
+
+extern "C" int vlo_scans_organise(vlo_handle *h)
+{
+    if (!h) return VLO_ERR_INVALID_ARG;
+    if (h->sb.n_scans < 1) { h->err = "no scans uploaded"; return VLO_ERR_STATE; }
+    cudaSetDevice(h->cfg.device);
+    return vlo_launch_organise(h);
+}
+
+extern "C" int vlo_scans_extract(vlo_handle *h)
+{
+    if (!h) return VLO_ERR_INVALID_ARG;
+    if (h->sb.n_scans < 1) { h->err = "no scans uploaded"; return VLO_ERR_STATE; }
+    cudaSetDevice(h->cfg.device);
+    return vlo_launch_extract(h);
+}
+
+extern "C" int vlo_scans_counts(vlo_handle *h, vlo_feature_counts *counts)
+{
+    if (!h || !counts) return VLO_ERR_INVALID_ARG;
+    int B = h->sb.n_scans;
+    std::vector<int> tmp((size_t)B * 8);
+    VLO_CUDA(cudaMemcpyAsync(tmp.data(), h->sb.counts, sizeof(int) * tmp.size(), cudaMemcpyDeviceToHost, h->stream));
+    int rc = vlo_synchronize(h); if (rc) return rc;
+    for (int b = 0; b < B; b++) {
+        counts[b].n_valid = tmp[b * 8]; counts[b].n_sharp = tmp[b * 8 + 1]; counts[b].n_less_sharp = tmp[b * 8 + 2];
+        counts[b].n_flat = tmp[b * 8 + 3]; counts[b].n_less_flat = tmp[b * 8 + 4];
+    }
+    return VLO_OK;
+}
+
+extern "C" int vlo_scan_get_cloud(vlo_handle *h, int scan, float *cloud, int *ring_start, int *src_index)
+{
+    if (!h || scan < 0 || scan >= h->sb.n_scans) return VLO_ERR_INVALID_ARG;
+    int rc = vlo_synchronize(h); if (rc) return rc;
+    int cnt[8];
+    VLO_CUDA(cudaMemcpy(cnt, h->sb.counts + scan * 8, sizeof(cnt), cudaMemcpyDeviceToHost));
+    size_t N = h->cfg.max_points;
+    if (cloud) VLO_CUDA(cudaMemcpy(cloud, h->sb.cloud + scan * N, sizeof(float4) * (size_t)cnt[0], cudaMemcpyDeviceToHost));
+    if (src_index) VLO_CUDA(cudaMemcpy(src_index, h->sb.src_index + scan * N, sizeof(int) * (size_t)cnt[0], cudaMemcpyDeviceToHost));
+    if (ring_start) VLO_CUDA(cudaMemcpy(ring_start, h->sb.ring_start + scan * (VLO_MAX_RINGS + 1), sizeof(int) * (size_t)(h->cfg.n_rings + 1), cudaMemcpyDeviceToHost));
+    return VLO_OK;
+}
+
+extern "C" int vlo_scan_get_features(vlo_handle *h, int scan, int8_t *label, float *curvature, uint8_t *picked,
+                                     int *sharp_idx, int *less_sharp_idx, int *flat_idx, float *less_flat,
+                                     int *lsharp_ring_start, int *lflat_ring_start)
+{
+    if (!h || scan < 0 || scan >= h->sb.n_scans) return VLO_ERR_INVALID_ARG;
+    int rc = vlo_synchronize(h); if (rc) return rc;
+    ScanBatchDev &sb = h->sb;
+    int cnt[8];
+    VLO_CUDA(cudaMemcpy(cnt, sb.counts + scan * 8, sizeof(cnt), cudaMemcpyDeviceToHost));
+    size_t N = h->cfg.max_points; int R = h->cfg.n_rings;
+    if (label) VLO_CUDA(cudaMemcpy(label, sb.label + scan * N, (size_t)cnt[0], cudaMemcpyDeviceToHost));
+    if (curvature) VLO_CUDA(cudaMemcpy(curvature, sb.curvature + scan * N, sizeof(float) * (size_t)cnt[0], cudaMemcpyDeviceToHost));
+    if (picked) VLO_CUDA(cudaMemcpy(picked, sb.picked + scan * N, (size_t)cnt[0], cudaMemcpyDeviceToHost));
+    if (sharp_idx) VLO_CUDA(cudaMemcpy(sharp_idx, sb.sharp_idx + (size_t)scan * h->cap_sharp, sizeof(int) * (size_t)cnt[1], cudaMemcpyDeviceToHost));
+    if (less_sharp_idx) VLO_CUDA(cudaMemcpy(less_sharp_idx, sb.lsharp_idx + (size_t)scan * h->cap_lsharp, sizeof(int) * (size_t)cnt[2], cudaMemcpyDeviceToHost));
+    if (flat_idx) VLO_CUDA(cudaMemcpy(flat_idx, sb.flat_idx + (size_t)scan * h->cap_flat, sizeof(int) * (size_t)cnt[3], cudaMemcpyDeviceToHost));
+    if (lsharp_ring_start) VLO_CUDA(cudaMemcpy(lsharp_ring_start, sb.lsharp_ring_start + scan * (VLO_MAX_RINGS + 1), sizeof(int) * (size_t)(R + 1), cudaMemcpyDeviceToHost));
+    if (lflat_ring_start) VLO_CUDA(cudaMemcpy(lflat_ring_start, sb.lflat_ring_start + scan * (VLO_MAX_RINGS + 1), sizeof(int) * (size_t)(R + 1), cudaMemcpyDeviceToHost));
+    if (less_flat) {
+        std::vector<int> rs(R + 1), lc(R);
+        VLO_CUDA(cudaMemcpy(rs.data(), sb.ring_start + scan * (VLO_MAX_RINGS + 1), sizeof(int) * (size_t)(R + 1), cudaMemcpyDeviceToHost));
+        VLO_CUDA(cudaMemcpy(lc.data(), sb.lflat_cnt + scan * R, sizeof(int) * (size_t)R, cudaMemcpyDeviceToHost));
+        size_t o = 0;
+        for (int r = 0; r < R; r++) {
+            if (lc[r] > 0) VLO_CUDA(cudaMemcpy(less_flat + o * 4, sb.lflat_slotted + scan * N + rs[r], sizeof(float4) * (size_t)lc[r], cudaMemcpyDeviceToHost));
+            o += (size_t)lc[r];
+        }
+    }
+    return VLO_OK;
+}

@@ -1,0 +1,195 @@
+// Internal definitions shared by the sm_100a kernels and the C-ABI (include/vlo.h).
+// Compiled with --fmad=false: every float32 expression that is compared bit-for-bit against the
+// oracle must evaluate as separate IEEE mul/add (see DESIGN.md "Determinism").
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/vlo.h"
+
+#define VLO_NTERM 28          // 21 upper-tri AtA + 6 AtB + sum of squared weighted residuals
+#define VLO_PI_D 3.14159265358979323846
+
+struct VoxelGridDev {         // one voxel-hash grid over one target cloud
+    float cell, inv_cell;
+    int   table_size;         // power of two
+    unsigned long long *keys; // packed cell coords, ~0ull = empty
+    int  *cell_start;         // into sorted_pts
+    int  *cell_count;
+    int  *cell_cursor;
+    float4 *sorted_pts;       // xyz + original index bits in w
+    int   n_points;
+};
+
+// Device-resident state of a batch of scans (capacities from vlo_config)
+struct ScanBatchDev {
+    int    n_scans;
+    int    stride;            // floats per raw point
+    const float *raw;         // device pointer (owned or borrowed)
+    float *raw_owned;
+    int   *raw_offset;        // [B+1] device
+    // K0
+    int   *first_half;        // [B]  first valid index with halfPassed condition
+    float *ori_bounds;        // [B][2] startOri, endOri
+    int   *tile_hist;         // [B][R][tiles]
+    float4 *cloud;            // [B][N] ring-major
+    int   *ring_start;        // [B][R+1]
+    int   *src_index;         // [B][N]
+    // K1
+    int8_t *label;            // [B][N]
+    float  *curvature;        // [B][N]
+    uint8_t *picked;          // [B][N]
+    int   *slot_sharp;        // [B][R][NR][max_sharp]   cloud indices, -1 padded
+    int   *slot_lsharp;       // [B][R][NR][max_lsharp]
+    int   *slot_flat;         // [B][R][NR][max_flat]
+    uint8_t *slot_cnt;        // [B][R][NR][4]  (sharp, lsharp, flat, unused)
+    float4 *lflat_slotted;    // [B][N]  ring r's centroids at [ring_start[r], +lflat_cnt[r])
+    int   *lflat_cnt;         // [B][R]
+    // K1b dense feature packs
+    int   *counts;            // [B][8]: n_valid n_sharp n_lsharp n_flat n_lflat status
+    int   *sharp_idx, *lsharp_idx, *flat_idx;   // [B][cap]
+    float4 *sharp_pts, *lsharp_pts, *flat_pts;  // [B][cap]
+    float4 *lflat_pts;                          // [B][N] dense
+    int   *lsharp_ring_start, *lflat_ring_start; // [B][R+1]
+};
+
+struct vlo_handle {
+    vlo_config cfg;
+    cudaStream_t stream;
+    std::string err;
+    long long launches;
+    int tiles_per_scan;
+    int cap_sharp, cap_lsharp, cap_flat;
+    ScanBatchDev sb;
+    int *status_word;          // device: sticky error bits from kernels
+    // registration workspace
+    int   max_pairs;
+    float *pair_T;             // [P][6]
+    float *pair_seed;
+    int   *pair_last, *pair_cur;
+    int   *pair_state;         // [P][4]: converged, iterations, is_degenerate, status
+    int   *pair_cidx;          // [P][cap_sharp][2]
+    int   *pair_sidx;          // [P][cap_flat][3]
+    int   *pair_trace;         // first-association copy for parity tests (5 rounds)
+    vlo_result *pair_result;   // device results [P]
+    float4 *tgt_corner, *tgt_surf;   // [B][cap] last clouds moved to sweep end (online) or aliases
+    // grids for scan-to-scan targets (one per scan) and the map
+    std::vector<VoxelGridDev> grid_corner, grid_surf;   // host copies of device descriptors
+    VoxelGridDev *d_grid_corner, *d_grid_surf;          // device arrays [B]
+    VoxelGridDev map_grid[2];
+    VoxelGridDev *d_map_grid;
+    float4 *map_pts[2];
+    int map_n[2];
+    // mapping workspace
+    float *map_partials;       // [n][blocks][28]
+    int   *map_idx5;           // [n][Q][5]
+    // pinned staging
+    void *pinned; size_t pinned_bytes;
+    // online state
+    int online_have_last; float online_T[6]; float online_sum[6]; float online_map_T[6];
+    int online_slot;
+};
+
+#define VLO_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return VLO_ERR_CUDA; } } while (0)
+
+// ----------------------------------------------------------------------------------------------
+// deterministic float32 elementary functions (Cephes single-precision kernels, no FMA): the same
+// published algorithm the oracle restates in oracle/detmath.h.
+__device__ __forceinline__ void vlo_sincosf(float x, float &s_out, float &c_out)
+{
+    const float two_over_pi = 0.63661977236758134308f;
+    const float P1 = 1.5703125f, P2 = 4.837512969970703125e-4f, P3 = 7.54978995489188216e-8f;
+    float kf = rintf(x * two_over_pi);
+    int k = (int)kf;
+    float r = x - kf * P1;
+    r = r - kf * P2;
+    r = r - kf * P3;
+    float z = r * r;
+    float sp = -1.9515295891e-4f * z;
+    sp = sp + 8.3321608736e-3f;
+    sp = sp * z;
+    sp = sp - 1.6666654611e-1f;
+    sp = sp * z;
+    sp = sp * r;
+    float sn = sp + r;
+    float cp = 2.443315711809948e-5f * z;
+    cp = cp - 1.388731625493765e-3f;
+    cp = cp * z;
+    cp = cp + 4.166664568298827e-2f;
+    cp = cp * z;
+    cp = cp * z;
+    float hz = 0.5f * z;
+    float cs = cp - hz;
+    cs = cs + 1.0f;
+    switch (k & 3) {
+    case 0: s_out = sn;  c_out = cs;  break;
+    case 1: s_out = cs;  c_out = -sn; break;
+    case 2: s_out = -sn; c_out = -cs; break;
+    default: s_out = -cs; c_out = sn; break;
+    }
+}
+
+__device__ __forceinline__ float vlo_atanf(float xx)
+{
+    float x = fabsf(xx), y;
+    if (x > 2.414213562373095f) { y = 1.5707963267948966f; x = -(1.0f / x); }
+    else if (x > 0.4142135623730950f) { y = 0.7853981633974483f; x = (x - 1.0f) / (x + 1.0f); }
+    else y = 0.0f;
+    float z = x * x;
+    float p = 8.05374449538e-2f * z;
+    p = p - 1.38776856032e-1f;
+    p = p * z;
+    p = p + 1.99777106478e-1f;
+    p = p * z;
+    p = p - 3.33329491539e-1f;
+    p = p * z;
+    p = p * x;
+    p = p + x;
+    y = y + p;
+    return (xx < 0.0f) ? -y : y;
+}
+
+__device__ __forceinline__ float vlo_atan2f(float y, float x)
+{
+    const float PI_F = 3.14159265358979323846f, PIO2_F = 1.5707963267948966f;
+    if (x == 0.0f) { if (y > 0.0f) return PIO2_F; if (y < 0.0f) return -PIO2_F; return 0.0f; }
+    float a = vlo_atanf(y / x);
+    if (x < 0.0f) { if (y < 0.0f) return a - PI_F; return a + PI_F; }
+    return a;
+}
+
+__device__ __forceinline__ float sqdiff3(float ax, float ay, float az, float bx, float by, float bz)
+{
+    float dx = ax - bx, dy = ay - by, dz = az - bz;
+    return (dx * dx + dy * dy) + dz * dz;
+}
+
+// transformToStart: T = rx ry rz tx ty tz
+__device__ __forceinline__ float4 vlo_to_start(const float *T, float4 p, int deskew, float inv_period)
+{
+    float s = deskew ? inv_period * (p.w - (float)(int)p.w) : 1.0f;
+    float x = p.x - s * T[3], y = p.y - s * T[4], z = p.z - s * T[5];
+    float sx, cx, sy, cy, sz, cz;
+    vlo_sincosf(-s * T[0], sx, cx);
+    vlo_sincosf(-s * T[1], sy, cy);
+    vlo_sincosf(-s * T[2], sz, cz);
+    float x0 = x; x = cz * x0 - sz * y; y = sz * x0 + cz * y;          // rotZ
+    float y0 = y; y = cx * y0 - sx * z; z = sx * y0 + cx * z;          // rotX
+    x0 = x;       x = cy * x0 + sy * z; z = cy * z - sy * x0;          // rotY
+    return make_float4(x, y, z, p.w);
+}
+
+// kernels' host launchers -----------------------------------------------------------------------
+int vlo_launch_organise(vlo_handle *h);
+int vlo_launch_extract(vlo_handle *h);
+int vlo_launch_grid_build(vlo_handle *h, VoxelGridDev *d_grids, const std::vector<VoxelGridDev> &grids,
+                          const float4 *pts_base, size_t pts_stride, const int *counts_base, int counts_stride,
+                          int counts_field, int n_grids, int max_pts);
+int vlo_launch_register_pairs(vlo_handle *h, int n_pairs, int have_last_T, const float *d_last_T);
+int vlo_launch_imu(vlo_handle *h, const double *d_t, const double *d_acc, const double *d_gyro, int n_samples,
+                   const double *d_t0, const double *d_t1, const double *d_bias, int n_factors, vlo_preint *d_out);
+int vlo_map_build_impl(vlo_handle *h, int which, const float *pts, int n, int on_device);
+int vlo_launch_register_map(vlo_handle *h, const int *d_scans, int n, int max_q);
+int vlo_launch_map_knn(vlo_handle *h, int which, const float4 *d_q, int nq, int k, int *d_idx, float *d_d2);
