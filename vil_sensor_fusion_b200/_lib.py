@@ -68,6 +68,7 @@ SYMBOLS = {
     "vlo_scan_get_cloud": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP]),
     "vlo_scan_get_features": (C.c_int, [_VP, C.c_int] + [_VP] * 9),
     "vlo_register_pairs": (C.c_int, [_VP, _VP, _VP, C.c_int, _VP, _VP, _VP]),
+    "vlo_set_trace": (C.c_int, [_VP, C.c_int]),
     "vlo_pair_get_correspondences": (C.c_int, [_VP, C.c_int, C.c_int, _VP, _VP]),
     "vlo_map_build": (C.c_int, [_VP, _VP, C.c_int, _VP, C.c_int, C.c_int]),
     "vlo_register_map": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP]),

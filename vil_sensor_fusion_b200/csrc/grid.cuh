@@ -16,17 +16,6 @@
 
 #define GRID_EMPTY 0xFFFFFFFFFFFFFFFFull
 
-struct GridSet {
-    float cell, inv_cell;
-    int ts;              // table size (power of two)
-    int max_pts;
-    int G;
-    unsigned long long *keys;
-    int *cnt;
-    int *start;
-    float4 *sorted;
-};
-
 __device__ __forceinline__ unsigned long long grid_key(int ix, int iy, int iz)
 {
     return ((unsigned long long)(unsigned)(ix + (1 << 20)) << 42) | ((unsigned long long)(unsigned)(iy + (1 << 20)) << 21)

@@ -2,18 +2,6 @@
 // See grid.cuh for the layout and the exactness contract.
 #include "grid.cuh"
 
-// point sources: ring-slotted clouds (ring r's live points at [ring_off[r], +ring_cnt[r]) of a
-// per-grid base array; dense index = dense_start[r] + offset) or plain dense arrays.
-struct GridSource {
-    const float4 *pts; size_t pts_stride;       // per grid
-    const int *ring_off; int ring_off_stride;   // [R+1] slot offsets (NULL -> dense source)
-    const int *ring_cnt; int ring_cnt_stride;   // [R]
-    const int *dense_start; int dense_start_stride; // [R+1]
-    const int *n_dense; int n_dense_stride; int n_dense_field;   // dense sources: point count per grid
-    int n_rings;
-    const int *grid_scan;                        // optional indirection: grid g reads scan grid_scan[g]
-};
-
 __device__ __forceinline__ bool grid_src_point(const GridSource &src, int g, int i, float4 &p, unsigned &tag)
 {
     int b = src.grid_scan ? src.grid_scan[g] : g;

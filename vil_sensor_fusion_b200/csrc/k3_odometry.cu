@@ -1,0 +1,426 @@
+// K3/K5  scan-to-scan registration (LaserOdometry): association on the voxel-hash grids of the
+// previous sweep + fused linearisation / deterministic reduction / on-device solve.
+// Replaces BasicLaserOdometry::process of the `loam` nodelet (gtsam_fusion/launch/loam.launch:40-45;
+// knobs loam_params.yaml:36-39); SURVEY.md Appendix A.4-A.7 is the algorithm, oracle/laser_odometry.c
+// the frozen operation order (R1 three-level blocked summation, R2..R5).
+//   k3_assoc : one warp per feature point: transformToStart, exact 1-NN, ring-constrained partner
+//              search with upstream's forward/backward tie order, all on the grids (grid.cuh)
+//   k3_gn    : one CTA per scan pair runs up to 5 Gauss-Newton iterations between associations:
+//              thread per correspondence -> 28 products -> shared-memory transposed R1 reduction ->
+//              warp 0 solves (QR), iteration 0 also runs the single-warp Jacobi degeneracy test.
+// The host enqueues [k3_assoc, k3_gn] x ceil(maxIter/5) back to back; convergence is a device flag,
+// so control never returns to the host inside a registration.
+#include "grid.cuh"
+#include "dense6.cuh"
+
+struct OdomParams {
+    // features of the current sweep (queries) and the previous sweep (targets), per scan
+    const float4 *sharp_pts, *flat_pts; int cap_sharp, cap_flat;
+    const float4 *lsharp_pts; int cap_lsharp;            // dense ring-major, intensity = ring (+relTime)
+    const float4 *lflat_slotted; int N;                  // ring-slotted
+    const int *ring_start, *lflat_cnt, *lsharp_ring_start, *lflat_ring_start;   // [B][R+1] / [B][R]
+    const int *counts;                                   // [B][8]
+    int n_rings;
+    // pairs
+    const int *pair_last, *pair_cur; float *pair_T; int *pair_state; int *cidx, *sidx; vlo_result *result;
+    GridSet gc, gsf;                                     // corner / surf grids, grid index = scan index
+    int deskew; float inv_period; int fwd_quirk;
+    int max_iter; float degen_thr, dT_abort, dR_abort, rot_thr, trans_thr;
+};
+
+__device__ __forceinline__ float4 lflat_point(const OdomParams &p, int scan, int dense)
+{
+    // dense index -> ring-slotted address
+    const int *ds = p.lflat_ring_start + (size_t)scan * (VLO_MAX_RINGS + 1);
+    int lo = 0, hi = p.n_rings;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (ds[mid] <= dense) lo = mid; else hi = mid; }
+    int slot = p.ring_start[(size_t)scan * (VLO_MAX_RINGS + 1) + lo] + (dense - ds[lo]);
+    return p.lflat_slotted[(size_t)scan * p.N + slot];
+}
+
+__global__ void __launch_bounds__(256) k3_assoc(OdomParams p, int n_pairs)
+{
+    const int pair = blockIdx.y;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (p.pair_state[pair * 4 + 0]) return;                          // converged
+    const int last = p.pair_last[pair], cur = p.pair_cur[pair];
+    const int n_sharp = p.counts[cur * 8 + 1], n_flat = p.counts[cur * 8 + 3];
+    const int n_lc = p.counts[last * 8 + 2], n_ls = p.counts[last * 8 + 4];
+    if (!(n_lc > 10 && n_ls > 100)) return;
+    float T[6];
+    #pragma unroll
+    for (int a = 0; a < 6; a++) T[a] = p.pair_T[pair * 6 + a];
+    if (w < p.cap_sharp) {
+        if (w >= n_sharp) return;
+        float4 q = vlo_to_start(T, p.sharp_pts[(size_t)cur * p.cap_sharp + w], p.deskew, p.inv_period);
+        TopK<1> nn;
+        grid_search<1>(p.gc, last, q.x, q.y, q.z, 25.0f, FilterAll(), nn, lane);
+        int i1 = -1, i2 = -1;
+        if (nn.tag[0] != GRID_NOTAG) {
+            i1 = (int)(nn.tag[0] & 0xFFFFFFu);
+            int ring = (int)(nn.tag[0] >> 24);
+            FilterPartner f; f.ind = i1; f.ring_lo = ring - 2; f.ring_hi = ring + 2; f.skip_ring = ring;
+            f.fwd_bound = p.fwd_quirk ? min(n_sharp, n_lc) : n_lc;
+            TopK<1> pr;
+            grid_search<1>(p.gc, last, q.x, q.y, q.z, 25.0f, f, pr, lane);
+            if (pr.tag[0] != GRID_NOTAG) i2 = (int)(pr.tag[0] & 0xFFFFFFu);
+        }
+        if (lane == 0) {
+            int *o = p.cidx + ((size_t)pair * p.cap_sharp + w) * 2;
+            o[0] = i1; o[1] = i2;
+        }
+    } else {
+        int f_i = w - p.cap_sharp;
+        if (f_i >= n_flat) return;
+        float4 q = vlo_to_start(T, p.flat_pts[(size_t)cur * p.cap_flat + f_i], p.deskew, p.inv_period);
+        TopK<1> nn;
+        grid_search<1>(p.gsf, last, q.x, q.y, q.z, 25.0f, FilterAll(), nn, lane);
+        int i1 = -1, i2 = -1, i3 = -1;
+        if (nn.tag[0] != GRID_NOTAG) {
+            i1 = (int)(nn.tag[0] & 0xFFFFFFu);
+            int ring = (int)(nn.tag[0] >> 24);
+            int fb = p.fwd_quirk ? min(n_flat, n_ls) : n_ls;
+            FilterPartner f2; f2.ind = i1; f2.ring_lo = ring; f2.ring_hi = ring; f2.skip_ring = -1; f2.fwd_bound = fb;
+            FilterPartner f3; f3.ind = i1; f3.ring_lo = ring - 2; f3.ring_hi = ring + 2; f3.skip_ring = ring; f3.fwd_bound = fb;
+            TopK<1> p2, p3;
+            grid_search<1>(p.gsf, last, q.x, q.y, q.z, 25.0f, f2, p2, lane);
+            grid_search<1>(p.gsf, last, q.x, q.y, q.z, 25.0f, f3, p3, lane);
+            if (p2.tag[0] != GRID_NOTAG) i2 = (int)(p2.tag[0] & 0xFFFFFFu);
+            if (p3.tag[0] != GRID_NOTAG) i3 = (int)(p3.tag[0] & 0xFFFFFFu);
+        }
+        if (lane == 0) {
+            int *o = p.sidx + ((size_t)pair * p.cap_flat + f_i) * 3;
+            o[0] = i1; o[1] = i2; o[2] = i3;
+        }
+    }
+}
+
+// Jacobian row of upstream's odometry step (s = 1), expression order as oracle/laser_odometry.c
+__device__ __forceinline__ void odom_jacobian_row(const float *T, const float *trig, float x, float y, float z,
+                                                  const float *coeff, float *row, float &bval)
+{
+    float srx = trig[0], crx = trig[1], sry = trig[2], cry = trig[3], srz = trig[4], crz = trig[5];
+    float tx = T[3], ty = T[4], tz = T[5];
+    float cx_ = coeff[0], cy_ = coeff[1], cz_ = coeff[2];
+    float arx = (-crx * sry * srz * x + crx * crz * sry * y + srx * sry * z
+                 + tx * crx * sry * srz - ty * crx * crz * sry - tz * srx * sry) * cx_
+              + (srx * srz * x - crz * srx * y + crx * z
+                 + ty * crz * srx - tz * crx - tx * srx * srz) * cy_
+              + (crx * cry * srz * x - crx * cry * crz * y - cry * srx * z
+                 + tz * cry * srx + ty * crx * cry * crz - tx * crx * cry * srz) * cz_;
+    float ary = ((-crz * sry - cry * srx * srz) * x
+                 + (cry * crz * srx - sry * srz) * y - crx * cry * z
+                 + tx * (crz * sry + cry * srx * srz) + ty * (sry * srz - cry * crz * srx)
+                 + tz * crx * cry) * cx_
+              + ((cry * crz - srx * sry * srz) * x
+                 + (cry * srz + crz * srx * sry) * y - crx * sry * z
+                 + tz * crx * sry - ty * (cry * srz + crz * srx * sry)
+                 - tx * (cry * crz - srx * sry * srz)) * cz_;
+    float arz = ((-cry * srz - crz * srx * sry) * x + (cry * crz - srx * sry * srz) * y
+                 + tx * (cry * srz + crz * srx * sry) - ty * (cry * crz - srx * sry * srz)) * cx_
+              + (-crx * crz * x - crx * srz * y
+                 + ty * crx * srz + tx * crx * crz) * cy_
+              + ((cry * crz * srx - sry * srz) * x + (crz * sry + cry * srx * srz) * y
+                 + tx * (sry * srz - cry * crz * srx) - ty * (crz * sry + cry * srx * srz)) * cz_;
+    float atx = -(cry * crz - srx * sry * srz) * cx_ + crx * srz * cy_ - (crz * sry + cry * srx * srz) * cz_;
+    float aty = -(cry * srz + crz * srx * sry) * cx_ - crx * crz * cy_ - (sry * srz - cry * crz * srx) * cz_;
+    float atz = crx * sry * cx_ - srx * cy_ - crx * cry * cz_;
+    row[0] = arx; row[1] = ary; row[2] = arz; row[3] = atx; row[4] = aty; row[5] = atz;
+    bval = (float)(-0.05 * (double)coeff[3]);
+}
+
+__device__ __forceinline__ bool edge_coeff(float4 sel, float4 a, float4 b, int iter, float *coeff)
+{
+    float x0 = sel.x, y0 = sel.y, z0 = sel.z, x1 = a.x, y1 = a.y, z1 = a.z, x2 = b.x, y2 = b.y, z2 = b.z;
+    float m1 = (x0 - x1) * (y0 - y2) - (x0 - x2) * (y0 - y1);
+    float m2 = (x0 - x1) * (z0 - z2) - (x0 - x2) * (z0 - z1);
+    float m3 = (y0 - y1) * (z0 - z2) - (y0 - y2) * (z0 - z1);
+    float a012 = sqrtf(m1 * m1 + m2 * m2 + m3 * m3);
+    float l12 = sqrtf((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2) + (z1 - z2) * (z1 - z2));
+    float la = ((y1 - y2) * m1 + (z1 - z2) * m2) / a012 / l12;
+    float lb = -((x1 - x2) * m1 - (z1 - z2) * m3) / a012 / l12;
+    float lc = -((x1 - x2) * m2 + (y1 - y2) * m3) / a012 / l12;
+    float ld2 = a012 / l12;
+    float s = 1.0f;
+    if (iter >= 5) s = 1.0f - 1.8f * fabsf(ld2);
+    coeff[0] = s * la; coeff[1] = s * lb; coeff[2] = s * lc; coeff[3] = s * ld2;
+    return (double)s > 0.1 && ld2 != 0.0f;
+}
+
+__device__ __forceinline__ bool plane_coeff(float4 sel, float4 t1, float4 t2, float4 t3, int iter, float *coeff)
+{
+    float pa = (t2.y - t1.y) * (t3.z - t1.z) - (t3.y - t1.y) * (t2.z - t1.z);
+    float pb = (t2.z - t1.z) * (t3.x - t1.x) - (t3.z - t1.z) * (t2.x - t1.x);
+    float pc = (t2.x - t1.x) * (t3.y - t1.y) - (t3.x - t1.x) * (t2.y - t1.y);
+    float pd = -(pa * t1.x + pb * t1.y + pc * t1.z);
+    float ps = sqrtf(pa * pa + pb * pb + pc * pc);
+    pa = pa / ps; pb = pb / ps; pc = pc / ps; pd = pd / ps;
+    float pd2 = pa * sel.x + pb * sel.y + pc * sel.z + pd;
+    float s = 1.0f;
+    if (iter >= 5) {
+        float dist = sqrtf(sel.x * sel.x + sel.y * sel.y + sel.z * sel.z);
+        s = 1.0f - 1.8f * fabsf(pd2) / sqrtf(dist);
+    }
+    coeff[0] = s * pa; coeff[1] = s * pb; coeff[2] = s * pc; coeff[3] = s * pd2;
+    return (double)s > 0.1 && pd2 != 0.0f;
+}
+
+#define GN_THREADS 256
+#define TSTRIDE 29     // padded row of the transposed term buffer
+
+// R1 block reduction of one chunk of 256 queries held in smem terms[256][TSTRIDE]:
+// 224 threads sum 32 consecutive queries each (level 1), then 28 threads fold the 8 level-1 sums into
+// the running level-2 accumulator; level 2 closes into level 3 every 1024 queries.
+__device__ __forceinline__ void r1_chunk(float *terms, float *l1buf, float *l2acc, float *l3acc, int chunk, int n_chunks, int q_total, int tid)
+{
+    __syncthreads();
+    if (tid < 8 * VLO_NTERM) {
+        int g = tid / VLO_NTERM, e = tid % VLO_NTERM;
+        float l1 = 0.0f;
+        const float *src = terms + (size_t)(g * 32) * TSTRIDE + e;
+        #pragma unroll 8
+        for (int k = 0; k < 32; k++) l1 = l1 + src[(size_t)k * TSTRIDE];
+        l1buf[g * VLO_NTERM + e] = l1;
+    }
+    __syncthreads();
+    if (tid < VLO_NTERM) {
+        float l2 = l2acc[tid];
+        for (int g = 0; g < 8; g++) if (chunk * 256 + g * 32 < q_total) l2 = l2 + l1buf[g * VLO_NTERM + tid];
+        if ((chunk & 3) == 3 || chunk == n_chunks - 1) { l3acc[tid] = l3acc[tid] + l2; l2 = 0.0f; }
+        l2acc[tid] = l2;
+    }
+}
+
+__global__ void __launch_bounds__(GN_THREADS) k3_gn(OdomParams p, int iter_base, int n_iters)
+{
+    __shared__ float terms[GN_THREADS * TSTRIDE];
+    __shared__ float l1buf[8 * VLO_NTERM];
+    __shared__ float l2acc[VLO_NTERM], l3acc[VLO_NTERM];
+    __shared__ float trig[6];
+    __shared__ GnScratch S;
+    __shared__ int s_ne, s_np;
+    const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int *state = p.pair_state + pair * 4;      // converged, iterations, is_degenerate, status
+    if (state[0]) return;
+    const int last = p.pair_last[pair], cur = p.pair_cur[pair];
+    const int n_sharp = p.counts[cur * 8 + 1], n_flat = p.counts[cur * 8 + 3];
+    const int n_lc = p.counts[last * 8 + 2], n_ls = p.counts[last * 8 + 4];
+    vlo_result *res = p.result + pair;
+    if (!(n_lc > 10 && n_ls > 100)) {           // upstream: not enough points in the last clouds -> no optimisation
+        if (tid == 0 && iter_base == 0) { state[1] = 0; state[3] = VLO_SOFT_TOO_FEW_CORR; res->status = VLO_SOFT_TOO_FEW_CORR; res->iterations = 0; }
+        return;
+    }
+    if (tid < 6) S.T[tid] = p.pair_T[pair * 6 + tid];
+    if (tid == 0) {
+        S.is_degenerate = state[2]; S.converged = 0; S.status = state[3]; S.iterations = state[1];
+        S.n_edge = res->n_corr_edge; S.n_plane = res->n_corr_plane;
+    }
+    if (tid < 36 && iter_base > 0) S.P[tid] = res->P[tid];
+    if (tid < VLO_NTERM) S.total[tid] = 0.0f;
+    __syncthreads();
+    const int q_total = n_sharp + n_flat;
+    const int n_chunks = (q_total + 255) / 256;
+    bool have_total = false, did_eig = false;
+    for (int it = iter_base; it < iter_base + n_iters && it < p.max_iter; it++) {
+        if (tid == 0) {
+            vlo_sincosf(S.T[0], trig[0], trig[1]);
+            vlo_sincosf(S.T[1], trig[2], trig[3]);
+            vlo_sincosf(S.T[2], trig[4], trig[5]);
+            s_ne = 0; s_np = 0;
+        }
+        if (tid < VLO_NTERM) { l2acc[tid] = 0.0f; l3acc[tid] = 0.0f; }
+        __syncthreads();
+        float T[6];
+        #pragma unroll
+        for (int a = 0; a < 6; a++) T[a] = S.T[a];
+        int my_edge = 0, my_plane = 0;
+        for (int chunk = 0; chunk < n_chunks; chunk++) {
+            int i = chunk * 256 + tid;
+            float t[VLO_NTERM];
+            #pragma unroll
+            for (int e = 0; e < VLO_NTERM; e++) t[e] = 0.0f;
+            if (i < q_total) {
+                float coeff[4]; bool keep = false; float4 ori;
+                if (i < n_sharp) {
+                    const int *ci = p.cidx + ((size_t)pair * p.cap_sharp + i) * 2;
+                    int i1 = ci[0], i2 = ci[1];
+                    ori = p.sharp_pts[(size_t)cur * p.cap_sharp + i];
+                    if (i2 >= 0) {
+                        float4 sel = vlo_to_start(T, ori, p.deskew, p.inv_period);
+                        float4 a = p.lsharp_pts[(size_t)last * p.cap_lsharp + i1];
+                        float4 b = p.lsharp_pts[(size_t)last * p.cap_lsharp + i2];
+                        keep = edge_coeff(sel, a, b, it, coeff);
+                        if (keep) my_edge++;
+                    }
+                } else {
+                    int f_i = i - n_sharp;
+                    const int *si = p.sidx + ((size_t)pair * p.cap_flat + f_i) * 3;
+                    int i1 = si[0], i2 = si[1], i3 = si[2];
+                    ori = p.flat_pts[(size_t)cur * p.cap_flat + f_i];
+                    if (i2 >= 0 && i3 >= 0) {
+                        float4 sel = vlo_to_start(T, ori, p.deskew, p.inv_period);
+                        float4 t1 = lflat_point(p, last, i1), t2 = lflat_point(p, last, i2), t3 = lflat_point(p, last, i3);
+                        keep = plane_coeff(sel, t1, t2, t3, it, coeff);
+                        if (keep) my_plane++;
+                    }
+                }
+                if (keep) {
+                    float row[6], bval;
+                    odom_jacobian_row(T, trig, ori.x, ori.y, ori.z, coeff, row, bval);
+                    int e = 0;
+                    #pragma unroll
+                    for (int a = 0; a < 6; a++)
+                        #pragma unroll
+                        for (int b = a; b < 6; b++) t[e++] = row[a] * row[b];
+                    #pragma unroll
+                    for (int a = 0; a < 6; a++) t[e++] = row[a] * bval;
+                    t[e] = coeff[3] * coeff[3];
+                }
+            }
+            __syncthreads();     // previous chunk's level-1 reads are done
+            #pragma unroll
+            for (int e = 0; e < VLO_NTERM; e++) terms[tid * TSTRIDE + e] = t[e];
+            r1_chunk(terms, l1buf, l2acc, l3acc, chunk, n_chunks, q_total, tid);
+        }
+        // correspondence counts
+        unsigned be = __reduce_add_sync(0xffffffffu, my_edge), bp = __reduce_add_sync(0xffffffffu, my_plane);
+        if (lane == 0) { atomicAdd(&s_ne, (int)be); atomicAdd(&s_np, (int)bp); }
+        __syncthreads();
+        if (tid == 0) S.iterations = it + 1;
+        if (s_ne + s_np < 10) { __syncthreads(); continue; }     // upstream: `continue` without update
+        if (tid < VLO_NTERM) S.total[tid] = l3acc[tid];
+        if (tid == 0) { S.n_edge = s_ne; S.n_plane = s_np; S.status = VLO_OK; }
+        have_total = true;
+        if (it == 0) did_eig = true;
+        __syncthreads();
+        if (warp == 0) vlo_gn_update_warp(S, it, p.degen_thr, p.dT_abort, p.dR_abort, lane);
+        __syncthreads();
+        if (S.converged) break;
+    }
+    __syncthreads();
+    if (tid < 6) { p.pair_T[pair * 6 + tid] = S.T[tid]; res->transform[tid] = S.T[tid]; }
+    if (did_eig) {
+        if (tid < 36) res->P[tid] = S.P[tid];
+        if (tid < 6) res->eig[tid] = S.eval[tid];
+    }
+    if (tid == 0) {
+        state[0] = S.converged; state[1] = S.iterations; state[2] = S.is_degenerate; state[3] = S.status;
+        res->iterations = S.iterations; res->is_degenerate = S.is_degenerate; res->status = S.status;
+        if (have_total) {
+            res->n_corr_edge = S.n_edge; res->n_corr_plane = S.n_plane;
+            vlo_finish_result(S, p.rot_thr, p.trans_thr, res);
+        }
+    }
+}
+
+// reset per-pair state and seed the transform
+__global__ void k3_init_pairs(OdomParams p, const float *seeds, int n_pairs)
+{
+    int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= n_pairs) return;
+    for (int a = 0; a < 6; a++) p.pair_T[pair * 6 + a] = seeds ? seeds[pair * 6 + a] : 0.0f;
+    int *st = p.pair_state + pair * 4;
+    st[0] = 0; st[1] = 0; st[2] = 0; st[3] = VLO_SOFT_TOO_FEW_CORR;
+    vlo_result *r = p.result + pair;
+    for (int a = 0; a < 6; a++) { r->transform[a] = p.pair_T[pair * 6 + a]; r->eig[a] = 0.0f; }
+    for (int a = 0; a < 36; a++) { r->hessian[a] = 0.0f; r->P[a] = (a % 7 == 0) ? 1.0f : 0.0f; r->cov[a] = 0.0; }
+    r->is_degenerate = 0; r->iterations = 0; r->n_corr_edge = 0; r->n_corr_plane = 0;
+    r->logdet_rot = 0.f; r->logdet_trans = 0.f; r->pass_dopt = 0; r->status = VLO_SOFT_TOO_FEW_CORR;
+}
+
+// transformToEnd applied in place to the previous sweep's target clouds (online mode)
+__global__ void __launch_bounds__(256) k3_to_end(OdomParams p, const int *scans, const float *Ts, int n, int which)
+{
+    int k = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    int scan = scans[k];
+    float T[6];
+    #pragma unroll
+    for (int a = 0; a < 6; a++) T[a] = Ts[k * 6 + a];
+    float4 *ptr;
+    if (which == 0) {
+        if (i >= p.counts[scan * 8 + 2]) return;
+        ptr = (float4 *)p.lsharp_pts + (size_t)scan * p.cap_lsharp + i;
+    } else {
+        const int *rs = p.ring_start + (size_t)scan * (VLO_MAX_RINGS + 1);
+        if (i >= rs[p.n_rings]) return;
+        int lo = 0, hi = p.n_rings;
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (rs[mid] <= i) lo = mid; else hi = mid; }
+        if (i - rs[lo] >= p.lflat_cnt[(size_t)scan * p.n_rings + lo]) return;
+        ptr = (float4 *)p.lflat_slotted + (size_t)scan * p.N + i;
+    }
+    float4 v = *ptr;
+    float4 q = vlo_to_start(T, v, p.deskew, p.inv_period);
+    float sx, cx, sy, cy, sz, cz;
+    vlo_sincosf(T[0], sx, cx); vlo_sincosf(T[1], sy, cy); vlo_sincosf(T[2], sz, cz);
+    float x = q.x, y = q.y, z = q.z;
+    float x0 = x; x = cy * x0 + sy * z; z = cy * z - sy * x0;          // rotY(ry)
+    float y0 = y; y = cx * y0 - sx * z; z = sx * y0 + cx * z;          // rotX(rx)
+    x0 = x;       x = cz * x0 - sz * y; y = sz * x0 + cz * y;          // rotZ(rz)
+    *ptr = make_float4(x + T[3], y + T[4], z + T[5], (float)(int)v.w);
+}
+
+static OdomParams make_params(vlo_handle *h)
+{
+    ScanBatchDev &sb = h->sb; const vlo_config &c = h->cfg;
+    OdomParams p;
+    p.sharp_pts = sb.sharp_pts; p.flat_pts = sb.flat_pts; p.cap_sharp = h->cap_sharp; p.cap_flat = h->cap_flat;
+    p.lsharp_pts = sb.lsharp_pts; p.cap_lsharp = h->cap_lsharp; p.lflat_slotted = sb.lflat_slotted; p.N = c.max_points;
+    p.ring_start = sb.ring_start; p.lflat_cnt = sb.lflat_cnt; p.lsharp_ring_start = sb.lsharp_ring_start;
+    p.lflat_ring_start = sb.lflat_ring_start; p.counts = sb.counts; p.n_rings = c.n_rings;
+    p.pair_last = h->pair_last; p.pair_cur = h->pair_cur; p.pair_T = h->pair_T; p.pair_state = h->pair_state;
+    p.cidx = h->pair_cidx; p.sidx = h->pair_sidx; p.result = h->pair_result;
+    p.gc = h->gs_corner; p.gsf = h->gs_surf;
+    p.deskew = c.deskew; p.inv_period = 1.0f / c.scan_period; p.fwd_quirk = c.odom_forward_bound_quirk;
+    p.max_iter = c.odom_max_iterations; p.degen_thr = c.odom_degen_eig; p.dT_abort = c.odom_delta_t_abort;
+    p.dR_abort = c.odom_delta_r_abort; p.rot_thr = c.dopt_rot_threshold; p.trans_thr = c.dopt_trans_threshold;
+    return p;
+}
+
+// builds the corner / surf grids of every resident scan (grid index = scan index)
+int vlo_build_scan_grids(vlo_handle *h)
+{
+    ScanBatchDev &sb = h->sb; const vlo_config &c = h->cfg;
+    GridSource sc;
+    sc.pts = sb.lsharp_pts; sc.pts_stride = (size_t)h->cap_lsharp; sc.ring_off = nullptr; sc.ring_off_stride = 0;
+    sc.ring_cnt = nullptr; sc.ring_cnt_stride = 0; sc.dense_start = nullptr; sc.dense_start_stride = 0;
+    sc.n_dense = sb.counts; sc.n_dense_stride = 8; sc.n_dense_field = 2; sc.n_rings = c.n_rings; sc.grid_scan = nullptr;
+    int rc = vlo_grid_build(h, h->gs_corner, sc, sb.n_scans, h->cap_lsharp); if (rc) return rc;
+    GridSource ss;
+    ss.pts = sb.lflat_slotted; ss.pts_stride = (size_t)c.max_points; ss.ring_off = sb.ring_start; ss.ring_off_stride = VLO_MAX_RINGS + 1;
+    ss.ring_cnt = sb.lflat_cnt; ss.ring_cnt_stride = c.n_rings; ss.dense_start = sb.lflat_ring_start; ss.dense_start_stride = VLO_MAX_RINGS + 1;
+    ss.n_dense = nullptr; ss.n_dense_stride = 0; ss.n_dense_field = 0; ss.n_rings = c.n_rings; ss.grid_scan = nullptr;
+    rc = vlo_grid_build(h, h->gs_surf, ss, sb.n_scans, c.max_points); if (rc) return rc;
+    h->grids_valid = 1;
+    return VLO_OK;
+}
+
+int vlo_launch_register_pairs(vlo_handle *h, int n_pairs, const float *d_seeds, const float *d_last_T)
+{
+    OdomParams p = make_params(h);
+    const vlo_config &c = h->cfg;
+    k3_init_pairs<<<(n_pairs + 127) / 128, 128, 0, h->stream>>>(p, d_seeds, n_pairs);
+    h->launches += 1;
+    if (d_last_T) {
+        dim3 g0((h->cap_lsharp + 255) / 256, n_pairs), g1((c.max_points + 255) / 256, n_pairs);
+        k3_to_end<<<g0, 256, 0, h->stream>>>(p, h->pair_last, d_last_T, n_pairs, 0);
+        k3_to_end<<<g1, 256, 0, h->stream>>>(p, h->pair_last, d_last_T, n_pairs, 1);
+        h->launches += 2;
+        h->grids_valid = 0;
+    }
+    if (!h->grids_valid) { int rc = vlo_build_scan_grids(h); if (rc) return rc; }
+    int n_warps = h->cap_sharp + h->cap_flat;
+    dim3 ga((n_warps * 32 + 255) / 256, n_pairs);
+    size_t trace_stride = (size_t)n_pairs * (h->cap_sharp * 2 + h->cap_flat * 3);
+    for (int base = 0, round = 0; base < c.odom_max_iterations; base += 5, round++) {
+        k3_assoc<<<ga, 256, 0, h->stream>>>(p, n_pairs);
+        if (h->trace && round < 5) {
+            int *dst = h->pair_trace + (size_t)round * trace_stride;
+            VLO_CUDA(cudaMemcpyAsync(dst, h->pair_cidx, sizeof(int) * (size_t)n_pairs * h->cap_sharp * 2, cudaMemcpyDeviceToDevice, h->stream));
+            VLO_CUDA(cudaMemcpyAsync(dst + (size_t)n_pairs * h->cap_sharp * 2, h->pair_sidx, sizeof(int) * (size_t)n_pairs * h->cap_flat * 3, cudaMemcpyDeviceToDevice, h->stream));
+        }
+        k3_gn<<<n_pairs, GN_THREADS, 0, h->stream>>>(p, base, 5);
+        h->launches += 2;
+    }
+    VLO_CUDA(cudaGetLastError());
+    return VLO_OK;
+}

@@ -51,18 +51,21 @@ static int ensure_pinned(vlo_handle *h, size_t bytes)
     return VLO_OK;
 }
 
-static int alloc_grid(vlo_handle *h, VoxelGridDev &g, int max_pts, float cell)
+static int alloc_gridset(vlo_handle *h, GridSet &g, int n_grids, int max_pts, float cell)
 {
-    int ts = 256; while (ts < 2 * max_pts) ts <<= 1;
-    g.cell = cell; g.inv_cell = 1.0f / cell; g.table_size = ts; g.n_points = 0;
-    HALLOC(g.keys, (size_t)ts); HALLOC(g.cell_start, (size_t)ts); HALLOC(g.cell_count, (size_t)ts);
-    HALLOC(g.cell_cursor, (size_t)ts); HALLOC(g.sorted_pts, (size_t)max_pts);
+    int ts = 1024; while (ts < max_pts) ts <<= 1;
+    g.cell = cell; g.inv_cell = 1.0f / cell; g.ts = ts; g.max_pts = max_pts; g.G = n_grids;
+    cudaError_t e;
+    if ((e = dalloc(&g.keys, (size_t)n_grids * ts)) != cudaSuccess || (e = dalloc(&g.cnt, (size_t)n_grids * ts)) != cudaSuccess ||
+        (e = dalloc(&g.start, (size_t)n_grids * (ts + 1))) != cudaSuccess || (e = dalloc(&g.sorted, (size_t)n_grids * max_pts)) != cudaSuccess) {
+        h->err = std::string("cudaMalloc grid: ") + cudaGetErrorString(e); return VLO_ERR_CUDA;
+    }
     return VLO_OK;
 }
 
-static void free_grid(VoxelGridDev &g)
+static void free_gridset(GridSet &g)
 {
-    cudaFree(g.keys); cudaFree(g.cell_start); cudaFree(g.cell_count); cudaFree(g.cell_cursor); cudaFree(g.sorted_pts);
+    cudaFree(g.keys); cudaFree(g.cnt); cudaFree(g.start); cudaFree(g.sorted);
     memset(&g, 0, sizeof(g));
 }
 
@@ -83,10 +86,11 @@ extern "C" int vlo_create(const vlo_config *cfg, vlo_handle **out)
     vlo_handle *h = new vlo_handle();
     h->cfg = c; h->launches = 0; h->pinned = nullptr; h->pinned_bytes = 0;
     memset(&h->sb, 0, sizeof(h->sb));
-    h->d_grid_corner = h->d_grid_surf = nullptr; h->d_map_grid = nullptr;
-    memset(h->map_grid, 0, sizeof(h->map_grid)); h->map_pts[0] = h->map_pts[1] = nullptr; h->map_n[0] = h->map_n[1] = 0;
+    memset(&h->gs_corner, 0, sizeof(GridSet)); memset(&h->gs_surf, 0, sizeof(GridSet)); memset(h->gs_map, 0, sizeof(h->gs_map));
+    h->map_pts[0] = h->map_pts[1] = nullptr; h->map_n = nullptr; h->map_n_host[0] = h->map_n_host[1] = 0;
+    h->grids_valid = 0; h->trace = 0; h->pair_last_T = nullptr;
     h->status_word = nullptr; h->pair_T = h->pair_seed = nullptr; h->pair_last = h->pair_cur = h->pair_state = nullptr;
-    h->pair_cidx = h->pair_sidx = h->pair_trace = nullptr; h->pair_result = nullptr; h->tgt_corner = h->tgt_surf = nullptr;
+    h->pair_cidx = h->pair_sidx = h->pair_trace = nullptr; h->pair_result = nullptr;
     h->map_partials = nullptr; h->map_idx5 = nullptr;
     h->online_have_last = 0; h->online_slot = 0;
     memset(h->online_T, 0, sizeof(h->online_T)); memset(h->online_sum, 0, sizeof(h->online_sum));
@@ -112,7 +116,6 @@ extern "C" int vlo_create(const vlo_config *cfg, vlo_handle **out)
     HALLOC(sb.counts, (size_t)B * 8);
     HALLOC(sb.sharp_idx, (size_t)B * h->cap_sharp); HALLOC(sb.lsharp_idx, (size_t)B * h->cap_lsharp); HALLOC(sb.flat_idx, (size_t)B * h->cap_flat);
     HALLOC(sb.sharp_pts, (size_t)B * h->cap_sharp); HALLOC(sb.lsharp_pts, (size_t)B * h->cap_lsharp); HALLOC(sb.flat_pts, (size_t)B * h->cap_flat);
-    HALLOC(sb.lflat_pts, (size_t)B * N);
     HALLOC(sb.lsharp_ring_start, (size_t)B * (VLO_MAX_RINGS + 1)); HALLOC(sb.lflat_ring_start, (size_t)B * (VLO_MAX_RINGS + 1));
     cudaMemset(sb.counts, 0, (size_t)B * 8 * sizeof(int));
     // registration workspace: at most one pair per resident scan
@@ -122,24 +125,16 @@ extern "C" int vlo_create(const vlo_config *cfg, vlo_handle **out)
     HALLOC(h->pair_cidx, (size_t)B * h->cap_sharp * 2); HALLOC(h->pair_sidx, (size_t)B * h->cap_flat * 3);
     HALLOC(h->pair_trace, (size_t)B * 5 * (h->cap_sharp * 2 + h->cap_flat * 3));
     HALLOC(h->pair_result, (size_t)B);
-    HALLOC(h->tgt_corner, (size_t)B * h->cap_lsharp); HALLOC(h->tgt_surf, (size_t)B * N);
-    h->grid_corner.resize(B); h->grid_surf.resize(B);
-    for (int b = 0; b < B; b++) {
-        memset(&h->grid_corner[b], 0, sizeof(VoxelGridDev)); memset(&h->grid_surf[b], 0, sizeof(VoxelGridDev));
-    }
-    for (int b = 0; b < B; b++) {
-        int rc = alloc_grid(h, h->grid_corner[b], h->cap_lsharp, c.odom_cell_size); if (rc) return rc;
-        rc = alloc_grid(h, h->grid_surf[b], N, c.odom_cell_size); if (rc) return rc;
-    }
-    HALLOC(h->d_grid_corner, (size_t)B); HALLOC(h->d_grid_surf, (size_t)B);
-    cudaMemcpy(h->d_grid_corner, h->grid_corner.data(), sizeof(VoxelGridDev) * B, cudaMemcpyHostToDevice);
-    cudaMemcpy(h->d_grid_surf, h->grid_surf.data(), sizeof(VoxelGridDev) * B, cudaMemcpyHostToDevice);
+    HALLOC(h->pair_last_T, (size_t)B * 6);
+    { int rc = alloc_gridset(h, h->gs_corner, B, h->cap_lsharp, c.odom_cell_size); if (rc) { vlo_destroy(h); return rc; } }
+    { int rc = alloc_gridset(h, h->gs_surf, B, N, c.odom_cell_size); if (rc) { vlo_destroy(h); return rc; } }
+    HALLOC(h->map_n, 8);
+    cudaMemset(h->map_n, 0, 8 * sizeof(int));
     if (c.max_map_points > 0) {
         for (int w = 0; w < 2; w++) {
             HALLOC(h->map_pts[w], (size_t)c.max_map_points);
-            int rc = alloc_grid(h, h->map_grid[w], c.max_map_points, c.map_cell_size); if (rc) return rc;
+            int rc = alloc_gridset(h, h->gs_map[w], 1, c.max_map_points, c.map_cell_size); if (rc) { vlo_destroy(h); return rc; }
         }
-        HALLOC(h->d_map_grid, 2);
         int qcap = h->cap_lsharp + N;
         HALLOC(h->map_partials, (size_t)B * ((qcap + 31) / 32 + 2) * VLO_NTERM);
         HALLOC(h->map_idx5, (size_t)B * qcap * 5);
@@ -158,13 +153,11 @@ extern "C" void vlo_destroy(vlo_handle *h)
     void *ptrs[] = { sb.raw_owned, sb.raw_offset, sb.first_half, sb.ori_bounds, sb.tile_hist, sb.cloud, sb.ring_start, sb.src_index,
                      sb.label, sb.curvature, sb.picked, sb.slot_sharp, sb.slot_lsharp, sb.slot_flat, sb.slot_cnt, sb.lflat_slotted,
                      sb.lflat_cnt, sb.counts, sb.sharp_idx, sb.lsharp_idx, sb.flat_idx, sb.sharp_pts, sb.lsharp_pts, sb.flat_pts,
-                     sb.lflat_pts, sb.lsharp_ring_start, sb.lflat_ring_start, h->status_word, h->pair_T, h->pair_seed, h->pair_last,
-                     h->pair_cur, h->pair_state, h->pair_cidx, h->pair_sidx, h->pair_trace, h->pair_result, h->tgt_corner, h->tgt_surf,
-                     h->d_grid_corner, h->d_grid_surf, h->d_map_grid, h->map_pts[0], h->map_pts[1], h->map_partials, h->map_idx5 };
+                     sb.lsharp_ring_start, sb.lflat_ring_start, h->status_word, h->pair_T, h->pair_seed, h->pair_last,
+                     h->pair_cur, h->pair_state, h->pair_cidx, h->pair_sidx, h->pair_trace, h->pair_result, h->pair_last_T, h->map_n,
+                     h->map_pts[0], h->map_pts[1], h->map_partials, h->map_idx5 };
     for (void *p : ptrs) if (p) cudaFree(p);
-    for (auto &g : h->grid_corner) free_grid(g);
-    for (auto &g : h->grid_surf) free_grid(g);
-    free_grid(h->map_grid[0]); free_grid(h->map_grid[1]);
+    free_gridset(h->gs_corner); free_gridset(h->gs_surf); free_gridset(h->gs_map[0]); free_gridset(h->gs_map[1]);
     if (h->pinned) cudaFreeHost(h->pinned);
     cudaStreamDestroy(h->stream);
     delete h;
@@ -225,6 +218,7 @@ extern "C" int vlo_scans_extract(vlo_handle *h)
     if (!h) return VLO_ERR_INVALID_ARG;
     if (h->sb.n_scans < 1) { h->err = "no scans uploaded"; return VLO_ERR_STATE; }
     cudaSetDevice(h->cfg.device);
+    h->grids_valid = 0;
     return vlo_launch_extract(h);
 }
 
@@ -283,5 +277,58 @@ extern "C" int vlo_scan_get_features(vlo_handle *h, int scan, int8_t *label, flo
             o += (size_t)lc[r];
         }
     }
+    return VLO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scan-to-scan
+extern "C" int vlo_set_trace(vlo_handle *h, int enable) { if (!h) return VLO_ERR_INVALID_ARG; h->trace = enable ? 1 : 0; return VLO_OK; }
+
+extern "C" int vlo_register_pairs(vlo_handle *h, const int *last, const int *cur, int n_pairs,
+                                  const float *seeds, const float *last_transforms, vlo_result *out)
+{
+    if (!h || !last || !cur || !out || n_pairs < 1) return VLO_ERR_INVALID_ARG;
+    if (n_pairs > h->max_pairs) { h->err = "n_pairs exceeds max_scans"; return VLO_ERR_CAPACITY; }
+    for (int p = 0; p < n_pairs; p++)
+        if (last[p] < 0 || last[p] >= h->sb.n_scans || cur[p] < 0 || cur[p] >= h->sb.n_scans) { h->err = "pair index outside the resident batch"; return VLO_ERR_INVALID_ARG; }
+    cudaSetDevice(h->cfg.device);
+    size_t need = sizeof(int) * 2 * (size_t)n_pairs + sizeof(float) * 12 * (size_t)n_pairs + sizeof(vlo_result) * (size_t)n_pairs;
+    int rc = ensure_pinned(h, need); if (rc) return rc;
+    char *pp = (char *)h->pinned;
+    vlo_result *pres = (vlo_result *)pp; pp += sizeof(vlo_result) * (size_t)n_pairs;
+    int *pl = (int *)pp; pp += sizeof(int) * (size_t)n_pairs;
+    int *pc = (int *)pp; pp += sizeof(int) * (size_t)n_pairs;
+    float *ps = (float *)pp; pp += sizeof(float) * 6 * (size_t)n_pairs;
+    float *pt = (float *)pp;
+    memcpy(pl, last, sizeof(int) * (size_t)n_pairs); memcpy(pc, cur, sizeof(int) * (size_t)n_pairs);
+    VLO_CUDA(cudaMemcpyAsync(h->pair_last, pl, sizeof(int) * (size_t)n_pairs, cudaMemcpyHostToDevice, h->stream));
+    VLO_CUDA(cudaMemcpyAsync(h->pair_cur, pc, sizeof(int) * (size_t)n_pairs, cudaMemcpyHostToDevice, h->stream));
+    if (seeds) { memcpy(ps, seeds, sizeof(float) * 6 * (size_t)n_pairs);
+        VLO_CUDA(cudaMemcpyAsync(h->pair_seed, ps, sizeof(float) * 6 * (size_t)n_pairs, cudaMemcpyHostToDevice, h->stream)); }
+    if (last_transforms) { memcpy(pt, last_transforms, sizeof(float) * 6 * (size_t)n_pairs);
+        VLO_CUDA(cudaMemcpyAsync(h->pair_last_T, pt, sizeof(float) * 6 * (size_t)n_pairs, cudaMemcpyHostToDevice, h->stream)); }
+    rc = vlo_launch_register_pairs(h, n_pairs, seeds ? h->pair_seed : nullptr, last_transforms ? h->pair_last_T : nullptr);
+    if (rc) return rc;
+    VLO_CUDA(cudaMemcpyAsync(pres, h->pair_result, sizeof(vlo_result) * (size_t)n_pairs, cudaMemcpyDeviceToHost, h->stream));
+    rc = vlo_synchronize(h); if (rc) return rc;
+    memcpy(out, pres, sizeof(vlo_result) * (size_t)n_pairs);
+    h->last_n_pairs = n_pairs;
+    int soft = VLO_OK;
+    for (int p = 0; p < n_pairs; p++) if (out[p].status == VLO_SOFT_TOO_FEW_CORR) soft = VLO_SOFT_TOO_FEW_CORR;
+    return soft;
+}
+
+extern "C" int vlo_pair_get_correspondences(vlo_handle *h, int pair, int round, int *corner_idx, int *surf_idx)
+{
+    if (!h || pair < 0 || pair >= h->last_n_pairs || round < 0 || round >= 5) return VLO_ERR_INVALID_ARG;
+    if (!h->trace) { h->err = "enable tracing with vlo_set_trace before registering"; return VLO_ERR_STATE; }
+    int rc = vlo_synchronize(h); if (rc) return rc;
+    int P = h->last_n_pairs;
+    size_t trace_stride = (size_t)P * (h->cap_sharp * 2 + h->cap_flat * 3);
+    const int *base = h->pair_trace + (size_t)round * trace_stride;
+    int cur; VLO_CUDA(cudaMemcpy(&cur, h->pair_cur + pair, sizeof(int), cudaMemcpyDeviceToHost));
+    int cnt[8]; VLO_CUDA(cudaMemcpy(cnt, h->sb.counts + cur * 8, sizeof(cnt), cudaMemcpyDeviceToHost));
+    if (corner_idx && cnt[1] > 0) VLO_CUDA(cudaMemcpy(corner_idx, base + (size_t)pair * h->cap_sharp * 2, sizeof(int) * 2 * (size_t)cnt[1], cudaMemcpyDeviceToHost));
+    if (surf_idx && cnt[3] > 0) VLO_CUDA(cudaMemcpy(surf_idx, base + (size_t)P * h->cap_sharp * 2 + (size_t)pair * h->cap_flat * 3, sizeof(int) * 3 * (size_t)cnt[3], cudaMemcpyDeviceToHost));
     return VLO_OK;
 }

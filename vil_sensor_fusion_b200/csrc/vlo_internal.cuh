@@ -11,15 +11,29 @@
 #define VLO_NTERM 28          // 21 upper-tri AtA + 6 AtB + sum of squared weighted residuals
 #define VLO_PI_D 3.14159265358979323846
 
-struct VoxelGridDev {         // one voxel-hash grid over one target cloud
+// One set of voxel-hash grids (see grid.cuh for the layout contract)
+struct GridSet {
     float cell, inv_cell;
-    int   table_size;         // power of two
-    unsigned long long *keys; // packed cell coords, ~0ull = empty
-    int  *cell_start;         // into sorted_pts
-    int  *cell_count;
-    int  *cell_cursor;
-    float4 *sorted_pts;       // xyz + original index bits in w
-    int   n_points;
+    int ts;              // table size per grid (power of two)
+    int max_pts;
+    int G;
+    unsigned long long *keys;
+    int *cnt;
+    int *start;
+    float4 *sorted;
+};
+
+// where a grid build reads its points from: ring-slotted clouds (ring r's live points at
+// [ring_off[r], +ring_cnt[r]) of a per-scan base array; dense index = dense_start[r] + offset) or
+// plain dense arrays (ring taken from int(intensity)).
+struct GridSource {
+    const float4 *pts; size_t pts_stride;
+    const int *ring_off; int ring_off_stride;
+    const int *ring_cnt; int ring_cnt_stride;
+    const int *dense_start; int dense_start_stride;
+    const int *n_dense; int n_dense_stride; int n_dense_field;
+    int n_rings;
+    const int *grid_scan;                        // optional: grid g reads scan grid_scan[g]
 };
 
 // Device-resident state of a batch of scans (capacities from vlo_config)
@@ -73,14 +87,14 @@ struct vlo_handle {
     int   *pair_sidx;          // [P][cap_flat][3]
     int   *pair_trace;         // first-association copy for parity tests (5 rounds)
     vlo_result *pair_result;   // device results [P]
-    float4 *tgt_corner, *tgt_surf;   // [B][cap] last clouds moved to sweep end (online) or aliases
-    // grids for scan-to-scan targets (one per scan) and the map
-    std::vector<VoxelGridDev> grid_corner, grid_surf;   // host copies of device descriptors
-    VoxelGridDev *d_grid_corner, *d_grid_surf;          // device arrays [B]
-    VoxelGridDev map_grid[2];
-    VoxelGridDev *d_map_grid;
+    float *pair_last_T;        // [P][6] staging of last_transforms
+    int grids_valid, trace, last_n_pairs;
+    // grids for scan-to-scan targets (grid index = scan index) and the map (0 corner, 1 surf)
+    GridSet gs_corner, gs_surf;
+    GridSet gs_map[2];
     float4 *map_pts[2];
-    int map_n[2];
+    int *map_n;                // device [8]: [2] = n_corner, [4] = n_surf (same layout as counts rows)
+    int map_n_host[2];
     // mapping workspace
     float *map_partials;       // [n][blocks][28]
     int   *map_idx5;           // [n][Q][5]
@@ -184,12 +198,10 @@ __device__ __forceinline__ float4 vlo_to_start(const float *T, float4 p, int des
 // kernels' host launchers -----------------------------------------------------------------------
 int vlo_launch_organise(vlo_handle *h);
 int vlo_launch_extract(vlo_handle *h);
-int vlo_launch_grid_build(vlo_handle *h, VoxelGridDev *d_grids, const std::vector<VoxelGridDev> &grids,
-                          const float4 *pts_base, size_t pts_stride, const int *counts_base, int counts_stride,
-                          int counts_field, int n_grids, int max_pts);
-int vlo_launch_register_pairs(vlo_handle *h, int n_pairs, int have_last_T, const float *d_last_T);
+int vlo_grid_build(vlo_handle *h, const GridSet &gs, const GridSource &src, int n_grids, int n_slots);
+int vlo_grid_knn(vlo_handle *h, const GridSet &gs, int g, const float4 *d_q, int nq, int k, float dmax, int *d_idx, float *d_d2);
+int vlo_build_scan_grids(vlo_handle *h);
+int vlo_launch_register_pairs(vlo_handle *h, int n_pairs, const float *d_seeds, const float *d_last_T);
+int vlo_launch_register_map(vlo_handle *h, const int *d_scans, int n, const float *d_seeds);
 int vlo_launch_imu(vlo_handle *h, const double *d_t, const double *d_acc, const double *d_gyro, int n_samples,
                    const double *d_t0, const double *d_t1, const double *d_bias, int n_factors, vlo_preint *d_out);
-int vlo_map_build_impl(vlo_handle *h, int which, const float *pts, int n, int on_device);
-int vlo_launch_register_map(vlo_handle *h, const int *d_scans, int n, int max_q);
-int vlo_launch_map_knn(vlo_handle *h, int which, const float4 *d_q, int nq, int k, int *d_idx, float *d_d2);

@@ -1,8 +1,6 @@
 // temporary: entry points not implemented yet
 #include "vlo_internal.cuh"
 #define NOTIMPL(h) do { if (h) (h)->err = "not implemented"; return VLO_ERR_STATE; } while (0)
-extern "C" int vlo_register_pairs(vlo_handle *h, const int *, const int *, int, const float *, const float *, vlo_result *) { NOTIMPL(h); }
-extern "C" int vlo_pair_get_correspondences(vlo_handle *h, int, int, int *, int *) { NOTIMPL(h); }
 extern "C" int vlo_map_build(vlo_handle *h, const float *, int, const float *, int, int) { NOTIMPL(h); }
 extern "C" int vlo_register_map(vlo_handle *h, const int *, int, const float *, vlo_result *) { NOTIMPL(h); }
 extern "C" int vlo_map_get_correspondences(vlo_handle *h, int, int *, int *) { NOTIMPL(h); }
