@@ -158,14 +158,19 @@ int vlo_map_build(vlo_handle *h, const float *corner_xyzi, int n_corner, const f
 /* registers the corner (less sharp) / surface (less flat) features of resident scans [0,n) against the map */
 int vlo_register_map(vlo_handle *h, const int *scans, int n, const float *seeds /* n*6 transformTobeMapped */, vlo_result *out);
 int vlo_map_get_correspondences(vlo_handle *h, int slot, int *corner_idx5, int *surf_idx5);
-/* exact k-NN service on the map grids (k <= 8): which = 0 corner, 1 surf; queries host xyzi */
-int vlo_map_knn(vlo_handle *h, int which, const float *queries_xyzi, int nq, int k, int *idx, float *d2);
+/* exact k-NN service on the map grids (k = 1 or 5, neighbours with d2 < max_d2): which = 0 corner, 1 surf;
+ * queries host xyzi; missing neighbours are idx -1 / d2 +inf */
+int vlo_map_knn(vlo_handle *h, int which, const float *queries_xyzi, int nq, int k, float max_d2, int *idx, float *d2);
 
 /* ---------------------------------------------------------------- online tick */
 /* One LOAM tick: organise + extract + scan-to-scan against the previous tick (seeded with the
  * previous transform) [+ scan-to-map when a map is resident]; `odom` / `mapped` may be NULL. */
 int vlo_process_scan(vlo_handle *h, const float *raw, int n_points, int stride_floats, double stamp,
                      vlo_result *odom, vlo_result *mapped);
+int vlo_online_reset(vlo_handle *h);
+/* accumulated odometry pose (transformSum) and last mapped pose (transformAftMapped), LOAM order/axes */
+int vlo_online_pose(vlo_handle *h, float *sum6, float *mapped6);
+int vlo_online_set_map_pose(vlo_handle *h, const float *pose6);
 
 /* ---------------------------------------------------------------- IMU */
 /* Batched IMUManager::getFactor over one time-sorted sample stream (host pointers):

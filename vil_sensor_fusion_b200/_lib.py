@@ -73,7 +73,10 @@ SYMBOLS = {
     "vlo_map_build": (C.c_int, [_VP, _VP, C.c_int, _VP, C.c_int, C.c_int]),
     "vlo_register_map": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP]),
     "vlo_map_get_correspondences": (C.c_int, [_VP, C.c_int, _VP, _VP]),
-    "vlo_map_knn": (C.c_int, [_VP, C.c_int, _VP, C.c_int, C.c_int, _VP, _VP]),
+    "vlo_map_knn": (C.c_int, [_VP, C.c_int, _VP, C.c_int, C.c_int, C.c_float, _VP, _VP]),
+    "vlo_online_reset": (C.c_int, [_VP]),
+    "vlo_online_pose": (C.c_int, [_VP, _VP, _VP]),
+    "vlo_online_set_map_pose": (C.c_int, [_VP, _VP]),
     "vlo_process_scan": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_double, C.POINTER(Result), C.POINTER(Result)]),
     "vlo_imu_preintegrate_batch": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, _VP, _VP, _VP, C.c_int, _VP]),
     "vlo_pose_diff": (None, [_VP, _VP, _VP]),

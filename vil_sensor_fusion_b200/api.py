@@ -192,12 +192,21 @@ class Handle:
         self._check(self.lib.vlo_map_get_correspondences(self._h, slot, _ptr(ci), _ptr(si)))
         return ci[:n_corner], si[:n_surf]
 
-    def map_knn(self, which: int, queries, k: int):
+    def map_knn(self, which: int, queries, k: int, max_d2: float = 25.0):
         q = np.ascontiguousarray(queries, np.float32)
         idx = np.zeros((q.shape[0], k), np.int32)
         d2 = np.zeros((q.shape[0], k), np.float32)
-        self._check(self.lib.vlo_map_knn(self._h, which, _ptr(q), q.shape[0], k, _ptr(idx), _ptr(d2)))
+        self._check(self.lib.vlo_map_knn(self._h, which, _ptr(q), q.shape[0], k, max_d2, _ptr(idx), _ptr(d2)))
         return idx, d2
+
+    def online_pose(self):
+        s = np.zeros(6, np.float32)
+        m = np.zeros(6, np.float32)
+        self._check(self.lib.vlo_online_pose(self._h, _ptr(s), _ptr(m)))
+        return s, m
+
+    def online_set_map_pose(self, pose6):
+        self._check(self.lib.vlo_online_set_map_pose(self._h, _ptr(np.ascontiguousarray(pose6, np.float32))))
 
     # ---- online
     def process_scan(self, raw: np.ndarray, stamp: float = 0.0, want_map: bool = False):

@@ -9,7 +9,7 @@
 #define K0_TILE 256
 
 struct K0Params {
-    const float *raw; const int *raw_offset; int stride;
+    const float *raw; const int *raw_offset; int stride; int scan_first;   // raw_offset: [b] = {begin, count}
     int n_rings; float lower_deg, factor, scan_period;
     int N;            // capacity per scan
     int tiles;        // tiles per scan (capacity)
@@ -31,7 +31,8 @@ __global__ void k0_bounds(K0Params p, float *ori_bounds, int *first_half, int n_
 {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_scans) return;
-    int o0 = p.raw_offset[b], o1 = p.raw_offset[b + 1];
+    b += p.scan_first;
+    int o0 = p.raw_offset[2 * b], o1 = o0 + p.raw_offset[2 * b + 1];
     first_half[b] = 0x7fffffff;
     if (o1 <= o0) { ori_bounds[2 * b] = 0.f; ori_bounds[2 * b + 1] = 0.f; return; }
     const float *f = p.raw + (size_t)o0 * p.stride, *l = p.raw + (size_t)(o1 - 1) * p.stride;
@@ -47,8 +48,8 @@ __global__ void __launch_bounds__(K0_TILE) k0_classify(K0Params p, const float *
 {
     __shared__ int hist[VLO_MAX_RINGS];
     __shared__ int s_first;
-    int b = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
-    int o0 = p.raw_offset[b], n = p.raw_offset[b + 1] - o0;
+    int b = p.scan_first + blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+    int o0 = p.raw_offset[2 * b], n = p.raw_offset[2 * b + 1];
     if (tile * K0_TILE >= n) {   // still must zero the histogram column for the scan kernel
         if (tid < p.n_rings) tile_hist[((size_t)b * p.n_rings + tid) * p.tiles + tile] = 0;
         return;
@@ -79,8 +80,8 @@ __global__ void __launch_bounds__(K0_TILE) k0_classify(K0Params p, const float *
 __global__ void __launch_bounds__(256) k0_scan(K0Params p, int *tile_hist, int *ring_start, int *counts)
 {
     __shared__ int ring_total[VLO_MAX_RINGS];
-    int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    int n = p.raw_offset[b + 1] - p.raw_offset[b];
+    int b = p.scan_first + blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    int n = p.raw_offset[2 * b + 1];
     int tiles = (n + K0_TILE - 1) / K0_TILE;
     for (int r = warp; r < p.n_rings; r += nw) {
         int *row = tile_hist + ((size_t)b * p.n_rings + r) * p.tiles;
@@ -111,8 +112,8 @@ __global__ void __launch_bounds__(K0_TILE) k0_scatter(K0Params p, const float *o
                                                        float4 *cloud, int *src_index)
 {
     __shared__ int warp_cnt[K0_TILE / 32][VLO_MAX_RINGS];
-    int b = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    int o0 = p.raw_offset[b], n = p.raw_offset[b + 1] - o0;
+    int b = p.scan_first + blockIdx.y, tile = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int o0 = p.raw_offset[2 * b], n = p.raw_offset[2 * b + 1];
     if (tile * K0_TILE >= n) return;
     for (int k = tid; k < (K0_TILE / 32) * VLO_MAX_RINGS; k += K0_TILE) (&warp_cnt[0][0])[k] = 0;
     __syncthreads();
@@ -159,7 +160,7 @@ int vlo_launch_organise(vlo_handle *h)
     p.n_rings = h->cfg.n_rings; p.lower_deg = h->cfg.lower_deg;
     p.factor = (float)(h->cfg.n_rings - 1) / (h->cfg.upper_deg - h->cfg.lower_deg);
     p.scan_period = h->cfg.scan_period; p.N = h->cfg.max_points; p.tiles = h->tiles_per_scan;
-    int B = sb.n_scans;
+    int B = sb.scan_count; p.scan_first = sb.scan_first;
     k0_bounds<<<(B + 127) / 128, 128, 0, h->stream>>>(p, sb.ori_bounds, sb.first_half, B);
     dim3 grid(h->tiles_per_scan, B);
     k0_classify<<<grid, K0_TILE, 0, h->stream>>>(p, sb.ori_bounds, sb.first_half, sb.tile_hist);

@@ -19,7 +19,7 @@
 struct K1Params {
     const float4 *cloud; const int *ring_start; int N; int n_rings;
     int K, NR, max_sharp, max_lsharp, max_flat; float thr; float leaf;
-    int MR, HT;
+    int MR, HT; int scan_first;
     int8_t *label; float *curvature; uint8_t *picked;
     int *slot_sharp, *slot_lsharp, *slot_flat; uint8_t *slot_cnt;
     float4 *lflat_slotted; int *lflat_cnt;
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_extract(K1Params p)
     __shared__ int s_sp[VLO_MAX_REGIONS], s_ep[VLO_MAX_REGIONS];
     __shared__ int s_warp_scan[K1_THREADS / 32];
     __shared__ int s_seq;
-    const int r = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r = blockIdx.x, b = p.scan_first + blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int start = p.ring_start[b * (VLO_MAX_RINGS + 1) + r];
     const int n = p.ring_start[b * (VLO_MAX_RINGS + 1) + r + 1] - start;
     const int K = p.K, NR = p.NR;
@@ -358,7 +358,7 @@ struct K1bParams {
     const float4 *cloud; int N; int n_rings, NR, max_sharp, max_lsharp, max_flat;
     const int *slot_sharp, *slot_lsharp, *slot_flat; const uint8_t *slot_cnt; const int *lflat_cnt;
     int *counts; int *sharp_idx, *lsharp_idx, *flat_idx; float4 *sharp_pts, *lsharp_pts, *flat_pts;
-    int cap_sharp, cap_lsharp, cap_flat;
+    int cap_sharp, cap_lsharp, cap_flat; int scan_first;
     int *lsharp_ring_start, *lflat_ring_start;
 };
 
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(256) k1b_compact(K1bParams p)
     __shared__ int off_sharp[VLO_MAX_RINGS * VLO_MAX_REGIONS + 1];
     __shared__ int off_ls[VLO_MAX_RINGS * VLO_MAX_REGIONS + 1];
     __shared__ int off_flat[VLO_MAX_RINGS * VLO_MAX_REGIONS + 1];
-    const int b = blockIdx.x, tid = threadIdx.x;
+    const int b = p.scan_first + blockIdx.x, tid = threadIdx.x;
     const int nsec = p.n_rings * p.NR;
     if (tid == 0) {
         int a = 0, l = 0, f = 0;
@@ -435,7 +435,8 @@ int vlo_launch_extract(vlo_handle *h)
         VLO_CUDA(cudaFuncSetAttribute(k1_extract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    dim3 grid(c.n_rings, sb.n_scans);
+    p.scan_first = sb.scan_first;
+    dim3 grid(c.n_rings, sb.scan_count);
     k1_extract<<<grid, K1_THREADS, smem, h->stream>>>(p);
     K1bParams q;
     q.cloud = sb.cloud; q.N = c.max_points; q.n_rings = c.n_rings; q.NR = c.feature_regions;
@@ -446,7 +447,8 @@ int vlo_launch_extract(vlo_handle *h)
     q.sharp_pts = sb.sharp_pts; q.lsharp_pts = sb.lsharp_pts; q.flat_pts = sb.flat_pts;
     q.cap_sharp = h->cap_sharp; q.cap_lsharp = h->cap_lsharp; q.cap_flat = h->cap_flat;
     q.lsharp_ring_start = sb.lsharp_ring_start; q.lflat_ring_start = sb.lflat_ring_start;
-    k1b_compact<<<sb.n_scans, 256, 0, h->stream>>>(q);
+    q.scan_first = sb.scan_first;
+    k1b_compact<<<sb.scan_count, 256, 0, h->stream>>>(q);
     h->launches += 2;
     VLO_CUDA(cudaGetLastError());
     return VLO_OK;

@@ -24,9 +24,9 @@ __device__ __forceinline__ bool grid_src_point(const GridSource &src, int g, int
     return true;
 }
 
-__global__ void __launch_bounds__(256) k2_count(GridSet gs, GridSource src, int n_slots)
+__global__ void __launch_bounds__(256) k2_count(GridSet gs, GridSource src, int n_slots, int g_first)
 {
-    int g = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    int g = g_first + blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_slots) return;
     float4 p; unsigned tag;
     if (!grid_src_point(src, g, i, p, tag)) return;
@@ -42,11 +42,11 @@ __global__ void __launch_bounds__(256) k2_count(GridSet gs, GridSource src, int 
     atomicAdd(&gs.cnt[(size_t)g * gs.ts + slot], 1);
 }
 
-__global__ void __launch_bounds__(1024) k2_scan(GridSet gs)
+__global__ void __launch_bounds__(1024) k2_scan(GridSet gs, int g_first)
 {
     __shared__ int warp_sum[32];
     __shared__ int carry_s;
-    int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int g = g_first + blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int *cnt = gs.cnt + (size_t)g * gs.ts;
     int *start = gs.start + (size_t)g * (gs.ts + 1);
     if (tid == 0) carry_s = 0;
@@ -74,9 +74,9 @@ __global__ void __launch_bounds__(1024) k2_scan(GridSet gs)
     if (tid == 0) start[gs.ts] = carry_s;
 }
 
-__global__ void __launch_bounds__(256) k2_scatter(GridSet gs, GridSource src, int n_slots)
+__global__ void __launch_bounds__(256) k2_scatter(GridSet gs, GridSource src, int n_slots, int g_first)
 {
-    int g = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    int g = g_first + blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_slots) return;
     float4 p; unsigned tag;
     if (!grid_src_point(src, g, i, p, tag)) return;
@@ -86,15 +86,15 @@ __global__ void __launch_bounds__(256) k2_scatter(GridSet gs, GridSource src, in
     gs.sorted[(size_t)g * gs.max_pts + pos] = make_float4(p.x, p.y, p.z, __uint_as_float(tag));
 }
 
-int vlo_grid_build(vlo_handle *h, const GridSet &gs, const GridSource &src, int n_grids, int n_slots)
+int vlo_grid_build(vlo_handle *h, const GridSet &gs, const GridSource &src, int g_first, int n_grids, int n_slots)
 {
     if (n_grids <= 0) return VLO_OK;
-    VLO_CUDA(cudaMemsetAsync(gs.keys, 0xFF, sizeof(unsigned long long) * (size_t)n_grids * gs.ts, h->stream));
-    VLO_CUDA(cudaMemsetAsync(gs.cnt, 0, sizeof(int) * (size_t)n_grids * gs.ts, h->stream));
+    VLO_CUDA(cudaMemsetAsync(gs.keys + (size_t)g_first * gs.ts, 0xFF, sizeof(unsigned long long) * (size_t)n_grids * gs.ts, h->stream));
+    VLO_CUDA(cudaMemsetAsync(gs.cnt + (size_t)g_first * gs.ts, 0, sizeof(int) * (size_t)n_grids * gs.ts, h->stream));
     dim3 grid((n_slots + 255) / 256, n_grids);
-    k2_count<<<grid, 256, 0, h->stream>>>(gs, src, n_slots);
-    k2_scan<<<n_grids, 1024, 0, h->stream>>>(gs);
-    k2_scatter<<<grid, 256, 0, h->stream>>>(gs, src, n_slots);
+    k2_count<<<grid, 256, 0, h->stream>>>(gs, src, n_slots, g_first);
+    k2_scan<<<n_grids, 1024, 0, h->stream>>>(gs, g_first);
+    k2_scatter<<<grid, 256, 0, h->stream>>>(gs, src, n_slots, g_first);
     h->launches += 3;
     VLO_CUDA(cudaGetLastError());
     return VLO_OK;

@@ -376,25 +376,24 @@ static OdomParams make_params(vlo_handle *h)
     return p;
 }
 
-// builds the corner / surf grids of every resident scan (grid index = scan index)
-int vlo_build_scan_grids(vlo_handle *h)
+// builds the corner / surf grids of resident scans [first, first + count) (grid index = scan index)
+int vlo_build_scan_grids(vlo_handle *h, int first, int count)
 {
     ScanBatchDev &sb = h->sb; const vlo_config &c = h->cfg;
     GridSource sc;
     sc.pts = sb.lsharp_pts; sc.pts_stride = (size_t)h->cap_lsharp; sc.ring_off = nullptr; sc.ring_off_stride = 0;
     sc.ring_cnt = nullptr; sc.ring_cnt_stride = 0; sc.dense_start = nullptr; sc.dense_start_stride = 0;
     sc.n_dense = sb.counts; sc.n_dense_stride = 8; sc.n_dense_field = 2; sc.n_rings = c.n_rings; sc.grid_scan = nullptr;
-    int rc = vlo_grid_build(h, h->gs_corner, sc, sb.n_scans, h->cap_lsharp); if (rc) return rc;
+    int rc = vlo_grid_build(h, h->gs_corner, sc, first, count, h->cap_lsharp); if (rc) return rc;
     GridSource ss;
     ss.pts = sb.lflat_slotted; ss.pts_stride = (size_t)c.max_points; ss.ring_off = sb.ring_start; ss.ring_off_stride = VLO_MAX_RINGS + 1;
     ss.ring_cnt = sb.lflat_cnt; ss.ring_cnt_stride = c.n_rings; ss.dense_start = sb.lflat_ring_start; ss.dense_start_stride = VLO_MAX_RINGS + 1;
     ss.n_dense = nullptr; ss.n_dense_stride = 0; ss.n_dense_field = 0; ss.n_rings = c.n_rings; ss.grid_scan = nullptr;
-    rc = vlo_grid_build(h, h->gs_surf, ss, sb.n_scans, c.max_points); if (rc) return rc;
-    h->grids_valid = 1;
+    rc = vlo_grid_build(h, h->gs_surf, ss, first, count, c.max_points); if (rc) return rc;
     return VLO_OK;
 }
 
-int vlo_launch_register_pairs(vlo_handle *h, int n_pairs, const float *d_seeds, const float *d_last_T)
+int vlo_launch_register_pairs(vlo_handle *h, int n_pairs, const float *d_seeds, const float *d_last_T, int only_grid_scan)
 {
     OdomParams p = make_params(h);
     const vlo_config &c = h->cfg;
@@ -407,7 +406,8 @@ int vlo_launch_register_pairs(vlo_handle *h, int n_pairs, const float *d_seeds, 
         h->launches += 2;
         h->grids_valid = 0;
     }
-    if (!h->grids_valid) { int rc = vlo_build_scan_grids(h); if (rc) return rc; }
+    if (only_grid_scan >= 0) { int rc = vlo_build_scan_grids(h, only_grid_scan, 1); if (rc) return rc; h->grids_valid = 1; }
+    if (!h->grids_valid) { int rc = vlo_build_scan_grids(h, 0, h->sb.n_scans); if (rc) return rc; h->grids_valid = 1; }
     int n_warps = h->cap_sharp + h->cap_flat;
     dim3 ga((n_warps * 32 + 255) / 256, n_pairs);
     size_t trace_stride = (size_t)n_pairs * (h->cap_sharp * 2 + h->cap_flat * 3);

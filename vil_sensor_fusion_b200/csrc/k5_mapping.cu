@@ -1,0 +1,391 @@
+// K5  scan-to-map registration (LaserMapping) against a device-resident voxel-hash map.
+// Replaces BasicLaserMapping::optimizeTransformTobeMapped of the `loam` nodelet
+// (gtsam_fusion/launch/loam.launch:47-52; knobs loam_params.yaml:44-46,53); SURVEY.md Appendix A.8 is
+// the algorithm, oracle/laser_mapping.c the frozen operation order.  Per Gauss-Newton iteration:
+//   k5_knn   one warp per feature point: pointAssociateToMap + exact 5-NN (d2 < 1) on the map grid
+//   k5_lin   one thread per feature point: 3x3 covariance eigen (corner) / 5x3 least-squares plane
+//            (surface), residual, Jacobian row, 28 products; level-1 sums of the R1 reduction per
+//            32 consecutive points
+//   k5_solve one CTA per scan: levels 2/3 of R1 in fixed order, QR solve, (iteration 0) single-warp
+//            Jacobi degeneracy test + remapping, pose update, convergence flag, result record
+// All launches are enqueued back to back; converged scans skip work through a device flag.
+#include "grid.cuh"
+#include "dense6.cuh"
+
+struct MapParams {
+    const float4 *lsharp_pts; int cap_lsharp; const float4 *lflat_slotted; int N;
+    const int *ring_start, *lflat_ring_start, *counts; int n_rings;
+    const int *scans;            // [n] resident scan index per slot
+    float *T; int *state; vlo_result *result;     // per slot
+    int *idx5; int qcap;         // [n][qcap][5]
+    float *partials; int pcap;   // [n][pcap][28] level-1 sums
+    int *ncorr;                  // [n][2]
+    GridSet gm0, gm1; const float4 *map0, *map1; const int *map_n;
+    int max_iter; float degen_thr, dT_abort, dR_abort, rot_thr, trans_thr;
+};
+
+__device__ __forceinline__ float4 map_query_point(const MapParams &p, int scan, int i, int n_ls, bool &corner)
+{
+    corner = i < n_ls;
+    if (corner) return p.lsharp_pts[(size_t)scan * p.cap_lsharp + i];
+    int dense = i - n_ls;
+    const int *ds = p.lflat_ring_start + (size_t)scan * (VLO_MAX_RINGS + 1);
+    int lo = 0, hi = p.n_rings;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (ds[mid] <= dense) lo = mid; else hi = mid; }
+    int slot = p.ring_start[(size_t)scan * (VLO_MAX_RINGS + 1) + lo] + (dense - ds[lo]);
+    return p.lflat_slotted[(size_t)scan * p.N + slot];
+}
+
+__device__ __forceinline__ float4 to_map(const float *T, const float *trig, float4 pi)
+{
+    float x = pi.x, y = pi.y, z = pi.z;
+    float sx = trig[0], cx = trig[1], sy = trig[2], cy = trig[3], sz = trig[4], cz = trig[5];
+    float x0 = x; x = cz * x0 - sz * y; y = sz * x0 + cz * y;
+    float y0 = y; y = cx * y0 - sx * z; z = sx * y0 + cx * z;
+    x0 = x;       x = cy * x0 + sy * z; z = cy * z - sy * x0;
+    return make_float4(x + T[3], y + T[4], z + T[5], pi.w);
+}
+
+__global__ void __launch_bounds__(256) k5_knn(MapParams p)
+{
+    const int k = blockIdx.y;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (p.state[k * 4 + 0]) return;
+    const int scan = p.scans[k];
+    const int n_ls = p.counts[scan * 8 + 2], n_lf = p.counts[scan * 8 + 4];
+    if (w >= n_ls + n_lf) return;
+    if (!(p.map_n[2] > 10 && p.map_n[4] > 100)) return;
+    float T[6], trig[6];
+    #pragma unroll
+    for (int a = 0; a < 6; a++) T[a] = p.T[k * 6 + a];
+    vlo_sincosf(T[0], trig[0], trig[1]); vlo_sincosf(T[1], trig[2], trig[3]); vlo_sincosf(T[2], trig[4], trig[5]);
+    bool corner;
+    float4 ori = map_query_point(p, scan, w, n_ls, corner);
+    float4 sel = to_map(T, trig, ori);
+    TopK<5> best;
+    if (corner) grid_search<5>(p.gm0, 0, sel.x, sel.y, sel.z, 1.0f, FilterAll(), best, lane);
+    else        grid_search<5>(p.gm1, 0, sel.x, sel.y, sel.z, 1.0f, FilterAll(), best, lane);
+    if (lane == 0) {
+        int *o = p.idx5 + ((size_t)k * p.qcap + w) * 5;
+        bool ok = best.tag[4] != GRID_NOTAG;
+        #pragma unroll
+        for (int j = 0; j < 5; j++) o[j] = ok ? (int)(best.tag[j] & 0xFFFFFFu) : -1;
+    }
+}
+
+// cyclic Jacobi on a symmetric 3x3; eval ascending, evec[k*3+i] = component i of eigenvector k
+__device__ inline void eig3_jacobi(const float *Ain, float *eval, float *evec)
+{
+    float A[3][3], V[3][3];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { A[i][j] = Ain[i * 3 + j]; V[i][j] = (i == j) ? 1.0f : 0.0f; }
+    for (int sweep = 0; sweep < 6; sweep++) {
+        #pragma unroll
+        for (int m = 0; m < 3; m++) {
+            const int p = (m == 2) ? 1 : 0, q = (m == 0) ? 1 : 2;
+            float apq = A[p][q];
+            if (apq == 0.0f) continue;
+            float theta = (A[q][q] - A[p][p]) / (2.0f * apq);
+            float t = 1.0f / (fabsf(theta) + sqrtf(theta * theta + 1.0f));
+            if (theta < 0.0f) t = -t;
+            float c = 1.0f / sqrtf(t * t + 1.0f), s = t * c;
+            #pragma unroll
+            for (int i = 0; i < 3; i++) { float aip = A[i][p], aiq = A[i][q]; A[i][p] = c * aip - s * aiq; A[i][q] = s * aip + c * aiq; }
+            #pragma unroll
+            for (int j = 0; j < 3; j++) { float apj = A[p][j], aqj = A[q][j]; A[p][j] = c * apj - s * aqj; A[q][j] = s * apj + c * aqj; }
+            #pragma unroll
+            for (int i = 0; i < 3; i++) { float vip = V[i][p], viq = V[i][q]; V[i][p] = c * vip - s * viq; V[i][q] = s * vip + c * viq; }
+            A[q][p] = A[p][q];
+            const int r = 3 - p - q;
+            A[r][p] = A[p][r]; A[r][q] = A[q][r];
+        }
+    }
+    int order[3] = { 0, 1, 2 };
+    for (int i = 1; i < 3; i++) {
+        int v = order[i], j = i;
+        while (j >= 1 && A[v][v] < A[order[j - 1]][order[j - 1]]) { order[j] = order[j - 1]; j--; }
+        order[j] = v;
+    }
+    for (int k = 0; k < 3; k++) {
+        eval[k] = A[order[k]][order[k]];
+        for (int i = 0; i < 3; i++) evec[k * 3 + i] = V[i][order[k]];
+    }
+}
+
+__device__ inline void lstsq53(const float (*Ain)[3], float *x)
+{
+    float A[5][3], b[5];
+    int perm[3] = { 0, 1, 2 };
+    for (int i = 0; i < 5; i++) { for (int j = 0; j < 3; j++) A[i][j] = Ain[i][j]; b[i] = -1.0f; }
+    float maxn2 = 0.0f;
+    for (int j = 0; j < 3; j++) { float s = 0.0f; for (int i = 0; i < 5; i++) s += A[i][j] * A[i][j]; if (s > maxn2) maxn2 = s; }
+    float mx = sqrtf(maxn2) * FLT_EPSILON;
+    float thr_helper = (mx * mx) / 5.0f;
+    int nonzero = 3;
+    for (int k = 0; k < 3; k++) {
+        int piv = k; float best = -1.0f;
+        for (int j = k; j < 3; j++) { float s = 0.0f; for (int i = k; i < 5; i++) s += A[i][j] * A[i][j]; if (s > best) { best = s; piv = j; } }
+        if (nonzero == 3 && best < thr_helper * (float)(5 - k)) nonzero = k;
+        if (piv != k) {
+            for (int i = 0; i < 5; i++) { float t = A[i][k]; A[i][k] = A[i][piv]; A[i][piv] = t; }
+            int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t;
+        }
+        float nrm = sqrtf(best);
+        if (nrm == 0.0f) continue;
+        float alpha = (A[k][k] >= 0.0f) ? -nrm : nrm;
+        float v[5] = { 0.f, 0.f, 0.f, 0.f, 0.f };
+        for (int i = k; i < 5; i++) v[i] = A[i][k];
+        v[k] = v[k] - alpha;
+        float vn2 = 0.0f;
+        for (int i = k; i < 5; i++) vn2 += v[i] * v[i];
+        if (vn2 == 0.0f) continue;
+        for (int j = k; j < 3; j++) {
+            float dot = 0.0f;
+            for (int i = k; i < 5; i++) dot += v[i] * A[i][j];
+            float f = (2.0f * dot) / vn2;
+            for (int i = k; i < 5; i++) A[i][j] = A[i][j] - f * v[i];
+        }
+        float dot = 0.0f;
+        for (int i = k; i < 5; i++) dot += v[i] * b[i];
+        float f = (2.0f * dot) / vn2;
+        for (int i = k; i < 5; i++) b[i] = b[i] - f * v[i];
+    }
+    float y[3] = { 0.f, 0.f, 0.f };
+    for (int i = nonzero - 1; i >= 0; i--) {
+        float s = b[i];
+        for (int j = i + 1; j < nonzero; j++) s = s - A[i][j] * y[j];
+        y[i] = s / A[i][i];
+    }
+    for (int i = 0; i < 3; i++) x[perm[i]] = y[i];
+}
+
+__device__ inline bool map_edge_coeff(float4 sel, const float4 *nb, float *coeff)
+{
+    float vx = 0.0f, vy = 0.0f, vz = 0.0f;
+    for (int j = 0; j < 5; j++) { vx += nb[j].x; vy += nb[j].y; vz += nb[j].z; }
+    vx = vx / 5.0f; vy = vy / 5.0f; vz = vz / 5.0f;
+    float a00 = 0, a10 = 0, a20 = 0, a11 = 0, a21 = 0, a22 = 0;
+    for (int j = 0; j < 5; j++) {
+        float ax = nb[j].x - vx, ay = nb[j].y - vy, az = nb[j].z - vz;
+        a00 += ax * ax; a10 += ax * ay; a20 += ax * az; a11 += ay * ay; a21 += ay * az; a22 += az * az;
+    }
+    float M[9];
+    M[0] = a00 / 5.0f; M[4] = a11 / 5.0f; M[8] = a22 / 5.0f;
+    M[3] = M[1] = a10 / 5.0f; M[6] = M[2] = a20 / 5.0f; M[7] = M[5] = a21 / 5.0f;
+    float ev[3], evec[9];
+    eig3_jacobi(M, ev, evec);
+    if (!(ev[2] > 3.0f * ev[1])) return false;
+    float x0 = sel.x, y0 = sel.y, z0 = sel.z;
+    float x1 = (float)((double)vx + 0.1 * (double)evec[6]), y1 = (float)((double)vy + 0.1 * (double)evec[7]), z1 = (float)((double)vz + 0.1 * (double)evec[8]);
+    float x2 = (float)((double)vx - 0.1 * (double)evec[6]), y2 = (float)((double)vy - 0.1 * (double)evec[7]), z2 = (float)((double)vz - 0.1 * (double)evec[8]);
+    float m1 = (x0 - x1) * (y0 - y2) - (x0 - x2) * (y0 - y1);
+    float m2 = (x0 - x1) * (z0 - z2) - (x0 - x2) * (z0 - z1);
+    float m3 = (y0 - y1) * (z0 - z2) - (y0 - y2) * (z0 - z1);
+    float a012 = sqrtf(m1 * m1 + m2 * m2 + m3 * m3);
+    float l12 = sqrtf((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2) + (z1 - z2) * (z1 - z2));
+    float la = ((y1 - y2) * m1 + (z1 - z2) * m2) / a012 / l12;
+    float lb = -((x1 - x2) * m1 - (z1 - z2) * m3) / a012 / l12;
+    float lc = -((x1 - x2) * m2 + (y1 - y2) * m3) / a012 / l12;
+    float ld2 = a012 / l12;
+    float s = 1.0f - 0.9f * fabsf(ld2);
+    coeff[0] = s * la; coeff[1] = s * lb; coeff[2] = s * lc; coeff[3] = s * ld2;
+    return (double)s > 0.1;
+}
+
+__device__ inline bool map_plane_coeff(float4 sel, const float4 *nb, float *coeff)
+{
+    float A0[5][3], X0[3];
+    for (int j = 0; j < 5; j++) { A0[j][0] = nb[j].x; A0[j][1] = nb[j].y; A0[j][2] = nb[j].z; }
+    lstsq53(A0, X0);
+    float pa = X0[0], pb = X0[1], pc = X0[2], pd = 1.0f;
+    float ps = sqrtf(pa * pa + pb * pb + pc * pc);
+    pa = pa / ps; pb = pb / ps; pc = pc / ps; pd = pd / ps;
+    for (int j = 0; j < 5; j++)
+        if ((double)fabsf(pa * nb[j].x + pb * nb[j].y + pc * nb[j].z + pd) > 0.2) return false;
+    float pd2 = pa * sel.x + pb * sel.y + pc * sel.z + pd;
+    float s = 1.0f - 0.9f * fabsf(pd2) / sqrtf(sqrtf(sel.x * sel.x + sel.y * sel.y + sel.z * sel.z));
+    coeff[0] = s * pa; coeff[1] = s * pb; coeff[2] = s * pc; coeff[3] = s * pd2;
+    return (double)s > 0.1;
+}
+
+#define LIN_THREADS 256
+#define LSTRIDE 29
+
+__global__ void __launch_bounds__(LIN_THREADS) k5_lin(MapParams p)
+{
+    __shared__ float terms[LIN_THREADS * LSTRIDE];
+    __shared__ int s_ne, s_np;
+    const int k = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    if (p.state[k * 4 + 0]) return;
+    const int scan = p.scans[k];
+    const int n_ls = p.counts[scan * 8 + 2], n_lf = p.counts[scan * 8 + 4];
+    const int q_total = n_ls + n_lf;
+    const int i = blockIdx.x * LIN_THREADS + tid;
+    if (blockIdx.x * LIN_THREADS >= q_total) return;
+    if (!(p.map_n[2] > 10 && p.map_n[4] > 100)) return;
+    if (tid == 0) { s_ne = 0; s_np = 0; }
+    float T[6], trig[6];
+    #pragma unroll
+    for (int a = 0; a < 6; a++) T[a] = p.T[k * 6 + a];
+    vlo_sincosf(T[0], trig[0], trig[1]); vlo_sincosf(T[1], trig[2], trig[3]); vlo_sincosf(T[2], trig[4], trig[5]);
+    float t[VLO_NTERM];
+    #pragma unroll
+    for (int e = 0; e < VLO_NTERM; e++) t[e] = 0.0f;
+    int my_e = 0, my_p = 0;
+    if (i < q_total) {
+        const int *id = p.idx5 + ((size_t)k * p.qcap + i) * 5;
+        if (id[4] >= 0) {
+            bool corner;
+            float4 ori = map_query_point(p, scan, i, n_ls, corner);
+            float4 sel = to_map(T, trig, ori);
+            const float4 *map = corner ? p.map0 : p.map1;
+            float4 nb[5];
+            #pragma unroll
+            for (int j = 0; j < 5; j++) nb[j] = map[id[j]];
+            float coeff[4];
+            bool keep = corner ? map_edge_coeff(sel, nb, coeff) : map_plane_coeff(sel, nb, coeff);
+            if (keep) {
+                if (corner) my_e = 1; else my_p = 1;
+                float srx = trig[0], crx = trig[1], sry = trig[2], cry = trig[3], srz = trig[4], crz = trig[5];
+                float x = ori.x, y = ori.y, z = ori.z, cx_ = coeff[0], cy_ = coeff[1], cz_ = coeff[2];
+                float row[6];
+                row[0] = (crx * sry * srz * x + crx * crz * sry * y - srx * sry * z) * cx_
+                       + (-srx * srz * x - crz * srx * y - crx * z) * cy_
+                       + (crx * cry * srz * x + crx * cry * crz * y - cry * srx * z) * cz_;
+                row[1] = ((cry * srx * srz - crz * sry) * x + (sry * srz + cry * crz * srx) * y + crx * cry * z) * cx_
+                       + ((-cry * crz - srx * sry * srz) * x + (cry * srz - crz * srx * sry) * y - crx * sry * z) * cz_;
+                row[2] = ((crz * srx * sry - cry * srz) * x + (-cry * crz - srx * sry * srz) * y) * cx_
+                       + (crx * crz * x - crx * srz * y) * cy_
+                       + ((sry * srz + cry * crz * srx) * x + (crz * sry - cry * srx * srz) * y) * cz_;
+                row[3] = cx_; row[4] = cy_; row[5] = cz_;
+                float bval = -coeff[3];
+                int e = 0;
+                #pragma unroll
+                for (int a = 0; a < 6; a++)
+                    #pragma unroll
+                    for (int b = a; b < 6; b++) t[e++] = row[a] * row[b];
+                #pragma unroll
+                for (int a = 0; a < 6; a++) t[e++] = row[a] * bval;
+                t[e] = coeff[3] * coeff[3];
+            }
+        }
+    }
+    #pragma unroll
+    for (int e = 0; e < VLO_NTERM; e++) terms[tid * LSTRIDE + e] = t[e];
+    unsigned be = __reduce_add_sync(0xffffffffu, my_e), bp = __reduce_add_sync(0xffffffffu, my_p);
+    __syncthreads();
+    if (lane == 0) { atomicAdd(&s_ne, (int)be); atomicAdd(&s_np, (int)bp); }
+    if (tid < 8 * VLO_NTERM) {
+        int g = tid / VLO_NTERM, e = tid % VLO_NTERM;
+        if (blockIdx.x * LIN_THREADS + g * 32 < q_total) {
+            float l1 = 0.0f;
+            const float *src = terms + (size_t)(g * 32) * LSTRIDE + e;
+            #pragma unroll 8
+            for (int q = 0; q < 32; q++) l1 = l1 + src[(size_t)q * LSTRIDE];
+            p.partials[((size_t)k * p.pcap + blockIdx.x * 8 + g) * VLO_NTERM + e] = l1;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) { atomicAdd(&p.ncorr[k * 2], s_ne); atomicAdd(&p.ncorr[k * 2 + 1], s_np); }
+}
+
+#define SOLVE_THREADS 256
+__global__ void __launch_bounds__(SOLVE_THREADS) k5_solve(MapParams p, int it)
+{
+    __shared__ GnScratch S;
+    __shared__ float l2[64 * VLO_NTERM];
+    const int k = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int *state = p.state + k * 4;
+    if (state[0]) return;
+    const int scan = p.scans[k];
+    vlo_result *res = p.result + k;
+    const int q_total = p.counts[scan * 8 + 2] + p.counts[scan * 8 + 4];
+    if (!(p.map_n[2] > 10 && p.map_n[4] > 100)) {
+        if (tid == 0) { state[0] = 1; state[1] = 0; res->iterations = 0; res->status = VLO_SOFT_TOO_FEW_CORR; }
+        return;
+    }
+    const int n_edge = p.ncorr[k * 2], n_plane = p.ncorr[k * 2 + 1];
+    __syncthreads();
+    if (tid == 0) { p.ncorr[k * 2] = 0; p.ncorr[k * 2 + 1] = 0; state[1] = it + 1; res->iterations = it + 1; }
+    if (n_edge + n_plane < 50) return;            // upstream `continue`
+    if (tid < 6) S.T[tid] = p.T[k * 6 + tid];
+    if (tid < 36 && it > 0) S.P[tid] = res->P[tid];
+    if (tid == 0) { S.is_degenerate = state[2]; S.converged = 0; S.n_edge = n_edge; S.n_plane = n_plane; }
+    // R1 levels 2 and 3 over the level-1 sums
+    const int n_l1 = (q_total + 31) / 32, n_l2 = (n_l1 + 31) / 32;
+    float l3 = 0.0f;
+    for (int base = 0; base < n_l2; base += 64) {
+        __syncthreads();
+        for (int task = tid; task < 64 * VLO_NTERM; task += SOLVE_THREADS) {
+            int b2 = base + task / VLO_NTERM, e = task % VLO_NTERM;
+            if (b2 < n_l2) {
+                float acc = 0.0f;
+                int lo = b2 * 32, hi = min(n_l1, lo + 32);
+                const float *src = p.partials + ((size_t)k * p.pcap + lo) * VLO_NTERM + e;
+                for (int q = lo; q < hi; q++, src += VLO_NTERM) acc = acc + *src;
+                l2[(task / VLO_NTERM) * VLO_NTERM + e] = acc;
+            }
+        }
+        __syncthreads();
+        if (tid < VLO_NTERM) {
+            int cnt = min(64, n_l2 - base);
+            for (int b = 0; b < cnt; b++) l3 = l3 + l2[b * VLO_NTERM + tid];
+        }
+    }
+    if (tid < VLO_NTERM) S.total[tid] = l3;
+    __syncthreads();
+    if (warp == 0) vlo_gn_update_warp(S, it, p.degen_thr, p.dT_abort, p.dR_abort, lane);
+    __syncthreads();
+    if (tid < 6) { p.T[k * 6 + tid] = S.T[tid]; res->transform[tid] = S.T[tid]; }
+    if (it == 0) {
+        if (tid < 36) res->P[tid] = S.P[tid];
+        if (tid < 6) res->eig[tid] = S.eval[tid];
+    }
+    if (tid == 0) {
+        state[0] = S.converged; state[2] = S.is_degenerate; state[3] = VLO_OK;
+        res->is_degenerate = S.is_degenerate; res->status = VLO_OK;
+        res->n_corr_edge = n_edge; res->n_corr_plane = n_plane;
+        vlo_finish_result(S, p.rot_thr, p.trans_thr, res);
+    }
+}
+
+__global__ void k5_init(MapParams p, const float *seeds, int n)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    for (int a = 0; a < 6; a++) p.T[k * 6 + a] = seeds[k * 6 + a];
+    int *st = p.state + k * 4;
+    st[0] = 0; st[1] = 0; st[2] = 0; st[3] = VLO_SOFT_TOO_FEW_CORR;
+    p.ncorr[k * 2] = 0; p.ncorr[k * 2 + 1] = 0;
+    vlo_result *r = p.result + k;
+    for (int a = 0; a < 6; a++) { r->transform[a] = seeds[k * 6 + a]; r->eig[a] = 0.0f; }
+    for (int a = 0; a < 36; a++) { r->hessian[a] = 0.0f; r->P[a] = (a % 7 == 0) ? 1.0f : 0.0f; r->cov[a] = 0.0; }
+    r->is_degenerate = 0; r->iterations = 0; r->n_corr_edge = 0; r->n_corr_plane = 0;
+    r->logdet_rot = 0.f; r->logdet_trans = 0.f; r->pass_dopt = 0; r->status = VLO_SOFT_TOO_FEW_CORR;
+}
+
+int vlo_launch_register_map(vlo_handle *h, const int *d_scans, int n, const float *d_seeds)
+{
+    ScanBatchDev &sb = h->sb; const vlo_config &c = h->cfg;
+    MapParams p;
+    p.lsharp_pts = sb.lsharp_pts; p.cap_lsharp = h->cap_lsharp; p.lflat_slotted = sb.lflat_slotted; p.N = c.max_points;
+    p.ring_start = sb.ring_start; p.lflat_ring_start = sb.lflat_ring_start; p.counts = sb.counts; p.n_rings = c.n_rings;
+    p.scans = d_scans; p.T = h->map_T; p.state = h->map_state; p.result = h->map_result;
+    p.idx5 = h->map_idx5; p.qcap = h->cap_lsharp + c.max_points;
+    p.partials = h->map_partials; p.pcap = (p.qcap + 31) / 32 + 8; p.ncorr = h->map_ncorr;
+    p.gm0 = h->gs_map[0]; p.gm1 = h->gs_map[1]; p.map0 = h->map_pts[0]; p.map1 = h->map_pts[1]; p.map_n = h->map_n;
+    p.max_iter = c.map_max_iterations; p.degen_thr = c.map_degen_eig; p.dT_abort = c.map_delta_t_abort;
+    p.dR_abort = c.map_delta_r_abort; p.rot_thr = c.dopt_rot_threshold; p.trans_thr = c.dopt_trans_threshold;
+    k5_init<<<(n + 127) / 128, 128, 0, h->stream>>>(p, d_seeds, n);
+    h->launches += 1;
+    // grids sized by the largest feature count actually present would need a sync; use capacity
+    int qmax = h->map_qmax > 0 ? h->map_qmax : p.qcap;
+    dim3 gk((qmax * 32 + 255) / 256, n), gl((qmax + LIN_THREADS - 1) / LIN_THREADS, n);
+    for (int it = 0; it < c.map_max_iterations; it++) {
+        k5_knn<<<gk, 256, 0, h->stream>>>(p);
+        k5_lin<<<gl, LIN_THREADS, 0, h->stream>>>(p);
+        k5_solve<<<n, SOLVE_THREADS, 0, h->stream>>>(p, it);
+        h->launches += 3;
+    }
+    VLO_CUDA(cudaGetLastError());
+    return VLO_OK;
+}

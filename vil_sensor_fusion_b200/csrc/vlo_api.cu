@@ -91,10 +91,12 @@ extern "C" int vlo_create(const vlo_config *cfg, vlo_handle **out)
     h->grids_valid = 0; h->trace = 0; h->pair_last_T = nullptr;
     h->status_word = nullptr; h->pair_T = h->pair_seed = nullptr; h->pair_last = h->pair_cur = h->pair_state = nullptr;
     h->pair_cidx = h->pair_sidx = h->pair_trace = nullptr; h->pair_result = nullptr;
-    h->map_partials = nullptr; h->map_idx5 = nullptr;
+    h->map_partials = nullptr; h->map_idx5 = nullptr; h->map_T = h->map_seed = nullptr; h->map_state = h->map_ncorr = h->map_scans = nullptr;
+    h->map_result = nullptr; h->map_qmax = 0; h->last_n_map = 0; h->last_n_pairs = 0;
+    h->imu_buf = nullptr; h->imu_buf_bytes = 0; h->imu_out = nullptr; h->imu_out_cap = 0;
     h->online_have_last = 0; h->online_slot = 0;
     memset(h->online_T, 0, sizeof(h->online_T)); memset(h->online_sum, 0, sizeof(h->online_sum));
-    memset(h->online_map_T, 0, sizeof(h->online_map_T));
+    memset(h->online_map_bef, 0, sizeof(h->online_map_bef)); memset(h->online_map_aft, 0, sizeof(h->online_map_aft)); h->online_ticks = 0;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return VLO_ERR_CUDA; }
     const int B = c.max_scans, N = c.max_points, R = c.n_rings, NR = c.feature_regions;
     h->tiles_per_scan = (N + 255) / 256;
@@ -104,8 +106,8 @@ extern "C" int vlo_create(const vlo_config *cfg, vlo_handle **out)
     ScanBatchDev &sb = h->sb;
     HALLOC(h->status_word, 1);
     cudaMemset(h->status_word, 0, sizeof(int));
-    HALLOC(sb.raw_owned, (size_t)B * N * 4);
-    HALLOC(sb.raw_offset, (size_t)B + 1);
+    HALLOC(sb.raw_owned, (size_t)B * N * 4 + 64);
+    HALLOC(sb.raw_offset, (size_t)B * 2);
     HALLOC(sb.first_half, (size_t)B); HALLOC(sb.ori_bounds, (size_t)B * 2);
     HALLOC(sb.tile_hist, (size_t)B * R * h->tiles_per_scan);
     HALLOC(sb.cloud, (size_t)B * N); HALLOC(sb.ring_start, (size_t)B * (VLO_MAX_RINGS + 1)); HALLOC(sb.src_index, (size_t)B * N);
@@ -136,8 +138,10 @@ extern "C" int vlo_create(const vlo_config *cfg, vlo_handle **out)
             int rc = alloc_gridset(h, h->gs_map[w], 1, c.max_map_points, c.map_cell_size); if (rc) { vlo_destroy(h); return rc; }
         }
         int qcap = h->cap_lsharp + N;
-        HALLOC(h->map_partials, (size_t)B * ((qcap + 31) / 32 + 2) * VLO_NTERM);
+        HALLOC(h->map_partials, (size_t)B * ((qcap + 31) / 32 + 8) * VLO_NTERM);
         HALLOC(h->map_idx5, (size_t)B * qcap * 5);
+        HALLOC(h->map_T, (size_t)B * 6); HALLOC(h->map_seed, (size_t)B * 6); HALLOC(h->map_state, (size_t)B * 4);
+        HALLOC(h->map_ncorr, (size_t)B * 2); HALLOC(h->map_scans, (size_t)B); HALLOC(h->map_result, (size_t)B);
     }
     if (cudaDeviceSynchronize() != cudaSuccess) { h->err = "device sync after allocation failed"; vlo_destroy(h); return VLO_ERR_CUDA; }
     *out = h;
@@ -155,7 +159,8 @@ extern "C" void vlo_destroy(vlo_handle *h)
                      sb.lflat_cnt, sb.counts, sb.sharp_idx, sb.lsharp_idx, sb.flat_idx, sb.sharp_pts, sb.lsharp_pts, sb.flat_pts,
                      sb.lsharp_ring_start, sb.lflat_ring_start, h->status_word, h->pair_T, h->pair_seed, h->pair_last,
                      h->pair_cur, h->pair_state, h->pair_cidx, h->pair_sidx, h->pair_trace, h->pair_result, h->pair_last_T, h->map_n,
-                     h->map_pts[0], h->map_pts[1], h->map_partials, h->map_idx5 };
+                     h->map_pts[0], h->map_pts[1], h->map_partials, h->map_idx5, h->map_T, h->map_seed, h->map_state, h->map_ncorr,
+                     h->map_scans, h->map_result, h->imu_buf, h->imu_out };
     for (void *p : ptrs) if (p) cudaFree(p);
     free_gridset(h->gs_corner); free_gridset(h->gs_surf); free_gridset(h->gs_map[0]); free_gridset(h->gs_map[1]);
     if (h->pinned) cudaFreeHost(h->pinned);
@@ -188,10 +193,10 @@ extern "C" int vlo_scans_upload(vlo_handle *h, const float *raw, const int *offs
     cudaSetDevice(h->cfg.device);
     ScanBatchDev &sb = h->sb;
     size_t total = (size_t)(offsets[n_scans] - offsets[0]);
-    int rc = ensure_pinned(h, sizeof(int) * (size_t)(h->cfg.max_scans + 1)); if (rc) return rc;
+    int rc = ensure_pinned(h, sizeof(int) * 2 * (size_t)h->cfg.max_scans); if (rc) return rc;
     int *poff = (int *)h->pinned;
-    for (int s = 0; s <= n_scans; s++) poff[s] = offsets[s] - offsets[0];
-    VLO_CUDA(cudaMemcpyAsync(sb.raw_offset, poff, sizeof(int) * (size_t)(n_scans + 1), cudaMemcpyHostToDevice, h->stream));
+    for (int s = 0; s < n_scans; s++) { poff[2 * s] = offsets[s] - offsets[0]; poff[2 * s + 1] = offsets[s + 1] - offsets[s]; }
+    VLO_CUDA(cudaMemcpyAsync(sb.raw_offset, poff, sizeof(int) * 2 * (size_t)n_scans, cudaMemcpyHostToDevice, h->stream));
     if (on_device) {
         sb.raw = raw + (size_t)offsets[0] * stride;
     } else {
@@ -201,7 +206,8 @@ extern "C" int vlo_scans_upload(vlo_handle *h, const float *raw, const int *offs
     }
     // the offsets staging buffer is reused by the next call: make the copy complete first
     VLO_CUDA(cudaStreamSynchronize(h->stream));
-    sb.n_scans = n_scans; sb.stride = stride;
+    sb.n_scans = n_scans; sb.stride = stride; sb.scan_first = 0; sb.scan_count = n_scans;
+    h->online_have_last = 0;
     return VLO_OK;
 }
 
@@ -218,7 +224,7 @@ extern "C" int vlo_scans_extract(vlo_handle *h)
     if (!h) return VLO_ERR_INVALID_ARG;
     if (h->sb.n_scans < 1) { h->err = "no scans uploaded"; return VLO_ERR_STATE; }
     cudaSetDevice(h->cfg.device);
-    h->grids_valid = 0;
+    h->grids_valid = 0; h->map_qmax = 0;
     return vlo_launch_extract(h);
 }
 
@@ -232,6 +238,7 @@ extern "C" int vlo_scans_counts(vlo_handle *h, vlo_feature_counts *counts)
     for (int b = 0; b < B; b++) {
         counts[b].n_valid = tmp[b * 8]; counts[b].n_sharp = tmp[b * 8 + 1]; counts[b].n_less_sharp = tmp[b * 8 + 2];
         counts[b].n_flat = tmp[b * 8 + 3]; counts[b].n_less_flat = tmp[b * 8 + 4];
+        h->map_qmax = std::max(h->map_qmax, tmp[b * 8 + 2] + tmp[b * 8 + 4]);
     }
     return VLO_OK;
 }
@@ -307,7 +314,7 @@ extern "C" int vlo_register_pairs(vlo_handle *h, const int *last, const int *cur
         VLO_CUDA(cudaMemcpyAsync(h->pair_seed, ps, sizeof(float) * 6 * (size_t)n_pairs, cudaMemcpyHostToDevice, h->stream)); }
     if (last_transforms) { memcpy(pt, last_transforms, sizeof(float) * 6 * (size_t)n_pairs);
         VLO_CUDA(cudaMemcpyAsync(h->pair_last_T, pt, sizeof(float) * 6 * (size_t)n_pairs, cudaMemcpyHostToDevice, h->stream)); }
-    rc = vlo_launch_register_pairs(h, n_pairs, seeds ? h->pair_seed : nullptr, last_transforms ? h->pair_last_T : nullptr);
+    rc = vlo_launch_register_pairs(h, n_pairs, seeds ? h->pair_seed : nullptr, last_transforms ? h->pair_last_T : nullptr, -1);
     if (rc) return rc;
     VLO_CUDA(cudaMemcpyAsync(pres, h->pair_result, sizeof(vlo_result) * (size_t)n_pairs, cudaMemcpyDeviceToHost, h->stream));
     rc = vlo_synchronize(h); if (rc) return rc;

@@ -39,6 +39,7 @@ struct GridSource {
 // Device-resident state of a batch of scans (capacities from vlo_config)
 struct ScanBatchDev {
     int    n_scans;
+    int    scan_first, scan_count;   // range the next organise / extract launch covers
     int    stride;            // floats per raw point
     const float *raw;         // device pointer (owned or borrowed)
     float *raw_owned;
@@ -95,14 +96,18 @@ struct vlo_handle {
     float4 *map_pts[2];
     int *map_n;                // device [8]: [2] = n_corner, [4] = n_surf (same layout as counts rows)
     int map_n_host[2];
-    // mapping workspace
-    float *map_partials;       // [n][blocks][28]
-    int   *map_idx5;           // [n][Q][5]
+    // mapping workspace (slot k of a vlo_register_map call)
+    float *map_partials;       // [n][pcap][28] level-1 sums
+    int   *map_idx5;           // [n][qcap][5]
+    float *map_T; float *map_seed; int *map_state; int *map_ncorr; int *map_scans; vlo_result *map_result;
+    int map_qmax, last_n_map;
+    // IMU staging (grown on demand)
+    double *imu_buf; size_t imu_buf_bytes; vlo_preint *imu_out; int imu_out_cap;
     // pinned staging
     void *pinned; size_t pinned_bytes;
     // online state
-    int online_have_last; float online_T[6]; float online_sum[6]; float online_map_T[6];
-    int online_slot;
+    int online_have_last; float online_T[6]; float online_sum[6]; float online_map_bef[6], online_map_aft[6];
+    int online_slot; long long online_ticks;
 };
 
 #define VLO_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
@@ -198,10 +203,10 @@ __device__ __forceinline__ float4 vlo_to_start(const float *T, float4 p, int des
 // kernels' host launchers -----------------------------------------------------------------------
 int vlo_launch_organise(vlo_handle *h);
 int vlo_launch_extract(vlo_handle *h);
-int vlo_grid_build(vlo_handle *h, const GridSet &gs, const GridSource &src, int n_grids, int n_slots);
+int vlo_grid_build(vlo_handle *h, const GridSet &gs, const GridSource &src, int g_first, int n_grids, int n_slots);
 int vlo_grid_knn(vlo_handle *h, const GridSet &gs, int g, const float4 *d_q, int nq, int k, float dmax, int *d_idx, float *d_d2);
-int vlo_build_scan_grids(vlo_handle *h);
-int vlo_launch_register_pairs(vlo_handle *h, int n_pairs, const float *d_seeds, const float *d_last_T);
+int vlo_build_scan_grids(vlo_handle *h, int first, int count);
+int vlo_launch_register_pairs(vlo_handle *h, int n_pairs, const float *d_seeds, const float *d_last_T, int only_grid_scan);
 int vlo_launch_register_map(vlo_handle *h, const int *d_scans, int n, const float *d_seeds);
 int vlo_launch_imu(vlo_handle *h, const double *d_t, const double *d_acc, const double *d_gyro, int n_samples,
                    const double *d_t0, const double *d_t1, const double *d_bias, int n_factors, vlo_preint *d_out);
