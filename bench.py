@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 LiDAR-odometry hot path.
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on):
+  HDL-64-shaped scans (64 x 1800 = 115 200 points) -> ring organise (K0) -> feature extraction (K1)
+  -> scan-to-map registration against a 1M-point voxel-hash map incl. eigenvalue degeneracy test,
+  solution remapping and the D-optimality gate (K2/K5/K4).
+One "step" = one batch of `--batch` scans per GPU through that path.  `value` = whole-job scans/s with
+the raw clouds already resident in HBM; `e2e` = the same through the C-ABI with HOST (pinned) buffers,
+host->device copies of the clouds and device->host reads of the results inside the timed region.
+N > 1: frames are sharded by contiguous range across ranks (one process per GPU, own map replica),
+no collective in the per-scan path, one gather of the result records per step ("scaling": "weak").
+
+`--impl reference` times the CPU restatement of the reference path (oracle/, kd-tree based, all host
+threads, frames in parallel) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "LiDAR scans/sec (HDL-64 scan-to-map registration + degeneracy, 1M-point map)"
+UNIT = "scans/s"
+POOL = 8                 # distinct synthetic scans cycled through a batch
+N_MAP = 1_000_000
+SEED_PERTURB = np.array([0.004, -0.006, 0.003, 0.06, -0.04, 0.08], np.float32)
+
+
+def make_workload(pool: int, rank: int = 0):
+    from vil_sensor_fusion_b200 import synth
+    scene = synth.scene_room(0)
+    traj = synth.Trajectory()
+    raws, seeds = [], []
+    for k in range(pool):
+        t = 0.1 * (k + pool * rank)
+        raws.append(synth.make_scan(scene, "HDL-64E", t0=t, traj=traj, rolling=False, noise_sigma=0.01, seed=k + 100 * rank))
+        gt = synth.loam_map_pose(traj.rotation(t), traj.position(t)).astype(np.float32)
+        seeds.append(gt + SEED_PERTURB)
+    cm, sm = synth.make_voxel_map(scene, N_MAP, seed=1)
+    return raws, np.stack(seeds), cm, sm
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.samples.append(line.strip())
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(stage: str, counts, n_map_pts, iters_done):
+    """ALGORITHMIC bytes one launch of `stage` moves for the batch (SURVEY.md 8d formulas)."""
+    nv = sum(c["n_valid"] for c in counts)
+    nfeat = sum(c["n_sharp"] + c["n_less_sharp"] + c["n_flat"] + c["n_less_flat"] for c in counts)
+    q = sum(c["n_less_sharp"] + c["n_less_flat"] for c in counts)
+    if stage == "k0_organise":
+        return nv * (16 + 16)                                # raw xyz(i) in, ring-major float4 out
+    if stage == "k1_extract":
+        return nv * 21 + 4 * nfeat                           # 16 in + 4 curvature + 1 label, + index lists
+    if stage == "k1b_compact":
+        return 2 * 20 * sum(c["n_sharp"] + c["n_less_sharp"] + c["n_flat"] for c in counts)
+    if stage == "k5_knn":
+        return n_map_pts * 16 + q * 16 + q * 5 * 4           # map read once + queries + 5 indices each
+    if stage == "k5_lin":
+        return q * (16 + 5 * 4 + 5 * 16) + (q // 32 + 1) * 28 * 4   # 116 B per query + level-1 sums
+    if stage == "k5_solve":
+        return (q // 32 + 1) * 28 * 4
+    return 0
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from vil_sensor_fusion_b200 import api, bag
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if rank == 0 and world > 1:
+            print("warning: WORLD_SIZE %d != --gpus %d" % (world, args.gpus), file=sys.stderr)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    B = args.batch
+    raws_pool, seeds_pool, cm, sm = make_workload(POOL, rank)
+    raws = [raws_pool[k % POOL] for k in range(B)]
+    seeds = np.stack([seeds_pool[k % POOL] for k in range(B)])
+    offs = np.zeros(B + 1, np.int32)
+    offs[1:] = np.cumsum([r.shape[0] for r in raws])
+    n_pts = int(offs[-1])
+    host = torch.empty((n_pts, 4), dtype=torch.float32).pin_memory()
+    host.numpy()[:] = np.concatenate(raws, axis=0)
+    dev = host.to("cuda", non_blocking=False)
+    scans_idx = np.arange(B, dtype=np.int32)
+    h2d_bytes = n_pts * 16
+    d2h_bytes = B * api.RESULT_DTYPE.itemsize
+
+    cfg = api.default_config("HDL-64E", deskew=0, max_scans=B, max_points=131072,
+                             max_map_points=int(max(len(cm), len(sm))), device=local_rank)
+    h = api.Handle(cfg)
+    h.map_build(cm, sm)
+    stream = torch.cuda.ExternalStream(h.stream_ptr(), device=torch.device("cuda", local_rank))
+
+    def step(on_device: bool):
+        if on_device:
+            h.upload_raw(dev.data_ptr(), offs, 4, True)
+        else:
+            h.upload_raw(host.data_ptr(), offs, 4, False)
+        h.organise()
+        h.extract()
+        res = h.register_map(scans_idx, seeds)
+        if world > 1:
+            res = bag.gather_results(res)              # the one exchange step (result records only)
+        return res
+
+    def barrier():
+        torch.cuda.synchronize()
+        h.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- correctness guard: the timed path must do the work (converged, correspondences found)
+    res = step(True)
+    counts = h.counts()
+    ok = int(np.sum(res["status"] == 0))
+    if ok < len(res):
+        print("warning: %d of %d registrations reported a soft status" % (len(res) - ok, len(res)), file=sys.stderr)
+
+    for _ in range(max(args.warmup - 1, 0)):
+        step(True)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    time.sleep(0.25)
+    h.set_profiling(True)
+    launches0 = h.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        res = step(True)
+    ev1.record(stream)
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = h.launch_count() - launches0
+    stages = h.stage_times()
+    h.set_profiling(False)
+
+    # ---- e2e: HOST buffers, H2D of the clouds and D2H of the results inside the timed region
+    for _ in range(2):
+        step(False)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        res_e2e = step(False)
+    e1.record(stream)
+    barrier()
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_dev_ms = e0.elapsed_time(e1)
+    e2e_ms = max(e2e_wall_ms, e2e_dev_ms)
+    clocks.stop()
+
+    # ---- online latency (single scan per call, the online path): p50 / p95 of vlo_process_scan
+    p50 = p95 = None
+    if rank == 0:
+        from vil_sensor_fusion_b200 import synth
+        cfg1 = api.default_config("HDL-64E", deskew=0, max_scans=2, max_points=131072,
+                                  max_map_points=int(max(len(cm), len(sm))), device=local_rank)
+        with api.Handle(cfg1) as h1:
+            h1.map_build(cm, sm)
+            traj = synth.Trajectory()
+            h1.online_set_map_pose(synth.loam_map_pose(traj.rotation(0.0), traj.position(0.0)).astype(np.float32))
+            lat = []
+            for rep in range(4):
+                for k in range(POOL):
+                    if k == 0:
+                        h1.lib.vlo_online_reset(h1._h)
+                        h1.online_set_map_pose(synth.loam_map_pose(traj.rotation(0.0), traj.position(0.0)).astype(np.float32))
+                    t1 = time.perf_counter()
+                    h1.process_scan(raws_pool[k], 0.1 * k, want_map=True)
+                    if rep > 0 and k > 0:
+                        lat.append((time.perf_counter() - t1) * 1e3)
+            lat.sort()
+            p50 = lat[len(lat) // 2]
+            p95 = lat[int(len(lat) * 0.95)]
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_ms, float(launches)], dtype=torch.float64, device="cuda")
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dev_ms, e2e_ms = float(tmax[0]), float(tmax[1])
+        launches = int(tsum[2])
+    ms_per_step = dev_ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+    e2e_value = world * B / (e2e_ms / args.steps * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+        n_map_pts = len(cm) + len(sm)
+        mean_iters = float(np.mean(res["iterations"]))
+        table = {}
+        for name, (ms, n) in stages.items():
+            if n == 0:
+                continue
+            # k5_* launch max_iter times but only the first `iterations` do work: average over working launches
+            working = n
+            if name.startswith("k5_"):
+                working = max(1, int(round(args.steps * min(mean_iters, cfg.map_max_iterations))))
+            avg_ms = ms / working
+            ab = algorithmic_bytes(name, counts, n_map_pts, mean_iters)
+            table[name] = {"ms_total": round(ms, 4), "launches": n, "working_launches": working, "avg_ms": round(avg_ms, 5),
+                           "algorithmic_bytes": ab, "achieved_gbs": round(ab / (avg_ms * 1e-3) / 1e9, 2) if avg_ms > 0 else None,
+                           "frac": round(ab / (avg_ms * 1e-3) / 1e9 / peak, 4) if avg_ms > 0 else None}
+        dom = max(table, key=lambda k: table[k]["ms_total"])
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
+            traffic = tr.get(dom, {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": table[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": table[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                    "share_of_step": round(table[dom]["ms_total"] / dev_ms, 4)}
+        out = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "hdl64_scan_to_map_1M: HDL-64-shaped scans (64x1800) -> organise + feature extraction + "
+                                   "scan-to-map registration (<=10 GN iterations, 5-NN on a 1M-point voxel-hash map) + eigen-degeneracy "
+                                   "+ D-opt gate", "scans_per_step_per_gpu": B, "points_per_scan": int(n_pts // B),
+                       "map_points": int(n_map_pts), "parallelism": "frame-range dp%d" % world,
+                       "l2": "inputs %.0f MB per step > 126 MB L2" % (h2d_bytes / 1e6), "mean_gn_iterations": round(mean_iters, 2),
+                       "pool": "%d distinct scans cycled" % POOL},
+            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
+                    "ms_per_step": round(e2e_ms / args.steps, 4), "wall_ms": round(e2e_wall_ms, 3), "device_ms": round(e2e_dev_ms, 3)},
+            "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+            "roofline": roofline,
+            "stages": table,
+            "latency": {"p50_ms_per_scan": None if p50 is None else round(p50, 4), "p95_ms_per_scan": None if p95 is None else round(p95, 4),
+                        "what": "vlo_process_scan: one online tick (H2D + organise + extract + scan-to-scan + scan-to-map + results D2H)"},
+            "ok_registrations": ok, "mean_corr": [float(np.mean(res["n_corr_edge"])), float(np.mean(res["n_corr_plane"]))],
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(raws_pool, seeds_pool, cm, sm, threads=1, n_scans=args.cpu_sample)
+        print(json.dumps(out))
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(raws_pool, seeds_pool, cm, sm, threads: int, n_scans: int):
+    """The oracle (CPU restatement of the reference path, kd-tree based) on a bounded sample."""
+    from oracle import oracle as orc
+    cfg = orc.default_config("HDL-64E", deskew=0)
+    m = orc.CpuMap(cfg, cm, sm)
+    raws = [raws_pool[k % len(raws_pool)] for k in range(n_scans)]
+    seeds = np.stack([seeds_pool[k % len(raws_pool)] for k in range(n_scans)])
+    m.batch_scan_to_map(raws[:max(1, threads)], seeds[:max(1, threads)], threads)       # warm-up (page in, caches)
+    t0 = time.perf_counter()
+    res = m.batch_scan_to_map(raws, seeds, threads)
+    dt = time.perf_counter() - t0
+    m.close()
+    return {"value": round(n_scans / dt, 3), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d HDL-64 scans of the same workload (organise + extract + scan-to-map on the 1M map, kd-trees prebuilt), %.1f s"
+                      % (n_scans, dt), "mean_gn_iterations": float(np.mean([r["iterations"] for r in res]))}
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement on all host threads; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    raws_pool, seeds_pool, cm, sm = make_workload(POOL, 0)
+    from oracle import oracle as orc
+    cfg = orc.default_config("HDL-64E", deskew=0)
+    m = orc.CpuMap(cfg, cm, sm)
+    n_per_step = max(threads, 4) * 2
+    raws = [raws_pool[k % POOL] for k in range(n_per_step)]
+    seeds = np.stack([seeds_pool[k % POOL] for k in range(n_per_step)])
+    for _ in range(min(args.warmup, 2)):
+        m.batch_scan_to_map(raws, seeds, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = m.batch_scan_to_map(raws, seeds, threads)
+    dt = time.perf_counter() - t0
+    m.close()
+    value = n_per_step * args.steps / dt
+    out = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "hdl64_scan_to_map_1M (CPU restatement of the reference path: oracle/, kd-tree based)",
+                   "scans_per_step": n_per_step, "map_points": int(len(cm) + len(sm))},
+        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d scans per step x %d steps, frames spread over %d threads" % (n_per_step, args.steps, threads)},
+        "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "mean_gn_iterations": float(np.mean([r["iterations"] for r in res])),
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=128, help="scans per step per GPU")
+    ap.add_argument("--impl", default="vlo", choices=["vlo", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=96, help="scans in the bounded CPU-baseline sample (~15 s on one core)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "vlo" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

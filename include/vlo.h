@@ -1,6 +1,6 @@
 /* vlo.h -- C-ABI of libvlo.so: the B200 (sm_100a) LiDAR-odometry hot path behind gtsam_fusion.
  *
- * Plain C, caller-owned buffers, int status codes, no exceptions, no torch types.  One handle =
+ * Plain C, caller-owned buffers, int status codes, no exceptions, only C scalar and pointer types.  One handle =
  * one CUDA stream + all device memory; re-entrant per handle, not thread-safe within a handle
  * (the reference's callers are single-threaded spinners: gtsam_fusion/src/gtsam_fusion_node.cpp:101,
  * gtsam_fusion/src/degerate_odometry_filter.cpp:50).
@@ -127,6 +127,15 @@ const char *vlo_version(void);
 int         vlo_synchronize(vlo_handle *h);
 /* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
 long long   vlo_launch_count(const vlo_handle *h);
+
+/* per-stage device timing (CUDA events on the handle's stream around every launch group); stage
+ * names via vlo_stage_name(0 .. vlo_stage_count()-1); vlo_get_stage_times drains the accumulators */
+int         vlo_set_profiling(vlo_handle *h, int enable);
+int         vlo_stage_count(void);
+const char *vlo_stage_name(int stage);
+int         vlo_get_stage_times(vlo_handle *h, float *ms, int *launches);
+/* the handle's cudaStream_t (so a caller can record its own events on it) */
+void       *vlo_stream(vlo_handle *h);
 
 /* ---------------------------------------------------------------- scans (batch of B <= max_scans) */
 /* raw: concatenated clouds, `stride_floats` float32 per point, x y z first (ROS axes), scan s owns

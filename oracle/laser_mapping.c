@@ -208,10 +208,35 @@ static void fill_terms(const float *row, float bval, float w, float *t)
     t[e++] = w * w;
 }
 
+static void mapping_register_impl(const orc_config *c,
+                          const orc_pt *corner_q, int n_cq, const orc_pt *surf_q, int n_sq,
+                          const orc_pt *corner_map, int n_cm, const orc_pt *surf_map, int n_sm,
+                          const float *seed, int use_kdtree, const orc_kdtree *kc_in, const orc_kdtree *ks_in,
+                          orc_reg_result *res, int *trace_idx, float *trace_T);
+
 void orc_mapping_register(const orc_config *c,
                           const orc_pt *corner_q, int n_cq, const orc_pt *surf_q, int n_sq,
                           const orc_pt *corner_map, int n_cm, const orc_pt *surf_map, int n_sm,
                           const float *seed, int use_kdtree,
+                          orc_reg_result *res, int *trace_idx, float *trace_T)
+{
+    mapping_register_impl(c, corner_q, n_cq, surf_q, n_sq, corner_map, n_cm, surf_map, n_sm, seed, use_kdtree, NULL, NULL, res, trace_idx, trace_T);
+}
+
+/* same, with prebuilt kd-trees over the map clouds (CPU baseline: the trees are reused across frames) */
+void orc_mapping_register_trees(const orc_config *c,
+                                const orc_pt *corner_q, int n_cq, const orc_pt *surf_q, int n_sq,
+                                const orc_pt *corner_map, int n_cm, const orc_kdtree *kc,
+                                const orc_pt *surf_map, int n_sm, const orc_kdtree *ks,
+                                const float *seed, orc_reg_result *res)
+{
+    mapping_register_impl(c, corner_q, n_cq, surf_q, n_sq, corner_map, n_cm, surf_map, n_sm, seed, 1, kc, ks, res, NULL, NULL);
+}
+
+static void mapping_register_impl(const orc_config *c,
+                          const orc_pt *corner_q, int n_cq, const orc_pt *surf_q, int n_sq,
+                          const orc_pt *corner_map, int n_cm, const orc_pt *surf_map, int n_sm,
+                          const float *seed, int use_kdtree, const orc_kdtree *kc_in, const orc_kdtree *ks_in,
                           orc_reg_result *res, int *trace_idx, float *trace_T)
 {
     memset(res, 0, sizeof(*res));
@@ -224,8 +249,9 @@ void orc_mapping_register(const orc_config *c,
         for (int a = 0; a < 6; a++) res->transform[a] = T[a];
         return;
     }
-    orc_kdtree *kc = use_kdtree ? orc_kdtree_build(corner_map, n_cm) : NULL;
-    orc_kdtree *ks = use_kdtree ? orc_kdtree_build(surf_map, n_sm) : NULL;
+    orc_kdtree *kc_own = (use_kdtree && !kc_in) ? orc_kdtree_build(corner_map, n_cm) : NULL;
+    orc_kdtree *ks_own = (use_kdtree && !ks_in) ? orc_kdtree_build(surf_map, n_sm) : NULL;
+    const orc_kdtree *kc = kc_in ? kc_in : kc_own, *ks = ks_in ? ks_in : ks_own;
     float *terms = (float *)malloc(sizeof(float) * (size_t)(Q + 1) * NTERM);
     for (; it < c->map_max_iterations; it++) {
         float trig[6];
@@ -265,6 +291,6 @@ void orc_mapping_register(const orc_config *c,
     }
     res->iterations = it;
     for (int a = 0; a < 6; a++) res->transform[a] = T[a];
-    orc_kdtree_free(kc); orc_kdtree_free(ks);
+    orc_kdtree_free(kc_own); orc_kdtree_free(ks_own);
     free(terms);
 }

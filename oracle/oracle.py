@@ -303,3 +303,33 @@ def pose_diff(before7, after7):
     lib().orc_pose_diff(_p(np.ascontiguousarray(before7, np.float64)), _p(np.ascontiguousarray(after7, np.float64)),
                         _p(out))
     return out
+
+
+class CpuMap:
+    """Map clouds + kd-trees built once (bench.py's CPU baseline and --impl reference legs)."""
+
+    def __init__(self, cfg, corner_map, surf_map):
+        self.cfg = cfg
+        self.cm = np.ascontiguousarray(corner_map, np.float32)
+        self.sm = np.ascontiguousarray(surf_map, np.float32)
+        L = lib()
+        L.orc_map_create.restype = C.c_void_p
+        self._m = C.c_void_p(L.orc_map_create(C.byref(cfg), _p(self.cm), self.cm.shape[0], _p(self.sm), self.sm.shape[0]))
+
+    def close(self):
+        if self._m:
+            lib().orc_map_free(self._m)
+            self._m = None
+
+    def batch_scan_to_map(self, raws, seeds, n_threads=1):
+        """organise + extract + scan-to-map registration (+ D-opt gate) for every frame; frames are
+        spread over n_threads threads."""
+        raws = [np.ascontiguousarray(r, np.float32) for r in raws]
+        stride = raws[0].shape[1]
+        offs = np.zeros(len(raws) + 1, np.int32)
+        offs[1:] = np.cumsum([r.shape[0] for r in raws])
+        raw = np.concatenate(raws, axis=0)
+        seeds = np.ascontiguousarray(seeds, np.float32).reshape(len(raws), 6)
+        res = (RegResult * len(raws))()
+        lib().orc_batch_scan_to_map(self._m, _p(raw), _p(offs), len(raws), stride, _p(seeds), res, int(n_threads))
+        return [_result_dict(r) for r in res]

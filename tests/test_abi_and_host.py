@@ -1,0 +1,104 @@
+"""CPU-side checks of the drop-in boundary: libvlo.so loads, exports every symbol include/vlo.h
+declares, struct layouts match the header, host helpers work, and the product path fails loudly
+without a GPU instead of falling back to the CPU."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    from vil_sensor_fusion_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        g.build()
+    return _lib.load()
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "vlo.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(vlo_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    from vil_sensor_fusion_b200 import _lib
+    names = _declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), "libvlo.so does not export %s" % n
+        assert n in _lib.SYMBOLS, "%s is declared in vlo.h but not bound in _lib.SYMBOLS" % n
+    for n in _lib.SYMBOLS:
+        assert n in names, "%s is bound but not declared in include/vlo.h" % n
+
+
+def test_struct_layouts_match_header(tmp_path):
+    from vil_sensor_fusion_b200 import _lib
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "vlo.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(vlo_config),sizeof(vlo_result),sizeof(vlo_feature_counts),sizeof(vlo_preint),'
+                   'offsetof(vlo_config,cov_accel),offsetof(vlo_result,cov),offsetof(vlo_preint,cov));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    exp = [C.sizeof(_lib.Config), C.sizeof(_lib.Result), C.sizeof(_lib.FeatureCounts), C.sizeof(_lib.Preint),
+           _lib.Config.cov_accel.offset, _lib.Result.cov.offset, _lib.Preint.cov.offset]
+    assert got == exp
+
+
+def test_header_is_plain_c_and_cites_reference():
+    hdr = open(os.path.join(ROOT, "include", "vlo.h")).read()
+    assert "torch" not in hdr.lower() and 'extern "C"' in hdr
+    for cite in ("degerate_odometry_filter.cpp", "IMUManager.cpp:27-74", "SensorManagerRos.cpp:122-158", "loam_params.yaml"):
+        assert cite in hdr
+
+
+def test_default_config_mirrors_reference_yaml(lib):
+    from vil_sensor_fusion_b200 import api
+    c = api.default_config("HDL-64E")
+    assert (c.n_rings, c.feature_regions, c.curvature_region, c.max_corner_sharp, c.max_corner_less_sharp, c.max_surface_flat) == (64, 6, 5, 2, 20, 4)
+    assert (c.odom_max_iterations, c.map_max_iterations, c.odom_degen_eig, c.map_degen_eig) == (25, 10, 30.0, 40.0)
+    assert abs(c.dopt_rot_threshold - 11.5) < 1e-6 and abs(c.dopt_trans_threshold - 28.9) < 1e-5
+    assert (c.cov_accel, c.cov_bias_acc, c.cov_integration) == (1e-6, 1e-4, 1e-8)
+    with pytest.raises(ValueError):
+        api.default_config("no-such-lidar")
+
+
+def test_host_helpers_without_gpu(lib, orc):
+    from vil_sensor_fusion_b200 import api
+    np.testing.assert_allclose(api.pose_diff([0, 0, 0, 1, 0, 0, 0], [1, 1, 1, 1, 0, 0, 0]), [1, 1, 1, 1, 0, 0, 0])   # UnitTests.cpp:228-233
+    rng = np.random.default_rng(0)
+    A = rng.normal(size=(50, 6)) * np.array([40, 40, 40, 4, 4, 4])
+    H = (A.T @ A).astype(np.float32)
+    ok, lr, lt = api.dopt_gate(H)
+    oko, lro, lto = orc.dopt_gate(H)
+    assert ok == oko
+    np.testing.assert_allclose([lr, lt], [lro, lto], rtol=1e-6)
+    st = api.hessian_stack(np.zeros(7, api.RESULT_DTYPE))
+    assert st.shape == (6, 6, 7) and st.dtype == np.float64        # make_prettier_graphs.py:440 layout
+
+
+def test_no_cpu_fallback_without_device(lib):
+    """On a box without a GPU the product refuses to run (VLO_ERR_NO_DEVICE); it never routes to the oracle."""
+    import torch
+    from vil_sensor_fusion_b200 import api
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(api.VloError) as e:
+        api.Handle(api.default_config("VLP-16"))
+    assert e.value.code == -4
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "vil_sensor_fusion_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt and "vlo_oracle.h" not in txt, f

@@ -61,6 +61,11 @@ SYMBOLS = {
     "vlo_version": (C.c_char_p, []),
     "vlo_synchronize": (C.c_int, [_VP]),
     "vlo_launch_count": (C.c_longlong, [_VP]),
+    "vlo_set_profiling": (C.c_int, [_VP, C.c_int]),
+    "vlo_stage_count": (C.c_int, []),
+    "vlo_stage_name": (C.c_char_p, [C.c_int]),
+    "vlo_get_stage_times": (C.c_int, [_VP, _VP, _VP]),
+    "vlo_stream": (C.c_void_p, [_VP]),
     "vlo_scans_upload": (C.c_int, [_VP, _VP, _VP, C.c_int, C.c_int, C.c_int]),
     "vlo_scans_organise": (C.c_int, [_VP]),
     "vlo_scans_extract": (C.c_int, [_VP]),

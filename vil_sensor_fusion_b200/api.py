@@ -120,6 +120,20 @@ class Handle:
     def synchronize(self):
         self._check(self.lib.vlo_synchronize(self._h))
 
+    def set_profiling(self, enable: bool = True):
+        self._check(self.lib.vlo_set_profiling(self._h, int(enable)))
+
+    def stage_times(self):
+        """{stage name: (accumulated ms, launch groups)} since the last call."""
+        n = self.lib.vlo_stage_count()
+        ms = np.zeros(n, np.float32)
+        cnt = np.zeros(n, np.int32)
+        self._check(self.lib.vlo_get_stage_times(self._h, _ptr(ms), _ptr(cnt)))
+        return {self.lib.vlo_stage_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
+
+    def stream_ptr(self) -> int:
+        return int(self.lib.vlo_stream(self._h) or 0)
+
     def launch_count(self) -> int:
         return int(self.lib.vlo_launch_count(self._h))
 

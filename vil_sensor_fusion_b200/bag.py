@@ -1,0 +1,73 @@
+"""Offline whole-bag reprocessing: independent scan-pair (or scan-to-map) registrations over a frame
+range, sharded by contiguous frame range across ranks (one process per GPU), with ONE exchange step:
+the final gather of the per-frame result records.  No collective in the per-scan path.
+
+The gathered `(6,6,T)` Hessian stack is what the reference's analysis tooling consumes
+(vil_fusion/python/make_prettier_graphs.py:411-474 `numpify_diagnostics`, :547-576 `apply_degen_function`).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .api import RESULT_DTYPE, Handle, hessian_stack  # noqa: F401
+
+
+def frame_range(n_frames: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous range [lo, hi) of rank `rank`: [r*N/G, (r+1)*N/G)."""
+    return (n_frames * rank) // world, (n_frames * (rank + 1)) // world
+
+
+def reprocess_pairs(h: Handle, get_scan, first: int, last: int, batch: int, seeds=None) -> np.ndarray:
+    """Registers every consecutive pair (k, k+1) with first <= k < last-1 from `seeds[k]` (or zero):
+    frames are processed in resident batches of `batch` scans, overlapping by one frame.
+    get_scan(k) -> float32 (n, stride) raw cloud.  Returns a RESULT_DTYPE array of length last-first-1."""
+    out = []
+    k = first
+    while k < last - 1:
+        hi = min(last, k + batch)
+        scans = [get_scan(i) for i in range(k, hi)]
+        h.upload(scans)
+        h.organise()
+        h.extract()
+        n = hi - k
+        sd = None if seeds is None else np.asarray(seeds[k - first:k - first + n - 1], np.float32)
+        out.append(h.register_pairs(np.arange(n - 1), np.arange(1, n), seeds=sd))
+        k = hi - 1
+    return np.concatenate(out) if out else np.zeros(0, RESULT_DTYPE)
+
+
+def reprocess_map(h: Handle, get_scan, first: int, last: int, batch: int, seeds) -> np.ndarray:
+    """Scan-to-map registration of frames [first, last) against the handle's resident map."""
+    out = []
+    for k in range(first, last, batch):
+        hi = min(last, k + batch)
+        h.upload([get_scan(i) for i in range(k, hi)])
+        h.organise()
+        h.extract()
+        out.append(h.register_map(np.arange(hi - k), np.asarray(seeds[k - first:hi - first], np.float32)))
+    return np.concatenate(out) if out else np.zeros(0, RESULT_DTYPE)
+
+
+def gather_results(local: np.ndarray, group=None, device=None) -> np.ndarray:
+    """The single exchange step: all ranks contribute their result records, every rank receives the
+    concatenation in rank (= frame) order.  Works on NCCL (device tensors over NVLink) and gloo (CPU)."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local.copy()
+    world = dist.get_world_size(group)
+    backend = dist.get_backend(group)
+    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu"))
+    n_local = torch.tensor([local.shape[0]], dtype=torch.int64, device=dev)
+    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(counts, n_local, group=group)
+    counts = [int(c.item()) for c in counts]
+    nmax = max(counts)
+    item = RESULT_DTYPE.itemsize
+    buf = np.zeros(nmax * item, np.uint8)
+    buf[:local.shape[0] * item] = np.frombuffer(np.ascontiguousarray(local).tobytes(), np.uint8)
+    mine = torch.from_numpy(buf).to(dev)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    out = [np.frombuffer(p.cpu().numpy().tobytes()[:c * item], RESULT_DTYPE) for p, c in zip(parts, counts)]
+    return np.concatenate(out)

@@ -161,12 +161,14 @@ int vlo_launch_organise(vlo_handle *h)
     p.factor = (float)(h->cfg.n_rings - 1) / (h->cfg.upper_deg - h->cfg.lower_deg);
     p.scan_period = h->cfg.scan_period; p.N = h->cfg.max_points; p.tiles = h->tiles_per_scan;
     int B = sb.scan_count; p.scan_first = sb.scan_first;
+    vlo_prof_begin(h, ST_ORGANISE);
     k0_bounds<<<(B + 127) / 128, 128, 0, h->stream>>>(p, sb.ori_bounds, sb.first_half, B);
     dim3 grid(h->tiles_per_scan, B);
     k0_classify<<<grid, K0_TILE, 0, h->stream>>>(p, sb.ori_bounds, sb.first_half, sb.tile_hist);
     k0_scan<<<B, 256, 0, h->stream>>>(p, sb.tile_hist, sb.ring_start, sb.counts);
     k0_scatter<<<grid, K0_TILE, 0, h->stream>>>(p, sb.ori_bounds, sb.first_half, sb.tile_hist, sb.ring_start,
                                                 sb.cloud, sb.src_index);
+    vlo_prof_end(h, ST_ORGANISE);
     h->launches += 4;
     VLO_CUDA(cudaGetLastError());
     return VLO_OK;

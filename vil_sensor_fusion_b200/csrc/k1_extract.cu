@@ -437,7 +437,7 @@ int vlo_launch_extract(vlo_handle *h)
     }
     p.scan_first = sb.scan_first;
     dim3 grid(c.n_rings, sb.scan_count);
-    k1_extract<<<grid, K1_THREADS, smem, h->stream>>>(p);
+    VLO_PROF(h, ST_EXTRACT, (k1_extract<<<grid, K1_THREADS, smem, h->stream>>>(p)));
     K1bParams q;
     q.cloud = sb.cloud; q.N = c.max_points; q.n_rings = c.n_rings; q.NR = c.feature_regions;
     q.max_sharp = c.max_corner_sharp; q.max_lsharp = c.max_corner_less_sharp; q.max_flat = c.max_surface_flat;
@@ -448,7 +448,7 @@ int vlo_launch_extract(vlo_handle *h)
     q.cap_sharp = h->cap_sharp; q.cap_lsharp = h->cap_lsharp; q.cap_flat = h->cap_flat;
     q.lsharp_ring_start = sb.lsharp_ring_start; q.lflat_ring_start = sb.lflat_ring_start;
     q.scan_first = sb.scan_first;
-    k1b_compact<<<sb.scan_count, 256, 0, h->stream>>>(q);
+    VLO_PROF(h, ST_COMPACT, (k1b_compact<<<sb.scan_count, 256, 0, h->stream>>>(q)));
     h->launches += 2;
     VLO_CUDA(cudaGetLastError());
     return VLO_OK;

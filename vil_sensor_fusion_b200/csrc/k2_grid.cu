@@ -89,12 +89,14 @@ __global__ void __launch_bounds__(256) k2_scatter(GridSet gs, GridSource src, in
 int vlo_grid_build(vlo_handle *h, const GridSet &gs, const GridSource &src, int g_first, int n_grids, int n_slots)
 {
     if (n_grids <= 0) return VLO_OK;
+    vlo_prof_begin(h, ST_GRID_BUILD);
     VLO_CUDA(cudaMemsetAsync(gs.keys + (size_t)g_first * gs.ts, 0xFF, sizeof(unsigned long long) * (size_t)n_grids * gs.ts, h->stream));
     VLO_CUDA(cudaMemsetAsync(gs.cnt + (size_t)g_first * gs.ts, 0, sizeof(int) * (size_t)n_grids * gs.ts, h->stream));
     dim3 grid((n_slots + 255) / 256, n_grids);
     k2_count<<<grid, 256, 0, h->stream>>>(gs, src, n_slots, g_first);
     k2_scan<<<n_grids, 1024, 0, h->stream>>>(gs, g_first);
     k2_scatter<<<grid, 256, 0, h->stream>>>(gs, src, n_slots, g_first);
+    vlo_prof_end(h, ST_GRID_BUILD);
     h->launches += 3;
     VLO_CUDA(cudaGetLastError());
     return VLO_OK;

@@ -401,8 +401,10 @@ int vlo_launch_register_pairs(vlo_handle *h, int n_pairs, const float *d_seeds, 
     h->launches += 1;
     if (d_last_T) {
         dim3 g0((h->cap_lsharp + 255) / 256, n_pairs), g1((c.max_points + 255) / 256, n_pairs);
+        vlo_prof_begin(h, ST_TO_END);
         k3_to_end<<<g0, 256, 0, h->stream>>>(p, h->pair_last, d_last_T, n_pairs, 0);
         k3_to_end<<<g1, 256, 0, h->stream>>>(p, h->pair_last, d_last_T, n_pairs, 1);
+        vlo_prof_end(h, ST_TO_END);
         h->launches += 2;
         h->grids_valid = 0;
     }
@@ -412,13 +414,13 @@ int vlo_launch_register_pairs(vlo_handle *h, int n_pairs, const float *d_seeds, 
     dim3 ga((n_warps * 32 + 255) / 256, n_pairs);
     size_t trace_stride = (size_t)n_pairs * (h->cap_sharp * 2 + h->cap_flat * 3);
     for (int base = 0, round = 0; base < c.odom_max_iterations; base += 5, round++) {
-        k3_assoc<<<ga, 256, 0, h->stream>>>(p, n_pairs);
+        VLO_PROF(h, ST_ASSOC, (k3_assoc<<<ga, 256, 0, h->stream>>>(p, n_pairs)));
         if (h->trace && round < 5) {
             int *dst = h->pair_trace + (size_t)round * trace_stride;
             VLO_CUDA(cudaMemcpyAsync(dst, h->pair_cidx, sizeof(int) * (size_t)n_pairs * h->cap_sharp * 2, cudaMemcpyDeviceToDevice, h->stream));
             VLO_CUDA(cudaMemcpyAsync(dst + (size_t)n_pairs * h->cap_sharp * 2, h->pair_sidx, sizeof(int) * (size_t)n_pairs * h->cap_flat * 3, cudaMemcpyDeviceToDevice, h->stream));
         }
-        k3_gn<<<n_pairs, GN_THREADS, 0, h->stream>>>(p, base, 5);
+        VLO_PROF(h, ST_GN, (k3_gn<<<n_pairs, GN_THREADS, 0, h->stream>>>(p, base, 5)));
         h->launches += 2;
     }
     VLO_CUDA(cudaGetLastError());

@@ -381,9 +381,9 @@ int vlo_launch_register_map(vlo_handle *h, const int *d_scans, int n, const floa
     int qmax = h->map_qmax > 0 ? h->map_qmax : p.qcap;
     dim3 gk((qmax * 32 + 255) / 256, n), gl((qmax + LIN_THREADS - 1) / LIN_THREADS, n);
     for (int it = 0; it < c.map_max_iterations; it++) {
-        k5_knn<<<gk, 256, 0, h->stream>>>(p);
-        k5_lin<<<gl, LIN_THREADS, 0, h->stream>>>(p);
-        k5_solve<<<n, SOLVE_THREADS, 0, h->stream>>>(p, it);
+        VLO_PROF(h, ST_MAP_KNN, (k5_knn<<<gk, 256, 0, h->stream>>>(p)));
+        VLO_PROF(h, ST_MAP_LIN, (k5_lin<<<gl, LIN_THREADS, 0, h->stream>>>(p)));
+        VLO_PROF(h, ST_MAP_SOLVE, (k5_solve<<<n, SOLVE_THREADS, 0, h->stream>>>(p, it)));
         h->launches += 3;
     }
     VLO_CUDA(cudaGetLastError());

@@ -216,7 +216,7 @@ int vlo_launch_imu(vlo_handle *h, const double *d_t, const double *d_acc, const 
     ImuParamsDev prm = { h->cfg.cov_accel, h->cfg.cov_gyro, h->cfg.cov_integration, h->cfg.cov_bias_acc, h->cfg.cov_bias_omega,
                          h->cfg.cov_bias_acc_omega_int };
     int blocks = (n_factors + IMU_WARPS - 1) / IMU_WARPS;
-    k6_imu_preintegrate<<<blocks, IMU_WARPS * 32, 0, h->stream>>>(prm, d_t, d_acc, d_gyro, n_samples, d_t0, d_t1, d_bias, n_factors, d_out);
+    VLO_PROF(h, ST_IMU, (k6_imu_preintegrate<<<blocks, IMU_WARPS * 32, 0, h->stream>>>(prm, d_t, d_acc, d_gyro, n_samples, d_t0, d_t1, d_bias, n_factors, d_out)));
     h->launches += 1;
     VLO_CUDA(cudaGetLastError());
     return VLO_OK;

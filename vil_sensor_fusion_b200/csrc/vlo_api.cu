@@ -94,7 +94,7 @@ extern "C" int vlo_create(const vlo_config *cfg, vlo_handle **out)
     h->map_partials = nullptr; h->map_idx5 = nullptr; h->map_T = h->map_seed = nullptr; h->map_state = h->map_ncorr = h->map_scans = nullptr;
     h->map_result = nullptr; h->map_qmax = 0; h->last_n_map = 0; h->last_n_pairs = 0;
     h->imu_buf = nullptr; h->imu_buf_bytes = 0; h->imu_out = nullptr; h->imu_out_cap = 0;
-    h->online_have_last = 0; h->online_slot = 0;
+    h->online_have_last = 0; h->online_slot = 0; h->prof_enabled = 0; h->prof_used = 0;
     memset(h->online_T, 0, sizeof(h->online_T)); memset(h->online_sum, 0, sizeof(h->online_sum));
     memset(h->online_map_bef, 0, sizeof(h->online_map_bef)); memset(h->online_map_aft, 0, sizeof(h->online_map_aft)); h->online_ticks = 0;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return VLO_ERR_CUDA; }
@@ -164,6 +164,7 @@ extern "C" void vlo_destroy(vlo_handle *h)
     for (void *p : ptrs) if (p) cudaFree(p);
     free_gridset(h->gs_corner); free_gridset(h->gs_surf); free_gridset(h->gs_map[0]); free_gridset(h->gs_map[1]);
     if (h->pinned) cudaFreeHost(h->pinned);
+    for (auto &e : h->prof_events) cudaEventDestroy(e);
     cudaStreamDestroy(h->stream);
     delete h;
 }

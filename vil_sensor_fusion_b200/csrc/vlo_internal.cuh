@@ -103,12 +103,22 @@ struct vlo_handle {
     int map_qmax, last_n_map;
     // IMU staging (grown on demand)
     double *imu_buf; size_t imu_buf_bytes; vlo_preint *imu_out; int imu_out_cap;
+    // stage profiling
+    int prof_enabled; std::vector<cudaEvent_t> prof_events; std::vector<int> prof_stage; size_t prof_used;
     // pinned staging
     void *pinned; size_t pinned_bytes;
     // online state
     int online_have_last; float online_T[6]; float online_sum[6]; float online_map_bef[6], online_map_aft[6];
     int online_slot; long long online_ticks;
 };
+
+// per-stage device timing (bench.py's roofline leg): CUDA events on the handle's stream around
+// every launch group, summed per stage by vlo_get_stage_times
+enum VloStage { ST_ORGANISE = 0, ST_EXTRACT, ST_COMPACT, ST_GRID_BUILD, ST_TO_END, ST_ASSOC, ST_GN, ST_MAP_KNN, ST_MAP_LIN,
+                ST_MAP_SOLVE, ST_IMU, ST_COUNT };
+void vlo_prof_begin(vlo_handle *h, int stage);
+void vlo_prof_end(vlo_handle *h, int stage);
+#define VLO_PROF(h, stage, stmt) do { vlo_prof_begin(h, stage); stmt; vlo_prof_end(h, stage); } while (0)
 
 #define VLO_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return VLO_ERR_CUDA; } } while (0)

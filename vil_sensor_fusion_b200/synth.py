@@ -419,3 +419,70 @@ def loam_map_pose(R_ros, p_ros) -> np.ndarray:
     R = _M_ROS2LOAM @ R_ros @ _M_ROS2LOAM.T
     t = _M_ROS2LOAM @ p_ros
     return np.concatenate([loam_euler_from_R(R), t])
+
+
+def make_voxel_map(scene: Scene, n_points: int, seed: int = 1, surf_leaf: float = 0.4, corner_leaf: float = 0.2,
+                   tile_pitch=(45.0, 35.0)):
+    """Map clouds at LOAM's own map density (loam_params.yaml:47-48: cornerFilterSize 0.2, surfaceFilterSize
+    0.4): every scene surface is covered by a jittered lattice with one point per `surf_leaf` cell and every
+    edge by one point per `corner_leaf`; the scene is then replicated on a grid of tiles (a building of
+    identical rooms) until the map holds ~n_points, so a 1M-point map stays at realistic density while only
+    the tile around the origin is ever observed.  Returns (corner, surf) float32 (N,4), LOAM axes.
+    """
+    g = np.random.default_rng(seed)
+    lo, hi = _scene_bounds(scene, 60.0)
+    surf = []
+
+    def lattice(u0, u1, v0, v1, leaf):
+        nu, nv = max(int((u1 - u0) / leaf), 1), max(int((v1 - v0) / leaf), 1)
+        uu, vv = np.meshgrid(u0 + (np.arange(nu) + 0.5) * leaf, v0 + (np.arange(nv) + 0.5) * leaf, indexing="ij")
+        uu = uu + g.uniform(-0.3, 0.3, uu.shape) * leaf
+        vv = vv + g.uniform(-0.3, 0.3, vv.shape) * leaf
+        return uu.ravel(), vv.ravel()
+
+    for pl in scene.planes:
+        ax = int(np.argmax(np.abs(pl[:3])))
+        o = [a for a in range(3) if a != ax]
+        u, v = lattice(lo[o[0]], hi[o[0]], lo[o[1]], hi[o[1]], surf_leaf)
+        p = np.empty((u.size, 3))
+        p[:, ax] = -pl[3] * pl[ax]
+        p[:, o[0]] = u
+        p[:, o[1]] = v
+        surf.append(p)
+    for cx, cy, r in scene.cylinders:
+        th, z = lattice(0.0, 2 * math.pi * r, lo[2], hi[2], surf_leaf)
+        surf.append(np.stack([cx + r * np.cos(th / r), cy + r * np.sin(th / r), z], -1))
+    for b in scene.boxes:
+        for ax in range(3):
+            o = [a for a in range(3) if a != ax]
+            for side in (0, 1):
+                if ax == 2 and side == 0:
+                    continue
+                u, v = lattice(b[o[0]], b[3 + o[0]], b[o[1]], b[3 + o[1]], surf_leaf)
+                p = np.empty((u.size, 3))
+                p[:, ax] = b[ax + 3 * side]
+                p[:, o[0]] = u
+                p[:, o[1]] = v
+                surf.append(p)
+    surf = np.concatenate(surf)
+    corner = []
+    for a, b in _scene_edges(scene, (lo, hi)):
+        L = np.linalg.norm(b - a)
+        n = max(int(L / corner_leaf), 1)
+        t = ((np.arange(n) + 0.5) / n)[:, None]
+        corner.append(a[None] * (1 - t) + b[None] * t + g.uniform(-0.02, 0.02, (n, 3)))
+    corner = np.concatenate(corner)
+    per_tile = len(surf) + len(corner)
+    n_tiles = max(1, int(round(n_points / per_tile)))
+    side = int(math.ceil(math.sqrt(n_tiles)))
+    offs = []
+    for k in range(n_tiles):          # spiral-free simple grid centred on the origin tile
+        i, j = k % side, k // side
+        offs.append(((i - side // 2) * tile_pitch[0], (j - side // 2) * tile_pitch[1]))
+    offs.sort(key=lambda o: abs(o[0]) + abs(o[1]))
+    cs, ss = [], []
+    for ox, oy in offs:
+        d = np.array([ox, oy, 0.0])
+        cs.append(corner + d)
+        ss.append(surf + d)
+    return _ros_to_loam4(np.concatenate(cs)), _ros_to_loam4(np.concatenate(ss))
