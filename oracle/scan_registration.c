@@ -136,7 +136,8 @@ static void mark_as_picked(const orc_pt *cloud, uint8_t *picked, int K, int idx,
  *   V1  output order = order of first appearance of the voxel along the ring (PCL: ascending linear
  *       voxel index, an artefact of its sort key);
  *   V2  centroid = voxel origin + mean of the members' offsets, the offsets quantised to 2^-20 m and
- *       summed as integers (order independent; <= 0.5 um from any float-order sum);
+ *       summed as integers (order independent; <= 0.5 um from any float-order sum), the mean taken
+ *       as one float32 division (float)sum / (float)count;
  *       intensity likewise on its fractional part (rel-time), integer part = ring. */
 typedef struct { int ix, iy, iz; int first; int cnt; long long sx, sy, sz, sw; } vox_grp;
 #define VOX_Q 1048576.0f
@@ -173,12 +174,13 @@ static int voxel_downsample(const orc_pt *in, int n, float leaf, orc_pt *out)
         g[gi].cnt++;
     }
     for (int k = 0; k < m; k++) {
-        double c = (double)g[k].cnt;
+        float c = (float)g[k].cnt;
+        const float q = 1.0f / 1048576.0f;
         float ox = (float)g[k].ix * leaf, oy = (float)g[k].iy * leaf, oz = (float)g[k].iz * leaf;
-        out[k].x = ox + (float)(((double)g[k].sx / c) * (1.0 / 1048576.0));
-        out[k].y = oy + (float)(((double)g[k].sy / c) * (1.0 / 1048576.0));
-        out[k].z = oz + (float)(((double)g[k].sz / c) * (1.0 / 1048576.0));
-        out[k].w = (float)(int)in[g[k].first].w + (float)(((double)g[k].sw / c) * (1.0 / 1048576.0));
+        out[k].x = ox + ((float)(int)g[k].sx / c) * q;
+        out[k].y = oy + ((float)(int)g[k].sy / c) * q;
+        out[k].z = oz + ((float)(int)g[k].sz / c) * q;
+        out[k].w = (float)(int)in[g[k].first].w + ((float)(int)g[k].sw / c) * q;
     }
     free(table); free(g);
     return m;

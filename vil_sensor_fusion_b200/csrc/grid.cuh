@@ -11,10 +11,17 @@
 // d2 = ((dx*dx) + (dy*dy)) + (dz*dz) in float32 (no FMA); shells of cells are visited outwards and
 // the search stops only when the k-th best distance is strictly inside the visited cube (minus a
 // slack that covers the rounding of floor(p * inv_cell)), so storage order never matters.
+//
+// Work distribution (round-1 ncu: the lane-per-cell version spent 30 % of its instructions in
+// divergent top-k insertions): the 32 lanes first resolve up to 32 cells of the shell (one hash
+// probe each), a warp scan turns the cell populations into one flat candidate range, and the lanes
+// then stride over that range -- every lane sees the same number of candidates whatever the
+// per-cell populations are.
 #pragma once
 #include "vlo_internal.cuh"
 
 #define GRID_EMPTY 0xFFFFFFFFFFFFFFFFull
+#define GRID_SCRATCH_INTS 64      // per-warp shared-memory scratch (inclusive prefix + base offsets)
 
 __device__ __forceinline__ unsigned long long grid_key(int ix, int iy, int iz)
 {
@@ -45,7 +52,7 @@ struct FilterAll {          // plain k-NN, ties -> lowest dense index
     __device__ __forceinline__ bool operator()(unsigned tag, unsigned &tie) const { tie = tag & 0xFFFFFFu; return true; }
 };
 // upstream's partner loops: forward indices first (ascending), then backward
-// (descending); `ring_lo..ring_hi` admissible rings, `skip_ring` excluded (or -1), `same_ring_only`.
+// (descending); `ring_lo..ring_hi` admissible rings, `skip_ring` excluded (or -1).
 struct FilterPartner {
     int ind;        // dense index of the nearest neighbour
     int ring_lo, ring_hi, skip_ring;
@@ -71,15 +78,17 @@ template <int K> struct TopK {
     }
     __device__ __forceinline__ void insert(unsigned dd, unsigned tt, unsigned tg) {
         if (!(dd < d[K - 1] || (dd == d[K - 1] && tt < t[K - 1]))) return;
-        d[K - 1] = dd; t[K - 1] = tt; tag[K - 1] = tg;
+        // walk down from the end shifting larger entries up; stop at the first smaller one
+        bool placed = false;
         #pragma unroll
         for (int i = K - 1; i > 0; i--) {
-            if (d[i] < d[i - 1] || (d[i] == d[i - 1] && t[i] < t[i - 1])) {
-                unsigned a = d[i]; d[i] = d[i - 1]; d[i - 1] = a;
-                a = t[i]; t[i] = t[i - 1]; t[i - 1] = a;
-                a = tag[i]; tag[i] = tag[i - 1]; tag[i - 1] = a;
+            if (!placed) {
+                bool up = dd < d[i - 1] || (dd == d[i - 1] && tt < t[i - 1]);
+                if (up) { d[i] = d[i - 1]; t[i] = t[i - 1]; tag[i] = tag[i - 1]; }
+                else { d[i] = dd; t[i] = tt; tag[i] = tg; placed = true; }
             }
         }
+        if (!placed) { d[0] = dd; t[0] = tt; tag[0] = tg; }
     }
     __device__ __forceinline__ void pop() {
         #pragma unroll
@@ -90,10 +99,11 @@ template <int K> struct TopK {
 
 // Warp-cooperative exact search.  All 32 lanes call it with the same query; on return every lane
 // holds the global K best in `best` (d = float bits of d2; tag == GRID_NOTAG means "none").
-// Candidates need d2 < dmax (strict) and must pass the filter.
+// Candidates need d2 < dmax (strict) and must pass the filter.  `scratch`: GRID_SCRATCH_INTS ints of
+// shared memory private to this warp.
 template <int K, typename Filter>
 __device__ void grid_search(const GridSet &gs, int g, float qx, float qy, float qz, float dmax,
-                            const Filter &flt, TopK<K> &best, int lane)
+                            const Filter &flt, TopK<K> &best, int lane, int *scratch)
 {
     const int *start = gs.start + (size_t)g * (gs.ts + 1);
     const float4 *sorted = gs.sorted + (size_t)g * gs.max_pts;
@@ -104,20 +114,37 @@ __device__ void grid_search(const GridSet &gs, int g, float qx, float qy, float 
         const int side = 2 * rho + 1, ncell = side * side * side;   // rho == 1 also covers the centre cell
         TopK<K> loc;
         if (lane == 0) loc = best; else loc.init(best.d[K - 1], best.t[K - 1]);
-        for (int c = lane; c < ncell; c += 32) {
-            int dx = c % side - rho, dy = (c / side) % side - rho, dz = c / (side * side) - rho;
-            if (rho > 1 && abs(dx) < rho && abs(dy) < rho && abs(dz) < rho) continue;   // interior: already visited
-            int slot = grid_find(gs, g, cx + dx, cy + dy, cz + dz);
-            if (slot < 0) continue;
-            int s0 = start[slot], s1 = start[slot + 1];
-            for (int k = s0; k < s1; k++) {
-                float4 p = sorted[k];
+        for (int c0 = 0; c0 < ncell; c0 += 32) {
+            const int c = c0 + lane;
+            int s0 = 0, n = 0;
+            if (c < ncell) {
+                int dx = c % side - rho, dy = (c / side) % side - rho, dz = c / (side * side) - rho;
+                bool shell = rho == 1 || abs(dx) == rho || abs(dy) == rho || abs(dz) == rho;   // interior: already visited
+                if (shell) {
+                    int slot = grid_find(gs, g, cx + dx, cy + dy, cz + dz);
+                    if (slot >= 0) { s0 = start[slot]; n = start[slot + 1] - s0; }
+                }
+            }
+            int inc = n;
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+            const int total = __shfl_sync(0xffffffffu, inc, 31);
+            if (total == 0) continue;
+            scratch[lane] = inc;                 // inclusive prefix of the cell populations
+            scratch[32 + lane] = s0 - (inc - n); // flat index j inside cell e maps to sorted[base[e] + j]
+            __syncwarp();
+            for (int j = lane; j < total; j += 32) {
+                int e = 0;                       // first cell whose inclusive prefix exceeds j
+                #pragma unroll
+                for (int step = 16; step >= 1; step >>= 1) if (scratch[e + step - 1] <= j) e += step;
+                float4 p = sorted[scratch[32 + e] + j];
                 float ddx = p.x - qx, ddy = p.y - qy, ddz = p.z - qz;
                 float d2 = (ddx * ddx + ddy * ddy) + ddz * ddz;
                 unsigned tie, tag = __float_as_uint(p.w);
                 if (!(d2 < dmax) || !flt(tag, tie)) continue;
                 loc.insert(__float_as_uint(d2), tie, tag);
             }
+            __syncwarp();
         }
         #pragma unroll
         for (int i = 0; i < K; i++) {

@@ -138,13 +138,102 @@ __device__ void k1_sector_greedy(const K1Params &p, const K1Smem &s, int lane, i
     }
 }
 
+// Register-resident variant (sectors of up to 32*MAXS points, i.e. every real lidar): each lane keeps
+// the curvature of its lane-strided points and two eligibility bit masks in registers, so a pick is
+// a local scan over MAXS registers + 2 REDUX + 1 ballot; shared memory is touched only to publish
+// the suppression marks.  Same selection order as k1_sector_greedy, bit for bit.
+template <int MAXS>
+__device__ void k1_sector_greedy_regs(const K1Params &p, const K1Smem &s, int lane, int sec, int sp, int ep, int start,
+                                      uint8_t *own, const uint8_t *prev, int view_prev_lo, int view_prev_hi, int b, int r)
+{
+    const int K = p.K;
+    size_t slot_base = ((size_t)(b * p.n_rings + r) * p.NR + sec);
+    unsigned cb[MAXS];
+    unsigned el_c = 0u, el_f = 0u;            // eligibility: corner (c > thr) / flat (c < thr), not picked
+    #pragma unroll
+    for (int k = 0; k < MAXS; k++) {
+        int i = sp + lane + 32 * k;
+        cb[k] = 0u;
+        if (i <= ep) {
+            float c = s.curv[i];
+            cb[k] = __float_as_uint(c);
+            bool pk = (s.flag[i] & 16) || own[i] || (i >= view_prev_lo && i <= view_prev_hi && prev[i]);
+            if (!pk && c > p.thr) el_c |= 1u << k;
+            if (!pk && c < p.thr) el_f |= 1u << k;
+        }
+    }
+    int n_sharp = 0, n_ls = 0, n_flat = 0;
+    for (int phase = 0; phase < 2; phase++) {
+        const int max_picks = phase == 0 ? p.max_lsharp : p.max_flat;
+        for (int pick = 0; pick < max_picks; pick++) {
+            int idx;
+            if (phase == 0) {                 // largest (curvature, index)
+                unsigned best_c = 0u; int best_k = -1;
+                #pragma unroll
+                for (int k = 0; k < MAXS; k++) if (((el_c >> k) & 1u) && cb[k] >= best_c) { best_c = cb[k]; best_k = k; }
+                unsigned m = __reduce_max_sync(0xffffffffu, best_k >= 0 ? best_c : 0u);
+                if (m == 0u) break;
+                int cand = (best_k >= 0 && best_c == m) ? sp + lane + 32 * best_k : -1;
+                idx = __reduce_max_sync(0xffffffffu, cand);
+            } else {                          // smallest (curvature, index)
+                unsigned best_c = 0xffffffffu; int best_k = -1;
+                #pragma unroll
+                for (int k = MAXS - 1; k >= 0; k--) if (((el_f >> k) & 1u) && cb[k] <= best_c) { best_c = cb[k]; best_k = k; }
+                unsigned m = __reduce_min_sync(0xffffffffu, best_k >= 0 ? best_c : 0xffffffffu);
+                if (m == 0xffffffffu) break;
+                int cand = (best_k >= 0 && best_c == m) ? sp + lane + 32 * best_k : 0x7fffffff;
+                idx = __reduce_min_sync(0xffffffffu, cand);
+            }
+            if (lane == 0) {
+                if (phase == 0) {
+                    if (pick < p.max_sharp) { s.label[idx] = 2; p.slot_sharp[slot_base * p.max_sharp + n_sharp] = start + idx; }
+                    else s.label[idx] = 1;
+                    p.slot_lsharp[slot_base * p.max_lsharp + n_ls] = start + idx;
+                } else {
+                    s.label[idx] = -1; p.slot_flat[slot_base * p.max_flat + n_flat] = start + idx;
+                }
+            }
+            if (phase == 0) { if (pick < p.max_sharp) n_sharp++; n_ls++; } else n_flat++;
+            // markAsPicked: +-K neighbours while consecutive gaps stay <= 0.05
+            unsigned g = 1u;
+            if (lane < K) g = (s.flag[idx + lane] >> 3) & 1u;
+            else if (lane >= 16 && lane < 16 + K) g = (s.flag[idx - 1 - (lane - 16)] >> 3) & 1u;
+            unsigned bal = __ballot_sync(0xffffffffu, g);
+            int fcount = min(K, __ffs(bal & 0xffffu) - 1);
+            int bcount = min(K, __ffs(bal >> 16) - 1);
+            if (lane == 0) own[idx] = 1;
+            if (lane < fcount) own[idx + 1 + lane] = 1;
+            if (lane >= 16 && lane - 16 < bcount) own[idx - 1 - (lane - 16)] = 1;
+            // clear eligibility of my point inside [idx - bcount, idx + fcount] (at most one per lane: width <= 2K+1 < 32)
+            int lo = idx - bcount, hi = idx + fcount;
+            int k0 = (lo - sp - lane + 31) >> 5;            // first k with sp + lane + 32k >= lo
+            if (lo - sp - lane < 0) k0 = 0;
+            int i0 = sp + lane + 32 * k0;
+            if (k0 < MAXS && i0 >= lo && i0 <= hi) { el_c &= ~(1u << k0); el_f &= ~(1u << k0); }
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        uint8_t *c = p.slot_cnt + slot_base * 4;
+        c[0] = (uint8_t)n_sharp; c[1] = (uint8_t)n_ls; c[2] = (uint8_t)n_flat; c[3] = 0;
+    }
+}
+
+#define K1_MAXS 12
+__device__ __forceinline__ void k1_greedy_dispatch(const K1Params &p, const K1Smem &s, int lane, int sec, int sp, int ep, int start,
+                                                   uint8_t *own, const uint8_t *prev, int vlo, int vhi, int b, int r)
+{
+    if (ep - sp + 1 <= 32 * K1_MAXS) k1_sector_greedy_regs<K1_MAXS>(p, s, lane, sec, sp, ep, start, own, prev, vlo, vhi, b, r);
+    else k1_sector_greedy(p, s, lane, sec, sp, ep, start, own, prev, vlo, vhi, b, r);
+}
+
 extern __shared__ __align__(16) unsigned char k1_smem_raw[];
 
 __global__ void __launch_bounds__(K1_THREADS) k1_extract(K1Params p)
 {
     __shared__ int s_sp[VLO_MAX_REGIONS], s_ep[VLO_MAX_REGIONS];
     __shared__ int s_warp_scan[K1_THREADS / 32];
-    __shared__ int s_seq;
+    __shared__ int s_seq, s_all_valid;
     const int r = blockIdx.x, b = p.scan_first + blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int start = p.ring_start[b * (VLO_MAX_RINGS + 1) + r];
     const int n = p.ring_start[b * (VLO_MAX_RINGS + 1) + r + 1] - start;
@@ -174,7 +263,15 @@ __global__ void __launch_bounds__(K1_THREADS) k1_extract(K1Params p)
         int ep = (a * (NR - 1 - tid) + e * (tid + 1)) / NR - 1;
         s_sp[tid] = sp - start; s_ep[tid] = ep - start;
     }
-    if (tid == 0) s_seq = 0;
+    if (tid == 0) {
+        s_seq = 0;
+        int a = start + K, e = start + n - 1 - K, ok = 1;
+        for (int j = 0; j < NR; j++) {
+            int sp = (a * (NR - j) + e * j) / NR, ep = (a * (NR - 1 - j) + e * (j + 1)) / NR - 1;
+            if (!(ep > sp)) ok = 0;
+        }
+        s_all_valid = ok;         // every sector non-empty: "inside some sector" == inside [sp_0, ep_last]
+    }
     __syncthreads();
     // ---- B1: per-point flags
     for (int i = tid; i < n; i += K1_THREADS) {
@@ -212,6 +309,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_extract(K1Params p)
     __syncthreads();
     // ---- B2: window-OR -> base picked (bit4);  C: curvature inside sector ranges
     const int lo_all = s_sp[0], hi_all = s_ep[NR - 1];
+    const bool all_valid = s_all_valid != 0;
     for (int i = tid; i < n; i += K1_THREADS) {
         unsigned pk = (s.flag[i] >> 2) & 1u;
         for (int m = 0; m <= K; m++) {
@@ -220,8 +318,8 @@ __global__ void __launch_bounds__(K1_THREADS) k1_extract(K1Params p)
         }
         float cv = 0.f;
         if (i >= lo_all && i <= hi_all) {
-            bool in = false;
-            for (int j = 0; j < NR; j++) in |= (s_ep[j] > s_sp[j] && i >= s_sp[j] && i <= s_ep[j]);
+            bool in = all_valid;
+            if (!all_valid) for (int j = 0; j < NR; j++) in |= (s_ep[j] > s_sp[j] && i >= s_sp[j] && i <= s_ep[j]);
             if (in) {
                 float wgt = (float)(-2 * K);
                 float dx = wgt * s.x[i], dy = wgt * s.y[i], dz = wgt * s.z[i];
@@ -250,8 +348,8 @@ __global__ void __launch_bounds__(K1_THREADS) k1_extract(K1Params p)
     // ---- D: greedy selection
     if (!s_seq) {
         if (warp < NR && s_ep[warp] > s_sp[warp])
-            k1_sector_greedy(p, s, lane, warp, s_sp[warp], s_ep[warp], start,
-                             (warp & 1) ? s.mark1 : s.mark0, (warp & 1) ? s.mark0 : s.mark1, 1, 0, b, r);
+            k1_greedy_dispatch(p, s, lane, warp, s_sp[warp], s_ep[warp], start,
+                               (warp & 1) ? s.mark1 : s.mark0, (warp & 1) ? s.mark0 : s.mark1, 1, 0, b, r);
         __syncthreads();
         if (warp == 0) {
             for (int j = 1; j < NR; j++) {
@@ -264,7 +362,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_extract(K1Params p)
                     for (int q = s_sp[j] - K + lane; q <= s_ep[j] + K; q += 32) if (q >= 0 && q < n) own[q] = 0;
                     for (int q = s_sp[j] + lane; q <= s_ep[j]; q += 32) s.label[q] = 0;
                     __syncwarp();
-                    k1_sector_greedy(p, s, lane, j, s_sp[j], s_ep[j], start, own, prev, s_sp[j], s_sp[j] + K - 1, b, r);
+                    k1_greedy_dispatch(p, s, lane, j, s_sp[j], s_ep[j], start, own, prev, s_sp[j], s_sp[j] + K - 1, b, r);
                     __syncwarp();
                 }
             }
@@ -273,7 +371,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_extract(K1Params p)
         // short rings: sectors strictly in order on one warp, a single mark array sees everything
         for (int j = 0; j < NR; j++) {
             if (!(s_ep[j] > s_sp[j])) continue;
-            k1_sector_greedy(p, s, lane, j, s_sp[j], s_ep[j], start, s.mark0, s.mark1, 1, 0, b, r);
+            k1_greedy_dispatch(p, s, lane, j, s_sp[j], s_ep[j], start, s.mark0, s.mark1, 1, 0, b, r);
             __syncwarp();
         }
     }
@@ -293,8 +391,10 @@ __global__ void __launch_bounds__(K1_THREADS) k1_extract(K1Params p)
     for (int i = tid; i < n; i += K1_THREADS) {
         int so = -1;
         bool in = false;
-        if (i >= lo_all && i <= hi_all)
-            for (int j = 0; j < NR; j++) in |= (s_ep[j] > s_sp[j] && i >= s_sp[j] && i <= s_ep[j]);
+        if (i >= lo_all && i <= hi_all) {
+            in = all_valid;
+            if (!all_valid) for (int j = 0; j < NR; j++) in |= (s_ep[j] > s_sp[j] && i >= s_sp[j] && i <= s_ep[j]);
+        }
         if (in && s.label[i] <= 0) {
             float x = s.x[i], y = s.y[i], z = s.z[i], w = s.w[i];
             int ix = (int)floorf(x * inv), iy = (int)floorf(y * inv), iz = (int)floorf(z * inv);
@@ -320,34 +420,39 @@ __global__ void __launch_bounds__(K1_THREADS) k1_extract(K1Params p)
         slot_of[i] = so;
     }
     __syncthreads();
-    // leaders in index order: thread t owns the contiguous chunk [t*per, (t+1)*per)
-    const int per = (n + K1_THREADS - 1) / K1_THREADS;
-    int i0 = tid * per, i1 = min(n, i0 + per);
+    // leaders (first point of each voxel) in index order: warp w owns the contiguous segment
+    // [w*seg, (w+1)*seg), walks it 32 points at a time and ranks leaders with ballots (no bank conflicts)
+    const int seg = (((n + K1_THREADS / 32 - 1) / (K1_THREADS / 32)) + 31) & ~31;
+    const int w0 = warp * seg, w1 = min(n, w0 + seg);
     int cnt = 0;
-    for (int i = i0; i < i1; i++) { int so = slot_of[i]; if (so >= 0 && s.vfirst[so] == i) cnt++; }
-    int inc = cnt;
-    #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
-    if (lane == 31) s_warp_scan[warp] = inc;
+    for (int i = w0 + lane; i < w0 + seg; i += 32) {
+        bool lead = false;
+        if (i < w1) { int so = slot_of[i]; lead = so >= 0 && s.vfirst[so] == i; }
+        cnt += __popc(__ballot_sync(0xffffffffu, lead));
+    }
+    if (lane == 0) s_warp_scan[warp] = cnt;
     __syncthreads();
     int woff = 0, total = 0;
     for (int wv = 0; wv < K1_THREADS / 32; wv++) { int v = s_warp_scan[wv]; if (wv < warp) woff += v; total += v; }
-    int pos = woff + inc - cnt;
-    for (int i = i0; i < i1; i++) {
-        int so = slot_of[i];
-        if (so >= 0 && s.vfirst[so] == i) {
-            double c = (double)s.vcnt[so];
+    int pos = woff;
+    for (int i = w0 + lane; i < w0 + seg; i += 32) {
+        bool lead = false; int so = -1;
+        if (i < w1) { so = slot_of[i]; lead = so >= 0 && s.vfirst[so] == i; }
+        unsigned bal = __ballot_sync(0xffffffffu, lead);
+        if (lead) {
+            float c = (float)s.vcnt[so];
             float x = s.x[i], y = s.y[i], z = s.z[i];
             int ix = (int)floorf(x * inv), iy = (int)floorf(y * inv), iz = (int)floorf(z * inv);
             float ox = (float)ix * leaf, oy = (float)iy * leaf, oz = (float)iz * leaf;
+            const float q = 1.0f / 1048576.0f;
             float4 o;
-            o.x = ox + (float)(((double)s.vsx[so] / c) * (1.0 / 1048576.0));
-            o.y = oy + (float)(((double)s.vsy[so] / c) * (1.0 / 1048576.0));
-            o.z = oz + (float)(((double)s.vsz[so] / c) * (1.0 / 1048576.0));
-            o.w = (float)(int)s.w[i] + (float)(((double)s.vsw[so] / c) * (1.0 / 1048576.0));
-            p.lflat_slotted[gbase + pos] = o;
-            pos++;
+            o.x = ox + ((float)s.vsx[so] / c) * q;
+            o.y = oy + ((float)s.vsy[so] / c) * q;
+            o.z = oz + ((float)s.vsz[so] / c) * q;
+            o.w = (float)(int)s.w[i] + ((float)s.vsw[so] / c) * q;
+            p.lflat_slotted[gbase + pos + __popc(bal & ((1u << lane) - 1u))] = o;
         }
+        pos += __popc(bal);
     }
     if (tid == 0) p.lflat_cnt[b * p.n_rings + r] = total;
 }

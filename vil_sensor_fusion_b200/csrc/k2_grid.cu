@@ -1,6 +1,7 @@
 // K2  voxel-hash build (count -> scan -> scatter) for a set of grids, plus a k-NN service kernel.
 // See grid.cuh for the layout and the exactness contract.
 #include "grid.cuh"
+#include <algorithm>
 
 __device__ __forceinline__ bool grid_src_point(const GridSource &src, int g, int i, float4 &p, unsigned &tag)
 {
@@ -106,24 +107,27 @@ int vlo_grid_build(vlo_handle *h, const GridSet &gs, const GridSource &src, int 
 template <int K>
 __global__ void __launch_bounds__(256) k2_knn(GridSet gs, int g, const float4 *q, int nq, float dmax, int *idx, float *d2)
 {
-    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (w >= nq) return;
-    float4 p = q[w];
-    TopK<K> best;
-    grid_search<K>(gs, g, p.x, p.y, p.z, dmax, FilterAll(), best, lane);
-    if (lane == 0) {
-        #pragma unroll
-        for (int i = 0; i < K; i++) {
-            bool ok = best.tag[i] != GRID_NOTAG;
-            idx[(size_t)w * K + i] = ok ? (int)(best.tag[i] & 0xFFFFFFu) : -1;
-            d2[(size_t)w * K + i] = ok ? __uint_as_float(best.d[i]) : __int_as_float(0x7f800000);
+    __shared__ int scratch[8][GRID_SCRATCH_INTS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nq; w += n_warps) {
+        float4 p = q[w];
+        TopK<K> best;
+        grid_search<K>(gs, g, p.x, p.y, p.z, dmax, FilterAll(), best, lane, scratch[warp]);
+        if (lane == 0) {
+            #pragma unroll
+            for (int i = 0; i < K; i++) {
+                bool ok = best.tag[i] != GRID_NOTAG;
+                idx[(size_t)w * K + i] = ok ? (int)(best.tag[i] & 0xFFFFFFu) : -1;
+                d2[(size_t)w * K + i] = ok ? __uint_as_float(best.d[i]) : __int_as_float(0x7f800000);
+            }
         }
     }
 }
 
 int vlo_grid_knn(vlo_handle *h, const GridSet &gs, int g, const float4 *d_q, int nq, int k, float dmax, int *d_idx, float *d_d2)
 {
-    int blocks = (nq * 32 + 255) / 256;
+    int blocks = std::min((nq * 32 + 255) / 256, 148 * 8);
     if (nq <= 0) return VLO_OK;
     if (k == 1) k2_knn<1><<<blocks, 256, 0, h->stream>>>(gs, g, d_q, nq, dmax, d_idx, d_d2);
     else if (k == 5) k2_knn<5><<<blocks, 256, 0, h->stream>>>(gs, g, d_q, nq, dmax, d_idx, d_d2);

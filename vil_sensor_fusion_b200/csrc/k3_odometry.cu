@@ -12,6 +12,7 @@
 // so control never returns to the host inside a registration.
 #include "grid.cuh"
 #include "dense6.cuh"
+#include <algorithm>
 
 struct OdomParams {
     // features of the current sweep (queries) and the previous sweep (targets), per scan
@@ -40,8 +41,10 @@ __device__ __forceinline__ float4 lflat_point(const OdomParams &p, int scan, int
 
 __global__ void __launch_bounds__(256) k3_assoc(OdomParams p, int n_pairs)
 {
+    __shared__ int scratch[8][GRID_SCRATCH_INTS];
     const int pair = blockIdx.y;
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
     if (p.pair_state[pair * 4 + 0]) return;                          // converged
     const int last = p.pair_last[pair], cur = p.pair_cur[pair];
     const int n_sharp = p.counts[cur * 8 + 1], n_flat = p.counts[cur * 8 + 3];
@@ -50,47 +53,48 @@ __global__ void __launch_bounds__(256) k3_assoc(OdomParams p, int n_pairs)
     float T[6];
     #pragma unroll
     for (int a = 0; a < 6; a++) T[a] = p.pair_T[pair * 6 + a];
-    if (w < p.cap_sharp) {
-        if (w >= n_sharp) return;
-        float4 q = vlo_to_start(T, p.sharp_pts[(size_t)cur * p.cap_sharp + w], p.deskew, p.inv_period);
-        TopK<1> nn;
-        grid_search<1>(p.gc, last, q.x, q.y, q.z, 25.0f, FilterAll(), nn, lane);
-        int i1 = -1, i2 = -1;
-        if (nn.tag[0] != GRID_NOTAG) {
-            i1 = (int)(nn.tag[0] & 0xFFFFFFu);
-            int ring = (int)(nn.tag[0] >> 24);
-            FilterPartner f; f.ind = i1; f.ring_lo = ring - 2; f.ring_hi = ring + 2; f.skip_ring = ring;
-            f.fwd_bound = p.fwd_quirk ? min(n_sharp, n_lc) : n_lc;
-            TopK<1> pr;
-            grid_search<1>(p.gc, last, q.x, q.y, q.z, 25.0f, f, pr, lane);
-            if (pr.tag[0] != GRID_NOTAG) i2 = (int)(pr.tag[0] & 0xFFFFFFu);
-        }
-        if (lane == 0) {
-            int *o = p.cidx + ((size_t)pair * p.cap_sharp + w) * 2;
-            o[0] = i1; o[1] = i2;
-        }
-    } else {
-        int f_i = w - p.cap_sharp;
-        if (f_i >= n_flat) return;
-        float4 q = vlo_to_start(T, p.flat_pts[(size_t)cur * p.cap_flat + f_i], p.deskew, p.inv_period);
-        TopK<1> nn;
-        grid_search<1>(p.gsf, last, q.x, q.y, q.z, 25.0f, FilterAll(), nn, lane);
-        int i1 = -1, i2 = -1, i3 = -1;
-        if (nn.tag[0] != GRID_NOTAG) {
-            i1 = (int)(nn.tag[0] & 0xFFFFFFu);
-            int ring = (int)(nn.tag[0] >> 24);
-            int fb = p.fwd_quirk ? min(n_flat, n_ls) : n_ls;
-            FilterPartner f2; f2.ind = i1; f2.ring_lo = ring; f2.ring_hi = ring; f2.skip_ring = -1; f2.fwd_bound = fb;
-            FilterPartner f3; f3.ind = i1; f3.ring_lo = ring - 2; f3.ring_hi = ring + 2; f3.skip_ring = ring; f3.fwd_bound = fb;
-            TopK<1> p2, p3;
-            grid_search<1>(p.gsf, last, q.x, q.y, q.z, 25.0f, f2, p2, lane);
-            grid_search<1>(p.gsf, last, q.x, q.y, q.z, 25.0f, f3, p3, lane);
-            if (p2.tag[0] != GRID_NOTAG) i2 = (int)(p2.tag[0] & 0xFFFFFFu);
-            if (p3.tag[0] != GRID_NOTAG) i3 = (int)(p3.tag[0] & 0xFFFFFFu);
-        }
-        if (lane == 0) {
-            int *o = p.sidx + ((size_t)pair * p.cap_flat + f_i) * 3;
-            o[0] = i1; o[1] = i2; o[2] = i3;
+    // persistent warps stride over the compact query index space [sharp..., flat...]
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_sharp + n_flat; w += n_warps) {
+        if (w < n_sharp) {
+            float4 q = vlo_to_start(T, p.sharp_pts[(size_t)cur * p.cap_sharp + w], p.deskew, p.inv_period);
+            TopK<1> nn;
+            grid_search<1>(p.gc, last, q.x, q.y, q.z, 25.0f, FilterAll(), nn, lane, scratch[warp]);
+            int i1 = -1, i2 = -1;
+            if (nn.tag[0] != GRID_NOTAG) {
+                i1 = (int)(nn.tag[0] & 0xFFFFFFu);
+                int ring = (int)(nn.tag[0] >> 24);
+                FilterPartner f; f.ind = i1; f.ring_lo = ring - 2; f.ring_hi = ring + 2; f.skip_ring = ring;
+                f.fwd_bound = p.fwd_quirk ? min(n_sharp, n_lc) : n_lc;
+                TopK<1> pr;
+                grid_search<1>(p.gc, last, q.x, q.y, q.z, 25.0f, f, pr, lane, scratch[warp]);
+                if (pr.tag[0] != GRID_NOTAG) i2 = (int)(pr.tag[0] & 0xFFFFFFu);
+            }
+            if (lane == 0) {
+                int *o = p.cidx + ((size_t)pair * p.cap_sharp + w) * 2;
+                o[0] = i1; o[1] = i2;
+            }
+        } else {
+            int f_i = w - n_sharp;
+            float4 q = vlo_to_start(T, p.flat_pts[(size_t)cur * p.cap_flat + f_i], p.deskew, p.inv_period);
+            TopK<1> nn;
+            grid_search<1>(p.gsf, last, q.x, q.y, q.z, 25.0f, FilterAll(), nn, lane, scratch[warp]);
+            int i1 = -1, i2 = -1, i3 = -1;
+            if (nn.tag[0] != GRID_NOTAG) {
+                i1 = (int)(nn.tag[0] & 0xFFFFFFu);
+                int ring = (int)(nn.tag[0] >> 24);
+                int fb = p.fwd_quirk ? min(n_flat, n_ls) : n_ls;
+                FilterPartner f2; f2.ind = i1; f2.ring_lo = ring; f2.ring_hi = ring; f2.skip_ring = -1; f2.fwd_bound = fb;
+                FilterPartner f3; f3.ind = i1; f3.ring_lo = ring - 2; f3.ring_hi = ring + 2; f3.skip_ring = ring; f3.fwd_bound = fb;
+                TopK<1> p2, p3;
+                grid_search<1>(p.gsf, last, q.x, q.y, q.z, 25.0f, f2, p2, lane, scratch[warp]);
+                grid_search<1>(p.gsf, last, q.x, q.y, q.z, 25.0f, f3, p3, lane, scratch[warp]);
+                if (p2.tag[0] != GRID_NOTAG) i2 = (int)(p2.tag[0] & 0xFFFFFFu);
+                if (p3.tag[0] != GRID_NOTAG) i3 = (int)(p3.tag[0] & 0xFFFFFFu);
+            }
+            if (lane == 0) {
+                int *o = p.sidx + ((size_t)pair * p.cap_flat + f_i) * 3;
+                o[0] = i1; o[1] = i2; o[2] = i3;
+            }
         }
     }
 }
@@ -410,8 +414,11 @@ int vlo_launch_register_pairs(vlo_handle *h, int n_pairs, const float *d_seeds, 
     }
     if (only_grid_scan >= 0) { int rc = vlo_build_scan_grids(h, only_grid_scan, 1); if (rc) return rc; h->grids_valid = 1; }
     if (!h->grids_valid) { int rc = vlo_build_scan_grids(h, 0, h->sb.n_scans); if (rc) return rc; h->grids_valid = 1; }
+    // persistent association grid: enough CTAs to fill the machine, warps stride over the queries
     int n_warps = h->cap_sharp + h->cap_flat;
-    dim3 ga((n_warps * 32 + 255) / 256, n_pairs);
+    int ctas = (n_warps * 32 + 255) / 256;
+    int fill = (148 * 8 + n_pairs - 1) / n_pairs;
+    dim3 ga(std::max(1, std::min(ctas, fill)), n_pairs);
     size_t trace_stride = (size_t)n_pairs * (h->cap_sharp * 2 + h->cap_flat * 3);
     for (int base = 0, round = 0; base < c.odom_max_iterations; base += 5, round++) {
         VLO_PROF(h, ST_ASSOC, (k3_assoc<<<ga, 256, 0, h->stream>>>(p, n_pairs)));

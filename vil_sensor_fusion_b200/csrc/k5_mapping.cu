@@ -11,6 +11,7 @@
 // All launches are enqueued back to back; converged scans skip work through a device flag.
 #include "grid.cuh"
 #include "dense6.cuh"
+#include <algorithm>
 
 struct MapParams {
     const float4 *lsharp_pts; int cap_lsharp; const float4 *lflat_slotted; int N;
@@ -48,28 +49,32 @@ __device__ __forceinline__ float4 to_map(const float *T, const float *trig, floa
 
 __global__ void __launch_bounds__(256) k5_knn(MapParams p)
 {
+    __shared__ int scratch[8][GRID_SCRATCH_INTS];
     const int k = blockIdx.y;
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
     if (p.state[k * 4 + 0]) return;
     const int scan = p.scans[k];
     const int n_ls = p.counts[scan * 8 + 2], n_lf = p.counts[scan * 8 + 4];
-    if (w >= n_ls + n_lf) return;
     if (!(p.map_n[2] > 10 && p.map_n[4] > 100)) return;
     float T[6], trig[6];
     #pragma unroll
     for (int a = 0; a < 6; a++) T[a] = p.T[k * 6 + a];
     vlo_sincosf(T[0], trig[0], trig[1]); vlo_sincosf(T[1], trig[2], trig[3]); vlo_sincosf(T[2], trig[4], trig[5]);
-    bool corner;
-    float4 ori = map_query_point(p, scan, w, n_ls, corner);
-    float4 sel = to_map(T, trig, ori);
-    TopK<5> best;
-    if (corner) grid_search<5>(p.gm0, 0, sel.x, sel.y, sel.z, 1.0f, FilterAll(), best, lane);
-    else        grid_search<5>(p.gm1, 0, sel.x, sel.y, sel.z, 1.0f, FilterAll(), best, lane);
-    if (lane == 0) {
-        int *o = p.idx5 + ((size_t)k * p.qcap + w) * 5;
-        bool ok = best.tag[4] != GRID_NOTAG;
-        #pragma unroll
-        for (int j = 0; j < 5; j++) o[j] = ok ? (int)(best.tag[j] & 0xFFFFFFu) : -1;
+    // persistent warps stride over the feature points of this scan
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_ls + n_lf; w += n_warps) {
+        bool corner;
+        float4 ori = map_query_point(p, scan, w, n_ls, corner);
+        float4 sel = to_map(T, trig, ori);
+        TopK<5> best;
+        if (corner) grid_search<5>(p.gm0, 0, sel.x, sel.y, sel.z, 1.0f, FilterAll(), best, lane, scratch[warp]);
+        else        grid_search<5>(p.gm1, 0, sel.x, sel.y, sel.z, 1.0f, FilterAll(), best, lane, scratch[warp]);
+        if (lane == 0) {
+            int *o = p.idx5 + ((size_t)k * p.qcap + w) * 5;
+            bool ok = best.tag[4] != GRID_NOTAG;
+            #pragma unroll
+            for (int j = 0; j < 5; j++) o[j] = ok ? (int)(best.tag[j] & 0xFFFFFFu) : -1;
+        }
     }
 }
 
@@ -379,7 +384,8 @@ int vlo_launch_register_map(vlo_handle *h, const int *d_scans, int n, const floa
     h->launches += 1;
     // grids sized by the largest feature count actually present would need a sync; use capacity
     int qmax = h->map_qmax > 0 ? h->map_qmax : p.qcap;
-    dim3 gk((qmax * 32 + 255) / 256, n), gl((qmax + LIN_THREADS - 1) / LIN_THREADS, n);
+    int knn_ctas = (qmax * 32 + 255) / 256, knn_fill = (148 * 8 + n - 1) / n;
+    dim3 gk(std::max(1, std::min(knn_ctas, knn_fill)), n), gl((qmax + LIN_THREADS - 1) / LIN_THREADS, n);
     for (int it = 0; it < c.map_max_iterations; it++) {
         VLO_PROF(h, ST_MAP_KNN, (k5_knn<<<gk, 256, 0, h->stream>>>(p)));
         VLO_PROF(h, ST_MAP_LIN, (k5_lin<<<gl, LIN_THREADS, 0, h->stream>>>(p)));
