@@ -79,7 +79,8 @@ typedef struct vlo_config {
     float map_delta_r_abort;           /* mapDeltaRAbort 0.05 (46) */
     float map_degen_eig;               /* mapDegenEigVal 40 (53) */
     float map_cell_size;               /* voxel-hash cell edge for the map grids (m); not in the reference */
-    float odom_cell_size;              /* voxel-hash cell edge for scan-to-scan target grids (m) */
+    float odom_cell_size;              /* voxel-hash cell edge of the scan-to-scan surface (less-flat) target grids (m) */
+    float odom_corner_cell_size;       /* same for the sparse corner (less-sharp) target grids; 5 m = the 25 m^2 search radius */
     /* ---- gtsam_fusion_filter (fusion_params.yaml:35-36) ---- */
     float dopt_rot_threshold;          /* filter/rot_degen_threshold 11.5 */
     float dopt_trans_threshold;        /* filter/trans_degen_threshold 28.9 */

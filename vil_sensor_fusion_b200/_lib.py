@@ -20,7 +20,7 @@ class Config(C.Structure):
         ("odom_max_iterations", C.c_int), ("odom_delta_t_abort", C.c_float), ("odom_delta_r_abort", C.c_float),
         ("odom_degen_eig", C.c_float), ("deskew", C.c_int), ("odom_forward_bound_quirk", C.c_int),
         ("map_max_iterations", C.c_int), ("map_delta_t_abort", C.c_float), ("map_delta_r_abort", C.c_float),
-        ("map_degen_eig", C.c_float), ("map_cell_size", C.c_float), ("odom_cell_size", C.c_float),
+        ("map_degen_eig", C.c_float), ("map_cell_size", C.c_float), ("odom_cell_size", C.c_float), ("odom_corner_cell_size", C.c_float),
         ("dopt_rot_threshold", C.c_float), ("dopt_trans_threshold", C.c_float),
         ("cov_accel", C.c_double), ("cov_gyro", C.c_double), ("cov_integration", C.c_double),
         ("cov_bias_acc", C.c_double), ("cov_bias_omega", C.c_double), ("cov_bias_acc_omega_int", C.c_double),

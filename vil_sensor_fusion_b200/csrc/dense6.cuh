@@ -7,62 +7,91 @@
 #include "vlo_internal.cuh"
 #include <float.h>
 
+// Fully unrolled with static indices so the 6x6 working set lives in registers (dynamic indexing
+// would push it to local memory: round-1 profile of the online tick); the pivot swap and the
+// rank-limited back substitution are predicated instead of indexed.  Same operations, same order.
 __device__ inline void vlo_solve6_colpiv_qr(const float *Ain, const float *bin, float *x)
 {
     float A[6][6], b[6];
     int perm[6];
-    for (int i = 0; i < 6; i++) { for (int j = 0; j < 6; j++) A[i][j] = Ain[i * 6 + j]; b[i] = bin[i]; perm[i] = i; }
+    #pragma unroll
+    for (int i = 0; i < 6; i++) {
+        #pragma unroll
+        for (int j = 0; j < 6; j++) A[i][j] = Ain[i * 6 + j];
+        b[i] = bin[i]; perm[i] = i;
+    }
     float maxn2 = 0.0f;
+    #pragma unroll
     for (int j = 0; j < 6; j++) {
         float s = 0.0f;
+        #pragma unroll
         for (int i = 0; i < 6; i++) s += A[i][j] * A[i][j];
         if (s > maxn2) maxn2 = s;
     }
     float mx = sqrtf(maxn2) * FLT_EPSILON;
     float thr_helper = (mx * mx) / 6.0f;
     int nonzero = 6;
+    #pragma unroll
     for (int k = 0; k < 6; k++) {
         int piv = k; float best = -1.0f;
+        #pragma unroll
         for (int j = k; j < 6; j++) {
             float s = 0.0f;
+            #pragma unroll
             for (int i = k; i < 6; i++) s += A[i][j] * A[i][j];
             if (s > best) { best = s; piv = j; }
         }
         if (nonzero == 6 && best < thr_helper * (float)(6 - k)) nonzero = k;
-        if (piv != k) {
-            for (int i = 0; i < 6; i++) { float t = A[i][k]; A[i][k] = A[i][piv]; A[i][piv] = t; }
-            int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t;
+        #pragma unroll
+        for (int j = k + 1; j < 6; j++) {
+            if (piv == j) {
+                #pragma unroll
+                for (int i = 0; i < 6; i++) { float t = A[i][k]; A[i][k] = A[i][j]; A[i][j] = t; }
+                int t = perm[k]; perm[k] = perm[j]; perm[j] = t;
+            }
         }
         float nrm = sqrtf(best);
-        if (nrm == 0.0f) continue;
-        float alpha = (A[k][k] >= 0.0f) ? -nrm : nrm;
-        float v[6];
-        for (int i = 0; i < 6; i++) v[i] = 0.0f;
-        for (int i = k; i < 6; i++) v[i] = A[i][k];
-        v[k] = v[k] - alpha;
-        float vn2 = 0.0f;
-        for (int i = k; i < 6; i++) vn2 += v[i] * v[i];
-        if (vn2 == 0.0f) continue;
-        for (int j = k; j < 6; j++) {
-            float dot = 0.0f;
-            for (int i = k; i < 6; i++) dot += v[i] * A[i][j];
-            float f = (2.0f * dot) / vn2;
-            for (int i = k; i < 6; i++) A[i][j] = A[i][j] - f * v[i];
-        }
-        {
-            float dot = 0.0f;
-            for (int i = k; i < 6; i++) dot += v[i] * b[i];
-            float f = (2.0f * dot) / vn2;
-            for (int i = k; i < 6; i++) b[i] = b[i] - f * v[i];
+        if (nrm != 0.0f) {
+            float alpha = (A[k][k] >= 0.0f) ? -nrm : nrm;
+            float v[6];
+            #pragma unroll
+            for (int i = 0; i < 6; i++) v[i] = (i >= k) ? A[i][k] : 0.0f;
+            v[k] = v[k] - alpha;
+            float vn2 = 0.0f;
+            #pragma unroll
+            for (int i = k; i < 6; i++) vn2 += v[i] * v[i];
+            if (vn2 != 0.0f) {
+                #pragma unroll
+                for (int j = k; j < 6; j++) {
+                    float dot = 0.0f;
+                    #pragma unroll
+                    for (int i = k; i < 6; i++) dot += v[i] * A[i][j];
+                    float f = (2.0f * dot) / vn2;
+                    #pragma unroll
+                    for (int i = k; i < 6; i++) A[i][j] = A[i][j] - f * v[i];
+                }
+                float dot = 0.0f;
+                #pragma unroll
+                for (int i = k; i < 6; i++) dot += v[i] * b[i];
+                float f = (2.0f * dot) / vn2;
+                #pragma unroll
+                for (int i = k; i < 6; i++) b[i] = b[i] - f * v[i];
+            }
         }
     }
     float y[6];
+    #pragma unroll
     for (int i = 0; i < 6; i++) y[i] = 0.0f;
-    for (int i = nonzero - 1; i >= 0; i--) {
-        float s = b[i];
-        for (int j = i + 1; j < nonzero; j++) s = s - A[i][j] * y[j];
-        y[i] = s / A[i][i];
+    #pragma unroll
+    for (int i = 5; i >= 0; i--) {
+        if (i < nonzero) {
+            float s = b[i];
+            #pragma unroll
+            for (int j = i + 1; j < 6; j++) if (j < nonzero) s = s - A[i][j] * y[j];
+            y[i] = s / A[i][i];
+        }
     }
+    #pragma unroll
     for (int i = 0; i < 6; i++) x[perm[i]] = y[i];
 }
 
@@ -153,24 +182,6 @@ __device__ inline float vlo_det3(const float *H, int o)
     return (a - b) + c;
 }
 
-// float64 inverse via Gauss-Jordan with partial pivoting; returns false if singular
-__device__ inline bool vlo_inv6d(const double *A, double *Ai)
-{
-    double M[6][12];
-    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) { M[i][j] = A[i * 6 + j]; M[i][6 + j] = (i == j) ? 1.0 : 0.0; }
-    for (int k = 0; k < 6; k++) {
-        int p = k; double mx = fabs(M[k][k]);
-        for (int i = k + 1; i < 6; i++) if (fabs(M[i][k]) > mx) { mx = fabs(M[i][k]); p = i; }
-        if (mx == 0.0) return false;
-        if (p != k) for (int j = 0; j < 12; j++) { double t = M[k][j]; M[k][j] = M[p][j]; M[p][j] = t; }
-        double d = M[k][k];
-        for (int j = 0; j < 12; j++) M[k][j] /= d;
-        for (int i = 0; i < 6; i++) if (i != k) { double f = M[i][k]; for (int j = 0; j < 12; j++) M[i][j] -= f * M[k][j]; }
-    }
-    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) Ai[i * 6 + j] = M[i][6 + j];
-    return true;
-}
-
 // Shared-memory scratch of one Gauss-Newton problem (one CTA or one warp owns it)
 struct GnScratch {
     float total[VLO_NTERM];
@@ -239,20 +250,20 @@ __device__ inline void vlo_gn_update_warp(GnScratch &S, int iter, float degen_th
     __syncwarp();
 }
 
-// result record from the last linearisation's totals (oracle: orc_finish_result); one thread
+// result record from the last linearisation's totals (oracle: orc_finish_result); one thread.
+// The float64 covariance sigma^2 (AtA)^-1 is finished on the host right after the result record is
+// copied back (vlo_finish_cov_host): the device only stages sum((s d)^2) in cov[0] and n in cov[1].
 __device__ inline void vlo_finish_result(const GnScratch &S, float rot_thr, float trans_thr, vlo_result *res)
 {
     int e = 0;
-    for (int a = 0; a < 6; a++) for (int b = a; b < 6; b++) { res->hessian[a * 6 + b] = S.total[e]; res->hessian[b * 6 + a] = S.total[e]; e++; }
+    #pragma unroll
+    for (int a = 0; a < 6; a++)
+        #pragma unroll
+        for (int b = a; b < 6; b++) { res->hessian[a * 6 + b] = S.total[e]; res->hessian[b * 6 + a] = S.total[e]; e++; }
     float rot = logf(vlo_det3(res->hessian, 3));
     float trans = logf(vlo_det3(res->hessian, 0));
     res->logdet_rot = rot; res->logdet_trans = trans;
     res->pass_dopt = ((double)rot < (double)rot_thr || (double)trans < (double)trans_thr) ? 0 : 1;
-    double Hd[36], Hi[36];
-    for (int i = 0; i < 36; i++) Hd[i] = (double)res->hessian[i];
-    int n = S.n_edge + S.n_plane;
-    double dof = n > 6 ? (double)(n - 6) : 1.0;
-    double sigma2 = (double)S.total[27] / dof;
-    if (vlo_inv6d(Hd, Hi)) for (int i = 0; i < 36; i++) res->cov[i] = sigma2 * Hi[i];
-    else for (int i = 0; i < 36; i++) res->cov[i] = __longlong_as_double(0x7ff8000000000000ll);
+    res->cov[0] = (double)S.total[27];
+    res->cov[1] = (double)(S.n_edge + S.n_plane);
 }

@@ -118,7 +118,9 @@ __device__ void grid_search(const GridSet &gs, int g, float qx, float qy, float 
             const int c = c0 + lane;
             int s0 = 0, n = 0;
             if (c < ncell) {
-                int dx = c % side - rho, dy = (c / side) % side - rho, dz = c / (side * side) - rho;
+                int dx, dy, dz;
+                if (rho == 1) { dx = c % 3 - 1; dy = (c / 3) % 3 - 1; dz = c / 9 - 1; }            // constant divisors
+                else { dx = c % side - rho; dy = (c / side) % side - rho; dz = c / (side * side) - rho; }
                 bool shell = rho == 1 || abs(dx) == rho || abs(dy) == rho || abs(dz) == rho;   // interior: already visited
                 if (shell) {
                     int slot = grid_find(gs, g, cx + dx, cy + dy, cz + dz);

@@ -465,36 +465,62 @@ struct K1bParams {
     int *counts; int *sharp_idx, *lsharp_idx, *flat_idx; float4 *sharp_pts, *lsharp_pts, *flat_pts;
     int cap_sharp, cap_lsharp, cap_flat; int scan_first;
     int *lsharp_ring_start, *lflat_ring_start;
+    const int *ring_start; int *lflat_d2s;
 };
+
+// exclusive scan of one int per thread over a 256-thread block; returns the block total in `total`
+__device__ __forceinline__ int k1b_block_scan(int v, int *warp_buf, int &total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+    __syncthreads();                       // warp_buf may still be read from a previous call
+    if (lane == 31) warp_buf[warp] = inc;
+    __syncthreads();
+    int woff = 0; total = 0;
+    #pragma unroll
+    for (int w = 0; w < 8; w++) { int s = warp_buf[w]; if (w < warp) woff += s; total += s; }
+    return woff + inc - v;
+}
 
 __global__ void __launch_bounds__(256) k1b_compact(K1bParams p)
 {
     __shared__ int off_sharp[VLO_MAX_RINGS * VLO_MAX_REGIONS + 1];
     __shared__ int off_ls[VLO_MAX_RINGS * VLO_MAX_REGIONS + 1];
     __shared__ int off_flat[VLO_MAX_RINGS * VLO_MAX_REGIONS + 1];
+    __shared__ int warp_buf[8];
     const int b = p.scan_first + blockIdx.x, tid = threadIdx.x;
     const int nsec = p.n_rings * p.NR;
-    if (tid == 0) {
+    {
+        // per-thread chunk of consecutive sectors, block scan of the chunk sums, then local running offsets
+        const int per = (nsec + 255) / 256, k0 = min(nsec, tid * per), k1 = min(nsec, k0 + per);
         int a = 0, l = 0, f = 0;
-        for (int k = 0; k < nsec; k++) {
+        for (int k = k0; k < k1; k++) { const uint8_t *c = p.slot_cnt + ((size_t)b * nsec + k) * 4; a += c[0]; l += c[1]; f += c[2]; }
+        int ta, tl, tf;
+        int ba = k1b_block_scan(a, warp_buf, ta), bl = k1b_block_scan(l, warp_buf, tl), bf = k1b_block_scan(f, warp_buf, tf);
+        for (int k = k0; k < k1; k++) {
             const uint8_t *c = p.slot_cnt + ((size_t)b * nsec + k) * 4;
-            off_sharp[k] = a; off_ls[k] = l; off_flat[k] = f;
-            a += c[0]; l += c[1]; f += c[2];
+            off_sharp[k] = ba; off_ls[k] = bl; off_flat[k] = bf;
+            ba += c[0]; bl += c[1]; bf += c[2];
         }
-        off_sharp[nsec] = a; off_ls[nsec] = l; off_flat[nsec] = f;
-        int lf = 0;
-        for (int r = 0; r < p.n_rings; r++) {
-            p.lsharp_ring_start[b * (VLO_MAX_RINGS + 1) + r] = off_ls[r * p.NR];
-            p.lflat_ring_start[b * (VLO_MAX_RINGS + 1) + r] = lf;
-            lf += p.lflat_cnt[b * p.n_rings + r];
+        if (tid == 0) { off_sharp[nsec] = ta; off_ls[nsec] = tl; off_flat[nsec] = tf; }
+        int cnt = (tid < p.n_rings) ? p.lflat_cnt[b * p.n_rings + tid] : 0, tlf;
+        int lf0 = k1b_block_scan(cnt, warp_buf, tlf);
+        __syncthreads();
+        if (tid <= VLO_MAX_RINGS) {
+            p.lsharp_ring_start[b * (VLO_MAX_RINGS + 1) + tid] = (tid < p.n_rings) ? off_ls[tid * p.NR] : tl;
+            p.lflat_ring_start[b * (VLO_MAX_RINGS + 1) + tid] = (tid < p.n_rings) ? lf0 : tlf;
         }
-        for (int r = p.n_rings; r <= VLO_MAX_RINGS; r++) {
-            p.lsharp_ring_start[b * (VLO_MAX_RINGS + 1) + r] = l;
-            p.lflat_ring_start[b * (VLO_MAX_RINGS + 1) + r] = lf;
-        }
-        p.counts[b * 8 + 1] = a; p.counts[b * 8 + 2] = l; p.counts[b * 8 + 3] = f; p.counts[b * 8 + 4] = lf;
+        if (tid == 0) { p.counts[b * 8 + 1] = ta; p.counts[b * 8 + 2] = tl; p.counts[b * 8 + 3] = tf; p.counts[b * 8 + 4] = tlf; }
     }
     __syncthreads();
+    // dense less-flat index -> slot (consumers address the ring-slotted cloud without a search)
+    for (int r = tid >> 5; r < p.n_rings; r += blockDim.x >> 5) {
+        int d0 = p.lflat_ring_start[b * (VLO_MAX_RINGS + 1) + r], s0 = p.ring_start[b * (VLO_MAX_RINGS + 1) + r];
+        int cnt = p.lflat_cnt[b * p.n_rings + r];
+        for (int j = tid & 31; j < cnt; j += 32) p.lflat_d2s[(size_t)b * p.N + d0 + j] = s0 + j;
+    }
     const float4 *cloud = p.cloud + (size_t)b * p.N;
     const int maxq = max(p.max_lsharp, max(p.max_sharp, p.max_flat));
     for (int k = tid; k < nsec * maxq; k += blockDim.x) {
@@ -552,6 +578,7 @@ int vlo_launch_extract(vlo_handle *h)
     q.sharp_pts = sb.sharp_pts; q.lsharp_pts = sb.lsharp_pts; q.flat_pts = sb.flat_pts;
     q.cap_sharp = h->cap_sharp; q.cap_lsharp = h->cap_lsharp; q.cap_flat = h->cap_flat;
     q.lsharp_ring_start = sb.lsharp_ring_start; q.lflat_ring_start = sb.lflat_ring_start;
+    q.ring_start = sb.ring_start; q.lflat_d2s = sb.lflat_d2s;
     q.scan_first = sb.scan_first;
     VLO_PROF(h, ST_COMPACT, (k1b_compact<<<sb.scan_count, 256, 0, h->stream>>>(q)));
     h->launches += 2;

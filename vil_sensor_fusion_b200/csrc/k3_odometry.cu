@@ -21,6 +21,7 @@ struct OdomParams {
     const float4 *lflat_slotted; int N;                  // ring-slotted
     const int *ring_start, *lflat_cnt, *lsharp_ring_start, *lflat_ring_start;   // [B][R+1] / [B][R]
     const int *counts;                                   // [B][8]
+    const int *lflat_d2s;                                // [B][N] dense less-flat index -> slot
     int n_rings;
     // pairs
     const int *pair_last, *pair_cur; float *pair_T; int *pair_state; int *cidx, *sidx; vlo_result *result;
@@ -31,12 +32,7 @@ struct OdomParams {
 
 __device__ __forceinline__ float4 lflat_point(const OdomParams &p, int scan, int dense)
 {
-    // dense index -> ring-slotted address
-    const int *ds = p.lflat_ring_start + (size_t)scan * (VLO_MAX_RINGS + 1);
-    int lo = 0, hi = p.n_rings;
-    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (ds[mid] <= dense) lo = mid; else hi = mid; }
-    int slot = p.ring_start[(size_t)scan * (VLO_MAX_RINGS + 1) + lo] + (dense - ds[lo]);
-    return p.lflat_slotted[(size_t)scan * p.N + slot];
+    return p.lflat_slotted[(size_t)scan * p.N + p.lflat_d2s[(size_t)scan * p.N + dense]];
 }
 
 __global__ void __launch_bounds__(256) k3_assoc(OdomParams p, int n_pairs)
@@ -370,7 +366,7 @@ static OdomParams make_params(vlo_handle *h)
     p.sharp_pts = sb.sharp_pts; p.flat_pts = sb.flat_pts; p.cap_sharp = h->cap_sharp; p.cap_flat = h->cap_flat;
     p.lsharp_pts = sb.lsharp_pts; p.cap_lsharp = h->cap_lsharp; p.lflat_slotted = sb.lflat_slotted; p.N = c.max_points;
     p.ring_start = sb.ring_start; p.lflat_cnt = sb.lflat_cnt; p.lsharp_ring_start = sb.lsharp_ring_start;
-    p.lflat_ring_start = sb.lflat_ring_start; p.counts = sb.counts; p.n_rings = c.n_rings;
+    p.lflat_ring_start = sb.lflat_ring_start; p.counts = sb.counts; p.lflat_d2s = sb.lflat_d2s; p.n_rings = c.n_rings;
     p.pair_last = h->pair_last; p.pair_cur = h->pair_cur; p.pair_T = h->pair_T; p.pair_state = h->pair_state;
     p.cidx = h->pair_cidx; p.sidx = h->pair_sidx; p.result = h->pair_result;
     p.gc = h->gs_corner; p.gsf = h->gs_surf;

@@ -15,7 +15,7 @@
 
 struct MapParams {
     const float4 *lsharp_pts; int cap_lsharp; const float4 *lflat_slotted; int N;
-    const int *ring_start, *lflat_ring_start, *counts; int n_rings;
+    const int *ring_start, *lflat_ring_start, *counts, *lflat_d2s; int n_rings;
     const int *scans;            // [n] resident scan index per slot
     float *T; int *state; vlo_result *result;     // per slot
     int *idx5; int qcap;         // [n][qcap][5]
@@ -29,11 +29,7 @@ __device__ __forceinline__ float4 map_query_point(const MapParams &p, int scan, 
 {
     corner = i < n_ls;
     if (corner) return p.lsharp_pts[(size_t)scan * p.cap_lsharp + i];
-    int dense = i - n_ls;
-    const int *ds = p.lflat_ring_start + (size_t)scan * (VLO_MAX_RINGS + 1);
-    int lo = 0, hi = p.n_rings;
-    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (ds[mid] <= dense) lo = mid; else hi = mid; }
-    int slot = p.ring_start[(size_t)scan * (VLO_MAX_RINGS + 1) + lo] + (dense - ds[lo]);
+    int slot = p.lflat_d2s[(size_t)scan * p.N + (i - n_ls)];
     return p.lflat_slotted[(size_t)scan * p.N + slot];
 }
 
@@ -373,7 +369,7 @@ int vlo_launch_register_map(vlo_handle *h, const int *d_scans, int n, const floa
     ScanBatchDev &sb = h->sb; const vlo_config &c = h->cfg;
     MapParams p;
     p.lsharp_pts = sb.lsharp_pts; p.cap_lsharp = h->cap_lsharp; p.lflat_slotted = sb.lflat_slotted; p.N = c.max_points;
-    p.ring_start = sb.ring_start; p.lflat_ring_start = sb.lflat_ring_start; p.counts = sb.counts; p.n_rings = c.n_rings;
+    p.ring_start = sb.ring_start; p.lflat_ring_start = sb.lflat_ring_start; p.counts = sb.counts; p.lflat_d2s = sb.lflat_d2s; p.n_rings = c.n_rings;
     p.scans = d_scans; p.T = h->map_T; p.state = h->map_state; p.result = h->map_result;
     p.idx5 = h->map_idx5; p.qcap = h->cap_lsharp + c.max_points;
     p.partials = h->map_partials; p.pcap = (p.qcap + 31) / 32 + 8; p.ncorr = h->map_ncorr;

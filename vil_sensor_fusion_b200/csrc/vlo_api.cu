@@ -22,7 +22,7 @@ extern "C" void vlo_default_config(vlo_config *c)
     c->odom_max_iterations = 25; c->odom_delta_t_abort = 0.05f; c->odom_delta_r_abort = 0.05f; c->odom_degen_eig = 30.0f;
     c->deskew = 1; c->odom_forward_bound_quirk = 0;
     c->map_max_iterations = 10; c->map_delta_t_abort = 0.05f; c->map_delta_r_abort = 0.05f; c->map_degen_eig = 40.0f;
-    c->map_cell_size = 1.0f; c->odom_cell_size = 1.0f;
+    c->map_cell_size = 1.0f; c->odom_cell_size = 1.0f; c->odom_corner_cell_size = 5.0f;
     c->dopt_rot_threshold = 11.5f; c->dopt_trans_threshold = 28.9f;
     c->cov_accel = 1e-6; c->cov_gyro = 1e-6; c->cov_integration = 1e-8; c->cov_bias_acc = 1e-4;
     c->cov_bias_omega = 1e-6; c->cov_bias_acc_omega_int = 1e-4;
@@ -118,6 +118,7 @@ extern "C" int vlo_create(const vlo_config *cfg, vlo_handle **out)
     HALLOC(sb.counts, (size_t)B * 8);
     HALLOC(sb.sharp_idx, (size_t)B * h->cap_sharp); HALLOC(sb.lsharp_idx, (size_t)B * h->cap_lsharp); HALLOC(sb.flat_idx, (size_t)B * h->cap_flat);
     HALLOC(sb.sharp_pts, (size_t)B * h->cap_sharp); HALLOC(sb.lsharp_pts, (size_t)B * h->cap_lsharp); HALLOC(sb.flat_pts, (size_t)B * h->cap_flat);
+    HALLOC(sb.lflat_d2s, (size_t)B * N);
     HALLOC(sb.lsharp_ring_start, (size_t)B * (VLO_MAX_RINGS + 1)); HALLOC(sb.lflat_ring_start, (size_t)B * (VLO_MAX_RINGS + 1));
     cudaMemset(sb.counts, 0, (size_t)B * 8 * sizeof(int));
     // registration workspace: at most one pair per resident scan
@@ -128,7 +129,7 @@ extern "C" int vlo_create(const vlo_config *cfg, vlo_handle **out)
     HALLOC(h->pair_trace, (size_t)B * 5 * (h->cap_sharp * 2 + h->cap_flat * 3));
     HALLOC(h->pair_result, (size_t)B);
     HALLOC(h->pair_last_T, (size_t)B * 6);
-    { int rc = alloc_gridset(h, h->gs_corner, B, h->cap_lsharp, c.odom_cell_size); if (rc) { vlo_destroy(h); return rc; } }
+    { int rc = alloc_gridset(h, h->gs_corner, B, h->cap_lsharp, c.odom_corner_cell_size > 0.f ? c.odom_corner_cell_size : 5.0f); if (rc) { vlo_destroy(h); return rc; } }
     { int rc = alloc_gridset(h, h->gs_surf, B, N, c.odom_cell_size); if (rc) { vlo_destroy(h); return rc; } }
     HALLOC(h->map_n, 8);
     cudaMemset(h->map_n, 0, 8 * sizeof(int));
@@ -157,7 +158,7 @@ extern "C" void vlo_destroy(vlo_handle *h)
     void *ptrs[] = { sb.raw_owned, sb.raw_offset, sb.first_half, sb.ori_bounds, sb.tile_hist, sb.cloud, sb.ring_start, sb.src_index,
                      sb.label, sb.curvature, sb.picked, sb.slot_sharp, sb.slot_lsharp, sb.slot_flat, sb.slot_cnt, sb.lflat_slotted,
                      sb.lflat_cnt, sb.counts, sb.sharp_idx, sb.lsharp_idx, sb.flat_idx, sb.sharp_pts, sb.lsharp_pts, sb.flat_pts,
-                     sb.lsharp_ring_start, sb.lflat_ring_start, h->status_word, h->pair_T, h->pair_seed, h->pair_last,
+                     sb.lsharp_ring_start, sb.lflat_ring_start, sb.lflat_d2s, h->status_word, h->pair_T, h->pair_seed, h->pair_last,
                      h->pair_cur, h->pair_state, h->pair_cidx, h->pair_sidx, h->pair_trace, h->pair_result, h->pair_last_T, h->map_n,
                      h->map_pts[0], h->map_pts[1], h->map_partials, h->map_idx5, h->map_T, h->map_seed, h->map_state, h->map_ncorr,
                      h->map_scans, h->map_result, h->imu_buf, h->imu_out };
@@ -320,6 +321,7 @@ extern "C" int vlo_register_pairs(vlo_handle *h, const int *last, const int *cur
     VLO_CUDA(cudaMemcpyAsync(pres, h->pair_result, sizeof(vlo_result) * (size_t)n_pairs, cudaMemcpyDeviceToHost, h->stream));
     rc = vlo_synchronize(h); if (rc) return rc;
     memcpy(out, pres, sizeof(vlo_result) * (size_t)n_pairs);
+    for (int p = 0; p < n_pairs; p++) vlo_finish_cov_host(&out[p]);
     h->last_n_pairs = n_pairs;
     int soft = VLO_OK;
     for (int p = 0; p < n_pairs; p++) if (out[p].status == VLO_SOFT_TOO_FEW_CORR) soft = VLO_SOFT_TOO_FEW_CORR;

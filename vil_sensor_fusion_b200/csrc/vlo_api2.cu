@@ -17,6 +17,38 @@ static int ensure_pinned2(vlo_handle *h, size_t bytes)
 }
 
 // ---------------------------------------------------------------------------------------------
+// covariance of a registration result (R4: sigma^2 (AtA)^-1, float64), finished on the host: the
+// device staged sum((s d)^2) in cov[0] and the correspondence count in cov[1]
+static bool inv6d_host(const double *A, double *Ai)
+{
+    double M[6][12];
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) { M[i][j] = A[i * 6 + j]; M[i][6 + j] = (i == j) ? 1.0 : 0.0; }
+    for (int k = 0; k < 6; k++) {
+        int p = k; double mx = fabs(M[k][k]);
+        for (int i = k + 1; i < 6; i++) if (fabs(M[i][k]) > mx) { mx = fabs(M[i][k]); p = i; }
+        if (mx == 0.0) return false;
+        if (p != k) for (int j = 0; j < 12; j++) { double t = M[k][j]; M[k][j] = M[p][j]; M[p][j] = t; }
+        double d = M[k][k];
+        for (int j = 0; j < 12; j++) M[k][j] /= d;
+        for (int i = 0; i < 6; i++) if (i != k) { double f = M[i][k]; for (int j = 0; j < 12; j++) M[i][j] -= f * M[k][j]; }
+    }
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) Ai[i * 6 + j] = M[i][6 + j];
+    return true;
+}
+
+void vlo_finish_cov_host(vlo_result *r)
+{
+    int n = r->n_corr_edge + r->n_corr_plane;
+    if (n <= 0) { for (int i = 0; i < 36; i++) r->cov[i] = 0.0; return; }
+    double ssq = r->cov[0];
+    double dof = n > 6 ? (double)(n - 6) : 1.0, sigma2 = ssq / dof;
+    double Hd[36], Hi[36];
+    for (int i = 0; i < 36; i++) Hd[i] = (double)r->hessian[i];
+    if (inv6d_host(Hd, Hi)) for (int i = 0; i < 36; i++) r->cov[i] = sigma2 * Hi[i];
+    else for (int i = 0; i < 36; i++) r->cov[i] = NAN;
+}
+
+// ---------------------------------------------------------------------------------------------
 // scan-to-map
 extern "C" int vlo_map_build(vlo_handle *h, const float *corner, int n_corner, const float *surf, int n_surf, int on_device)
 {
@@ -62,6 +94,7 @@ extern "C" int vlo_register_map(vlo_handle *h, const int *scans, int n, const fl
     VLO_CUDA(cudaMemcpyAsync(pres, h->map_result, sizeof(vlo_result) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
     rc = vlo_synchronize(h); if (rc) return rc;
     memcpy(out, pres, sizeof(vlo_result) * (size_t)n);
+    for (int k = 0; k < n; k++) vlo_finish_cov_host(&out[k]);
     h->last_n_map = n;
     int soft = VLO_OK;
     for (int k = 0; k < n; k++) if (out[k].status == VLO_SOFT_TOO_FEW_CORR) soft = VLO_SOFT_TOO_FEW_CORR;
@@ -222,8 +255,9 @@ extern "C" int vlo_process_scan(vlo_handle *h, const float *raw, int n_points, i
     int soft = VLO_OK;
     bool did_odom = false;
     if (h->online_have_last) {
-        int pl[2] = { last, cur };
-        float seedT[12];
+        int *pl = poff + 2;                                      // pinned staging (after the offsets)
+        float *seedT = (float *)(pl + 2);
+        pl[0] = last; pl[1] = cur;
         memcpy(seedT, h->online_T, sizeof(float) * 6);          // seed = previous transform (constant velocity)
         memcpy(seedT + 6, h->online_T, sizeof(float) * 6);      // last sweep is moved to its end with the same transform
         VLO_CUDA(cudaMemcpyAsync(h->pair_last, &pl[0], sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -236,6 +270,7 @@ extern "C" int vlo_process_scan(vlo_handle *h, const float *raw, int n_points, i
         VLO_CUDA(cudaMemcpyAsync(pres, h->pair_result, sizeof(vlo_result), cudaMemcpyDeviceToHost, h->stream));
         rc = vlo_synchronize(h); if (rc) return rc;
         h->last_n_pairs = 1;
+        vlo_finish_cov_host(pres);
         if (pres->status == VLO_OK) memcpy(h->online_T, pres->transform, sizeof(float) * 6);
         else soft = pres->status;
         vlo_accumulate_pose(h->online_sum, h->online_T, 1.0f, h->online_sum);

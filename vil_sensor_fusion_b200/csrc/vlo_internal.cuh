@@ -67,6 +67,7 @@ struct ScanBatchDev {
     float4 *sharp_pts, *lsharp_pts, *flat_pts;  // [B][cap]
     float4 *lflat_pts;                          // [B][N] dense
     int   *lsharp_ring_start, *lflat_ring_start; // [B][R+1]
+    int   *lflat_d2s;         // [B][N] dense less-flat index -> slot in lflat_slotted
 };
 
 struct vlo_handle {
@@ -211,6 +212,7 @@ __device__ __forceinline__ float4 vlo_to_start(const float *T, float4 p, int des
 }
 
 // kernels' host launchers -----------------------------------------------------------------------
+void vlo_finish_cov_host(vlo_result *r);
 int vlo_launch_organise(vlo_handle *h);
 int vlo_launch_extract(vlo_handle *h);
 int vlo_grid_build(vlo_handle *h, const GridSet &gs, const GridSource &src, int g_first, int n_grids, int n_slots);
