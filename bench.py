@@ -224,7 +224,7 @@ def run_gpu(args):
 
     # ---- online latency (single scan per call, the online path): p50 / p95 of vlo_process_scan
     p50 = p95 = None
-    if rank == 0:
+    if rank == 0 and not args.no_latency:
         from vil_sensor_fusion_b200 import synth
         cfg1 = api.default_config("HDL-64E", deskew=0, max_scans=2, max_points=131072,
                                   max_map_points=int(max(len(cm), len(sm))), device=local_rank)
@@ -380,6 +380,7 @@ def main():
     ap.add_argument("--batch", type=int, default=128, help="scans per step per GPU")
     ap.add_argument("--impl", default="vlo", choices=["vlo", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true", help="skip the online-tick latency leg (profiling runs)")
     ap.add_argument("--cpu-sample", type=int, default=96, help="scans in the bounded CPU-baseline sample (~15 s on one core)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "vlo" else args.warmup
