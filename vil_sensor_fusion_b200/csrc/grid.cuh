@@ -169,3 +169,91 @@ __device__ void grid_search(const GridSet &gs, int g, float qx, float qy, float 
         if (b2 >= dmax) break;
     }
 }
+
+// ----------------------------------------------------------------------------------------------
+// Thread-level exact search (one query per thread) for searches whose radius is about one cell:
+// scan-to-map 5-NN with d2 < 1 on ~1 m cells.  Round-1 ncu of the warp-cooperative version on this
+// workload: 540 warp-instructions per query, issue-bound, most of it per-query overhead (27 hash
+// probes, prefix scan, per-candidate binary search, 5-round merge).  Here a thread walks the
+// (2 rho + 1)^3 cells around its query nearest-first and skips every cell (and whole rows / slabs)
+// whose box cannot hold a point closer than the current K-th best, so a typical query probes ~8 cells
+// and reads ~50 candidates.  Neighbouring queries (consecutive points of a ring) visit the same cells,
+// which keeps the loads in L1/L2.  Same exactness contract as grid_search: (d2, tie) lexicographic,
+// d2 = ((dx*dx) + (dy*dy)) + (dz*dz), pruning bounds shrunk by `slack` to cover floor() rounding.
+template <int K> struct TopKT {
+    unsigned long long key[K];      // (float bits of d2) << 32 | tie
+    unsigned tag[K];
+    __device__ __forceinline__ void init(float dmax) {
+        #pragma unroll
+        for (int i = 0; i < K; i++) { key[i] = (unsigned long long)__float_as_uint(dmax) << 32; tag[i] = GRID_NOTAG; }
+    }
+    __device__ __forceinline__ float kth() const { return __uint_as_float((unsigned)(key[K - 1] >> 32)); }
+    __device__ __forceinline__ void insert(unsigned long long kk, unsigned tg) {
+        if (kk >= key[K - 1]) return;
+        #pragma unroll
+        for (int i = K - 1; i > 0; i--) {
+            bool a = kk < key[i - 1], b = kk < key[i];
+            key[i] = a ? key[i - 1] : (b ? kk : key[i]);
+            tag[i] = a ? tag[i - 1] : (b ? tg : tag[i]);
+        }
+        if (kk < key[0]) { key[0] = kk; tag[0] = tg; }
+    }
+};
+
+// offset of step a (0, 1, 2, 3, 4, ..) along an axis: 0, +s, -s, +2s, -2s, ..  (s = side of the nearer face)
+__device__ __forceinline__ int grid_step_offset(int a, int s) { int m = (a + 1) >> 1; return (a & 1) ? s * m : -s * m; }
+// lower bound of |q - p| along one axis for points binned `o` cells away from the query's cell c
+__device__ __forceinline__ float grid_axis_lb(int o, int c, float q, float cell, float slack)
+{
+    if (o == 0) return 0.0f;
+    float d = (o > 0) ? ((float)(c + o) * cell - q) - slack : (q - (float)(c + o + 1) * cell) - slack;
+    return fmaxf(d, 0.0f);
+}
+
+template <int K, typename Filter>
+__device__ __forceinline__ void grid_search_thread(const GridSet &gs, int g, float qx, float qy, float qz, float dmax, int rho,
+                                                   const Filter &flt, TopKT<K> &best)
+{
+    const int *start = gs.start + (size_t)g * (gs.ts + 1);
+    const float4 *sorted = gs.sorted + (size_t)g * gs.max_pts;
+    const float cell = gs.cell, slack = 1e-3f * gs.cell;
+    const float fx = qx * gs.inv_cell, fy = qy * gs.inv_cell, fz = qz * gs.inv_cell;
+    const int cx = (int)floorf(fx), cy = (int)floorf(fy), cz = (int)floorf(fz);
+    const int sx = (fx - (float)cx >= 0.5f) ? 1 : -1, sy = (fy - (float)cy >= 0.5f) ? 1 : -1, sz = (fz - (float)cz >= 0.5f) ? 1 : -1;
+    const int side = 2 * rho + 1;
+    best.init(dmax);
+    for (int az = 0; az < side; az++) {
+        const int oz = grid_step_offset(az, sz);
+        const float lz = grid_axis_lb(oz, cz, qz, cell, slack), lz2 = lz * lz;
+        if (lz2 > best.kth()) continue;
+        for (int ay = 0; ay < side; ay++) {
+            const int oy = grid_step_offset(ay, sy);
+            const float ly = grid_axis_lb(oy, cy, qy, cell, slack), lyz2 = ly * ly + lz2;
+            if (lyz2 > best.kth()) continue;
+            for (int ax = 0; ax < side; ax++) {
+                const int ox = grid_step_offset(ax, sx);
+                const float lx = grid_axis_lb(ox, cx, qx, cell, slack);
+                if (lx * lx + lyz2 > best.kth()) continue;
+                const int slot = grid_find(gs, g, cx + ox, cy + oy, cz + oz);
+                if (slot < 0) continue;
+                const int j0 = start[slot], j1 = start[slot + 1];
+                for (int j = j0; j < j1; j++) {
+                    const float4 p = sorted[j];
+                    const float ddx = p.x - qx, ddy = p.y - qy, ddz = p.z - qz;
+                    const float d2 = (ddx * ddx + ddy * ddy) + ddz * ddz;
+                    unsigned tie; const unsigned tag = __float_as_uint(p.w);
+                    if (!(d2 < dmax) || !flt(tag, tie)) continue;
+                    best.insert(((unsigned long long)__float_as_uint(d2) << 32) | tie, tag);
+                }
+            }
+        }
+    }
+}
+
+// cells per axis side the thread search must cover so that no point with d2 < dmax is missed
+static inline int grid_thread_rho(float cell, float dmax)
+{
+    float need = sqrtf(dmax) + 1e-3f * cell;
+    int rho = (int)ceilf(need / cell);
+    return rho < 1 ? 1 : rho;
+}

@@ -465,7 +465,7 @@ struct K1bParams {
     int *counts; int *sharp_idx, *lsharp_idx, *flat_idx; float4 *sharp_pts, *lsharp_pts, *flat_pts;
     int cap_sharp, cap_lsharp, cap_flat; int scan_first;
     int *lsharp_ring_start, *lflat_ring_start;
-    const int *ring_start; int *lflat_d2s;
+    const int *ring_start; const float4 *lflat_slotted; float4 *lflat_pts;
 };
 
 // exclusive scan of one int per thread over a 256-thread block; returns the block total in `total`
@@ -515,11 +515,14 @@ __global__ void __launch_bounds__(256) k1b_compact(K1bParams p)
         if (tid == 0) { p.counts[b * 8 + 1] = ta; p.counts[b * 8 + 2] = tl; p.counts[b * 8 + 3] = tf; p.counts[b * 8 + 4] = tlf; }
     }
     __syncthreads();
-    // dense less-flat index -> slot (consumers address the ring-slotted cloud without a search)
+    // dense less-flat cloud: ring r's centroids move from their ring slot to [lflat_ring_start[r], +cnt)
+    // (coalesced float4 copies; every consumer downstream reads the dense array)
     for (int r = tid >> 5; r < p.n_rings; r += blockDim.x >> 5) {
         int d0 = p.lflat_ring_start[b * (VLO_MAX_RINGS + 1) + r], s0 = p.ring_start[b * (VLO_MAX_RINGS + 1) + r];
         int cnt = p.lflat_cnt[b * p.n_rings + r];
-        for (int j = tid & 31; j < cnt; j += 32) p.lflat_d2s[(size_t)b * p.N + d0 + j] = s0 + j;
+        const float4 *src = p.lflat_slotted + (size_t)b * p.N + s0;
+        float4 *dst = p.lflat_pts + (size_t)b * p.N + d0;
+        for (int j = tid & 31; j < cnt; j += 32) dst[j] = src[j];
     }
     const float4 *cloud = p.cloud + (size_t)b * p.N;
     const int maxq = max(p.max_lsharp, max(p.max_sharp, p.max_flat));
@@ -578,7 +581,7 @@ int vlo_launch_extract(vlo_handle *h)
     q.sharp_pts = sb.sharp_pts; q.lsharp_pts = sb.lsharp_pts; q.flat_pts = sb.flat_pts;
     q.cap_sharp = h->cap_sharp; q.cap_lsharp = h->cap_lsharp; q.cap_flat = h->cap_flat;
     q.lsharp_ring_start = sb.lsharp_ring_start; q.lflat_ring_start = sb.lflat_ring_start;
-    q.ring_start = sb.ring_start; q.lflat_d2s = sb.lflat_d2s;
+    q.ring_start = sb.ring_start; q.lflat_slotted = sb.lflat_slotted; q.lflat_pts = sb.lflat_pts;
     q.scan_first = sb.scan_first;
     VLO_PROF(h, ST_COMPACT, (k1b_compact<<<sb.scan_count, 256, 0, h->stream>>>(q)));
     h->launches += 2;

@@ -18,10 +18,9 @@ struct OdomParams {
     // features of the current sweep (queries) and the previous sweep (targets), per scan
     const float4 *sharp_pts, *flat_pts; int cap_sharp, cap_flat;
     const float4 *lsharp_pts; int cap_lsharp;            // dense ring-major, intensity = ring (+relTime)
-    const float4 *lflat_slotted; int N;                  // ring-slotted
-    const int *ring_start, *lflat_cnt, *lsharp_ring_start, *lflat_ring_start;   // [B][R+1] / [B][R]
+    const float4 *lflat_pts; int N;                      // dense less-flat cloud [B][N]
+    const int *lsharp_ring_start, *lflat_ring_start;     // [B][R+1]
     const int *counts;                                   // [B][8]
-    const int *lflat_d2s;                                // [B][N] dense less-flat index -> slot
     int n_rings;
     // pairs
     const int *pair_last, *pair_cur; float *pair_T; int *pair_state; int *cidx, *sidx; vlo_result *result;
@@ -32,7 +31,7 @@ struct OdomParams {
 
 __device__ __forceinline__ float4 lflat_point(const OdomParams &p, int scan, int dense)
 {
-    return p.lflat_slotted[(size_t)scan * p.N + p.lflat_d2s[(size_t)scan * p.N + dense]];
+    return p.lflat_pts[(size_t)scan * p.N + dense];
 }
 
 __global__ void __launch_bounds__(256) k3_assoc(OdomParams p, int n_pairs)
@@ -341,12 +340,8 @@ __global__ void __launch_bounds__(256) k3_to_end(OdomParams p, const int *scans,
         if (i >= p.counts[scan * 8 + 2]) return;
         ptr = (float4 *)p.lsharp_pts + (size_t)scan * p.cap_lsharp + i;
     } else {
-        const int *rs = p.ring_start + (size_t)scan * (VLO_MAX_RINGS + 1);
-        if (i >= rs[p.n_rings]) return;
-        int lo = 0, hi = p.n_rings;
-        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (rs[mid] <= i) lo = mid; else hi = mid; }
-        if (i - rs[lo] >= p.lflat_cnt[(size_t)scan * p.n_rings + lo]) return;
-        ptr = (float4 *)p.lflat_slotted + (size_t)scan * p.N + i;
+        if (i >= p.counts[scan * 8 + 4]) return;
+        ptr = (float4 *)p.lflat_pts + (size_t)scan * p.N + i;
     }
     float4 v = *ptr;
     float4 q = vlo_to_start(T, v, p.deskew, p.inv_period);
@@ -364,9 +359,9 @@ static OdomParams make_params(vlo_handle *h)
     ScanBatchDev &sb = h->sb; const vlo_config &c = h->cfg;
     OdomParams p;
     p.sharp_pts = sb.sharp_pts; p.flat_pts = sb.flat_pts; p.cap_sharp = h->cap_sharp; p.cap_flat = h->cap_flat;
-    p.lsharp_pts = sb.lsharp_pts; p.cap_lsharp = h->cap_lsharp; p.lflat_slotted = sb.lflat_slotted; p.N = c.max_points;
-    p.ring_start = sb.ring_start; p.lflat_cnt = sb.lflat_cnt; p.lsharp_ring_start = sb.lsharp_ring_start;
-    p.lflat_ring_start = sb.lflat_ring_start; p.counts = sb.counts; p.lflat_d2s = sb.lflat_d2s; p.n_rings = c.n_rings;
+    p.lsharp_pts = sb.lsharp_pts; p.cap_lsharp = h->cap_lsharp; p.lflat_pts = sb.lflat_pts; p.N = c.max_points;
+    p.lsharp_ring_start = sb.lsharp_ring_start;
+    p.lflat_ring_start = sb.lflat_ring_start; p.counts = sb.counts; p.n_rings = c.n_rings;
     p.pair_last = h->pair_last; p.pair_cur = h->pair_cur; p.pair_T = h->pair_T; p.pair_state = h->pair_state;
     p.cidx = h->pair_cidx; p.sidx = h->pair_sidx; p.result = h->pair_result;
     p.gc = h->gs_corner; p.gsf = h->gs_surf;
@@ -386,9 +381,9 @@ int vlo_build_scan_grids(vlo_handle *h, int first, int count)
     sc.n_dense = sb.counts; sc.n_dense_stride = 8; sc.n_dense_field = 2; sc.n_rings = c.n_rings; sc.grid_scan = nullptr;
     int rc = vlo_grid_build(h, h->gs_corner, sc, first, count, h->cap_lsharp); if (rc) return rc;
     GridSource ss;
-    ss.pts = sb.lflat_slotted; ss.pts_stride = (size_t)c.max_points; ss.ring_off = sb.ring_start; ss.ring_off_stride = VLO_MAX_RINGS + 1;
-    ss.ring_cnt = sb.lflat_cnt; ss.ring_cnt_stride = c.n_rings; ss.dense_start = sb.lflat_ring_start; ss.dense_start_stride = VLO_MAX_RINGS + 1;
-    ss.n_dense = nullptr; ss.n_dense_stride = 0; ss.n_dense_field = 0; ss.n_rings = c.n_rings; ss.grid_scan = nullptr;
+    ss.pts = sb.lflat_pts; ss.pts_stride = (size_t)c.max_points; ss.ring_off = nullptr; ss.ring_off_stride = 0;
+    ss.ring_cnt = nullptr; ss.ring_cnt_stride = 0; ss.dense_start = nullptr; ss.dense_start_stride = 0;
+    ss.n_dense = sb.counts; ss.n_dense_stride = 8; ss.n_dense_field = 4; ss.n_rings = c.n_rings; ss.grid_scan = nullptr;
     rc = vlo_grid_build(h, h->gs_surf, ss, first, count, c.max_points); if (rc) return rc;
     return VLO_OK;
 }

@@ -2,7 +2,8 @@
 // Replaces BasicLaserMapping::optimizeTransformTobeMapped of the `loam` nodelet
 // (gtsam_fusion/launch/loam.launch:47-52; knobs loam_params.yaml:44-46,53); SURVEY.md Appendix A.8 is
 // the algorithm, oracle/laser_mapping.c the frozen operation order.  Per Gauss-Newton iteration:
-//   k5_knn   one warp per feature point: pointAssociateToMap + exact 5-NN (d2 < 1) on the map grid
+//   k5_knn   one thread per feature point: pointAssociateToMap + exact 5-NN (d2 < 1) on the map grid
+//            (grid.cuh grid_search_thread: nearest-first cell walk with box pruning)
 //   k5_lin   one thread per feature point: 3x3 covariance eigen (corner) / 5x3 least-squares plane
 //            (surface), residual, Jacobian row, 28 products; level-1 sums of the R1 reduction per
 //            32 consecutive points
@@ -14,14 +15,14 @@
 #include <algorithm>
 
 struct MapParams {
-    const float4 *lsharp_pts; int cap_lsharp; const float4 *lflat_slotted; int N;
-    const int *ring_start, *lflat_ring_start, *counts, *lflat_d2s; int n_rings;
+    const float4 *lsharp_pts; int cap_lsharp; const float4 *lflat_pts; int N;
+    const int *counts; int n_rings;
     const int *scans;            // [n] resident scan index per slot
     float *T; int *state; vlo_result *result;     // per slot
     int *idx5; int qcap;         // [n][qcap][5]
     float *partials; int pcap;   // [n][pcap][28] level-1 sums
     int *ncorr;                  // [n][2]
-    GridSet gm0, gm1; const float4 *map0, *map1; const int *map_n;
+    GridSet gm0, gm1; int rho0, rho1; const float4 *map0, *map1; const int *map_n;
     int max_iter; float degen_thr, dT_abort, dR_abort, rot_thr, trans_thr;
 };
 
@@ -29,9 +30,10 @@ __device__ __forceinline__ float4 map_query_point(const MapParams &p, int scan, 
 {
     corner = i < n_ls;
     if (corner) return p.lsharp_pts[(size_t)scan * p.cap_lsharp + i];
-    int slot = p.lflat_d2s[(size_t)scan * p.N + (i - n_ls)];
-    return p.lflat_slotted[(size_t)scan * p.N + slot];
+    return p.lflat_pts[(size_t)scan * p.N + (i - n_ls)];
 }
+
+#define KNN_THREADS 128
 
 __device__ __forceinline__ float4 to_map(const float *T, const float *trig, float4 pi)
 {
@@ -43,35 +45,30 @@ __device__ __forceinline__ float4 to_map(const float *T, const float *trig, floa
     return make_float4(x + T[3], y + T[4], z + T[5], pi.w);
 }
 
-__global__ void __launch_bounds__(256) k5_knn(MapParams p)
+__global__ void __launch_bounds__(KNN_THREADS, 8) k5_knn(MapParams p)
 {
-    __shared__ int scratch[8][GRID_SCRATCH_INTS];
-    const int k = blockIdx.y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    __shared__ float s_T[6], s_trig[6];
+    const int k = blockIdx.y, tid = threadIdx.x;
     if (p.state[k * 4 + 0]) return;
     const int scan = p.scans[k];
     const int n_ls = p.counts[scan * 8 + 2], n_lf = p.counts[scan * 8 + 4];
+    if (blockIdx.x * KNN_THREADS >= n_ls + n_lf) return;
     if (!(p.map_n[2] > 10 && p.map_n[4] > 100)) return;
-    float T[6], trig[6];
+    if (tid < 6) s_T[tid] = p.T[k * 6 + tid];
+    if (tid < 3) vlo_sincosf(p.T[k * 6 + tid], s_trig[2 * tid], s_trig[2 * tid + 1]);
+    __syncthreads();
+    const int i = blockIdx.x * KNN_THREADS + tid;
+    if (i >= n_ls + n_lf) return;
+    bool corner;
+    float4 ori = map_query_point(p, scan, i, n_ls, corner);
+    float4 sel = to_map(s_T, s_trig, ori);
+    TopKT<5> best;
+    if (corner) grid_search_thread<5>(p.gm0, 0, sel.x, sel.y, sel.z, 1.0f, p.rho0, FilterAll(), best);
+    else        grid_search_thread<5>(p.gm1, 0, sel.x, sel.y, sel.z, 1.0f, p.rho1, FilterAll(), best);
+    int *o = p.idx5 + ((size_t)k * p.qcap + i) * 5;
+    const bool ok = best.tag[4] != GRID_NOTAG;
     #pragma unroll
-    for (int a = 0; a < 6; a++) T[a] = p.T[k * 6 + a];
-    vlo_sincosf(T[0], trig[0], trig[1]); vlo_sincosf(T[1], trig[2], trig[3]); vlo_sincosf(T[2], trig[4], trig[5]);
-    // persistent warps stride over the feature points of this scan
-    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_ls + n_lf; w += n_warps) {
-        bool corner;
-        float4 ori = map_query_point(p, scan, w, n_ls, corner);
-        float4 sel = to_map(T, trig, ori);
-        TopK<5> best;
-        if (corner) grid_search<5>(p.gm0, 0, sel.x, sel.y, sel.z, 1.0f, FilterAll(), best, lane, scratch[warp]);
-        else        grid_search<5>(p.gm1, 0, sel.x, sel.y, sel.z, 1.0f, FilterAll(), best, lane, scratch[warp]);
-        if (lane == 0) {
-            int *o = p.idx5 + ((size_t)k * p.qcap + w) * 5;
-            bool ok = best.tag[4] != GRID_NOTAG;
-            #pragma unroll
-            for (int j = 0; j < 5; j++) o[j] = ok ? (int)(best.tag[j] & 0xFFFFFFu) : -1;
-        }
-    }
+    for (int j = 0; j < 5; j++) o[j] = ok ? (int)(best.tag[j] & 0xFFFFFFu) : -1;
 }
 
 // cyclic Jacobi on a symmetric 3x3; eval ascending, evec[k*3+i] = component i of eigenvector k
@@ -368,22 +365,21 @@ int vlo_launch_register_map(vlo_handle *h, const int *d_scans, int n, const floa
 {
     ScanBatchDev &sb = h->sb; const vlo_config &c = h->cfg;
     MapParams p;
-    p.lsharp_pts = sb.lsharp_pts; p.cap_lsharp = h->cap_lsharp; p.lflat_slotted = sb.lflat_slotted; p.N = c.max_points;
-    p.ring_start = sb.ring_start; p.lflat_ring_start = sb.lflat_ring_start; p.counts = sb.counts; p.lflat_d2s = sb.lflat_d2s; p.n_rings = c.n_rings;
+    p.lsharp_pts = sb.lsharp_pts; p.cap_lsharp = h->cap_lsharp; p.lflat_pts = sb.lflat_pts; p.N = c.max_points;
+    p.counts = sb.counts; p.n_rings = c.n_rings;
     p.scans = d_scans; p.T = h->map_T; p.state = h->map_state; p.result = h->map_result;
     p.idx5 = h->map_idx5; p.qcap = h->cap_lsharp + c.max_points;
     p.partials = h->map_partials; p.pcap = (p.qcap + 31) / 32 + 8; p.ncorr = h->map_ncorr;
-    p.gm0 = h->gs_map[0]; p.gm1 = h->gs_map[1]; p.map0 = h->map_pts[0]; p.map1 = h->map_pts[1]; p.map_n = h->map_n;
+    p.gm0 = h->gs_map[0]; p.gm1 = h->gs_map[1]; p.rho0 = grid_thread_rho(p.gm0.cell, 1.0f); p.rho1 = grid_thread_rho(p.gm1.cell, 1.0f); p.map0 = h->map_pts[0]; p.map1 = h->map_pts[1]; p.map_n = h->map_n;
     p.max_iter = c.map_max_iterations; p.degen_thr = c.map_degen_eig; p.dT_abort = c.map_delta_t_abort;
     p.dR_abort = c.map_delta_r_abort; p.rot_thr = c.dopt_rot_threshold; p.trans_thr = c.dopt_trans_threshold;
     k5_init<<<(n + 127) / 128, 128, 0, h->stream>>>(p, d_seeds, n);
     h->launches += 1;
     // grids sized by the largest feature count actually present would need a sync; use capacity
     int qmax = h->map_qmax > 0 ? h->map_qmax : p.qcap;
-    int knn_ctas = (qmax * 32 + 255) / 256, knn_fill = (148 * 8 + n - 1) / n;
-    dim3 gk(std::max(1, std::min(knn_ctas, knn_fill)), n), gl((qmax + LIN_THREADS - 1) / LIN_THREADS, n);
+    dim3 gk((qmax + KNN_THREADS - 1) / KNN_THREADS, n), gl((qmax + LIN_THREADS - 1) / LIN_THREADS, n);
     for (int it = 0; it < c.map_max_iterations; it++) {
-        VLO_PROF(h, ST_MAP_KNN, (k5_knn<<<gk, 256, 0, h->stream>>>(p)));
+        VLO_PROF(h, ST_MAP_KNN, (k5_knn<<<gk, KNN_THREADS, 0, h->stream>>>(p)));
         VLO_PROF(h, ST_MAP_LIN, (k5_lin<<<gl, LIN_THREADS, 0, h->stream>>>(p)));
         VLO_PROF(h, ST_MAP_SOLVE, (k5_solve<<<n, SOLVE_THREADS, 0, h->stream>>>(p, it)));
         h->launches += 3;

@@ -22,7 +22,7 @@ extern "C" void vlo_default_config(vlo_config *c)
     c->odom_max_iterations = 25; c->odom_delta_t_abort = 0.05f; c->odom_delta_r_abort = 0.05f; c->odom_degen_eig = 30.0f;
     c->deskew = 1; c->odom_forward_bound_quirk = 0;
     c->map_max_iterations = 10; c->map_delta_t_abort = 0.05f; c->map_delta_r_abort = 0.05f; c->map_degen_eig = 40.0f;
-    c->map_cell_size = 1.0f; c->odom_cell_size = 1.0f; c->odom_corner_cell_size = 5.0f;
+    c->map_cell_size = 1.0625f; c->odom_cell_size = 1.0f; c->odom_corner_cell_size = 5.0f;
     c->dopt_rot_threshold = 11.5f; c->dopt_trans_threshold = 28.9f;
     c->cov_accel = 1e-6; c->cov_gyro = 1e-6; c->cov_integration = 1e-8; c->cov_bias_acc = 1e-4;
     c->cov_bias_omega = 1e-6; c->cov_bias_acc_omega_int = 1e-4;
@@ -118,7 +118,7 @@ extern "C" int vlo_create(const vlo_config *cfg, vlo_handle **out)
     HALLOC(sb.counts, (size_t)B * 8);
     HALLOC(sb.sharp_idx, (size_t)B * h->cap_sharp); HALLOC(sb.lsharp_idx, (size_t)B * h->cap_lsharp); HALLOC(sb.flat_idx, (size_t)B * h->cap_flat);
     HALLOC(sb.sharp_pts, (size_t)B * h->cap_sharp); HALLOC(sb.lsharp_pts, (size_t)B * h->cap_lsharp); HALLOC(sb.flat_pts, (size_t)B * h->cap_flat);
-    HALLOC(sb.lflat_d2s, (size_t)B * N);
+    HALLOC(sb.lflat_pts, (size_t)B * N);
     HALLOC(sb.lsharp_ring_start, (size_t)B * (VLO_MAX_RINGS + 1)); HALLOC(sb.lflat_ring_start, (size_t)B * (VLO_MAX_RINGS + 1));
     cudaMemset(sb.counts, 0, (size_t)B * 8 * sizeof(int));
     // registration workspace: at most one pair per resident scan
@@ -158,7 +158,7 @@ extern "C" void vlo_destroy(vlo_handle *h)
     void *ptrs[] = { sb.raw_owned, sb.raw_offset, sb.first_half, sb.ori_bounds, sb.tile_hist, sb.cloud, sb.ring_start, sb.src_index,
                      sb.label, sb.curvature, sb.picked, sb.slot_sharp, sb.slot_lsharp, sb.slot_flat, sb.slot_cnt, sb.lflat_slotted,
                      sb.lflat_cnt, sb.counts, sb.sharp_idx, sb.lsharp_idx, sb.flat_idx, sb.sharp_pts, sb.lsharp_pts, sb.flat_pts,
-                     sb.lsharp_ring_start, sb.lflat_ring_start, sb.lflat_d2s, h->status_word, h->pair_T, h->pair_seed, h->pair_last,
+                     sb.lsharp_ring_start, sb.lflat_ring_start, sb.lflat_pts, h->status_word, h->pair_T, h->pair_seed, h->pair_last,
                      h->pair_cur, h->pair_state, h->pair_cidx, h->pair_sidx, h->pair_trace, h->pair_result, h->pair_last_T, h->map_n,
                      h->map_pts[0], h->map_pts[1], h->map_partials, h->map_idx5, h->map_T, h->map_seed, h->map_state, h->map_ncorr,
                      h->map_scans, h->map_result, h->imu_buf, h->imu_out };
@@ -276,16 +276,7 @@ extern "C" int vlo_scan_get_features(vlo_handle *h, int scan, int8_t *label, flo
     if (flat_idx) VLO_CUDA(cudaMemcpy(flat_idx, sb.flat_idx + (size_t)scan * h->cap_flat, sizeof(int) * (size_t)cnt[3], cudaMemcpyDeviceToHost));
     if (lsharp_ring_start) VLO_CUDA(cudaMemcpy(lsharp_ring_start, sb.lsharp_ring_start + scan * (VLO_MAX_RINGS + 1), sizeof(int) * (size_t)(R + 1), cudaMemcpyDeviceToHost));
     if (lflat_ring_start) VLO_CUDA(cudaMemcpy(lflat_ring_start, sb.lflat_ring_start + scan * (VLO_MAX_RINGS + 1), sizeof(int) * (size_t)(R + 1), cudaMemcpyDeviceToHost));
-    if (less_flat) {
-        std::vector<int> rs(R + 1), lc(R);
-        VLO_CUDA(cudaMemcpy(rs.data(), sb.ring_start + scan * (VLO_MAX_RINGS + 1), sizeof(int) * (size_t)(R + 1), cudaMemcpyDeviceToHost));
-        VLO_CUDA(cudaMemcpy(lc.data(), sb.lflat_cnt + scan * R, sizeof(int) * (size_t)R, cudaMemcpyDeviceToHost));
-        size_t o = 0;
-        for (int r = 0; r < R; r++) {
-            if (lc[r] > 0) VLO_CUDA(cudaMemcpy(less_flat + o * 4, sb.lflat_slotted + scan * N + rs[r], sizeof(float4) * (size_t)lc[r], cudaMemcpyDeviceToHost));
-            o += (size_t)lc[r];
-        }
-    }
+    if (less_flat && cnt[4] > 0) VLO_CUDA(cudaMemcpy(less_flat, sb.lflat_pts + scan * N, sizeof(float4) * (size_t)cnt[4], cudaMemcpyDeviceToHost));
     return VLO_OK;
 }
 

@@ -59,15 +59,14 @@ struct ScanBatchDev {
     int   *slot_lsharp;       // [B][R][NR][max_lsharp]
     int   *slot_flat;         // [B][R][NR][max_flat]
     uint8_t *slot_cnt;        // [B][R][NR][4]  (sharp, lsharp, flat, unused)
-    float4 *lflat_slotted;    // [B][N]  ring r's centroids at [ring_start[r], +lflat_cnt[r])
+    float4 *lflat_slotted;    // [B][N]  K1 scratch: ring r's centroids at [ring_start[r], +lflat_cnt[r]); K1b packs them into lflat_pts
     int   *lflat_cnt;         // [B][R]
     // K1b dense feature packs
     int   *counts;            // [B][8]: n_valid n_sharp n_lsharp n_flat n_lflat status
     int   *sharp_idx, *lsharp_idx, *flat_idx;   // [B][cap]
     float4 *sharp_pts, *lsharp_pts, *flat_pts;  // [B][cap]
-    float4 *lflat_pts;                          // [B][N] dense
+    float4 *lflat_pts;                          // [B][N] dense less-flat cloud (ring-major, ring r at [lflat_ring_start[r], ..))
     int   *lsharp_ring_start, *lflat_ring_start; // [B][R+1]
-    int   *lflat_d2s;         // [B][N] dense less-flat index -> slot in lflat_slotted
 };
 
 struct vlo_handle {
