@@ -114,10 +114,10 @@ def algorithmic_bytes(stage: str, counts, n_map_pts, iters_done):
         return nv * 21 + 4 * nfeat                           # 16 in + 4 curvature + 1 label, + index lists
     if stage == "k1b_compact":
         return 2 * 20 * sum(c["n_sharp"] + c["n_less_sharp"] + c["n_flat"] for c in counts)
-    if stage == "k5_knn":
-        return n_map_pts * 16 + q * 16 + q * 5 * 4           # map read once + queries + 5 indices each
-    if stage == "k5_lin":
-        return q * (16 + 5 * 4 + 5 * 16) + (q // 32 + 1) * 28 * 4   # 116 B per query + level-1 sums
+    if stage == "k5_assoc_lin":
+        # fused association + linearisation: map read once + query in + 5 neighbour indices out + level-1 sums
+        # (the 5 x 16 B neighbour gather of SURVEY 8d's 116 B/query stays on chip in the fused kernel)
+        return n_map_pts * 16 + q * (16 + 5 * 4) + (q // 32 + 1) * 28 * 4
     if stage == "k5_solve":
         return (q // 32 + 1) * 28 * 4
     return 0
@@ -156,6 +156,8 @@ def run_gpu(args):
 
     cfg = api.default_config("HDL-64E", deskew=0, max_scans=B, max_points=131072,
                              max_map_points=int(max(len(cm), len(sm))), device=local_rank)
+    if os.environ.get("VLO_MAP_CELL"):
+        cfg.map_cell_size = float(os.environ["VLO_MAP_CELL"])          # tuning experiments only
     h = api.Handle(cfg)
     h.map_build(cm, sm)
     stream = torch.cuda.ExternalStream(h.stream_ptr(), device=torch.device("cuda", local_rank))

@@ -200,6 +200,28 @@ template <int K> struct TopKT {
     }
 };
 
+// key-only variant for plain k-NN (FilterAll: the tie IS the dense index, so no tag is carried)
+template <int K> struct TopKI {
+    unsigned long long key[K];      // (float bits of d2) << 32 | dense index; low word ~0 = empty
+    __device__ __forceinline__ void init(float dmax) {
+        #pragma unroll
+        for (int i = 0; i < K; i++) key[i] = ((unsigned long long)__float_as_uint(dmax) << 32) | 0xFFFFFFFFull;
+    }
+    __device__ __forceinline__ float kth() const { return __uint_as_float((unsigned)(key[K - 1] >> 32)); }
+    __device__ __forceinline__ bool valid(int i) const { return (unsigned)key[i] != 0xFFFFFFFFu; }
+    __device__ __forceinline__ int index(int i) const { return (int)((unsigned)key[i] & 0xFFFFFFu); }
+    __device__ __forceinline__ void insert(unsigned long long kk, unsigned) {
+        if (kk >= key[K - 1]) return;
+        #pragma unroll
+        for (int i = 0; i < K; i++) {           // bubble the new key down, carrying the displaced one
+            bool lt = kk < key[i];
+            unsigned long long lo = lt ? kk : key[i];
+            kk = lt ? key[i] : kk;
+            key[i] = lo;
+        }
+    }
+};
+
 // offset of step a (0, 1, 2, 3, 4, ..) along an axis: 0, +s, -s, +2s, -2s, ..  (s = side of the nearer face)
 __device__ __forceinline__ int grid_step_offset(int a, int s) { int m = (a + 1) >> 1; return (a & 1) ? s * m : -s * m; }
 // lower bound of |q - p| along one axis for points binned `o` cells away from the query's cell c
@@ -210,9 +232,9 @@ __device__ __forceinline__ float grid_axis_lb(int o, int c, float q, float cell,
     return fmaxf(d, 0.0f);
 }
 
-template <int K, typename Filter>
+template <typename Top, typename Filter>
 __device__ __forceinline__ void grid_search_thread(const GridSet &gs, int g, float qx, float qy, float qz, float dmax, int rho,
-                                                   const Filter &flt, TopKT<K> &best)
+                                                   const Filter &flt, Top &best)
 {
     const int *start = gs.start + (size_t)g * (gs.ts + 1);
     const float4 *sorted = gs.sorted + (size_t)g * gs.max_pts;

@@ -2,11 +2,10 @@
 // Replaces BasicLaserMapping::optimizeTransformTobeMapped of the `loam` nodelet
 // (gtsam_fusion/launch/loam.launch:47-52; knobs loam_params.yaml:44-46,53); SURVEY.md Appendix A.8 is
 // the algorithm, oracle/laser_mapping.c the frozen operation order.  Per Gauss-Newton iteration:
-//   k5_knn   one thread per feature point: pointAssociateToMap + exact 5-NN (d2 < 1) on the map grid
-//            (grid.cuh grid_search_thread: nearest-first cell walk with box pruning)
-//   k5_lin   one thread per feature point: 3x3 covariance eigen (corner) / 5x3 least-squares plane
-//            (surface), residual, Jacobian row, 28 products; level-1 sums of the R1 reduction per
-//            32 consecutive points
+//   k5_assoc_lin  one thread per feature point: pointAssociateToMap + exact 5-NN (d2 < 1) on the map
+//            grid (grid.cuh grid_search_thread: nearest-first cell walk with box pruning), then
+//            3x3 covariance eigen (corner) / 5x3 least-squares plane (surface), residual, Jacobian
+//            row, 28 products; level-1 sums of the R1 reduction per 32 consecutive points
 //   k5_solve one CTA per scan: levels 2/3 of R1 in fixed order, QR solve, (iteration 0) single-warp
 //            Jacobi degeneracy test + remapping, pose update, convergence flag, result record
 // All launches are enqueued back to back; converged scans skip work through a device flag.
@@ -43,32 +42,6 @@ __device__ __forceinline__ float4 to_map(const float *T, const float *trig, floa
     float y0 = y; y = cx * y0 - sx * z; z = sx * y0 + cx * z;
     x0 = x;       x = cy * x0 + sy * z; z = cy * z - sy * x0;
     return make_float4(x + T[3], y + T[4], z + T[5], pi.w);
-}
-
-__global__ void __launch_bounds__(KNN_THREADS, 8) k5_knn(MapParams p)
-{
-    __shared__ float s_T[6], s_trig[6];
-    const int k = blockIdx.y, tid = threadIdx.x;
-    if (p.state[k * 4 + 0]) return;
-    const int scan = p.scans[k];
-    const int n_ls = p.counts[scan * 8 + 2], n_lf = p.counts[scan * 8 + 4];
-    if (blockIdx.x * KNN_THREADS >= n_ls + n_lf) return;
-    if (!(p.map_n[2] > 10 && p.map_n[4] > 100)) return;
-    if (tid < 6) s_T[tid] = p.T[k * 6 + tid];
-    if (tid < 3) vlo_sincosf(p.T[k * 6 + tid], s_trig[2 * tid], s_trig[2 * tid + 1]);
-    __syncthreads();
-    const int i = blockIdx.x * KNN_THREADS + tid;
-    if (i >= n_ls + n_lf) return;
-    bool corner;
-    float4 ori = map_query_point(p, scan, i, n_ls, corner);
-    float4 sel = to_map(s_T, s_trig, ori);
-    TopKT<5> best;
-    if (corner) grid_search_thread<5>(p.gm0, 0, sel.x, sel.y, sel.z, 1.0f, p.rho0, FilterAll(), best);
-    else        grid_search_thread<5>(p.gm1, 0, sel.x, sel.y, sel.z, 1.0f, p.rho1, FilterAll(), best);
-    int *o = p.idx5 + ((size_t)k * p.qcap + i) * 5;
-    const bool ok = best.tag[4] != GRID_NOTAG;
-    #pragma unroll
-    for (int j = 0; j < 5; j++) o[j] = ok ? (int)(best.tag[j] & 0xFFFFFFu) : -1;
 }
 
 // cyclic Jacobi on a symmetric 3x3; eval ascending, evec[k*3+i] = component i of eigenvector k
@@ -205,45 +178,55 @@ __device__ inline bool map_plane_coeff(float4 sel, const float4 *nb, float *coef
     return (double)s > 0.1;
 }
 
-#define LIN_THREADS 256
 #define LSTRIDE 29
 
-__global__ void __launch_bounds__(LIN_THREADS) k5_lin(MapParams p)
+// One Gauss-Newton linearisation of a batch: thread i of slot k owns feature point i of the scan
+// (corners first, then surface points) and does association AND linearisation -- exact 5-NN on the
+// map grid, line / plane fit, residual, Jacobian row, 28 products -- so the neighbour coordinates
+// never leave the SM between the two; each warp then closes level 1 of the R1 sum (32 consecutive
+// points, sequential order) through a shared-memory transpose.
+__global__ void __launch_bounds__(KNN_THREADS, 4) k5_assoc_lin(MapParams p)
 {
-    __shared__ float terms[LIN_THREADS * LSTRIDE];
+    __shared__ float terms[KNN_THREADS * LSTRIDE];
+    __shared__ float s_T[6], s_trig[6];
     __shared__ int s_ne, s_np;
     const int k = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     if (p.state[k * 4 + 0]) return;
     const int scan = p.scans[k];
     const int n_ls = p.counts[scan * 8 + 2], n_lf = p.counts[scan * 8 + 4];
     const int q_total = n_ls + n_lf;
-    const int i = blockIdx.x * LIN_THREADS + tid;
-    if (blockIdx.x * LIN_THREADS >= q_total) return;
+    if (blockIdx.x * KNN_THREADS >= q_total) return;
     if (!(p.map_n[2] > 10 && p.map_n[4] > 100)) return;
+    if (tid < 6) s_T[tid] = p.T[k * 6 + tid];
+    if (tid < 3) vlo_sincosf(p.T[k * 6 + tid], s_trig[2 * tid], s_trig[2 * tid + 1]);
     if (tid == 0) { s_ne = 0; s_np = 0; }
-    float T[6], trig[6];
-    #pragma unroll
-    for (int a = 0; a < 6; a++) T[a] = p.T[k * 6 + a];
-    vlo_sincosf(T[0], trig[0], trig[1]); vlo_sincosf(T[1], trig[2], trig[3]); vlo_sincosf(T[2], trig[4], trig[5]);
+    __syncthreads();
+    const int i = blockIdx.x * KNN_THREADS + tid;
     float t[VLO_NTERM];
     #pragma unroll
     for (int e = 0; e < VLO_NTERM; e++) t[e] = 0.0f;
     int my_e = 0, my_p = 0;
     if (i < q_total) {
-        const int *id = p.idx5 + ((size_t)k * p.qcap + i) * 5;
-        if (id[4] >= 0) {
-            bool corner;
-            float4 ori = map_query_point(p, scan, i, n_ls, corner);
-            float4 sel = to_map(T, trig, ori);
+        bool corner;
+        const float4 ori = map_query_point(p, scan, i, n_ls, corner);
+        const float4 sel = to_map(s_T, s_trig, ori);
+        TopKI<5> best;
+        if (corner) grid_search_thread(p.gm0, 0, sel.x, sel.y, sel.z, 1.0f, p.rho0, FilterAll(), best);
+        else        grid_search_thread(p.gm1, 0, sel.x, sel.y, sel.z, 1.0f, p.rho1, FilterAll(), best);
+        const bool ok = best.valid(4);
+        int *o = p.idx5 + ((size_t)k * p.qcap + i) * 5;
+        #pragma unroll
+        for (int j = 0; j < 5; j++) o[j] = ok ? best.index(j) : -1;
+        if (ok) {
             const float4 *map = corner ? p.map0 : p.map1;
             float4 nb[5];
             #pragma unroll
-            for (int j = 0; j < 5; j++) nb[j] = map[id[j]];
+            for (int j = 0; j < 5; j++) nb[j] = map[best.index(j)];
             float coeff[4];
             bool keep = corner ? map_edge_coeff(sel, nb, coeff) : map_plane_coeff(sel, nb, coeff);
             if (keep) {
                 if (corner) my_e = 1; else my_p = 1;
-                float srx = trig[0], crx = trig[1], sry = trig[2], cry = trig[3], srz = trig[4], crz = trig[5];
+                float srx = s_trig[0], crx = s_trig[1], sry = s_trig[2], cry = s_trig[3], srz = s_trig[4], crz = s_trig[5];
                 float x = ori.x, y = ori.y, z = ori.z, cx_ = coeff[0], cy_ = coeff[1], cz_ = coeff[2];
                 float row[6];
                 row[0] = (crx * sry * srz * x + crx * crz * sry * y - srx * sry * z) * cx_
@@ -270,20 +253,19 @@ __global__ void __launch_bounds__(LIN_THREADS) k5_lin(MapParams p)
     #pragma unroll
     for (int e = 0; e < VLO_NTERM; e++) terms[tid * LSTRIDE + e] = t[e];
     unsigned be = __reduce_add_sync(0xffffffffu, my_e), bp = __reduce_add_sync(0xffffffffu, my_p);
+    if (lane == 0 && (be | bp)) { atomicAdd(&s_ne, (int)be); atomicAdd(&s_np, (int)bp); }
     __syncthreads();
-    if (lane == 0) { atomicAdd(&s_ne, (int)be); atomicAdd(&s_np, (int)bp); }
-    if (tid < 8 * VLO_NTERM) {
+    if (tid < (KNN_THREADS / 32) * VLO_NTERM) {
         int g = tid / VLO_NTERM, e = tid % VLO_NTERM;
-        if (blockIdx.x * LIN_THREADS + g * 32 < q_total) {
+        if (blockIdx.x * KNN_THREADS + g * 32 < q_total) {
             float l1 = 0.0f;
             const float *src = terms + (size_t)(g * 32) * LSTRIDE + e;
             #pragma unroll 8
             for (int q = 0; q < 32; q++) l1 = l1 + src[(size_t)q * LSTRIDE];
-            p.partials[((size_t)k * p.pcap + blockIdx.x * 8 + g) * VLO_NTERM + e] = l1;
+            p.partials[((size_t)k * p.pcap + blockIdx.x * (KNN_THREADS / 32) + g) * VLO_NTERM + e] = l1;
         }
     }
-    __syncthreads();
-    if (tid == 0) { atomicAdd(&p.ncorr[k * 2], s_ne); atomicAdd(&p.ncorr[k * 2 + 1], s_np); }
+    if (tid == 0 && (s_ne | s_np)) { atomicAdd(&p.ncorr[k * 2], s_ne); atomicAdd(&p.ncorr[k * 2 + 1], s_np); }
 }
 
 #define SOLVE_THREADS 256
@@ -377,12 +359,11 @@ int vlo_launch_register_map(vlo_handle *h, const int *d_scans, int n, const floa
     h->launches += 1;
     // grids sized by the largest feature count actually present would need a sync; use capacity
     int qmax = h->map_qmax > 0 ? h->map_qmax : p.qcap;
-    dim3 gk((qmax + KNN_THREADS - 1) / KNN_THREADS, n), gl((qmax + LIN_THREADS - 1) / LIN_THREADS, n);
+    dim3 gk((qmax + KNN_THREADS - 1) / KNN_THREADS, n);
     for (int it = 0; it < c.map_max_iterations; it++) {
-        VLO_PROF(h, ST_MAP_KNN, (k5_knn<<<gk, KNN_THREADS, 0, h->stream>>>(p)));
-        VLO_PROF(h, ST_MAP_LIN, (k5_lin<<<gl, LIN_THREADS, 0, h->stream>>>(p)));
+        VLO_PROF(h, ST_MAP_LIN, (k5_assoc_lin<<<gk, KNN_THREADS, 0, h->stream>>>(p)));
         VLO_PROF(h, ST_MAP_SOLVE, (k5_solve<<<n, SOLVE_THREADS, 0, h->stream>>>(p, it)));
-        h->launches += 3;
+        h->launches += 2;
     }
     VLO_CUDA(cudaGetLastError());
     return VLO_OK;
