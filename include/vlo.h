@@ -20,6 +20,7 @@
  *                              (+ gtsam PreintegratedCombinedMeasurements::integrateMeasurement it calls, :50-52,64)
  *   vlo_pose_diff              SensorManagerRos::poseDiff, gtsam_fusion/src/gtsam_fusion/SensorManagerRos.cpp:122-158
  *   vlo_process_scan           one LOAM tick of the online path
+ *   vlo_bag_register_*         offline replay of a whole bag through the same nodelets (loam.launch:54-57)
  *
  * Status: 0 ok; <0 error (vlo_last_error has text); >0 soft conditions mirroring the reference's
  * silent drops (e.g. VLO_SOFT_TOO_FEW_CORR).
@@ -181,6 +182,23 @@ int vlo_online_reset(vlo_handle *h);
 /* accumulated odometry pose (transformSum) and last mapped pose (transformAftMapped), LOAM order/axes */
 int vlo_online_pose(vlo_handle *h, float *sum6, float *mapped6);
 int vlo_online_set_map_pose(vlo_handle *h, const float *pose6);
+
+/* ---------------------------------------------------------------- whole-bag streaming */
+/* Offline reprocessing of a bag handed over as host batches (each <= max_scans/2 scans; `raw`/`offsets` as in
+ * vlo_scans_upload, host memory, pinned for full PCIe rate).  Batch k+1 is copied to the device on a second
+ * stream while batch k's kernels run; one synchronisation at the end.  Replaces replaying the bag through the
+ * `loam` nodelets (gtsam_fusion/launch/loam.launch:54-57 `rosbag play`; vil_fusion/python/quick_autoexperiments.py:49-50).
+ *   vlo_bag_register_map  : scan-to-map of every scan from seeds[n_scans*6]; out = sum(n_scans) records in order
+ *   vlo_bag_register_pairs: scan-to-scan of the consecutive pairs (i, i+1) inside each batch from seeds[(n_scans-1)*6]
+ *                           (NULL = zero seed); out = sum(n_scans - 1) records; overlap batches by one frame to chain */
+typedef struct vlo_bag_batch {
+    const float *raw;          /* concatenated clouds of this batch (host) */
+    const int   *offsets;      /* n_scans + 1 point offsets into raw */
+    int          n_scans;
+    const float *seeds;
+} vlo_bag_batch;
+int vlo_bag_register_map(vlo_handle *h, const vlo_bag_batch *batches, int n_batches, int stride_floats, vlo_result *out);
+int vlo_bag_register_pairs(vlo_handle *h, const vlo_bag_batch *batches, int n_batches, int stride_floats, vlo_result *out);
 
 /* ---------------------------------------------------------------- IMU */
 /* Batched IMUManager::getFactor over one time-sorted sample stream (host pointers):

@@ -36,6 +36,10 @@ class Result(C.Structure):
     ]
 
 
+class BagBatch(C.Structure):
+    _fields_ = [("raw", C.c_void_p), ("offsets", C.c_void_p), ("n_scans", C.c_int), ("seeds", C.c_void_p)]
+
+
 class FeatureCounts(C.Structure):
     _fields_ = [("n_valid", C.c_int), ("n_sharp", C.c_int), ("n_less_sharp", C.c_int), ("n_flat", C.c_int),
                 ("n_less_flat", C.c_int)]
@@ -83,6 +87,8 @@ SYMBOLS = {
     "vlo_online_pose": (C.c_int, [_VP, _VP, _VP]),
     "vlo_online_set_map_pose": (C.c_int, [_VP, _VP]),
     "vlo_process_scan": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_double, C.POINTER(Result), C.POINTER(Result)]),
+    "vlo_bag_register_map": (C.c_int, [_VP, C.POINTER(BagBatch), C.c_int, C.c_int, _VP]),
+    "vlo_bag_register_pairs": (C.c_int, [_VP, C.POINTER(BagBatch), C.c_int, C.c_int, _VP]),
     "vlo_imu_preintegrate_batch": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, _VP, _VP, _VP, C.c_int, _VP]),
     "vlo_pose_diff": (None, [_VP, _VP, _VP]),
     "vlo_dopt_gate": (C.c_int, [_VP, C.c_double, C.c_double, C.POINTER(C.c_float), C.POINTER(C.c_float)]),

@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import Config, FeatureCounts, Preint, Result
+from ._lib import BagBatch, Config, FeatureCounts, Preint, Result
 
 LIDAR = {"VLP-16": (-15.0, 15.0, 16), "HDL-32": (-30.67, 10.67, 32), "HDL-64E": (-24.9, 2.0, 64)}
 
@@ -232,6 +232,36 @@ class Handle:
         o = np.frombuffer(bytes(odom), RESULT_DTYPE)[0]
         m = np.frombuffer(bytes(mapped), RESULT_DTYPE)[0] if want_map else None
         return rc, o, m
+
+    # ---- whole-bag streaming (copy of batch k+1 overlaps the kernels of batch k)
+    def _bag(self, fn, batches, stride, pairs: bool) -> np.ndarray:
+        """batches: list of (raw, offsets, seeds); raw = host float32 array or an int address of pinned memory."""
+        arr = (BagBatch * len(batches))()
+        keep = []
+        n_out = 0
+        for i, (raw, offsets, seeds) in enumerate(batches):
+            offsets = np.ascontiguousarray(offsets, np.int32)
+            n = len(offsets) - 1
+            if not isinstance(raw, int):
+                raw = np.ascontiguousarray(raw, np.float32)
+            if seeds is not None:
+                seeds = np.ascontiguousarray(seeds, np.float32).reshape(n - 1 if pairs else n, 6)
+            keep.append((raw, offsets, seeds))
+            arr[i].raw = raw if isinstance(raw, int) else raw.ctypes.data
+            arr[i].offsets = offsets.ctypes.data
+            arr[i].n_scans = n
+            arr[i].seeds = None if seeds is None else seeds.ctypes.data
+            n_out += (n - 1) if pairs else n
+        out = np.zeros(max(n_out, 1), RESULT_DTYPE)
+        self._check(fn(self._h, arr, len(batches), stride, _ptr(out)))
+        self.n_scans = 2 * (self.cfg.max_scans // 2)
+        return out[:n_out]
+
+    def bag_register_map(self, batches, stride: int = 4) -> np.ndarray:
+        return self._bag(self.lib.vlo_bag_register_map, batches, stride, False)
+
+    def bag_register_pairs(self, batches, stride: int = 4) -> np.ndarray:
+        return self._bag(self.lib.vlo_bag_register_pairs, batches, stride, True)
 
     # ---- IMU
     def imu_preintegrate_batch(self, t, acc, gyro, t0, t1, bias=None) -> np.ndarray:
