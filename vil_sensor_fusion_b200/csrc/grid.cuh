@@ -203,9 +203,10 @@ template <int K> struct TopKT {
 // key-only variant for plain k-NN (FilterAll: the tie IS the dense index, so no tag is carried)
 template <int K> struct TopKI {
     unsigned long long key[K];      // (float bits of d2) << 32 | dense index; low word ~0 = empty
-    __device__ __forceinline__ void init(float dmax) {
+    // placeholders admit every key with d2 <= thr (the search pre-filters d2 < dmax, so thr = dmax stays exclusive)
+    __device__ __forceinline__ void init(float thr) {
         #pragma unroll
-        for (int i = 0; i < K; i++) key[i] = ((unsigned long long)__float_as_uint(dmax) << 32) | 0xFFFFFFFFull;
+        for (int i = 0; i < K; i++) key[i] = ((unsigned long long)__float_as_uint(thr) << 32) | 0xFFFFFFFFull;
     }
     __device__ __forceinline__ float kth() const { return __uint_as_float((unsigned)(key[K - 1] >> 32)); }
     __device__ __forceinline__ bool valid(int i) const { return (unsigned)key[i] != 0xFFFFFFFFu; }
@@ -232,9 +233,11 @@ __device__ __forceinline__ float grid_axis_lb(int o, int c, float q, float cell,
     return fmaxf(d, 0.0f);
 }
 
+// `bound` < dmax (optional): a distance known to be reached by at least K admissible points (e.g. the previous
+// iteration's neighbours seen from the new pose) -- the walk then starts with a tight pruning radius.
 template <typename Top, typename Filter>
 __device__ __forceinline__ void grid_search_thread(const GridSet &gs, int g, float qx, float qy, float qz, float dmax, int rho,
-                                                   const Filter &flt, Top &best)
+                                                   const Filter &flt, Top &best, float bound = -1.0f)
 {
     const int *start = gs.start + (size_t)g * (gs.ts + 1);
     const float4 *sorted = gs.sorted + (size_t)g * gs.max_pts;
@@ -243,7 +246,7 @@ __device__ __forceinline__ void grid_search_thread(const GridSet &gs, int g, flo
     const int cx = (int)floorf(fx), cy = (int)floorf(fy), cz = (int)floorf(fz);
     const int sx = (fx - (float)cx >= 0.5f) ? 1 : -1, sy = (fy - (float)cy >= 0.5f) ? 1 : -1, sz = (fz - (float)cz >= 0.5f) ? 1 : -1;
     const int side = 2 * rho + 1;
-    best.init(dmax);
+    best.init((bound >= 0.0f && bound < dmax) ? bound : dmax);
     for (int az = 0; az < side; az++) {
         const int oz = grid_step_offset(az, sz);
         const float lz = grid_axis_lb(oz, cz, qz, cell, slack), lz2 = lz * lz;

@@ -12,6 +12,7 @@
 #include "grid.cuh"
 #include "dense6.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 struct MapParams {
     const float4 *lsharp_pts; int cap_lsharp; const float4 *lflat_pts; int N;
@@ -180,92 +181,109 @@ __device__ inline bool map_plane_coeff(float4 sel, const float4 *nb, float *coef
 
 #define LSTRIDE 29
 
-// One Gauss-Newton linearisation of a batch: thread i of slot k owns feature point i of the scan
-// (corners first, then surface points) and does association AND linearisation -- exact 5-NN on the
-// map grid, line / plane fit, residual, Jacobian row, 28 products -- so the neighbour coordinates
-// never leave the SM between the two; each warp then closes level 1 of the R1 sum (32 consecutive
-// points, sequential order) through a shared-memory transpose.
-__global__ void __launch_bounds__(KNN_THREADS, 4) k5_assoc_lin(MapParams p)
+// One Gauss-Newton linearisation of a batch.  Warp tile t of slot k owns feature points [32 t, 32 t + 32) of
+// the scan (corners first, then surface points); a thread does association AND linearisation for its
+// point -- exact 5-NN on the map grid, line / plane fit, residual, Jacobian row, 28 products -- so the
+// neighbour coordinates never leave the SM between the two; the warp then closes level 1 of the R1 sum
+// (its 32 consecutive points, sequential order) through a per-warp shared-memory transpose.  Warps are
+// independent (no block barrier) and persistent: tile = blockIdx.x * warps + warp, strided by the grid.
+// From the second iteration on, the previous iteration's neighbours (still in idx5) seen from the new pose
+// bound the 5th-neighbour distance, so the cell walk starts with a tight pruning radius.
+#define AL_WARPS (KNN_THREADS / 32)
+__global__ void __launch_bounds__(KNN_THREADS, 5) k5_assoc_lin(MapParams p, int it)
 {
-    __shared__ float terms[KNN_THREADS * LSTRIDE];
-    __shared__ float s_T[6], s_trig[6];
-    __shared__ int s_ne, s_np;
-    const int k = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    __shared__ float terms[AL_WARPS][32 * LSTRIDE];
+    const int k = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (p.state[k * 4 + 0]) return;
     const int scan = p.scans[k];
     const int n_ls = p.counts[scan * 8 + 2], n_lf = p.counts[scan * 8 + 4];
-    const int q_total = n_ls + n_lf;
-    if (blockIdx.x * KNN_THREADS >= q_total) return;
+    const int q_total = n_ls + n_lf, n_tiles = (q_total + 31) >> 5;
+    if (blockIdx.x * AL_WARPS >= n_tiles) return;
     if (!(p.map_n[2] > 10 && p.map_n[4] > 100)) return;
-    if (tid < 6) s_T[tid] = p.T[k * 6 + tid];
-    if (tid < 3) vlo_sincosf(p.T[k * 6 + tid], s_trig[2 * tid], s_trig[2 * tid + 1]);
-    if (tid == 0) { s_ne = 0; s_np = 0; }
-    __syncthreads();
-    const int i = blockIdx.x * KNN_THREADS + tid;
-    float t[VLO_NTERM];
-    #pragma unroll
-    for (int e = 0; e < VLO_NTERM; e++) t[e] = 0.0f;
-    int my_e = 0, my_p = 0;
-    if (i < q_total) {
-        bool corner;
-        const float4 ori = map_query_point(p, scan, i, n_ls, corner);
-        const float4 sel = to_map(s_T, s_trig, ori);
-        TopKI<5> best;
-        if (corner) grid_search_thread(p.gm0, 0, sel.x, sel.y, sel.z, 1.0f, p.rho0, FilterAll(), best);
-        else        grid_search_thread(p.gm1, 0, sel.x, sel.y, sel.z, 1.0f, p.rho1, FilterAll(), best);
-        const bool ok = best.valid(4);
-        int *o = p.idx5 + ((size_t)k * p.qcap + i) * 5;
+    float T[6], trig[6];
+    {
+        float sv = 0.0f, cv = 0.0f;
+        if (lane < 3) vlo_sincosf(p.T[k * 6 + lane], sv, cv);
         #pragma unroll
-        for (int j = 0; j < 5; j++) o[j] = ok ? best.index(j) : -1;
-        if (ok) {
+        for (int a = 0; a < 3; a++) { trig[2 * a] = __shfl_sync(0xffffffffu, sv, a); trig[2 * a + 1] = __shfl_sync(0xffffffffu, cv, a); }
+        #pragma unroll
+        for (int a = 0; a < 6; a++) T[a] = p.T[k * 6 + a];
+    }
+    float *wterms = terms[warp];
+    int tot_e = 0, tot_p = 0;
+    for (int tile = blockIdx.x * AL_WARPS + warp; tile < n_tiles; tile += gridDim.x * AL_WARPS) {
+        const int i = tile * 32 + lane;
+        float t[VLO_NTERM];
+        #pragma unroll
+        for (int e = 0; e < VLO_NTERM; e++) t[e] = 0.0f;
+        int my_e = 0, my_p = 0;
+        if (i < q_total) {
+            bool corner;
+            const float4 ori = map_query_point(p, scan, i, n_ls, corner);
+            const float4 sel = to_map(T, trig, ori);
             const float4 *map = corner ? p.map0 : p.map1;
-            float4 nb[5];
+            int *o = p.idx5 + ((size_t)k * p.qcap + i) * 5;
+            float bound = -1.0f;
+            if (it > 0 && o[4] >= 0) {
+                bound = 0.0f;
+                #pragma unroll
+                for (int j = 0; j < 5; j++) {
+                    const float4 m = map[o[j]];
+                    const float ddx = m.x - sel.x, ddy = m.y - sel.y, ddz = m.z - sel.z;
+                    bound = fmaxf(bound, (ddx * ddx + ddy * ddy) + ddz * ddz);
+                }
+            }
+            TopKI<5> best;
+            if (corner) grid_search_thread(p.gm0, 0, sel.x, sel.y, sel.z, 1.0f, p.rho0, FilterAll(), best, bound);
+            else        grid_search_thread(p.gm1, 0, sel.x, sel.y, sel.z, 1.0f, p.rho1, FilterAll(), best, bound);
+            const bool ok = best.valid(4);
             #pragma unroll
-            for (int j = 0; j < 5; j++) nb[j] = map[best.index(j)];
-            float coeff[4];
-            bool keep = corner ? map_edge_coeff(sel, nb, coeff) : map_plane_coeff(sel, nb, coeff);
-            if (keep) {
-                if (corner) my_e = 1; else my_p = 1;
-                float srx = s_trig[0], crx = s_trig[1], sry = s_trig[2], cry = s_trig[3], srz = s_trig[4], crz = s_trig[5];
-                float x = ori.x, y = ori.y, z = ori.z, cx_ = coeff[0], cy_ = coeff[1], cz_ = coeff[2];
-                float row[6];
-                row[0] = (crx * sry * srz * x + crx * crz * sry * y - srx * sry * z) * cx_
-                       + (-srx * srz * x - crz * srx * y - crx * z) * cy_
-                       + (crx * cry * srz * x + crx * cry * crz * y - cry * srx * z) * cz_;
-                row[1] = ((cry * srx * srz - crz * sry) * x + (sry * srz + cry * crz * srx) * y + crx * cry * z) * cx_
-                       + ((-cry * crz - srx * sry * srz) * x + (cry * srz - crz * srx * sry) * y - crx * sry * z) * cz_;
-                row[2] = ((crz * srx * sry - cry * srz) * x + (-cry * crz - srx * sry * srz) * y) * cx_
-                       + (crx * crz * x - crx * srz * y) * cy_
-                       + ((sry * srz + cry * crz * srx) * x + (crz * sry - cry * srx * srz) * y) * cz_;
-                row[3] = cx_; row[4] = cy_; row[5] = cz_;
-                float bval = -coeff[3];
-                int e = 0;
+            for (int j = 0; j < 5; j++) o[j] = ok ? best.index(j) : -1;
+            if (ok) {
+                float4 nb[5];
                 #pragma unroll
-                for (int a = 0; a < 6; a++)
+                for (int j = 0; j < 5; j++) nb[j] = map[best.index(j)];
+                float coeff[4];
+                bool keep = corner ? map_edge_coeff(sel, nb, coeff) : map_plane_coeff(sel, nb, coeff);
+                if (keep) {
+                    if (corner) my_e = 1; else my_p = 1;
+                    float srx = trig[0], crx = trig[1], sry = trig[2], cry = trig[3], srz = trig[4], crz = trig[5];
+                    float x = ori.x, y = ori.y, z = ori.z, cx_ = coeff[0], cy_ = coeff[1], cz_ = coeff[2];
+                    float row[6];
+                    row[0] = (crx * sry * srz * x + crx * crz * sry * y - srx * sry * z) * cx_
+                           + (-srx * srz * x - crz * srx * y - crx * z) * cy_
+                           + (crx * cry * srz * x + crx * cry * crz * y - cry * srx * z) * cz_;
+                    row[1] = ((cry * srx * srz - crz * sry) * x + (sry * srz + cry * crz * srx) * y + crx * cry * z) * cx_
+                           + ((-cry * crz - srx * sry * srz) * x + (cry * srz - crz * srx * sry) * y - crx * sry * z) * cz_;
+                    row[2] = ((crz * srx * sry - cry * srz) * x + (-cry * crz - srx * sry * srz) * y) * cx_
+                           + (crx * crz * x - crx * srz * y) * cy_
+                           + ((sry * srz + cry * crz * srx) * x + (crz * sry - cry * srx * srz) * y) * cz_;
+                    row[3] = cx_; row[4] = cy_; row[5] = cz_;
+                    float bval = -coeff[3];
+                    int e = 0;
                     #pragma unroll
-                    for (int b = a; b < 6; b++) t[e++] = row[a] * row[b];
-                #pragma unroll
-                for (int a = 0; a < 6; a++) t[e++] = row[a] * bval;
-                t[e] = coeff[3] * coeff[3];
+                    for (int a = 0; a < 6; a++)
+                        #pragma unroll
+                        for (int b = a; b < 6; b++) t[e++] = row[a] * row[b];
+                    #pragma unroll
+                    for (int a = 0; a < 6; a++) t[e++] = row[a] * bval;
+                    t[e] = coeff[3] * coeff[3];
+                }
             }
         }
-    }
-    #pragma unroll
-    for (int e = 0; e < VLO_NTERM; e++) terms[tid * LSTRIDE + e] = t[e];
-    unsigned be = __reduce_add_sync(0xffffffffu, my_e), bp = __reduce_add_sync(0xffffffffu, my_p);
-    if (lane == 0 && (be | bp)) { atomicAdd(&s_ne, (int)be); atomicAdd(&s_np, (int)bp); }
-    __syncthreads();
-    if (tid < (KNN_THREADS / 32) * VLO_NTERM) {
-        int g = tid / VLO_NTERM, e = tid % VLO_NTERM;
-        if (blockIdx.x * KNN_THREADS + g * 32 < q_total) {
+        __syncwarp();                       // the previous tile's column sums are done with wterms
+        #pragma unroll
+        for (int e = 0; e < VLO_NTERM; e++) wterms[lane * LSTRIDE + e] = t[e];
+        tot_e += (int)__reduce_add_sync(0xffffffffu, my_e); tot_p += (int)__reduce_add_sync(0xffffffffu, my_p);
+        __syncwarp();
+        if (lane < VLO_NTERM) {
             float l1 = 0.0f;
-            const float *src = terms + (size_t)(g * 32) * LSTRIDE + e;
             #pragma unroll 8
-            for (int q = 0; q < 32; q++) l1 = l1 + src[(size_t)q * LSTRIDE];
-            p.partials[((size_t)k * p.pcap + blockIdx.x * (KNN_THREADS / 32) + g) * VLO_NTERM + e] = l1;
+            for (int q = 0; q < 32; q++) l1 = l1 + wterms[q * LSTRIDE + lane];
+            p.partials[((size_t)k * p.pcap + tile) * VLO_NTERM + lane] = l1;
         }
     }
-    if (tid == 0 && (s_ne | s_np)) { atomicAdd(&p.ncorr[k * 2], s_ne); atomicAdd(&p.ncorr[k * 2 + 1], s_np); }
+    if (lane == 0 && (tot_e | tot_p)) { atomicAdd(&p.ncorr[k * 2], tot_e); atomicAdd(&p.ncorr[k * 2 + 1], tot_p); }
 }
 
 #define SOLVE_THREADS 256
@@ -359,9 +377,12 @@ int vlo_launch_register_map(vlo_handle *h, const int *d_scans, int n, const floa
     h->launches += 1;
     // grids sized by the largest feature count actually present would need a sync; use capacity
     int qmax = h->map_qmax > 0 ? h->map_qmax : p.qcap;
-    dim3 gk((qmax + KNN_THREADS - 1) / KNN_THREADS, n);
+    // persistent warps: ~8 waves of CTAs at 5 per SM (measured best: short tiles balance the per-query variance),
+    // never more than one warp per 32 queries
+    int ctas_cap = (qmax + KNN_THREADS - 1) / KNN_THREADS, ctas_fill = (148 * 5 * 8 + n - 1) / n;
+    dim3 gk(std::max(1, std::min(ctas_cap, ctas_fill)), n);
     for (int it = 0; it < c.map_max_iterations; it++) {
-        VLO_PROF(h, ST_MAP_LIN, (k5_assoc_lin<<<gk, KNN_THREADS, 0, h->stream>>>(p)));
+        VLO_PROF(h, ST_MAP_LIN, (k5_assoc_lin<<<gk, KNN_THREADS, 0, h->stream>>>(p, it)));
         VLO_PROF(h, ST_MAP_SOLVE, (k5_solve<<<n, SOLVE_THREADS, 0, h->stream>>>(p, it)));
         h->launches += 2;
     }
