@@ -116,8 +116,8 @@ def algorithmic_bytes(stage: str, counts, n_map_pts, iters_done):
     if stage == "k1b_compact":
         return 2 * 20 * sum(c["n_sharp"] + c["n_less_sharp"] + c["n_flat"] for c in counts)
     if stage == "k5_assoc_lin":
-        # fused association + linearisation: map read once + query in + 5 neighbour indices out + level-1 sums
-        # (the 5 x 16 B neighbour gather of SURVEY 8d's 116 B/query stays on chip in the fused kernel)
+        # fused association + linearisation, one Gauss-Newton iteration: map read once + query in + 5 neighbour
+        # indices out + level-1 sums out (the 5 x 16 B neighbour gather of SURVEY 8d's 116 B/query stays on chip)
         return n_map_pts * 16 + q * (16 + 5 * 4) + (q // 32 + 1) * 28 * 4
     if stage == "k5_solve":
         return (q // 32 + 1) * 28 * 4
@@ -292,7 +292,8 @@ def run_gpu(args):
                 continue
             # k5_* launch max_iter times but only the first `iterations` do work: average over working launches
             working = n
-            if name.startswith("k5_"):
+            if name in ("k5_assoc_lin", "k5_solve"):
+                # max_iter launches per call, only the first `iterations` do work: average over the working launches
                 working = max(1, int(round(args.steps * min(mean_iters, cfg.map_max_iterations))))
             avg_ms = ms / working
             ab = algorithmic_bytes(name, counts, n_map_pts, mean_iters)

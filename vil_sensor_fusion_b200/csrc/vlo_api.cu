@@ -92,7 +92,7 @@ extern "C" int vlo_create(const vlo_config *cfg, vlo_handle **out)
     h->status_word = nullptr; h->pair_T = h->pair_seed = nullptr; h->pair_last = h->pair_cur = h->pair_state = nullptr;
     h->pair_cidx = h->pair_sidx = h->pair_trace = nullptr; h->pair_result = nullptr;
     h->map_partials = nullptr; h->map_idx5 = nullptr; h->map_T = h->map_seed = nullptr; h->map_state = h->map_ncorr = h->map_scans = nullptr;
-    h->map_result = nullptr; h->map_qmax = 0; h->last_n_map = 0; h->last_n_pairs = 0;
+    h->map_result = nullptr; h->coop_resident = 0; h->map_qmax = 0; h->last_n_map = 0; h->last_n_pairs = 0;
     h->imu_buf = nullptr; h->imu_buf_bytes = 0; h->imu_out = nullptr; h->imu_out_cap = 0;
     h->online_have_last = 0; h->online_slot = 0; h->prof_enabled = 0; h->prof_used = 0;
     memset(h->online_T, 0, sizeof(h->online_T)); memset(h->online_sum, 0, sizeof(h->online_sum));

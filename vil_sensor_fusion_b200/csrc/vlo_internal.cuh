@@ -101,6 +101,7 @@ struct vlo_handle {
     int   *map_idx5;           // [n][qcap][5]
     float *map_T; float *map_seed; int *map_state; int *map_ncorr; int *map_scans; vlo_result *map_result;
     int map_qmax, last_n_map;
+    int coop_resident;
     // IMU staging (grown on demand)
     double *imu_buf; size_t imu_buf_bytes; vlo_preint *imu_out; int imu_out_cap;
     // stage profiling
