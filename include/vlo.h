@@ -87,6 +87,16 @@ typedef struct vlo_config {
     float dopt_trans_threshold;        /* filter/trans_degen_threshold 28.9 */
     /* ---- IMU noise (fusion_params.yaml:22-27, ImuManagerRos.cpp:20-33) ---- */
     double cov_accel, cov_gyro, cov_integration, cov_bias_acc, cov_bias_omega, cov_bias_acc_omega_int;
+    /* ---- LaserMapping, map side (loam_params.yaml:35,47-52) ---- */
+    float corner_filter_size;          /* cornerFilterSize 0.2 (47): VoxelGrid leaf of the corner stack and the corner map; 0 = off */
+    float surface_filter_size;         /* surfaceFilterSize 0.4 (48) */
+    float map_cube_size;               /* mapCubeSize 10.0 (49) */
+    int   map_dims[3];                 /* mapDimensionsInCubes [101,51,101] (50) */
+    int   map_start_cubes[3];          /* mapStartLocationInCubes [50,25,50] (51) */
+    int   n_neighbor_cubes;            /* numNeighborSubmapCubes 5 (52); <= 5 */
+    int   io_ratio;                    /* ioRatio 2 (35): the online tick runs LaserMapping on every io_ratio-th sweep */
+    int   hessian_order;               /* 0: OptStatus.hessian in LOAM's order (rx ry rz tx ty tz); 1: (tx ty tz rx ry rz), i.e.
+                                          block(0,0) really is translation as degerate_odometry_filter.cpp:32-33 labels it */
 } vlo_config;
 
 /* One registration result = one nav_msgs/Odometry + loam/OptStatus pair of the reference. */
@@ -121,7 +131,7 @@ typedef struct vlo_preint {    /* gtsam::PreintegratedCombinedMeasurements as PO
 
 /* ---------------------------------------------------------------- lifecycle */
 void        vlo_default_config(vlo_config *cfg);            /* loam_params.yaml / fusion_params.yaml defaults, VLP-16 */
-int         vlo_set_lidar(vlo_config *cfg, const char *name); /* "VLP-16" | "HDL-32" | "HDL-64E" (loam_params.yaml:22) */
+int         vlo_set_lidar(vlo_config *cfg, const char *name); /* "VLP-16" | "HDL-32" | "HDL-64E" | "O1-16" | "O1-64" | "Bperl-32" (loam_params.yaml:22) */
 int         vlo_create(const vlo_config *cfg, vlo_handle **out);
 void        vlo_destroy(vlo_handle *h);
 const char *vlo_last_error(const vlo_handle *h);
@@ -166,12 +176,32 @@ int vlo_pair_get_correspondences(vlo_handle *h, int pair, int round, int *corner
 
 /* ---------------------------------------------------------------- scan-to-map (LaserMapping) */
 int vlo_map_build(vlo_handle *h, const float *corner_xyzi, int n_corner, const float *surf_xyzi, int n_surf, int on_device);
-/* registers the corner (less sharp) / surface (less flat) features of resident scans [0,n) against the map */
+/* registers the down-sampled corner (less sharp) / surface (less flat) stacks of resident scans against the map */
 int vlo_register_map(vlo_handle *h, const int *scans, int n, const float *seeds /* n*6 transformTobeMapped */, vlo_result *out);
 int vlo_map_get_correspondences(vlo_handle *h, int slot, int *corner_idx5, int *surf_idx5);
 /* exact k-NN service on the map grids (k = 1 or 5, neighbours with d2 < max_d2): which = 0 corner, 1 surf;
  * queries host xyzi; missing neighbours are idx -1 / d2 +inf */
 int vlo_map_knn(vlo_handle *h, int which, const float *queries_xyzi, int nq, int k, float max_d2, int *idx, float *d2);
+
+/* ---- maintained map: BasicLaserMapping::process of the `loam` nodelet laserMapping (loam.launch:47-52), map side.
+ * The map lives on the device as voxel centroids (corner leaf cornerFilterSize, surface leaf surfaceFilterSize) tagged
+ * with their cube (mapCubeSize); a point's index = order of voxel creation.
+ *   vlo_map_reset    empties the map and re-centres the cube window (mapStartLocationInCubes)
+ *   vlo_map_insert   upstream's insertion step alone: points (host, sensor frame) moved with pose6, binned into cubes,
+ *                    touched voxels re-filtered (e.g. to preload a prior map)
+ *   vlo_map_process  one LaserMapping tick for resident scan `scan`: window shift + FOV-valid sub-map around `seed6`,
+ *                    stack down-sampling, optimisation against the sub-map (skipped when it holds <= 10 corner or <= 100
+ *                    surface points), insertion with the optimised pose.  info[6] (optional) = down-sampled stack sizes,
+ *                    sub-map sizes, map sizes after insertion (corner, surface each)
+ *   vlo_map_get_points  copy-back for parity tests / tooling: xyz0 per point + packed cube (bit 30 = evicted) */
+int vlo_map_reset(vlo_handle *h);
+int vlo_map_insert(vlo_handle *h, const float *corner_xyzi, int n_corner, const float *surf_xyzi, int n_surf, const float *pose6);
+int vlo_map_process(vlo_handle *h, int scan, const float *seed6, vlo_result *out, int *info);
+int vlo_map_size(vlo_handle *h, int *n_corner, int *n_surf);
+int vlo_map_get_points(vlo_handle *h, int which, float *xyzi, int *cube);
+/* down-sampled stacks (cornerFilterSize / surfaceFilterSize VoxelGrid of the less-sharp / less-flat clouds) of a resident
+ * scan: the query clouds of vlo_register_map / vlo_map_process.  Any pointer may be NULL. */
+int vlo_scan_get_stack(vlo_handle *h, int scan, float *corner_xyzi, int *n_corner, float *surf_xyzi, int *n_surf);
 
 /* ---------------------------------------------------------------- online tick */
 /* One LOAM tick: organise + extract + scan-to-scan against the previous tick (seeded with the

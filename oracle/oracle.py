@@ -32,6 +32,8 @@ class Config(C.Structure):
         ("odom_degen_eig", C.c_float), ("map_max_iterations", C.c_int), ("map_delta_t_abort", C.c_float),
         ("map_delta_r_abort", C.c_float), ("map_degen_eig", C.c_float), ("deskew", C.c_int),
         ("odom_forward_bound_quirk", C.c_int), ("dopt_rot_threshold", C.c_float), ("dopt_trans_threshold", C.c_float),
+        ("corner_filter_size", C.c_float), ("surface_filter_size", C.c_float), ("map_cube_size", C.c_float),
+        ("map_dims", C.c_int * 3), ("map_start_cubes", C.c_int * 3), ("n_neighbor_cubes", C.c_int), ("io_ratio", C.c_int),
     ]
 
 
@@ -83,6 +85,10 @@ def lib():
         _lib.orc_dopt_gate.restype = C.c_int
         _lib.orc_edge_coeff.restype = C.c_int
         _lib.orc_plane_coeff.restype = C.c_int
+        _lib.orc_voxel_downsample.restype = C.c_int
+        _lib.orc_lmap_create.restype = C.c_void_p
+        _lib.orc_lmap_size.restype = C.c_int
+        _lib.orc_lmap_submap.restype = C.c_int
     return _lib
 
 
@@ -266,6 +272,73 @@ def mapping_register(cfg, corner_q, surf_q, corner_map, surf_map, seed, use_kdtr
         out["trace_idx"] = tr_idx
         out["trace_T"] = tr_T
     return out
+
+
+def voxel_downsample(pts, leaf):
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 4)
+    out = np.zeros((max(len(pts), 1), 4), np.float32)
+    m = lib().orc_voxel_downsample(_p(pts), len(pts), C.c_float(leaf), _p(out))
+    return out[:m].copy()
+
+
+class LaserMap:
+    """BasicLaserMapping's map side (oracle/laser_map.c): cube window, sub-map selection, stack down-sampling,
+    registration against the sub-map, insertion + voxel re-filtering."""
+
+    def __init__(self, cfg, cap=1 << 20):
+        self.cfg, self.cap = cfg, cap
+        self._m = C.c_void_p(lib().orc_lmap_create(C.byref(cfg), cap))
+
+    def close(self):
+        if self._m:
+            lib().orc_lmap_free(self._m)
+            self._m = None
+
+    def __del__(self):
+        self.close()
+
+    def size(self, which):
+        return lib().orc_lmap_size(self._m, which)
+
+    def points(self, which):
+        n = self.size(which)
+        pts = np.zeros((max(n, 1), 4), np.float32)
+        cube = np.zeros(max(n, 1), np.int32)
+        lib().orc_lmap_get(self._m, which, _p(pts), _p(cube))
+        return pts[:n].copy(), cube[:n].copy()
+
+    def window(self):
+        cen = np.zeros(3, np.int32)
+        lib().orc_lmap_window(self._m, _p(cen))
+        return cen
+
+    def submap_ids(self, which):
+        ids = np.zeros(max(self.size(which), 1), np.int32)
+        n = lib().orc_lmap_submap(self._m, which, _p(ids))
+        return ids[:n].copy()
+
+    def insert(self, corner, surf, T):
+        c = np.ascontiguousarray(corner, np.float32).reshape(-1, 4)
+        s = np.ascontiguousarray(surf, np.float32).reshape(-1, 4)
+        lib().orc_lmap_insert(self._m, _p(c), len(c), _p(s), len(s), _p(np.ascontiguousarray(T, np.float32)))
+
+    def select(self, T):
+        side = 2 * self.cfg.n_neighbor_cubes + 1
+        centre = np.zeros(3, np.int32)
+        mask = np.zeros(side ** 3, np.uint8)
+        lib().orc_lmap_select(self._m, _p(np.ascontiguousarray(T, np.float32)), _p(centre), _p(mask))
+        return centre, mask.reshape(side, side, side)
+
+    def process(self, corner_stack, surf_stack, seed):
+        c = np.ascontiguousarray(corner_stack, np.float32).reshape(-1, 4)
+        s = np.ascontiguousarray(surf_stack, np.float32).reshape(-1, 4)
+        res = RegResult()
+        info = np.zeros(6, np.int32)
+        lib().orc_lmap_process(self._m, _p(c), len(c), _p(s), len(s), _p(np.ascontiguousarray(seed, np.float32)),
+                               C.byref(res), _p(info))
+        out = _result_dict(res)
+        out["info"] = dict(n_ds=(int(info[0]), int(info[1])), n_sub=(int(info[2]), int(info[3])), n_map=(int(info[4]), int(info[5])))
+        return out
 
 
 def imu_params(cov_accel=1e-6, cov_gyro=1e-6, cov_integration=1e-8, cov_bias_acc=1e-4, cov_bias_omega=1e-6,

@@ -55,7 +55,12 @@ void orc_frame_scan_to_map(const orc_map *m, const float *raw, int n, int stride
     orc_organise(c, raw, n, stride, cloud, rs, NULL);
     orc_extract(c, cloud, rs, label, curv, NULL, sharp, ls, fl, lflat, lsr, lfr, &fc);
     for (int i = 0; i < fc.n_less_sharp; i++) lsharp[i] = cloud[ls[i]];
-    orc_mapping_register_trees(c, lsharp, fc.n_less_sharp, lflat, fc.n_less_flat, m->corner_map, m->n_cm, m->kc,
+    /* the stacks LaserMapping optimises with are VoxelGrid-filtered (cornerFilterSize / surfaceFilterSize); cloud[] is
+     * free to be reused as the output buffers now */
+    orc_pt *cds = cloud, *sds = cloud + fc.n_less_sharp;
+    int ncd = orc_voxel_downsample(lsharp, fc.n_less_sharp, c->corner_filter_size, cds);
+    int nsd = orc_voxel_downsample(lflat, fc.n_less_flat, c->surface_filter_size, sds);
+    orc_mapping_register_trees(c, cds, ncd, sds, nsd, m->corner_map, m->n_cm, m->kc,
                                m->surf_map, m->n_sm, m->ks, seed, res);
     if (counts) *counts = fc;
     free(cloud); free(lflat); free(lsharp); free(label); free(curv); free(sharp); free(ls); free(fl); free(rs); free(lsr); free(lfr);

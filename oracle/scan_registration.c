@@ -36,6 +36,13 @@ void orc_default_config(orc_config *c)
     c->odom_forward_bound_quirk = 0;
     c->dopt_rot_threshold = 11.5f;
     c->dopt_trans_threshold = 28.9f;
+    c->corner_filter_size = 0.2f;
+    c->surface_filter_size = 0.4f;
+    c->map_cube_size = 10.0f;
+    c->map_dims[0] = 101; c->map_dims[1] = 51; c->map_dims[2] = 101;
+    c->map_start_cubes[0] = 50; c->map_start_cubes[1] = 25; c->map_start_cubes[2] = 50;
+    c->n_neighbor_cubes = 5;
+    c->io_ratio = 2;
 }
 
 /* MultiScanMapper::getRingForAngle: int(((angle*180/M_PI) - lower) * factor + 0.5) */
@@ -184,6 +191,13 @@ static int voxel_downsample(const orc_pt *in, int n, float leaf, orc_pt *out)
     }
     free(table); free(g);
     return m;
+}
+
+/* leaf <= 0: no filtering (copy) */
+int orc_voxel_downsample(const orc_pt *in, int n, float leaf, orc_pt *out)
+{
+    if (!(leaf > 0.0f)) { memcpy(out, in, sizeof(orc_pt) * (size_t)n); return n; }
+    return voxel_downsample(in, n, leaf, out);
 }
 
 void orc_extract(const orc_config *c, const orc_pt *cloud, const int *ring_start,

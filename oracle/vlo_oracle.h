@@ -50,6 +50,14 @@ typedef struct {
     int   odom_forward_bound_quirk;    /* 1: forward partner loop bounded by #query features (upstream quirk) */
     float dopt_rot_threshold;          /* fusion_params.yaml:35  11.5 */
     float dopt_trans_threshold;        /* fusion_params.yaml:36  28.9 */
+    /* LaserMapping map side (loam_params.yaml:35,47-52) */
+    float corner_filter_size;          /* cornerFilterSize 0.2 (47); 0 = stack not down-sampled */
+    float surface_filter_size;         /* surfaceFilterSize 0.4 (48) */
+    float map_cube_size;               /* mapCubeSize 10.0 (49) */
+    int   map_dims[3];                 /* mapDimensionsInCubes [101,51,101] (50) */
+    int   map_start_cubes[3];          /* mapStartLocationInCubes [50,25,50] (51) */
+    int   n_neighbor_cubes;            /* numNeighborSubmapCubes 5 (52) */
+    int   io_ratio;                    /* ioRatio 2 (35): mapping runs on every io_ratio-th sweep */
 } orc_config;
 
 void orc_default_config(orc_config *c);
@@ -134,6 +142,22 @@ void orc_mapping_register(const orc_config *c,
                           const orc_pt *corner_map, int n_corner_map, const orc_pt *surf_map, int n_surf_map,
                           const float *seed /*transformTobeMapped*/, int use_kdtree,
                           orc_reg_result *res, int *trace_idx /*5 per query, first association*/, float *trace_T);
+
+/* pcl::VoxelGrid restated (V1/V2 of scan_registration.c): centroids in order of first appearance; returns count */
+int orc_voxel_downsample(const orc_pt *in, int n, float leaf, orc_pt *out);
+
+/* ---- LaserMapping map maintenance (A.8 map side; laser_map.c) ---- */
+typedef struct orc_lmap orc_lmap;
+orc_lmap *orc_lmap_create(const orc_config *c, int cap);
+void orc_lmap_free(orc_lmap *m);
+int  orc_lmap_size(const orc_lmap *m, int which);
+void orc_lmap_get(const orc_lmap *m, int which, orc_pt *pts, int *cube);
+void orc_lmap_window(const orc_lmap *m, int *cen3);
+int  orc_lmap_submap(const orc_lmap *m, int which, int *ids);
+void orc_lmap_insert(orc_lmap *m, const orc_pt *corner, int nc, const orc_pt *surf, int ns, const float *T);
+void orc_lmap_select(orc_lmap *m, const float *T, int *centre_abs, uint8_t *mask);
+void orc_lmap_process(orc_lmap *m, const orc_pt *corner_stack, int nc, const orc_pt *surf_stack, int ns,
+                      const float *seed, orc_reg_result *res, int *info);
 
 /* ---- IMU (Appendix B + IMUManager.cpp:27-74) ---- */
 typedef struct {

@@ -15,7 +15,10 @@ def _setup(orc, lidar, raw, n_map, max_points):
     gcfg = api.default_config(lidar, deskew=0, max_scans=2, max_points=max_points, max_map_points=max(len(cm), len(sm)))
     c, rs, _ = orc.organise(ocfg, raw)
     f = orc.extract(ocfg, c, rs)
-    return ocfg, gcfg, cm, sm, c[f["less_sharp_idx"]], f["less_flat"]
+    # the scan-to-map queries are the VoxelGrid-filtered stacks (cornerFilterSize 0.2 / surfaceFilterSize 0.4)
+    cq = orc.voxel_downsample(c[f["less_sharp_idx"]], ocfg.corner_filter_size)
+    sq = orc.voxel_downsample(f["less_flat"], ocfg.surface_filter_size)
+    return ocfg, gcfg, cm, sm, cq, sq
 
 
 def test_map_knn_exact(orc):
@@ -107,3 +110,148 @@ def test_empty_map_soft_status(orc):
         r = h.register_map([0], [seed])[0]
         assert r["status"] == 1 and r["iterations"] == 0
         np.testing.assert_array_equal(r["transform"], seed)
+
+
+@pytest.mark.parametrize("lidar,max_points", [("VLP-16", 32768), ("HDL-64E", 131072)])
+def test_stack_downsample_bit_exact(orc, lidar, max_points):
+    """K7 stack VoxelGrid (order of first appearance, integer centroid sums) equals the oracle bit for bit;
+    a filter size of 0 passes the cloud through."""
+    from vil_sensor_fusion_b200 import api, synth
+    raws = [synth.make_scan(synth.scene_room(0), lidar, pose=(synth.rot_zyx(0.3 * k, 0, 0), np.array([1.0 * k, 0.5, 0.1])), rolling=False)
+            for k in range(2)]
+    ocfg = orc.default_config(lidar, deskew=0)
+    for cf, sf in ((0.2, 0.4), (0.0, 0.4), (0.3, 0.0)):
+        gcfg = api.default_config(lidar, deskew=0, max_scans=2, max_points=max_points, max_map_points=1000,
+                                  corner_filter_size=cf, surface_filter_size=sf)
+        with api.Handle(gcfg) as h:
+            h.upload(raws)
+            h.organise()
+            h.extract()
+            for k, raw in enumerate(raws):
+                c, rs, _ = orc.organise(ocfg, raw)
+                f = orc.extract(ocfg, c, rs)
+                cg, sg = h.get_stack(k)
+                co = orc.voxel_downsample(c[f["less_sharp_idx"]], cf)
+                so = orc.voxel_downsample(f["less_flat"], sf)
+                np.testing.assert_array_equal(cg.view(np.uint32), co.view(np.uint32))
+                np.testing.assert_array_equal(sg.view(np.uint32), so.view(np.uint32))
+                assert len(so) < len(f["less_flat"]) or sf == 0.0
+
+
+def _lm_sequence(orc, lidar, n_ticks, max_points, cfg_kw, traj_scale=1.0):
+    from vil_sensor_fusion_b200 import api, synth
+    scene = synth.scene_room(0)
+    traj = synth.Trajectory()
+    ocfg = orc.default_config(lidar, deskew=0, **cfg_kw)
+    gcfg = api.default_config(lidar, deskew=0, max_scans=2, max_points=max_points, max_map_points=300000, **cfg_kw)
+    raws = [synth.make_scan(scene, lidar, t0=0.1 * k * traj_scale, traj=traj, rolling=False) for k in range(n_ticks)]
+    return ocfg, gcfg, raws
+
+
+@pytest.mark.parametrize("lidar,max_points,n_ticks", [("VLP-16", 32768, 6), ("HDL-64E", 131072, 3)])
+def test_laser_mapping_ticks_bit_exact(orc, lidar, max_points, n_ticks):
+    """BasicLaserMapping::process chained over a sequence (each tick seeded with the previous mapped pose): poses,
+    Hessians, down-sampled stack / sub-map / map sizes and the whole map (points by index, cube tags) equal the
+    oracle's bit for bit after every tick."""
+    from vil_sensor_fusion_b200 import api
+    ocfg, gcfg, raws = _lm_sequence(orc, lidar, n_ticks, max_points, {})
+    om = orc.LaserMap(ocfg, cap=300000)
+    seed = np.zeros(6, np.float32)
+    with api.Handle(gcfg) as h:
+        h.map_reset()
+        for k, raw in enumerate(raws):
+            c, rs, _ = orc.organise(ocfg, raw)
+            f = orc.extract(ocfg, c, rs)
+            ro = om.process(c[f["less_sharp_idx"]], f["less_flat"], seed)
+            h.upload([raw])
+            h.organise()
+            h.extract()
+            rg, info = h.map_process(0, seed)
+            assert info == ro["info"], (k, info, ro["info"])
+            assert rg["status"] == ro["status"] and rg["iterations"] == ro["iterations"], k
+            np.testing.assert_array_equal(rg["transform"].view(np.uint32), ro["transform"].view(np.uint32), err_msg="tick %d" % k)
+            np.testing.assert_array_equal(rg["hessian"].view(np.uint32), ro["hessian"].view(np.uint32))
+            for w in range(2):
+                pg, cg = h.map_points(w)
+                po, co = om.points(w)
+                np.testing.assert_array_equal(cg, co, err_msg="cube tags, tick %d cloud %d" % (k, w))
+                np.testing.assert_array_equal(pg.view(np.uint32), po.view(np.uint32), err_msg="map points, tick %d cloud %d" % (k, w))
+            seed = ro["transform"]
+        if k >= 1:
+            assert ro["status"] == 0 and ro["info"]["n_sub"][1] > 100
+    om.close()
+
+
+def test_laser_mapping_window_shift_and_fov(orc):
+    """Small cube window (7 x 7 x 7 cubes of 4 m, +-1 neighbour cubes): the window shifts as the sensor moves, cubes
+    leave it (evicted points), the sub-map is the FOV-valid neighbourhood -- all bit-exact against the oracle."""
+    from vil_sensor_fusion_b200 import api, synth
+    kw = dict(map_cube_size=4.0, n_neighbor_cubes=1)
+    ocfg, gcfg, _ = _lm_sequence(orc, "VLP-16", 0, 32768, kw)
+    for cfg in (ocfg, gcfg):
+        cfg.map_dims[0] = cfg.map_dims[1] = cfg.map_dims[2] = 7
+        cfg.map_start_cubes[0] = cfg.map_start_cubes[1] = cfg.map_start_cubes[2] = 3
+    scene = synth.scene_room(0)
+    om = orc.LaserMap(ocfg, cap=300000)
+    evicted = 0
+    with api.Handle(gcfg) as h:
+        h.map_reset()
+        for k in range(7):
+            p = np.array([-8.0 + 3.0 * k, 0.4 * k, 0.1])
+            R = synth.rot_zyx(0.05 * k, 0.0, 0.0)
+            raw = synth.make_scan(scene, "VLP-16", pose=(R, p), rolling=False)
+            seed = synth.loam_map_pose(R, p).astype(np.float32) + np.array([0.002, -0.003, 0.001, 0.03, -0.02, 0.04], np.float32)
+            c, rs, _ = orc.organise(ocfg, raw)
+            f = orc.extract(ocfg, c, rs)
+            ro = om.process(c[f["less_sharp_idx"]], f["less_flat"], seed)
+            h.upload([raw])
+            h.organise()
+            h.extract()
+            rg, info = h.map_process(0, seed)
+            assert info == ro["info"], (k, info, ro["info"])
+            np.testing.assert_array_equal(rg["transform"].view(np.uint32), ro["transform"].view(np.uint32), err_msg="tick %d" % k)
+            for w in range(2):
+                pg, cg = h.map_points(w)
+                po, co = om.points(w)
+                np.testing.assert_array_equal(cg, co)
+                np.testing.assert_array_equal(pg.view(np.uint32), po.view(np.uint32))
+                evicted += int(np.count_nonzero(co & (1 << 30)))
+            # the sub-map is a strict subset of the map: the neighbourhood is 3 cubes wide, the window 7
+            assert ro["info"]["n_sub"][1] < ro["info"]["n_map"][1]
+    assert evicted > 0, "the window never shifted far enough to drop a cube"
+    assert not np.array_equal(om.window(), [3, 3, 3])
+    om.close()
+
+
+def test_map_insert_preload_and_capacity(orc):
+    """vlo_map_insert (upstream's insertion step alone) on a large host cloud, in two chunks, equals the oracle;
+    inserting the same cloud twice creates no new voxel; a full map reports VLO_ERR_CAPACITY."""
+    from vil_sensor_fusion_b200 import api, synth
+    scene = synth.scene_room(0)
+    cm, sm = synth.sample_map_points(scene, 120000, seed=5)
+    ocfg = orc.default_config("VLP-16", deskew=0)
+    gcfg = api.default_config("VLP-16", deskew=0, max_scans=2, max_points=32768, max_map_points=200000)
+    pose = np.array([0.01, -0.02, 0.03, 0.5, -0.25, 1.0], np.float32)
+    om = orc.LaserMap(ocfg, cap=200000)
+    om.insert(cm, sm, pose)
+    with api.Handle(gcfg) as h:
+        h.map_reset()
+        h.map_insert(cm, sm, pose)
+        for w in range(2):
+            pg, cg = h.map_points(w)
+            po, co = om.points(w)
+            np.testing.assert_array_equal(cg, co)
+            np.testing.assert_array_equal(pg.view(np.uint32), po.view(np.uint32))
+        n0 = h.map_size()
+        h.map_insert(cm, sm, pose)
+        om.insert(cm, sm, pose)
+        assert h.map_size() == n0 == (om.size(0), om.size(1))
+        pg, _ = h.map_points(1)
+        np.testing.assert_array_equal(pg.view(np.uint32), om.points(1)[0].view(np.uint32))
+    om.close()
+    small = api.default_config("VLP-16", deskew=0, max_scans=2, max_points=32768, max_map_points=1000)
+    with api.Handle(small) as h:
+        h.map_reset()
+        with pytest.raises(api.VloError) as e:
+            h.map_insert(cm, sm, pose)
+        assert e.value.code == -3

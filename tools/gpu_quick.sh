@@ -2,7 +2,7 @@
 # Quick iteration call: parity tests + bench without the CPU legs.  Usage: bash tools/gpu_quick.sh tag [extra bench args]
 TAG=${1:-q}; shift
 OUT=gpurun_out/$TAG; mkdir -p $OUT
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee $OUT/pytest_gpu.txt
+timeout -k 10 420 python -m pytest tests -m gpu -x -q --timeout 150 2>&1 | tail -15 | tee $OUT/pytest_gpu.txt
 timeout 900 python bench.py --no-cpu-baseline "$@" > $OUT/bench.json 2> $OUT/bench.err; tail -5 $OUT/bench.err
 python - <<PY
 import json

@@ -24,6 +24,9 @@ class Config(C.Structure):
         ("dopt_rot_threshold", C.c_float), ("dopt_trans_threshold", C.c_float),
         ("cov_accel", C.c_double), ("cov_gyro", C.c_double), ("cov_integration", C.c_double),
         ("cov_bias_acc", C.c_double), ("cov_bias_omega", C.c_double), ("cov_bias_acc_omega_int", C.c_double),
+        ("corner_filter_size", C.c_float), ("surface_filter_size", C.c_float), ("map_cube_size", C.c_float),
+        ("map_dims", C.c_int * 3), ("map_start_cubes", C.c_int * 3), ("n_neighbor_cubes", C.c_int), ("io_ratio", C.c_int),
+        ("hessian_order", C.c_int),
     ]
 
 
@@ -83,6 +86,12 @@ SYMBOLS = {
     "vlo_register_map": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP]),
     "vlo_map_get_correspondences": (C.c_int, [_VP, C.c_int, _VP, _VP]),
     "vlo_map_knn": (C.c_int, [_VP, C.c_int, _VP, C.c_int, C.c_int, C.c_float, _VP, _VP]),
+    "vlo_map_reset": (C.c_int, [_VP]),
+    "vlo_map_insert": (C.c_int, [_VP, _VP, C.c_int, _VP, C.c_int, _VP]),
+    "vlo_map_process": (C.c_int, [_VP, C.c_int, _VP, C.POINTER(Result), _VP]),
+    "vlo_map_size": (C.c_int, [_VP, _VP, _VP]),
+    "vlo_map_get_points": (C.c_int, [_VP, C.c_int, _VP, _VP]),
+    "vlo_scan_get_stack": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP, _VP]),
     "vlo_online_reset": (C.c_int, [_VP]),
     "vlo_online_pose": (C.c_int, [_VP, _VP, _VP]),
     "vlo_online_set_map_pose": (C.c_int, [_VP, _VP]),

@@ -213,6 +213,45 @@ class Handle:
         self._check(self.lib.vlo_map_knn(self._h, which, _ptr(q), q.shape[0], k, max_d2, _ptr(idx), _ptr(d2)))
         return idx, d2
 
+    # ---- maintained map (LaserMapping's map side)
+    def map_reset(self):
+        self._check(self.lib.vlo_map_reset(self._h))
+
+    def map_insert(self, corner_xyzi, surf_xyzi, pose6):
+        c = np.ascontiguousarray(corner_xyzi, np.float32).reshape(-1, 4)
+        s = np.ascontiguousarray(surf_xyzi, np.float32).reshape(-1, 4)
+        self._check(self.lib.vlo_map_insert(self._h, _ptr(c), c.shape[0], _ptr(s), s.shape[0],
+                                            _ptr(np.ascontiguousarray(pose6, np.float32))))
+
+    def map_process(self, scan: int, seed6):
+        """One LaserMapping tick for a resident scan; returns (result record, info dict)."""
+        out = Result()
+        info = np.zeros(6, np.int32)
+        self._check(self.lib.vlo_map_process(self._h, scan, _ptr(np.ascontiguousarray(seed6, np.float32)), C.byref(out), _ptr(info)))
+        r = np.frombuffer(bytes(out), RESULT_DTYPE)[0]
+        return r, dict(n_ds=(int(info[0]), int(info[1])), n_sub=(int(info[2]), int(info[3])), n_map=(int(info[4]), int(info[5])))
+
+    def map_size(self):
+        a, b = C.c_int(0), C.c_int(0)
+        self._check(self.lib.vlo_map_size(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def map_points(self, which: int):
+        n = self.map_size()[which]
+        pts = np.zeros((max(n, 1), 4), np.float32)
+        cube = np.zeros(max(n, 1), np.int32)
+        self._check(self.lib.vlo_map_get_points(self._h, which, _ptr(pts), _ptr(cube)))
+        return pts[:n], cube[:n]
+
+    def get_stack(self, scan: int):
+        """Down-sampled corner / surface stacks of a resident scan (the scan-to-map query clouds)."""
+        nc, ns = C.c_int(0), C.c_int(0)
+        self._check(self.lib.vlo_scan_get_stack(self._h, scan, None, C.byref(nc), None, C.byref(ns)))
+        c = np.zeros((max(nc.value, 1), 4), np.float32)
+        s = np.zeros((max(ns.value, 1), 4), np.float32)
+        self._check(self.lib.vlo_scan_get_stack(self._h, scan, _ptr(c), None, _ptr(s), None))
+        return c[:nc.value], s[:ns.value]
+
     def online_pose(self):
         s = np.zeros(6, np.float32)
         m = np.zeros(6, np.float32)

@@ -20,6 +20,15 @@ __device__ __forceinline__ bool grid_src_point(const GridSource &src, int g, int
     }
     int n = src.n_dense[(size_t)b * src.n_dense_stride + src.n_dense_field];
     if (i >= n) return false;
+    if (src.cube) {                              // sub-map of the maintained map: live points of the masked cubes
+        const int cv = src.cube[i];
+        if (cv & LM_DEAD) return false;
+        const int r0 = ((cv & 1023) - 512) - src.mask_lo[0], r1 = (((cv >> 10) & 1023) - 512) - src.mask_lo[1],
+                  r2 = (((cv >> 20) & 1023) - 512) - src.mask_lo[2], sd = src.mask_side;
+        if (r0 < 0 || r0 >= sd || r1 < 0 || r1 >= sd || r2 < 0 || r2 >= sd) return false;
+        const int bit = (r2 * sd + r1) * sd + r0;
+        if (!((src.mask[bit >> 5] >> (bit & 31)) & 1u)) return false;
+    }
     p = src.pts[(size_t)b * src.pts_stride + i];
     tag = ((unsigned)(int)p.w << 24) | (unsigned)i;
     return true;
@@ -43,36 +52,77 @@ __global__ void __launch_bounds__(256) k2_count(GridSet gs, GridSource src, int 
     atomicAdd(&gs.cnt[(size_t)g * gs.ts + slot], 1);
 }
 
-__global__ void __launch_bounds__(1024) k2_scan(GridSet gs, int g_first)
+// exclusive scan of cnt -> start, three passes over blocks of GRID_SCAN_BLOCK slots (1024 threads x 4):
+//   k2_scan_partial  block sums;  k2_scan_bsums  one CTA per grid scans them (+ start[ts] = total);
+//   k2_scan_final    block-local exclusive scan + block offset
+__device__ __forceinline__ int k2_block_excl_scan4(int v0, int v1, int v2, int v3, int *warp_sum, int &block_total)
 {
-    __shared__ int warp_sum[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int mine = v0 + v1 + v2 + v3;
+    int inc = mine;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+    if (lane == 31) warp_sum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = warp_sum[lane], winc = w;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, winc, d); if (lane >= d) winc += u; }
+        warp_sum[lane] = winc - w;
+        if (lane == 31) warp_sum[32] = winc;
+    }
+    __syncthreads();
+    block_total = warp_sum[32];
+    return warp_sum[warp] + inc - mine;
+}
+
+__global__ void __launch_bounds__(1024) k2_scan_partial(GridSet gs, int g_first)
+{
+    __shared__ int warp_sum[33];
+    const int g = g_first + blockIdx.y, nblk = (gs.ts + GRID_SCAN_BLOCK - 1) / GRID_SCAN_BLOCK;
+    const int base = blockIdx.x * GRID_SCAN_BLOCK + threadIdx.x * 4;
+    int4 v = make_int4(0, 0, 0, 0);
+    if (base < gs.ts) v = *(const int4 *)(gs.cnt + (size_t)g * gs.ts + base);
+    int total;
+    k2_block_excl_scan4(v.x, v.y, v.z, v.w, warp_sum, total);
+    if (threadIdx.x == 0) gs.bsum[(size_t)g * nblk + blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) k2_scan_bsums(GridSet gs, int g_first)
+{
+    __shared__ int warp_sum[33];
     __shared__ int carry_s;
-    int g = g_first + blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int *cnt = gs.cnt + (size_t)g * gs.ts;
-    int *start = gs.start + (size_t)g * (gs.ts + 1);
+    const int g = g_first + blockIdx.x, nblk = (gs.ts + GRID_SCAN_BLOCK - 1) / GRID_SCAN_BLOCK, tid = threadIdx.x;
+    int *bs = gs.bsum + (size_t)g * nblk;
     if (tid == 0) carry_s = 0;
     __syncthreads();
-    for (int base = 0; base < gs.ts; base += 1024) {
-        int v = cnt[base + tid];
-        int inc = v;
-        #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
-        if (lane == 31) warp_sum[warp] = inc;
+    for (int base = 0; base < nblk; base += 1024) {
+        const int i = base + tid;
+        const int v = i < nblk ? bs[i] : 0;
+        int total;
+        const int ex = k2_block_excl_scan4(v, 0, 0, 0, warp_sum, total);
+        const int carry = carry_s;
+        if (i < nblk) bs[i] = carry + ex;
         __syncthreads();
-        if (warp == 0) {
-            int w = warp_sum[lane], winc = w;
-            #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, winc, d); if (lane >= d) winc += u; }
-            warp_sum[lane] = winc - w;
-        }
-        __syncthreads();
-        int carry = carry_s;
-        start[base + tid] = carry + warp_sum[warp] + inc - v;
-        __syncthreads();
-        if (tid == 1023) carry_s = carry + warp_sum[warp] + inc;
+        if (tid == 0) carry_s = carry + total;
         __syncthreads();
     }
-    if (tid == 0) start[gs.ts] = carry_s;
+    if (tid == 0) gs.start[(size_t)g * (gs.ts + 1) + gs.ts] = carry_s;
+}
+
+__global__ void __launch_bounds__(1024) k2_scan_final(GridSet gs, int g_first)
+{
+    __shared__ int warp_sum[33];
+    const int g = g_first + blockIdx.y, nblk = (gs.ts + GRID_SCAN_BLOCK - 1) / GRID_SCAN_BLOCK;
+    const int base = blockIdx.x * GRID_SCAN_BLOCK + threadIdx.x * 4;
+    int4 v = make_int4(0, 0, 0, 0);
+    if (base < gs.ts) v = *(const int4 *)(gs.cnt + (size_t)g * gs.ts + base);
+    int total;
+    const int ex = k2_block_excl_scan4(v.x, v.y, v.z, v.w, warp_sum, total) + gs.bsum[(size_t)g * nblk + blockIdx.x];
+    if (base < gs.ts) {
+        int *st = gs.start + (size_t)g * (gs.ts + 1) + base;      // rows of ts + 1 ints: not 16-byte aligned in general
+        st[0] = ex; st[1] = ex + v.x; st[2] = ex + v.x + v.y; st[3] = ex + v.x + v.y + v.z;
+    }
 }
 
 __global__ void __launch_bounds__(256) k2_scatter(GridSet gs, GridSource src, int n_slots, int g_first)
@@ -95,10 +145,13 @@ int vlo_grid_build(vlo_handle *h, const GridSet &gs, const GridSource &src, int 
     VLO_CUDA(cudaMemsetAsync(gs.cnt + (size_t)g_first * gs.ts, 0, sizeof(int) * (size_t)n_grids * gs.ts, h->stream));
     dim3 grid((n_slots + 255) / 256, n_grids);
     k2_count<<<grid, 256, 0, h->stream>>>(gs, src, n_slots, g_first);
-    k2_scan<<<n_grids, 1024, 0, h->stream>>>(gs, g_first);
+    const int nblk = (gs.ts + GRID_SCAN_BLOCK - 1) / GRID_SCAN_BLOCK;
+    k2_scan_partial<<<dim3(nblk, n_grids), 1024, 0, h->stream>>>(gs, g_first);
+    k2_scan_bsums<<<n_grids, 1024, 0, h->stream>>>(gs, g_first);
+    k2_scan_final<<<dim3(nblk, n_grids), 1024, 0, h->stream>>>(gs, g_first);
     k2_scatter<<<grid, 256, 0, h->stream>>>(gs, src, n_slots, g_first);
     vlo_prof_end(h, ST_GRID_BUILD);
-    h->launches += 3;
+    h->launches += 5;
     VLO_CUDA(cudaGetLastError());
     return VLO_OK;
 }

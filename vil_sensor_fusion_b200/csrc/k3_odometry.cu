@@ -375,16 +375,31 @@ static OdomParams make_params(vlo_handle *h)
 int vlo_build_scan_grids(vlo_handle *h, int first, int count)
 {
     ScanBatchDev &sb = h->sb; const vlo_config &c = h->cfg;
-    GridSource sc;
+    GridSource sc = {};
     sc.pts = sb.lsharp_pts; sc.pts_stride = (size_t)h->cap_lsharp; sc.ring_off = nullptr; sc.ring_off_stride = 0;
     sc.ring_cnt = nullptr; sc.ring_cnt_stride = 0; sc.dense_start = nullptr; sc.dense_start_stride = 0;
     sc.n_dense = sb.counts; sc.n_dense_stride = 8; sc.n_dense_field = 2; sc.n_rings = c.n_rings; sc.grid_scan = nullptr;
     int rc = vlo_grid_build(h, h->gs_corner, sc, first, count, h->cap_lsharp); if (rc) return rc;
-    GridSource ss;
+    GridSource ss = {};
     ss.pts = sb.lflat_pts; ss.pts_stride = (size_t)c.max_points; ss.ring_off = nullptr; ss.ring_off_stride = 0;
     ss.ring_cnt = nullptr; ss.ring_cnt_stride = 0; ss.dense_start = nullptr; ss.dense_start_stride = 0;
     ss.n_dense = sb.counts; ss.n_dense_stride = 8; ss.n_dense_field = 4; ss.n_rings = c.n_rings; ss.grid_scan = nullptr;
     rc = vlo_grid_build(h, h->gs_surf, ss, first, count, c.max_points); if (rc) return rc;
+    return VLO_OK;
+}
+
+// transformToEnd of the target clouds (less sharp, less flat) of scans d_scans[0..n) with transforms d_T[n][6]
+int vlo_launch_to_end(vlo_handle *h, const int *d_scans, const float *d_T, int n)
+{
+    OdomParams p = make_params(h);
+    dim3 g0((h->cap_lsharp + 255) / 256, n), g1((h->cfg.max_points + 255) / 256, n);
+    vlo_prof_begin(h, ST_TO_END);
+    k3_to_end<<<g0, 256, 0, h->stream>>>(p, d_scans, d_T, n, 0);
+    k3_to_end<<<g1, 256, 0, h->stream>>>(p, d_scans, d_T, n, 1);
+    vlo_prof_end(h, ST_TO_END);
+    h->launches += 2;
+    h->grids_valid = 0;
+    VLO_CUDA(cudaGetLastError());
     return VLO_OK;
 }
 

@@ -447,12 +447,14 @@ int vlo_launch_register_map(vlo_handle *h, const int *d_scans, int n, const floa
 {
     ScanBatchDev &sb = h->sb; const vlo_config &c = h->cfg;
     MapParams p;
-    p.lsharp_pts = sb.lsharp_pts; p.cap_lsharp = h->cap_lsharp; p.lflat_pts = sb.lflat_pts; p.N = c.max_points;
-    p.counts = sb.counts; p.n_rings = c.n_rings;
+    // queries = the sweep's down-sampled corner / surface stacks (k7_map.cu; same strides as the feature clouds)
+    (void)sb;
+    p.lsharp_pts = h->lm.ds_pts[0]; p.cap_lsharp = h->cap_lsharp; p.lflat_pts = h->lm.ds_pts[1]; p.N = c.max_points;
+    p.counts = h->lm.ds_counts; p.n_rings = c.n_rings;
     p.scans = d_scans; p.T = h->map_T; p.state = h->map_state; p.result = h->map_result;
     p.idx5 = h->map_idx5; p.qcap = h->cap_lsharp + c.max_points;
     p.partials = h->map_partials; p.pcap = (p.qcap + 31) / 32 + 8; p.ncorr = h->map_ncorr;
-    p.gm0 = h->gs_map[0]; p.gm1 = h->gs_map[1]; p.rho0 = grid_thread_rho(p.gm0.cell, 1.0f); p.rho1 = grid_thread_rho(p.gm1.cell, 1.0f); p.map0 = h->map_pts[0]; p.map1 = h->map_pts[1]; p.map_n = h->map_n;
+    p.gm0 = h->gs_map[0]; p.gm1 = h->gs_map[1]; p.rho0 = grid_thread_rho(p.gm0.cell, 1.0f); p.rho1 = grid_thread_rho(p.gm1.cell, 1.0f); p.map0 = h->map_pts[0]; p.map1 = h->map_pts[1]; p.map_n = h->lm.mode == 2 ? h->lm.sub_n : h->map_n;
     p.max_iter = c.map_max_iterations; p.degen_thr = c.map_degen_eig; p.dT_abort = c.map_delta_t_abort;
     p.dR_abort = c.map_delta_r_abort; p.rot_thr = c.dopt_rot_threshold; p.trans_thr = c.dopt_trans_threshold;
     k5_init<<<(n + 127) / 128, 128, 0, h->stream>>>(p, d_seeds, n);

@@ -26,6 +26,10 @@ extern "C" void vlo_default_config(vlo_config *c)
     c->dopt_rot_threshold = 11.5f; c->dopt_trans_threshold = 28.9f;
     c->cov_accel = 1e-6; c->cov_gyro = 1e-6; c->cov_integration = 1e-8; c->cov_bias_acc = 1e-4;
     c->cov_bias_omega = 1e-6; c->cov_bias_acc_omega_int = 1e-4;
+    c->corner_filter_size = 0.2f; c->surface_filter_size = 0.4f; c->map_cube_size = 10.0f;
+    c->map_dims[0] = 101; c->map_dims[1] = 51; c->map_dims[2] = 101;
+    c->map_start_cubes[0] = 50; c->map_start_cubes[1] = 25; c->map_start_cubes[2] = 50;
+    c->n_neighbor_cubes = 5; c->io_ratio = 2; c->hessian_order = 0;
 }
 
 extern "C" int vlo_set_lidar(vlo_config *c, const char *name)
@@ -53,11 +57,12 @@ static int ensure_pinned(vlo_handle *h, size_t bytes)
 
 static int alloc_gridset(vlo_handle *h, GridSet &g, int n_grids, int max_pts, float cell)
 {
-    int ts = 1024; while (ts < max_pts) ts <<= 1;
+    int ts = 1024; while (ts <= max_pts) ts <<= 1;      // at least one empty slot: every probe sequence terminates
     g.cell = cell; g.inv_cell = 1.0f / cell; g.ts = ts; g.max_pts = max_pts; g.G = n_grids;
     cudaError_t e;
     if ((e = dalloc(&g.keys, (size_t)n_grids * ts)) != cudaSuccess || (e = dalloc(&g.cnt, (size_t)n_grids * ts)) != cudaSuccess ||
-        (e = dalloc(&g.start, (size_t)n_grids * (ts + 1))) != cudaSuccess || (e = dalloc(&g.sorted, (size_t)n_grids * max_pts)) != cudaSuccess) {
+        (e = dalloc(&g.start, (size_t)n_grids * (ts + 1))) != cudaSuccess || (e = dalloc(&g.sorted, (size_t)n_grids * max_pts)) != cudaSuccess ||
+        (e = dalloc(&g.bsum, (size_t)n_grids * ((ts + GRID_SCAN_BLOCK - 1) / GRID_SCAN_BLOCK))) != cudaSuccess) {
         h->err = std::string("cudaMalloc grid: ") + cudaGetErrorString(e); return VLO_ERR_CUDA;
     }
     return VLO_OK;
@@ -65,7 +70,7 @@ static int alloc_gridset(vlo_handle *h, GridSet &g, int n_grids, int max_pts, fl
 
 static void free_gridset(GridSet &g)
 {
-    cudaFree(g.keys); cudaFree(g.cnt); cudaFree(g.start); cudaFree(g.sorted);
+    cudaFree(g.keys); cudaFree(g.cnt); cudaFree(g.start); cudaFree(g.sorted); cudaFree(g.bsum);
     memset(&g, 0, sizeof(g));
 }
 
@@ -85,7 +90,7 @@ extern "C" int vlo_create(const vlo_config *cfg, vlo_handle **out)
     if (cudaSetDevice(c.device) != cudaSuccess) return VLO_ERR_NO_DEVICE;
     vlo_handle *h = new vlo_handle();
     h->cfg = c; h->launches = 0; h->pinned = nullptr; h->pinned_bytes = 0;
-    memset(&h->sb, 0, sizeof(h->sb));
+    memset(&h->sb, 0, sizeof(h->sb)); memset(&h->lm, 0, sizeof(h->lm));
     memset(&h->gs_corner, 0, sizeof(GridSet)); memset(&h->gs_surf, 0, sizeof(GridSet)); memset(h->gs_map, 0, sizeof(h->gs_map));
     h->map_pts[0] = h->map_pts[1] = nullptr; h->map_n = nullptr; h->map_n_host[0] = h->map_n_host[1] = 0;
     h->grids_valid = 0; h->trace = 0; h->pair_last_T = nullptr;
@@ -143,6 +148,7 @@ extern "C" int vlo_create(const vlo_config *cfg, vlo_handle **out)
         HALLOC(h->map_idx5, (size_t)B * qcap * 5);
         HALLOC(h->map_T, (size_t)B * 6); HALLOC(h->map_seed, (size_t)B * 6); HALLOC(h->map_state, (size_t)B * 4);
         HALLOC(h->map_ncorr, (size_t)B * 2); HALLOC(h->map_scans, (size_t)B); HALLOC(h->map_result, (size_t)B);
+        { int rc = vlo_lm_alloc(h); if (rc) { vlo_destroy(h); return rc; } }
     }
     if (cudaDeviceSynchronize() != cudaSuccess) { h->err = "device sync after allocation failed"; vlo_destroy(h); return VLO_ERR_CUDA; }
     *out = h;
@@ -163,6 +169,7 @@ extern "C" void vlo_destroy(vlo_handle *h)
                      h->map_pts[0], h->map_pts[1], h->map_partials, h->map_idx5, h->map_T, h->map_seed, h->map_state, h->map_ncorr,
                      h->map_scans, h->map_result, h->imu_buf, h->imu_out };
     for (void *p : ptrs) if (p) cudaFree(p);
+    vlo_lm_free(h);
     free_gridset(h->gs_corner); free_gridset(h->gs_surf); free_gridset(h->gs_map[0]); free_gridset(h->gs_map[1]);
     if (h->pinned) cudaFreeHost(h->pinned);
     for (auto &e : h->prof_events) cudaEventDestroy(e);
@@ -180,6 +187,11 @@ extern "C" int vlo_synchronize(vlo_handle *h)
     int st = 0;
     VLO_CUDA(cudaMemcpy(&st, h->status_word, sizeof(int), cudaMemcpyDeviceToHost));
     if (st & 1) { h->err = "a ring holds more points than max_ring_points"; return VLO_ERR_CAPACITY; }
+    if (st & 2) {       // reported once: the map keeps working with the voxels it has
+        int cleared = st & ~2;
+        cudaMemcpy(h->status_word, &cleared, sizeof(int), cudaMemcpyHostToDevice);
+        h->err = "the maintained map is full (max_map_points): new voxels were dropped"; return VLO_ERR_CAPACITY;
+    }
     return VLO_OK;
 }
 
@@ -226,7 +238,7 @@ extern "C" int vlo_scans_extract(vlo_handle *h)
     if (!h) return VLO_ERR_INVALID_ARG;
     if (h->sb.n_scans < 1) { h->err = "no scans uploaded"; return VLO_ERR_STATE; }
     cudaSetDevice(h->cfg.device);
-    h->grids_valid = 0; h->map_qmax = 0;
+    h->grids_valid = 0; h->map_qmax = 0; h->lm.ds_valid = 0;
     return vlo_launch_extract(h);
 }
 
@@ -240,7 +252,7 @@ extern "C" int vlo_scans_counts(vlo_handle *h, vlo_feature_counts *counts)
     for (int b = 0; b < B; b++) {
         counts[b].n_valid = tmp[b * 8]; counts[b].n_sharp = tmp[b * 8 + 1]; counts[b].n_less_sharp = tmp[b * 8 + 2];
         counts[b].n_flat = tmp[b * 8 + 3]; counts[b].n_less_flat = tmp[b * 8 + 4];
-        h->map_qmax = std::max(h->map_qmax, tmp[b * 8 + 2] + tmp[b * 8 + 4]);
+        h->map_qmax = std::max(h->map_qmax, tmp[b * 8 + 2] + tmp[b * 8 + 4]);     // upper bound of the down-sampled stack sizes
     }
     return VLO_OK;
 }

@@ -63,8 +63,9 @@ extern "C" int vlo_map_build(vlo_handle *h, const float *corner, int n_corner, c
     VLO_CUDA(cudaMemcpyAsync(h->map_n, mn, sizeof(mn), cudaMemcpyHostToDevice, h->stream));
     VLO_CUDA(cudaStreamSynchronize(h->stream));
     h->map_n_host[0] = n_corner; h->map_n_host[1] = n_surf;
+    h->lm.mode = 1;                                   // static map: indices are the caller's, no cube window, no insertion
     for (int w = 0; w < 2; w++) {
-        GridSource src;
+        GridSource src = {};
         src.pts = h->map_pts[w]; src.pts_stride = 0; src.ring_off = nullptr; src.ring_off_stride = 0; src.ring_cnt = nullptr;
         src.ring_cnt_stride = 0; src.dense_start = nullptr; src.dense_start_stride = 0;
         src.n_dense = h->map_n; src.n_dense_stride = 0; src.n_dense_field = w == 0 ? 2 : 4; src.n_rings = 1; src.grid_scan = nullptr;
@@ -90,6 +91,7 @@ extern "C" int vlo_register_map(vlo_handle *h, const int *scans, int n, const fl
     memcpy(ps, scans, sizeof(int) * (size_t)n); memcpy(pseed, seeds, sizeof(float) * 6 * (size_t)n);
     VLO_CUDA(cudaMemcpyAsync(h->map_scans, ps, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
     VLO_CUDA(cudaMemcpyAsync(h->map_seed, pseed, sizeof(float) * 6 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    if (!h->lm.ds_valid) { rc = vlo_launch_stack_ds(h, 0, h->sb.n_scans); if (rc) return rc; h->lm.ds_valid = 1; }
     rc = vlo_launch_register_map(h, h->map_scans, n, h->map_seed); if (rc) return rc;
     VLO_CUDA(cudaMemcpyAsync(pres, h->map_result, sizeof(vlo_result) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
     rc = vlo_synchronize(h); if (rc) return rc;
@@ -107,7 +109,7 @@ extern "C" int vlo_map_get_correspondences(vlo_handle *h, int slot, int *corner_
     if (!h || slot < 0 || slot >= h->last_n_map) return VLO_ERR_INVALID_ARG;
     int rc = vlo_synchronize(h); if (rc) return rc;
     int scan; VLO_CUDA(cudaMemcpy(&scan, h->map_scans + slot, sizeof(int), cudaMemcpyDeviceToHost));
-    int cnt[8]; VLO_CUDA(cudaMemcpy(cnt, h->sb.counts + scan * 8, sizeof(cnt), cudaMemcpyDeviceToHost));
+    int cnt[8]; VLO_CUDA(cudaMemcpy(cnt, h->lm.ds_counts + scan * 8, sizeof(cnt), cudaMemcpyDeviceToHost));
     size_t qcap = (size_t)h->cap_lsharp + h->cfg.max_points;
     const int *base = h->map_idx5 + (size_t)slot * qcap * 5;
     if (corner_idx5 && cnt[2] > 0) VLO_CUDA(cudaMemcpy(corner_idx5, base, sizeof(int) * 5 * (size_t)cnt[2], cudaMemcpyDeviceToHost));
@@ -264,10 +266,13 @@ extern "C" int vlo_process_scan(vlo_handle *h, const float *raw, int n_points, i
         VLO_CUDA(cudaMemcpyAsync(h->pair_cur, &pl[1], sizeof(int), cudaMemcpyHostToDevice, h->stream));
         VLO_CUDA(cudaMemcpyAsync(h->pair_seed, seedT, sizeof(float) * 6, cudaMemcpyHostToDevice, h->stream));
         VLO_CUDA(cudaMemcpyAsync(h->pair_last_T, seedT + 6, sizeof(float) * 6, cudaMemcpyHostToDevice, h->stream));
-        // the first registered sweep has no estimate of its own motion yet: upstream stores it untouched
-        const float *lastT = (h->online_ticks >= 2 && h->cfg.deskew) ? h->pair_last_T : nullptr;
-        rc = vlo_launch_register_pairs(h, 1, h->pair_seed, lastT, last); if (rc) return rc;
+        // `last` was already moved to its sweep end right after its own registration (below); the first sweep has no
+        // estimate of its own motion and stays untouched, as upstream stores it
+        rc = vlo_launch_register_pairs(h, 1, h->pair_seed, nullptr, last); if (rc) return rc;
         VLO_CUDA(cudaMemcpyAsync(pres, h->pair_result, sizeof(vlo_result), cudaMemcpyDeviceToHost, h->stream));
+        // transformToEnd of this sweep's target clouds with its own transform (device-resident, no host round trip):
+        // they are the next tick's `last` clouds and the stack LaserMapping receives
+        if (h->cfg.deskew) { rc = vlo_launch_to_end(h, h->pair_cur, h->pair_T, 1); if (rc) return rc; }
         rc = vlo_synchronize(h); if (rc) return rc;
         h->last_n_pairs = 1;
         vlo_finish_cov_host(pres);
@@ -282,17 +287,31 @@ extern "C" int vlo_process_scan(vlo_handle *h, const float *raw, int n_points, i
     if (!did_odom && odom) { memset(odom, 0, sizeof(*odom)); for (int a = 0; a < 6; a++) odom->P[a * 7] = 1.0f; odom->status = VLO_SOFT_TOO_FEW_CORR; }
     if (mapped) {
         memset(mapped, 0, sizeof(*mapped)); mapped->status = VLO_SOFT_TOO_FEW_CORR;
-        if (h->cfg.max_map_points > 0 && h->map_n_host[0] > 10 && h->map_n_host[1] > 100) {
+        for (int a = 0; a < 6; a++) mapped->P[a * 7] = 1.0f;
+        // upstream: laserOdometry hands a sweep to laserMapping when ioRatio < 2 or frameCount % ioRatio == 1
+        const bool due = h->cfg.io_ratio < 2 || (h->online_ticks % h->cfg.io_ratio) == 1;
+        if (h->cfg.max_map_points > 0 && due) {
             // transformAssociateToMap: seed = aft * bef^-1 * sum
             double Ma[4][4], Mb[4][4], Ms[4][4], Mbi[4][4], Mt[4][4];
             euler_to_M(h->online_map_aft, Ma); euler_to_M(h->online_map_bef, Mb); euler_to_M(h->online_sum, Ms);
             M_inv(Mb, Mbi); M_mul(Ma, Mbi, Mt); M_mul(Mt, Ms, Mt);
             float seed[6]; M_to_euler(Mt, seed);
-            int sc = cur;
-            rc = vlo_register_map(h, &sc, 1, seed, mapped);
-            if (rc < 0) return rc;
-            if (mapped->status == VLO_OK) { memcpy(h->online_map_aft, mapped->transform, sizeof(float) * 6); memcpy(h->online_map_bef, h->online_sum, sizeof(float) * 6); }
-            else soft = mapped->status;
+            rc = vlo_launch_stack_ds(h, cur, 1); if (rc) return rc;
+            h->lm.ds_valid = 1;
+            int mrc = VLO_OK;
+            if (h->lm.mode == 1) {
+                // static map (vlo_map_build): registration only
+                if (h->map_n_host[0] > 10 && h->map_n_host[1] > 100) { int sc = cur; mrc = vlo_register_map(h, &sc, 1, seed, mapped); }
+            } else {
+                // maintained map: the whole BasicLaserMapping::process (sub-map, optimisation, insertion)
+                mrc = vlo_map_process(h, cur, seed, mapped, nullptr);
+            }
+            if (mrc < 0) return mrc;
+            if (mapped->status == VLO_OK || h->lm.mode != 1) {
+                // transformUpdate: upstream stores the pose whether or not the optimisation ran
+                memcpy(h->online_map_aft, mapped->transform, sizeof(float) * 6); memcpy(h->online_map_bef, h->online_sum, sizeof(float) * 6);
+            }
+            if (mapped->status != VLO_OK) soft = mapped->status;
         }
     }
     h->online_have_last = 1; h->online_slot = last; h->online_ticks++;

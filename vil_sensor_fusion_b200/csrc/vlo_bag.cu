@@ -101,6 +101,7 @@ int bag_run(vlo_handle *h, const vlo_bag_batch *batches, int n_batches, int stri
         rc = vlo_launch_extract(h); if (rc) return rc;
         h->map_qmax = 0;
         if (mode == 0) {
+            rc = vlo_launch_stack_ds(h, first, n); if (rc) return rc;
             rc = vlo_launch_register_map(h, d_idx, n, d_seed); if (rc) return rc;
             VLO_CUDA(cudaMemcpyAsync(pres + done, h->map_result, sizeof(vlo_result) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
         } else if (n_res > 0) {
@@ -117,7 +118,7 @@ int bag_run(vlo_handle *h, const vlo_bag_batch *batches, int n_batches, int stri
         VLO_CUDA(cudaEventRecord(ctx.raw_free[half], h->stream));
         done += (size_t)n_res;
     }
-    h->grids_valid = 0;
+    h->grids_valid = 0; h->lm.ds_valid = 0;
     VLO_CUDA(cudaStreamSynchronize(ctx.copy_stream));
     int rc = vlo_synchronize(h); if (rc) return rc;
     memcpy(out, pres, sizeof(vlo_result) * n_out);

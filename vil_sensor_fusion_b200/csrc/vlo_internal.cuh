@@ -21,7 +21,9 @@ struct GridSet {
     int *cnt;
     int *start;
     float4 *sorted;
+    int *bsum;           // [G][ts / GRID_SCAN_BLOCK] block sums of the build's parallel scan
 };
+#define GRID_SCAN_BLOCK 4096
 
 // where a grid build reads its points from: ring-slotted clouds (ring r's live points at
 // [ring_off[r], +ring_cnt[r]) of a per-scan base array; dense index = dense_start[r] + offset) or
@@ -34,6 +36,10 @@ struct GridSource {
     const int *n_dense; int n_dense_stride; int n_dense_field;
     int n_rings;
     const int *grid_scan;                        // optional: grid g reads scan grid_scan[g]
+    // optional sub-map filter (maintained map, k7_map.cu): point i is taken iff its cube is live and masked
+    const int *cube;                             // [n] packed cube coordinates | LM_DEAD
+    unsigned mask[42];                           // (2 nb + 1)^3 bits, x fastest
+    int mask_lo[3], mask_side;                   // cube coordinates of mask bit (0,0,0); side = 2 nb + 1
 };
 
 // Device-resident state of a batch of scans (capacities from vlo_config)
@@ -69,6 +75,29 @@ struct ScanBatchDev {
     int   *lsharp_ring_start, *lflat_ring_start; // [B][R+1]
 };
 
+// Maintained map (LaserMapping's map side, k7_map.cu).  Per cloud w (0 corner, 1 surface): leaf hash
+// (cube, voxel) -> point index, per-point cube tag, accumulators of the insertion in flight.
+#define LM_DEAD (1 << 30)
+struct LaserMapDev {
+    int lts;                              // leaf hash size (power of two)
+    unsigned long long *lkeys[2]; int *lval[2]; int *lfirst[2];
+    int *cube[2];                         // [cap]
+    int *acc[2];                          // [cap][4] sum x y z (2^-20 m), count
+    int *stamp[2]; uint8_t *fresh[2];     // [cap]
+    float4 *pm[2]; int *qslot[2]; int *qcube[2];   // per stack point temporaries [qcap_w]
+    float4 *ins_pts[2]; int *ins_n;       // staging of vlo_map_insert's host points; ins_n[8] like counts rows
+    float *ins_T;                         // [6]
+    int tick;
+    int cen[3];                           // laserCloudCenWidth / Height / Depth
+    int *sub_n;                           // device [8]: [2] / [4] = sub-map sizes (what k5 gates on)
+    // stack down-sampling (per resident scan)
+    float4 *ds_pts[2]; int *ds_counts;    // [B][cap_lsharp] / [B][N]; [B][8] fields 2 / 4
+    unsigned long long *ds_keys; int *ds_rec; int *ds_slot;   // [B][hts]; [B][hts][8]; [B][cap_lsharp + N]
+    int ds_hoff[2], ds_hsize[2], ds_hts;
+    int ds_valid;                         // down-sampled stacks of the resident batch are current
+    int mode;                             // 0 no map, 1 static (vlo_map_build), 2 maintained
+};
+
 struct vlo_handle {
     vlo_config cfg;
     cudaStream_t stream;
@@ -102,6 +131,7 @@ struct vlo_handle {
     float *map_T; float *map_seed; int *map_state; int *map_ncorr; int *map_scans; vlo_result *map_result;
     int map_qmax, last_n_map;
     int coop_resident;
+    LaserMapDev lm;
     // IMU staging (grown on demand)
     double *imu_buf; size_t imu_buf_bytes; vlo_preint *imu_out; int imu_out_cap;
     // stage profiling
@@ -116,7 +146,7 @@ struct vlo_handle {
 // per-stage device timing (bench.py's roofline leg): CUDA events on the handle's stream around
 // every launch group, summed per stage by vlo_get_stage_times
 enum VloStage { ST_ORGANISE = 0, ST_EXTRACT, ST_COMPACT, ST_GRID_BUILD, ST_TO_END, ST_ASSOC, ST_GN, ST_MAP_KNN, ST_MAP_LIN,
-                ST_MAP_SOLVE, ST_IMU, ST_COUNT };
+                ST_MAP_SOLVE, ST_IMU, ST_STACK_DS, ST_MAP_INSERT, ST_COUNT };
 void vlo_prof_begin(vlo_handle *h, int stage);
 void vlo_prof_end(vlo_handle *h, int stage);
 #define VLO_PROF(h, stage, stmt) do { vlo_prof_begin(h, stage); stmt; vlo_prof_end(h, stage); } while (0)
@@ -211,6 +241,17 @@ __device__ __forceinline__ float4 vlo_to_start(const float *T, float4 p, int des
     return make_float4(x, y, z, p.w);
 }
 
+// pointAssociateToMap: rotZ(rz) rotX(rx) rotY(ry) then + t; trig = srx crx sry cry srz crz
+__device__ __forceinline__ float4 vlo_to_map(const float *T, const float *trig, float4 pi)
+{
+    float x = pi.x, y = pi.y, z = pi.z;
+    float sx = trig[0], cx = trig[1], sy = trig[2], cy = trig[3], sz = trig[4], cz = trig[5];
+    float x0 = x; x = cz * x0 - sz * y; y = sz * x0 + cz * y;
+    float y0 = y; y = cx * y0 - sx * z; z = sx * y0 + cx * z;
+    x0 = x;       x = cy * x0 + sy * z; z = cy * z - sy * x0;
+    return make_float4(x + T[3], y + T[4], z + T[5], pi.w);
+}
+
 // kernels' host launchers -----------------------------------------------------------------------
 void vlo_finish_cov_host(vlo_result *r);
 int vlo_launch_organise(vlo_handle *h);
@@ -219,6 +260,10 @@ int vlo_grid_build(vlo_handle *h, const GridSet &gs, const GridSource &src, int 
 int vlo_grid_knn(vlo_handle *h, const GridSet &gs, int g, const float4 *d_q, int nq, int k, float dmax, int *d_idx, float *d_d2);
 int vlo_build_scan_grids(vlo_handle *h, int first, int count);
 int vlo_launch_register_pairs(vlo_handle *h, int n_pairs, const float *d_seeds, const float *d_last_T, int only_grid_scan);
+int vlo_launch_to_end(vlo_handle *h, const int *d_scans, const float *d_T, int n);
 int vlo_launch_register_map(vlo_handle *h, const int *d_scans, int n, const float *d_seeds);
+int vlo_launch_stack_ds(vlo_handle *h, int first, int count);
+int vlo_lm_alloc(vlo_handle *h);
+void vlo_lm_free(vlo_handle *h);
 int vlo_launch_imu(vlo_handle *h, const double *d_t, const double *d_acc, const double *d_gyro, int n_samples,
                    const double *d_t0, const double *d_t1, const double *d_bias, int n_factors, vlo_preint *d_out);
