@@ -104,11 +104,13 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def algorithmic_bytes(stage: str, counts, n_map_pts, iters_done):
-    """ALGORITHMIC bytes one launch of `stage` moves for the batch (SURVEY.md 8d formulas)."""
+def algorithmic_bytes(stage: str, counts, n_map_pts, iters_done, q_stack=None):
+    """ALGORITHMIC bytes one launch of `stage` moves for the batch (SURVEY.md 8d formulas).
+    q_stack = total size of the down-sampled corner + surface stacks (the scan-to-map queries)."""
     nv = sum(c["n_valid"] for c in counts)
     nfeat = sum(c["n_sharp"] + c["n_less_sharp"] + c["n_flat"] + c["n_less_flat"] for c in counts)
-    q = sum(c["n_less_sharp"] + c["n_less_flat"] for c in counts)
+    q_in = sum(c["n_less_sharp"] + c["n_less_flat"] for c in counts)
+    q = q_in if q_stack is None else q_stack
     if stage == "k0_organise":
         return nv * (16 + 16)                                # raw xyz(i) in, ring-major float4 out
     if stage == "k1_extract":
@@ -121,6 +123,8 @@ def algorithmic_bytes(stage: str, counts, n_map_pts, iters_done):
         return n_map_pts * 16 + q * (16 + 5 * 4) + (q // 32 + 1) * 28 * 4
     if stage == "k5_solve":
         return (q // 32 + 1) * 28 * 4
+    if stage == "k7_stack_ds":
+        return q_in * 16 + q * 16                            # stacks in, voxel centroids out
     return 0
 
 
@@ -185,6 +189,8 @@ def run_gpu(args):
     # ---- correctness guard: the timed path must do the work (converged, correspondences found)
     res = step(True)
     counts = h.counts()
+    nc_ds, ns_ds = h.stack_counts(B)
+    q_stack = int(nc_ds.sum() + ns_ds.sum())
     ok = int(np.sum(res["status"] == 0))
     if ok < len(res):
         print("warning: %d of %d registrations reported a soft status" % (len(res) - ok, len(res)), file=sys.stderr)
@@ -241,9 +247,10 @@ def run_gpu(args):
 
     # ---- online latency (single scan per call, the online path): p50 / p95 of vlo_process_scan
     p50 = p95 = None
+    extra_lat = {}
     if rank == 0 and not args.no_latency:
         from vil_sensor_fusion_b200 import synth
-        cfg1 = api.default_config("HDL-64E", deskew=0, max_scans=2, max_points=131072,
+        cfg1 = api.default_config("HDL-64E", deskew=0, max_scans=2, max_points=131072, io_ratio=1,
                                   max_map_points=int(max(len(cm), len(sm))), device=local_rank)
         with api.Handle(cfg1) as h1:
             h1.map_build(cm, sm)
@@ -262,6 +269,39 @@ def run_gpu(args):
             lat.sort()
             p50 = lat[len(lat) // 2]
             p95 = lat[int(len(lat) * 0.95)]
+            # scan-to-map registration + degeneracy alone (north-star target: p50 < 1 ms): the scan is resident and
+            # extracted, the call uploads the seed, registers against the 1M-point map and reads the record back
+            h1.upload([raws_pool[k % POOL] for k in range(2)])
+            h1.organise()
+            h1.extract()
+            h1.register_map([0], [seeds_pool[0]])
+            lat_map = []
+            for rep in range(40):
+                k = rep % 2
+                t1 = time.perf_counter()
+                h1.register_map([k], [seeds_pool[k]])
+                lat_map.append((time.perf_counter() - t1) * 1e3)
+            lat_map.sort()
+            extra_lat["scan_to_map_p50_ms"] = round(lat_map[len(lat_map) // 2], 4)
+            extra_lat["scan_to_map_p95_ms"] = round(lat_map[int(len(lat_map) * 0.95)], 4)
+        # the same tick with the MAINTAINED map (BasicLaserMapping::process: sub-map selection, optimisation, insertion)
+        cfg2 = api.default_config("HDL-64E", deskew=0, max_scans=2, max_points=131072, io_ratio=1,
+                                  max_map_points=1 << 20, device=local_rank)
+        with api.Handle(cfg2) as h2:
+            lat2 = []
+            for rep in range(3):
+                h2.lib.vlo_online_reset(h2._h)
+                h2.map_reset()
+                h2.map_insert(cm, sm, np.zeros(6, np.float32))          # prior map: the same 1M points, voxel-filtered
+                h2.online_set_map_pose(synth.loam_map_pose(traj.rotation(0.0), traj.position(0.0)).astype(np.float32))
+                for k in range(POOL):
+                    t1 = time.perf_counter()
+                    h2.process_scan(raws_pool[k], 0.1 * k, want_map=True)
+                    if rep > 0 and k > 0:
+                        lat2.append((time.perf_counter() - t1) * 1e3)
+            lat2.sort()
+            extra_lat["maintained_map_tick_p50_ms"] = round(lat2[len(lat2) // 2], 4)
+            extra_lat["maintained_map_points"] = list(h2.map_size())
 
     # max over ranks
     if world > 1:
@@ -296,7 +336,7 @@ def run_gpu(args):
                 # max_iter launches per call, only the first `iterations` do work: average over the working launches
                 working = max(1, int(round(args.steps * min(mean_iters, cfg.map_max_iterations))))
             avg_ms = ms / working
-            ab = algorithmic_bytes(name, counts, n_map_pts, mean_iters)
+            ab = algorithmic_bytes(name, counts, n_map_pts, mean_iters, q_stack)
             table[name] = {"ms_total": round(ms, 4), "launches": n, "working_launches": working, "avg_ms": round(avg_ms, 5),
                            "algorithmic_bytes": ab, "achieved_gbs": round(ab / (avg_ms * 1e-3) / 1e9, 2) if avg_ms > 0 else None,
                            "frac": round(ab / (avg_ms * 1e-3) / 1e9 / peak, 4) if avg_ms > 0 else None}
@@ -327,7 +367,8 @@ def run_gpu(args):
             "roofline": roofline,
             "stages": table,
             "latency": {"p50_ms_per_scan": None if p50 is None else round(p50, 4), "p95_ms_per_scan": None if p95 is None else round(p95, 4),
-                        "what": "vlo_process_scan: one online tick (H2D + organise + extract + scan-to-scan + scan-to-map + results D2H)"},
+                        "what": "vlo_process_scan: one online tick (H2D + organise + extract + scan-to-scan + scan-to-map + results D2H)",
+                        **extra_lat},
             "ok_registrations": ok, "mean_corr": [float(np.mean(res["n_corr_edge"])), float(np.mean(res["n_corr_plane"]))],
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -202,6 +202,8 @@ int vlo_map_get_points(vlo_handle *h, int which, float *xyzi, int *cube);
 /* down-sampled stacks (cornerFilterSize / surfaceFilterSize VoxelGrid of the less-sharp / less-flat clouds) of a resident
  * scan: the query clouds of vlo_register_map / vlo_map_process.  Any pointer may be NULL. */
 int vlo_scan_get_stack(vlo_handle *h, int scan, float *corner_xyzi, int *n_corner, float *surf_xyzi, int *n_surf);
+/* sizes of the down-sampled stacks of every resident scan (n_scans ints each) */
+int vlo_scans_stack_counts(vlo_handle *h, int *n_corner, int *n_surf);
 
 /* ---------------------------------------------------------------- online tick */
 /* One LOAM tick: organise + extract + scan-to-scan against the previous tick (seeded with the

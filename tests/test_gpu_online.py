@@ -49,6 +49,79 @@ def test_online_sequence_matches_oracle_chain(orc):
     assert np.all(np.abs(sum_o[3:] - gt[3:]) < 0.05), (sum_o, gt)
 
 
+def _euler_to_M(T):
+    sx, cx, sy, cy, sz, cz = np.sin(T[0]), np.cos(T[0]), np.sin(T[1]), np.cos(T[1]), np.sin(T[2]), np.cos(T[2])
+    M = np.eye(4)
+    M[0, :3] = [cy * cz + sy * sx * sz, -cy * sz + sy * sx * cz, sy * cx]
+    M[1, :3] = [cx * sz, cx * cz, -sx]
+    M[2, :3] = [-sy * cz + cy * sx * sz, sy * sz + cy * sx * cz, cy * cx]
+    M[:3, 3] = T[3:6]
+    return M
+
+
+def _M_to_euler(M):
+    return np.array([-np.arcsin(np.clip(M[1, 2], -1, 1)), np.arctan2(M[0, 2], M[2, 2]), np.arctan2(M[1, 0], M[1, 1]),
+                     M[0, 3], M[1, 3], M[2, 3]], np.float32)
+
+
+@pytest.mark.parametrize("io_ratio", [1, 2])
+def test_online_with_maintained_map_matches_oracle_chain(orc, io_ratio):
+    """The full online tick (multiScanRegistration -> laserOdometry -> laserMapping with its map maintenance ->
+    transformAssociateToMap) over a rolling-shutter VLP-16 sequence equals the oracle chained the same way: odometry
+    bit-exact, mapped pose within the north-star tolerance (the seed goes through float64 host trigonometry), map
+    sizes equal; laserMapping runs on every io_ratio-th sweep (upstream: frameCount % ioRatio == 1)."""
+    from vil_sensor_fusion_b200 import api, synth
+    traj = synth.Trajectory()
+    ocfg = orc.default_config("VLP-16", deskew=1, io_ratio=io_ratio)
+    gcfg = api.default_config("VLP-16", deskew=1, max_scans=2, max_points=32768, max_map_points=200000, io_ratio=io_ratio)
+    raws = [scenes.vlp16_scan(0.1 * k) for k in range(6)]
+    om = orc.LaserMap(ocfg, cap=200000)
+    T_prev = np.zeros(6, np.float32)
+    sum_o = np.zeros(6, np.float32)
+    aft = np.zeros(6, np.float32)
+    bef = np.zeros(6, np.float32)
+    prev = None
+    n_mapped = 0
+    with api.Handle(gcfg) as h:
+        h.map_reset()
+        for k, raw in enumerate(raws):
+            rc, odom, mapped = h.process_scan(raw, stamp=0.1 * k, want_map=True)
+            c, rs, _ = orc.organise(ocfg, raw)
+            f = orc.extract(ocfg, c, rs)
+            lc, ls = c[f["less_sharp_idx"]], f["less_flat"]
+            if k >= 1:
+                ro = orc.odometry_register(ocfg, c[f["sharp_idx"]], c[f["flat_idx"]], prev[0], prev[1], prev[2], prev[3], seed=T_prev)
+                np.testing.assert_array_equal(odom["transform"].view(np.uint32), ro["transform"].view(np.uint32), err_msg="tick %d" % k)
+                T_prev = ro["transform"]
+                sum_o = orc.accumulate_pose(sum_o, T_prev)
+                lc = orc.transform_to_end(ocfg, T_prev, lc)
+                ls = orc.transform_to_end(ocfg, T_prev, ls)
+            prev = (lc, f["less_sharp_ring_start"], ls, f["less_flat_ring_start"])
+            due = io_ratio < 2 or k % io_ratio == 1
+            if not due:
+                assert mapped["status"] == 1 and mapped["iterations"] == 0
+                continue
+            seed = _M_to_euler(_euler_to_M(aft) @ np.linalg.inv(_euler_to_M(bef)) @ _euler_to_M(sum_o))
+            rm = om.process(lc, ls, seed)
+            n_mapped += 1
+            assert mapped["status"] == rm["status"], k
+            dT = np.abs(mapped["transform"] - rm["transform"])
+            assert np.all(dT[:3] <= 1e-5) and np.all(dT[3:] <= 1e-4), (k, dT)
+            assert h.map_size() == (om.size(0), om.size(1)), k
+            aft, bef = rm["transform"], sum_o.copy()
+        _, m = h.online_pose()
+        assert np.all(np.abs(m - aft) <= 1e-4)
+    assert n_mapped == (6 if io_ratio == 1 else 3)
+    # sanity against ground truth: odometry = motion since sweep 0's end (t = 0.1); the map frame is sweep 0 as it was
+    # stored (not de-skewed, i.e. about mid-sweep), the mapped pose is sweep 5's end (t = 0.6)
+    gt_o = synth.loam_sweep_transform(traj.rotation(0.6), traj.position(0.6), traj.rotation(0.1), traj.position(0.1))
+    assert np.all(np.abs(sum_o[3:] - gt_o[3:]) < 0.06), (sum_o, gt_o)
+    if io_ratio == 1:
+        gt_m = synth.loam_sweep_transform(traj.rotation(0.6), traj.position(0.6), traj.rotation(0.05), traj.position(0.05))
+        assert np.all(np.abs(aft[3:] - gt_m[3:]) < 0.08), (aft, gt_m)
+    om.close()
+
+
 def test_pose_diff_kat():
     """gtsam_fusion/test/UnitTests.cpp:183-233: identity -> (1,1,1) gives a between translation (1,1,1)."""
     from vil_sensor_fusion_b200 import api

@@ -92,6 +92,7 @@ SYMBOLS = {
     "vlo_map_size": (C.c_int, [_VP, _VP, _VP]),
     "vlo_map_get_points": (C.c_int, [_VP, C.c_int, _VP, _VP]),
     "vlo_scan_get_stack": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP, _VP]),
+    "vlo_scans_stack_counts": (C.c_int, [_VP, _VP, _VP]),
     "vlo_online_reset": (C.c_int, [_VP]),
     "vlo_online_pose": (C.c_int, [_VP, _VP, _VP]),
     "vlo_online_set_map_pose": (C.c_int, [_VP, _VP]),

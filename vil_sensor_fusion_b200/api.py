@@ -243,6 +243,12 @@ class Handle:
         self._check(self.lib.vlo_map_get_points(self._h, which, _ptr(pts), _ptr(cube)))
         return pts[:n], cube[:n]
 
+    def stack_counts(self, n_scans: int):
+        nc = np.zeros(n_scans, np.int32)
+        ns = np.zeros(n_scans, np.int32)
+        self._check(self.lib.vlo_scans_stack_counts(self._h, _ptr(nc), _ptr(ns)))
+        return nc, ns
+
     def get_stack(self, scan: int):
         """Down-sampled corner / surface stacks of a resident scan (the scan-to-map query clouds)."""
         nc, ns = C.c_int(0), C.c_int(0)

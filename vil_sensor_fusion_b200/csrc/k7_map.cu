@@ -37,6 +37,15 @@ struct StackDsParams {
     int wmask;                                  // bit w set: cloud w is filtered here (leaf > 0)
 };
 
+// table size actually used for a stack of n points: the smallest power of two >= 2 n (at most the allocated one), so
+// that the slots a sweep touches stay L2-resident instead of being spread over a worst-case-sized table
+__device__ __forceinline__ int k7_ds_table_size(int n, int alloc)
+{
+    int hs = 1024;
+    while (hs < 2 * n) hs <<= 1;
+    return min(hs, alloc);
+}
+
 // record of a hash slot: sx sy sz sw cnt first pad pad (one 32-byte sector)
 __global__ void __launch_bounds__(256) k7_ds_bin(StackDsParams p)
 {
@@ -48,7 +57,7 @@ __global__ void __launch_bounds__(256) k7_ds_bin(StackDsParams p)
     const float4 v = p.src[w][(size_t)b * p.stride[w] + i];
     const int ix = (int)floorf(v.x * inv), iy = (int)floorf(v.y * inv), iz = (int)floorf(v.z * inv);
     const unsigned long long key = grid_key(ix, iy, iz);
-    const int hs = p.hsize[w];
+    const int hs = k7_ds_table_size(n, p.hsize[w]);
     unsigned long long *keys = p.keys + (size_t)b * p.hts + p.hoff[w];
     int slot = (int)(grid_hash(ix, iy, iz) & (unsigned)(hs - 1));
     while (true) {
@@ -531,6 +540,20 @@ extern "C" int vlo_scan_get_stack(vlo_handle *h, int scan, float *corner, int *n
     if (n_surf) *n_surf = cnt[4];
     if (corner && cnt[2] > 0) VLO_CUDA(cudaMemcpy(corner, h->lm.ds_pts[0] + (size_t)scan * h->cap_lsharp, sizeof(float4) * (size_t)cnt[2], cudaMemcpyDeviceToHost));
     if (surf && cnt[4] > 0) VLO_CUDA(cudaMemcpy(surf, h->lm.ds_pts[1] + (size_t)scan * h->cfg.max_points, sizeof(float4) * (size_t)cnt[4], cudaMemcpyDeviceToHost));
+    return VLO_OK;
+}
+
+extern "C" int vlo_scans_stack_counts(vlo_handle *h, int *n_corner, int *n_surf)
+{
+    if (!h || !n_corner || !n_surf) return VLO_ERR_INVALID_ARG;
+    if (h->cfg.max_map_points <= 0) { h->err = "handle created with max_map_points = 0"; return VLO_ERR_STATE; }
+    cudaSetDevice(h->cfg.device);
+    if (!h->lm.ds_valid) { int rc = vlo_launch_stack_ds(h, 0, h->sb.n_scans); if (rc) return rc; h->lm.ds_valid = 1; }
+    const int B = h->sb.n_scans;
+    std::vector<int> tmp((size_t)B * 8);
+    VLO_CUDA(cudaMemcpyAsync(tmp.data(), h->lm.ds_counts, sizeof(int) * tmp.size(), cudaMemcpyDeviceToHost, h->stream));
+    int rc = vlo_synchronize(h); if (rc) return rc;
+    for (int b = 0; b < B; b++) { n_corner[b] = tmp[b * 8 + 2]; n_surf[b] = tmp[b * 8 + 4]; }
     return VLO_OK;
 }
 
