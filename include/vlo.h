@@ -153,6 +153,11 @@ void       *vlo_stream(vlo_handle *h);
 /* raw: concatenated clouds, `stride_floats` float32 per point, x y z first (ROS axes), scan s owns
  * points [offsets[s], offsets[s+1]).  `on_device` != 0: raw is a device pointer (offsets stay host). */
 int vlo_scans_upload(vlo_handle *h, const float *raw, const int *offsets, int n_scans, int stride_floats, int on_device);
+/* the same for a sensor_msgs/PointCloud2 payload as it arrives (Appendix C of SURVEY.md; the reference tooling reshapes it as
+ * float32[-1, point_step/4], vil_fusion/python/downsample_pointcloud.py:45-46): `data` = concatenated `data` blobs,
+ * point_step bytes per point, FLOAT32 x / y / z at the byte offsets of fields[] (multiples of 4) */
+int vlo_scans_upload_pc2(vlo_handle *h, const void *data, const int *offsets, int n_scans, int point_step,
+                         int x_offset, int y_offset, int z_offset, int on_device);
 int vlo_scans_organise(vlo_handle *h);                      /* K0: axis swap, ring id, rel-time, ring-major float4 */
 int vlo_scans_extract(vlo_handle *h);                       /* K1: curvature, masks, sector selection, less-flat voxel filter */
 int vlo_scans_counts(vlo_handle *h, vlo_feature_counts *counts /* n_scans */);

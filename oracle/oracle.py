@@ -98,7 +98,8 @@ def _p(a, t=None):
     return a.ctypes.data_as(C.c_void_p)
 
 
-LIDAR = {"VLP-16": (-15.0, 15.0, 16), "HDL-32": (-30.67, 10.67, 32), "HDL-64E": (-24.9, 2.0, 64)}
+LIDAR = {"VLP-16": (-15.0, 15.0, 16), "HDL-32": (-30.67, 10.67, 32), "HDL-64E": (-24.9, 2.0, 64),
+         "O1-16": (-16.611, 16.611, 16), "O1-64": (-16.611, 16.611, 64), "Bperl-32": (2.3125, 89.5, 32)}
 
 
 def default_config(lidar: str = "VLP-16", **kw) -> Config:

@@ -91,3 +91,43 @@ def test_ring_capacity_error(orc):
         with pytest.raises(api.VloError) as e:
             h.synchronize()
         assert e.value.code == -3
+
+
+@pytest.mark.parametrize("lidar", ["HDL-32", "O1-16", "O1-64", "Bperl-32"])
+def test_other_lidar_presets_bit_exact(orc, lidar):
+    """Every `lidar` preset of loam_params.yaml:22: ring assignment, rel-time and features equal the oracle."""
+    from vil_sensor_fusion_b200 import api, synth
+    ocfg, gcfg = _cfgs(orc, lidar, max_scans=2, max_points=131072)
+    scene = synth.scene_room(0)
+    raws = [synth.make_scan(scene, lidar, t0=0.1 * k, traj=synth.Trajectory(), rolling=bool(k)) for k in range(2)]
+    with api.Handle(gcfg) as h:
+        h.upload(raws)
+        h.organise()
+        h.extract()
+        for i, raw in enumerate(raws):
+            fo = _check_scan(orc, h, ocfg, i, raw)
+            assert len(fo["flat_idx"]) > 50
+
+
+def test_pointcloud2_layouts(orc):
+    """sensor_msgs/PointCloud2 payloads with other field layouts (CARLA: 3 floats; a driver with x y z at offsets
+    4 / 8 / 16 of a 32-byte point) give exactly the organised cloud of the plain xyzi payload."""
+    from vil_sensor_fusion_b200 import api
+    ocfg, gcfg = _cfgs(orc, "VLP-16", max_scans=2, max_points=65536)      # staging holds max_points * 16 bytes per scan
+    raws = [scenes.vlp16_scan(0.0), scenes.ragged_scan()]
+    rng = np.random.default_rng(0)
+    with api.Handle(gcfg) as h:
+        for step, (xo, yo, zo) in ((12, (0, 4, 8)), (32, (4, 8, 16)), (20, (8, 0, 16))):
+            msgs = []
+            for raw in raws:
+                buf = rng.normal(0, 50, (raw.shape[0], step // 4)).astype(np.float32)      # junk in the other fields
+                buf[:, xo // 4], buf[:, yo // 4], buf[:, zo // 4] = raw[:, 0], raw[:, 1], raw[:, 2]
+                msgs.append(dict(data=buf.tobytes(), point_step=step, fields=dict(x=xo, y=yo, z=zo)))
+            h.upload_pointcloud2(msgs)
+            h.organise()
+            h.extract()
+            for i, raw in enumerate(raws):
+                _check_scan(orc, h, ocfg, i, raw)
+        bad = dict(data=np.zeros(30, np.uint8).tobytes(), point_step=10, fields=dict(x=0, y=4, z=8))
+        with pytest.raises(api.VloError):
+            h.upload_pointcloud2([bad])

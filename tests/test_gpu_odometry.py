@@ -129,3 +129,30 @@ def test_too_few_features_soft_status(orc):
         r = h.register_pairs([0], [1])[0]
         assert r["status"] == 1 and r["iterations"] == 0
         assert np.all(r["transform"] == 0)
+
+
+def test_hessian_order_option(orc):
+    """vlo_config.hessian_order = 1 publishes AtA / covariance in (t; r) order: a pure permutation of the
+    default record, with the D-opt gate re-read on the permuted matrix exactly as degerate_odometry_filter.cpp:32-46
+    would (block(0,0) -> "trans", block(3,3) -> "rot")."""
+    from vil_sensor_fusion_b200 import api
+    raws = [scenes.vlp16_scan(0.0, rolling=False), scenes.vlp16_scan(0.1, rolling=False)]
+    out = []
+    for order in (0, 1):
+        gcfg = api.default_config("VLP-16", deskew=0, max_scans=2, max_points=32768, hessian_order=order)
+        with api.Handle(gcfg) as h:
+            h.upload(raws)
+            h.organise()
+            h.extract()
+            out.append(h.register_pairs([0], [1])[0])
+    a, b = out
+    perm = [3, 4, 5, 0, 1, 2]
+    Ha, Hb = a["hessian"].reshape(6, 6), b["hessian"].reshape(6, 6)
+    np.testing.assert_array_equal(Hb, Ha[np.ix_(perm, perm)])
+    np.testing.assert_array_equal(b["cov"].reshape(6, 6), a["cov"].reshape(6, 6)[np.ix_(perm, perm)])
+    np.testing.assert_array_equal(a["transform"], b["transform"])
+    np.testing.assert_allclose(b["logdet_trans"], a["logdet_rot"], rtol=1e-5)
+    np.testing.assert_allclose(b["logdet_rot"], a["logdet_trans"], rtol=1e-5)
+    passed, lr, lt = api.dopt_gate(Hb)
+    assert passed == bool(b["pass_dopt"])
+    np.testing.assert_allclose([lr, lt], [b["logdet_rot"], b["logdet_trans"]], rtol=1e-6)

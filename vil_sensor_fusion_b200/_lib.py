@@ -74,6 +74,7 @@ SYMBOLS = {
     "vlo_get_stage_times": (C.c_int, [_VP, _VP, _VP]),
     "vlo_stream": (C.c_void_p, [_VP]),
     "vlo_scans_upload": (C.c_int, [_VP, _VP, _VP, C.c_int, C.c_int, C.c_int]),
+    "vlo_scans_upload_pc2": (C.c_int, [_VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "vlo_scans_organise": (C.c_int, [_VP]),
     "vlo_scans_extract": (C.c_int, [_VP]),
     "vlo_scans_counts": (C.c_int, [_VP, C.POINTER(FeatureCounts)]),

@@ -111,6 +111,18 @@ class Handle:
         self._check(self.lib.vlo_scans_upload(self._h, _ptr(raw_ptr), _ptr(offsets), len(offsets) - 1, stride, int(on_device)))
         self.n_scans = len(offsets) - 1
 
+    def upload_pointcloud2(self, msgs):
+        """msgs: list of dicts shaped like sensor_msgs/PointCloud2 -- {data: bytes / uint8 array, point_step: int,
+        fields: {name: byte offset}} (FLOAT32 x, y, z).  All messages of one call share a layout."""
+        step = int(msgs[0]["point_step"])
+        f = msgs[0]["fields"]
+        blobs = [np.frombuffer(m["data"], np.uint8) if not isinstance(m["data"], np.ndarray) else m["data"].view(np.uint8).ravel() for m in msgs]
+        offs = np.zeros(len(msgs) + 1, np.int32)
+        offs[1:] = np.cumsum([b.size // step for b in blobs])
+        data = np.ascontiguousarray(np.concatenate(blobs))
+        self._check(self.lib.vlo_scans_upload_pc2(self._h, _ptr(data), _ptr(offs), len(msgs), step, int(f["x"]), int(f["y"]), int(f["z"]), 0))
+        self.n_scans = len(msgs)
+
     def organise(self):
         self._check(self.lib.vlo_scans_organise(self._h))
 
@@ -138,10 +150,10 @@ class Handle:
         return int(self.lib.vlo_launch_count(self._h))
 
     def counts(self):
-        arr = (FeatureCounts * self.n_scans)()
+        arr = (FeatureCounts * max(self.n_scans, self.cfg.max_scans))()     # the library writes one record per resident scan
         self._check(self.lib.vlo_scans_counts(self._h, arr))
         return [dict(n_valid=a.n_valid, n_sharp=a.n_sharp, n_less_sharp=a.n_less_sharp, n_flat=a.n_flat,
-                     n_less_flat=a.n_less_flat) for a in arr]
+                     n_less_flat=a.n_less_flat) for a in arr[:self.n_scans]]
 
     def get_cloud(self, scan: int):
         c = self.counts()[scan]

@@ -10,6 +10,7 @@
 
 struct K0Params {
     const float *raw; const int *raw_offset; int stride; int scan_first;   // raw_offset: [b] = {begin, count}
+    int xo, yo, zo;   // float offsets of the ROS x, y, z fields inside a point
     int n_rings; float lower_deg, factor, scan_period;
     int N;            // capacity per scan
     int tiles;        // tiles per scan (capacity)
@@ -36,8 +37,8 @@ __global__ void k0_bounds(K0Params p, float *ori_bounds, int *first_half, int n_
     first_half[b] = 0x7fffffff;
     if (o1 <= o0) { ori_bounds[2 * b] = 0.f; ori_bounds[2 * b + 1] = 0.f; return; }
     const float *f = p.raw + (size_t)o0 * p.stride, *l = p.raw + (size_t)(o1 - 1) * p.stride;
-    float startOri = -vlo_atan2f(f[1], f[0]);
-    float endOri = -vlo_atan2f(l[1], l[0]) + 2.0f * (float)VLO_PI_D;
+    float startOri = -vlo_atan2f(f[p.yo], f[p.xo]);
+    float endOri = -vlo_atan2f(l[p.yo], l[p.xo]) + 2.0f * (float)VLO_PI_D;
     if ((double)(endOri - startOri) > 3 * VLO_PI_D) endOri = (float)((double)endOri - 2 * VLO_PI_D);
     else if ((double)(endOri - startOri) < VLO_PI_D) endOri = (float)((double)endOri + 2 * VLO_PI_D);
     ori_bounds[2 * b] = startOri; ori_bounds[2 * b + 1] = endOri;
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(K0_TILE) k0_classify(K0Params p, const float *
     int i = tile * K0_TILE + tid;
     if (i < n) {
         const float *q = p.raw + (size_t)(o0 + i) * p.stride;
-        float x = q[1], y = q[2], z = q[0];
+        float x = q[p.yo], y = q[p.zo], z = q[p.xo];
         int ring = k0_ring(p, x, y, z);
         if (ring >= 0) {
             atomicAdd(&hist[ring], 1);
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(K0_TILE) k0_scatter(K0Params p, const float *o
     int ring = -1; float x = 0.f, y = 0.f, z = 0.f;
     if (i < n) {
         const float *q = p.raw + (size_t)(o0 + i) * p.stride;
-        x = q[1]; y = q[2]; z = q[0];
+        x = q[p.yo]; y = q[p.zo]; z = q[p.xo];
         ring = k0_ring(p, x, y, z);
     }
     unsigned mask = __match_any_sync(0xffffffffu, ring);
@@ -157,6 +158,7 @@ int vlo_launch_organise(vlo_handle *h)
     ScanBatchDev &sb = h->sb;
     K0Params p;
     p.raw = sb.raw; p.raw_offset = sb.raw_offset; p.stride = sb.stride;
+    p.xo = sb.xyz_off[0]; p.yo = sb.xyz_off[1]; p.zo = sb.xyz_off[2];
     p.n_rings = h->cfg.n_rings; p.lower_deg = h->cfg.lower_deg;
     p.factor = (float)(h->cfg.n_rings - 1) / (h->cfg.upper_deg - h->cfg.lower_deg);
     p.scan_period = h->cfg.scan_period; p.N = h->cfg.max_points; p.tiles = h->tiles_per_scan;

@@ -23,6 +23,7 @@ struct MapParams {
     int *idx5; int qcap;         // [n][qcap][5]
     float *partials; int pcap;   // [n][pcap][28] level-1 sums
     int *ncorr;                  // [n][2]
+    int *done;                   // [n] CTAs of the slot that finished their tiles (k5_assoc_lin)
     GridSet gm0, gm1; int rho0, rho1; const float4 *map0, *map1; const int *map_n;
     int max_iter; float degen_thr, dT_abort, dR_abort, rot_thr, trans_thr;
 };
@@ -355,20 +356,24 @@ namespace cg = cooperative_groups;
 __global__ void __launch_bounds__(KNN_THREADS, 5) k5_assoc_lin(MapParams p, int it)
 {
     __shared__ float terms[AL_WARPS][32 * LSTRIDE];
+    __shared__ SolveSmem M;
+    __shared__ int s_last;
     const int k = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // state is written only by the slot's LAST CTA (below), after every CTA of the slot has passed this read
     if (p.state[k * 4 + 0]) return;
     const int scan = p.scans[k];
     const int n_tiles = (p.counts[scan * 8 + 2] + p.counts[scan * 8 + 4] + 31) >> 5;
-    if (!(p.map_n[2] > 10 && p.map_n[4] > 100)) return;
-    for (int tile = blockIdx.x * AL_WARPS + warp; tile < n_tiles; tile += gridDim.x * AL_WARPS)
-        k5_tile(p, k, tile, it, terms[warp], lane);
-}
-
-__global__ void __launch_bounds__(KNN_THREADS) k5_solve(MapParams p, int it)
-{
-    __shared__ SolveSmem M;
-    if (p.state[blockIdx.x * 4 + 0]) return;
-    k5_solve_slot(p, blockIdx.x, it, M);
+    if (p.map_n[2] > 10 && p.map_n[4] > 100)
+        for (int tile = blockIdx.x * AL_WARPS + warp; tile < n_tiles; tile += gridDim.x * AL_WARPS)
+            k5_tile(p, k, tile, it, terms[warp], lane);
+    // the CTA that finishes last solves the slot: no second launch, no idle tail between the two phases
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); s_last = atomicAdd(&p.done[k], 1) == (int)gridDim.x - 1; }
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x == 0) p.done[k] = 0;
+    __threadfence();
+    k5_solve_slot(p, k, it, M);
 }
 
 // Latency path (online tick, a few slots): the whole registration in ONE cooperative launch.
@@ -435,7 +440,7 @@ __global__ void k5_init(MapParams p, const float *seeds, int n)
     for (int a = 0; a < 6; a++) p.T[k * 6 + a] = seeds[k * 6 + a];
     int *st = p.state + k * 4;
     st[0] = 0; st[1] = 0; st[2] = 0; st[3] = VLO_SOFT_TOO_FEW_CORR;
-    p.ncorr[k * 2] = 0; p.ncorr[k * 2 + 1] = 0;
+    p.ncorr[k * 2] = 0; p.ncorr[k * 2 + 1] = 0; p.done[k] = 0;
     vlo_result *r = p.result + k;
     for (int a = 0; a < 6; a++) { r->transform[a] = seeds[k * 6 + a]; r->eig[a] = 0.0f; }
     for (int a = 0; a < 36; a++) { r->hessian[a] = 0.0f; r->P[a] = (a % 7 == 0) ? 1.0f : 0.0f; r->cov[a] = 0.0; }
@@ -453,7 +458,7 @@ int vlo_launch_register_map(vlo_handle *h, const int *d_scans, int n, const floa
     p.counts = h->lm.ds_counts; p.n_rings = c.n_rings;
     p.scans = d_scans; p.T = h->map_T; p.state = h->map_state; p.result = h->map_result;
     p.idx5 = h->map_idx5; p.qcap = h->cap_lsharp + c.max_points;
-    p.partials = h->map_partials; p.pcap = (p.qcap + 31) / 32 + 8; p.ncorr = h->map_ncorr;
+    p.partials = h->map_partials; p.pcap = (p.qcap + 31) / 32 + 8; p.ncorr = h->map_ncorr; p.done = h->map_done;
     p.gm0 = h->gs_map[0]; p.gm1 = h->gs_map[1]; p.rho0 = grid_thread_rho(p.gm0.cell, 1.0f); p.rho1 = grid_thread_rho(p.gm1.cell, 1.0f); p.map0 = h->map_pts[0]; p.map1 = h->map_pts[1]; p.map_n = h->lm.mode == 2 ? h->lm.sub_n : h->map_n;
     p.max_iter = c.map_max_iterations; p.degen_thr = c.map_degen_eig; p.dT_abort = c.map_delta_t_abort;
     p.dR_abort = c.map_delta_r_abort; p.rot_thr = c.dopt_rot_threshold; p.trans_thr = c.dopt_trans_threshold;
@@ -483,9 +488,8 @@ int vlo_launch_register_map(vlo_handle *h, const int *d_scans, int n, const floa
         dim3 gk(std::max(1, std::min(ctas_cap, ctas_fill)), n);
         for (int it = 0; it < c.map_max_iterations; it++) {
             VLO_PROF(h, ST_MAP_LIN, (k5_assoc_lin<<<gk, KNN_THREADS, 0, h->stream>>>(p, it)));
-            VLO_PROF(h, ST_MAP_SOLVE, (k5_solve<<<n, KNN_THREADS, 0, h->stream>>>(p, it)));
         }
-        h->launches += 1 + 2 * c.map_max_iterations;
+        h->launches += 1 + c.map_max_iterations;
     }
     VLO_CUDA(cudaGetLastError());
     return VLO_OK;

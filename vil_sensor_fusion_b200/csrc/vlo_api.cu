@@ -37,6 +37,11 @@ extern "C" int vlo_set_lidar(vlo_config *c, const char *name)
     if (!strcmp(name, "VLP-16")) { c->n_rings = 16; c->lower_deg = -15.0f; c->upper_deg = 15.0f; return VLO_OK; }
     if (!strcmp(name, "HDL-32")) { c->n_rings = 32; c->lower_deg = -30.67f; c->upper_deg = 10.67f; return VLO_OK; }
     if (!strcmp(name, "HDL-64E")) { c->n_rings = 64; c->lower_deg = -24.9f; c->upper_deg = 2.0f; return VLO_OK; }
+    // the fork's additional presets named in loam_params.yaml:22 (values: the sensors' data-sheet fields of view; the fork's
+    // own numbers are not in /root/reference)
+    if (!strcmp(name, "O1-16")) { c->n_rings = 16; c->lower_deg = -16.611f; c->upper_deg = 16.611f; return VLO_OK; }
+    if (!strcmp(name, "O1-64")) { c->n_rings = 64; c->lower_deg = -16.611f; c->upper_deg = 16.611f; return VLO_OK; }
+    if (!strcmp(name, "Bperl-32")) { c->n_rings = 32; c->lower_deg = 2.3125f; c->upper_deg = 89.5f; return VLO_OK; }
     return VLO_ERR_INVALID_ARG;
 }
 
@@ -96,7 +101,7 @@ extern "C" int vlo_create(const vlo_config *cfg, vlo_handle **out)
     h->grids_valid = 0; h->trace = 0; h->pair_last_T = nullptr;
     h->status_word = nullptr; h->pair_T = h->pair_seed = nullptr; h->pair_last = h->pair_cur = h->pair_state = nullptr;
     h->pair_cidx = h->pair_sidx = h->pair_trace = nullptr; h->pair_result = nullptr;
-    h->map_partials = nullptr; h->map_idx5 = nullptr; h->map_T = h->map_seed = nullptr; h->map_state = h->map_ncorr = h->map_scans = nullptr;
+    h->map_partials = nullptr; h->map_idx5 = nullptr; h->map_T = h->map_seed = nullptr; h->map_state = h->map_ncorr = h->map_scans = h->map_done = nullptr;
     h->map_result = nullptr; h->coop_resident = 0; h->map_qmax = 0; h->last_n_map = 0; h->last_n_pairs = 0;
     h->imu_buf = nullptr; h->imu_buf_bytes = 0; h->imu_out = nullptr; h->imu_out_cap = 0;
     h->online_have_last = 0; h->online_slot = 0; h->prof_enabled = 0; h->prof_used = 0;
@@ -147,7 +152,7 @@ extern "C" int vlo_create(const vlo_config *cfg, vlo_handle **out)
         HALLOC(h->map_partials, (size_t)B * ((qcap + 31) / 32 + 8) * VLO_NTERM);
         HALLOC(h->map_idx5, (size_t)B * qcap * 5);
         HALLOC(h->map_T, (size_t)B * 6); HALLOC(h->map_seed, (size_t)B * 6); HALLOC(h->map_state, (size_t)B * 4);
-        HALLOC(h->map_ncorr, (size_t)B * 2); HALLOC(h->map_scans, (size_t)B); HALLOC(h->map_result, (size_t)B);
+        HALLOC(h->map_ncorr, (size_t)B * 2); HALLOC(h->map_done, (size_t)B); HALLOC(h->map_scans, (size_t)B); HALLOC(h->map_result, (size_t)B);
         { int rc = vlo_lm_alloc(h); if (rc) { vlo_destroy(h); return rc; } }
     }
     if (cudaDeviceSynchronize() != cudaSuccess) { h->err = "device sync after allocation failed"; vlo_destroy(h); return VLO_ERR_CUDA; }
@@ -166,7 +171,7 @@ extern "C" void vlo_destroy(vlo_handle *h)
                      sb.lflat_cnt, sb.counts, sb.sharp_idx, sb.lsharp_idx, sb.flat_idx, sb.sharp_pts, sb.lsharp_pts, sb.flat_pts,
                      sb.lsharp_ring_start, sb.lflat_ring_start, sb.lflat_pts, h->status_word, h->pair_T, h->pair_seed, h->pair_last,
                      h->pair_cur, h->pair_state, h->pair_cidx, h->pair_sidx, h->pair_trace, h->pair_result, h->pair_last_T, h->map_n,
-                     h->map_pts[0], h->map_pts[1], h->map_partials, h->map_idx5, h->map_T, h->map_seed, h->map_state, h->map_ncorr,
+                     h->map_pts[0], h->map_pts[1], h->map_partials, h->map_idx5, h->map_T, h->map_seed, h->map_state, h->map_ncorr, h->map_done,
                      h->map_scans, h->map_result, h->imu_buf, h->imu_out };
     for (void *p : ptrs) if (p) cudaFree(p);
     vlo_lm_free(h);
@@ -195,6 +200,21 @@ extern "C" int vlo_synchronize(vlo_handle *h)
     return VLO_OK;
 }
 
+extern "C" int vlo_scans_upload_pc2(vlo_handle *h, const void *data, const int *offsets, int n_scans, int point_step,
+                                    int x_offset, int y_offset, int z_offset, int on_device)
+{
+    // sensor_msgs/PointCloud2: little-endian float32 fields at byte offsets inside points of point_step bytes
+    if (!h || point_step < 12 || (point_step & 3) || (x_offset & 3) || (y_offset & 3) || (z_offset & 3) || x_offset < 0 || y_offset < 0 ||
+        z_offset < 0 || x_offset + 4 > point_step || y_offset + 4 > point_step || z_offset + 4 > point_step ||
+        x_offset == y_offset || x_offset == z_offset || y_offset == z_offset) {
+        if (h) h->err = "PointCloud2 layout: point_step and the x/y/z offsets must be multiples of 4 inside the point (FLOAT32 fields)";
+        return VLO_ERR_INVALID_ARG;
+    }
+    int rc = vlo_scans_upload(h, (const float *)data, offsets, n_scans, point_step / 4, on_device);
+    if (rc == VLO_OK) { h->sb.xyz_off[0] = x_offset / 4; h->sb.xyz_off[1] = y_offset / 4; h->sb.xyz_off[2] = z_offset / 4; }
+    return rc;
+}
+
 extern "C" int vlo_scans_upload(vlo_handle *h, const float *raw, const int *offsets, int n_scans, int stride, int on_device)
 {
     if (!h || !raw || !offsets || n_scans < 1 || stride < 3) return VLO_ERR_INVALID_ARG;
@@ -221,6 +241,7 @@ extern "C" int vlo_scans_upload(vlo_handle *h, const float *raw, const int *offs
     // the offsets staging buffer is reused by the next call: make the copy complete first
     VLO_CUDA(cudaStreamSynchronize(h->stream));
     sb.n_scans = n_scans; sb.stride = stride; sb.scan_first = 0; sb.scan_count = n_scans;
+    sb.xyz_off[0] = 0; sb.xyz_off[1] = 1; sb.xyz_off[2] = 2;
     h->online_have_last = 0;
     return VLO_OK;
 }
@@ -324,7 +345,7 @@ extern "C" int vlo_register_pairs(vlo_handle *h, const int *last, const int *cur
     VLO_CUDA(cudaMemcpyAsync(pres, h->pair_result, sizeof(vlo_result) * (size_t)n_pairs, cudaMemcpyDeviceToHost, h->stream));
     rc = vlo_synchronize(h); if (rc) return rc;
     memcpy(out, pres, sizeof(vlo_result) * (size_t)n_pairs);
-    for (int p = 0; p < n_pairs; p++) vlo_finish_cov_host(&out[p]);
+    for (int p = 0; p < n_pairs; p++) vlo_finish_cov_host(&out[p], &h->cfg);
     h->last_n_pairs = n_pairs;
     int soft = VLO_OK;
     for (int p = 0; p < n_pairs; p++) if (out[p].status == VLO_SOFT_TOO_FEW_CORR) soft = VLO_SOFT_TOO_FEW_CORR;

@@ -36,7 +36,28 @@ static bool inv6d_host(const double *A, double *Ai)
     return true;
 }
 
-void vlo_finish_cov_host(vlo_result *r)
+static float det3h(const float *H, int off);
+
+// vlo_config.hessian_order = 1: the published matrices leave in (tx ty tz rx ry rz) order -- block(0,0) is then really
+// the translation block the filter labels it (degerate_odometry_filter.cpp:32-33) -- and the gate is
+// re-evaluated on the permuted matrix exactly as the filter would read it
+static void apply_hessian_order(vlo_result *r, const vlo_config *cfg)
+{
+    if (!cfg || cfg->hessian_order != 1) return;
+    float Hp[36]; double Cp[36];
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) {
+        const int si = (i + 3) % 6, sj = (j + 3) % 6;
+        Hp[i * 6 + j] = r->hessian[si * 6 + sj]; Cp[i * 6 + j] = r->cov[si * 6 + sj];
+    }
+    memcpy(r->hessian, Hp, sizeof(Hp)); memcpy(r->cov, Cp, sizeof(Cp));
+    if (r->n_corr_edge + r->n_corr_plane > 0) {
+        const float rot = logf(det3h(r->hessian, 3)), trans = logf(det3h(r->hessian, 0));
+        r->logdet_rot = rot; r->logdet_trans = trans;
+        r->pass_dopt = ((double)rot < (double)cfg->dopt_rot_threshold || (double)trans < (double)cfg->dopt_trans_threshold) ? 0 : 1;
+    }
+}
+
+void vlo_finish_cov_host(vlo_result *r, const vlo_config *cfg)
 {
     int n = r->n_corr_edge + r->n_corr_plane;
     if (n <= 0) { for (int i = 0; i < 36; i++) r->cov[i] = 0.0; return; }
@@ -46,6 +67,7 @@ void vlo_finish_cov_host(vlo_result *r)
     for (int i = 0; i < 36; i++) Hd[i] = (double)r->hessian[i];
     if (inv6d_host(Hd, Hi)) for (int i = 0; i < 36; i++) r->cov[i] = sigma2 * Hi[i];
     else for (int i = 0; i < 36; i++) r->cov[i] = NAN;
+    apply_hessian_order(r, cfg);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -96,7 +118,7 @@ extern "C" int vlo_register_map(vlo_handle *h, const int *scans, int n, const fl
     VLO_CUDA(cudaMemcpyAsync(pres, h->map_result, sizeof(vlo_result) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
     rc = vlo_synchronize(h); if (rc) return rc;
     memcpy(out, pres, sizeof(vlo_result) * (size_t)n);
-    for (int k = 0; k < n; k++) vlo_finish_cov_host(&out[k]);
+    for (int k = 0; k < n; k++) vlo_finish_cov_host(&out[k], &h->cfg);
     h->last_n_map = n;
     int soft = VLO_OK;
     for (int k = 0; k < n; k++) if (out[k].status == VLO_SOFT_TOO_FEW_CORR) soft = VLO_SOFT_TOO_FEW_CORR;
@@ -250,6 +272,7 @@ extern "C" int vlo_process_scan(vlo_handle *h, const float *raw, int n_points, i
     VLO_CUDA(cudaMemcpyAsync(dst, raw, sizeof(float) * (size_t)n_points * stride, cudaMemcpyHostToDevice, h->stream));
     VLO_CUDA(cudaMemcpyAsync(sb.raw_offset + 2 * cur, poff, sizeof(int) * 2, cudaMemcpyHostToDevice, h->stream));
     sb.raw = sb.raw_owned; sb.stride = stride; sb.n_scans = 2; sb.scan_first = cur; sb.scan_count = 1;
+    sb.xyz_off[0] = 0; sb.xyz_off[1] = 1; sb.xyz_off[2] = 2;
     rc = vlo_launch_organise(h); if (rc) return rc;
     rc = vlo_launch_extract(h); if (rc) return rc;
     h->map_qmax = 0;
@@ -275,7 +298,7 @@ extern "C" int vlo_process_scan(vlo_handle *h, const float *raw, int n_points, i
         if (h->cfg.deskew) { rc = vlo_launch_to_end(h, h->pair_cur, h->pair_T, 1); if (rc) return rc; }
         rc = vlo_synchronize(h); if (rc) return rc;
         h->last_n_pairs = 1;
-        vlo_finish_cov_host(pres);
+        vlo_finish_cov_host(pres, &h->cfg);
         if (pres->status == VLO_OK) memcpy(h->online_T, pres->transform, sizeof(float) * 6);
         else soft = pres->status;
         vlo_accumulate_pose(h->online_sum, h->online_T, 1.0f, h->online_sum);

@@ -67,6 +67,7 @@ int bag_run(vlo_handle *h, const vlo_bag_batch *batches, int n_batches, int stri
 
     VLO_CUDA(cudaStreamSynchronize(h->stream));
     sb.raw = sb.raw_owned; sb.stride = stride; sb.n_scans = 2 * HB;
+    sb.xyz_off[0] = 0; sb.xyz_off[1] = 1; sb.xyz_off[2] = 2;
     h->online_have_last = 0;
     size_t done = 0;
     for (int b = 0; b < n_batches; b++) {
@@ -123,7 +124,7 @@ int bag_run(vlo_handle *h, const vlo_bag_batch *batches, int n_batches, int stri
     int rc = vlo_synchronize(h); if (rc) return rc;
     memcpy(out, pres, sizeof(vlo_result) * n_out);
     int soft = VLO_OK;
-    for (size_t k = 0; k < n_out; k++) { vlo_finish_cov_host(&out[k]); if (out[k].status == VLO_SOFT_TOO_FEW_CORR) soft = VLO_SOFT_TOO_FEW_CORR; }
+    for (size_t k = 0; k < n_out; k++) { vlo_finish_cov_host(&out[k], &h->cfg); if (out[k].status == VLO_SOFT_TOO_FEW_CORR) soft = VLO_SOFT_TOO_FEW_CORR; }
     h->last_n_map = 0; h->last_n_pairs = 0;
     return soft;
 }

@@ -47,6 +47,7 @@ struct ScanBatchDev {
     int    n_scans;
     int    scan_first, scan_count;   // range the next organise / extract launch covers
     int    stride;            // floats per raw point
+    int    xyz_off[3];        // float offsets of the x, y, z fields inside a raw point (PointCloud2 fields[].offset / 4)
     const float *raw;         // device pointer (owned or borrowed)
     float *raw_owned;
     int   *raw_offset;        // [B+1] device
@@ -128,7 +129,7 @@ struct vlo_handle {
     // mapping workspace (slot k of a vlo_register_map call)
     float *map_partials;       // [n][pcap][28] level-1 sums
     int   *map_idx5;           // [n][qcap][5]
-    float *map_T; float *map_seed; int *map_state; int *map_ncorr; int *map_scans; vlo_result *map_result;
+    float *map_T; float *map_seed; int *map_state; int *map_ncorr; int *map_done; int *map_scans; vlo_result *map_result;
     int map_qmax, last_n_map;
     int coop_resident;
     LaserMapDev lm;
@@ -253,7 +254,7 @@ __device__ __forceinline__ float4 vlo_to_map(const float *T, const float *trig, 
 }
 
 // kernels' host launchers -----------------------------------------------------------------------
-void vlo_finish_cov_host(vlo_result *r);
+void vlo_finish_cov_host(vlo_result *r, const vlo_config *cfg);
 int vlo_launch_organise(vlo_handle *h);
 int vlo_launch_extract(vlo_handle *h);
 int vlo_grid_build(vlo_handle *h, const GridSet &gs, const GridSource &src, int g_first, int n_grids, int n_slots);

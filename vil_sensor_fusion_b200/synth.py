@@ -25,6 +25,10 @@ LIDAR_MODELS = {
     "VLP-16": (-15.0, 15.0, 16),
     "HDL-32": (-30.67, 10.67, 32),
     "HDL-64E": (-24.9, 2.0, 64),
+    # additional presets named by loam_params.yaml:22 (data-sheet fields of view)
+    "O1-16": (-16.611, 16.611, 16),
+    "O1-64": (-16.611, 16.611, 64),
+    "Bperl-32": (2.3125, 89.5, 32),
 }
 
 
