@@ -9,8 +9,9 @@
 //      the reduction, ballot for the +-K neighbour suppression.  Sectors run concurrently on
 //      separate warps; the only cross-sector dependency (suppression marks spilling into the next
 //      sector's first K points) is checked afterwards and the rare conflicting sector is redone.
-//   F  less-flat voxel filter: shared-memory hash on the voxel triple, integer (order-free) sums,
-//      output in order of first appearance (block scan of leader flags).
+//   F  less-flat voxel filter (k1c_lessflat, a kernel of its own so that neither phase's shared memory limits the
+//      other's occupancy): shared-memory hash on the voxel triple, integer (order-free) sums, points kept in
+//      registers, output in order of first appearance (ballot ranks + one 64-entry scan).
 #include "vlo_internal.cuh"
 
 #define K1_THREADS 256
@@ -27,30 +28,23 @@ struct K1Params {
 };
 
 struct K1Smem {
-    float *x, *y, *z, *w;
-    float *curv;            // later reused as int slot_of[]
-    uint8_t *flag;          // bit0 f1, bit1 f2, bit2 f3, bit3 gap(i,i+1) > 0.05, bit4 base picked
+    float *x, *y, *z;
+    float *curv;
+    uint8_t *flag;          // bit2 f3 (until B2), bit3 gap(i,i+1) > 0.05, bit4 base picked
     uint8_t *mark0, *mark1; // suppression marks written by even / odd sectors
     int8_t *label;
-    unsigned long long *vkey;
-    int *vfirst, *vcnt, *vsx, *vsy, *vsz, *vsw;
+    unsigned *w1, *w2;      // occlusion flags f1 / f2 as one bit per point (ballot words)
 };
 
-__device__ __forceinline__ K1Smem k1_carve(unsigned char *base, int MR, int HT)
+__device__ __forceinline__ K1Smem k1_carve(unsigned char *base, int MR)
 {
     K1Smem s;
-    s.vkey = (unsigned long long *)base; base += (size_t)HT * 8;
     s.x = (float *)base; base += (size_t)MR * 4;
     s.y = (float *)base; base += (size_t)MR * 4;
     s.z = (float *)base; base += (size_t)MR * 4;
-    s.w = (float *)base; base += (size_t)MR * 4;
     s.curv = (float *)base; base += (size_t)MR * 4;
-    s.vfirst = (int *)base; base += (size_t)HT * 4;
-    s.vcnt = (int *)base; base += (size_t)HT * 4;
-    s.vsx = (int *)base; base += (size_t)HT * 4;
-    s.vsy = (int *)base; base += (size_t)HT * 4;
-    s.vsz = (int *)base; base += (size_t)HT * 4;
-    s.vsw = (int *)base; base += (size_t)HT * 4;
+    s.w1 = (unsigned *)base; base += (size_t)(MR / 32 + 2) * 4;
+    s.w2 = (unsigned *)base; base += (size_t)(MR / 32 + 2) * 4;
     s.flag = base; base += MR;
     s.mark0 = base; base += MR;
     s.mark1 = base; base += MR;
@@ -58,7 +52,28 @@ __device__ __forceinline__ K1Smem k1_carve(unsigned char *base, int MR, int HT)
     return s;
 }
 
-static size_t k1_smem_bytes(int MR, int HT) { return (size_t)HT * 8 + (size_t)MR * 20 + (size_t)HT * 24 + (size_t)MR * 4; }
+static size_t k1_smem_bytes(int MR) { return (size_t)MR * 16 + (size_t)(MR / 32 + 2) * 8 + (size_t)MR * 4; }
+
+// less-flat voxel hash (k1c_lessflat)
+struct K1cSmem {
+    unsigned long long *vkey;
+    int *vfirst, *vcnt, *vsx, *vsy, *vsz, *vsw;
+};
+
+__device__ __forceinline__ K1cSmem k1c_carve(unsigned char *base, int HT)
+{
+    K1cSmem s;
+    s.vkey = (unsigned long long *)base; base += (size_t)HT * 8;
+    s.vfirst = (int *)base; base += (size_t)HT * 4;
+    s.vcnt = (int *)base; base += (size_t)HT * 4;
+    s.vsx = (int *)base; base += (size_t)HT * 4;
+    s.vsy = (int *)base; base += (size_t)HT * 4;
+    s.vsz = (int *)base; base += (size_t)HT * 4;
+    s.vsw = (int *)base;
+    return s;
+}
+
+static size_t k1c_smem_bytes(int HT) { return (size_t)HT * 32; }
 
 // one sector's greedy selection, executed by one full warp.
 // view_prev_lo..view_prev_hi: index range (ring-relative) where the previous sector's marks are visible.
@@ -229,17 +244,35 @@ __device__ __forceinline__ void k1_greedy_dispatch(const K1Params &p, const K1Sm
 
 extern __shared__ __align__(16) unsigned char k1_smem_raw[];
 
+// sector bounds of a ring (upstream's integer arithmetic on absolute indices); returns whether every sector is non-empty
+__device__ __forceinline__ void k1_sector_bounds(int start, int n, int K, int NR, int tid, int *s_sp, int *s_ep, int *s_all_valid)
+{
+    if (tid < NR) {
+        int a = start + K, e = start + n - 1 - K;
+        int sp = (a * (NR - tid) + e * tid) / NR;
+        int ep = (a * (NR - 1 - tid) + e * (tid + 1)) / NR - 1;
+        s_sp[tid] = sp - start; s_ep[tid] = ep - start;
+    }
+    if (tid == 0) {
+        int a = start + K, e = start + n - 1 - K, ok = 1;
+        for (int j = 0; j < NR; j++) {
+            int sp = (a * (NR - j) + e * j) / NR, ep = (a * (NR - 1 - j) + e * (j + 1)) / NR - 1;
+            if (!(ep > sp)) ok = 0;
+        }
+        *s_all_valid = ok;        // every sector non-empty: "inside some sector" == inside [sp_0, ep_last]
+    }
+}
+
 __global__ void __launch_bounds__(K1_THREADS) k1_extract(K1Params p)
 {
     __shared__ int s_sp[VLO_MAX_REGIONS], s_ep[VLO_MAX_REGIONS];
-    __shared__ int s_warp_scan[K1_THREADS / 32];
     __shared__ int s_seq, s_all_valid;
     const int r = blockIdx.x, b = p.scan_first + blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int start = p.ring_start[b * (VLO_MAX_RINGS + 1) + r];
     const int n = p.ring_start[b * (VLO_MAX_RINGS + 1) + r + 1] - start;
     const int K = p.K, NR = p.NR;
     const size_t gbase = (size_t)b * p.N + start;
-    K1Smem s = k1_carve(k1_smem_raw, p.MR, p.HT);
+    K1Smem s = k1_carve(k1_smem_raw, p.MR);
 
     // slot counters default to zero
     if (tid < NR * 4) p.slot_cnt[((size_t)(b * p.n_rings + r) * NR) * 4 + tid] = 0;
@@ -254,67 +287,70 @@ __global__ void __launch_bounds__(K1_THREADS) k1_extract(K1Params p)
     // ---- A: stage ring
     for (int i = tid; i < n; i += K1_THREADS) {
         float4 v = p.cloud[gbase + i];
-        s.x[i] = v.x; s.y[i] = v.y; s.z[i] = v.z; s.w[i] = v.w;
-        s.label[i] = 0; s.mark0[i] = 0; s.mark1[i] = 0; s.curv[i] = 0.f;
+        s.x[i] = v.x; s.y[i] = v.y; s.z[i] = v.z;
+        s.label[i] = 0; s.mark0[i] = 0; s.mark1[i] = 0;
     }
-    if (tid < NR) {
-        int a = start + K, e = start + n - 1 - K;     // absolute, as upstream's integer arithmetic
-        int sp = (a * (NR - tid) + e * tid) / NR;
-        int ep = (a * (NR - 1 - tid) + e * (tid + 1)) / NR - 1;
-        s_sp[tid] = sp - start; s_ep[tid] = ep - start;
-    }
-    if (tid == 0) {
-        s_seq = 0;
-        int a = start + K, e = start + n - 1 - K, ok = 1;
-        for (int j = 0; j < NR; j++) {
-            int sp = (a * (NR - j) + e * j) / NR, ep = (a * (NR - 1 - j) + e * (j + 1)) / NR - 1;
-            if (!(ep > sp)) ok = 0;
-        }
-        s_all_valid = ok;         // every sector non-empty: "inside some sector" == inside [sp_0, ep_last]
-    }
+    for (int k = tid; k < p.MR / 32 + 2; k += K1_THREADS) { s.w1[k] = 0u; s.w2[k] = 0u; }
+    if (tid == 0) s_seq = 0;
+    k1_sector_bounds(start, n, K, NR, tid, s_sp, s_ep, &s_all_valid);
     __syncthreads();
-    // ---- B1: per-point flags
-    for (int i = tid; i < n; i += K1_THREADS) {
+    // ---- B1: per-point flags; f1 / f2 (occlusion marks that spread over K neighbours) go to one-bit-per-point words
+    for (int base = warp * 32; base < n; base += K1_THREADS) {
+        const int i = base + lane;
         unsigned f = 0;
-        float px = s.x[i], py = s.y[i], pz = s.z[i];
-        float diffNext = 0.f;
-        if (i + 1 < n) {
-            diffNext = sqdiff3(s.x[i + 1], s.y[i + 1], s.z[i + 1], px, py, pz);
-            if ((double)diffNext > 0.05) f |= 8u;
-        }
-        if (i >= K && i < n - 1 - K) {
-            bool cont = false;
-            if ((double)diffNext > 0.1) {
-                float nx = s.x[i + 1], ny = s.y[i + 1], nz = s.z[i + 1];
-                float depth1 = sqrtf((px * px + py * py) + pz * pz);
-                float depth2 = sqrtf((nx * nx + ny * ny) + nz * nz);
-                if (depth1 > depth2) {
-                    float wq = depth2 / depth1;
-                    float wd = sqrtf(sqdiff3(nx, ny, nz, px * wq, py * wq, pz * wq)) / depth2;
-                    if ((double)wd < 0.1) { f |= 1u; cont = true; }
-                } else {
-                    float wq = depth1 / depth2;
-                    float wd = sqrtf(sqdiff3(px, py, pz, nx * wq, ny * wq, nz * wq)) / depth1;
-                    if ((double)wd < 0.1) f |= 2u;
+        if (i < n) {
+            float px = s.x[i], py = s.y[i], pz = s.z[i];
+            float diffNext = 0.f;
+            if (i + 1 < n) {
+                diffNext = sqdiff3(s.x[i + 1], s.y[i + 1], s.z[i + 1], px, py, pz);
+                if ((double)diffNext > 0.05) f |= 8u;
+            }
+            if (i >= K && i < n - 1 - K) {
+                bool cont = false;
+                if ((double)diffNext > 0.1) {
+                    float nx = s.x[i + 1], ny = s.y[i + 1], nz = s.z[i + 1];
+                    float depth1 = sqrtf((px * px + py * py) + pz * pz);
+                    float depth2 = sqrtf((nx * nx + ny * ny) + nz * nz);
+                    if (depth1 > depth2) {
+                        float wq = depth2 / depth1;
+                        float wd = sqrtf(sqdiff3(nx, ny, nz, px * wq, py * wq, pz * wq)) / depth2;
+                        if ((double)wd < 0.1) { f |= 1u; cont = true; }
+                    } else {
+                        float wq = depth1 / depth2;
+                        float wd = sqrtf(sqdiff3(px, py, pz, nx * wq, ny * wq, nz * wq)) / depth1;
+                        if ((double)wd < 0.1) f |= 2u;
+                    }
+                }
+                if (!cont) {
+                    float diffPrev = sqdiff3(px, py, pz, s.x[i - 1], s.y[i - 1], s.z[i - 1]);
+                    float dis = (px * px + py * py) + pz * pz;
+                    if ((double)diffNext > 0.0002 * (double)dis && (double)diffPrev > 0.0002 * (double)dis) f |= 4u;
                 }
             }
-            if (!cont) {
-                float diffPrev = sqdiff3(px, py, pz, s.x[i - 1], s.y[i - 1], s.z[i - 1]);
-                float dis = (px * px + py * py) + pz * pz;
-                if ((double)diffNext > 0.0002 * (double)dis && (double)diffPrev > 0.0002 * (double)dis) f |= 4u;
-            }
+            s.flag[i] = (uint8_t)(f & 12u);
         }
-        s.flag[i] = (uint8_t)f;
+        const unsigned b1 = __ballot_sync(0xffffffffu, f & 1u), b2 = __ballot_sync(0xffffffffu, f & 2u);
+        if (lane == 0) { s.w1[base >> 5] = b1; s.w2[base >> 5] = b2; }
     }
     __syncthreads();
-    // ---- B2: window-OR -> base picked (bit4);  C: curvature inside sector ranges
+    // ---- B2: window-OR -> base picked (bit4): f3(i) | any f1 in [i, i+K] | any f2 in [i-1-K, i-1];  C: curvature
     const int lo_all = s_sp[0], hi_all = s_ep[NR - 1];
     const bool all_valid = s_all_valid != 0;
     for (int i = tid; i < n; i += K1_THREADS) {
-        unsigned pk = (s.flag[i] >> 2) & 1u;
-        for (int m = 0; m <= K; m++) {
-            int a = i + m; if (a < n) pk |= (s.flag[a] & 1u);
-            int c = i - 1 - m; if (c >= 0) pk |= ((s.flag[c] >> 1) & 1u);
+        const unsigned fl = s.flag[i];
+        unsigned pk = (fl >> 2) & 1u;
+        {
+            const int j = i >> 5;
+            const unsigned v = __funnelshift_r(s.w1[j], s.w1[j + 1], i & 31);
+            pk |= (v & ((2u << K) - 1u)) != 0u;
+        }
+        {
+            const int lo = max(i - 1 - K, 0), len = i - lo;
+            if (len > 0) {
+                const int j = lo >> 5;
+                const unsigned v = __funnelshift_r(s.w2[j], s.w2[j + 1], lo & 31);
+                pk |= (v & ((1u << len) - 1u)) != 0u;
+            }
         }
         float cv = 0.f;
         if (i >= lo_all && i <= hi_all) {
@@ -333,10 +369,8 @@ __global__ void __launch_bounds__(K1_THREADS) k1_extract(K1Params p)
         }
         s.curv[i] = cv;
         p.curvature[gbase + i] = cv;
-        s.mark1[i] = (uint8_t)pk;     // stash: flag bytes are still being read by other threads
+        s.flag[i] = (uint8_t)((fl & 8u) | (pk << 4));       // nobody else reads this byte before the barrier
     }
-    __syncthreads();
-    for (int i = tid; i < n; i += K1_THREADS) { s.flag[i] = (uint8_t)(s.flag[i] | (s.mark1[i] << 4)); s.mark1[i] = 0; }
     // decide concurrent vs sequential sector processing
     if (tid == 0) {
         int seq = 0;
@@ -381,80 +415,112 @@ __global__ void __launch_bounds__(K1_THREADS) k1_extract(K1Params p)
         p.label[gbase + i] = s.label[i];
         p.picked[gbase + i] = (uint8_t)(((s.flag[i] >> 4) & 1u) | s.mark0[i] | s.mark1[i]);
     }
-    // ---- F: less-flat voxel filter
-    int *slot_of = (int *)s.curv;
+}
+
+// ---- F: less-flat voxel filter of one ring (pcl::VoxelGrid, leaf lessFlatFilterSize; V1 / V2 of the oracle).
+// Thread t keeps points t, t + 256, .. in registers (MAXP of them); the shared memory holds nothing but the hash,
+// so three CTAs fit an SM.  Output order = first appearance of the voxel along the ring: leaders are ranked by
+// (chunk of 256, warp, lane) with ballots and one scan of the MAXP x 8 warp counts.
+template <int MAXP>
+__global__ void __launch_bounds__(K1_THREADS) k1c_lessflat(K1Params p)
+{
+    __shared__ int s_sp[VLO_MAX_REGIONS], s_ep[VLO_MAX_REGIONS];
+    __shared__ int s_all_valid;
+    __shared__ int s_cnt[MAXP * (K1_THREADS / 32) + 1];
+    const int r = blockIdx.x, b = p.scan_first + blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int start = p.ring_start[b * (VLO_MAX_RINGS + 1) + r];
+    const int n = p.ring_start[b * (VLO_MAX_RINGS + 1) + r + 1] - start;
+    const int K = p.K, NR = p.NR;
+    if (n <= 2 * K + 1 || n > p.MR) return;              // k1_extract left lflat_cnt = 0 for these rings
+    const size_t gbase = (size_t)b * p.N + start;
+    K1cSmem s = k1c_carve(k1_smem_raw, p.HT);
     for (int k = tid; k < p.HT; k += K1_THREADS) {
         s.vkey[k] = K1_EMPTY; s.vfirst[k] = 0x7fffffff; s.vcnt[k] = 0; s.vsx[k] = 0; s.vsy[k] = 0; s.vsz[k] = 0; s.vsw[k] = 0;
     }
+    k1_sector_bounds(start, n, K, NR, tid, s_sp, s_ep, &s_all_valid);
     __syncthreads();
+    const int lo_all = s_sp[0], hi_all = s_ep[NR - 1];
+    const bool all_valid = s_all_valid != 0;
     const float leaf = p.leaf, inv = 1.0f / p.leaf;
-    for (int i = tid; i < n; i += K1_THREADS) {
-        int so = -1;
-        bool in = false;
-        if (i >= lo_all && i <= hi_all) {
-            in = all_valid;
-            if (!all_valid) for (int j = 0; j < NR; j++) in |= (s_ep[j] > s_sp[j] && i >= s_sp[j] && i <= s_ep[j]);
-        }
-        if (in && s.label[i] <= 0) {
-            float x = s.x[i], y = s.y[i], z = s.z[i], w = s.w[i];
-            int ix = (int)floorf(x * inv), iy = (int)floorf(y * inv), iz = (int)floorf(z * inv);
-            unsigned long long key = ((unsigned long long)(unsigned)(ix + (1 << 20)) << 42)
-                                   | ((unsigned long long)(unsigned)(iy + (1 << 20)) << 21)
-                                   | (unsigned long long)(unsigned)(iz + (1 << 20));
-            unsigned hsh = ((unsigned)ix * 73856093u) ^ ((unsigned)iy * 19349663u) ^ ((unsigned)iz * 83492791u);
-            int slot = (int)(hsh & (unsigned)(p.HT - 1));
-            while (true) {
-                unsigned long long old = atomicCAS(&s.vkey[slot], K1_EMPTY, key);
-                if (old == K1_EMPTY || old == key) break;
-                slot = (slot + 1) & (p.HT - 1);
+    float4 v[MAXP]; int so[MAXP];
+    #pragma unroll
+    for (int k = 0; k < MAXP; k++) {
+        const int i = k * K1_THREADS + tid;
+        so[k] = -1;
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n) {
+            bool in = false;
+            if (i >= lo_all && i <= hi_all) {
+                in = all_valid;
+                if (!all_valid) for (int j = 0; j < NR; j++) in |= (s_ep[j] > s_sp[j] && i >= s_sp[j] && i <= s_ep[j]);
             }
-            float ox = (float)ix * leaf, oy = (float)iy * leaf, oz = (float)iz * leaf;
-            atomicMin(&s.vfirst[slot], i);
-            atomicAdd(&s.vcnt[slot], 1);
-            atomicAdd(&s.vsx[slot], (int)rintf((x - ox) * 1048576.0f));
-            atomicAdd(&s.vsy[slot], (int)rintf((y - oy) * 1048576.0f));
-            atomicAdd(&s.vsz[slot], (int)rintf((z - oz) * 1048576.0f));
-            atomicAdd(&s.vsw[slot], (int)rintf((w - (float)(int)w) * 1048576.0f));
-            so = slot;
+            if (in && p.label[gbase + i] <= 0) {
+                const float4 q = p.cloud[gbase + i];
+                v[k] = q;
+                const int ix = (int)floorf(q.x * inv), iy = (int)floorf(q.y * inv), iz = (int)floorf(q.z * inv);
+                const unsigned long long key = ((unsigned long long)(unsigned)(ix + (1 << 20)) << 42)
+                                             | ((unsigned long long)(unsigned)(iy + (1 << 20)) << 21)
+                                             | (unsigned long long)(unsigned)(iz + (1 << 20));
+                const unsigned hsh = ((unsigned)ix * 73856093u) ^ ((unsigned)iy * 19349663u) ^ ((unsigned)iz * 83492791u);
+                int slot = (int)(hsh & (unsigned)(p.HT - 1));
+                while (true) {
+                    unsigned long long old = atomicCAS(&s.vkey[slot], K1_EMPTY, key);
+                    if (old == K1_EMPTY || old == key) break;
+                    slot = (slot + 1) & (p.HT - 1);
+                }
+                const float ox = (float)ix * leaf, oy = (float)iy * leaf, oz = (float)iz * leaf;
+                atomicMin(&s.vfirst[slot], i);
+                atomicAdd(&s.vcnt[slot], 1);
+                atomicAdd(&s.vsx[slot], (int)rintf((q.x - ox) * 1048576.0f));
+                atomicAdd(&s.vsy[slot], (int)rintf((q.y - oy) * 1048576.0f));
+                atomicAdd(&s.vsz[slot], (int)rintf((q.z - oz) * 1048576.0f));
+                atomicAdd(&s.vsw[slot], (int)rintf((q.w - (float)(int)q.w) * 1048576.0f));
+                so[k] = slot;
+            }
         }
-        slot_of[i] = so;
     }
     __syncthreads();
-    // leaders (first point of each voxel) in index order: warp w owns the contiguous segment
-    // [w*seg, (w+1)*seg), walks it 32 points at a time and ranks leaders with ballots (no bank conflicts)
-    const int seg = (((n + K1_THREADS / 32 - 1) / (K1_THREADS / 32)) + 31) & ~31;
-    const int w0 = warp * seg, w1 = min(n, w0 + seg);
-    int cnt = 0;
-    for (int i = w0 + lane; i < w0 + seg; i += 32) {
-        bool lead = false;
-        if (i < w1) { int so = slot_of[i]; lead = so >= 0 && s.vfirst[so] == i; }
-        cnt += __popc(__ballot_sync(0xffffffffu, lead));
+    unsigned bal[MAXP];
+    #pragma unroll
+    for (int k = 0; k < MAXP; k++) {
+        const bool lead = so[k] >= 0 && s.vfirst[so[k]] == k * K1_THREADS + tid;
+        bal[k] = __ballot_sync(0xffffffffu, lead);
+        if (lane == 0) s_cnt[k * (K1_THREADS / 32) + warp] = __popc(bal[k]);
     }
-    if (lane == 0) s_warp_scan[warp] = cnt;
     __syncthreads();
-    int woff = 0, total = 0;
-    for (int wv = 0; wv < K1_THREADS / 32; wv++) { int v = s_warp_scan[wv]; if (wv < warp) woff += v; total += v; }
-    int pos = woff;
-    for (int i = w0 + lane; i < w0 + seg; i += 32) {
-        bool lead = false; int so = -1;
-        if (i < w1) { so = slot_of[i]; lead = so >= 0 && s.vfirst[so] == i; }
-        unsigned bal = __ballot_sync(0xffffffffu, lead);
-        if (lead) {
-            float c = (float)s.vcnt[so];
-            float x = s.x[i], y = s.y[i], z = s.z[i];
-            int ix = (int)floorf(x * inv), iy = (int)floorf(y * inv), iz = (int)floorf(z * inv);
-            float ox = (float)ix * leaf, oy = (float)iy * leaf, oz = (float)iz * leaf;
-            const float q = 1.0f / 1048576.0f;
-            float4 o;
-            o.x = ox + ((float)s.vsx[so] / c) * q;
-            o.y = oy + ((float)s.vsy[so] / c) * q;
-            o.z = oz + ((float)s.vsz[so] / c) * q;
-            o.w = (float)(int)s.w[i] + ((float)s.vsw[so] / c) * q;
-            p.lflat_slotted[gbase + pos + __popc(bal & ((1u << lane) - 1u))] = o;
-        }
-        pos += __popc(bal);
+    if (warp == 0) {
+        // exclusive scan of the MAXP * 8 counts in (chunk, warp) order
+        constexpr int NE = MAXP * (K1_THREADS / 32), PER = (NE + 31) / 32;
+        int loc[PER], sum = 0;
+        #pragma unroll
+        for (int e = 0; e < PER; e++) { const int idx = lane * PER + e; loc[e] = idx < NE ? s_cnt[idx] : 0; sum += loc[e]; }
+        int inc = sum;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+        int run = inc - sum;
+        #pragma unroll
+        for (int e = 0; e < PER; e++) { const int idx = lane * PER + e; if (idx < NE) s_cnt[idx] = run; run += loc[e]; }
+        if (lane == 31) s_cnt[NE] = inc;
     }
-    if (tid == 0) p.lflat_cnt[b * p.n_rings + r] = total;
+    __syncthreads();
+    #pragma unroll
+    for (int k = 0; k < MAXP; k++) {
+        if (!((bal[k] >> lane) & 1u)) continue;
+        const int slot = so[k];
+        const int pos = s_cnt[k * (K1_THREADS / 32) + warp] + __popc(bal[k] & ((1u << lane) - 1u));
+        const float4 q = v[k];
+        const float c = (float)s.vcnt[slot];
+        const int ix = (int)floorf(q.x * inv), iy = (int)floorf(q.y * inv), iz = (int)floorf(q.z * inv);
+        const float ox = (float)ix * leaf, oy = (float)iy * leaf, oz = (float)iz * leaf;
+        const float qq = 1.0f / 1048576.0f;
+        float4 o;
+        o.x = ox + ((float)s.vsx[slot] / c) * qq;
+        o.y = oy + ((float)s.vsy[slot] / c) * qq;
+        o.z = oz + ((float)s.vsz[slot] / c) * qq;
+        o.w = (float)(int)q.w + ((float)s.vsw[slot] / c) * qq;
+        p.lflat_slotted[gbase + pos] = o;
+    }
+    if (tid == 0) p.lflat_cnt[b * p.n_rings + r] = s_cnt[MAXP * (K1_THREADS / 32)];
 }
 
 // K1b  compaction: per scan, exclusive scans of the per-(ring, sector) counters -> dense index
@@ -563,15 +629,25 @@ int vlo_launch_extract(vlo_handle *h)
     p.label = sb.label; p.curvature = sb.curvature; p.picked = sb.picked;
     p.slot_sharp = sb.slot_sharp; p.slot_lsharp = sb.slot_lsharp; p.slot_flat = sb.slot_flat; p.slot_cnt = sb.slot_cnt;
     p.lflat_slotted = sb.lflat_slotted; p.lflat_cnt = sb.lflat_cnt; p.status_word = h->status_word;
-    size_t smem = k1_smem_bytes(p.MR, p.HT);
-    static size_t configured = 0;
+    const size_t smem = k1_smem_bytes(p.MR), smem_c = k1c_smem_bytes(p.HT);
+    static size_t configured = 0, configured_c = 0;
     if (smem > configured) {
         VLO_CUDA(cudaFuncSetAttribute(k1_extract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
+    if (smem_c > configured_c) {
+        VLO_CUDA(cudaFuncSetAttribute(k1c_lessflat<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+        VLO_CUDA(cudaFuncSetAttribute(k1c_lessflat<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+        configured_c = smem_c;
+    }
     p.scan_first = sb.scan_first;
     dim3 grid(c.n_rings, sb.scan_count);
-    VLO_PROF(h, ST_EXTRACT, (k1_extract<<<grid, K1_THREADS, smem, h->stream>>>(p)));
+    vlo_prof_begin(h, ST_EXTRACT);
+    k1_extract<<<grid, K1_THREADS, smem, h->stream>>>(p);
+    if (p.MR <= 8 * K1_THREADS) k1c_lessflat<8><<<grid, K1_THREADS, smem_c, h->stream>>>(p);
+    else k1c_lessflat<16><<<grid, K1_THREADS, smem_c, h->stream>>>(p);
+    vlo_prof_end(h, ST_EXTRACT);
+    h->launches += 1;
     K1bParams q;
     q.cloud = sb.cloud; q.N = c.max_points; q.n_rings = c.n_rings; q.NR = c.feature_regions;
     q.max_sharp = c.max_corner_sharp; q.max_lsharp = c.max_corner_less_sharp; q.max_flat = c.max_surface_flat;
