@@ -6,7 +6,6 @@
 // reduction) and the per-ring push_back becomes a stable 3-kernel counting sort by ring.
 #include "vlo_internal.cuh"
 
-#define K0_TILE 256
 
 struct K0Params {
     const float *raw; const int *raw_offset; int stride; int scan_first;   // raw_offset: [b] = {begin, count}
@@ -45,7 +44,8 @@ __global__ void k0_bounds(K0Params p, float *ori_bounds, int *first_half, int n_
 }
 
 // pass 1: per-tile ring histogram + first index passing the half-sweep test
-__global__ void __launch_bounds__(K0_TILE) k0_classify(K0Params p, const float *ori_bounds, int *first_half, int *tile_hist)
+__global__ void __launch_bounds__(K0_TILE) k0_classify(K0Params p, const float *ori_bounds, int *first_half, int *tile_hist,
+                                                        int8_t *ring_of, float *ori_of)
 {
     __shared__ int hist[VLO_MAX_RINGS];
     __shared__ int s_first;
@@ -63,10 +63,12 @@ __global__ void __launch_bounds__(K0_TILE) k0_classify(K0Params p, const float *
         const float *q = p.raw + (size_t)(o0 + i) * p.stride;
         float x = q[p.yo], y = q[p.zo], z = q[p.xo];
         int ring = k0_ring(p, x, y, z);
+        ring_of[(size_t)b * p.N + i] = (int8_t)ring;            // the scatter pass reuses ring and raw orientation
         if (ring >= 0) {
             atomicAdd(&hist[ring], 1);
             float startOri = ori_bounds[2 * b];
             float ori = -vlo_atan2f(x, z);
+            ori_of[(size_t)b * p.N + i] = ori;
             if ((double)ori < (double)startOri - VLO_PI_D / 2) ori = (float)((double)ori + 2 * VLO_PI_D);
             else if ((double)ori > (double)startOri + VLO_PI_D * 3 / 2) ori = (float)((double)ori - 2 * VLO_PI_D);
             if ((double)(ori - startOri) > VLO_PI_D) atomicMin(&s_first, i);
@@ -107,12 +109,18 @@ __global__ void __launch_bounds__(256) k0_scan(K0Params p, int *tile_hist, int *
     }
 }
 
-// pass 3: stable scatter into ring-major order, rel-time with the final half-sweep rule
+// pass 3: stable scatter into ring-major order, rel-time with the final half-sweep rule.  The tile is first sorted by
+// ring in shared memory, so that each ring's run of the tile leaves as one contiguous, coalesced burst.
 __global__ void __launch_bounds__(K0_TILE) k0_scatter(K0Params p, const float *ori_bounds, const int *first_half,
                                                        const int *tile_hist, const int *ring_start,
-                                                       float4 *cloud, int *src_index)
+                                                       const int8_t *ring_of, const float *ori_of, float4 *cloud, int *src_index)
 {
     __shared__ int warp_cnt[K0_TILE / 32][VLO_MAX_RINGS];
+    __shared__ int run_start[VLO_MAX_RINGS + 1];     // sorted position where ring r's run of this tile starts
+    __shared__ int run_dst[VLO_MAX_RINGS];           // global position (within the scan) of that run
+    __shared__ float4 sorted[K0_TILE];
+    __shared__ int sorted_src[K0_TILE];
+    __shared__ int8_t sorted_ring[K0_TILE];
     int b = p.scan_first + blockIdx.y, tile = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int o0 = p.raw_offset[2 * b], n = p.raw_offset[2 * b + 1];
     if (tile * K0_TILE >= n) return;
@@ -123,7 +131,7 @@ __global__ void __launch_bounds__(K0_TILE) k0_scatter(K0Params p, const float *o
     if (i < n) {
         const float *q = p.raw + (size_t)(o0 + i) * p.stride;
         x = q[p.yo]; y = q[p.zo]; z = q[p.xo];
-        ring = k0_ring(p, x, y, z);
+        ring = ring_of[(size_t)b * p.N + i];
     }
     unsigned mask = __match_any_sync(0xffffffffu, ring);
     int rank = __popc(mask & ((1u << lane) - 1u));
@@ -131,26 +139,50 @@ __global__ void __launch_bounds__(K0_TILE) k0_scatter(K0Params p, const float *o
     __syncthreads();
     if (tid < p.n_rings) {
         int run = 0;
-        #pragma unroll
+        #pragma unroll 8
         for (int w = 0; w < K0_TILE / 32; w++) { int v = warp_cnt[w][tid]; warp_cnt[w][tid] = run; run += v; }
+        run_start[tid + 1] = run;                                 // ring totals of the tile, scanned below
+        run_dst[tid] = ring_start[b * (VLO_MAX_RINGS + 1) + tid] + tile_hist[((size_t)b * p.n_rings + tid) * p.tiles + tile];
     }
     __syncthreads();
-    if (ring < 0) return;
-    float startOri = ori_bounds[2 * b], endOri = ori_bounds[2 * b + 1];
-    float ori = -vlo_atan2f(x, z);
-    if (i <= first_half[b]) {
-        if ((double)ori < (double)startOri - VLO_PI_D / 2) ori = (float)((double)ori + 2 * VLO_PI_D);
-        else if ((double)ori > (double)startOri + VLO_PI_D * 3 / 2) ori = (float)((double)ori - 2 * VLO_PI_D);
-    } else {
-        ori = (float)((double)ori + 2 * VLO_PI_D);
-        if ((double)ori < (double)endOri - VLO_PI_D * 3 / 2) ori = (float)((double)ori + 2 * VLO_PI_D);
-        else if ((double)ori > (double)endOri + VLO_PI_D / 2) ori = (float)((double)ori - 2 * VLO_PI_D);
+    if (warp == 0) {
+        // inclusive scan of the (up to 128) ring totals: 4 consecutive entries per lane + one shuffle scan
+        int loc[4], sum = 0;
+        #pragma unroll
+        for (int e = 0; e < 4; e++) { const int r = lane * 4 + e; loc[e] = r < p.n_rings ? run_start[r + 1] : 0; sum += loc[e]; }
+        int inc = sum;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+        int run = inc - sum;
+        #pragma unroll
+        for (int e = 0; e < 4; e++) { const int r = lane * 4 + e; run += loc[e]; if (r < p.n_rings) run_start[r + 1] = run; }
+        if (lane == 0) run_start[0] = 0;
     }
-    float relTime = p.scan_period * (ori - startOri) / (endOri - startOri);
-    int pos = ring_start[b * (VLO_MAX_RINGS + 1) + ring]
-            + tile_hist[((size_t)b * p.n_rings + ring) * p.tiles + tile] + warp_cnt[warp][ring] + rank;
-    cloud[(size_t)b * p.N + pos] = make_float4(x, y, z, (float)ring + relTime);
-    src_index[(size_t)b * p.N + pos] = i;
+    __syncthreads();
+    if (ring >= 0) {
+        float startOri = ori_bounds[2 * b], endOri = ori_bounds[2 * b + 1];
+        float ori = ori_of[(size_t)b * p.N + i];
+        if (i <= first_half[b]) {
+            if ((double)ori < (double)startOri - VLO_PI_D / 2) ori = (float)((double)ori + 2 * VLO_PI_D);
+            else if ((double)ori > (double)startOri + VLO_PI_D * 3 / 2) ori = (float)((double)ori - 2 * VLO_PI_D);
+        } else {
+            ori = (float)((double)ori + 2 * VLO_PI_D);
+            if ((double)ori < (double)endOri - VLO_PI_D * 3 / 2) ori = (float)((double)ori + 2 * VLO_PI_D);
+            else if ((double)ori > (double)endOri + VLO_PI_D / 2) ori = (float)((double)ori - 2 * VLO_PI_D);
+        }
+        float relTime = p.scan_period * (ori - startOri) / (endOri - startOri);
+        const int sp = run_start[ring] + warp_cnt[warp][ring] + rank;
+        sorted[sp] = make_float4(x, y, z, (float)ring + relTime);
+        sorted_src[sp] = i;
+        sorted_ring[sp] = (int8_t)ring;
+    }
+    __syncthreads();
+    if (tid < run_start[p.n_rings]) {
+        const int r = sorted_ring[tid];
+        const size_t pos = (size_t)b * p.N + run_dst[r] + (tid - run_start[r]);
+        cloud[pos] = sorted[tid];
+        src_index[pos] = sorted_src[tid];
+    }
 }
 
 int vlo_launch_organise(vlo_handle *h)
@@ -166,10 +198,10 @@ int vlo_launch_organise(vlo_handle *h)
     vlo_prof_begin(h, ST_ORGANISE);
     k0_bounds<<<(B + 127) / 128, 128, 0, h->stream>>>(p, sb.ori_bounds, sb.first_half, B);
     dim3 grid(h->tiles_per_scan, B);
-    k0_classify<<<grid, K0_TILE, 0, h->stream>>>(p, sb.ori_bounds, sb.first_half, sb.tile_hist);
+    k0_classify<<<grid, K0_TILE, 0, h->stream>>>(p, sb.ori_bounds, sb.first_half, sb.tile_hist, sb.ring_of, sb.ori_of);
     k0_scan<<<B, 256, 0, h->stream>>>(p, sb.tile_hist, sb.ring_start, sb.counts);
     k0_scatter<<<grid, K0_TILE, 0, h->stream>>>(p, sb.ori_bounds, sb.first_half, sb.tile_hist, sb.ring_start,
-                                                sb.cloud, sb.src_index);
+                                                sb.ring_of, sb.ori_of, sb.cloud, sb.src_index);
     vlo_prof_end(h, ST_ORGANISE);
     h->launches += 4;
     VLO_CUDA(cudaGetLastError());

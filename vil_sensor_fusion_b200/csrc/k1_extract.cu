@@ -556,7 +556,10 @@ __global__ void __launch_bounds__(256) k1b_compact(K1bParams p)
     __shared__ int off_ls[VLO_MAX_RINGS * VLO_MAX_REGIONS + 1];
     __shared__ int off_flat[VLO_MAX_RINGS * VLO_MAX_REGIONS + 1];
     __shared__ int warp_buf[8];
-    const int b = p.scan_first + blockIdx.x, tid = threadIdx.x;
+    __shared__ int lf_start[VLO_MAX_RINGS + 1];
+    // K1B_PARTS CTAs per scan: each redoes the (tiny) prefix scans and takes its share of the copies and gathers;
+    // part 0 alone publishes the counts and ring offsets
+    const int b = p.scan_first + blockIdx.x, tid = threadIdx.x, part = blockIdx.y, parts = gridDim.y;
     const int nsec = p.n_rings * p.NR;
     {
         // per-thread chunk of consecutive sectors, block scan of the chunk sums, then local running offsets
@@ -575,16 +578,19 @@ __global__ void __launch_bounds__(256) k1b_compact(K1bParams p)
         int lf0 = k1b_block_scan(cnt, warp_buf, tlf);
         __syncthreads();
         if (tid <= VLO_MAX_RINGS) {
-            p.lsharp_ring_start[b * (VLO_MAX_RINGS + 1) + tid] = (tid < p.n_rings) ? off_ls[tid * p.NR] : tl;
-            p.lflat_ring_start[b * (VLO_MAX_RINGS + 1) + tid] = (tid < p.n_rings) ? lf0 : tlf;
+            lf_start[tid] = (tid < p.n_rings) ? lf0 : tlf;
+            if (part == 0) {
+                p.lsharp_ring_start[b * (VLO_MAX_RINGS + 1) + tid] = (tid < p.n_rings) ? off_ls[tid * p.NR] : tl;
+                p.lflat_ring_start[b * (VLO_MAX_RINGS + 1) + tid] = (tid < p.n_rings) ? lf0 : tlf;
+            }
         }
-        if (tid == 0) { p.counts[b * 8 + 1] = ta; p.counts[b * 8 + 2] = tl; p.counts[b * 8 + 3] = tf; p.counts[b * 8 + 4] = tlf; }
+        if (tid == 0 && part == 0) { p.counts[b * 8 + 1] = ta; p.counts[b * 8 + 2] = tl; p.counts[b * 8 + 3] = tf; p.counts[b * 8 + 4] = tlf; }
     }
     __syncthreads();
     // dense less-flat cloud: ring r's centroids move from their ring slot to [lflat_ring_start[r], +cnt)
     // (coalesced float4 copies; every consumer downstream reads the dense array)
-    for (int r = tid >> 5; r < p.n_rings; r += blockDim.x >> 5) {
-        int d0 = p.lflat_ring_start[b * (VLO_MAX_RINGS + 1) + r], s0 = p.ring_start[b * (VLO_MAX_RINGS + 1) + r];
+    for (int r = part * (blockDim.x >> 5) + (tid >> 5); r < p.n_rings; r += parts * (blockDim.x >> 5)) {
+        int d0 = lf_start[r], s0 = p.ring_start[b * (VLO_MAX_RINGS + 1) + r];
         int cnt = p.lflat_cnt[b * p.n_rings + r];
         const float4 *src = p.lflat_slotted + (size_t)b * p.N + s0;
         float4 *dst = p.lflat_pts + (size_t)b * p.N + d0;
@@ -592,7 +598,7 @@ __global__ void __launch_bounds__(256) k1b_compact(K1bParams p)
     }
     const float4 *cloud = p.cloud + (size_t)b * p.N;
     const int maxq = max(p.max_lsharp, max(p.max_sharp, p.max_flat));
-    for (int k = tid; k < nsec * maxq; k += blockDim.x) {
+    for (int k = part * blockDim.x + tid; k < nsec * maxq; k += parts * blockDim.x) {
         int sec = k / maxq, q = k % maxq;
         const uint8_t *c = p.slot_cnt + ((size_t)b * nsec + sec) * 4;
         if (q < p.max_lsharp && q < c[1]) {
@@ -659,7 +665,7 @@ int vlo_launch_extract(vlo_handle *h)
     q.lsharp_ring_start = sb.lsharp_ring_start; q.lflat_ring_start = sb.lflat_ring_start;
     q.ring_start = sb.ring_start; q.lflat_slotted = sb.lflat_slotted; q.lflat_pts = sb.lflat_pts;
     q.scan_first = sb.scan_first;
-    VLO_PROF(h, ST_COMPACT, (k1b_compact<<<sb.scan_count, 256, 0, h->stream>>>(q)));
+    VLO_PROF(h, ST_COMPACT, (k1b_compact<<<dim3(sb.scan_count, sb.scan_count >= 64 ? 8 : 16), 256, 0, h->stream>>>(q)));
     h->launches += 2;
     VLO_CUDA(cudaGetLastError());
     return VLO_OK;

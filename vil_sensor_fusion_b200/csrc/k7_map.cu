@@ -47,33 +47,48 @@ __device__ __forceinline__ int k7_ds_table_size(int n, int alloc)
 }
 
 // record of a hash slot: sx sy sz sw cnt first pad pad (one 32-byte sector)
+// Consecutive points of a ring fall into the same 0.2 / 0.4 m voxel more often than not: the lanes of a warp that share
+// a voxel (match_any on the key) reduce their integer sums with REDUX first and one lane issues the atomics.
 __global__ void __launch_bounds__(256) k7_ds_bin(StackDsParams p)
 {
-    const int b = p.scan_first + blockIdx.y, w = blockIdx.z, i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = p.scan_first + blockIdx.y, w = blockIdx.z, i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     if (!((p.wmask >> w) & 1)) return;
     const int n = p.counts[b * 8 + (w ? 4 : 2)];
-    if (i >= n) return;
+    if ((int)(blockIdx.x * blockDim.x) >= n) return;                 // whole CTA out of range
+    const bool valid = i < n;
     const float leaf = p.leaf[w], inv = 1.0f / leaf;
-    const float4 v = p.src[w][(size_t)b * p.stride[w] + i];
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) v = p.src[w][(size_t)b * p.stride[w] + i];
     const int ix = (int)floorf(v.x * inv), iy = (int)floorf(v.y * inv), iz = (int)floorf(v.z * inv);
-    const unsigned long long key = grid_key(ix, iy, iz);
-    const int hs = k7_ds_table_size(n, p.hsize[w]);
-    unsigned long long *keys = p.keys + (size_t)b * p.hts + p.hoff[w];
-    int slot = (int)(grid_hash(ix, iy, iz) & (unsigned)(hs - 1));
-    while (true) {
-        unsigned long long old = atomicCAS(&keys[slot], LM_EMPTY, key);
-        if (old == LM_EMPTY || old == key) break;
-        slot = (slot + 1) & (hs - 1);
-    }
-    int *rec = p.rec + ((size_t)b * p.hts + p.hoff[w] + slot) * 8;
+    // lanes past the end get private keys (bit 63 is never set in a grid key)
+    const unsigned long long key = valid ? grid_key(ix, iy, iz) : (0x8000000000000000ull | (unsigned long long)lane);
     const float ox = (float)ix * leaf, oy = (float)iy * leaf, oz = (float)iz * leaf;
-    atomicAdd(&rec[0], (int)rintf((v.x - ox) * LM_QF));
-    atomicAdd(&rec[1], (int)rintf((v.y - oy) * LM_QF));
-    atomicAdd(&rec[2], (int)rintf((v.z - oz) * LM_QF));
-    atomicAdd(&rec[3], (int)rintf((v.w - (float)(int)v.w) * LM_QF));
-    atomicAdd(&rec[4], 1);
-    atomicMin(&rec[5], i);
-    p.slot_of[(size_t)b * p.qstride + (w ? p.qoff1 : 0) + i] = slot;
+    int qx = (int)rintf((v.x - ox) * LM_QF), qy = (int)rintf((v.y - oy) * LM_QF), qz = (int)rintf((v.z - oz) * LM_QF);
+    int qw = (int)rintf((v.w - (float)(int)v.w) * LM_QF);
+    const unsigned grp = __match_any_sync(0xffffffffu, key);
+    const int leader = __ffs(grp) - 1;
+    int cnt = 1, first = i;
+    if (grp != (1u << lane)) {                                        // shared voxel: reduce inside the group
+        qx = __reduce_add_sync(grp, qx); qy = __reduce_add_sync(grp, qy); qz = __reduce_add_sync(grp, qz);
+        qw = __reduce_add_sync(grp, qw); cnt = __popc(grp); first = __reduce_min_sync(grp, i);
+    }
+    int slot = 0;
+    if (valid && lane == leader) {
+        const int hs = k7_ds_table_size(n, p.hsize[w]);
+        unsigned long long *keys = p.keys + (size_t)b * p.hts + p.hoff[w];
+        slot = (int)(grid_hash(ix, iy, iz) & (unsigned)(hs - 1));
+        while (true) {
+            unsigned long long old = atomicCAS(&keys[slot], LM_EMPTY, key);
+            if (old == LM_EMPTY || old == key) break;
+            slot = (slot + 1) & (hs - 1);
+        }
+        int *rec = p.rec + ((size_t)b * p.hts + p.hoff[w] + slot) * 8;
+        atomicAdd(&rec[0], qx); atomicAdd(&rec[1], qy); atomicAdd(&rec[2], qz); atomicAdd(&rec[3], qw);
+        atomicAdd(&rec[4], cnt);
+        atomicMin(&rec[5], first);
+    }
+    slot = __shfl_sync(0xffffffffu, slot, leader);
+    if (valid) p.slot_of[(size_t)b * p.qstride + (w ? p.qoff1 : 0) + i] = slot;
 }
 
 // ordered block scan of one flag per thread (1024 threads); returns the exclusive rank, `total` = block total
@@ -90,10 +105,13 @@ __device__ __forceinline__ int k7_block_rank(bool flag, int *warp_buf, int &tota
     return off + __popc(bal & ((1u << lane) - 1u));
 }
 
+// Four points per thread and round: the four (slot, leader-index) load chains of a thread are independent, so the
+// L2 latency of the hash records overlaps; leaders are ranked in index order = (sub-chunk j, warp, lane).
+#define K7_EMIT_PER 4
 __global__ void __launch_bounds__(1024) k7_ds_emit(StackDsParams p)
 {
-    __shared__ int warp_buf[32];
-    const int b = p.scan_first + blockIdx.x, w = blockIdx.y, tid = threadIdx.x;
+    __shared__ int s_cnt[K7_EMIT_PER * 32 + 1];
+    const int b = p.scan_first + blockIdx.x, w = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (!((p.wmask >> w) & 1)) return;
     const int n = p.counts[b * 8 + (w ? 4 : 2)];
     const float leaf = p.leaf[w], inv = 1.0f / leaf;
@@ -102,29 +120,57 @@ __global__ void __launch_bounds__(1024) k7_ds_emit(StackDsParams p)
     const int *slot_of = p.slot_of + (size_t)b * p.qstride + (w ? p.qoff1 : 0);
     float4 *dst = p.dst[w] + (size_t)b * p.stride[w];
     int carry = 0;
-    for (int base = 0; base < n; base += 1024) {
-        const int i = base + tid;
-        int slot = -1; bool lead = false;
-        if (i < n) { slot = slot_of[i]; lead = recs[slot * 8 + 5] == i; }
-        int total;
-        const int pos = carry + k7_block_rank(lead, warp_buf, total);
-        if (lead) {
-            int *rec = recs + slot * 8;
+    for (int base = 0; base < n; base += 1024 * K7_EMIT_PER) {
+        int slot[K7_EMIT_PER]; unsigned bal[K7_EMIT_PER];
+        #pragma unroll
+        for (int j = 0; j < K7_EMIT_PER; j++) { const int i = base + j * 1024 + tid; slot[j] = i < n ? slot_of[i] : -1; }
+        #pragma unroll
+        for (int j = 0; j < K7_EMIT_PER; j++) {
+            const int i = base + j * 1024 + tid;
+            const bool lead = slot[j] >= 0 && recs[slot[j] * 8 + 5] == i;
+            bal[j] = __ballot_sync(0xffffffffu, lead);
+        }
+        __syncthreads();                                   // s_cnt may still be read from the previous round
+        if (lane == 0) {
+            #pragma unroll
+            for (int j = 0; j < K7_EMIT_PER; j++) s_cnt[j * 32 + warp] = __popc(bal[j]);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            int loc[K7_EMIT_PER], sum = 0;
+            #pragma unroll
+            for (int e = 0; e < K7_EMIT_PER; e++) { loc[e] = s_cnt[lane * K7_EMIT_PER + e]; sum += loc[e]; }
+            int inc = sum;
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+            int run = inc - sum;
+            #pragma unroll
+            for (int e = 0; e < K7_EMIT_PER; e++) { s_cnt[lane * K7_EMIT_PER + e] = run; run += loc[e]; }
+            if (lane == 31) s_cnt[K7_EMIT_PER * 32] = inc;
+        }
+        __syncthreads();
+        #pragma unroll
+        for (int j = 0; j < K7_EMIT_PER; j++) {
+            if (!((bal[j] >> lane) & 1u)) continue;
+            const int i = base + j * 1024 + tid;
+            const int pos = carry + s_cnt[j * 32 + warp] + __popc(bal[j] & ((1u << lane) - 1u));
+            int *rec = recs + slot[j] * 8;
             const float4 v = p.src[w][(size_t)b * p.stride[w] + i];
             const int ix = (int)floorf(v.x * inv), iy = (int)floorf(v.y * inv), iz = (int)floorf(v.z * inv);
             const float ox = (float)ix * leaf, oy = (float)iy * leaf, oz = (float)iz * leaf;
+            const int4 sums = *(const int4 *)rec;
             const float c = (float)rec[4], q = 1.0f / 1048576.0f;
             float4 o;
-            o.x = ox + ((float)rec[0] / c) * q;
-            o.y = oy + ((float)rec[1] / c) * q;
-            o.z = oz + ((float)rec[2] / c) * q;
-            o.w = (float)(int)v.w + ((float)rec[3] / c) * q;
+            o.x = ox + ((float)sums.x / c) * q;
+            o.y = oy + ((float)sums.y / c) * q;
+            o.z = oz + ((float)sums.z / c) * q;
+            o.w = (float)(int)v.w + ((float)sums.w / c) * q;
             dst[pos] = o;
             // the leader owns the slot: leave it clean for the next sweep (others only compare rec[5] with their index)
-            rec[0] = 0; rec[1] = 0; rec[2] = 0; rec[3] = 0; rec[4] = 0; rec[5] = 0x7fffffff;
-            keys[slot] = LM_EMPTY;
+            *(int4 *)rec = make_int4(0, 0, 0, 0); rec[4] = 0; rec[5] = 0x7fffffff;
+            keys[slot[j]] = LM_EMPTY;
         }
-        carry += total;
+        carry += s_cnt[K7_EMIT_PER * 32];
     }
     if (tid == 0) p.ds_counts[b * 8 + (w ? 4 : 2)] = carry;
 }

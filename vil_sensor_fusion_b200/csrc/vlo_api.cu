@@ -109,7 +109,7 @@ extern "C" int vlo_create(const vlo_config *cfg, vlo_handle **out)
     memset(h->online_map_bef, 0, sizeof(h->online_map_bef)); memset(h->online_map_aft, 0, sizeof(h->online_map_aft)); h->online_ticks = 0;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return VLO_ERR_CUDA; }
     const int B = c.max_scans, N = c.max_points, R = c.n_rings, NR = c.feature_regions;
-    h->tiles_per_scan = (N + 255) / 256;
+    h->tiles_per_scan = (N + K0_TILE - 1) / K0_TILE;
     h->cap_sharp = R * NR * std::max(c.max_corner_sharp, 1);
     h->cap_lsharp = R * NR * std::max(c.max_corner_less_sharp, 1);
     h->cap_flat = R * NR * std::max(c.max_surface_flat, 1);
@@ -120,6 +120,7 @@ extern "C" int vlo_create(const vlo_config *cfg, vlo_handle **out)
     HALLOC(sb.raw_offset, (size_t)B * 2);
     HALLOC(sb.first_half, (size_t)B); HALLOC(sb.ori_bounds, (size_t)B * 2);
     HALLOC(sb.tile_hist, (size_t)B * R * h->tiles_per_scan);
+    HALLOC(sb.ring_of, (size_t)B * N); HALLOC(sb.ori_of, (size_t)B * N);
     HALLOC(sb.cloud, (size_t)B * N); HALLOC(sb.ring_start, (size_t)B * (VLO_MAX_RINGS + 1)); HALLOC(sb.src_index, (size_t)B * N);
     HALLOC(sb.label, (size_t)B * N); HALLOC(sb.curvature, (size_t)B * N); HALLOC(sb.picked, (size_t)B * N);
     HALLOC(sb.slot_sharp, (size_t)B * h->cap_sharp); HALLOC(sb.slot_lsharp, (size_t)B * h->cap_lsharp);
@@ -166,7 +167,7 @@ extern "C" void vlo_destroy(vlo_handle *h)
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
     ScanBatchDev &sb = h->sb;
-    void *ptrs[] = { sb.raw_owned, sb.raw_offset, sb.first_half, sb.ori_bounds, sb.tile_hist, sb.cloud, sb.ring_start, sb.src_index,
+    void *ptrs[] = { sb.raw_owned, sb.raw_offset, sb.first_half, sb.ori_bounds, sb.tile_hist, sb.ring_of, sb.ori_of, sb.cloud, sb.ring_start, sb.src_index,
                      sb.label, sb.curvature, sb.picked, sb.slot_sharp, sb.slot_lsharp, sb.slot_flat, sb.slot_cnt, sb.lflat_slotted,
                      sb.lflat_cnt, sb.counts, sb.sharp_idx, sb.lsharp_idx, sb.flat_idx, sb.sharp_pts, sb.lsharp_pts, sb.flat_pts,
                      sb.lsharp_ring_start, sb.lflat_ring_start, sb.lflat_pts, h->status_word, h->pair_T, h->pair_seed, h->pair_last,

@@ -8,6 +8,7 @@
 #include <vector>
 #include "../../include/vlo.h"
 
+#define K0_TILE 1024          // raw points per CTA of the organise passes (k0_organise.cu)
 #define VLO_NTERM 28          // 21 upper-tri AtA + 6 AtB + sum of squared weighted residuals
 #define VLO_PI_D 3.14159265358979323846
 
@@ -55,6 +56,7 @@ struct ScanBatchDev {
     int   *first_half;        // [B]  first valid index with halfPassed condition
     float *ori_bounds;        // [B][2] startOri, endOri
     int   *tile_hist;         // [B][R][tiles]
+    int8_t *ring_of; float *ori_of;   // [B][N] ring id (-1 = dropped) and raw orientation per raw point (K0 pass 1 -> pass 3)
     float4 *cloud;            // [B][N] ring-major
     int   *ring_start;        // [B][R+1]
     int   *src_index;         // [B][N]
