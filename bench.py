@@ -128,6 +128,28 @@ def algorithmic_bytes(stage: str, counts, n_map_pts, iters_done, q_stack=None):
     return 0
 
 
+def bind_to_gpu_numa(local_rank: int):
+    """Pin this rank's threads to the CPUs next to its GPU before any pinned host memory is allocated (first touch puts
+    the staging buffers on the GPU's NUMA node): N ranks streaming scans over PCIe must not share one socket's memory."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        dev = "/sys/bus/pci/devices/%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        cpus = set()
+        for part in open(dev + "/local_cpulist").read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return open(dev + "/numa_node").read().strip()
+    except Exception:
+        return None
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -142,7 +164,10 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa(local_rank) if world > 1 else None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")               # NCCL's version banner goes to stdout: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     B = args.batch
@@ -174,10 +199,7 @@ def run_gpu(args):
             h.upload_raw(host.data_ptr(), offs, 4, False)
         h.organise()
         h.extract()
-        res = h.register_map(scans_idx, seeds)
-        if world > 1:
-            res = bag.gather_results(res)              # the one exchange step (result records only)
-        return res
+        return h.register_map(scans_idx, seeds)
 
     def barrier():
         torch.cuda.synchronize()
@@ -206,8 +228,15 @@ def run_gpu(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
+    all_res = []
     for _ in range(args.steps):
         res = step(True)
+        all_res.append(res)
+    if world > 1:
+        # the ONE exchange step of the whole job: every rank's result records, gathered once over NVLink (NCCL
+        # all_gather of (K * B) x 480-byte records); nothing collective happens per scan or per batch
+        gathered = bag.gather_results(np.concatenate(all_res))
+        assert len(gathered) == world * args.steps * B
     ev1.record(stream)
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
@@ -227,20 +256,25 @@ def run_gpu(args):
     def e2e_pass(n_steps):
         r = h.bag_register_map(one_step * n_steps, stride=4)
         if world > 1:
-            r = bag.gather_results(r)
+            bag.gather_results(r)                       # the job's single exchange step, inside the timed region
         return r
 
     e2e_pass(2)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record(stream)
-    res_e2e = e2e_pass(args.steps)
-    e1.record(stream)
-    barrier()
-    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
-    e2e_dev_ms = e0.elapsed_time(e1)
-    e2e_ms = max(e2e_wall_ms, e2e_dev_ms)
+    # three passes of K steps, the MEDIAN pass is reported (host-side PCIe / scheduling hiccups on a shared box make
+    # single passes noisy; every pass is listed in e2e.passes_ms_per_step)
+    e2e_passes = []
+    for _ in range(3):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        res_e2e = e2e_pass(args.steps)
+        e1.record(stream)
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        e2e_passes.append((max(wall, e0.elapsed_time(e1)), wall, e0.elapsed_time(e1)))
+    e2e_ms, e2e_wall_ms, e2e_dev_ms = sorted(e2e_passes)[1]
+    e2e_all = [p_[0] for p_ in e2e_passes]
     if not np.array_equal(res_e2e["transform"][:B].view(np.uint32), res["transform"][:B].view(np.uint32)):
         print("warning: streaming e2e results differ from the resident-batch results", file=sys.stderr)
     clocks.stop()
@@ -252,6 +286,13 @@ def run_gpu(args):
         from vil_sensor_fusion_b200 import synth
         cfg1 = api.default_config("HDL-64E", deskew=0, max_scans=2, max_points=131072, io_ratio=1,
                                   max_map_points=int(max(len(cm), len(sm))), device=local_rank)
+        # the caller's scan buffers are pinned (as a driver's DMA buffers would be): numpy views of pinned torch tensors
+        pinned_pool = []
+        for r in raws_pool:
+            tp = torch.empty(r.shape, dtype=torch.float32).pin_memory()
+            tp.numpy()[:] = r
+            pinned_pool.append(tp)
+        raws_lat = [tp.numpy() for tp in pinned_pool]
         with api.Handle(cfg1) as h1:
             h1.map_build(cm, sm)
             traj = synth.Trajectory()
@@ -263,7 +304,7 @@ def run_gpu(args):
                         h1.lib.vlo_online_reset(h1._h)
                         h1.online_set_map_pose(synth.loam_map_pose(traj.rotation(0.0), traj.position(0.0)).astype(np.float32))
                     t1 = time.perf_counter()
-                    h1.process_scan(raws_pool[k], 0.1 * k, want_map=True)
+                    h1.process_scan(raws_lat[k], 0.1 * k, want_map=True)
                     if rep > 0 and k > 0:
                         lat.append((time.perf_counter() - t1) * 1e3)
             lat.sort()
@@ -296,7 +337,7 @@ def run_gpu(args):
                 h2.online_set_map_pose(synth.loam_map_pose(traj.rotation(0.0), traj.position(0.0)).astype(np.float32))
                 for k in range(POOL):
                     t1 = time.perf_counter()
-                    h2.process_scan(raws_pool[k], 0.1 * k, want_map=True)
+                    h2.process_scan(raws_lat[k], 0.1 * k, want_map=True)
                     if rep > 0 and k > 0:
                         lat2.append((time.perf_counter() - t1) * 1e3)
             lat2.sort()
@@ -305,6 +346,10 @@ def run_gpu(args):
 
     # max over ranks
     if world > 1:
+        ta = torch.tensor(e2e_all, dtype=torch.float64, device="cuda")
+        dist.all_reduce(ta, op=dist.ReduceOp.MAX)      # a pass is as slow as its slowest rank
+        e2e_all = [float(v) for v in ta]
+        e2e_ms = sorted(e2e_all)[1]
         t = torch.tensor([dev_ms, e2e_ms, float(launches)], dtype=torch.float64, device="cuda")
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -359,15 +404,17 @@ def run_gpu(args):
                                    "+ D-opt gate", "scans_per_step_per_gpu": B, "points_per_scan": int(n_pts // B),
                        "map_points": int(n_map_pts), "parallelism": "frame-range dp%d" % world,
                        "l2": "inputs %.0f MB per step > 126 MB L2" % (h2d_bytes / 1e6), "mean_gn_iterations": round(mean_iters, 2),
-                       "pool": "%d distinct scans cycled" % POOL},
+                       "pool": "%d distinct scans cycled" % POOL, "exchange": "one all_gather of the result records per job" if world > 1 else "none",
+                       "numa_node": numa},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
-                    "ms_per_step": round(e2e_ms / args.steps, 4), "wall_ms": round(e2e_wall_ms, 3), "device_ms": round(e2e_dev_ms, 3)},
+                    "ms_per_step": round(e2e_ms / args.steps, 4), "wall_ms": round(e2e_wall_ms, 3), "device_ms": round(e2e_dev_ms, 3),
+                    "passes_ms_per_step": [round(v / args.steps, 4) for v in e2e_all], "reported": "median of 3 passes of K steps"},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "roofline": roofline,
             "stages": table,
             "latency": {"p50_ms_per_scan": None if p50 is None else round(p50, 4), "p95_ms_per_scan": None if p95 is None else round(p95, 4),
-                        "what": "vlo_process_scan: one online tick (H2D + organise + extract + scan-to-scan + scan-to-map + results D2H)",
+                        "what": "vlo_process_scan: one online tick (H2D from a pinned buffer + organise + extract + scan-to-scan + scan-to-map on every sweep (ioRatio 1) + results D2H)",
                         **extra_lat},
             "ok_registrations": ok, "mean_corr": [float(np.mean(res["n_corr_edge"])), float(np.mean(res["n_corr_plane"]))],
         }

@@ -6,7 +6,7 @@ from vil_sensor_fusion_b200 import api, synth
 scene = synth.scene_room(0); traj = synth.Trajectory()
 pool = [synth.make_scan(scene, "HDL-64E", t0=0.1 * k, traj=traj, rolling=False, noise_sigma=0.01, seed=k) for k in range(9)]
 cm, sm = synth.make_voxel_map(scene, 1000000, seed=1)
-cfg = api.default_config("HDL-64E", deskew=0, max_scans=2, max_points=131072, max_map_points=int(max(len(cm), len(sm))))
+cfg = api.default_config("HDL-64E", deskew=0, max_scans=2, max_points=131072, max_map_points=int(max(len(cm), len(sm))), io_ratio=1)
 with api.Handle(cfg) as h:
     h.map_build(cm, sm)
     h.online_set_map_pose(synth.loam_map_pose(traj.rotation(0.0), traj.position(0.0)).astype(np.float32))

@@ -94,7 +94,7 @@ extern "C" int vlo_create(const vlo_config *cfg, vlo_handle **out)
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || c.device >= ndev) return VLO_ERR_NO_DEVICE;
     if (cudaSetDevice(c.device) != cudaSuccess) return VLO_ERR_NO_DEVICE;
     vlo_handle *h = new vlo_handle();
-    h->cfg = c; h->launches = 0; h->pinned = nullptr; h->pinned_bytes = 0;
+    h->cfg = c; h->launches = 0; h->pinned = nullptr; h->pinned_bytes = 0; h->upload_pinned = nullptr;
     memset(&h->sb, 0, sizeof(h->sb)); memset(&h->lm, 0, sizeof(h->lm));
     memset(&h->gs_corner, 0, sizeof(GridSet)); memset(&h->gs_surf, 0, sizeof(GridSet)); memset(h->gs_map, 0, sizeof(h->gs_map));
     h->map_pts[0] = h->map_pts[1] = nullptr; h->map_n = nullptr; h->map_n_host[0] = h->map_n_host[1] = 0;
@@ -178,6 +178,7 @@ extern "C" void vlo_destroy(vlo_handle *h)
     vlo_lm_free(h);
     free_gridset(h->gs_corner); free_gridset(h->gs_surf); free_gridset(h->gs_map[0]); free_gridset(h->gs_map[1]);
     if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->upload_pinned) { cudaFreeHost(h->upload_pinned); cudaEventDestroy(h->upload_ev[0]); cudaEventDestroy(h->upload_ev[1]); }
     for (auto &e : h->prof_events) cudaEventDestroy(e);
     cudaStreamDestroy(h->stream);
     delete h;
@@ -228,19 +229,30 @@ extern "C" int vlo_scans_upload(vlo_handle *h, const float *raw, const int *offs
     cudaSetDevice(h->cfg.device);
     ScanBatchDev &sb = h->sb;
     size_t total = (size_t)(offsets[n_scans] - offsets[0]);
-    int rc = ensure_pinned(h, sizeof(int) * 2 * (size_t)h->cfg.max_scans); if (rc) return rc;
-    int *poff = (int *)h->pinned;
+    // offsets staging: two pinned halves used alternately, each guarded by an event, so that the call does not have to
+    // drain the stream before it returns (a device-resident batch is then enqueued without any host round trip)
+    const size_t half_bytes = sizeof(int) * 2 * (size_t)h->cfg.max_scans;
+    if (!h->upload_pinned) {
+        VLO_CUDA(cudaMallocHost((void **)&h->upload_pinned, half_bytes * 2));
+        for (int k = 0; k < 2; k++) VLO_CUDA(cudaEventCreateWithFlags(&h->upload_ev[k], cudaEventDisableTiming));
+        h->upload_parity = 0; h->upload_used[0] = h->upload_used[1] = 0;
+    }
+    const int par = h->upload_parity; h->upload_parity ^= 1;
+    if (h->upload_used[par]) VLO_CUDA(cudaEventSynchronize(h->upload_ev[par]));
+    int *poff = (int *)((char *)h->upload_pinned + half_bytes * par);
     for (int s = 0; s < n_scans; s++) { poff[2 * s] = offsets[s] - offsets[0]; poff[2 * s + 1] = offsets[s + 1] - offsets[s]; }
     VLO_CUDA(cudaMemcpyAsync(sb.raw_offset, poff, sizeof(int) * 2 * (size_t)n_scans, cudaMemcpyHostToDevice, h->stream));
+    VLO_CUDA(cudaEventRecord(h->upload_ev[par], h->stream));
+    h->upload_used[par] = 1;
     if (on_device) {
         sb.raw = raw + (size_t)offsets[0] * stride;
     } else {
         if (total * stride > (size_t)h->cfg.max_scans * h->cfg.max_points * 4) { h->err = "raw payload exceeds staging capacity (stride > 4?)"; return VLO_ERR_CAPACITY; }
         VLO_CUDA(cudaMemcpyAsync(sb.raw_owned, raw + (size_t)offsets[0] * stride, total * stride * sizeof(float), cudaMemcpyHostToDevice, h->stream));
         sb.raw = sb.raw_owned;
+        // the caller's buffer may be pageable or reused right after the call: the copy must have left it
+        VLO_CUDA(cudaStreamSynchronize(h->stream));
     }
-    // the offsets staging buffer is reused by the next call: make the copy complete first
-    VLO_CUDA(cudaStreamSynchronize(h->stream));
     sb.n_scans = n_scans; sb.stride = stride; sb.scan_first = 0; sb.scan_count = n_scans;
     sb.xyz_off[0] = 0; sb.xyz_off[1] = 1; sb.xyz_off[2] = 2;
     h->online_have_last = 0;

@@ -141,6 +141,7 @@ struct vlo_handle {
     int prof_enabled; std::vector<cudaEvent_t> prof_events; std::vector<int> prof_stage; size_t prof_used;
     // pinned staging
     void *pinned; size_t pinned_bytes;
+    void *upload_pinned; cudaEvent_t upload_ev[2]; int upload_parity, upload_used[2];   // vlo_scans_upload's offsets staging
     // online state
     int online_have_last; float online_T[6]; float online_sum[6]; float online_map_bef[6], online_map_aft[6];
     int online_slot; long long online_ticks;
