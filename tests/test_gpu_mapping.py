@@ -255,3 +255,48 @@ def test_map_insert_preload_and_capacity(orc):
         with pytest.raises(api.VloError) as e:
             h.map_insert(cm, sm, pose)
         assert e.value.code == -3
+
+
+def test_full_size_hdl64_against_1M_map(orc):
+    """BASELINE config 2 at full size: HDL-64-shaped scans against the 1M-point voxel map of the bench.  Two scans are
+    compared with the oracle bit for bit (kd-tree over the full map); all eight through size-independent properties:
+    convergence to ground truth from a perturbed seed, idempotence (restarting from the result moves the pose by less
+    than the convergence threshold) and batch-independence (a scan registered alone equals the same scan in a batch)."""
+    from vil_sensor_fusion_b200 import api, synth
+    scene = synth.scene_room(0)
+    traj = synth.Trajectory()
+    cm, sm = synth.make_voxel_map(scene, 1000000, seed=1)
+    assert len(cm) + len(sm) > 900000
+    n = 8
+    raws, gts = [], []
+    for k in range(n):
+        t = 0.1 * k
+        raws.append(synth.make_scan(scene, "HDL-64E", t0=t, traj=traj, rolling=False, noise_sigma=0.01, seed=k))
+        gts.append(synth.loam_map_pose(traj.rotation(t), traj.position(t)).astype(np.float32))
+    gts = np.stack(gts)
+    seeds = gts + np.array([0.006, -0.005, 0.004, 0.06, -0.04, 0.05], np.float32)
+    ocfg = orc.default_config("HDL-64E", deskew=0)
+    gcfg = api.default_config("HDL-64E", deskew=0, max_scans=n, max_points=131072, max_map_points=int(max(len(cm), len(sm))))
+    with api.Handle(gcfg) as h:
+        h.map_build(cm, sm)
+        h.upload(raws)
+        h.organise()
+        h.extract()
+        res = h.register_map(np.arange(n), seeds)
+        again = h.register_map(np.arange(n), res["transform"])
+        alone = h.register_map([3], [seeds[3]])[0]
+        stacks = [h.get_stack(k) for k in (0, 5)]
+    assert np.all(res["status"] == 0)
+    err = np.abs(res["transform"] - gts)
+    assert np.all(err[:, :3] < 2e-3) and np.all(err[:, 3:] < 2e-2), err.max(axis=0)
+    d = np.abs(again["transform"] - res["transform"])
+    assert np.all(d[:, :3] < np.deg2rad(0.05)) and np.all(d[:, 3:] < 0.05 / 100 * 2), d.max(axis=0)
+    assert np.all(again["iterations"] <= 2)
+    np.testing.assert_array_equal(alone["transform"].view(np.uint32), res["transform"][3].view(np.uint32))
+    np.testing.assert_array_equal(alone["hessian"].view(np.uint32), res["hessian"][3].view(np.uint32))
+    for (cq, sq), k in zip(stacks, (0, 5)):
+        ro = orc.mapping_register(ocfg, cq, sq, cm, sm, seeds[k], use_kdtree=True)
+        np.testing.assert_array_equal(res["transform"][k].view(np.uint32), ro["transform"].view(np.uint32))
+        np.testing.assert_array_equal(res["hessian"][k].view(np.uint32), ro["hessian"].view(np.uint32))
+        assert res["iterations"][k] == ro["iterations"]
+        np.testing.assert_allclose(res["eig"][k], ro["eig"], rtol=1e-4)
