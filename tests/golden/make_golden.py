@@ -72,6 +72,26 @@ def main():
     fct = orc.imu_get_factor(prm, t, acc, gyro, 0.0, 0.1000001)
     np.savez_compressed(os.path.join(OUT, "imu_testtest.npz"), t=t, acc=acc, gyro=gyro, dR=fct["dR"], dP=fct["dP"], dV=fct["dV"],
                         cov=fct["cov"], dt=fct["dt"], n=fct["n_integrated"], dP_dba=fct["dP_dba"], dV_dbg=fct["dV_dbg"])
+    # LaserMapping with its map maintenance: 4 ticks of a VLP-16 sequence (450 azimuth columns), each seeded with the
+    # previous mapped pose; the fixture keeps the inputs of tick 0 (to regenerate the others from the seed) and, per
+    # tick, pose / sizes / a checksum of the map
+    cfgl = orc.default_config("VLP-16", deskew=0)
+    lm = orc.LaserMap(cfgl, cap=100000)
+    seed_l = np.zeros(6, np.float32)
+    poses, infos, sums = [], [], []
+    for k in range(4):
+        raw = synth.make_scan(scene, "VLP-16", t0=0.1 * k, traj=traj, rolling=False, n_az=450)
+        c, rs, _ = orc.organise(cfgl, raw)
+        f = orc.extract(cfgl, c, rs)
+        r = lm.process(c[f["less_sharp_idx"]], f["less_flat"], seed_l)
+        seed_l = r["transform"]
+        poses.append(r["transform"])
+        infos.append(list(r["info"]["n_ds"]) + list(r["info"]["n_sub"]) + list(r["info"]["n_map"]) + [r["iterations"], r["status"]])
+        sums.append([float(lm.points(w)[0][:, :3].astype(np.float64).sum()) for w in range(2)])
+    pc, cc = lm.points(0)
+    np.savez_compressed(os.path.join(OUT, "vlp16_lasermap.npz"), poses=np.stack(poses), infos=np.array(infos), sums=np.array(sums),
+                        corner_map=pc, corner_cube=cc, surf_map_head=lm.points(1)[0][:256])
+    lm.close()
     print("golden fixtures written to", OUT)
 
 

@@ -246,3 +246,73 @@ def test_registration_recovers_motion(orc):
                               f0["less_flat_ring_start"], seed=gt0)
     assert r["status"] == 0 and not r["is_degenerate"]
     assert np.all(np.abs(r["transform"][:3] - gt1[:3]) < 1e-3) and np.all(np.abs(r["transform"][3:] - gt1[3:]) < 1e-2)
+
+
+def test_voxel_downsample_is_a_voxel_grid(orc):
+    """pcl::VoxelGrid restated (V1/V2): one output per occupied voxel, in order of first appearance, each the float64
+    centroid of its members to within the 2^-20 m quantisation; leaf <= 0 passes the cloud through."""
+    rng = np.random.default_rng(4)
+    pts = np.zeros((5000, 4), np.float32)
+    pts[:, :3] = rng.uniform(-20, 20, (5000, 3))
+    pts[:, 3] = rng.integers(0, 16, 5000) + rng.uniform(0, 0.09, 5000)
+    pts[100:200, :3] = pts[0:100, :3] + 1e-3          # guaranteed shared voxels
+    for leaf in (0.2, 0.4, 1.0):
+        out = orc.voxel_downsample(pts, leaf)
+        vox = np.floor(pts[:, :3].astype(np.float32) * np.float32(1.0 / leaf)).astype(np.int64)
+        keys, first, inv = np.unique(vox, axis=0, return_index=True, return_inverse=True)
+        order = np.argsort(first)                     # order of first appearance
+        assert len(out) == len(keys)
+        for rank, kidx in enumerate(order[:300]):
+            members = pts[inv.ravel() == kidx]
+            np.testing.assert_allclose(out[rank, :3], members[:, :3].astype(np.float64).mean(axis=0), atol=2e-6)
+            assert int(out[rank, 3]) == int(pts[first[kidx], 3])
+        assert np.all(np.floor(out[:, :3] * np.float32(1.0 / leaf)) == keys[order]) or leaf == 1.0
+    np.testing.assert_array_equal(orc.voxel_downsample(pts, 0.0), pts)
+
+
+def test_laser_map_maintenance_semantics(orc):
+    """oracle/laser_map.c, the frozen choices M1-M6: insertion creates one point per (cube, voxel) numbered by first
+    appearance; re-inserting the same cloud creates nothing and averages (c + p) / 2 = c; the FOV-valid sub-map leaves
+    out the cubes straight above / below the sensor; the window shift evicts cubes for good."""
+    from vil_sensor_fusion_b200 import synth
+    scene = synth.scene_room(0)
+    cm, sm = synth.sample_map_points(scene, 20000, seed=2)
+    cfg = orc.default_config("VLP-16", deskew=0)
+    ident = np.zeros(6, np.float32)
+    lm = orc.LaserMap(cfg, cap=50000)
+    lm.insert(cm, sm, ident)
+    n0 = (lm.size(0), lm.size(1))
+    p0, c0 = lm.points(1)
+    # one point per voxel, every centroid inside the voxel it was created for
+    vox = np.floor(p0[:, :3] * np.float32(1.0 / 0.4)).astype(np.int64)
+    assert len(np.unique(np.concatenate([vox, c0[:, None].astype(np.int64)], axis=1), axis=0)) == len(p0)
+    # creation order = first appearance of the voxel in the inserted cloud
+    vin = np.floor(sm[:, :3] * np.float32(1.0 / 0.4)).astype(np.int64)
+    _, first = np.unique(vin, axis=0, return_index=True)
+    np.testing.assert_array_equal(np.floor(sm[np.sort(first), :3] * np.float32(2.5)).astype(np.int64)[:200], vox[:200])
+    lm.insert(cm, sm, ident)
+    assert (lm.size(0), lm.size(1)) == n0
+    lm.insert(p0, p0[:0], ident)                      # nothing new from the corner side either
+    p1, _ = lm.points(1)
+    assert np.abs(p1[:, :3] - p0[:, :3]).max() < 0.2   # centroids moved inside their voxels only
+    # FOV test: sensor level at the origin -> the cube column straight above and below fails, the ring around passes
+    centre, mask = lm.select(ident)
+    nb = cfg.n_neighbor_cubes
+    assert mask[nb, nb, nb + 1] == 1 and mask[nb, nb + 1, nb] == 1       # (k, j, i) order: neighbours in z and in x
+    assert mask[nb, nb + 3, nb] == 0 and mask[nb, nb - 3, nb] == 0       # 3 cubes straight up / down (LOAM y is up)
+    lm.close()
+    # window shift: 7^3 cubes of 4 m; moving 3 cubes along x shifts the window and evicts the far cubes
+    small = orc.default_config("VLP-16", deskew=0, map_cube_size=4.0, n_neighbor_cubes=1)
+    for a in range(3):
+        small.map_dims[a] = 7
+        small.map_start_cubes[a] = 3
+    lm = orc.LaserMap(small, cap=50000)
+    lm.insert(cm, sm, ident)
+    before = lm.points(1)[1]
+    assert not np.any(before & (1 << 30))
+    far = np.array([0, 0, 0, 12.5, 0, 0], np.float32)
+    lm.select(far)
+    after = lm.points(1)[1]
+    assert np.array_equal(lm.window(), [2, 3, 3]) or lm.window()[0] < 3
+    assert np.any(after & (1 << 30)) and np.count_nonzero(after & (1 << 30)) < len(after)
+    lm.close()

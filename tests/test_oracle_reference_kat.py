@@ -122,3 +122,32 @@ def test_golden_imu_testtest_sequence(orc):
     cov = f["cov"]
     np.testing.assert_allclose(cov, cov.T, rtol=1e-12, atol=1e-20)
     assert np.all(np.linalg.eigvalsh(cov) > 0)
+
+
+def test_golden_vlp16_lasermap(orc):
+    """Regression golden of the LaserMapping map side (oracle/laser_map.c): 4 chained ticks reproduce the stored
+    poses, stack / sub-map / map sizes and map contents bit for bit."""
+    import os
+    from vil_sensor_fusion_b200 import synth
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "vlp16_lasermap.npz"))
+    scene = synth.scene_room(0)
+    traj = synth.Trajectory()
+    cfg = orc.default_config("VLP-16", deskew=0)
+    lm = orc.LaserMap(cfg, cap=100000)
+    seed = np.zeros(6, np.float32)
+    for k in range(4):
+        raw = synth.make_scan(scene, "VLP-16", t0=0.1 * k, traj=traj, rolling=False, n_az=450)
+        c, rs, _ = orc.organise(cfg, raw)
+        f = orc.extract(cfg, c, rs)
+        r = lm.process(c[f["less_sharp_idx"]], f["less_flat"], seed)
+        seed = r["transform"]
+        np.testing.assert_array_equal(r["transform"].view(np.uint32), g["poses"][k].view(np.uint32), err_msg="tick %d" % k)
+        info = list(r["info"]["n_ds"]) + list(r["info"]["n_sub"]) + list(r["info"]["n_map"]) + [r["iterations"], r["status"]]
+        np.testing.assert_array_equal(info, g["infos"][k])
+        sums = [float(lm.points(w)[0][:, :3].astype(np.float64).sum()) for w in range(2)]
+        np.testing.assert_array_equal(sums, g["sums"][k])
+    pc, cc = lm.points(0)
+    np.testing.assert_array_equal(pc.view(np.uint32), g["corner_map"].view(np.uint32))
+    np.testing.assert_array_equal(cc, g["corner_cube"])
+    np.testing.assert_array_equal(lm.points(1)[0][:256].view(np.uint32), g["surf_map_head"].view(np.uint32))
+    lm.close()
