@@ -102,3 +102,26 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt and "vlo_oracle.h" not in txt, f
+
+
+def test_ros_shim_compiles_against_mock_headers_and_links(tmp_path):
+    """the `loam`-compatible node (integration/ros/vlo_loam_node.cpp, the code INTEGRATION.md shows) is
+    compiled against the mock ROS headers under integration/mock and linked with libvlo.so, so every ABI call it makes
+    exists with that signature."""
+    import re
+    import subprocess
+    from vil_sensor_fusion_b200 import build
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "integration", "ros", "vlo_loam_node.cpp")
+    obj = str(tmp_path / "vlo_loam_node.o")
+    exe = str(tmp_path / "vlo_loam_node")
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror=implicit-function-declaration", "-I", os.path.join(root, "integration", "mock"),
+                        "-I", os.path.join(root, "include"), "-c", src, "-o", obj], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    libdir = os.path.dirname(build.lib_path())
+    r = subprocess.run(["g++", "-o", exe, obj, "-L", libdir, "-lvlo", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # the document shows the same code
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = re.search(r"```cpp\n(// vlo_loam_node\.cpp.*?)```", doc, re.S).group(1)
+    assert block.strip() in open(src).read()
