@@ -88,3 +88,25 @@ def test_bag_capacity_errors():
         with pytest.raises(api.VloError) as e:            # no map resident in this handle
             h.bag_register_map([(raw[: offs[1]], offs[:2], np.zeros((1, 6), np.float32))])
         assert e.value.code == -5
+
+
+def test_reprocess_pairs_from_a_ros_bag(tmp_path):
+    """A bag of PointCloud2 sweeps (5 floats per point, read without ROS) reprocessed from the file equals the same
+    sweeps handed over as arrays."""
+    from vil_sensor_fusion_b200 import api, bag, rosbag_io as rb
+    raws = [scenes.vlp16_scan(0.1 * k, rolling=False) for k in range(5)]
+    msgs = []
+    for k, r in enumerate(raws):
+        c5 = np.concatenate([r, np.full((len(r), 1), 7.0, np.float32)], axis=1)
+        msgs.append(("/lidar", "sensor_msgs/PointCloud2", rb.POINTCLOUD2_MD5, 100.0 + 0.1 * k,
+                     rb.make_pointcloud2(c5, 100.0 + 0.1 * k, field_names=("x", "y", "z", "intensity", "ring"), seq=k)))
+    path = str(tmp_path / "sweeps.bag")
+    rb.write_bag(path, msgs, compression="bz2", chunk_messages=2)
+    gcfg = api.default_config("VLP-16", deskew=0, max_scans=4, max_points=32768 + 8192)
+    with api.Handle(gcfg) as h:
+        res_bag, stamps = bag.reprocess_pairs_from_bag(h, path, "/lidar", batch=3)
+        res_arr = bag.reprocess_pairs(h, lambda k: raws[k], 0, 5, batch=3)
+    assert len(res_bag) == 4 and np.all(res_bag["status"] == 0)
+    np.testing.assert_allclose(stamps, 100.0 + 0.1 * np.arange(5), atol=1e-9)
+    np.testing.assert_array_equal(res_bag["transform"].view(np.uint32), res_arr["transform"].view(np.uint32))
+    np.testing.assert_array_equal(res_bag["hessian"].view(np.uint32), res_arr["hessian"].view(np.uint32))

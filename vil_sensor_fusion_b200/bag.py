@@ -48,6 +48,28 @@ def reprocess_map(h: Handle, get_scan, first: int, last: int, batch: int, seeds)
     return np.concatenate(out) if out else np.zeros(0, RESULT_DTYPE)
 
 
+def reprocess_pairs_from_bag(h: Handle, path: str, cloud_topic: str = "/lidar", first: int = 0, last: int | None = None,
+                             batch: int = 64) -> tuple[np.ndarray, np.ndarray]:
+    """Scan-to-scan registration of the consecutive PointCloud2 messages [first, last) of a ROS bag (v2.0, read by
+    rosbag_io without ROS; payloads go to the device as they are, x / y / z picked by their field offsets).
+    Returns (results for the pairs (k, k+1), message stamps of frames first .. last-1)."""
+    from . import rosbag_io
+    clouds, _ = rosbag_io.load_bag(path, cloud_topic)
+    last = len(clouds) if last is None else min(last, len(clouds))
+    out = []
+    k = first
+    while k < last - 1:
+        hi = min(last, k + batch)
+        h.upload_pointcloud2(clouds[k:hi])
+        h.organise()
+        h.extract()
+        n = hi - k
+        out.append(h.register_pairs(np.arange(n - 1), np.arange(1, n)))
+        k = hi - 1
+    stamps = np.array([c["stamp"] for c in clouds[first:last]])
+    return (np.concatenate(out) if out else np.zeros(0, RESULT_DTYPE)), stamps
+
+
 def gather_results(local: np.ndarray, group=None, device=None) -> np.ndarray:
     """The single exchange step: all ranks contribute their result records, every rank receives the
     concatenation in rank (= frame) order.  Works on NCCL (device tensors over NVLink) and gloo (CPU)."""
