@@ -434,6 +434,16 @@ __global__ void __launch_bounds__(K1_THREADS) k1c_lessflat(K1Params p)
     if (n <= 2 * K + 1 || n > p.MR) return;              // k1_extract left lflat_cnt = 0 for these rings
     const size_t gbase = (size_t)b * p.N + start;
     K1cSmem s = k1c_carve(k1_smem_raw, p.HT);
+    float4 v[MAXP]; int so[MAXP];
+    // all of the thread's points and labels are requested up front (independent loads in flight together); they land
+    // while the hash table is being cleared, and the insertions below run without waiting on global memory
+    int8_t lab[MAXP];
+    #pragma unroll
+    for (int k = 0; k < MAXP; k++) {
+        const int i = k * K1_THREADS + tid;
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f); lab[k] = 1;
+        if (i < n) { v[k] = p.cloud[gbase + i]; lab[k] = p.label[gbase + i]; }
+    }
     for (int k = tid; k < p.HT; k += K1_THREADS) {
         s.vkey[k] = K1_EMPTY; s.vfirst[k] = 0x7fffffff; s.vcnt[k] = 0; s.vsx[k] = 0; s.vsy[k] = 0; s.vsz[k] = 0; s.vsw[k] = 0;
     }
@@ -442,21 +452,18 @@ __global__ void __launch_bounds__(K1_THREADS) k1c_lessflat(K1Params p)
     const int lo_all = s_sp[0], hi_all = s_ep[NR - 1];
     const bool all_valid = s_all_valid != 0;
     const float leaf = p.leaf, inv = 1.0f / p.leaf;
-    float4 v[MAXP]; int so[MAXP];
     #pragma unroll
     for (int k = 0; k < MAXP; k++) {
         const int i = k * K1_THREADS + tid;
         so[k] = -1;
-        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < n) {
             bool in = false;
             if (i >= lo_all && i <= hi_all) {
                 in = all_valid;
                 if (!all_valid) for (int j = 0; j < NR; j++) in |= (s_ep[j] > s_sp[j] && i >= s_sp[j] && i <= s_ep[j]);
             }
-            if (in && p.label[gbase + i] <= 0) {
-                const float4 q = p.cloud[gbase + i];
-                v[k] = q;
+            if (in && lab[k] <= 0) {
+                const float4 q = v[k];
                 const int ix = (int)floorf(q.x * inv), iy = (int)floorf(q.y * inv), iz = (int)floorf(q.z * inv);
                 const unsigned long long key = ((unsigned long long)(unsigned)(ix + (1 << 20)) << 42)
                                              | ((unsigned long long)(unsigned)(iy + (1 << 20)) << 21)
