@@ -8,7 +8,7 @@
 #include <vector>
 #include "../../include/vlo.h"
 
-#define K0_TILE 1024          // raw points per CTA of the organise passes (k0_organise.cu)
+#define K0_TILE 512           // raw points per CTA of the organise passes (k0_organise.cu)
 #define VLO_NTERM 28          // 21 upper-tri AtA + 6 AtB + sum of squared weighted residuals
 #define VLO_PI_D 3.14159265358979323846
 
