@@ -117,12 +117,13 @@ def algorithmic_bytes(stage: str, counts, n_map_pts, iters_done, q_stack=None):
         return nv * 21 + 4 * nfeat                           # 16 in + 4 curvature + 1 label, + index lists
     if stage == "k1b_compact":
         return 2 * 20 * sum(c["n_sharp"] + c["n_less_sharp"] + c["n_flat"] for c in counts)
-    if stage == "k5_assoc_lin":
-        # fused association + linearisation, one Gauss-Newton iteration: map read once + query in + 5 neighbour
-        # indices out + level-1 sums out (the 5 x 16 B neighbour gather of SURVEY 8d's 116 B/query stays on chip)
-        return n_map_pts * 16 + q * (16 + 5 * 4) + (q // 32 + 1) * 28 * 4
-    if stage == "k5_solve":
-        return (q // 32 + 1) * 28 * 4
+    if stage == "k5_assoc":
+        # association, one Gauss-Newton iteration: map read once + query in + 5 neighbour indices out
+        return n_map_pts * 16 + q * (16 + 5 * 4)
+    if stage == "k5_lin":
+        # linearisation, one Gauss-Newton iteration (116 B per query = point + 5 indices + 5 gathered
+        # neighbours) + level-1 sums out and read back by the slot's solving warp
+        return q * (16 + 5 * 4 + 5 * 16) + 2 * (q // 32 + 1) * 28 * 4
     if stage == "k7_stack_ds":
         return q_in * 16 + q * 16                            # stacks in, voxel centroids out
     return 0
@@ -280,6 +281,23 @@ def run_gpu(args):
     if not np.array_equal(res_e2e["transform"][:B].view(np.uint32), res["transform"][:B].view(np.uint32)):
         print("warning: streaming e2e results differ from the resident-batch results", file=sys.stderr)
     clocks.stop()
+    # what bounds e2e: the same pinned buffer copied host -> device on its own (plain cudaMemcpyAsync, nothing else
+    # running) -- the PCIe rate of this box.  e2e.frac_of_pcie = (h2d bytes per step / e2e time per step) / that rate.
+    pcie_gbs = None
+    try:
+        best = None
+        for _ in range(4):
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            c0.record()
+            dev.copy_(host, non_blocking=True)
+            c1.record()
+            torch.cuda.synchronize()
+            t_ms = c0.elapsed_time(c1)
+            best = t_ms if best is None else min(best, t_ms)
+        pcie_gbs = h2d_bytes / (best * 1e-3) / 1e9
+    except Exception:
+        pass
 
     # ---- whole-bag scan-to-scan leg (BASELINE config 5 shape): independent registrations of consecutive
     # sweep pairs from a zero seed + degeneracy; sweeps in ping-pong order (0 1 .. 7 6 .. 0 1 ..) so that neighbours in
@@ -438,7 +456,7 @@ def run_gpu(args):
                 continue
             # k5_* launch max_iter times but only the first `iterations` do work: average over working launches
             working = n
-            if name in ("k5_assoc_lin", "k5_solve"):
+            if name in ("k5_assoc", "k5_lin"):
                 # max_iter launches per call, only the first `iterations` do work: average over the working launches
                 working = max(1, int(round(args.steps * min(mean_iters, cfg.map_max_iterations))))
             avg_ms = ms / working
@@ -469,7 +487,11 @@ def run_gpu(args):
                        "numa_node": numa},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                     "ms_per_step": round(e2e_ms / args.steps, 4), "wall_ms": round(e2e_wall_ms, 3), "device_ms": round(e2e_dev_ms, 3),
-                    "passes_ms_per_step": [round(v / args.steps, 4) for v in e2e_all], "reported": "median of 3 passes of K steps"},
+                    "passes_ms_per_step": [round(v / args.steps, 4) for v in e2e_all], "reported": "median of 3 passes of K steps",
+                    "pcie_h2d_gbs_measured": None if pcie_gbs is None else round(pcie_gbs, 2),
+                    "h2d_gbs_achieved": round(h2d_bytes / (e2e_ms / args.steps * 1e-3) / 1e9, 2),
+                    "frac_of_pcie": None if not pcie_gbs else round(h2d_bytes / (e2e_ms / args.steps * 1e-3) / 1e9 / pcie_gbs, 4),
+                    "bound": "PCIe host->device copy of the 16 B/point PointCloud2 payload (kernels overlap it)"},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "roofline": roofline,

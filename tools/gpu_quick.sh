@@ -7,7 +7,7 @@ timeout 900 python bench.py --no-cpu-baseline "$@" > $OUT/bench.json 2> $OUT/ben
 python - <<PY
 import json
 d=json.load(open("$OUT/bench.json"))
-print("value %.1f scans/s  e2e %.1f  ms/step %.3f  launches %d  lat p50 %s p95 %s" % (d["value"], d["e2e"]["value"], d["ms_per_step"], d["gpu_launches"], d["latency"]["p50_ms_per_scan"], d["latency"]["p95_ms_per_scan"]))
+print("value %.1f scans/s  e2e %.1f (pcie %s GB/s, frac %s)  ms/step %.3f  launches %d  lat p50 %s p95 %s" % (d["value"], d["e2e"]["value"], d["e2e"].get("pcie_h2d_gbs_measured"), d["e2e"].get("frac_of_pcie"), d["ms_per_step"], d["gpu_launches"], d["latency"]["p50_ms_per_scan"], d["latency"]["p95_ms_per_scan"]))
 for k,v in d["stages"].items(): print("  %-12s total %8.3f ms  avg %8.4f ms  %7.1f GB/s  frac %.4f" % (k, v["ms_total"], v["avg_ms"], v["achieved_gbs"], v["frac"]))
 print("  iters", d["config"]["mean_gn_iterations"], "corr", d["mean_corr"], "ok", d["ok_registrations"])
 PY

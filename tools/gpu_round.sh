@@ -18,8 +18,8 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --
     python bench.py --steps 1 --warmup 3 --batch 128 --no-cpu-baseline --no-latency > $OUT/bench_under_ncu.log 2>&1
 python tools/launch_shares.py $OUT/launches.csv | tee $OUT/launch_shares.txt
 echo "== ncu full captures"
-for K in k5_assoc_lin k1_extract k1c_lessflat k0_scatter; do
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:^$K\$ -s 2 -c 1 -f -o $OUT/full_$K \
+for K in k5_assoc k5_lin k1_extract k1c_lessflat k0_scatter; do
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:^$K -s 2 -c 1 -f -o $OUT/full_$K \
       python bench.py --steps 1 --warmup 3 --batch 128 --no-cpu-baseline --no-latency > $OUT/ncu_$K.log 2>&1
   ls -la $OUT/full_$K.ncu-rep
 done

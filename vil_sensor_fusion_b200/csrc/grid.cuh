@@ -275,6 +275,91 @@ __device__ __forceinline__ void grid_search_thread(const GridSet &gs, int g, flo
     }
 }
 
+// rho == 1 specialisation (the scan-to-map case: d2 < 1 on ~1 m cells).  The nested walk above makes a warp step
+// through the UNION of the cells its lanes visit (ncu r01c: 13.6 of 32 lanes active on average); here every lane keeps
+// its own 27-bit work mask and pops its own next cell, so the warp iterates max-over-lanes(non-empty cells) times.
+//   1. own cell (all lanes together): gives a k-th distance that is already nearly final
+//   2. one unrolled pass marks the neighbour cells whose box can still hold a closer point
+//   3. pop loop: next marked cell in nearest-first order, re-test against the current k-th distance, hash probe;
+//      pruned / absent / empty cells are skipped inside the pop, the candidate loop runs only on populated cells
+// Bit c of the mask is cell (ex, ey, ez), e = 0 own / 1 neighbour on the nearer side / 2 on the farther side, packed
+// two bits per cell in G27_E*; order = (far sides, non-zero offsets) ascending.  Same exactness contract as above: a
+// cell is skipped only when its box lower bound exceeds the k-th best, so the result is the exact (d2, tie) top-K.
+#define G27_EX 0x268a5849824504ull
+#define G27_EY 0x29a26522485110ull
+#define G27_EZ 0x2a689694205440ull
+
+__device__ __forceinline__ float grid_sel3(float a1, float a2, int e) { return e == 0 ? 0.0f : (e == 1 ? a1 : a2); }
+
+template <typename Top, typename Filter>
+__device__ __forceinline__ void grid_scan_range(const float4 *sorted, int j0, int j1, float qx, float qy, float qz, float dmax,
+                                                const Filter &flt, Top &best)
+{
+    // four candidates per round, their loads issued together (the r01c profile had 14 % of the stall samples on the
+    // one-load-per-iteration dependency); indices past the end are clamped to the last point and not inserted
+    for (int j = j0; j < j1; j += 4) {
+        float4 p[4];
+        #pragma unroll
+        for (int u = 0; u < 4; u++) p[u] = sorted[min(j + u, j1 - 1)];
+        #pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const float ddx = p[u].x - qx, ddy = p[u].y - qy, ddz = p[u].z - qz;
+            const float d2 = (ddx * ddx + ddy * ddy) + ddz * ddz;
+            unsigned tie; const unsigned tag = __float_as_uint(p[u].w);
+            if (j + u < j1 && d2 < dmax && flt(tag, tie))
+                best.insert(((unsigned long long)__float_as_uint(d2) << 32) | tie, tag);
+        }
+    }
+}
+
+template <typename Top, typename Filter>
+__device__ __forceinline__ void grid_search_thread27(const GridSet &gs, int g, float qx, float qy, float qz, float dmax,
+                                                     const Filter &flt, Top &best, float bound = -1.0f)
+{
+    const int *start = gs.start + (size_t)g * (gs.ts + 1);
+    const float4 *sorted = gs.sorted + (size_t)g * gs.max_pts;
+    const float cell = gs.cell, slack = 1e-3f * gs.cell;
+    const float fx = qx * gs.inv_cell, fy = qy * gs.inv_cell, fz = qz * gs.inv_cell;
+    const int cx = (int)floorf(fx), cy = (int)floorf(fy), cz = (int)floorf(fz);
+    const int sx = (fx - (float)cx >= 0.5f) ? 1 : -1, sy = (fy - (float)cy >= 0.5f) ? 1 : -1, sz = (fz - (float)cz >= 0.5f) ? 1 : -1;
+    best.init((bound >= 0.0f && bound < dmax) ? bound : dmax);
+    // squared per-axis lower bounds of the nearer ([1]) and farther ([2]) neighbour cell; [0] (own cell) is 0
+    float lx[3], ly[3], lz[3];
+    lx[0] = 0.0f; ly[0] = 0.0f; lz[0] = 0.0f;
+    { float a = grid_axis_lb(sx, cx, qx, cell, slack), b = grid_axis_lb(-sx, cx, qx, cell, slack); lx[1] = a * a; lx[2] = b * b; }
+    { float a = grid_axis_lb(sy, cy, qy, cell, slack), b = grid_axis_lb(-sy, cy, qy, cell, slack); ly[1] = a * a; ly[2] = b * b; }
+    { float a = grid_axis_lb(sz, cz, qz, cell, slack), b = grid_axis_lb(-sz, cz, qz, cell, slack); lz[1] = a * a; lz[2] = b * b; }
+    // one loop body serves the own cell (bit 0, popped by every lane in the first round) and the neighbours: the
+    // mask of neighbour cells is built right after the own cell has been scanned (single copy of the scan code --
+    // the kernel's instruction footprint matters: ncu showed no_instruction stalls with 150 KB of SASS)
+    unsigned mask = 1u;
+    bool own = true;
+    while (mask) {
+        int j0 = 0, j1 = 0;
+        do {
+            const int c = __ffs(mask) - 1;
+            mask &= mask - 1u;
+            const int ex = (int)(unsigned)(G27_EX >> (2 * c)) & 3, ey = (int)(unsigned)(G27_EY >> (2 * c)) & 3, ez = (int)(unsigned)(G27_EZ >> (2 * c)) & 3;
+            const float l2 = grid_sel3(lx[1], lx[2], ex) + (grid_sel3(ly[1], ly[2], ey) + grid_sel3(lz[1], lz[2], ez));
+            if (l2 > best.kth()) continue;
+            const int ox = ex == 0 ? 0 : (ex == 1 ? sx : -sx), oy = ey == 0 ? 0 : (ey == 1 ? sy : -sy), oz = ez == 0 ? 0 : (ez == 1 ? sz : -sz);
+            const int slot = grid_find(gs, g, cx + ox, cy + oy, cz + oz);
+            if (slot < 0) continue;
+            j0 = start[slot]; j1 = start[slot + 1];
+        } while (j1 == j0 && mask);
+        grid_scan_range(sorted, j0, j1, qx, qy, qz, dmax, flt, best);
+        if (own) {
+            own = false;
+            const float kth = best.kth();
+            #pragma unroll
+            for (int c = 1; c < 27; c++) {
+                const int ex = (int)((G27_EX >> (2 * c)) & 3ull), ey = (int)((G27_EY >> (2 * c)) & 3ull), ez = (int)((G27_EZ >> (2 * c)) & 3ull);
+                if (!(lx[ex] + (ly[ey] + lz[ez]) > kth)) mask |= 1u << c;
+            }
+        }
+    }
+}
+
 // cells per axis side the thread search must cover so that no point with d2 < dmax is missed
 static inline int grid_thread_rho(float cell, float dmax)
 {

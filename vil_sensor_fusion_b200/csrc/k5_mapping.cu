@@ -23,7 +23,7 @@ struct MapParams {
     int *idx5; int qcap;         // [n][qcap][5]
     float *partials; int pcap;   // [n][pcap][28] level-1 sums
     int *ncorr;                  // [n][2]
-    int *done;                   // [n] CTAs of the slot that finished their tiles (k5_assoc_lin)
+    int *done;                   // completion counters, convergence stamps, converged count, tile tickets (layout: see k5_build_list)
     GridSet gm0, gm1; int rho0, rho1; const float4 *map0, *map1; const int *map_n;
     int max_iter; float degen_thr, dT_abort, dR_abort, rot_thr, trans_thr;
 };
@@ -193,6 +193,11 @@ __device__ inline bool map_plane_coeff(float4 sel, const float4 *nb, float *coef
 // order) through a per-warp shared-memory transpose.  From the second iteration on, the previous
 // iteration's neighbours (still in idx5) seen from the new pose bound the 5th-neighbour distance, so the
 // cell walk starts with a tight pruning radius.
+// MODE 0: association + linearisation fused (the cooperative online-tick kernel); MODE 1: association only (writes idx5);
+// MODE 2: linearisation only (reads idx5).  The batch path runs 1 and 2 as separate kernels: each then has a small
+// instruction footprint and register budget (the fused kernel was 150 KB of SASS at 20 warps per SM and stalled on
+// instruction fetch as soon as its warps ran out of step); the arithmetic is the same, statement for statement.
+template <int MODE>
 __device__ __forceinline__ void k5_tile(const MapParams &p, int k, int tile, int it, float *wterms, int lane)
 {
     const int scan = p.scans[k];
@@ -218,26 +223,39 @@ __device__ __forceinline__ void k5_tile(const MapParams &p, int k, int tile, int
         const float4 sel = to_map(T, trig, ori);
         const float4 *map = corner ? p.map0 : p.map1;
         int *o = p.idx5 + ((size_t)k * p.qcap + i) * 5;
-        float bound = -1.0f;
-        if (it > 0 && o[4] >= 0) {
-            bound = 0.0f;
-            #pragma unroll
-            for (int j = 0; j < 5; j++) {
-                const float4 m = map[o[j]];
-                const float ddx = m.x - sel.x, ddy = m.y - sel.y, ddz = m.z - sel.z;
-                bound = fmaxf(bound, (ddx * ddx + ddy * ddy) + ddz * ddz);
+        bool ok;
+        int nbi[5];
+        if constexpr (MODE != 2) {
+            float bound = -1.0f;
+            if (it > 0 && o[4] >= 0) {
+                bound = 0.0f;
+                #pragma unroll
+                for (int j = 0; j < 5; j++) {
+                    const float4 m = map[o[j]];
+                    const float ddx = m.x - sel.x, ddy = m.y - sel.y, ddz = m.z - sel.z;
+                    bound = fmaxf(bound, (ddx * ddx + ddy * ddy) + ddz * ddz);
+                }
             }
+            TopKI<5> best;
+            // one search call for both clouds (per-lane grid descriptor): a second inlined copy of the search doubled
+            // the hot loop's instruction footprint
+            GridSet gm = corner ? p.gm0 : p.gm1;
+            const int rho = corner ? p.rho0 : p.rho1;
+            if (rho == 1) grid_search_thread27(gm, 0, sel.x, sel.y, sel.z, 1.0f, FilterAll(), best, bound);
+            else grid_search_thread(gm, 0, sel.x, sel.y, sel.z, 1.0f, rho, FilterAll(), best, bound);
+            ok = best.valid(4);
+            #pragma unroll
+            for (int j = 0; j < 5; j++) { nbi[j] = ok ? best.index(j) : -1; o[j] = nbi[j]; }
+        } else {
+            #pragma unroll
+            for (int j = 0; j < 5; j++) nbi[j] = o[j];
+            ok = nbi[4] >= 0;
         }
-        TopKI<5> best;
-        if (corner) grid_search_thread(p.gm0, 0, sel.x, sel.y, sel.z, 1.0f, p.rho0, FilterAll(), best, bound);
-        else        grid_search_thread(p.gm1, 0, sel.x, sel.y, sel.z, 1.0f, p.rho1, FilterAll(), best, bound);
-        const bool ok = best.valid(4);
-        #pragma unroll
-        for (int j = 0; j < 5; j++) o[j] = ok ? best.index(j) : -1;
+        if constexpr (MODE == 1) return;
         if (ok) {
             float4 nb[5];
             #pragma unroll
-            for (int j = 0; j < 5; j++) nb[j] = map[best.index(j)];
+            for (int j = 0; j < 5; j++) nb[j] = map[nbi[j]];
             float coeff[4];
             bool keep = corner ? map_edge_coeff(sel, nb, coeff) : map_plane_coeff(sel, nb, coeff);
             if (keep) {
@@ -266,6 +284,7 @@ __device__ __forceinline__ void k5_tile(const MapParams &p, int k, int tile, int
             }
         }
     }
+    if constexpr (MODE == 1) return;
     __syncwarp();                       // the previous tile's column sums are done with wterms
     #pragma unroll
     for (int e = 0; e < VLO_NTERM; e++) wterms[lane * LSTRIDE + e] = t[e];
@@ -350,30 +369,177 @@ __device__ __forceinline__ void k5_solve_slot(const MapParams &p, int k, int it,
 // slots still use the whole machine.
 namespace cg = cooperative_groups;
 
-// Throughput path (large batches): one launch per phase and iteration, converged slots exit at once.  Measured on
-// B200 with 128 scans per batch this beats the single cooperative launch by 10 % (dynamic CTA scheduling balances
-// the 3x spread in per-query cost; empty launches after convergence cost 8 us each).
-__global__ void __launch_bounds__(KNN_THREADS, 5) k5_assoc_lin(MapParams p, int it)
+// Throughput path (large batches): one launch per Gauss-Newton iteration over ONE flat list of the warp tiles of
+// all unconverged slots.  ncu r01c of the previous (slot, CTA-strided) launch shape: every warp owned a single tile,
+// per-tile cost varies 3x, and warps sat at the CTA's closing barrier for 11 % of the stall samples with 30 % of the
+// warp slots occupied.  Here
+//   * every CTA rebuilds the same compacted list (slot, tile prefix) from the convergence stamps,
+//   * a warp takes its first tile by position and every further one by global ticket (drawn before the current tile
+//     is worked on), so no warp idles while tiles are left anywhere in the batch,
+//   * the warp that completes a slot's last tile (per-slot completion counter) closes R1 levels 2/3, solves, tests
+//     degeneracy and updates the pose of that slot on its own -- a warp-level solve, no CTA barrier anywhere.
+// Convergence is a stamp (iteration at which the slot converged) rather than a flag: a slot solved early in launch
+// `it` must stay in the list of CTAs that start later in the same launch, or their ticket numbering would differ.
+struct SolveWarpSmem { GnScratch S; float l2[8 * VLO_NTERM]; };
+#define K5_NOT_CONVERGED 0x7fffffff
+
+__device__ __noinline__ void k5_solve_slot_warp(const MapParams &p, int k, int it, SolveWarpSmem &M, int lane, int n)
 {
-    __shared__ float terms[AL_WARPS][32 * LSTRIDE];
-    __shared__ SolveSmem M;
-    __shared__ int s_last;
-    const int k = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // state is written only by the slot's LAST CTA (below), after every CTA of the slot has passed this read
-    if (p.state[k * 4 + 0]) return;
+    GnScratch &S = M.S;
+    int *state = p.state + k * 4;
     const int scan = p.scans[k];
-    const int n_tiles = (p.counts[scan * 8 + 2] + p.counts[scan * 8 + 4] + 31) >> 5;
-    if (p.map_n[2] > 10 && p.map_n[4] > 100)
-        for (int tile = blockIdx.x * AL_WARPS + warp; tile < n_tiles; tile += gridDim.x * AL_WARPS)
-            k5_tile(p, k, tile, it, terms[warp], lane);
-    // the CTA that finishes last solves the slot: no second launch, no idle tail between the two phases
+    vlo_result *res = p.result + k;
+    const int q_total = p.counts[scan * 8 + 2] + p.counts[scan * 8 + 4];
+    if (!(p.map_n[2] > 10 && p.map_n[4] > 100)) {
+        if (lane == 0) { state[0] = 1; state[1] = 0; res->iterations = 0; res->status = VLO_SOFT_TOO_FEW_CORR; p.done[2 * k + 1] = it; atomicAdd(&p.done[2 * n], 1); }
+        return;
+    }
+    const int n_edge = __ldcg(p.ncorr + k * 2), n_plane = __ldcg(p.ncorr + k * 2 + 1);
+    __syncwarp();
+    if (lane == 0) { p.ncorr[k * 2] = 0; p.ncorr[k * 2 + 1] = 0; state[1] = it + 1; res->iterations = it + 1; }
+    if (n_edge + n_plane < 50) return;            // upstream `continue`
+    if (lane < 6) S.T[lane] = __ldcg(p.T + k * 6 + lane);
+    if (it > 0) for (int e = lane; e < 36; e += 32) S.P[e] = __ldcg(&res->P[e]);
+    if (lane == 0) { S.is_degenerate = __ldcg(state + 2); S.converged = 0; S.n_edge = n_edge; S.n_plane = n_plane; }
+    // R1 levels 2 and 3 over the level-1 sums, same order as k5_solve_slot
+    const int n_l1 = (q_total + 31) / 32, n_l2 = (n_l1 + 31) / 32;
+    float l3 = 0.0f;
+    for (int base = 0; base < n_l2; base += 8) {
+        __syncwarp();
+        for (int task = lane; task < 8 * VLO_NTERM; task += 32) {
+            const int b2 = base + task / VLO_NTERM, e = task % VLO_NTERM;
+            if (b2 < n_l2) {
+                float acc = 0.0f;
+                const int lo = b2 * 32, hi = min(n_l1, lo + 32);
+                const float *src = p.partials + ((size_t)k * p.pcap + lo) * VLO_NTERM + e;
+                for (int q = lo; q < hi; q++, src += VLO_NTERM) acc = acc + __ldcg(src);
+                M.l2[task] = acc;
+            }
+        }
+        __syncwarp();
+        if (lane < VLO_NTERM) {
+            const int cnt = min(8, n_l2 - base);
+            for (int b = 0; b < cnt; b++) l3 = l3 + M.l2[b * VLO_NTERM + lane];
+        }
+    }
+    if (lane < VLO_NTERM) S.total[lane] = l3;
+    __syncwarp();
+    vlo_gn_update_warp(S, it, p.degen_thr, p.dT_abort, p.dR_abort, lane);
+    if (lane < 6) { p.T[k * 6 + lane] = S.T[lane]; res->transform[lane] = S.T[lane]; }
+    if (it == 0) {
+        for (int e = lane; e < 36; e += 32) res->P[e] = S.P[e];
+        if (lane < 6) res->eig[lane] = S.eval[lane];
+    }
+    if (lane == 0) {
+        state[0] = S.converged; state[2] = S.is_degenerate; state[3] = VLO_OK;
+        if (S.converged) { p.done[2 * k + 1] = it; atomicAdd(&p.done[2 * n], 1); }
+        res->is_degenerate = S.is_degenerate; res->status = VLO_OK;
+        res->n_corr_edge = n_edge; res->n_corr_plane = n_plane;
+        vlo_finish_result(S, p.rot_thr, p.trans_thr, res);
+    }
+    __syncwarp();
+}
+
+// p.done: [n][2] = {tiles of the slot completed in this launch, iteration at which the slot converged}, then
+// [2 n] = number of slots that have converged (every later launch returns at once when it reaches n), then one ticket
+// counter per launch at [2 n + 1 + 2 it + phase]
+struct ListSmem { int warp_tot[AL_WARPS], warp_act[AL_WARPS], n_active; };
+
+// flat work list: the unconverged slots (order-preserving) with the prefix sums of their tile counts; returns the
+// number of active slots (the same in every CTA of the launch)
+__device__ __forceinline__ int k5_build_list(const MapParams &p, int it, int n, int *s_slot, int *s_pref, ListSmem &L)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { L.n_active = 0; s_pref[0] = 0; }
     __syncthreads();
-    if (threadIdx.x == 0) { __threadfence(); s_last = atomicAdd(&p.done[k], 1) == (int)gridDim.x - 1; }
-    __syncthreads();
-    if (!s_last) return;
-    if (threadIdx.x == 0) p.done[k] = 0;
-    __threadfence();
-    k5_solve_slot(p, k, it, M);
+    for (int base = 0; base < n; base += KNN_THREADS) {
+        const int k = base + tid;
+        int tiles = 0; bool act = false;
+        if (k < n && __ldcg(p.done + 2 * k + 1) >= it) {
+            const int scan = p.scans[k];
+            tiles = max(1, (p.counts[scan * 8 + 2] + p.counts[scan * 8 + 4] + 31) >> 5);   // an empty slot still gets solved
+            act = true;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, act);
+        int inc = tiles;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+        if (lane == 31) L.warp_tot[warp] = inc;
+        if (lane == 0) L.warp_act[warp] = __popc(bal);
+        __syncthreads();
+        int a0 = L.n_active, t0 = s_pref[a0];
+        for (int w = 0; w < warp; w++) { a0 += L.warp_act[w]; t0 += L.warp_tot[w]; }
+        if (act) {
+            const int pos = a0 + __popc(bal & ((1u << lane) - 1u));
+            s_slot[pos] = k;
+            s_pref[pos + 1] = t0 + inc;
+        }
+        __syncthreads();
+        if (tid == 0) { int a = 0; for (int w = 0; w < AL_WARPS; w++) a += L.warp_act[w]; L.n_active += a; }
+        __syncthreads();
+    }
+    return L.n_active;
+}
+
+// association of every unconverged slot's feature points (exact 5-NN, indices to idx5)
+__global__ void __launch_bounds__(KNN_THREADS) k5_assoc(MapParams p, int it, int n)
+{
+    extern __shared__ int s_dyn[];                 // [n] active slots, [n + 1] tile prefix
+    __shared__ ListSmem L;
+    if (__ldcg(p.done + 2 * n) >= n) return;       // everything converged in an earlier launch
+    if (!(p.map_n[2] > 10 && p.map_n[4] > 100)) return;
+    int *s_slot = s_dyn, *s_pref = s_dyn + n;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_active = k5_build_list(p, it, n, s_slot, s_pref, L);
+    if (n_active == 0) return;
+    const int total = s_pref[n_active];
+    const int n_static = gridDim.x * AL_WARPS;
+    int g = blockIdx.x * AL_WARPS + warp;
+    while (g < total) {
+        int nxt = 0;
+        if (lane == 0) nxt = n_static + atomicAdd(&p.done[2 * n + 1 + 2 * it], 1);
+        int lo = 0, hi = n_active;                  // slot j with pref[j] <= g < pref[j + 1]
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_pref[mid] <= g) lo = mid; else hi = mid; }
+        k5_tile<1>(p, s_slot[lo], g - s_pref[lo], it, nullptr, lane);
+        g = __shfl_sync(0xffffffffu, nxt, 0);
+    }
+}
+
+// linearisation + level-1 sums of every unconverged slot; the warp that completes a slot's last tile solves the slot
+__global__ void __launch_bounds__(KNN_THREADS) k5_lin(MapParams p, int it, int n)
+{
+    extern __shared__ int s_dyn[];
+    __shared__ float terms[AL_WARPS][32 * LSTRIDE];
+    __shared__ SolveWarpSmem M[AL_WARPS];
+    __shared__ ListSmem L;
+    if (__ldcg(p.done + 2 * n) >= n) return;
+    int *s_slot = s_dyn, *s_pref = s_dyn + n;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_active = k5_build_list(p, it, n, s_slot, s_pref, L);
+    if (n_active == 0) return;
+    const int total = s_pref[n_active];
+    const bool map_ok = p.map_n[2] > 10 && p.map_n[4] > 100;
+    const int n_static = gridDim.x * AL_WARPS;
+    int g = blockIdx.x * AL_WARPS + warp;
+    while (g < total) {
+        int nxt = 0;
+        if (lane == 0) nxt = n_static + atomicAdd(&p.done[2 * n + 2 + 2 * it], 1);
+        int lo = 0, hi = n_active;
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_pref[mid] <= g) lo = mid; else hi = mid; }
+        const int k = s_slot[lo], tile = g - s_pref[lo], n_tiles = s_pref[lo + 1] - s_pref[lo];
+        if (map_ok) k5_tile<2>(p, k, tile, it, terms[warp], lane);
+        __threadfence();                            // this tile's level-1 sums and counts before the completion count
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) last = atomicAdd(&p.done[2 * k], 1) == n_tiles - 1;
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            if (lane == 0) p.done[2 * k] = 0;
+            __threadfence();
+            k5_solve_slot_warp(p, k, it, M[warp], lane, n);
+        }
+        g = __shfl_sync(0xffffffffu, nxt, 0);
+    }
 }
 
 // Latency path (online tick, a few slots): the whole registration in ONE cooperative launch.
@@ -425,7 +591,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k5_register_coop(MapParams p, 
         for (int g = blockIdx.x * AL_WARPS + warp; g < total; g += gridDim.x * AL_WARPS) {
             int lo = 0, hi = n_active;              // slot j with pref[j] <= g < pref[j + 1]
             while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_pref[mid] <= g) lo = mid; else hi = mid; }
-            k5_tile(p, s_slot[lo], g - s_pref[lo], it, terms[warp], lane);
+            k5_tile<0>(p, s_slot[lo], g - s_pref[lo], it, terms[warp], lane);
         }
         grid.sync();
         for (int j = blockIdx.x; j < n_active; j += gridDim.x) k5_solve_slot(p, s_slot[j], it, M);
@@ -436,11 +602,12 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k5_register_coop(MapParams p, 
 __global__ void k5_init(MapParams p, const float *seeds, int n)
 {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x == 0) for (int i = threadIdx.x; i < 2 * p.max_iter + 1; i += blockDim.x) p.done[2 * n + i] = 0;   // converged count, tile tickets
     if (k >= n) return;
     for (int a = 0; a < 6; a++) p.T[k * 6 + a] = seeds[k * 6 + a];
     int *st = p.state + k * 4;
     st[0] = 0; st[1] = 0; st[2] = 0; st[3] = VLO_SOFT_TOO_FEW_CORR;
-    p.ncorr[k * 2] = 0; p.ncorr[k * 2 + 1] = 0; p.done[k] = 0;
+    p.ncorr[k * 2] = 0; p.ncorr[k * 2 + 1] = 0; p.done[2 * k] = 0; p.done[2 * k + 1] = K5_NOT_CONVERGED;
     vlo_result *r = p.result + k;
     for (int a = 0; a < 6; a++) { r->transform[a] = seeds[k * 6 + a]; r->eig[a] = 0.0f; }
     for (int a = 0; a < 36; a++) { r->hessian[a] = 0.0f; r->P[a] = (a % 7 == 0) ? 1.0f : 0.0f; r->cov[a] = 0.0; }
@@ -482,14 +649,24 @@ int vlo_launch_register_map(vlo_handle *h, const int *d_scans, int n, const floa
         vlo_prof_end(h, ST_MAP_KNN);
         h->launches += 2;
     } else {
-        // throughput path: ~8 waves of CTAs at 5 per SM (measured best: short strides balance the per-query
-        // variance), never more than one warp per 32 queries
-        int ctas_cap = (qmax + KNN_THREADS - 1) / KNN_THREADS, ctas_fill = (148 * 5 * 8 + n - 1) / n;
-        dim3 gk(std::max(1, std::min(ctas_cap, ctas_fill)), n);
-        for (int it = 0; it < c.map_max_iterations; it++) {
-            VLO_PROF(h, ST_MAP_LIN, (k5_assoc_lin<<<gk, KNN_THREADS, 0, h->stream>>>(p, it)));
+        // throughput path: two launches per Gauss-Newton iteration (association, then linearisation + solve), each a
+        // persistent grid over the flat tile list of the unconverged slots, never more warps than tiles
+        static int sms = 0, occ_a = 0, occ_l = 0;
+        if (!sms) {
+            VLO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device));
+            VLO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a, k5_assoc, KNN_THREADS, 2048));
+            VLO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, k5_lin, KNN_THREADS, 2048));
         }
-        h->launches += 1 + c.map_max_iterations;
+        const long long tiles = (long long)n * ((qmax + 31) / 32);
+        const long long want = (tiles + AL_WARPS - 1) / AL_WARPS;
+        const int ctas_a = (int)std::max<long long>(1, std::min<long long>((long long)sms * std::max(1, occ_a), want));
+        const int ctas_l = (int)std::max<long long>(1, std::min<long long>((long long)sms * std::max(1, occ_l), want));
+        const size_t dyn = sizeof(int) * (2 * (size_t)n + 2);
+        for (int it = 0; it < c.map_max_iterations; it++) {
+            VLO_PROF(h, ST_MAP_ASSOC, (k5_assoc<<<ctas_a, KNN_THREADS, dyn, h->stream>>>(p, it, n)));
+            VLO_PROF(h, ST_MAP_LIN, (k5_lin<<<ctas_l, KNN_THREADS, dyn, h->stream>>>(p, it, n)));
+        }
+        h->launches += 1 + 2 * c.map_max_iterations;
     }
     VLO_CUDA(cudaGetLastError());
     return VLO_OK;

@@ -2,7 +2,7 @@
 #include "vlo_internal.cuh"
 
 static const char *kStageNames[ST_COUNT] = { "k0_organise", "k1_extract", "k1b_compact", "k2_grid_build", "k3_to_end", "k3_assoc",
-                                             "k3_gn", "k5_register_coop", "k5_assoc_lin", "k5_solve", "k6_imu", "k7_stack_ds",
+                                             "k3_gn", "k5_register_coop", "k5_lin", "k5_assoc", "k6_imu", "k7_stack_ds",
                                              "k7_map_insert" };
 
 void vlo_prof_begin(vlo_handle *h, int stage)

@@ -153,7 +153,7 @@ extern "C" int vlo_create(const vlo_config *cfg, vlo_handle **out)
         HALLOC(h->map_partials, (size_t)B * ((qcap + 31) / 32 + 8) * VLO_NTERM);
         HALLOC(h->map_idx5, (size_t)B * qcap * 5);
         HALLOC(h->map_T, (size_t)B * 6); HALLOC(h->map_seed, (size_t)B * 6); HALLOC(h->map_state, (size_t)B * 4);
-        HALLOC(h->map_ncorr, (size_t)B * 2); HALLOC(h->map_done, (size_t)B); HALLOC(h->map_scans, (size_t)B); HALLOC(h->map_result, (size_t)B);
+        HALLOC(h->map_ncorr, (size_t)B * 2); HALLOC(h->map_done, (size_t)B * 2 + 2 * (size_t)std::max(1, c.map_max_iterations) + 1); HALLOC(h->map_scans, (size_t)B); HALLOC(h->map_result, (size_t)B);
         { int rc = vlo_lm_alloc(h); if (rc) { vlo_destroy(h); return rc; } }
     }
     if (cudaDeviceSynchronize() != cudaSuccess) { h->err = "device sync after allocation failed"; vlo_destroy(h); return VLO_ERR_CUDA; }

@@ -150,7 +150,7 @@ struct vlo_handle {
 // per-stage device timing (bench.py's roofline leg): CUDA events on the handle's stream around
 // every launch group, summed per stage by vlo_get_stage_times
 enum VloStage { ST_ORGANISE = 0, ST_EXTRACT, ST_COMPACT, ST_GRID_BUILD, ST_TO_END, ST_ASSOC, ST_GN, ST_MAP_KNN, ST_MAP_LIN,
-                ST_MAP_SOLVE, ST_IMU, ST_STACK_DS, ST_MAP_INSERT, ST_COUNT };
+                ST_MAP_ASSOC, ST_IMU, ST_STACK_DS, ST_MAP_INSERT, ST_COUNT };
 void vlo_prof_begin(vlo_handle *h, int stage);
 void vlo_prof_end(vlo_handle *h, int stage);
 #define VLO_PROF(h, stage, stmt) do { vlo_prof_begin(h, stage); stmt; vlo_prof_end(h, stage); } while (0)
