@@ -456,35 +456,58 @@ __global__ void __launch_bounds__(K1_THREADS) k1c_lessflat(K1Params p)
     for (int k = 0; k < MAXP; k++) {
         const int i = k * K1_THREADS + tid;
         so[k] = -1;
-        if (i < n) {
-            bool in = false;
-            if (i >= lo_all && i <= hi_all) {
-                in = all_valid;
-                if (!all_valid) for (int j = 0; j < NR; j++) in |= (s_ep[j] > s_sp[j] && i >= s_sp[j] && i <= s_ep[j]);
-            }
-            if (in && lab[k] <= 0) {
-                const float4 q = v[k];
-                const int ix = (int)floorf(q.x * inv), iy = (int)floorf(q.y * inv), iz = (int)floorf(q.z * inv);
-                const unsigned long long key = ((unsigned long long)(unsigned)(ix + (1 << 20)) << 42)
-                                             | ((unsigned long long)(unsigned)(iy + (1 << 20)) << 21)
-                                             | (unsigned long long)(unsigned)(iz + (1 << 20));
-                const unsigned hsh = ((unsigned)ix * 73856093u) ^ ((unsigned)iy * 19349663u) ^ ((unsigned)iz * 83492791u);
-                int slot = (int)(hsh & (unsigned)(p.HT - 1));
-                while (true) {
-                    unsigned long long old = atomicCAS(&s.vkey[slot], K1_EMPTY, key);
-                    if (old == K1_EMPTY || old == key) break;
-                    slot = (slot + 1) & (p.HT - 1);
-                }
-                const float ox = (float)ix * leaf, oy = (float)iy * leaf, oz = (float)iz * leaf;
-                atomicMin(&s.vfirst[slot], i);
-                atomicAdd(&s.vcnt[slot], 1);
-                atomicAdd(&s.vsx[slot], (int)rintf((q.x - ox) * 1048576.0f));
-                atomicAdd(&s.vsy[slot], (int)rintf((q.y - oy) * 1048576.0f));
-                atomicAdd(&s.vsz[slot], (int)rintf((q.z - oz) * 1048576.0f));
-                atomicAdd(&s.vsw[slot], (int)rintf((q.w - (float)(int)q.w) * 1048576.0f));
-                so[k] = slot;
-            }
+        bool in = false;
+        if (i < n && i >= lo_all && i <= hi_all) {
+            in = all_valid;
+            if (!all_valid) for (int j = 0; j < NR; j++) in |= (s_ep[j] > s_sp[j] && i >= s_sp[j] && i <= s_ep[j]);
         }
+        const bool take = in && lab[k] <= 0;
+        // The lanes of a warp hold consecutive points of the ring, and consecutive points share a 0.2 m voxel more often
+        // than not (3.5 cm apart at 10 m): a voxel shows up as a RUN of lanes.  Run heads come from one ballot, the
+        // run's integer sums from a five-step segmented shuffle reduction, and the head lane alone touches the hash
+        // (r01c ncu: 57 % of this kernel's shared-memory wavefronts were same-address atomic conflicts, the CAS probe
+        // its top stall).  A voxel re-entered later is a second run with its own atomics; integer sums are order-free,
+        // so the centroids stay bit-identical.
+        const float4 q = v[k];
+        int ix = 0, iy = 0, iz = 0, dx = 0, dy = 0, dz = 0, dw = 0;
+        unsigned long long key = 0x8000000000000000ull | (unsigned long long)lane;      // private key: not taken
+        if (take) {
+            ix = (int)floorf(q.x * inv); iy = (int)floorf(q.y * inv); iz = (int)floorf(q.z * inv);
+            key = ((unsigned long long)(unsigned)(ix + (1 << 20)) << 42) | ((unsigned long long)(unsigned)(iy + (1 << 20)) << 21)
+                | (unsigned long long)(unsigned)(iz + (1 << 20));
+            const float ox = (float)ix * leaf, oy = (float)iy * leaf, oz = (float)iz * leaf;
+            dx = (int)rintf((q.x - ox) * 1048576.0f); dy = (int)rintf((q.y - oy) * 1048576.0f);
+            dz = (int)rintf((q.z - oz) * 1048576.0f); dw = (int)rintf((q.w - (float)(int)q.w) * 1048576.0f);
+        }
+        const unsigned long long prevk = __shfl_up_sync(0xffffffffu, key, 1);
+        const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prevk != key);
+        const unsigned later = heads & ~((2u << lane) - 1u);
+        const int run_end = later ? (__ffs(later) - 2) : 31;
+        const int leader = 31 - __clz(heads & ((2u << lane) - 1u));
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int ax = __shfl_down_sync(0xffffffffu, dx, d), ay = __shfl_down_sync(0xffffffffu, dy, d);
+            const int az = __shfl_down_sync(0xffffffffu, dz, d), aw = __shfl_down_sync(0xffffffffu, dw, d);
+            if (lane + d <= run_end) { dx += ax; dy += ay; dz += az; dw += aw; }
+        }
+        int slot = -1;
+        if (take && lane == leader) {
+            const unsigned hsh = ((unsigned)ix * 73856093u) ^ ((unsigned)iy * 19349663u) ^ ((unsigned)iz * 83492791u);
+            slot = (int)(hsh & (unsigned)(p.HT - 1));
+            while (true) {
+                unsigned long long old = atomicCAS(&s.vkey[slot], K1_EMPTY, key);
+                if (old == K1_EMPTY || old == key) break;
+                slot = (slot + 1) & (p.HT - 1);
+            }
+            atomicMin(&s.vfirst[slot], i);
+            atomicAdd(&s.vcnt[slot], run_end - lane + 1);
+            atomicAdd(&s.vsx[slot], dx);
+            atomicAdd(&s.vsy[slot], dy);
+            atomicAdd(&s.vsz[slot], dz);
+            atomicAdd(&s.vsw[slot], dw);
+        }
+        slot = __shfl_sync(0xffffffffu, slot, leader);
+        if (take) so[k] = slot;
     }
     __syncthreads();
     unsigned bal[MAXP];

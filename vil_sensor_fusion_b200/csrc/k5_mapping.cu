@@ -75,63 +75,109 @@ __device__ inline void eig3_jacobi(const float *Ain, float *eval, float *evec)
             A[r][p] = A[p][r]; A[r][q] = A[q][r];
         }
     }
-    int order[3] = { 0, 1, 2 };
-    for (int i = 1; i < 3; i++) {
-        int v = order[i], j = i;
-        while (j >= 1 && A[v][v] < A[order[j - 1]][order[j - 1]]) { order[j] = order[j - 1]; j--; }
-        order[j] = v;
-    }
-    for (int k = 0; k < 3; k++) {
-        eval[k] = A[order[k]][order[k]];
-        for (int i = 0; i < 3; i++) evec[k * 3 + i] = V[i][order[k]];
-    }
+    // stable insertion sort of the three eigenpairs by eigenvalue (strict <), written as adjacent conditional swaps on
+    // named registers: no run-time array index, so nothing of this function lives in local memory
+    float e0 = A[0][0], e1 = A[1][1], e2 = A[2][2];
+    float c0[3] = { V[0][0], V[1][0], V[2][0] }, c1[3] = { V[0][1], V[1][1], V[2][1] }, c2[3] = { V[0][2], V[1][2], V[2][2] };
+    #define EIG3_SWAP(ea, ca, eb, cb) { float t_ = ea; ea = eb; eb = t_; _Pragma("unroll") for (int i_ = 0; i_ < 3; i_++) { float u_ = ca[i_]; ca[i_] = cb[i_]; cb[i_] = u_; } }
+    if (e1 < e0) EIG3_SWAP(e0, c0, e1, c1)
+    if (e2 < e1) { EIG3_SWAP(e1, c1, e2, c2) if (e1 < e0) EIG3_SWAP(e0, c0, e1, c1) }
+    #undef EIG3_SWAP
+    eval[0] = e0; eval[1] = e1; eval[2] = e2;
+    #pragma unroll
+    for (int i = 0; i < 3; i++) { evec[i] = c0[i]; evec[3 + i] = c1[i]; evec[6 + i] = c2[i]; }
 }
 
-__device__ inline void lstsq53(const float (*Ain)[3], float *x)
+// One Householder step of the 5x3 column-pivoted QR with every index a compile-time constant (K = step).
+template <int K>
+__device__ __forceinline__ void lstsq53_step(float (&A)[5][3], float (&b)[5], int (&perm)[3], int &nonzero, float thr_helper)
+{
+    int piv = K; float best = -1.0f;
+    #pragma unroll
+    for (int j = K; j < 3; j++) {
+        float s = 0.0f;
+        #pragma unroll
+        for (int i = K; i < 5; i++) s += A[i][j] * A[i][j];
+        if (s > best) { best = s; piv = j; }
+    }
+    if (nonzero == 3 && best < thr_helper * (float)(5 - K)) nonzero = K;
+    #pragma unroll
+    for (int j = K + 1; j < 3; j++)
+        if (piv == j) {
+            #pragma unroll
+            for (int i = 0; i < 5; i++) { float t = A[i][K]; A[i][K] = A[i][j]; A[i][j] = t; }
+            int t = perm[K]; perm[K] = perm[j]; perm[j] = t;
+        }
+    const float nrm = sqrtf(best);
+    if (nrm == 0.0f) return;
+    const float alpha = (A[K][K] >= 0.0f) ? -nrm : nrm;
+    float v[5];
+    #pragma unroll
+    for (int i = K; i < 5; i++) v[i] = A[i][K];
+    v[K] = v[K] - alpha;
+    float vn2 = 0.0f;
+    #pragma unroll
+    for (int i = K; i < 5; i++) vn2 += v[i] * v[i];
+    if (vn2 == 0.0f) return;
+    #pragma unroll
+    for (int j = K; j < 3; j++) {
+        float dot = 0.0f;
+        #pragma unroll
+        for (int i = K; i < 5; i++) dot += v[i] * A[i][j];
+        const float f = (2.0f * dot) / vn2;
+        #pragma unroll
+        for (int i = K; i < 5; i++) A[i][j] = A[i][j] - f * v[i];
+    }
+    float dot = 0.0f;
+    #pragma unroll
+    for (int i = K; i < 5; i++) dot += v[i] * b[i];
+    const float f = (2.0f * dot) / vn2;
+    #pragma unroll
+    for (int i = K; i < 5; i++) b[i] = b[i] - f * v[i];
+}
+
+// min ||A x + 1|| for the 5 x 3 neighbour matrix: column-pivoted Householder QR (Q1 of the oracle, orc_lstsq53), same
+// operations in the same order; the pivot swaps, the rank-dependent back-substitution and the final permutation are
+// spelled out on constant indices so that A, b, v stay in registers (the run-time-indexed version kept them in local
+// memory: 623 LDL/STL in the kernel)
+__device__ __forceinline__ void lstsq53(const float (*Ain)[3], float *x)
 {
     float A[5][3], b[5];
     int perm[3] = { 0, 1, 2 };
-    for (int i = 0; i < 5; i++) { for (int j = 0; j < 3; j++) A[i][j] = Ain[i][j]; b[i] = -1.0f; }
+    #pragma unroll
+    for (int i = 0; i < 5; i++) {
+        #pragma unroll
+        for (int j = 0; j < 3; j++) A[i][j] = Ain[i][j];
+        b[i] = -1.0f;
+    }
     float maxn2 = 0.0f;
-    for (int j = 0; j < 3; j++) { float s = 0.0f; for (int i = 0; i < 5; i++) s += A[i][j] * A[i][j]; if (s > maxn2) maxn2 = s; }
-    float mx = sqrtf(maxn2) * FLT_EPSILON;
-    float thr_helper = (mx * mx) / 5.0f;
+    #pragma unroll
+    for (int j = 0; j < 3; j++) {
+        float s = 0.0f;
+        #pragma unroll
+        for (int i = 0; i < 5; i++) s += A[i][j] * A[i][j];
+        if (s > maxn2) maxn2 = s;
+    }
+    const float mx = sqrtf(maxn2) * FLT_EPSILON;
+    const float thr_helper = (mx * mx) / 5.0f;
     int nonzero = 3;
-    for (int k = 0; k < 3; k++) {
-        int piv = k; float best = -1.0f;
-        for (int j = k; j < 3; j++) { float s = 0.0f; for (int i = k; i < 5; i++) s += A[i][j] * A[i][j]; if (s > best) { best = s; piv = j; } }
-        if (nonzero == 3 && best < thr_helper * (float)(5 - k)) nonzero = k;
-        if (piv != k) {
-            for (int i = 0; i < 5; i++) { float t = A[i][k]; A[i][k] = A[i][piv]; A[i][piv] = t; }
-            int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t;
-        }
-        float nrm = sqrtf(best);
-        if (nrm == 0.0f) continue;
-        float alpha = (A[k][k] >= 0.0f) ? -nrm : nrm;
-        float v[5] = { 0.f, 0.f, 0.f, 0.f, 0.f };
-        for (int i = k; i < 5; i++) v[i] = A[i][k];
-        v[k] = v[k] - alpha;
-        float vn2 = 0.0f;
-        for (int i = k; i < 5; i++) vn2 += v[i] * v[i];
-        if (vn2 == 0.0f) continue;
-        for (int j = k; j < 3; j++) {
-            float dot = 0.0f;
-            for (int i = k; i < 5; i++) dot += v[i] * A[i][j];
-            float f = (2.0f * dot) / vn2;
-            for (int i = k; i < 5; i++) A[i][j] = A[i][j] - f * v[i];
-        }
-        float dot = 0.0f;
-        for (int i = k; i < 5; i++) dot += v[i] * b[i];
-        float f = (2.0f * dot) / vn2;
-        for (int i = k; i < 5; i++) b[i] = b[i] - f * v[i];
+    lstsq53_step<0>(A, b, perm, nonzero, thr_helper);
+    lstsq53_step<1>(A, b, perm, nonzero, thr_helper);
+    lstsq53_step<2>(A, b, perm, nonzero, thr_helper);
+    float y0 = 0.f, y1 = 0.f, y2 = 0.f;
+    if (nonzero == 3) {
+        y2 = b[2] / A[2][2];
+        y1 = (b[1] - A[1][2] * y2) / A[1][1];
+        float s0 = b[0]; s0 = s0 - A[0][1] * y1; s0 = s0 - A[0][2] * y2;
+        y0 = s0 / A[0][0];
+    } else if (nonzero == 2) {
+        y1 = b[1] / A[1][1];
+        y0 = (b[0] - A[0][1] * y1) / A[0][0];
+    } else if (nonzero == 1) {
+        y0 = b[0] / A[0][0];
     }
-    float y[3] = { 0.f, 0.f, 0.f };
-    for (int i = nonzero - 1; i >= 0; i--) {
-        float s = b[i];
-        for (int j = i + 1; j < nonzero; j++) s = s - A[i][j] * y[j];
-        y[i] = s / A[i][i];
-    }
-    for (int i = 0; i < 3; i++) x[perm[i]] = y[i];
+    #pragma unroll
+    for (int c = 0; c < 3; c++) x[c] = (perm[0] == c) ? y0 : ((perm[1] == c) ? y1 : y2);
 }
 
 __device__ inline bool map_edge_coeff(float4 sel, const float4 *nb, float *coeff)
@@ -506,7 +552,7 @@ __global__ void __launch_bounds__(KNN_THREADS) k5_assoc(MapParams p, int it, int
 }
 
 // linearisation + level-1 sums of every unconverged slot; the warp that completes a slot's last tile solves the slot
-__global__ void __launch_bounds__(KNN_THREADS) k5_lin(MapParams p, int it, int n)
+__global__ void __launch_bounds__(KNN_THREADS, 6) k5_lin(MapParams p, int it, int n)
 {
     extern __shared__ int s_dyn[];
     __shared__ float terms[AL_WARPS][32 * LSTRIDE];

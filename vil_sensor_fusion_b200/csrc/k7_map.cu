@@ -47,48 +47,59 @@ __device__ __forceinline__ int k7_ds_table_size(int n, int alloc)
 }
 
 // record of a hash slot: sx sy sz sw cnt first pad pad (one 32-byte sector)
-// Consecutive points of a ring fall into the same 0.2 / 0.4 m voxel more often than not: the lanes of a warp that share
-// a voxel (match_any on the key) reduce their integer sums with REDUX first and one lane issues the atomics.
+// Consecutive points of a ring fall into the same 0.2 / 0.4 m voxel more often than not.  The lanes of a warp hold
+// consecutive points, so a voxel shows up as a RUN of lanes: run heads come from one ballot, the run's integer sums from
+// a five-step segmented shuffle reduction, and the head lane alone issues the atomics (count = run length, first =
+// the head's index).  A voxel that re-appears later in the warp is simply a second run with its own atomics -- the
+// sums are order-free.  (r01c ncu: match_any + REDUX on per-group masks were 35 % of this kernel's samples, and 87 % of
+// the 131 072 CTAs of the capacity-sized grid had nothing to do; the grid now strides over the points.)
+#define K7_BIN_CTAS 24
 __global__ void __launch_bounds__(256) k7_ds_bin(StackDsParams p)
 {
-    const int b = p.scan_first + blockIdx.y, w = blockIdx.z, i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    const int b = p.scan_first + blockIdx.y, w = blockIdx.z, lane = threadIdx.x & 31;
     if (!((p.wmask >> w) & 1)) return;
     const int n = p.counts[b * 8 + (w ? 4 : 2)];
-    if ((int)(blockIdx.x * blockDim.x) >= n) return;                 // whole CTA out of range
-    const bool valid = i < n;
     const float leaf = p.leaf[w], inv = 1.0f / leaf;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) v = p.src[w][(size_t)b * p.stride[w] + i];
-    const int ix = (int)floorf(v.x * inv), iy = (int)floorf(v.y * inv), iz = (int)floorf(v.z * inv);
-    // lanes past the end get private keys (bit 63 is never set in a grid key)
-    const unsigned long long key = valid ? grid_key(ix, iy, iz) : (0x8000000000000000ull | (unsigned long long)lane);
-    const float ox = (float)ix * leaf, oy = (float)iy * leaf, oz = (float)iz * leaf;
-    int qx = (int)rintf((v.x - ox) * LM_QF), qy = (int)rintf((v.y - oy) * LM_QF), qz = (int)rintf((v.z - oz) * LM_QF);
-    int qw = (int)rintf((v.w - (float)(int)v.w) * LM_QF);
-    const unsigned grp = __match_any_sync(0xffffffffu, key);
-    const int leader = __ffs(grp) - 1;
-    int cnt = 1, first = i;
-    if (grp != (1u << lane)) {                                        // shared voxel: reduce inside the group
-        qx = __reduce_add_sync(grp, qx); qy = __reduce_add_sync(grp, qy); qz = __reduce_add_sync(grp, qz);
-        qw = __reduce_add_sync(grp, qw); cnt = __popc(grp); first = __reduce_min_sync(grp, i);
-    }
-    int slot = 0;
-    if (valid && lane == leader) {
-        const int hs = k7_ds_table_size(n, p.hsize[w]);
-        unsigned long long *keys = p.keys + (size_t)b * p.hts + p.hoff[w];
-        slot = (int)(grid_hash(ix, iy, iz) & (unsigned)(hs - 1));
-        while (true) {
-            unsigned long long old = atomicCAS(&keys[slot], LM_EMPTY, key);
-            if (old == LM_EMPTY || old == key) break;
-            slot = (slot + 1) & (hs - 1);
+    const int hs = k7_ds_table_size(n, p.hsize[w]);
+    unsigned long long *keys = p.keys + (size_t)b * p.hts + p.hoff[w];
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {     // CTA-uniform bounds
+        const int i = base + threadIdx.x;
+        const bool valid = i < n;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) v = p.src[w][(size_t)b * p.stride[w] + i];
+        const int ix = (int)floorf(v.x * inv), iy = (int)floorf(v.y * inv), iz = (int)floorf(v.z * inv);
+        // lanes past the end get private keys (bit 63 is never set in a grid key)
+        const unsigned long long key = valid ? grid_key(ix, iy, iz) : (0x8000000000000000ull | (unsigned long long)lane);
+        const float ox = (float)ix * leaf, oy = (float)iy * leaf, oz = (float)iz * leaf;
+        int qx = (int)rintf((v.x - ox) * LM_QF), qy = (int)rintf((v.y - oy) * LM_QF), qz = (int)rintf((v.z - oz) * LM_QF);
+        int qw = (int)rintf((v.w - (float)(int)v.w) * LM_QF);
+        const unsigned long long prev = __shfl_up_sync(0xffffffffu, key, 1);
+        const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prev != key);
+        const unsigned later = heads & ~((2u << lane) - 1u);                   // heads strictly after this lane
+        const int run_end = later ? (__ffs(later) - 2) : 31;                     // last lane of this lane's run
+        const int leader = 31 - __clz(heads & ((2u << lane) - 1u));             // head lane of this lane's run
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int ax = __shfl_down_sync(0xffffffffu, qx, d), ay = __shfl_down_sync(0xffffffffu, qy, d);
+            const int az = __shfl_down_sync(0xffffffffu, qz, d), aw = __shfl_down_sync(0xffffffffu, qw, d);
+            if (lane + d <= run_end) { qx += ax; qy += ay; qz += az; qw += aw; }
         }
-        int *rec = p.rec + ((size_t)b * p.hts + p.hoff[w] + slot) * 8;
-        atomicAdd(&rec[0], qx); atomicAdd(&rec[1], qy); atomicAdd(&rec[2], qz); atomicAdd(&rec[3], qw);
-        atomicAdd(&rec[4], cnt);
-        atomicMin(&rec[5], first);
+        int slot = 0;
+        if (valid && lane == leader) {
+            slot = (int)(grid_hash(ix, iy, iz) & (unsigned)(hs - 1));
+            while (true) {
+                unsigned long long old = atomicCAS(&keys[slot], LM_EMPTY, key);
+                if (old == LM_EMPTY || old == key) break;
+                slot = (slot + 1) & (hs - 1);
+            }
+            int *rec = p.rec + ((size_t)b * p.hts + p.hoff[w] + slot) * 8;
+            atomicAdd(&rec[0], qx); atomicAdd(&rec[1], qy); atomicAdd(&rec[2], qz); atomicAdd(&rec[3], qw);
+            atomicAdd(&rec[4], run_end - lane + 1);
+            atomicMin(&rec[5], i);
+        }
+        slot = __shfl_sync(0xffffffffu, slot, leader);
+        if (valid) p.slot_of[(size_t)b * p.qstride + (w ? p.qoff1 : 0) + i] = slot;
     }
-    slot = __shfl_sync(0xffffffffu, slot, leader);
-    if (valid) p.slot_of[(size_t)b * p.qstride + (w ? p.qoff1 : 0) + i] = slot;
 }
 
 // ordered block scan of one flag per thread (1024 threads); returns the exclusive rank, `total` = block total
@@ -207,7 +218,7 @@ int vlo_launch_stack_ds(vlo_handle *h, int first, int count)
     }
     if (p.wmask) {
         const int qmax = std::max(h->cap_lsharp, c.max_points);
-        k7_ds_bin<<<dim3((qmax + 255) / 256, count, 2), 256, 0, h->stream>>>(p);
+        k7_ds_bin<<<dim3(std::min((qmax + 255) / 256, K7_BIN_CTAS), count, 2), 256, 0, h->stream>>>(p);
         k7_ds_emit<<<dim3(count, 2), 1024, 0, h->stream>>>(p);
         h->launches += 2;
     }
