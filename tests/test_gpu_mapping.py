@@ -300,3 +300,52 @@ def test_full_size_hdl64_against_1M_map(orc):
         np.testing.assert_array_equal(res["hessian"][k].view(np.uint32), ro["hessian"].view(np.uint32))
         assert res["iterations"][k] == ro["iterations"]
         np.testing.assert_allclose(res["eig"][k], ro["eig"], rtol=1e-4)
+
+
+def test_batch_path_edge_slots(orc):
+    """Batch path (more than 4 slots: k5_assoc / k5_lin over the flat tile list, warp-level solve): a slot whose scan yields
+    no feature points, a scan that appears twice, and a map that is too small -- every slot must equal the same scan
+    registered on its own (the cooperative single-launch path), field for field."""
+    from vil_sensor_fusion_b200 import api, synth
+    scene = synth.scene_room(0)
+    traj = synth.Trajectory()
+    cm, sm = synth.sample_map_points(scene, 150000, seed=1)
+    raws, seeds = [], []
+    for k in range(4):
+        t = 0.1 * k
+        raws.append(synth.make_scan(scene, "VLP-16", t0=t, traj=traj, rolling=False, noise_sigma=0.01, seed=k))
+        seeds.append(synth.loam_map_pose(traj.rotation(t), traj.position(t)).astype(np.float32)
+                     + np.array([0.004, -0.006, 0.003, 0.05, -0.04, 0.06], np.float32))
+    raws.append(raws[0][:40].copy())            # 40 points: every ring is too short for features -> no queries
+    seeds.append(seeds[0].copy())
+    raws.append(raws[1].copy())                 # the same scan twice in one batch
+    seeds.append(seeds[1].copy())
+    seeds = np.stack(seeds)
+    n = len(raws)
+    gcfg = api.default_config("VLP-16", deskew=0, max_scans=n, max_points=32768, max_map_points=int(max(len(cm), len(sm))))
+    fields = ("transform", "hessian", "eig", "P", "iterations", "n_corr_edge", "n_corr_plane", "status", "is_degenerate")
+    with api.Handle(gcfg) as h:
+        h.map_build(cm, sm)
+        h.upload(raws)
+        h.organise()
+        h.extract()
+        batch = h.register_map(np.arange(n), seeds)
+        alone = [h.register_map([k], [seeds[k]])[0] for k in range(n)]
+        again = h.register_map(np.arange(n), seeds)          # workspace counters are left clean for the next call
+        # too-small map: every slot reports the soft status and keeps its seed
+        h.map_build(np.zeros((5, 4), np.float32), np.zeros((50, 4), np.float32))
+        small = h.register_map(np.arange(n), seeds)
+    for k in range(n):
+        for f in fields:
+            a, b = np.asarray(batch[f][k]), np.asarray(alone[k][f])
+            if a.dtype.kind == "f":
+                np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32), err_msg="slot %d field %s" % (k, f))
+            else:
+                np.testing.assert_array_equal(a, b, err_msg="slot %d field %s" % (k, f))
+            np.testing.assert_array_equal(np.asarray(again[f][k]), a, err_msg="second call, slot %d field %s" % (k, f))
+    assert batch["status"][4] != 0 and batch["n_corr_edge"][4] == 0 and batch["n_corr_plane"][4] == 0
+    np.testing.assert_array_equal(batch["transform"][4], seeds[4])
+    np.testing.assert_array_equal(batch["transform"][5].view(np.uint32), batch["transform"][1].view(np.uint32))
+    assert np.all(batch["status"][:4] == 0)
+    assert np.all(small["status"] == 1) and np.all(small["iterations"] == 0)
+    np.testing.assert_array_equal(small["transform"], seeds)
