@@ -288,6 +288,7 @@ __device__ __forceinline__ void grid_search_thread(const GridSet &gs, int g, flo
 #define G27_EX 0x268a5849824504ull
 #define G27_EY 0x29a26522485110ull
 #define G27_EZ 0x2a689694205440ull
+#define G27_REBUILDS 3           // mask passes: after the own cell and after each of the next two scanned cells
 
 __device__ __forceinline__ float grid_sel3(float a1, float a2, int e) { return e == 0 ? 0.0f : (e == 1 ? a1 : a2); }
 
@@ -333,7 +334,7 @@ __device__ __forceinline__ void grid_search_thread27(const GridSet &gs, int g, f
     // mask of neighbour cells is built right after the own cell has been scanned (single copy of the scan code --
     // the kernel's instruction footprint matters: ncu showed no_instruction stalls with 150 KB of SASS)
     unsigned mask = 1u;
-    bool own = true;
+    int rebuild = G27_REBUILDS;
     while (mask) {
         int j0 = 0, j1 = 0;
         do {
@@ -348,14 +349,21 @@ __device__ __forceinline__ void grid_search_thread27(const GridSet &gs, int g, f
             j0 = start[slot]; j1 = start[slot + 1];
         } while (j1 == j0 && mask);
         grid_scan_range(sorted, j0, j1, qx, qy, qz, dmax, flt, best);
-        if (own) {
-            own = false;
+        if (rebuild > 0) {
+            // after the own cell: mark the neighbour cells that can still hold a closer point; after each of the next
+            // scans: drop the marks the tighter k-th distance has made pointless (a lane whose own cell held fewer than K
+            // points starts with all 26 neighbours marked and would otherwise pop and re-test every one of them while
+            // the other 31 lanes wait)
+            const unsigned keep = (rebuild == G27_REBUILDS) ? 0xFFFFFFFFu : mask;
+            rebuild--;
             const float kth = best.kth();
+            unsigned m2 = 0u;
             #pragma unroll
             for (int c = 1; c < 27; c++) {
                 const int ex = (int)((G27_EX >> (2 * c)) & 3ull), ey = (int)((G27_EY >> (2 * c)) & 3ull), ez = (int)((G27_EZ >> (2 * c)) & 3ull);
-                if (!(lx[ex] + (ly[ey] + lz[ez]) > kth)) mask |= 1u << c;
+                if (!(lx[ex] + (ly[ey] + lz[ez]) > kth)) m2 |= 1u << c;
             }
+            mask = m2 & keep;
         }
     }
 }
