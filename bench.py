@@ -169,7 +169,9 @@ def run_gpu(args):
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
             os.environ.pop("NCCL_DEBUG")               # NCCL's version banner goes to stdout: keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a rank that dies must not leave the others waiting for NCCL's default 10 minutes
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=240))
 
     B = args.batch
     raws_pool, seeds_pool, cm, sm = make_workload(POOL, rank)
@@ -204,9 +206,12 @@ def run_gpu(args):
         h.extract()
         return h.register_map(scans_idx, seeds)
 
-    def barrier():
+    def local_sync():
         torch.cuda.synchronize()
         h.synchronize()
+
+    def barrier():
+        local_sync()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
@@ -323,14 +328,14 @@ def run_gpu(args):
         pcounts = h.counts()
         for _ in range(2):
             pstep()
-        barrier()
+        local_sync()                    # rank 0 only: no collective here
         h.set_profiling(True)
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p0.record(stream)
         for _ in range(args.steps):
             rp = pstep()
         p1.record(stream)
-        barrier()
+        local_sync()                    # rank 0 only: no collective here
         pst = h.stage_times()
         h.set_profiling(False)
         p_ms = p0.elapsed_time(p1) / args.steps

@@ -161,3 +161,35 @@ def test_rosbag_v2_round_trip(tmp_path, compression):
     with pytest.raises(RuntimeError):
         open(str(tmp_path / "x.bag"), "wb").write(b"not a bag")
         list(rb.read_messages(str(tmp_path / "x.bag")))
+
+
+def test_bench_has_no_collective_inside_rank0_only_blocks():
+    """bench.py under torchrun: a collective (dist.*, the bench's barrier(), bag.gather_results) reached by rank 0 alone
+    deadlocks the job (seen on 2 GPUs: rank 0 in barrier() inside the whole-bag leg, rank 1 in the final all_reduce)."""
+    import ast
+    import os
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py")).read()
+    tree = ast.parse(src)
+
+    def mentions_rank0(test):
+        for node in ast.walk(test):
+            if isinstance(node, ast.Compare) and isinstance(node.left, ast.Name) and node.left.id == "rank" \
+                    and len(node.comparators) == 1 and isinstance(node.comparators[0], ast.Constant) and node.comparators[0].value == 0 \
+                    and isinstance(node.ops[0], ast.Eq):
+                return True
+        return False
+
+    bad = []
+    for node in ast.walk(tree):
+        if isinstance(node, ast.If) and mentions_rank0(node.test):
+            for stmt in node.body:
+                for sub in ast.walk(stmt):
+                    if isinstance(sub, ast.Call):
+                        f = sub.func
+                        if isinstance(f, ast.Name) and f.id == "barrier":
+                            bad.append(("barrier", sub.lineno))
+                        if isinstance(f, ast.Attribute) and isinstance(f.value, ast.Name) and f.value.id == "dist":
+                            bad.append(("dist." + f.attr, sub.lineno))
+                        if isinstance(f, ast.Attribute) and f.attr == "gather_results":
+                            bad.append(("gather_results", sub.lineno))
+    assert not bad, bad
