@@ -190,6 +190,7 @@ def run_gpu(args):
     # odom_cell_size: 0.7 m cells for the scan-to-scan surface grids of the whole-bag leg (tools/pairs_tune.py: batches
     # prefer smaller cells than the 1 m default that minimises the single-pair latency; results are identical)
     cfg = api.default_config("HDL-64E", deskew=0, max_scans=B, max_points=131072, odom_cell_size=0.7,
+                             odom_corner_cell_size=float(os.environ.get("VLO_CORNER_CELL", "5.0")),
                              max_map_points=int(max(len(cm), len(sm))), device=local_rank)
     if os.environ.get("VLO_MAP_CELL"):
         cfg.map_cell_size = float(os.environ["VLO_MAP_CELL"])          # tuning experiments only

@@ -156,3 +156,39 @@ def test_hessian_order_option(orc):
     passed, lr, lt = api.dopt_gate(Hb)
     assert passed == bool(b["pass_dopt"])
     np.testing.assert_allclose([lr, lt], [b["logdet_rot"], b["logdet_trans"]], rtol=1e-6)
+
+
+@pytest.mark.parametrize("lidar,max_points,cell", [("VLP-16", 32768, 1.0), ("HDL-64E", 131072, 0.7), ("VLP-16", 32768, 0.35)])
+def test_pairs_batch_thread_search_equals_oracle_and_single_pair_path(orc, lidar, max_points, cell):
+    """More than four pairs per call run the thread-per-query association (k3_assoc_thread: per-lane 27-cell search with
+    the exact warp-cooperative search as fallback; the 0.35 m cells make most VLP-16 partner searches take the fallback).
+    First-round correspondence indices and the converged result must equal the oracle's for two of the pairs, and every
+    pair must equal the same pair registered alone (warp-per-query kernel), bit for bit."""
+    from vil_sensor_fusion_b200 import api
+    mk = scenes.vlp16_scan if lidar == "VLP-16" else scenes.hdl64_scan
+    raws = [mk(0.1 * k, noise=0.01, seed=k) for k in range(7)]
+    ocfg = orc.default_config(lidar, deskew=0)
+    gcfg = api.default_config(lidar, deskew=0, max_scans=7, max_points=max_points, odom_cell_size=cell)
+    last, cur = np.arange(6), np.arange(1, 7)
+    with api.Handle(gcfg) as h:
+        h.lib.vlo_set_trace(h._h, 1)
+        h.upload(raws)
+        h.organise()
+        h.extract()
+        res = h.register_pairs(last, cur)
+        corr = {}
+        for p in (0, 4):
+            ro, n_sharp, n_flat = _oracle_pair(orc, ocfg, raws[p], raws[p + 1], None, None)
+            corr[p] = (ro, n_sharp, n_flat, h.pair_correspondences(p, 0, n_sharp, n_flat))
+        singles = [h.register_pairs([p], [p + 1])[0] for p in range(6)]
+    for p, (ro, n_sharp, n_flat, (ci, si)) in corr.items():
+        per = 2 * n_sharp + 3 * n_flat
+        np.testing.assert_array_equal(ci.ravel(), ro["trace_idx"][:2 * n_sharp], err_msg="corner correspondences, pair %d" % p)
+        np.testing.assert_array_equal(si.ravel(), ro["trace_idx"][2 * n_sharp:per], err_msg="surface correspondences, pair %d" % p)
+        _compare(ro, res[p], "%s batch pair %d" % (lidar, p))
+    for p in range(6):
+        for f in ("transform", "hessian", "eig", "P"):
+            np.testing.assert_array_equal(np.asarray(res[f][p]).view(np.uint32), np.asarray(singles[p][f]).view(np.uint32),
+                                          err_msg="pair %d field %s: batch vs single-pair path" % (p, f))
+        for f in ("iterations", "n_corr_edge", "n_corr_plane", "status", "is_degenerate"):
+            assert res[f][p] == singles[p][f], (p, f)

@@ -9,7 +9,7 @@ B = 128
 order = list(range(8)) + list(range(6, 0, -1))
 raws = [pool[order[k % len(order)]] for k in range(B)]
 ref = None
-for cc, sc in [(5.0, 1.0), (2.5, 1.0), (1.5, 1.0), (1.0, 1.0), (2.5, 0.7), (1.5, 0.5)]:
+for cc, sc in [(5.0, 0.7), (2.0, 0.7), (1.0, 0.7), (0.6, 0.7), (1.0, 0.5), (1.0, 1.0), (0.6, 0.4)]:
     cfg = api.default_config("HDL-64E", deskew=0, max_scans=B, max_points=131072, odom_corner_cell_size=cc, odom_cell_size=sc)
     with api.Handle(cfg) as h:
         h.upload(raws); h.organise(); h.extract()

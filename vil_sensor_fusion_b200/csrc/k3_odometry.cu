@@ -94,6 +94,93 @@ __global__ void __launch_bounds__(256) k3_assoc(OdomParams p, int n_pairs)
     }
 }
 
+// Batch variant of k3_assoc (whole-bag mode): ONE THREAD per feature point.  The warp-per-query search above spends
+// ~540 warp-instructions per query on its cooperative machinery (27 probes, prefix scan, merge rounds) -- fine for
+// the latency of a single pair, wasteful when thousands of queries are waiting.  Here a thread runs the per-lane
+// 27-cell search of grid.cuh for its own point, once per stage (nearest neighbour, partner(s)) through ONE inlined
+// copy of the search.  Exactness: the 27-cell block around the query's cell contains every point closer than one cell
+// edge, so a hit with d2 < (cell - slack)^2 is the global (d2, tie) minimum; a stage without such a hit (sparse
+// regions, far partners) is redone with the exact warp-cooperative search, one such lane at a time.
+struct FilterOdom {          // mode 0: plain nearest neighbour (tie = dense index); mode 1: FilterPartner's rules
+    int mode, ind, ring_lo, ring_hi, skip_ring, fwd_bound;
+    __device__ __forceinline__ bool operator()(unsigned tag, unsigned &tie) const
+    {
+        const int ring = (int)(tag >> 24), idx = (int)(tag & 0xFFFFFFu);
+        if (mode == 0) { tie = (unsigned)idx; return true; }
+        if (ring < ring_lo || ring > ring_hi || ring == skip_ring || idx == ind) return false;
+        if (idx > ind) { if (idx >= fwd_bound) return false; tie = (unsigned)(idx - ind); }
+        else tie = 0x40000000u + (unsigned)(ind - idx);
+        return true;
+    }
+};
+
+#define K3T_THREADS 128
+#define K3_THREAD_PAIRS 4        // up to this many pairs per call keep the warp-per-query kernel (latency of the online tick)
+__global__ void __launch_bounds__(K3T_THREADS) k3_assoc_thread(OdomParams p, int n_pairs)
+{
+    __shared__ int scratch[K3T_THREADS / 32][GRID_SCRATCH_INTS];
+    const int pair = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (p.pair_state[pair * 4 + 0]) return;                          // converged
+    const int last = p.pair_last[pair], cur = p.pair_cur[pair];
+    const int n_sharp = p.counts[cur * 8 + 1], n_flat = p.counts[cur * 8 + 3];
+    const int n_lc = p.counts[last * 8 + 2], n_ls = p.counts[last * 8 + 4];
+    if (!(n_lc > 10 && n_ls > 100)) return;
+    float T[6];
+    #pragma unroll
+    for (int a = 0; a < 6; a++) T[a] = p.pair_T[pair * 6 + a];
+    const int total = n_sharp + n_flat, n_warps = gridDim.x * (K3T_THREADS / 32);
+    for (int base = (blockIdx.x * (K3T_THREADS / 32) + warp) * 32; base < total; base += n_warps * 32) {   // warp-uniform
+        const int w = base + lane;
+        const bool valid = w < total, sharp = w < n_sharp;
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) q = vlo_to_start(T, sharp ? p.sharp_pts[(size_t)cur * p.cap_sharp + w] : p.flat_pts[(size_t)cur * p.cap_flat + (w - n_sharp)],
+                                    p.deskew, p.inv_period);
+        const GridSet gs = sharp ? p.gc : p.gsf;
+        const float edge = gs.cell - 2e-3f * gs.cell;
+        const float dfast = fminf(25.0f, edge * edge);
+        const int fb_bound = sharp ? (p.fwd_quirk ? min(n_sharp, n_lc) : n_lc) : (p.fwd_quirk ? min(n_flat, n_ls) : n_ls);
+        int i1 = -1, i2 = -1, i3 = -1, ring = 0;
+        #pragma unroll 1
+        for (int stage = 0; stage < 3; stage++) {
+            const bool act = valid && (stage == 0 || i1 >= 0) && (stage < 2 || !sharp);
+            FilterOdom f;
+            f.mode = stage == 0 ? 0 : 1; f.ind = i1; f.fwd_bound = fb_bound;
+            if (stage == 1 && !sharp) { f.ring_lo = ring; f.ring_hi = ring; f.skip_ring = -1; }      // same-ring partner of a flat point
+            else { f.ring_lo = ring - 2; f.ring_hi = ring + 2; f.skip_ring = ring; }
+            unsigned tag = GRID_NOTAG;
+            if (act) {
+                TopKT<1> best;
+                grid_search_thread27(gs, last, q.x, q.y, q.z, dfast, f, best);
+                tag = best.tag[0];
+            }
+            // stages the 27-cell block could not settle: exact warp-cooperative search, one lane's query at a time
+            unsigned redo = __ballot_sync(0xffffffffu, act && tag == GRID_NOTAG && dfast < 25.0f);
+            while (redo) {
+                const int src = __ffs(redo) - 1;
+                redo &= redo - 1u;
+                FilterOdom g;
+                g.mode = __shfl_sync(0xffffffffu, f.mode, src); g.ind = __shfl_sync(0xffffffffu, f.ind, src);
+                g.ring_lo = __shfl_sync(0xffffffffu, f.ring_lo, src); g.ring_hi = __shfl_sync(0xffffffffu, f.ring_hi, src);
+                g.skip_ring = __shfl_sync(0xffffffffu, f.skip_ring, src); g.fwd_bound = __shfl_sync(0xffffffffu, f.fwd_bound, src);
+                const float bx = __shfl_sync(0xffffffffu, q.x, src), by = __shfl_sync(0xffffffffu, q.y, src), bz = __shfl_sync(0xffffffffu, q.z, src);
+                const bool bsharp = __shfl_sync(0xffffffffu, (int)sharp, src) != 0;
+                TopK<1> r;
+                grid_search<1>(bsharp ? p.gc : p.gsf, last, bx, by, bz, 25.0f, g, r, lane, scratch[warp]);
+                if (lane == src) tag = r.tag[0];
+            }
+            const int idx = (act && tag != GRID_NOTAG) ? (int)(tag & 0xFFFFFFu) : -1;
+            if (stage == 0) { i1 = idx; ring = (int)(tag >> 24); }
+            else if (stage == 1) i2 = idx;
+            else i3 = idx;
+        }
+        if (valid) {
+            if (sharp) { int *o = p.cidx + ((size_t)pair * p.cap_sharp + w) * 2; o[0] = i1; o[1] = i2; }
+            else { int *o = p.sidx + ((size_t)pair * p.cap_flat + (w - n_sharp)) * 3; o[0] = i1; o[1] = i2; o[2] = i3; }
+        }
+    }
+}
+
 // Jacobian row of upstream's odometry step (s = 1), expression order as oracle/laser_odometry.c
 __device__ __forceinline__ void odom_jacobian_row(const float *T, const float *trig, float x, float y, float z,
                                                   const float *coeff, float *row, float &bval)
@@ -425,9 +512,12 @@ int vlo_launch_register_pairs(vlo_handle *h, int n_pairs, const float *d_seeds, 
     int ctas = (n_warps * 32 + 255) / 256;
     int fill = (148 * 8 + n_pairs - 1) / n_pairs;
     dim3 ga(std::max(1, std::min(ctas, fill)), n_pairs);
+    // batches: one thread per query (k3_assoc_thread), never more threads than queries
+    dim3 gt(std::max(1, (h->cap_sharp + h->cap_flat + K3T_THREADS - 1) / K3T_THREADS), n_pairs);
     size_t trace_stride = (size_t)n_pairs * (h->cap_sharp * 2 + h->cap_flat * 3);
     for (int base = 0, round = 0; base < c.odom_max_iterations; base += 5, round++) {
-        VLO_PROF(h, ST_ASSOC, (k3_assoc<<<ga, 256, 0, h->stream>>>(p, n_pairs)));
+        if (n_pairs > K3_THREAD_PAIRS) VLO_PROF(h, ST_ASSOC, (k3_assoc_thread<<<gt, K3T_THREADS, 0, h->stream>>>(p, n_pairs)));
+        else VLO_PROF(h, ST_ASSOC, (k3_assoc<<<ga, 256, 0, h->stream>>>(p, n_pairs)));
         if (h->trace && round < 5) {
             int *dst = h->pair_trace + (size_t)round * trace_stride;
             VLO_CUDA(cudaMemcpyAsync(dst, h->pair_cidx, sizeof(int) * (size_t)n_pairs * h->cap_sharp * 2, cudaMemcpyDeviceToDevice, h->stream));
