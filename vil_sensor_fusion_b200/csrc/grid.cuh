@@ -304,11 +304,13 @@ __device__ __forceinline__ void grid_scan_range(const float4 *sorted, int j0, in
         for (int u = 0; u < 4; u++) p[u] = sorted[min(j + u, j1 - 1)];
         #pragma unroll
         for (int u = 0; u < 4; u++) {
-            const float ddx = p[u].x - qx, ddy = p[u].y - qy, ddz = p[u].z - qz;
-            const float d2 = (ddx * ddx + ddy * ddy) + ddz * ddz;
+            // the filter looks at the tag only: candidates it rejects (four of five in a partner search) cost no arithmetic
             unsigned tie; const unsigned tag = __float_as_uint(p[u].w);
-            if (j + u < j1 && d2 < dmax && flt(tag, tie))
-                best.insert(((unsigned long long)__float_as_uint(d2) << 32) | tie, tag);
+            if (j + u < j1 && flt(tag, tie)) {
+                const float ddx = p[u].x - qx, ddy = p[u].y - qy, ddz = p[u].z - qz;
+                const float d2 = (ddx * ddx + ddy * ddy) + ddz * ddz;
+                if (d2 < dmax) best.insert(((unsigned long long)__float_as_uint(d2) << 32) | tie, tag);
+            }
         }
     }
 }
