@@ -97,6 +97,11 @@ typedef struct vlo_config {
     int   io_ratio;                    /* ioRatio 2 (35): the online tick runs LaserMapping on every io_ratio-th sweep */
     int   hessian_order;               /* 0: OptStatus.hessian in LOAM's order (rx ry rz tx ty tz); 1: (tx ty tz rx ry rz), i.e.
                                           block(0,0) really is translation as degerate_odometry_filter.cpp:32-33 labels it */
+    /* ---- MultiScanRegistration input options (loam_params.yaml:4-5,23) ---- */
+    int   rotate_input;                /* rotateInputCloud false (4) */
+    float input_rotation[3];           /* inputCloudRotation [0,0,0] (5): yaw pitch roll (rad); p' = Rz(yaw) Ry(pitch) Rx(roll) p, ROS frame */
+    int   ring_field;                  /* useCloudIntensityandRingFields (23): float index of a FLOAT32 `ring` field inside the point
+                                          (ring ids as delivered by the driver, e.g. Bpearl); -1 = ring from the vertical angle */
 } vlo_config;
 
 /* One registration result = one nav_msgs/Odometry + loam/OptStatus pair of the reference. */

@@ -43,6 +43,8 @@ void orc_default_config(orc_config *c)
     c->map_start_cubes[0] = 50; c->map_start_cubes[1] = 25; c->map_start_cubes[2] = 50;
     c->n_neighbor_cubes = 5;
     c->io_ratio = 2;
+    c->rotate_input = 0; c->input_rotation[0] = c->input_rotation[1] = c->input_rotation[2] = 0.0f;
+    c->ring_field = -1;
 }
 
 /* MultiScanMapper::getRingForAngle: int(((angle*180/M_PI) - lower) * factor + 0.5) */
@@ -54,17 +56,47 @@ static int ring_for_angle(const orc_config *c, float angle)
     return (int)v;
 }
 
+/* rotateInputCloud / inputCloudRotation (gtsam_fusion/config/.../loam_params.yaml:4-5; the code is in the un-vendored fork):
+ * frozen here as R = Rz(yaw) Ry(pitch) Rx(roll) applied to the ROS-frame point, matrix entries in double then rounded to
+ * float, products summed as (r0 x + r1 y) + r2 z. */
+static void input_rotation_matrix(const orc_config *c, float R[9])
+{
+    double cy = cos((double)c->input_rotation[0]), sy = sin((double)c->input_rotation[0]);
+    double cp = cos((double)c->input_rotation[1]), sp = sin((double)c->input_rotation[1]);
+    double cr = cos((double)c->input_rotation[2]), sr = sin((double)c->input_rotation[2]);
+    R[0] = (float)(cy * cp); R[1] = (float)(cy * sp * sr - sy * cr); R[2] = (float)(cy * sp * cr + sy * sr);
+    R[3] = (float)(sy * cp); R[4] = (float)(sy * sp * sr + cy * cr); R[5] = (float)(sy * sp * cr - cy * sr);
+    R[6] = (float)(-sp);     R[7] = (float)(cp * sr);                R[8] = (float)(cp * cr);
+}
+/* ROS-frame x y z of a raw point, rotated when rotateInputCloud is set */
+static inline void ros_point(const orc_config *c, const float *R, const float *p, float *rx, float *ry, float *rz)
+{
+    float x = p[0], y = p[1], z = p[2];
+    if (c->rotate_input) {
+        float ax = (R[0] * x + R[1] * y) + R[2] * z;
+        float ay = (R[3] * x + R[4] * y) + R[5] * z;
+        float az = (R[6] * x + R[7] * y) + R[8] * z;
+        x = ax; y = ay; z = az;
+    }
+    *rx = x; *ry = y; *rz = z;
+}
+
 int orc_organise(const orc_config *c, const float *raw, int n, int stride,
                  orc_pt *out, int *ring_start, int *src_index)
 {
+    float Rm[9];
+    input_rotation_matrix(c, Rm);
     const int R = c->n_rings;
     for (int r = 0; r <= R; r++) ring_start[r] = 0;
     if (n <= 0) return 0;
     int *ring = (int *)malloc(sizeof(int) * (size_t)n);
     float *inten = (float *)malloc(sizeof(float) * (size_t)n);
 
-    float startOri = -orc_atan2f(raw[1], raw[0]);
-    float endOri = -orc_atan2f(raw[(size_t)(n - 1) * stride + 1], raw[(size_t)(n - 1) * stride]) + 2.0f * (float)ORC_PI;
+    float fx, fy, fz, lx, ly, lz;
+    ros_point(c, Rm, raw, &fx, &fy, &fz);
+    ros_point(c, Rm, raw + (size_t)(n - 1) * stride, &lx, &ly, &lz);
+    float startOri = -orc_atan2f(fy, fx);
+    float endOri = -orc_atan2f(ly, lx) + 2.0f * (float)ORC_PI;
     if ((double)(endOri - startOri) > 3 * ORC_PI) endOri = (float)((double)endOri - 2 * ORC_PI);
     else if ((double)(endOri - startOri) < ORC_PI) endOri = (float)((double)endOri + 2 * ORC_PI);
 
@@ -72,12 +104,21 @@ int orc_organise(const orc_config *c, const float *raw, int n, int stride,
     int *count = (int *)calloc((size_t)R, sizeof(int));
     for (int i = 0; i < n; i++) {
         const float *p = raw + (size_t)i * stride;
-        float x = p[1], y = p[2], z = p[0];          /* LOAM frame: x<-y, y<-z, z<-x */
+        float rx, ry, rz;
+        ros_point(c, Rm, p, &rx, &ry, &rz);
+        float x = ry, y = rz, z = rx;                /* LOAM frame: x<-y, y<-z, z<-x */
         ring[i] = -1;
         if (!isfinite(x) || !isfinite(y) || !isfinite(z)) continue;
         if ((x * x + y * y) + z * z < 0.0001f) continue;
-        float angle = orc_atanf(y / sqrtf(x * x + z * z));
-        int id = ring_for_angle(c, angle);
+        int id;
+        if (c->ring_field >= 0) {                    /* ring id as delivered by the driver (useCloudIntensityandRingFields) */
+            float rf = p[c->ring_field];
+            if (!(rf >= 0.0f && rf < (float)R)) continue;       /* also rejects NaN */
+            id = (int)rf;
+        } else {
+            float angle = orc_atanf(y / sqrtf(x * x + z * z));
+            id = ring_for_angle(c, angle);
+        }
         if (id >= R || id < 0) continue;
         float ori = -orc_atan2f(x, z);
         if (!halfPassed) {
@@ -101,7 +142,9 @@ int orc_organise(const orc_config *c, const float *raw, int n, int stride,
         if (ring[i] < 0) continue;
         const float *p = raw + (size_t)i * stride;
         int o = cursor[ring[i]]++;
-        out[o].x = p[1]; out[o].y = p[2]; out[o].z = p[0]; out[o].w = inten[i];
+        float rx, ry, rz;
+        ros_point(c, Rm, p, &rx, &ry, &rz);
+        out[o].x = ry; out[o].y = rz; out[o].z = rx; out[o].w = inten[i];
         if (src_index) src_index[o] = i;
     }
     int total = ring_start[R];

@@ -58,6 +58,9 @@ typedef struct {
     int   map_start_cubes[3];          /* mapStartLocationInCubes [50,25,50] (51) */
     int   n_neighbor_cubes;            /* numNeighborSubmapCubes 5 (52) */
     int   io_ratio;                    /* ioRatio 2 (35): mapping runs on every io_ratio-th sweep */
+    int   rotate_input;                /* rotateInputCloud false (4) */
+    float input_rotation[3];           /* inputCloudRotation [0,0,0] (5): yaw pitch roll (rad), p' = Rz(yaw) Ry(pitch) Rx(roll) p in the ROS frame */
+    int   ring_field;                  /* useCloudIntensityandRingFields (23): float index of a FLOAT32 ring field in the point, -1 = ring from the vertical angle */
 } orc_config;
 
 void orc_default_config(orc_config *c);

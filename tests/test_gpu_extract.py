@@ -131,3 +131,45 @@ def test_pointcloud2_layouts(orc):
         bad = dict(data=np.zeros(30, np.uint8).tobytes(), point_step=10, fields=dict(x=0, y=4, z=8))
         with pytest.raises(api.VloError):
             h.upload_pointcloud2([bad])
+
+
+@pytest.mark.parametrize("opt", ["rotate", "ring_field", "both"])
+def test_input_rotation_and_ring_field_options(orc, opt):
+    """rotateInputCloud / inputCloudRotation and useCloudIntensityandRingFields (loam_params.yaml:4-5,23): organise and the
+    features that follow equal the oracle's bit for bit; the rotation really is Rz(yaw) Ry(pitch) Rx(roll) in the ROS frame;
+    ring ids are taken from the field (reversed order here, with out-of-range / NaN entries that must be dropped)."""
+    from vil_sensor_fusion_b200 import api
+    base = scenes.vlp16_scan(0.0, noise=0.01, seed=3)
+    ocfg0 = orc.default_config("VLP-16")
+    cloud0, _, src0 = orc.organise(ocfg0, base)
+    ring_by_src = np.full(len(base), -1.0, np.float32)
+    ring_by_src[src0] = np.floor(cloud0[:, 3])
+    raw = np.concatenate([base, (15.0 - ring_by_src)[:, None].astype(np.float32)], axis=1)     # stride 5, ring column reversed
+    raw[ring_by_src < 0, 4] = -1.0
+    raw[10:5000:97, 4] = np.nan
+    raw[20:5000:89, 4] = 16.0
+    kw = {}
+    if opt in ("rotate", "both"):
+        kw.update(rotate_input=1, input_rotation=(0.3, -0.1, 0.05))
+    if opt in ("ring_field", "both"):
+        kw.update(ring_field=4)
+    ocfg = orc.default_config("VLP-16", **kw)
+    gcfg = api.default_config("VLP-16", max_scans=2, max_points=65536, **kw)      # 5 floats per point: staging is sized for 4
+    with api.Handle(gcfg) as h:
+        h.upload([raw, raw[::-1].copy()])
+        h.organise()
+        h.extract()
+        fo = _check_scan(orc, h, ocfg, 0, raw)
+        _check_scan(orc, h, ocfg, 1, raw[::-1].copy())
+        cloud_g, rs_g, src_g = h.get_cloud(0)
+    assert len(fo["sharp_idx"]) > 20 and len(fo["flat_idx"]) > 100
+    if opt in ("rotate", "both"):
+        y, p, r = 0.3, -0.1, 0.05
+        Rz = np.array([[np.cos(y), -np.sin(y), 0], [np.sin(y), np.cos(y), 0], [0, 0, 1]])
+        Ry = np.array([[np.cos(p), 0, np.sin(p)], [0, 1, 0], [-np.sin(p), 0, np.cos(p)]])
+        Rx = np.array([[1, 0, 0], [0, np.cos(r), -np.sin(r)], [0, np.sin(r), np.cos(r)]])
+        ros = (Rz @ Ry @ Rx @ raw[src_g, :3].astype(np.float64).T).T
+        np.testing.assert_allclose(cloud_g[:, :3], ros[:, [1, 2, 0]], atol=2e-5)           # LOAM x y z = ROS y z x
+    if opt in ("ring_field", "both"):
+        np.testing.assert_array_equal(np.floor(cloud_g[:, 3]), raw[src_g, 4])                # ring id = the field's value
+        assert not np.any(np.isnan(raw[src_g, 4])) and np.all(raw[src_g, 4] < 16)

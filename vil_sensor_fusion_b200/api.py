@@ -45,6 +45,8 @@ def default_config(lidar: str = "VLP-16", **kw) -> Config:
     for k, v in kw.items():
         if not hasattr(c, k):
             raise AttributeError(k)
+        if k == "input_rotation":
+            v = (C.c_float * 3)(*v)
         setattr(c, k, v)
     return c
 

@@ -5,6 +5,7 @@
 // flag becomes "index of the first valid point whose branch-A orientation passes pi" (a min
 // reduction) and the per-ring push_back becomes a stable 3-kernel counting sort by ring.
 #include "vlo_internal.cuh"
+#include <cmath>
 
 
 struct K0Params {
@@ -13,12 +14,30 @@ struct K0Params {
     int n_rings; float lower_deg, factor, scan_period;
     int N;            // capacity per scan
     int tiles;        // tiles per scan (capacity)
+    int rotate; float R[9];   // rotateInputCloud / inputCloudRotation: R = Rz(yaw) Ry(pitch) Rx(roll), ROS frame
+    int ring_field;   // float index of a FLOAT32 ring field inside the point, -1 = ring from the vertical angle
 };
 
-__device__ __forceinline__ int k0_ring(const K0Params &p, float x, float y, float z)
+// LOAM-frame x / y / z (x = ROS y, y = ROS z, z = ROS x) of a raw point, rotated first when rotateInputCloud is set
+// (oracle: ros_point; products summed as (r0 x + r1 y) + r2 z)
+__device__ __forceinline__ void k0_point(const K0Params &p, const float *q, float &x, float &y, float &z)
+{
+    float rx = q[p.xo], ry = q[p.yo], rz = q[p.zo];
+    if (p.rotate) {
+        const float ax = (p.R[0] * rx + p.R[1] * ry) + p.R[2] * rz;
+        const float ay = (p.R[3] * rx + p.R[4] * ry) + p.R[5] * rz;
+        const float az = (p.R[6] * rx + p.R[7] * ry) + p.R[8] * rz;
+        rx = ax; ry = ay; rz = az;
+    }
+    x = ry; y = rz; z = rx;
+}
+
+// `rf`: the point's ring field when p.ring_field >= 0 (ring ids as delivered by the driver), unused otherwise
+__device__ __forceinline__ int k0_ring(const K0Params &p, float x, float y, float z, float rf)
 {
     if (!isfinite(x) || !isfinite(y) || !isfinite(z)) return -1;
     if ((x * x + y * y) + z * z < 0.0001f) return -1;
+    if (p.ring_field >= 0) return (rf >= 0.0f && rf < (float)p.n_rings) ? (int)rf : -1;      // also rejects NaN
     float angle = vlo_atanf(y / sqrtf(x * x + z * z));
     float a180 = angle * 180.0f;
     double v = ((double)a180 / VLO_PI_D - (double)p.lower_deg) * (double)p.factor + 0.5;
@@ -36,8 +55,11 @@ __global__ void k0_bounds(K0Params p, float *ori_bounds, int *first_half, int n_
     first_half[b] = 0x7fffffff;
     if (o1 <= o0) { ori_bounds[2 * b] = 0.f; ori_bounds[2 * b + 1] = 0.f; return; }
     const float *f = p.raw + (size_t)o0 * p.stride, *l = p.raw + (size_t)(o1 - 1) * p.stride;
-    float startOri = -vlo_atan2f(f[p.yo], f[p.xo]);
-    float endOri = -vlo_atan2f(l[p.yo], l[p.xo]) + 2.0f * (float)VLO_PI_D;
+    float fx, fy, fz, lx, ly, lz;                 // LOAM x = ROS y, LOAM z = ROS x
+    k0_point(p, f, fx, fy, fz);
+    k0_point(p, l, lx, ly, lz);
+    float startOri = -vlo_atan2f(fx, fz);
+    float endOri = -vlo_atan2f(lx, lz) + 2.0f * (float)VLO_PI_D;
     if ((double)(endOri - startOri) > 3 * VLO_PI_D) endOri = (float)((double)endOri - 2 * VLO_PI_D);
     else if ((double)(endOri - startOri) < VLO_PI_D) endOri = (float)((double)endOri + 2 * VLO_PI_D);
     ori_bounds[2 * b] = startOri; ori_bounds[2 * b + 1] = endOri;
@@ -61,8 +83,9 @@ __global__ void __launch_bounds__(K0_TILE) k0_classify(K0Params p, const float *
     int i = tile * K0_TILE + tid;
     if (i < n) {
         const float *q = p.raw + (size_t)(o0 + i) * p.stride;
-        float x = q[p.yo], y = q[p.zo], z = q[p.xo];
-        int ring = k0_ring(p, x, y, z);
+        float x, y, z;
+        k0_point(p, q, x, y, z);
+        int ring = k0_ring(p, x, y, z, p.ring_field >= 0 ? q[p.ring_field] : 0.0f);
         ring_of[(size_t)b * p.N + i] = (int8_t)ring;            // the scatter pass reuses ring and raw orientation
         if (ring >= 0) {
             atomicAdd(&hist[ring], 1);
@@ -130,7 +153,7 @@ __global__ void __launch_bounds__(K0_TILE) k0_scatter(K0Params p, const float *o
     int ring = -1; float x = 0.f, y = 0.f, z = 0.f;
     if (i < n) {
         const float *q = p.raw + (size_t)(o0 + i) * p.stride;
-        x = q[p.yo]; y = q[p.zo]; z = q[p.xo];
+        k0_point(p, q, x, y, z);
         ring = ring_of[(size_t)b * p.N + i];
     }
     unsigned mask = __match_any_sync(0xffffffffu, ring);
@@ -194,6 +217,18 @@ int vlo_launch_organise(vlo_handle *h)
     p.n_rings = h->cfg.n_rings; p.lower_deg = h->cfg.lower_deg;
     p.factor = (float)(h->cfg.n_rings - 1) / (h->cfg.upper_deg - h->cfg.lower_deg);
     p.scan_period = h->cfg.scan_period; p.N = h->cfg.max_points; p.tiles = h->tiles_per_scan;
+    {
+        // same expression, in double, as the oracle's input_rotation_matrix
+        const vlo_config &c = h->cfg;
+        const double cy = cos((double)c.input_rotation[0]), sy = sin((double)c.input_rotation[0]);
+        const double cp = cos((double)c.input_rotation[1]), sp = sin((double)c.input_rotation[1]);
+        const double cr = cos((double)c.input_rotation[2]), sr = sin((double)c.input_rotation[2]);
+        p.R[0] = (float)(cy * cp); p.R[1] = (float)(cy * sp * sr - sy * cr); p.R[2] = (float)(cy * sp * cr + sy * sr);
+        p.R[3] = (float)(sy * cp); p.R[4] = (float)(sy * sp * sr + cy * cr); p.R[5] = (float)(sy * sp * cr - cy * sr);
+        p.R[6] = (float)(-sp);     p.R[7] = (float)(cp * sr);                p.R[8] = (float)(cp * cr);
+        p.rotate = c.rotate_input ? 1 : 0;
+        p.ring_field = (c.ring_field >= 0 && c.ring_field < sb.stride) ? c.ring_field : -1;
+    }
     int B = sb.scan_count; p.scan_first = sb.scan_first;
     vlo_prof_begin(h, ST_ORGANISE);
     k0_bounds<<<(B + 127) / 128, 128, 0, h->stream>>>(p, sb.ori_bounds, sb.first_half, B);
