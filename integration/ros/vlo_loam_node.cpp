@@ -48,6 +48,21 @@ int main(int argc, char **argv) {
   vlo_config c; vlo_default_config(&c);
   std::string lidar = "VLP-16"; nh.getParam("lidar", lidar); vlo_set_lidar(&c, lidar.c_str());   // loam_params.yaml:22
   nh.getParam("scanPeriod", c.scan_period); nh.getParam("featureRegions", c.feature_regions);    // :3,25 ... same names
+  nh.getParam("curvatureRegion", c.curvature_region); nh.getParam("maxCornerSharp", c.max_corner_sharp);             // :26-27
+  nh.getParam("maxCornerLessSharp", c.max_corner_less_sharp); nh.getParam("maxSurfaceFlat", c.max_surface_flat);    // :28-29
+  nh.getParam("surfaceCurvatureThreshold", c.surface_curvature_threshold);                                         // :30
+  nh.getParam("lessFlatFilterSize", c.less_flat_filter_size);                                                      // :31
+  bool undistort = true, rotate = false, ring_fields = false;
+  nh.getParam("undistortInputCloud", undistort); c.deskew = undistort ? 1 : 0;                                     // :34
+  nh.getParam("odomMaxIterations", c.odom_max_iterations); nh.getParam("odomDeltaTAbort", c.odom_delta_t_abort);    // :36-37
+  nh.getParam("odomDeltaRAbort", c.odom_delta_r_abort);                                                            // :38
+  nh.getParam("mapMaxIterations", c.map_max_iterations); nh.getParam("mapDeltaTAbort", c.map_delta_t_abort);        // :44-45
+  nh.getParam("mapDeltaRAbort", c.map_delta_r_abort);                                                              // :46
+  std::vector<double> ypr;                                                                                         // :4-5
+  nh.getParam("rotateInputCloud", rotate); c.rotate_input = rotate ? 1 : 0;
+  if (nh.getParam("inputCloudRotation", ypr) && ypr.size() == 3) for (int i = 0; i < 3; i++) c.input_rotation[i] = (float)ypr[i];
+  // :23 useCloudIntensityandRingFields: ring ids from the cloud's FLOAT32 `ring` field; x y z intensity ring -> float index 4
+  nh.getParam("useCloudIntensityandRingFields", ring_fields); c.ring_field = ring_fields ? 4 : -1;
   nh.getParam("odomDegenEigVal", c.odom_degen_eig); nh.getParam("mapDegenEigVal", c.map_degen_eig); // :39,53
   nh.getParam("cornerFilterSize", c.corner_filter_size); nh.getParam("surfaceFilterSize", c.surface_filter_size);   // :47-48
   nh.getParam("mapCubeSize", c.map_cube_size); nh.getParam("numNeighborSubmapCubes", c.n_neighbor_cubes);          // :49,52
