@@ -316,3 +316,48 @@ def test_laser_map_maintenance_semantics(orc):
     assert np.array_equal(lm.window(), [2, 3, 3]) or lm.window()[0] < 3
     assert np.any(after & (1 << 30)) and np.count_nonzero(after & (1 << 30)) < len(after)
     lm.close()
+
+
+def test_organise_input_rotation_and_ring_field(orc):
+    """rotateInputCloud / inputCloudRotation and useCloudIntensityandRingFields (loam_params.yaml:4-5,23) in the oracle:
+    organising with the rotation option equals organising a cloud that numpy rotated by Rz(yaw) Ry(pitch) Rx(roll)
+    beforehand (same rings, same order, coordinates to float rounding); with a ring field the ids come from the field,
+    out-of-range and NaN entries are dropped, and the order inside a ring is still the arrival order."""
+    raw = scenes.vlp16_scan(0.0, noise=0.01, seed=3, n_az=600)
+    y, p, r = 0.3, -0.1, 0.05
+    Rz = np.array([[np.cos(y), -np.sin(y), 0], [np.sin(y), np.cos(y), 0], [0, 0, 1]])
+    Ry = np.array([[np.cos(p), 0, np.sin(p)], [0, 1, 0], [-np.sin(p), 0, np.cos(p)]])
+    Rx = np.array([[1, 0, 0], [0, np.cos(r), -np.sin(r)], [0, np.sin(r), np.cos(r)]])
+    pre = raw.copy()
+    pre[:, :3] = (Rz @ Ry @ Rx @ raw[:, :3].astype(np.float64).T).T.astype(np.float32)
+    c_rot, rs_rot, src_rot = orc.organise(orc.default_config("VLP-16", rotate_input=1, input_rotation=(y, p, r)), raw)
+    c_pre, rs_pre, src_pre = orc.organise(orc.default_config("VLP-16"), pre)
+    # a point within float rounding of a ring boundary may change ring between the two; everything else must agree
+    assert abs(len(c_rot) - len(c_pre)) <= 2
+    common = np.intersect1d(src_rot, src_pre)
+    assert len(common) >= len(src_rot) - 4
+    pos_rot = np.full(len(raw), -1); pos_rot[src_rot] = np.arange(len(src_rot))
+    pos_pre = np.full(len(raw), -1); pos_pre[src_pre] = np.arange(len(src_pre))
+    a, b = c_rot[pos_rot[common]], c_pre[pos_pre[common]]
+    np.testing.assert_allclose(a[:, :3], b[:, :3], atol=2e-5)
+    assert np.mean(np.floor(a[:, 3]) == np.floor(b[:, 3])) > 0.999
+    # identity rotation with the flag on changes nothing, bit for bit
+    c_id, rs_id, src_id = orc.organise(orc.default_config("VLP-16", rotate_input=1), raw)
+    c_0, rs_0, src_0 = orc.organise(orc.default_config("VLP-16"), raw)
+    np.testing.assert_array_equal(src_id, src_0)
+    np.testing.assert_array_equal(c_id.view(np.uint32), c_0.view(np.uint32))
+    # ring field: reversed ids, some invalid
+    ring_by_src = np.full(len(raw), -1.0, np.float32)
+    ring_by_src[src_0] = np.floor(c_0[:, 3])
+    raw5 = np.concatenate([raw, (15.0 - ring_by_src)[:, None].astype(np.float32)], axis=1)
+    raw5[ring_by_src < 0, 4] = -1.0
+    raw5[7::101, 4] = np.nan
+    raw5[11::103, 4] = 16.0
+    c_f, rs_f, src_f = orc.organise(orc.default_config("VLP-16", ring_field=4), raw5)
+    np.testing.assert_array_equal(np.floor(c_f[:, 3]), raw5[src_f, 4])
+    assert np.all(np.isfinite(raw5[src_f, 4])) and np.all((raw5[src_f, 4] >= 0) & (raw5[src_f, 4] < 16))
+    for ring in range(16):
+        seg = src_f[rs_f[ring]:rs_f[ring + 1]]
+        assert np.all(np.diff(seg) > 0)                                   # arrival order inside a ring
+    valid = np.isfinite(raw5[:, 4]) & (raw5[:, 4] >= 0) & (raw5[:, 4] < 16)
+    assert len(src_f) == int(valid.sum())
