@@ -2,14 +2,17 @@
 // Replaces BasicLaserMapping::optimizeTransformTobeMapped of the `loam` nodelet
 // (gtsam_fusion/launch/loam.launch:47-52; knobs loam_params.yaml:44-46,53); SURVEY.md Appendix A.8 is
 // the algorithm, oracle/laser_mapping.c the frozen operation order.  Per Gauss-Newton iteration:
-//   k5_tile  one thread per feature point: pointAssociateToMap + exact 5-NN (d2 < 1) on the map
-//            grid (grid.cuh grid_search_thread: nearest-first cell walk with box pruning), then
-//            3x3 covariance eigen (corner) / 5x3 least-squares plane (surface), residual, Jacobian
-//            row, 28 products; level-1 sums of the R1 reduction per 32 consecutive points
-//   k5_solve_slot  one CTA per scan: levels 2/3 of R1 in fixed order, QR solve, (iteration 0) single-warp
-//            Jacobi degeneracy test + remapping, pose update, convergence flag, result record
-// k5_register_coop runs both inside ONE cooperative launch with grid syncs between the phases: the
-// Gauss-Newton loop lives on the device and ends there.
+//   k5_tile<MODE>  one thread per feature point of a 32-point warp tile: pointAssociateToMap + exact 5-NN (d2 < 1) on
+//            the map grid (grid.cuh grid_search_thread27: per-lane 27-cell work mask, nearest-first, box pruning), then
+//            3x3 covariance eigen (corner) / 5x3 least-squares plane (surface), residual, Jacobian row, 28 products;
+//            level-1 sums of the R1 reduction per tile
+//   solve    levels 2/3 of R1 in fixed order, QR solve, (iteration 0) Jacobi degeneracy test + remapping, pose update,
+//            convergence, result record -- by a CTA (k5_solve_slot) or by a single warp (k5_solve_slot_warp)
+// Two launch strategies over the same device functions:
+//   batches      k5_assoc (association) + k5_lin (linearisation; the warp completing a slot's last tile solves it) per
+//                iteration, persistent grids over one flat ticketed tile list of the unconverged slots
+//   online tick  k5_register_coop: everything in ONE cooperative launch with grid syncs between the phases -- the
+//                Gauss-Newton loop lives on the device and ends there
 #include "grid.cuh"
 #include "dense6.cuh"
 #include <algorithm>
@@ -708,6 +711,10 @@ int vlo_launch_register_map(vlo_handle *h, const int *d_scans, int n, const floa
         const int ctas_a = (int)std::max<long long>(1, std::min<long long>((long long)sms * std::max(1, occ_a), want));
         const int ctas_l = (int)std::max<long long>(1, std::min<long long>((long long)sms * std::max(1, occ_l), want));
         const size_t dyn = sizeof(int) * (2 * (size_t)n + 2);
+        if (dyn > 24 * 1024) {          // the slot list lives in shared memory next to 22 KB of static scratch
+            h->err = "vlo_register_map: at most 3000 scans per call (split the batch)";
+            return VLO_ERR_CAPACITY;
+        }
         for (int it = 0; it < c.map_max_iterations; it++) {
             VLO_PROF(h, ST_MAP_ASSOC, (k5_assoc<<<ctas_a, KNN_THREADS, dyn, h->stream>>>(p, it, n)));
             VLO_PROF(h, ST_MAP_LIN, (k5_lin<<<ctas_l, KNN_THREADS, dyn, h->stream>>>(p, it, n)));
