@@ -23,3 +23,7 @@ for K in k5_assoc k5_lin k1_extract k1c_lessflat k0_scatter; do
       python bench.py --steps 1 --warmup 3 --batch 128 --no-cpu-baseline --no-latency > $OUT/ncu_$K.log 2>&1
   ls -la $OUT/full_$K.ncu-rep
 done
+echo "== whole-bag leg: full capture of the batch scan-to-scan association"
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:^k3_assoc_thread -s 1 -c 1 -f -o $OUT/full_k3_assoc_thread \
+    python tools/pairs_profile.py > $OUT/ncu_k3_assoc_thread.log 2>&1
+ls -la $OUT/full_k3_assoc_thread.ncu-rep
