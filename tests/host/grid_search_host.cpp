@@ -1,0 +1,111 @@
+// TEST INFRASTRUCTURE -- host emulation of the thread-level voxel-hash searches of vil_sensor_fusion_b200/csrc/grid.cuh.
+// The header is compiled as-is for the CPU (g++, -ffp-contract=off like nvcc --fmad=false): the CUDA qualifiers come
+// from <cuda_runtime.h>, the handful of device intrinsics the thread-level code uses are defined below, and the warp
+// collectives (used only by functions this harness never calls) are declared so that the header parses.
+// What it checks (tests/test_host_grid_search.py): grid_search_thread27 and grid_search_thread return exactly the
+// (d2, tie)-lexicographic top-K of a brute-force scan -- K = 5 plain (scan-to-map) and K = 1 with the partner filter
+// (scan-to-scan) -- on clouds with duplicates and lattice ties, for queries inside, at the border of and outside the
+// populated cells, with and without a caller-supplied bound.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
+template <class T> static inline T __ldg(const T *p) { return *p; }
+template <class T> static inline T __ldcg(const T *p) { return *p; }
+// warp collectives: never executed here
+template <class T> T __shfl_sync(unsigned, T v, int) { return v; }
+template <class T> T __shfl_up_sync(unsigned, T v, int) { return v; }
+template <class T> T __shfl_down_sync(unsigned, T v, int) { return v; }
+static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
+static inline unsigned __reduce_min_sync(unsigned, unsigned v) { return v; }
+static inline unsigned __reduce_max_sync(unsigned, unsigned v) { return v; }
+static inline int __reduce_min_sync(unsigned, int v) { return v; }
+static inline int __reduce_max_sync(unsigned, int v) { return v; }
+static inline int __reduce_add_sync(unsigned, int v) { return v; }
+static inline unsigned __match_any_sync(unsigned, int) { return 1u; }
+static inline void __syncwarp(unsigned = 0xffffffffu) {}
+static inline int __any_sync(unsigned, int p) { return p; }
+static inline int __all_sync(unsigned, int p) { return p; }
+
+#include "../../vil_sensor_fusion_b200/csrc/grid.cuh"
+
+// ---- host build of one grid (same layout contract as k2_grid.cu: keys / start / sorted, tag = ring << 24 | dense index)
+struct HostGrid {
+    GridSet gs;
+    std::vector<unsigned long long> keys; std::vector<int> cnt, start; std::vector<float4> sorted;
+};
+static void build_grid(HostGrid &g, const float *pts, const int *ring, int n, float cell)
+{
+    int ts = 1024; while (ts < 4 * n) ts <<= 1;
+    g.keys.assign(ts, GRID_EMPTY); g.cnt.assign(ts, 0); g.start.assign(ts + 1, 0); g.sorted.resize(n > 0 ? n : 1);
+    g.gs.cell = cell; g.gs.inv_cell = 1.0f / cell; g.gs.ts = ts; g.gs.max_pts = n; g.gs.G = 1;
+    std::vector<int> slot_of(n);
+    for (int i = 0; i < n; i++) {
+        int ix = (int)floorf(pts[4 * i] * g.gs.inv_cell), iy = (int)floorf(pts[4 * i + 1] * g.gs.inv_cell), iz = (int)floorf(pts[4 * i + 2] * g.gs.inv_cell);
+        unsigned long long key = grid_key(ix, iy, iz);
+        int slot = (int)(grid_hash(ix, iy, iz) & (unsigned)(ts - 1));
+        while (g.keys[slot] != GRID_EMPTY && g.keys[slot] != key) slot = (slot + 1) & (ts - 1);
+        g.keys[slot] = key; g.cnt[slot]++; slot_of[i] = slot;
+    }
+    for (int s = 0; s < ts; s++) g.start[s + 1] = g.start[s] + g.cnt[s];
+    std::vector<int> cur(g.start.begin(), g.start.end() - 1);
+    // storage order inside a cell must not matter: fill back to front
+    for (int i = n - 1; i >= 0; i--) {
+        unsigned tag = ((unsigned)ring[i] << 24) | (unsigned)i;
+        g.sorted[cur[slot_of[i]]++] = make_float4(pts[4 * i], pts[4 * i + 1], pts[4 * i + 2], __uint_as_float(tag));
+    }
+    g.gs.keys = g.keys.data(); g.gs.cnt = g.cnt.data(); g.gs.start = g.start.data(); g.gs.sorted = g.sorted.data(); g.gs.bsum = nullptr;
+}
+
+extern "C" {
+// plain K-NN (FilterAll), K = 5: mode 0 = grid_search_thread27 (cell must be >= sqrt(dmax)), 1 = grid_search_thread (any cell),
+// bound_mode 1: pass the exact K-th distance of a brute-force pass as the caller's bound (what k5 does from iteration 1 on)
+int host_knn5(const float *pts, int n, float cell, const float *q, int nq, float dmax, int mode, int bound_mode, int *idx_out, float *d2_out)
+{
+    std::vector<int> ring(n, 0);
+    HostGrid g; build_grid(g, pts, ring.data(), n, cell);
+    for (int k = 0; k < nq; k++) {
+        float qx = q[3 * k], qy = q[3 * k + 1], qz = q[3 * k + 2];
+        float bound = -1.0f;
+        if (bound_mode) {
+            std::vector<float> d;
+            for (int i = 0; i < n; i++) { float dx = pts[4 * i] - qx, dy = pts[4 * i + 1] - qy, dz = pts[4 * i + 2] - qz; float d2 = (dx * dx + dy * dy) + dz * dz; if (d2 < dmax) d.push_back(d2); }
+            if (d.size() >= 5) { std::sort(d.begin(), d.end()); bound = d[4]; }
+        }
+        TopKI<5> best;
+        if (mode == 0) grid_search_thread27(g.gs, 0, qx, qy, qz, dmax, FilterAll(), best, bound);
+        else grid_search_thread(g.gs, 0, qx, qy, qz, dmax, grid_thread_rho(cell, dmax), FilterAll(), best, bound);
+        for (int j = 0; j < 5; j++) {
+            idx_out[5 * k + j] = best.valid(j) ? best.index(j) : -1;
+            d2_out[5 * k + j] = __uint_as_float((unsigned)(best.key[j] >> 32));
+        }
+    }
+    return 0;
+}
+// filtered 1-NN with upstream's partner rules (FilterPartner): the 27-cell search limited to one cell edge, as
+// k3_assoc_thread uses it; returns -2 where that search cannot decide (the kernel falls back to the exact warp search)
+int host_partner(const float *pts, const int *ring, int n, float cell, const float *q, int nq, const int *ind, const int *ring_lo,
+                 const int *ring_hi, const int *skip, int fwd_bound, int *idx_out)
+{
+    HostGrid g; build_grid(g, pts, ring, n, cell);
+    const float edge = cell - 2e-3f * cell, dfast = fminf(25.0f, edge * edge);
+    for (int k = 0; k < nq; k++) {
+        FilterPartner f; f.ind = ind[k]; f.ring_lo = ring_lo[k]; f.ring_hi = ring_hi[k]; f.skip_ring = skip[k]; f.fwd_bound = fwd_bound;
+        TopKT<1> best;
+        grid_search_thread27(g.gs, 0, q[3 * k], q[3 * k + 1], q[3 * k + 2], dfast, f, best);
+        idx_out[k] = best.tag[0] != GRID_NOTAG ? (int)(best.tag[0] & 0xFFFFFFu) : (dfast < 25.0f ? -2 : -1);
+    }
+    return 0;
+}
+}

@@ -1,0 +1,131 @@
+"""Host emulation of the thread-level voxel-hash searches (csrc/grid.cuh compiled for the CPU, tests/host/): exactness
+against a brute-force scan.  Runs without a GPU, so the search logic behind the scan-to-map (k5_assoc) and batch
+scan-to-scan (k3_assoc_thread) association is checked on every CPU run as well as by the -m gpu parity tests."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "host", "grid_search_host.cpp")
+OUT = os.path.join(ROOT, "tests", "host", "_build", "libgridhost.so")
+
+
+@pytest.fixture(scope="module")
+def gh():
+    inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    if not os.path.exists(os.path.join(inc, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    deps = [SRC, os.path.join(ROOT, "vil_sensor_fusion_b200", "csrc", "grid.cuh"), os.path.join(ROOT, "vil_sensor_fusion_b200", "csrc", "vlo_internal.cuh")]
+    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
+        os.makedirs(os.path.dirname(OUT), exist_ok=True)
+        # -ffp-contract=off mirrors nvcc --fmad=false: d2 = ((dx*dx) + (dy*dy)) + (dz*dz) in separate IEEE operations
+        subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-I" + inc, SRC, "-o", OUT], check=True)
+    return C.CDLL(OUT)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _d2(pts, q):
+    d = pts[:, :3] - q[None, :3]
+    return (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]          # float32, same operation order
+
+
+def _brute_knn5(pts, q, dmax):
+    idx = np.full((len(q), 5), -1, np.int32)
+    d2o = np.full((len(q), 5), np.float32(dmax), np.float32)
+    for k in range(len(q)):
+        d2 = _d2(pts, q[k])
+        ok = np.nonzero(d2 < np.float32(dmax))[0]
+        if len(ok) >= 5:                                   # the kernels use the result only when all five exist
+            order = ok[np.lexsort((ok, d2[ok].view(np.uint32)))][:5]
+            idx[k] = order
+            d2o[k] = d2[order]
+    return idx, d2o
+
+
+def _map_like_cloud(rng, n_side=60):
+    # a floor and two walls on a 0.4 m lattice with jitter, exact duplicates and an empty region
+    g = (np.arange(n_side, dtype=np.float32) * np.float32(0.4)) - np.float32(12.0)
+    xx, yy = np.meshgrid(g, g)
+    floor = np.stack([xx.ravel(), np.full(xx.size, -1.0, np.float32), yy.ravel()], 1)
+    wall = np.stack([xx.ravel(), yy.ravel() * np.float32(0.25) + np.float32(2.0), np.full(xx.size, 7.3, np.float32)], 1)
+    wall2 = np.stack([np.full(xx.size, -5.05, np.float32), yy.ravel() * np.float32(0.25) + np.float32(2.0), xx.ravel()], 1)
+    pts = np.concatenate([floor, wall, wall2]).astype(np.float32)
+    pts[::3] += rng.normal(0, 0.03, (len(pts[::3]), 3)).astype(np.float32)
+    pts[100:160] = pts[0:60]                                # exact duplicates: ties resolved by the lower index
+    return np.concatenate([pts, np.zeros((len(pts), 1), np.float32)], 1)
+
+
+@pytest.mark.parametrize("mode,cell", [(0, 1.0625), (0, 1.5), (1, 1.0625), (1, 0.6), (1, 0.31)])
+@pytest.mark.parametrize("bound_mode", [0, 1])
+def test_thread_knn5_is_exact(gh, mode, cell, bound_mode):
+    rng = np.random.default_rng(7)
+    pts = _map_like_cloud(rng)
+    q = pts[rng.choice(len(pts), 700, replace=False), :3].copy()
+    q[:500] += rng.normal(0, 0.2, (500, 3)).astype(np.float32)          # near the surfaces
+    q[500:560] = pts[0:60, :3]                                            # d2 = 0 ties between i and i + 100
+    q[560:600] += np.float32(40.0)                                        # nothing within range
+    q[600:650, 1] += np.float32(0.9)                                      # about one search radius away: fewer than 5 in range
+    # cell-border cases: queries on exact multiples of the cell edge
+    q[650:700] = (np.round(q[650:700] / np.float32(cell)) * np.float32(cell)).astype(np.float32)
+    q = np.ascontiguousarray(q, np.float32)
+    idx = np.zeros((len(q), 5), np.int32)
+    d2 = np.zeros((len(q), 5), np.float32)
+    gh.host_knn5(_p(pts), len(pts), C.c_float(cell), _p(q), len(q), C.c_float(1.0), mode, bound_mode, _p(idx), _p(d2))
+    bi, bd = _brute_knn5(pts, q, 1.0)
+    full = bi[:, 4] >= 0
+    assert full.sum() > 400 and (~full).sum() > 30
+    np.testing.assert_array_equal(idx[full], bi[full])
+    np.testing.assert_array_equal(d2[full].view(np.uint32), bd[full].view(np.uint32))
+    assert np.all(idx[~full][:, 4] == -1)                                 # fewer than five within range: flagged, never invented
+
+
+def test_partner_search_fast_path_is_exact_or_undecided(gh):
+    """k3_assoc_thread's stage search: a hit of the 27-cell search limited to one cell edge is the global filtered
+    (d2, tie) minimum; where it reports 'undecided' no admissible candidate exists inside that radius."""
+    rng = np.random.default_rng(11)
+    n_rings, per = 16, 400
+    az = np.linspace(-np.pi, np.pi, per, endpoint=False, dtype=np.float32)
+    pts, ring = [], []
+    for r in range(n_rings):                                              # ring-major cloud, like a less-flat cloud
+        rad = np.float32(6.0) + np.float32(0.3) * rng.standard_normal(per).astype(np.float32)
+        el = np.float32(np.deg2rad(-15 + 2 * r))
+        pts.append(np.stack([rad * np.cos(az), rad * np.tan(el) * np.ones_like(az), rad * np.sin(az), np.zeros_like(az)], 1))
+        ring.append(np.full(per, r, np.int32))
+    pts = np.ascontiguousarray(np.concatenate(pts), np.float32)
+    ring = np.ascontiguousarray(np.concatenate(ring), np.int32)
+    n = len(pts)
+    nq = 600
+    src = rng.choice(n, nq, replace=False)
+    q = np.ascontiguousarray(pts[src, :3] + rng.normal(0, 0.05, (nq, 3)).astype(np.float32), np.float32)
+    ind = src.astype(np.int32)                                            # "nearest neighbour" = the point the query came from
+    same = rng.random(nq) < 0.4                                           # same-ring partner vs adjacent-ring partner
+    lo = np.where(same, ring[src], ring[src] - 2).astype(np.int32)
+    hi = np.where(same, ring[src], ring[src] + 2).astype(np.int32)
+    skip = np.where(same, -1, ring[src]).astype(np.int32)
+    for cell, fwd in ((0.7, n), (0.35, n), (1.0, n // 2)):
+        out = np.zeros(nq, np.int32)
+        gh.host_partner(_p(pts), _p(ring), n, C.c_float(cell), _p(q), nq, _p(ind), _p(lo), _p(hi), _p(skip), fwd, _p(out))
+        edge = np.float32(cell) - np.float32(2e-3) * np.float32(cell)
+        dfast = min(np.float32(25.0), edge * edge)
+        decided = 0
+        for k in range(nq):
+            d2 = _d2(pts, q[k])
+            idx = np.arange(n)
+            ok = (ring >= lo[k]) & (ring <= hi[k]) & (ring != skip[k]) & (idx != ind[k]) & ((idx < ind[k]) | (idx < fwd)) & (d2 < np.float32(25.0))
+            best = -1
+            if ok.any():
+                c = idx[ok]
+                tie = np.where(c > ind[k], c - ind[k], 0x40000000 + (ind[k] - c)).astype(np.int64)
+                best = c[np.lexsort((tie, d2[c].view(np.uint32)))][0]
+            if best >= 0 and d2[best] < dfast:
+                assert out[k] == best, (cell, k, out[k], best)
+                decided += 1
+            else:
+                assert out[k] == -2, (cell, k, out[k], best)
+        assert decided > nq // 3
