@@ -39,6 +39,9 @@ static inline int __any_sync(unsigned, int p) { return p; }
 static inline int __all_sync(unsigned, int p) { return p; }
 
 #include "../../vil_sensor_fusion_b200/csrc/grid.cuh"
+extern "C" {
+#include "../../oracle/detmath.h"
+}
 
 // ---- host build of one grid (same layout contract as k2_grid.cu: keys / start / sorted, tag = ring << 24 | dense index)
 struct HostGrid {
@@ -107,5 +110,21 @@ int host_partner(const float *pts, const int *ring, int n, float cell, const flo
         idx_out[k] = best.tag[0] != GRID_NOTAG ? (int)(best.tag[0] & 0xFFFFFFu) : (dfast < 25.0f ? -2 : -1);
     }
     return 0;
+}
+
+// D1 of DESIGN.md: the product's deterministic sin/cos/atan/atan2 (vlo_internal.cuh) and the oracle's (oracle/detmath.h) are
+// two texts of the same operation sequence -- count the inputs on which they differ in any bit
+static inline bool same_bits(float a, float b) { return __float_as_uint(a) == __float_as_uint(b) || (a != a && b != b); }
+long host_detmath_mismatches(const float *x, const float *y, long n)
+{
+    long bad = 0;
+    for (long i = 0; i < n; i++) {
+        float s1, c1, s2, c2;
+        vlo_sincosf(x[i], s1, c1); orc_sincosf(x[i], &s2, &c2);
+        if (!same_bits(s1, s2) || !same_bits(c1, c2)) bad++;
+        if (!same_bits(vlo_atanf(x[i]), orc_atanf(x[i]))) bad++;
+        if (!same_bits(vlo_atan2f(y[i], x[i]), orc_atan2f(y[i], x[i]))) bad++;
+    }
+    return bad;
 }
 }

@@ -18,7 +18,8 @@ def gh():
     inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
     if not os.path.exists(os.path.join(inc, "cuda_runtime.h")):
         pytest.skip("CUDA headers not found")
-    deps = [SRC, os.path.join(ROOT, "vil_sensor_fusion_b200", "csrc", "grid.cuh"), os.path.join(ROOT, "vil_sensor_fusion_b200", "csrc", "vlo_internal.cuh")]
+    deps = [SRC, os.path.join(ROOT, "vil_sensor_fusion_b200", "csrc", "grid.cuh"), os.path.join(ROOT, "vil_sensor_fusion_b200", "csrc", "vlo_internal.cuh"),
+            os.path.join(ROOT, "oracle", "detmath.h")]
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
         # -ffp-contract=off mirrors nvcc --fmad=false: d2 = ((dx*dx) + (dy*dy)) + (dz*dz) in separate IEEE operations
@@ -129,3 +130,17 @@ def test_partner_search_fast_path_is_exact_or_undecided(gh):
             else:
                 assert out[k] == -2, (cell, k, out[k], best)
         assert decided > nq // 3
+
+
+def test_detmath_product_text_equals_oracle_text(gh):
+    """D1: vlo_sincosf / vlo_atanf / vlo_atan2f of csrc/vlo_internal.cuh and orc_* of oracle/detmath.h, both
+    compiled without FMA contraction, agree bit for bit on two million inputs (angles, slopes, huge and tiny values,
+    signed zeros, infinities, NaN)."""
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.uniform(-7, 7, 600000), rng.standard_normal(400000) * 1e3, rng.standard_normal(400000) * 1e-4,
+                        np.float32(10.0) ** rng.uniform(-30, 30, 400000) * rng.choice([-1, 1], 400000),
+                        [0.0, -0.0, np.inf, -np.inf, np.nan, 1.0, -1.0, 2.414213562373095, 0.4142135623730950]]).astype(np.float32)
+    y = rng.permutation(x).astype(np.float32)
+    gh.host_detmath_mismatches.restype = C.c_long
+    bad = gh.host_detmath_mismatches(_p(x), _p(y), C.c_long(len(x)))
+    assert bad == 0, bad
