@@ -19,6 +19,7 @@ static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); re
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+using std::isfinite;                      // CUDA's global overloads
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 template <class T> static inline T __ldg(const T *p) { return *p; }
@@ -39,6 +40,8 @@ static inline int __any_sync(unsigned, int p) { return p; }
 static inline int __all_sync(unsigned, int p) { return p; }
 
 #include "../../vil_sensor_fusion_b200/csrc/grid.cuh"
+#include "../../vil_sensor_fusion_b200/csrc/dense6.cuh"
+#include "../../vil_sensor_fusion_b200/csrc/map_lin.cuh"
 extern "C" {
 #include "../../oracle/detmath.h"
 }
@@ -126,5 +129,29 @@ long host_detmath_mismatches(const float *x, const float *y, long n)
         if (!same_bits(vlo_atan2f(y[i], x[i]), orc_atan2f(y[i], x[i]))) bad++;
     }
     return bad;
+}
+
+// the scan-to-map linearisation of csrc/map_lin.cuh and the 6x6 solve of csrc/dense6.cuh, one call per input set
+void host_eig3(const float *A9, float *eval3, float *evec9) { eig3_jacobi(A9, eval3, evec9); }
+void host_lstsq53(const float *A15, float *x3) { lstsq53(reinterpret_cast<const float (*)[3]>(A15), x3); }
+int host_edge_coeff(const float *sel4, const float *nb20, float *coeff4)
+{
+    float4 nb[5];
+    for (int j = 0; j < 5; j++) nb[j] = make_float4(nb20[4 * j], nb20[4 * j + 1], nb20[4 * j + 2], nb20[4 * j + 3]);
+    return map_edge_coeff(make_float4(sel4[0], sel4[1], sel4[2], sel4[3]), nb, coeff4) ? 1 : 0;
+}
+int host_plane_coeff(const float *sel4, const float *nb20, float *coeff4)
+{
+    float4 nb[5];
+    for (int j = 0; j < 5; j++) nb[j] = make_float4(nb20[4 * j], nb20[4 * j + 1], nb20[4 * j + 2], nb20[4 * j + 3]);
+    return map_plane_coeff(make_float4(sel4[0], sel4[1], sel4[2], sel4[3]), nb, coeff4) ? 1 : 0;
+}
+void host_solve6(const float *A36, const float *b6, float *x6) { vlo_solve6_colpiv_qr(A36, b6, x6); }
+void host_to_map(const float *T6, const float *p4, float *out4)
+{
+    float trig[6];
+    for (int a = 0; a < 3; a++) vlo_sincosf(T6[a], trig[2 * a], trig[2 * a + 1]);
+    float4 o = to_map(T6, trig, make_float4(p4[0], p4[1], p4[2], p4[3]));
+    out4[0] = o.x; out4[1] = o.y; out4[2] = o.z; out4[3] = o.w;
 }
 }

@@ -144,3 +144,65 @@ def test_detmath_product_text_equals_oracle_text(gh):
     gh.host_detmath_mismatches.restype = C.c_long
     bad = gh.host_detmath_mismatches(_p(x), _p(y), C.c_long(len(x)))
     assert bad == 0, bad
+
+
+def test_map_linearisation_text_equals_oracle(gh, orc):
+    """csrc/map_lin.cuh (eig3_jacobi, lstsq53, map_edge_coeff, map_plane_coeff, to_map) and csrc/dense6.cuh
+    (vlo_solve6_colpiv_qr) compiled for the CPU give the oracle's results bit for bit: planar / linear / scattered /
+    rank-deficient neighbour sets, near and far query points."""
+    L = orc.lib()
+    rng = np.random.default_rng(5)
+    f32 = np.float32
+
+    def bits(a):
+        return np.ascontiguousarray(a, f32).view(np.uint32)
+
+    n_edge_kept = n_plane_kept = 0
+    for trial in range(4000):
+        kind = trial % 5
+        c = rng.uniform(-30, 30, 3)
+        if kind == 0:                                       # points on a plane (+ small noise)
+            u, v = np.linalg.qr(rng.standard_normal((3, 2)))[0].T
+            nb = c + np.outer(rng.uniform(-0.6, 0.6, 5), u) + np.outer(rng.uniform(-0.6, 0.6, 5), v) + rng.normal(0, 0.01, (5, 3))
+        elif kind == 1:                                     # points along a line
+            d = rng.standard_normal(3); d /= np.linalg.norm(d)
+            nb = c + np.outer(rng.uniform(-0.6, 0.6, 5), d) + rng.normal(0, 0.005, (5, 3))
+        elif kind == 2:                                     # a blob
+            nb = c + rng.normal(0, 0.3, (5, 3))
+        elif kind == 3:                                     # lattice plane through the origin region: rank-deficient A x = -1
+            nb = np.stack([rng.integers(-2, 3, 5) * 0.4, np.zeros(5), rng.integers(-2, 3, 5) * 0.4], 1)
+        else:                                               # duplicates
+            nb = np.repeat(c[None] + rng.normal(0, 0.2, (1, 3)), 5, 0); nb[3:] += rng.normal(0, 0.2, (2, 3))
+        nb4 = np.ascontiguousarray(np.concatenate([nb, np.zeros((5, 1))], 1), f32)
+        sel = np.ascontiguousarray(np.concatenate([nb4[:, :3].mean(0) + rng.normal(0, 0.15, 3), [3.25]]), f32)
+        # 3x3 eigen on the neighbours' covariance (float32 as the kernels form it is not needed here: any symmetric matrix)
+        M = np.cov(nb4[:, :3].T.astype(np.float64)).astype(f32)
+        M = ((M + M.T) * f32(0.5)).astype(f32)
+        e1, v1, e2, v2 = np.zeros(3, f32), np.zeros(9, f32), np.zeros(3, f32), np.zeros(9, f32)
+        gh.host_eig3(_p(M), _p(e1), _p(v1)); L.orc_eig3_jacobi(_p(M), _p(e2), _p(v2))
+        assert np.array_equal(bits(e1), bits(e2)) and np.array_equal(bits(v1), bits(v2)), ("eig3", trial)
+        A = np.ascontiguousarray(nb4[:, :3]); b = np.full(5, -1.0, f32)
+        x1, x2 = np.zeros(3, f32), np.zeros(3, f32)
+        gh.host_lstsq53(_p(A), _p(x1)); L.orc_lstsq53(_p(A), _p(b), _p(x2))
+        assert np.array_equal(bits(x1), bits(x2)), ("lstsq53", trial, x1, x2)
+        for fn_h, fn_o, tag in ((gh.host_edge_coeff, L.orc_map_edge_coeff, "edge"), (gh.host_plane_coeff, L.orc_map_plane_coeff, "plane")):
+            c1, c2 = np.zeros(4, f32), np.zeros(4, f32)
+            k1, k2 = fn_h(_p(sel), _p(nb4), _p(c1)), fn_o(_p(sel), _p(nb4), _p(c2))
+            assert k1 == k2, (tag, trial)
+            if k1:
+                assert np.array_equal(bits(c1), bits(c2)), (tag, trial, c1, c2)
+                if tag == "edge": n_edge_kept += 1
+                else: n_plane_kept += 1
+        # 6x6 normal equations from random Jacobian rows (sometimes rank-deficient)
+        J = rng.standard_normal((40, 6)).astype(f32)
+        if trial % 7 == 0:
+            J[:, 4] = J[:, 1]
+        H = np.ascontiguousarray(J.T @ J, f32); g = np.ascontiguousarray(J.T @ rng.standard_normal(40).astype(f32), f32)
+        s1, s2 = np.zeros(6, f32), np.zeros(6, f32)
+        gh.host_solve6(_p(H), _p(g), _p(s1)); L.orc_solve6_colpiv_qr(_p(H), _p(g), _p(s2))
+        assert np.array_equal(bits(s1), bits(s2)), ("solve6", trial)
+        T = np.ascontiguousarray(np.concatenate([rng.uniform(-3.2, 3.2, 3), rng.uniform(-50, 50, 3)]), f32)
+        o1, o2 = np.zeros(4, f32), np.zeros((1, 4), f32)
+        gh.host_to_map(_p(T), _p(sel), _p(o1)); L.orc_point_to_map(_p(T), _p(sel), 1, _p(o2))
+        assert np.array_equal(bits(o1), bits(o2[0])), ("to_map", trial)
+    assert n_edge_kept > 300 and n_plane_kept > 300, (n_edge_kept, n_plane_kept)
