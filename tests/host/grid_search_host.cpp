@@ -42,6 +42,7 @@ static inline int __all_sync(unsigned, int p) { return p; }
 #include "../../vil_sensor_fusion_b200/csrc/grid.cuh"
 #include "../../vil_sensor_fusion_b200/csrc/dense6.cuh"
 #include "../../vil_sensor_fusion_b200/csrc/map_lin.cuh"
+#include "../../vil_sensor_fusion_b200/csrc/odom_lin.cuh"
 extern "C" {
 #include "../../oracle/detmath.h"
 }
@@ -152,6 +153,23 @@ void host_to_map(const float *T6, const float *p4, float *out4)
     float trig[6];
     for (int a = 0; a < 3; a++) vlo_sincosf(T6[a], trig[2 * a], trig[2 * a + 1]);
     float4 o = to_map(T6, trig, make_float4(p4[0], p4[1], p4[2], p4[3]));
+    out4[0] = o.x; out4[1] = o.y; out4[2] = o.z; out4[3] = o.w;
+}
+
+// the scan-to-scan linearisation of csrc/odom_lin.cuh and transformToStart of vlo_internal.cuh
+static inline float4 f4(const float *p) { return make_float4(p[0], p[1], p[2], p[3]); }
+int host_odom_edge_coeff(const float *sel, const float *a, const float *b, int iter, float *coeff4) { return edge_coeff(f4(sel), f4(a), f4(b), iter, coeff4) ? 1 : 0; }
+int host_odom_plane_coeff(const float *sel, const float *t1, const float *t2, const float *t3, int iter, float *coeff4)
+{ return plane_coeff(f4(sel), f4(t1), f4(t2), f4(t3), iter, coeff4) ? 1 : 0; }
+void host_odom_jacobian_row(const float *T6, const float *ori4, const float *coeff4, float *row6, float *bval)
+{
+    float trig[6];
+    for (int a = 0; a < 3; a++) vlo_sincosf(T6[a], trig[2 * a], trig[2 * a + 1]);
+    odom_jacobian_row(T6, trig, ori4[0], ori4[1], ori4[2], coeff4, row6, *bval);
+}
+void host_to_start(const float *T6, const float *p4, int deskew, float inv_period, float *out4)
+{
+    float4 o = vlo_to_start(T6, f4(p4), deskew, inv_period);
     out4[0] = o.x; out4[1] = o.y; out4[2] = o.z; out4[3] = o.w;
 }
 }

@@ -206,3 +206,44 @@ def test_map_linearisation_text_equals_oracle(gh, orc):
         gh.host_to_map(_p(T), _p(sel), _p(o1)); L.orc_point_to_map(_p(T), _p(sel), 1, _p(o2))
         assert np.array_equal(bits(o1), bits(o2[0])), ("to_map", trial)
     assert n_edge_kept > 300 and n_plane_kept > 300, (n_edge_kept, n_plane_kept)
+
+
+def test_odometry_linearisation_text_equals_oracle(gh, orc):
+    """csrc/odom_lin.cuh (edge_coeff, plane_coeff, odom_jacobian_row) and vlo_to_start compiled for the CPU give the oracle's
+    results bit for bit, before and after the robust weight switches on (iteration 5)."""
+    L = orc.lib()
+    rng = np.random.default_rng(9)
+    f32 = np.float32
+
+    def bits(a):
+        return np.ascontiguousarray(a, f32).view(np.uint32)
+
+    def pt(v, w=0.0):
+        return np.ascontiguousarray(np.concatenate([v, [w]]), f32)
+
+    kept = 0
+    for trial in range(4000):
+        c = rng.uniform(-40, 40, 3)
+        a, b, t3 = (pt(c + rng.normal(0, 0.5, 3)) for _ in range(3))
+        sel = pt(c + rng.normal(0, 0.2 if trial % 3 else 0.01, 3), 7.03)
+        it = int(rng.integers(0, 12))
+        for fn_h, fn_o, args in ((gh.host_odom_edge_coeff, L.orc_edge_coeff, (a, b)), (gh.host_odom_plane_coeff, L.orc_plane_coeff, (a, b, t3))):
+            c1, c2 = np.zeros(4, f32), np.zeros(4, f32)
+            k1 = fn_h(_p(sel), *[_p(x) for x in args], it, _p(c1))
+            k2 = fn_o(_p(sel), *[_p(x) for x in args], it, _p(c2))
+            assert k1 == k2, (trial, it)
+            assert np.array_equal(bits(c1), bits(c2)), (trial, it, c1, c2)
+            kept += k1
+            T = np.ascontiguousarray(np.concatenate([rng.uniform(-0.3, 0.3, 3), rng.uniform(-2, 2, 3)]), f32)
+            r1, r2, b1, b2 = np.zeros(6, f32), np.zeros(6, f32), np.zeros(1, f32), np.zeros(1, f32)
+            gh.host_odom_jacobian_row(_p(T), _p(sel), _p(c1), _p(r1), _p(b1))
+            L.orc_odom_jacobian_row(_p(T), _p(sel), _p(c2), _p(r2), _p(b2))
+            assert np.array_equal(bits(r1), bits(r2)) and np.array_equal(bits(b1), bits(b2)), (trial, "jacobian")
+        for deskew in (0, 1):
+            cfg = orc.default_config("VLP-16", deskew=deskew)
+            T = np.ascontiguousarray(np.concatenate([rng.uniform(-0.3, 0.3, 3), rng.uniform(-2, 2, 3)]), f32)
+            o1 = np.zeros(4, f32)
+            gh.host_to_start(_p(T), _p(sel), deskew, C.c_float(1.0 / cfg.scan_period), _p(o1))
+            o2 = orc.transform_to_start(cfg, T, sel[None])[0]
+            assert np.array_equal(bits(o1), bits(o2)), (trial, "to_start", deskew)
+    assert kept > 3000
