@@ -247,3 +247,65 @@ def test_odometry_linearisation_text_equals_oracle(gh, orc):
             o2 = orc.transform_to_start(cfg, T, sel[None])[0]
             assert np.array_equal(bits(o1), bits(o2)), (trial, "to_start", deskew)
     assert kept > 3000
+
+
+@pytest.fixture(scope="module")
+def warp():
+    inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    if not os.path.exists(os.path.join(inc, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    src = os.path.join(ROOT, "tests", "host", "warp_emul_host.cpp")
+    out = os.path.join(ROOT, "tests", "host", "_build", "libwarpemul.so")
+    deps = [src, os.path.join(ROOT, "vil_sensor_fusion_b200", "csrc", "dense6.cuh"), os.path.join(ROOT, "vil_sensor_fusion_b200", "csrc", "vlo_internal.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.run(["g++", "-O2", "-std=c++20", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I" + inc, src, "-o", out], check=True)
+    return C.CDLL(out)
+
+
+def test_single_warp_jacobi_and_gn_update_equal_oracle(warp, orc):
+    """csrc/dense6.cuh's warp-level code run in lock step on 32 host threads (__syncwarp = a barrier): the single-warp 6x6
+    Jacobi (tournament order, three rotations per round from the same matrix) and the Gauss-Newton update with the
+    degeneracy projection equal the oracle's sequential C bit for bit -- well-conditioned, degenerate (corridor-like) and
+    rank-deficient normal matrices, iteration 0 (projection built) and later iterations (projection applied)."""
+    L = orc.lib()
+    from oracle.oracle import RegResult
+    rng = np.random.default_rng(13)
+    f32 = np.float32
+
+    def bits(a):
+        return np.ascontiguousarray(a, f32).view(np.uint32)
+
+    n_deg = 0
+    for trial in range(150):
+        rows = rng.standard_normal((300, 6)).astype(f32) * f32(3.0)
+        kind = trial % 3
+        if kind == 1:
+            rows[:, 3] *= f32(0.01)                        # one weak translation direction: eigenvalue below the threshold
+        elif kind == 2:
+            rows[:, 5] = rows[:, 4]                        # exactly rank-deficient
+        bvec = (rng.standard_normal(300) * 0.05).astype(f32)
+        H = np.ascontiguousarray(rows.T @ rows, f32)
+        H = np.triu(H) + np.triu(H, 1).T
+        e1, v1 = np.zeros(6, f32), np.zeros(36, f32)
+        warp.host_eig6_warp(_p(np.ascontiguousarray(H, f32)), _p(e1), _p(v1))
+        e2, v2 = orc.eig6(H)
+        assert np.array_equal(bits(e1), bits(e2)) and np.array_equal(bits(v1), bits(v2.ravel())), ("eig6", trial)
+        total = np.zeros(28, f32)
+        total[:21] = H[np.triu_indices(6)]
+        total[21:27] = (rows.T @ bvec).astype(f32)
+        total[27] = f32(bvec @ bvec)
+        T1 = (rng.standard_normal(6) * 0.1).astype(f32); T2 = T1.copy()
+        P1 = np.eye(6, dtype=f32).ravel().copy(); deg1 = C.c_int(0); ev1 = np.zeros(6, f32); conv1 = C.c_int(0)
+        res = RegResult(); conv2 = C.c_int(0)
+        for it in range(3):
+            tot = (total * f32(1.0 if it == 0 else 0.5 ** it)).astype(f32)      # later iterations: smaller steps
+            warp.host_gn_update_warp(_p(tot), it, C.c_float(30.0), C.c_float(0.05), C.c_float(0.05), _p(T1), _p(P1), C.byref(deg1), _p(ev1), C.byref(conv1))
+            L.orc_gn_update(_p(tot), it, C.c_float(30.0), C.c_float(0.05), C.c_float(0.05), _p(T2), C.byref(res), C.byref(conv2), 0)
+            assert np.array_equal(bits(T1), bits(T2)), ("T", trial, it)
+            assert deg1.value == res.is_degenerate and conv1.value == conv2.value, ("flags", trial, it)
+            if it == 0:
+                assert np.array_equal(bits(ev1), bits(np.array(res.eig[:], f32))), ("eig", trial)
+                assert np.array_equal(bits(P1), bits(np.array(res.P[:], f32))), ("P", trial)
+        n_deg += deg1.value
+    assert 40 < n_deg < 150
