@@ -1,0 +1,106 @@
+// TEST INFRASTRUCTURE -- a small SIMT emulator: runs CUDA kernels of this repository on the CPU, one host thread per CUDA
+// thread, CTAs one after the other.  __syncthreads / __syncwarp are barriers, the warp collectives exchange values through
+// a per-warp slot array between two barriers, atomics are GCC atomics on plain memory, `__shared__` variables are statics
+// (one CTA at a time).  Only what the emulated kernels use is implemented: full-mask collectives, one-dimensional blocks
+// whose size is a multiple of 32, no inter-CTA communication.  Arithmetic is the host's IEEE float32 with
+// -ffp-contract=off -- the same operations nvcc --fmad=false emits -- so results can be compared with the oracle bit for bit.
+#pragma once
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#undef __shared__
+#define __shared__ static
+#ifndef __launch_bounds__
+#define __launch_bounds__(...)
+#endif
+
+struct EmuWarp { std::barrier<> bar{32}; unsigned long long slot[32]; bool alive[32]; };
+struct EmuCta { std::unique_ptr<std::barrier<>> bar; std::vector<std::unique_ptr<EmuWarp>> warps; };
+static thread_local uint3 threadIdx, blockIdx;
+static thread_local dim3 blockDim, gridDim;
+static thread_local EmuWarp *emu_warp = nullptr;
+static thread_local EmuCta *emu_cta = nullptr;
+static thread_local int emu_lane = 0;
+
+static inline void __syncthreads() { emu_cta->bar->arrive_and_wait(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp->bar.arrive_and_wait(); }
+static inline void __threadfence() {}
+
+// publish a value, wait, let `f` read every lane's value, wait again (the slots may be overwritten afterwards)
+template <class F> static inline auto emu_collective(unsigned long long mine, F f)
+{
+    emu_warp->slot[emu_lane] = mine;
+    emu_warp->bar.arrive_and_wait();
+    auto r = f(emu_warp->slot, emu_warp->alive);
+    emu_warp->bar.arrive_and_wait();
+    return r;
+}
+template <class T> static inline unsigned long long emu_bits(T v) { unsigned long long u = 0; static_assert(sizeof(T) <= 8, ""); memcpy(&u, &v, sizeof(T)); return u; }
+template <class T> static inline T emu_from(unsigned long long u) { T v; memcpy(&v, &u, sizeof(T)); return v; }
+
+template <class T> static inline T __shfl_sync(unsigned, T v, int src)
+{ return emu_collective(emu_bits(v), [&](const unsigned long long *s, const bool *) { return emu_from<T>(s[src & 31]); }); }
+template <class T> static inline T __shfl_up_sync(unsigned, T v, int d)
+{ return emu_collective(emu_bits(v), [&](const unsigned long long *s, const bool *) { return emu_from<T>(s[emu_lane - d >= 0 ? emu_lane - d : emu_lane]); }); }
+template <class T> static inline T __shfl_down_sync(unsigned, T v, int d)
+{ return emu_collective(emu_bits(v), [&](const unsigned long long *s, const bool *) { return emu_from<T>(s[emu_lane + d < 32 ? emu_lane + d : emu_lane]); }); }
+static inline unsigned __ballot_sync(unsigned, int pred)
+{ return emu_collective(pred ? 1ull : 0ull, [&](const unsigned long long *s, const bool *a) { unsigned m = 0; for (int l = 0; l < 32; l++) if (a[l] && s[l]) m |= 1u << l; return m; }); }
+static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0u; }
+static inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, !pred) == 0u; }
+template <class T, class Op> static inline T emu_reduce(T v, Op op)
+{ return emu_collective(emu_bits(v), [&](const unsigned long long *s, const bool *a) { T r = v; for (int l = 0; l < 32; l++) if (a[l]) r = op(r, emu_from<T>(s[l])); return r; }); }
+static inline unsigned __reduce_max_sync(unsigned, unsigned v) { return emu_reduce(v, [](unsigned a, unsigned b) { return a > b ? a : b; }); }
+static inline unsigned __reduce_min_sync(unsigned, unsigned v) { return emu_reduce(v, [](unsigned a, unsigned b) { return a < b ? a : b; }); }
+static inline int __reduce_max_sync(unsigned, int v) { return emu_reduce(v, [](int a, int b) { return a > b ? a : b; }); }
+static inline int __reduce_min_sync(unsigned, int v) { return emu_reduce(v, [](int a, int b) { return a < b ? a : b; }); }
+static inline int __reduce_add_sync(unsigned, int v)
+{ return emu_collective(emu_bits(v), [&](const unsigned long long *s, const bool *a) { int r = 0; for (int l = 0; l < 32; l++) if (a[l]) r += emu_from<int>(s[l]); return r; }); }
+template <class T> static inline unsigned __match_any_sync(unsigned, T v)
+{ return emu_collective(emu_bits(v), [&](const unsigned long long *s, const bool *a) { unsigned m = 0; for (int l = 0; l < 32; l++) if (a[l] && s[l] == emu_bits(v)) m |= 1u << l; return m; }); }
+
+static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) { return (unsigned)((((unsigned long long)hi << 32) | lo) >> (shift & 31)); }
+template <class T> static inline T __ldg(const T *p) { return *p; }
+template <class T> static inline T __ldcg(const T *p) { return *p; }
+using std::isfinite;
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
+static inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline int atomicMin(int *p, int v) { int o = __atomic_load_n(p, __ATOMIC_SEQ_CST); while (v < o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {} return o; }
+static inline int atomicOr(int *p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned long long atomicCAS(unsigned long long *p, unsigned long long cmp, unsigned long long val)
+{ unsigned long long e = cmp; __atomic_compare_exchange_n(p, &e, val, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return e; }
+
+// kernel<<<grid, block>>>(args...): CTAs in order, the threads of a CTA concurrently
+template <class K, class... A> static void emu_launch(K kernel, dim3 grid, dim3 block, A... args)
+{
+    const int nthr = (int)block.x, nwarp = nthr / 32;
+    for (unsigned bz = 0; bz < grid.z; bz++) for (unsigned by = 0; by < grid.y; by++) for (unsigned bx = 0; bx < grid.x; bx++) {
+        EmuCta cta;
+        cta.bar.reset(new std::barrier<>(nthr));
+        for (int w = 0; w < nwarp; w++) { cta.warps.emplace_back(new EmuWarp()); for (int l = 0; l < 32; l++) cta.warps[w]->alive[l] = true; }
+        std::vector<std::thread> th;
+        th.reserve(nthr);
+        for (int t = 0; t < nthr; t++) th.emplace_back([&, t] {
+            threadIdx = make_uint3((unsigned)t, 0, 0); blockIdx = make_uint3(bx, by, bz); blockDim = block; gridDim = grid;
+            emu_cta = &cta; emu_warp = cta.warps[t / 32].get(); emu_lane = t % 32;
+            kernel(args...);
+            emu_warp->alive[emu_lane] = false;          // an exited thread no longer takes part in barriers or collectives
+            emu_warp->bar.arrive_and_drop();
+            cta.bar->arrive_and_drop();
+        });
+        for (auto &t : th) t.join();
+    }
+}
