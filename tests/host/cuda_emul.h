@@ -13,21 +13,25 @@
 #include <cstring>
 #include <memory>
 #include <thread>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #undef __shared__
 #define __shared__ static
+#undef __constant__
+#define __constant__ static          // per translation unit, as nvcc treats a __constant__ defined in a header
 #ifndef __launch_bounds__
 #define __launch_bounds__(...)
 #endif
 
 struct EmuWarp { std::barrier<> bar{32}; unsigned long long slot[32]; bool alive[32]; };
 struct EmuCta { std::unique_ptr<std::barrier<>> bar; std::vector<std::unique_ptr<EmuWarp>> warps; };
-static thread_local uint3 threadIdx, blockIdx;
-static thread_local dim3 blockDim, gridDim;
-static thread_local EmuWarp *emu_warp = nullptr;
-static thread_local EmuCta *emu_cta = nullptr;
-static thread_local int emu_lane = 0;
+inline thread_local uint3 threadIdx, blockIdx;
+inline thread_local dim3 blockDim, gridDim;
+inline thread_local EmuWarp *emu_warp = nullptr;
+inline thread_local EmuCta *emu_cta = nullptr;
+inline thread_local int emu_lane = 0;
 
 static inline void __syncthreads() { emu_cta->bar->arrive_and_wait(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp->bar.arrive_and_wait(); }
@@ -66,6 +70,14 @@ static inline int __reduce_add_sync(unsigned, int v)
 template <class T> static inline unsigned __match_any_sync(unsigned, T v)
 { return emu_collective(emu_bits(v), [&](const unsigned long long *s, const bool *a) { unsigned m = 0; for (int l = 0; l < 32; l++) if (a[l] && s[l] == emu_bits(v)) m |= 1u << l; return m; }); }
 
+#ifndef __noinline__
+#define __noinline__ __attribute__((noinline))
+#endif
+// kernels passed by name to the runtime's attribute / occupancy queries
+template <class T> static inline cudaError_t cudaFuncSetAttribute(T *, cudaFuncAttribute, int) { return cudaSuccess; }
+template <class T> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, T *, int, size_t) { *n = 1; return cudaSuccess; }
+static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
+static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
@@ -77,11 +89,20 @@ template <class T> static inline T __ldcg(const T *p) { return *p; }
 using std::isfinite;
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
-static inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
-static inline int atomicMin(int *p, int v) { int o = __atomic_load_n(p, __ATOMIC_SEQ_CST); while (v < o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {} return o; }
-static inline int atomicOr(int *p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
-static inline unsigned long long atomicCAS(unsigned long long *p, unsigned long long cmp, unsigned long long val)
-{ unsigned long long e = cmp; __atomic_compare_exchange_n(p, &e, val, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return e; }
+template <class T> static inline T atomicAdd(T *p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+template <class T> static inline T atomicSub(T *p, T v) { return __atomic_fetch_sub(p, v, __ATOMIC_SEQ_CST); }
+template <class T> static inline T atomicOr(T *p, T v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+template <class T> static inline T atomicExch(T *p, T v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+template <class T> static inline T atomicMin(T *p, T v) { T o = __atomic_load_n(p, __ATOMIC_SEQ_CST); while (v < o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {} return o; }
+template <class T> static inline T atomicMax(T *p, T v) { T o = __atomic_load_n(p, __ATOMIC_SEQ_CST); while (v > o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {} return o; }
+template <class T> static inline T atomicCAS(T *p, T cmp, T val) { T e = cmp; __atomic_compare_exchange_n(p, &e, val, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return e; }
+
+// cooperative launches run as ONE CTA here (the fake runtime reports one SM and one resident CTA), so a grid sync is the
+// CTA barrier and `__shared__` statics stay private to the only CTA there is
+namespace cooperative_groups {
+struct grid_group { void sync() const { emu_cta->bar->arrive_and_wait(); } };
+static inline grid_group this_grid() { return grid_group(); }
+}
 
 // kernel<<<grid, block>>>(args...): CTAs in order, the threads of a CTA concurrently
 template <class K, class... A> static void emu_launch(K kernel, dim3 grid, dim3 block, A... args)
@@ -103,4 +124,15 @@ template <class K, class... A> static void emu_launch(K kernel, dim3 grid, dim3 
         });
         for (auto &t : th) t.join();
     }
+}
+
+// cudaLaunchCooperativeKernel((void *)kernel, grid, block, args, ...): the argument array is unpacked by the kernel's own
+// parameter types
+template <class... P, size_t... I> static void emu_coop_call(void (*k)(P...), void **args, std::index_sequence<I...>)
+{ k(*reinterpret_cast<std::remove_reference_t<P> *>(args[I])...); }
+template <class... P> static cudaError_t emu_launch_coop(void (*k)(P...), dim3 grid, dim3 block, void **args)
+{
+    if (grid.x * grid.y * grid.z != 1) return cudaErrorCooperativeLaunchTooLarge;
+    emu_launch([=] { emu_coop_call(k, args, std::index_sequence_for<P...>()); }, grid, block);
+    return cudaSuccess;
 }

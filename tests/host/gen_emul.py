@@ -20,6 +20,11 @@ def _split_top(s):
 
 
 def rewrite(src: str) -> str:
+    # cudaLaunchCooperativeKernel((void *)kernel, grid, block, args, smem, stream) -> emu_launch_coop(kernel, grid, block, args)
+    def coop(m):
+        a = _split_top(m.group(1))
+        return "emu_launch_coop(%s, %s, %s, %s)" % (re.sub(r"^\(void \*\)", "", a[0]), a[1], a[2], a[3])
+    src = re.sub(r"cudaLaunchCooperativeKernel\(((?:[^()]|\([^()]*\))*)\)", coop, src)
     out, i = "", 0
     while True:
         j = src.find("<<<", i)

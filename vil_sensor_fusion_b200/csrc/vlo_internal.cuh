@@ -12,6 +12,14 @@
 #define VLO_NTERM 28          // 21 upper-tri AtA + 6 AtB + sum of squared weighted residuals
 #define VLO_PI_D 3.14159265358979323846
 
+// A kernel's dynamic shared memory as an int array.  Under the CPU emulation of tests/host/ (VLO_HOST_EMULATION) shared
+// memory is ordinary static storage, one CTA at a time.
+#ifdef VLO_HOST_EMULATION
+#define VLO_DYN_SMEM_INT(name) static int name[16384]
+#else
+#define VLO_DYN_SMEM_INT(name) extern __shared__ int name[]
+#endif
+
 // One set of voxel-hash grids (see grid.cuh for the layout contract)
 struct GridSet {
     float cell, inv_cell;
