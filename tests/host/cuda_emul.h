@@ -13,6 +13,9 @@
 #include <cstring>
 #include <memory>
 #include <thread>
+#include <atomic>
+#include <functional>
+#include <semaphore>
 #include <type_traits>
 #include <utility>
 #include <vector>
@@ -104,6 +107,48 @@ struct grid_group { void sync() const { emu_cta->bar->arrive_and_wait(); } };
 static inline grid_group this_grid() { return grid_group(); }
 }
 
+// The host threads that play the CUDA threads live in a pool (creating 512 threads per CTA dominated the run time):
+// worker t sleeps on its own semaphore, a launch wakes workers 0 .. blockDim-1 once per CTA and waits for all of them.
+struct EmuPool {
+    struct Worker { std::thread th; std::binary_semaphore go{0}; };
+    std::vector<std::unique_ptr<Worker>> workers;
+    std::function<void(int)> job;
+    std::atomic<int> remaining{0};
+    std::binary_semaphore done{0};
+    std::atomic<bool> quit{false};
+    void ensure(int n)
+    {
+        while ((int)workers.size() < n) {
+            const int id = (int)workers.size();
+            workers.emplace_back(new Worker());
+            Worker *w = workers.back().get();
+            w->th = std::thread([this, w, id] {
+                for (;;) {
+                    w->go.acquire();
+                    if (quit.load()) return;
+                    job(id);
+                    if (remaining.fetch_sub(1) == 1) done.release();
+                }
+            });
+        }
+    }
+    void run(int n, std::function<void(int)> f)
+    {
+        ensure(n);
+        job = std::move(f);
+        remaining.store(n);
+        for (int t = 0; t < n; t++) workers[t]->go.release();
+        done.acquire();
+    }
+    ~EmuPool()
+    {
+        quit.store(true);
+        for (auto &w : workers) w->go.release();
+        for (auto &w : workers) w->th.join();
+    }
+};
+inline EmuPool &emu_pool() { static EmuPool *p = new EmuPool(); return *p; }     // leaked on purpose: no join at exit
+
 // kernel<<<grid, block>>>(args...): CTAs in order, the threads of a CTA concurrently
 template <class K, class... A> static void emu_launch(K kernel, dim3 grid, dim3 block, A... args)
 {
@@ -112,9 +157,7 @@ template <class K, class... A> static void emu_launch(K kernel, dim3 grid, dim3 
         EmuCta cta;
         cta.bar.reset(new std::barrier<>(nthr));
         for (int w = 0; w < nwarp; w++) { cta.warps.emplace_back(new EmuWarp()); for (int l = 0; l < 32; l++) cta.warps[w]->alive[l] = true; }
-        std::vector<std::thread> th;
-        th.reserve(nthr);
-        for (int t = 0; t < nthr; t++) th.emplace_back([&, t] {
+        emu_pool().run(nthr, [&](int t) {
             threadIdx = make_uint3((unsigned)t, 0, 0); blockIdx = make_uint3(bx, by, bz); blockDim = block; gridDim = grid;
             emu_cta = &cta; emu_warp = cta.warps[t / 32].get(); emu_lane = t % 32;
             kernel(args...);
@@ -122,7 +165,6 @@ template <class K, class... A> static void emu_launch(K kernel, dim3 grid, dim3 
             emu_warp->bar.arrive_and_drop();
             cta.bar->arrive_and_drop();
         });
-        for (auto &t : th) t.join();
     }
 }
 
