@@ -38,7 +38,9 @@ def build(force=False):
         objs = list(ex.map(one, cus))
     fake = os.path.join(BUILD, "fake_cudart.o")
     subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-I" + inc, "-c", os.path.join(HOST, "fake_cudart.cpp"), "-o", fake], check=True)
-    subprocess.run(["g++", "-shared", "-pthread", "-o", out] + objs + [fake], check=True)
+    # -Bsymbolic: the library's cuda* calls must bind to its own fake runtime even when a real libcudart is already in the
+    # process (torch loads one with global visibility)
+    subprocess.run(["g++", "-shared", "-pthread", "-Wl,-Bsymbolic", "-o", out] + objs + [fake], check=True)
     return out
 
 
