@@ -8,7 +8,10 @@ import sys
 HOST = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HOST))
 CSRC = os.path.join(ROOT, "vil_sensor_fusion_b200", "csrc")
-BUILD = os.path.join(HOST, "_build")
+# VLO_EMUL_BUILD_DIR / VLO_EMUL_EXTRA_FLAGS: a second build next to the default one, e.g. with -fsanitize=address (memcheck of the
+# emulated kernels: LD_PRELOAD=$(gcc -print-file-name=libasan.so) pytest tests/test_host_library.py)
+BUILD = os.environ.get("VLO_EMUL_BUILD_DIR", os.path.join(HOST, "_build"))
+EXTRA = os.environ.get("VLO_EMUL_EXTRA_FLAGS", "").split()
 sys.path.insert(0, HOST)
 import gen_emul  # noqa: E402
 
@@ -31,16 +34,16 @@ def build(force=False):
         gen = os.path.join(BUILD, f[:-3] + ".emul.cpp")
         open(gen, "w").write(gen_emul.rewrite(open(os.path.join(CSRC, f)).read()))
         obj = gen[:-4] + ".o"
-        subprocess.run(["g++"] + FLAGS + ["-I" + inc, "-I" + CSRC, "-c", gen, "-o", obj], check=True)
+        subprocess.run(["g++"] + FLAGS + EXTRA + ["-I" + inc, "-I" + CSRC, "-c", gen, "-o", obj], check=True)
         return obj
 
     with cf.ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(one, cus))
     fake = os.path.join(BUILD, "fake_cudart.o")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-I" + inc, "-c", os.path.join(HOST, "fake_cudart.cpp"), "-o", fake], check=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC"] + EXTRA + ["-I" + inc, "-c", os.path.join(HOST, "fake_cudart.cpp"), "-o", fake], check=True)
     # -Bsymbolic: the library's cuda* calls must bind to its own fake runtime even when a real libcudart is already in the
     # process (torch loads one with global visibility)
-    subprocess.run(["g++", "-shared", "-pthread", "-Wl,-Bsymbolic", "-o", out] + objs + [fake], check=True)
+    subprocess.run(["g++", "-shared", "-pthread", "-Wl,-Bsymbolic"] + EXTRA + ["-o", out] + objs + [fake], check=True)
     return out
 
 
