@@ -141,7 +141,6 @@ __global__ void __launch_bounds__(1024) k7_ds_emit(StackDsParams p)
             const bool lead = slot[j] >= 0 && recs[slot[j] * 8 + 5] == i;
             bal[j] = __ballot_sync(0xffffffffu, lead);
         }
-        __syncthreads();                                   // s_cnt may still be read from the previous round
         if (lane == 0) {
             #pragma unroll
             for (int j = 0; j < K7_EMIT_PER; j++) s_cnt[j * 32 + warp] = __popc(bal[j]);
@@ -182,6 +181,10 @@ __global__ void __launch_bounds__(1024) k7_ds_emit(StackDsParams p)
             keys[slot[j]] = LM_EMPTY;
         }
         carry += s_cnt[K7_EMIT_PER * 32];
+        // end of the round: s_cnt is rewritten and the slots the leaders have just cleaned are compared (rec[5] == i) by the
+        // next round only after every thread is here (ThreadSanitizer over the CPU emulation flagged the barrier-less
+        // read of a slot another thread was still cleaning; either value compared unequal, but it was a race)
+        __syncthreads();
     }
     if (tid == 0) p.ds_counts[b * 8 + (w ? 4 : 2)] = carry;
 }
