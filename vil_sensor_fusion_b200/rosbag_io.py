@@ -49,17 +49,154 @@ def _records(buf: bytes, pos: int = 0) -> Iterator[tuple[dict, bytes]]:
         yield hdr, data
 
 
+# ---- LZ4 frame format (what rosbag's "lz4" chunks hold: roslz4 writes standard LZ4 frames).  The lz4 module is not in
+# this image, so the codec is written out: a block decoder (token / literals / offset / match length sequences, overlapping
+# matches copied byte-wise) under the frame layer (magic, FLG / BD, optional content size, block sizes with the
+# "stored uncompressed" bit, optional block / content checksums -- skipped, not verified).
+LZ4_MAGIC = 0x184D2204
+
+
+def _lz4_block_decode(src: bytes, out: bytearray) -> None:
+    i, n = 0, len(src)
+    while i < n:
+        token = src[i]
+        i += 1
+        lit = token >> 4
+        if lit == 15:
+            while True:
+                b = src[i]
+                i += 1
+                lit += b
+                if b != 255:
+                    break
+        out += src[i:i + lit]
+        i += lit
+        if i >= n:
+            break                                   # the last sequence has literals only
+        offset = src[i] | (src[i + 1] << 8)
+        i += 2
+        if offset == 0:
+            raise RuntimeError("corrupt lz4 block (zero offset)")
+        ml = token & 15
+        if ml == 15:
+            while True:
+                b = src[i]
+                i += 1
+                ml += b
+                if b != 255:
+                    break
+        ml += 4
+        start = len(out) - offset
+        if start < 0:
+            raise RuntimeError("corrupt lz4 block (offset before start)")
+        if offset >= ml:
+            out += out[start:start + ml]
+        else:                                       # overlapping match: the pattern repeats
+            for k in range(ml):
+                out.append(out[start + k])
+
+
+def lz4_frame_decompress(data: bytes) -> bytes:
+    pos, out = 0, bytearray()
+    while pos < len(data):                          # concatenated frames are allowed
+        (magic,) = struct.unpack_from("<I", data, pos)
+        if magic != LZ4_MAGIC:
+            raise RuntimeError("not an lz4 frame (magic %08x)" % magic)
+        flg, pos = data[pos + 4], pos + 6           # FLG, BD
+        if (flg >> 6) != 1:
+            raise RuntimeError("unsupported lz4 frame version")
+        block_checksum, content_size, content_checksum, dict_id = (flg >> 4) & 1, (flg >> 3) & 1, (flg >> 2) & 1, flg & 1
+        pos += 8 * content_size + 4 * dict_id + 1   # optional content size, dictionary id; header checksum byte
+        independent = (flg >> 5) & 1
+        frame_start = len(out)
+        while True:
+            (bs,) = struct.unpack_from("<I", data, pos)
+            pos += 4
+            if bs == 0:
+                break                               # end mark
+            stored, bs = bs >> 31, bs & 0x7FFFFFFF
+            block = data[pos:pos + bs]
+            pos += bs + 4 * block_checksum
+            if stored:
+                out += block
+            elif independent:
+                part = bytearray()
+                _lz4_block_decode(block, part)
+                out += part
+            else:                                   # linked blocks: matches may reach into the previous blocks of the frame
+                _lz4_block_decode(block, out)
+        pos += 4 * content_checksum
+        del frame_start
+    return bytes(out)
+
+
+def _lz4_block_encode(src: bytes) -> bytes:
+    """Greedy single-pass LZ4 block encoder (4-byte hash chain of depth 1): enough to write bags and to exercise every
+    branch of the decoder; format rules kept: last 5 bytes are literals, no match starts within the last 12 bytes."""
+    n, out, anchor, i, table = len(src), bytearray(), 0, 0, {}
+
+    def emit(lit_end, mlen, offset):
+        lit = lit_end - anchor
+        token = (min(lit, 15) << 4) | (min(mlen - 4, 15) if mlen else 0)
+        out.append(token)
+        if lit >= 15:
+            r = lit - 15
+            while r >= 255:
+                out.append(255)
+                r -= 255
+            out.append(r)
+        out.extend(src[anchor:lit_end])
+        if mlen:
+            out.extend(struct.pack("<H", offset))
+            if mlen - 4 >= 15:
+                r = mlen - 4 - 15
+                while r >= 255:
+                    out.append(255)
+                    r -= 255
+                out.append(r)
+
+    while i + 12 < n:
+        key = src[i:i + 4]
+        cand = table.get(key)
+        table[key] = i
+        if cand is not None and i - cand <= 0xFFFF:
+            m = 4
+            limit = n - 5 - i
+            while m < limit and src[cand + m] == src[i + m]:
+                m += 1
+            emit(i, m, i - cand)
+            i += m
+            anchor = i
+        else:
+            i += 1
+    emit(n, 0, 0)
+    return bytes(out)
+
+
+def lz4_frame_compress(data: bytes, block_size: int = 1 << 16) -> bytes:
+    """One LZ4 frame: version 1, independent blocks, no checksums, no content size (FLG 0x60, BD 64 KB)."""
+    out = bytearray(struct.pack("<I", LZ4_MAGIC) + bytes([0x60, 0x40, 0x82]))       # 0x82 = (xxh32(FLG BD) >> 8) & 0xff for 60 40
+    for a in range(0, len(data), block_size):
+        raw = data[a:a + block_size]
+        enc = _lz4_block_encode(raw)
+        if len(enc) < len(raw):
+            out += struct.pack("<I", len(enc)) + enc
+        else:
+            out += struct.pack("<I", len(raw) | 0x80000000) + raw
+    out += struct.pack("<I", 0)
+    return bytes(out)
+
+
 def _decompress(kind: bytes, data: bytes, size: int) -> bytes:
     if kind == b"none":
         return data
     if kind == b"bz2":
         return bz2.decompress(data)
     if kind == b"lz4":
-        try:
-            import lz4.frame                                   # optional
-        except ImportError as e:
-            raise RuntimeError("this bag uses lz4 chunks and the lz4 module is not installed") from e
-        return lz4.frame.decompress(data)
+        out = lz4_frame_decompress(data)
+        if size and len(out) != size:
+            raise RuntimeError("lz4 chunk inflates to %d bytes, header says %d" % (len(out), size))
+        return out
     raise RuntimeError("unknown chunk compression %r" % kind)
 
 
@@ -189,7 +326,7 @@ def _record(fields: dict, data: bytes) -> bytes:
 
 def write_bag(path: str, messages, compression: str = "none", chunk_messages: int = 64) -> None:
     """messages: iterable of (topic, type, md5sum, time [s], serialized bytes).  Writes chunks of `chunk_messages`
-    messages (compression "none" or "bz2") with their connection records, then connection + chunk-info records."""
+    messages (compression "none", "bz2" or "lz4") with their connection records, then connection + chunk-info records."""
     conns: dict[str, int] = {}
     conn_recs: dict[int, bytes] = {}
     chunks, cur, cur_times = [], [], []
@@ -198,7 +335,7 @@ def write_bag(path: str, messages, compression: str = "none", chunk_messages: in
         if not cur:
             return
         raw = b"".join(cur)
-        comp = raw if compression == "none" else bz2.compress(raw)
+        comp = raw if compression == "none" else (bz2.compress(raw) if compression == "bz2" else lz4_frame_compress(raw))
         chunks.append((_record({"op": bytes([OP_CHUNK]), "compression": compression.encode(), "size": struct.pack("<I", len(raw))}, comp),
                        min(cur_times), max(cur_times), len(cur_times)))
         cur.clear()
