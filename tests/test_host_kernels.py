@@ -100,3 +100,48 @@ def test_emulated_organise_and_extract_equal_oracle(emu, orc, case):
     fo = _compare(orc, ocfg, raw, o)
     if case != "ragged":
         assert len(fo["sharp_idx"]) > 20 and len(fo["flat_idx"]) > 60 and len(fo["less_flat"]) > 300
+
+
+def _random_scan(rng, kind):
+    """Small adversarial VLP-16-shaped clouds: what a driver can deliver, not only what a simulator does."""
+    n_az = int(rng.integers(30, 260))
+    az = np.sort(rng.uniform(-np.pi, np.pi, n_az)).astype(np.float32) if kind != "regular" else np.linspace(-np.pi, np.pi, n_az, endpoint=False, dtype=np.float32)
+    el = np.deg2rad(np.arange(-15, 16, 2)).astype(np.float32)
+    A, E = np.meshgrid(az, el, indexing="ij")                        # firing order: all 16 lasers per azimuth
+    rad = (4.0 + 3.0 * np.sin(3 * A) ** 2 + rng.normal(0, 0.02, A.shape)).astype(np.float32)
+    if kind == "steps":                                              # depth discontinuities -> occlusion / parallel-beam rules
+        rad += (np.floor(A * 2.5) % 2).astype(np.float32) * np.float32(2.5)
+    x, y, z = rad * np.cos(E) * np.cos(A), rad * np.cos(E) * np.sin(A), rad * np.sin(E)
+    raw = np.stack([x, y, z, np.ones_like(x)], -1).reshape(-1, 4).astype(np.float32)
+    if kind == "holes":
+        keep = rng.random(len(raw)) > 0.35
+        keep[:5] = True
+        raw = raw[keep]
+    if kind == "junk":
+        idx = rng.choice(len(raw), len(raw) // 10, replace=False)
+        raw[idx[: len(idx) // 3], 0] = np.nan
+        raw[idx[len(idx) // 3: 2 * len(idx) // 3]] = 0.0
+        raw[idx[2 * len(idx) // 3:], 2] *= 20.0                      # far outside the vertical field of view
+    if kind == "few_rings":                                          # only three rings return anything; one of them is short
+        ring = np.tile(np.arange(16), n_az)[: len(raw)]
+        raw = raw[np.isin(ring, (2, 3, 9))]
+        ring = np.tile(np.arange(16), n_az)[: 0]
+        raw = raw[: max(12, len(raw) - int(rng.integers(0, 40)))]
+    if kind == "duplicates":
+        raw[1::2] = raw[0::2][: len(raw[1::2])]                      # zero gaps between neighbours on a ring
+    if kind == "shuffled":                                           # unorganised arrival order
+        raw = raw[rng.permutation(len(raw))]
+    return np.ascontiguousarray(raw, np.float32)
+
+
+@pytest.mark.parametrize("kind", ["regular", "steps", "holes", "junk", "few_rings", "duplicates", "shuffled"])
+def test_emulated_extraction_on_adversarial_scans(emu, orc, kind):
+    from vil_sensor_fusion_b200 import api
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(kind.encode()))
+    ocfg = orc.default_config("VLP-16")
+    gcfg = api.default_config("VLP-16", max_scans=2, max_points=8192)
+    for rep in range(2):
+        raw = _random_scan(rng, kind)
+        o = _run(emu, gcfg, raw)
+        _compare(orc, ocfg, raw, o)
