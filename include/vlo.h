@@ -100,8 +100,11 @@ typedef struct vlo_config {
     /* ---- MultiScanRegistration input options (loam_params.yaml:4-5,23) ---- */
     int   rotate_input;                /* rotateInputCloud false (4) */
     float input_rotation[3];           /* inputCloudRotation [0,0,0] (5): yaw pitch roll (rad); p' = Rz(yaw) Ry(pitch) Rx(roll) p, ROS frame */
-    int   ring_field;                  /* useCloudIntensityandRingFields (23): float index of a FLOAT32 `ring` field inside the point
-                                          (ring ids as delivered by the driver, e.g. Bpearl); -1 = ring from the vertical angle */
+    int   ring_field;                  /* useCloudIntensityandRingFields (23): where the point's `ring` field is (ring ids as delivered by
+                                          the driver, e.g. Velodyne / Ouster / Bpearl clouds); -1 = ring from the vertical angle.
+                                          ring_field_type 0: index in float32 units of a FLOAT32 field; 1 / 2: BYTE offset of a
+                                          UINT16 / UINT8 field (PointCloud2 fields[].offset of the usual uint16 `ring`) */
+    int   ring_field_type;
 } vlo_config;
 
 /* One registration result = one nav_msgs/Odometry + loam/OptStatus pair of the reference. */

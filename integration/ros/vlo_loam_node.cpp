@@ -61,8 +61,10 @@ int main(int argc, char **argv) {
   std::vector<double> ypr;                                                                                         // :4-5
   nh.getParam("rotateInputCloud", rotate); c.rotate_input = rotate ? 1 : 0;
   if (nh.getParam("inputCloudRotation", ypr) && ypr.size() == 3) for (int i = 0; i < 3; i++) c.input_rotation[i] = (float)ypr[i];
-  // :23 useCloudIntensityandRingFields: ring ids from the cloud's FLOAT32 `ring` field; x y z intensity ring -> float index 4
-  nh.getParam("useCloudIntensityandRingFields", ring_fields); c.ring_field = ring_fields ? 4 : -1;
+  // :23 useCloudIntensityandRingFields: ring ids from the cloud's `ring` field.  velodyne_pointcloud's PointXYZIR: x y z
+  // intensity (float32) + ring (uint16) at byte 16 -> ring_field 16, type 1 (UINT16); an all-float32 cloud with a fifth
+  // `ring` column would be ring_field 4, type 0
+  nh.getParam("useCloudIntensityandRingFields", ring_fields); c.ring_field = ring_fields ? 16 : -1; c.ring_field_type = 1;
   nh.getParam("odomDegenEigVal", c.odom_degen_eig); nh.getParam("mapDegenEigVal", c.map_degen_eig); // :39,53
   nh.getParam("cornerFilterSize", c.corner_filter_size); nh.getParam("surfaceFilterSize", c.surface_filter_size);   // :47-48
   nh.getParam("mapCubeSize", c.map_cube_size); nh.getParam("numNeighborSubmapCubes", c.n_neighbor_cubes);          // :49,52

@@ -44,7 +44,7 @@ void orc_default_config(orc_config *c)
     c->n_neighbor_cubes = 5;
     c->io_ratio = 2;
     c->rotate_input = 0; c->input_rotation[0] = c->input_rotation[1] = c->input_rotation[2] = 0.0f;
-    c->ring_field = -1;
+    c->ring_field = -1; c->ring_field_type = 0;
 }
 
 /* MultiScanMapper::getRingForAngle: int(((angle*180/M_PI) - lower) * factor + 0.5) */
@@ -112,7 +112,12 @@ int orc_organise(const orc_config *c, const float *raw, int n, int stride,
         if ((x * x + y * y) + z * z < 0.0001f) continue;
         int id;
         if (c->ring_field >= 0) {                    /* ring id as delivered by the driver (useCloudIntensityandRingFields) */
-            float rf = p[c->ring_field];
+            float rf;
+            if (c->ring_field_type == 0) rf = p[c->ring_field];
+            else {
+                const unsigned char *bp = (const unsigned char *)p + c->ring_field;
+                rf = c->ring_field_type == 1 ? (float)(bp[0] | (bp[1] << 8)) : (float)bp[0];
+            }
             if (!(rf >= 0.0f && rf < (float)R)) continue;       /* also rejects NaN */
             id = (int)rf;
         } else {

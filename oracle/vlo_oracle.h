@@ -61,6 +61,7 @@ typedef struct {
     int   rotate_input;                /* rotateInputCloud false (4) */
     float input_rotation[3];           /* inputCloudRotation [0,0,0] (5): yaw pitch roll (rad), p' = Rz(yaw) Ry(pitch) Rx(roll) p in the ROS frame */
     int   ring_field;                  /* useCloudIntensityandRingFields (23): float index of a FLOAT32 ring field in the point, -1 = ring from the vertical angle */
+    int   ring_field_type;             /* 0: ring_field counts float32 units (FLOAT32 field); 1 / 2: ring_field is the BYTE offset of a UINT16 / UINT8 field */
 } orc_config;
 
 void orc_default_config(orc_config *c);

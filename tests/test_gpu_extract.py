@@ -133,7 +133,7 @@ def test_pointcloud2_layouts(orc):
             h.upload_pointcloud2([bad])
 
 
-@pytest.mark.parametrize("opt", ["rotate", "ring_field", "both"])
+@pytest.mark.parametrize("opt", ["rotate", "ring_field", "both", "uint16_ring"])
 def test_input_rotation_and_ring_field_options(orc, opt):
     """rotateInputCloud / inputCloudRotation and useCloudIntensityandRingFields (loam_params.yaml:4-5,23): organise and the
     features that follow equal the oracle's bit for bit; the rotation really is Rz(yaw) Ry(pitch) Rx(roll) in the ROS frame;
@@ -149,6 +149,15 @@ def test_input_rotation_and_ring_field_options(orc, opt):
     raw[10:5000:97, 4] = np.nan
     raw[20:5000:89, 4] = 16.0
     kw = {}
+    if opt == "uint16_ring":
+        # velodyne-style 24-byte point: x y z intensity (float32), ring (uint16) at byte 18 (not float-aligned), padding;
+        # dropped points carry an out-of-range id
+        rec = np.zeros((len(base), 24), np.uint8)
+        rec[:, :16] = base.view(np.uint8).reshape(len(base), 16)
+        ids = np.where(ring_by_src >= 0, 15 - ring_by_src, 200).astype(np.uint16)
+        rec[:, 18:20] = ids.view(np.uint8).reshape(-1, 2)
+        raw = np.ascontiguousarray(rec).view(np.float32).reshape(len(base), 6)
+        kw.update(ring_field=18, ring_field_type=1)
     if opt in ("rotate", "both"):
         kw.update(rotate_input=1, input_rotation=(0.3, -0.1, 0.05))
     if opt in ("ring_field", "both"):
@@ -170,6 +179,8 @@ def test_input_rotation_and_ring_field_options(orc, opt):
         Rx = np.array([[1, 0, 0], [0, np.cos(r), -np.sin(r)], [0, np.sin(r), np.cos(r)]])
         ros = (Rz @ Ry @ Rx @ raw[src_g, :3].astype(np.float64).T).T
         np.testing.assert_allclose(cloud_g[:, :3], ros[:, [1, 2, 0]], atol=2e-5)           # LOAM x y z = ROS y z x
+    if opt == "uint16_ring":
+        np.testing.assert_array_equal(np.floor(cloud_g[:, 3]), 15 - ring_by_src[src_g])
     if opt in ("ring_field", "both"):
         np.testing.assert_array_equal(np.floor(cloud_g[:, 3]), raw[src_g, 4])                # ring id = the field's value
         assert not np.any(np.isnan(raw[src_g, 4])) and np.all(raw[src_g, 4] < 16)

@@ -77,7 +77,7 @@ def _compare(orc, ocfg, raw, o):
     return fo
 
 
-@pytest.mark.parametrize("case", ["clean", "noisy_rolling", "ragged", "rotated_ring_field"])
+@pytest.mark.parametrize("case", ["clean", "noisy_rolling", "ragged", "rotated_ring_field", "uint16_ring", "uint8_ring"])
 def test_emulated_organise_and_extract_equal_oracle(emu, orc, case):
     from vil_sensor_fusion_b200 import api
     kw = {}
@@ -92,12 +92,29 @@ def test_emulated_organise_and_extract_equal_oracle(emu, orc, case):
         c0, _, s0 = orc.organise(orc.default_config("VLP-16"), base)
         ring = np.full(len(base), -1.0, np.float32)
         ring[s0] = np.floor(c0[:, 3])
-        raw = np.concatenate([base, ring[:, None]], 1).astype(np.float32)
-        kw = dict(rotate_input=1, input_rotation=(0.2, 0.05, -0.1), ring_field=4)
+        if case == "rotated_ring_field":
+            raw = np.concatenate([base, ring[:, None]], 1).astype(np.float32)
+            kw = dict(rotate_input=1, input_rotation=(0.2, 0.05, -0.1), ring_field=4)
+        else:
+            # a Velodyne-style point: x y z intensity (float32) + an integer ring field + padding, 24 bytes; dropped points
+            # carry ring 200 (out of range).  The ring order is reversed so that it cannot be confused with the angle rule.
+            rec = np.zeros((len(base), 24), np.uint8)
+            rec[:, :16] = base.view(np.uint8).reshape(len(base), 16)
+            ids = np.where(ring >= 0, 15 - ring, 200).astype(np.uint16)
+            if case == "uint16_ring":
+                rec[:, 18:20] = ids.view(np.uint8).reshape(-1, 2)            # byte offset 18: not float-aligned
+                kw = dict(ring_field=18, ring_field_type=1)
+            else:
+                rec[:, 21] = ids.astype(np.uint8)
+                kw = dict(ring_field=21, ring_field_type=2)
+            raw = np.ascontiguousarray(rec).view(np.float32).reshape(len(base), 6)
     ocfg = orc.default_config("VLP-16", **kw)
     gcfg = api.default_config("VLP-16", max_scans=2, max_points=8192, **kw)
     o = _run(emu, gcfg, raw)
     fo = _compare(orc, ocfg, raw, o)
+    if case in ("uint16_ring", "uint8_ring"):
+        nv = int(o["counts"][0])
+        np.testing.assert_array_equal(np.floor(o["cloud"][:nv, 3]), 15 - ring[o["src"][:nv]])       # ids really come from the field
     if case != "ragged":
         assert len(fo["sharp_idx"]) > 20 and len(fo["flat_idx"]) > 60 and len(fo["less_flat"]) > 300
 

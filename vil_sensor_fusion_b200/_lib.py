@@ -27,7 +27,7 @@ class Config(C.Structure):
         ("corner_filter_size", C.c_float), ("surface_filter_size", C.c_float), ("map_cube_size", C.c_float),
         ("map_dims", C.c_int * 3), ("map_start_cubes", C.c_int * 3), ("n_neighbor_cubes", C.c_int), ("io_ratio", C.c_int),
         ("hessian_order", C.c_int),
-        ("rotate_input", C.c_int), ("input_rotation", C.c_float * 3), ("ring_field", C.c_int),
+        ("rotate_input", C.c_int), ("input_rotation", C.c_float * 3), ("ring_field", C.c_int), ("ring_field_type", C.c_int),
     ]
 
 

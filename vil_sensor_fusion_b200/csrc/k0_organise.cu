@@ -15,7 +15,8 @@ struct K0Params {
     int N;            // capacity per scan
     int tiles;        // tiles per scan (capacity)
     int rotate; float R[9];   // rotateInputCloud / inputCloudRotation: R = Rz(yaw) Ry(pitch) Rx(roll), ROS frame
-    int ring_field;   // float index of a FLOAT32 ring field inside the point, -1 = ring from the vertical angle
+    int ring_field;   // ring field of the point: float index (ring_type 0, FLOAT32) or byte offset (1 UINT16, 2 UINT8); -1 = ring from the vertical angle
+    int ring_type;
 };
 
 // LOAM-frame x / y / z (x = ROS y, y = ROS z, z = ROS x) of a raw point, rotated first when rotateInputCloud is set
@@ -85,7 +86,15 @@ __global__ void __launch_bounds__(K0_TILE) k0_classify(K0Params p, const float *
         const float *q = p.raw + (size_t)(o0 + i) * p.stride;
         float x, y, z;
         k0_point(p, q, x, y, z);
-        int ring = k0_ring(p, x, y, z, p.ring_field >= 0 ? q[p.ring_field] : 0.0f);
+        float rf = 0.0f;
+        if (p.ring_field >= 0) {
+            if (p.ring_type == 0) rf = q[p.ring_field];
+            else {
+                const unsigned char *bp = reinterpret_cast<const unsigned char *>(q) + p.ring_field;
+                rf = p.ring_type == 1 ? (float)(bp[0] | (bp[1] << 8)) : (float)bp[0];
+            }
+        }
+        int ring = k0_ring(p, x, y, z, rf);
         ring_of[(size_t)b * p.N + i] = (int8_t)ring;            // the scatter pass reuses ring and raw orientation
         if (ring >= 0) {
             atomicAdd(&hist[ring], 1);
@@ -227,7 +236,10 @@ int vlo_launch_organise(vlo_handle *h)
         p.R[3] = (float)(sy * cp); p.R[4] = (float)(sy * sp * sr + cy * cr); p.R[5] = (float)(sy * sp * cr - cy * sr);
         p.R[6] = (float)(-sp);     p.R[7] = (float)(cp * sr);                p.R[8] = (float)(cp * cr);
         p.rotate = c.rotate_input ? 1 : 0;
-        p.ring_field = (c.ring_field >= 0 && c.ring_field < sb.stride) ? c.ring_field : -1;
+        p.ring_type = c.ring_field_type;
+        const int ring_bytes = c.ring_field_type == 0 ? 4 : (c.ring_field_type == 1 ? 2 : 1);
+        const int ring_off = c.ring_field_type == 0 ? c.ring_field * 4 : c.ring_field;
+        p.ring_field = (c.ring_field >= 0 && c.ring_field_type >= 0 && c.ring_field_type <= 2 && ring_off + ring_bytes <= sb.stride * 4) ? c.ring_field : -1;
     }
     int B = sb.scan_count; p.scan_first = sb.scan_first;
     vlo_prof_begin(h, ST_ORGANISE);

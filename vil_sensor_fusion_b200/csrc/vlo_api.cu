@@ -30,7 +30,7 @@ extern "C" void vlo_default_config(vlo_config *c)
     c->map_dims[0] = 101; c->map_dims[1] = 51; c->map_dims[2] = 101;
     c->map_start_cubes[0] = 50; c->map_start_cubes[1] = 25; c->map_start_cubes[2] = 50;
     c->n_neighbor_cubes = 5; c->io_ratio = 2; c->hessian_order = 0;
-    c->rotate_input = 0; c->input_rotation[0] = c->input_rotation[1] = c->input_rotation[2] = 0.0f; c->ring_field = -1;
+    c->rotate_input = 0; c->input_rotation[0] = c->input_rotation[1] = c->input_rotation[2] = 0.0f; c->ring_field = -1; c->ring_field_type = 0;
 }
 
 extern "C" int vlo_set_lidar(vlo_config *c, const char *name)
