@@ -13,6 +13,9 @@
 #include <cstring>
 #include <memory>
 #include <thread>
+#include <ucontext.h>
+#include <cstdio>
+#include <cstdlib>
 #include <atomic>
 #include <functional>
 #include <semaphore>
@@ -28,25 +31,166 @@
 #define __launch_bounds__(...)
 #endif
 
-struct EmuWarp { std::barrier<> bar{32}; unsigned long long slot[32]; bool alive[32]; };
-struct EmuCta { std::unique_ptr<std::barrier<>> bar; std::vector<std::unique_ptr<EmuWarp>> warps; };
+// Two ways to run the CUDA threads of a CTA:
+//   default      FIBERS: every CUDA thread is a ucontext fiber of ONE host thread, switched at barriers only -- no futexes, no
+//                kernel, deterministic interleaving; an order of magnitude faster than host threads for barrier-heavy kernels
+//   -DEMU_THREADS  real host threads from a pool, std::barrier -- what ThreadSanitizer / AddressSanitizer need
+#ifdef EMU_THREADS
+struct EmuBar {
+    std::barrier<> bar;
+    explicit EmuBar(int n) : bar(n) {}
+    void wait() { bar.arrive_and_wait(); }
+    void drop() { bar.arrive_and_drop(); }
+};
+#else
+static inline void emu_yield_until(const int *gen, int g);
+struct EmuBar {
+    int expected, arrived = 0, gen = 0;
+    explicit EmuBar(int n) : expected(n) {}
+    void wait()
+    {
+        const int g = gen;
+        if (++arrived == expected) { arrived = 0; gen++; return; }
+        emu_yield_until(&gen, g);
+    }
+    void drop() { if (--expected > 0 && arrived == expected) { arrived = 0; gen++; } }
+};
+#endif
+struct EmuWarp { EmuBar bar{32}; unsigned long long slot[32]; bool alive[32]; };
+struct EmuCta { std::unique_ptr<EmuBar> bar; std::vector<std::unique_ptr<EmuWarp>> warps; };
 inline thread_local uint3 threadIdx, blockIdx;
 inline thread_local dim3 blockDim, gridDim;
 inline thread_local EmuWarp *emu_warp = nullptr;
 inline thread_local EmuCta *emu_cta = nullptr;
 inline thread_local int emu_lane = 0;
 
-static inline void __syncthreads() { emu_cta->bar->arrive_and_wait(); }
-static inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp->bar.arrive_and_wait(); }
+#ifndef EMU_THREADS
+// Context switch between fibers.  glibc's swapcontext saves the signal mask with a system call on every switch, which
+// dominated the emulation; on x86-64 the switch is written out (callee-saved registers + SSE / x87 control words), anywhere
+// else ucontext is used.
+#if defined(__x86_64__)
+extern "C" void emu_switch(void **save_sp, void *load_sp);
+asm(R"(
+    .text
+    .weak emu_switch
+    .type emu_switch,@function
+emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    subq $8, %rsp
+    stmxcsr (%rsp)
+    fnstcw 4(%rsp)
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    ldmxcsr (%rsp)
+    fldcw 4(%rsp)
+    addq $8, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+    .size emu_switch,.-emu_switch
+)");
+struct EmuCtx {
+    void *sp = nullptr;
+    void prepare(char *stack, size_t size, void (*entry)())
+    {
+        uintptr_t top = ((uintptr_t)stack + size) & ~(uintptr_t)15;
+        void **p = (void **)(top - 16);                 // return-address slot: entry() starts with rsp % 16 == 8
+        *p = (void *)entry;
+        p -= 6;                                         // rbp rbx r12 r13 r14 r15
+        for (int i = 0; i < 6; i++) p[i] = nullptr;
+        p -= 1;                                         // mxcsr | x87 control word
+        unsigned mx; unsigned short cw;
+        asm volatile("stmxcsr %0" : "=m"(mx));
+        asm volatile("fnstcw %0" : "=m"(cw));
+        unsigned long long fp = (unsigned long long)mx | ((unsigned long long)cw << 32);
+        memcpy(p, &fp, 8);
+        sp = (void *)p;
+    }
+};
+static inline void emu_ctx_switch(EmuCtx &from, EmuCtx &to) { emu_switch(&from.sp, to.sp); }
+#else
+struct EmuCtx {
+    ucontext_t uc;
+    void prepare(char *stack, size_t size, void (*entry)())
+    { getcontext(&uc); uc.uc_stack.ss_sp = stack; uc.uc_stack.ss_size = size; uc.uc_link = nullptr; makecontext(&uc, entry, 0); }
+};
+static inline void emu_ctx_switch(EmuCtx &from, EmuCtx &to) { swapcontext(&from.uc, &to.uc); }
+#endif
+
+// round-robin fiber scheduler; a fiber parked on a barrier is not even switched to until the barrier's generation moves
+struct EmuFibers {
+    struct Fiber { EmuCtx ctx; const int *wait_gen = nullptr; int wait_val = 0; bool done = false; };
+    static constexpr size_t STACK = 256 * 1024;
+    EmuCtx main_ctx;
+    std::vector<Fiber> fibers;
+    std::vector<char *> stacks;
+    std::function<void(int)> body;
+    EmuCta *cta = nullptr;
+    int cur = -1;
+    static void trampoline();
+    void run(int n, EmuCta *c, std::function<void(int)> f)
+    {
+        body = std::move(f); cta = c;
+        while ((int)stacks.size() < n) stacks.push_back((char *)malloc(STACK));
+        fibers.assign(n, Fiber());
+        for (int t = 0; t < n; t++) fibers[t].ctx.prepare(stacks[t], STACK, &EmuFibers::trampoline);
+        int remaining = n;
+        while (remaining) {
+            bool progress = false;
+            for (int t = 0; t < n; t++) {
+                Fiber &fb = fibers[t];
+                if (fb.done || (fb.wait_gen && *fb.wait_gen == fb.wait_val)) continue;
+                fb.wait_gen = nullptr;
+                cur = t;
+                threadIdx = make_uint3((unsigned)t, 0, 0); emu_warp = cta->warps[t / 32].get(); emu_lane = t % 32;
+                emu_ctx_switch(main_ctx, fb.ctx);
+                progress = true;
+                if (fb.done) remaining--;
+            }
+            if (!progress) { fprintf(stderr, "[cuda emulation] deadlock: every live CUDA thread waits on a barrier\n"); abort(); }
+        }
+        cur = -1;
+    }
+    void park(const int *gen, int g)
+    {
+        Fiber &fb = fibers[cur];
+        fb.wait_gen = gen; fb.wait_val = g;
+        emu_ctx_switch(fb.ctx, main_ctx);
+    }
+};
+inline EmuFibers &emu_fibers() { static EmuFibers *p = new EmuFibers(); return *p; }
+inline void EmuFibers::trampoline()
+{
+    EmuFibers &s = emu_fibers();
+    const int t = s.cur;
+    s.body(t);
+    s.fibers[t].done = true;
+    emu_ctx_switch(s.fibers[t].ctx, s.main_ctx);        // never resumed
+    abort();
+}
+static inline void emu_yield_until(const int *gen, int g) { emu_fibers().park(gen, g); }
+#endif
+
+static inline void __syncthreads() { emu_cta->bar->wait(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp->bar.wait(); }
 static inline void __threadfence() {}
 
 // publish a value, wait, let `f` read every lane's value, wait again (the slots may be overwritten afterwards)
 template <class F> static inline auto emu_collective(unsigned long long mine, F f)
 {
     emu_warp->slot[emu_lane] = mine;
-    emu_warp->bar.arrive_and_wait();
+    emu_warp->bar.wait();
     auto r = f(emu_warp->slot, emu_warp->alive);
-    emu_warp->bar.arrive_and_wait();
+    emu_warp->bar.wait();
     return r;
 }
 template <class T> static inline unsigned long long emu_bits(T v) { unsigned long long u = 0; static_assert(sizeof(T) <= 8, ""); memcpy(&u, &v, sizeof(T)); return u; }
@@ -103,7 +247,7 @@ template <class T> static inline T atomicCAS(T *p, T cmp, T val) { T e = cmp; __
 // cooperative launches run as ONE CTA here (the fake runtime reports one SM and one resident CTA), so a grid sync is the
 // CTA barrier and `__shared__` statics stay private to the only CTA there is
 namespace cooperative_groups {
-struct grid_group { void sync() const { emu_cta->bar->arrive_and_wait(); } };
+struct grid_group { void sync() const { emu_cta->bar->wait(); } };
 static inline grid_group this_grid() { return grid_group(); }
 }
 
@@ -155,16 +299,23 @@ template <class K, class... A> static void emu_launch(K kernel, dim3 grid, dim3 
     const int nthr = (int)block.x, nwarp = nthr / 32;
     for (unsigned bz = 0; bz < grid.z; bz++) for (unsigned by = 0; by < grid.y; by++) for (unsigned bx = 0; bx < grid.x; bx++) {
         EmuCta cta;
-        cta.bar.reset(new std::barrier<>(nthr));
+        cta.bar.reset(new EmuBar(nthr));
         for (int w = 0; w < nwarp; w++) { cta.warps.emplace_back(new EmuWarp()); for (int l = 0; l < 32; l++) cta.warps[w]->alive[l] = true; }
-        emu_pool().run(nthr, [&](int t) {
+        auto body = [&](int t) {
             threadIdx = make_uint3((unsigned)t, 0, 0); blockIdx = make_uint3(bx, by, bz); blockDim = block; gridDim = grid;
             emu_cta = &cta; emu_warp = cta.warps[t / 32].get(); emu_lane = t % 32;
             kernel(args...);
-            emu_warp->alive[emu_lane] = false;          // an exited thread no longer takes part in barriers or collectives
-            emu_warp->bar.arrive_and_drop();
-            cta.bar->arrive_and_drop();
-        });
+            EmuWarp *w = cta.warps[t / 32].get();     // (a fiber's thread-locals are only valid while it runs)
+            w->alive[t % 32] = false;                 // an exited thread no longer takes part in barriers or collectives
+            w->bar.drop();
+            cta.bar->drop();
+        };
+#ifdef EMU_THREADS
+        emu_pool().run(nthr, body);
+#else
+        blockIdx = make_uint3(bx, by, bz); blockDim = block; gridDim = grid; emu_cta = &cta;
+        emu_fibers().run(nthr, &cta, body);
+#endif
     }
 }
 

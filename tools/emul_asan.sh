@@ -3,7 +3,7 @@
 # "Device" memory is calloc'd host memory and `__shared__` arrays are statics, so an out-of-bounds access of a kernel is a
 # heap / global redzone hit.  Usage: bash tools/emul_asan.sh [pytest args]   (default: tests/test_host_library.py)
 export VLO_EMUL_BUILD_DIR=${VLO_EMUL_BUILD_DIR:-/tmp/vlo_emul_asan}
-export VLO_EMUL_EXTRA_FLAGS="-fsanitize=address -fno-omit-frame-pointer"
+export VLO_EMUL_EXTRA_FLAGS="-DEMU_THREADS -fsanitize=address -fno-omit-frame-pointer"
 python tests/host/build_emul.py || exit 1
 ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 LD_PRELOAD=$(gcc -print-file-name=libasan.so) \
     python -m pytest ${@:-tests/test_host_library.py} -x -q -p no:cacheprovider
