@@ -5,5 +5,6 @@
 export VLO_EMUL_BUILD_DIR=${VLO_EMUL_BUILD_DIR:-/tmp/vlo_emul_asan}
 export VLO_EMUL_EXTRA_FLAGS="-DEMU_THREADS -fsanitize=address -fno-omit-frame-pointer"
 python tests/host/build_emul.py || exit 1
+if [ $# -eq 0 ]; then set -- tests/test_host_library.py; fi
 ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 LD_PRELOAD=$(gcc -print-file-name=libasan.so) \
-    python -m pytest ${@:-tests/test_host_library.py} -x -q -p no:cacheprovider
+    python -m pytest "$@" -x -q -p no:cacheprovider
