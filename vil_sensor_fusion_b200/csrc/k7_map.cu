@@ -328,8 +328,10 @@ __global__ void __launch_bounds__(1024) k7_ins_assign(MapInsParams p)
         }
         if (lead) p.lfirst[w][slot] = 0x7fffffff;
         carry += total;
+        // the next round compares lfirst of slots whose leaders have just reset it: order the two (ThreadSanitizer over the
+        // CPU emulation; either value compared unequal, but the accesses were unordered)
+        __syncthreads();
     }
-    __syncthreads();
     if (tid == 0) p.map_n[field] = min(p.cap, n_old + carry);
 }
 
