@@ -24,7 +24,7 @@ def build(force=False):
         return None
     os.makedirs(BUILD, exist_ok=True)
     out = os.path.join(BUILD, "libvlo_emul.so")
-    cus = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+    cus = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu") and not f.startswith("synth_"))      # libvlo_synth.so is a GPU-only bench tool
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HOST, f) for f in ("cuda_emul.h", "fake_cudart.cpp", "gen_emul.py", "build_emul.py")] + \
            [os.path.join(ROOT, "include", "vlo.h")]
     if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):

@@ -91,6 +91,17 @@ def test_ring_capacity_error(orc):
         with pytest.raises(api.VloError) as e:
             h.synchronize()
         assert e.value.code == -3
+        # reported once: the handle stays usable (the reference LOAM has no per-ring cap and carries on with the next sweep)
+        h.synchronize()
+        short = scenes.vlp16_scan(0.1, n_az=900)                # 900 points per ring: fits
+        h.upload([short])
+        h.organise()
+        h.extract()
+        h.synchronize()
+        ocfg = orc.default_config("VLP-16")
+        c, rs, _ = orc.organise(ocfg, short)
+        f = orc.extract(ocfg, c, rs)
+        np.testing.assert_array_equal(h.get_features(0)["label"], f["label"])
 
 
 @pytest.mark.parametrize("lidar", ["HDL-32", "O1-16", "O1-64", "Bperl-32"])

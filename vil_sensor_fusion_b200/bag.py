@@ -17,6 +17,24 @@ def frame_range(n_frames: int, rank: int, world: int) -> tuple[int, int]:
     return (n_frames * rank) // world, (n_frames * (rank + 1)) // world
 
 
+def pair_range(n_frames: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous range [lo, hi) of the scan PAIRS (k, k+1), 0 <= k < n_frames - 1, rank `rank` registers.  The rank loads
+    frames lo .. hi inclusive: the pair that crosses a shard boundary belongs to the lower rank, so the gathered
+    records are exactly the n_frames - 1 pairs in frame order (sharding FRAMES instead would drop one pair per
+    boundary)."""
+    n_pairs = max(n_frames - 1, 0)
+    return (n_pairs * rank) // world, (n_pairs * (rank + 1)) // world
+
+
+def reprocess_pairs_sharded(h: Handle, get_scan, n_frames: int, rank: int, world: int, batch: int, seeds=None, group=None) -> np.ndarray:
+    """Whole-bag scan-to-scan reprocessing on `world` ranks: this rank registers its pair_range, one gather at the end;
+    every rank returns all n_frames - 1 records in frame order."""
+    lo, hi = pair_range(n_frames, rank, world)
+    local = reprocess_pairs(h, get_scan, lo, hi + 1, batch, None if seeds is None else seeds[lo:hi]) if hi > lo else np.zeros(0, RESULT_DTYPE)
+    counts = [pair_range(n_frames, r, world)[1] - pair_range(n_frames, r, world)[0] for r in range(world)]
+    return gather_results(local, group=group, counts=counts)
+
+
 def reprocess_pairs(h: Handle, get_scan, first: int, last: int, batch: int, seeds=None) -> np.ndarray:
     """Registers every consecutive pair (k, k+1) with first <= k < last-1 from `seeds[k]` (or zero):
     frames are processed in resident batches of `batch` scans, overlapping by one frame.
@@ -70,9 +88,13 @@ def reprocess_pairs_from_bag(h: Handle, path: str, cloud_topic: str = "/lidar", 
     return (np.concatenate(out) if out else np.zeros(0, RESULT_DTYPE)), stamps
 
 
-def gather_results(local: np.ndarray, group=None, device=None) -> np.ndarray:
+def gather_results(local: np.ndarray, group=None, device=None, counts=None) -> np.ndarray:
     """The single exchange step: all ranks contribute their result records, every rank receives the
-    concatenation in rank (= frame) order.  Works on NCCL (device tensors over NVLink) and gloo (CPU)."""
+    concatenation in rank (= frame) order.  Works on NCCL (device tensors over NVLink) and gloo (CPU).
+
+    counts: records per rank when every rank can derive them (e.g. from pair_range) -- the exchange is then ONE
+    fixed-size all_gather_into_tensor of the padded record blocks with no count round trip and no host
+    synchronisation before the collective; without it one small all_gather of the counts precedes it."""
     import torch
     import torch.distributed as dist
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
@@ -80,16 +102,20 @@ def gather_results(local: np.ndarray, group=None, device=None) -> np.ndarray:
     world = dist.get_world_size(group)
     backend = dist.get_backend(group)
     dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu"))
-    n_local = torch.tensor([local.shape[0]], dtype=torch.int64, device=dev)
-    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(counts, n_local, group=group)
-    counts = [int(c.item()) for c in counts]
-    nmax = max(counts)
+    if counts is None:
+        n_local = torch.tensor([local.shape[0]], dtype=torch.int64, device=dev)
+        all_n = torch.zeros(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(all_n, n_local, group=group)
+        counts = all_n.tolist()
+    counts = [int(c) for c in counts]
+    assert counts[dist.get_rank(group)] == local.shape[0], "counts[rank] must equal the number of local records"
+    nmax = max(max(counts), 1)
     item = RESULT_DTYPE.itemsize
-    buf = np.zeros(nmax * item, np.uint8)
-    buf[:local.shape[0] * item] = np.frombuffer(np.ascontiguousarray(local).tobytes(), np.uint8)
-    mine = torch.from_numpy(buf).to(dev)
-    parts = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(parts, mine, group=group)
-    out = [np.frombuffer(p.cpu().numpy().tobytes()[:c * item], RESULT_DTYPE) for p, c in zip(parts, counts)]
+    mine = torch.zeros(nmax * item, dtype=torch.uint8, pin_memory=(dev.type == "cuda"))
+    mine[:local.shape[0] * item] = torch.from_numpy(np.frombuffer(np.ascontiguousarray(local).tobytes(), np.uint8).copy())
+    mine = mine.to(dev, non_blocking=True)
+    everything = torch.empty(world * nmax * item, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(everything, mine, group=group)
+    flat = everything.cpu().numpy()
+    out = [np.frombuffer(flat[r * nmax * item:r * nmax * item + c * item].tobytes(), RESULT_DTYPE) for r, c in enumerate(counts)]
     return np.concatenate(out)

@@ -670,7 +670,7 @@ int vlo_launch_extract(vlo_handle *h)
     p.slot_sharp = sb.slot_sharp; p.slot_lsharp = sb.slot_lsharp; p.slot_flat = sb.slot_flat; p.slot_cnt = sb.slot_cnt;
     p.lflat_slotted = sb.lflat_slotted; p.lflat_cnt = sb.lflat_cnt; p.status_word = h->status_word;
     const size_t smem = k1_smem_bytes(p.MR), smem_c = k1c_smem_bytes(p.HT);
-    static size_t configured = 0, configured_c = 0;
+    size_t &configured = h->k1_smem_configured, &configured_c = h->k1c_smem_configured;      // per handle = per device
     if (smem > configured) {
         VLO_CUDA(cudaFuncSetAttribute(k1_extract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;

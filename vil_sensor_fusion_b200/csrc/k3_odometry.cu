@@ -1,16 +1,17 @@
-// K3/K5  scan-to-scan registration (LaserOdometry): association on the voxel-hash grids of the
-// previous sweep + fused linearisation / deterministic reduction / on-device solve.
+// K3  scan-to-scan registration (LaserOdometry): association on the ring-segment box index of the previous sweep
+// (segbox.cuh) + fused linearisation / deterministic reduction / on-device solve.
 // Replaces BasicLaserOdometry::process of the `loam` nodelet (gtsam_fusion/launch/loam.launch:40-45;
 // knobs loam_params.yaml:36-39); SURVEY.md Appendix A.4-A.7 is the algorithm, oracle/laser_odometry.c
 // the frozen operation order (R1 three-level blocked summation, R2..R5).
+//   k3_seg_build : boxes over the ring-major target clouds (32-point arcs, 32-arc groups), one CTA per (scan, cloud)
 //   k3_assoc : one warp per feature point: transformToStart, exact 1-NN, ring-constrained partner
-//              search with upstream's forward/backward tie order, all on the grids (grid.cuh)
+//              search with upstream's forward/backward tie order
 //   k3_gn    : one CTA per scan pair runs up to 5 Gauss-Newton iterations between associations:
 //              thread per correspondence -> 28 products -> shared-memory transposed R1 reduction ->
 //              warp 0 solves (QR), iteration 0 also runs the single-warp Jacobi degeneracy test.
 // The host enqueues [k3_assoc, k3_gn] x ceil(maxIter/5) back to back; convergence is a device flag,
 // so control never returns to the host inside a registration.
-#include "grid.cuh"
+#include "segbox.cuh"
 #include "dense6.cuh"
 #include "odom_lin.cuh"
 #include <algorithm>
@@ -25,7 +26,7 @@ struct OdomParams {
     int n_rings;
     // pairs
     const int *pair_last, *pair_cur; float *pair_T; int *pair_state; int *cidx, *sidx; vlo_result *result;
-    GridSet gc, gsf;                                     // corner / surf grids, grid index = scan index
+    SegSet ss;                                           // ring-segment box index of every resident scan's target clouds
     int deskew; float inv_period; int fwd_quirk;
     int max_iter; float degen_thr, dT_abort, dR_abort, rot_thr, trans_thr;
 };
@@ -35,93 +36,162 @@ __device__ __forceinline__ float4 lflat_point(const OdomParams &p, int scan, int
     return p.lflat_pts[(size_t)scan * p.N + dense];
 }
 
-__global__ void __launch_bounds__(256) k3_assoc(OdomParams p, int n_pairs)
+// ---- ring-segment box index of the target clouds (segbox.cuh): one CTA per (scan, cloud) --------------------------
+#define SEGB_THREADS 512
+struct SegBuildParams {
+    const float4 *pts[2]; size_t stride[2]; const int *ring_start[2];      // dense ring-major clouds + [B][VLO_MAX_RINGS + 1]
+    int n_rings, scan_first;
+    SegSet ss;
+};
+
+__device__ __forceinline__ int seg_cell_of(const float4 lo, const float4 hi, const float *glo, const float *gsc)
 {
-    __shared__ int scratch[8][GRID_SCRATCH_INTS];
-    const int pair = blockIdx.y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    if (p.pair_state[pair * 4 + 0]) return;                          // converged
-    const int last = p.pair_last[pair], cur = p.pair_cur[pair];
-    const int n_sharp = p.counts[cur * 8 + 1], n_flat = p.counts[cur * 8 + 3];
-    const int n_lc = p.counts[last * 8 + 2], n_ls = p.counts[last * 8 + 4];
-    if (!(n_lc > 10 && n_ls > 100)) return;
-    float T[6];
+    const float cx = 0.5f * (lo.x + hi.x), cy = 0.5f * (lo.y + hi.y), cz = 0.5f * (lo.z + hi.z);
+    const int ix = min(15, max(0, (int)((cx - glo[0]) * gsc[0]))), iy = min(3, max(0, (int)((cy - glo[1]) * gsc[1])));
+    const int iz = min(15, max(0, (int)((cz - glo[2]) * gsc[2])));
+    int m = 0;                                   // Morton order in the horizontal plane (x left, z forward), height fastest
     #pragma unroll
-    for (int a = 0; a < 6; a++) T[a] = p.pair_T[pair * 6 + a];
-    // persistent warps stride over the compact query index space [sharp..., flat...]
-    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_sharp + n_flat; w += n_warps) {
-        if (w < n_sharp) {
-            float4 q = vlo_to_start(T, p.sharp_pts[(size_t)cur * p.cap_sharp + w], p.deskew, p.inv_period);
-            TopK<1> nn;
-            grid_search<1>(p.gc, last, q.x, q.y, q.z, 25.0f, FilterAll(), nn, lane, scratch[warp]);
-            int i1 = -1, i2 = -1;
-            if (nn.tag[0] != GRID_NOTAG) {
-                i1 = (int)(nn.tag[0] & 0xFFFFFFu);
-                int ring = (int)(nn.tag[0] >> 24);
-                FilterPartner f; f.ind = i1; f.ring_lo = ring - 2; f.ring_hi = ring + 2; f.skip_ring = ring;
-                f.fwd_bound = p.fwd_quirk ? min(n_sharp, n_lc) : n_lc;
-                TopK<1> pr;
-                grid_search<1>(p.gc, last, q.x, q.y, q.z, 25.0f, f, pr, lane, scratch[warp]);
-                if (pr.tag[0] != GRID_NOTAG) i2 = (int)(pr.tag[0] & 0xFFFFFFu);
-            }
-            if (lane == 0) {
-                int *o = p.cidx + ((size_t)pair * p.cap_sharp + w) * 2;
-                o[0] = i1; o[1] = i2;
-            }
-        } else {
-            int f_i = w - n_sharp;
-            float4 q = vlo_to_start(T, p.flat_pts[(size_t)cur * p.cap_flat + f_i], p.deskew, p.inv_period);
-            TopK<1> nn;
-            grid_search<1>(p.gsf, last, q.x, q.y, q.z, 25.0f, FilterAll(), nn, lane, scratch[warp]);
-            int i1 = -1, i2 = -1, i3 = -1;
-            if (nn.tag[0] != GRID_NOTAG) {
-                i1 = (int)(nn.tag[0] & 0xFFFFFFu);
-                int ring = (int)(nn.tag[0] >> 24);
-                int fb = p.fwd_quirk ? min(n_flat, n_ls) : n_ls;
-                FilterPartner f2; f2.ind = i1; f2.ring_lo = ring; f2.ring_hi = ring; f2.skip_ring = -1; f2.fwd_bound = fb;
-                FilterPartner f3; f3.ind = i1; f3.ring_lo = ring - 2; f3.ring_hi = ring + 2; f3.skip_ring = ring; f3.fwd_bound = fb;
-                TopK<1> p2, p3;
-                grid_search<1>(p.gsf, last, q.x, q.y, q.z, 25.0f, f2, p2, lane, scratch[warp]);
-                grid_search<1>(p.gsf, last, q.x, q.y, q.z, 25.0f, f3, p3, lane, scratch[warp]);
-                if (p2.tag[0] != GRID_NOTAG) i2 = (int)(p2.tag[0] & 0xFFFFFFu);
-                if (p3.tag[0] != GRID_NOTAG) i3 = (int)(p3.tag[0] & 0xFFFFFFu);
-            }
-            if (lane == 0) {
-                int *o = p.sidx + ((size_t)pair * p.cap_flat + f_i) * 3;
-                o[0] = i1; o[1] = i2; o[2] = i3;
-            }
+    for (int b = 0; b < 4; b++) m |= (((ix >> b) & 1) << (2 * b)) | (((iz >> b) & 1) << (2 * b + 1));
+    return (m << 2) | iy;
+}
+
+__device__ __forceinline__ float seg_warp_min(float v) {
+    #pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) v = fminf(v, __shfl_down_sync(0xffffffffu, v, d));
+    return v;
+}
+__device__ __forceinline__ float seg_warp_max(float v) {
+    #pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) v = fmaxf(v, __shfl_down_sync(0xffffffffu, v, d));
+    return v;
+}
+
+__global__ void __launch_bounds__(SEGB_THREADS) k3_seg_build(SegBuildParams p)
+{
+    __shared__ int s_seg_ring[VLO_MAX_RINGS + 1];
+    __shared__ int s_hist[SEG_CELLS];
+    __shared__ int s_wsum[SEGB_THREADS / 32];
+    __shared__ float s_red[6][SEGB_THREADS / 32];
+    __shared__ float s_glo[3], s_gsc[3];
+    const int b = p.scan_first + blockIdx.x, w = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float4 *pts = p.pts[w] + (size_t)b * p.stride[w];
+    const int *rs = p.ring_start[w] + b * (VLO_MAX_RINGS + 1);
+    float4 *fbox = p.ss.fbox[w] + (size_t)b * p.ss.max_seg[w] * 2;
+    float4 *cbox = p.ss.cbox[w] + (size_t)b * p.ss.max_coarse[w] * 2;
+    int *perm = p.ss.perm[w] + (size_t)b * p.ss.max_seg[w];
+    int *seg_ring = p.ss.seg_ring[w] + b * (VLO_MAX_RINGS + 1);
+    const float INF = __int_as_float(0x7f800000);
+    // 1. segments per ring (ceil(n_r / 32)), exclusive prefix
+    if (warp == 0) {
+        int carry = 0;
+        for (int r0 = 0; r0 < p.n_rings; r0 += 32) {
+            const int r = r0 + lane;
+            const int v = r < p.n_rings ? (rs[r + 1] - rs[r] + 31) >> 5 : 0;
+            int inc = v;
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+            if (r < p.n_rings) s_seg_ring[r] = carry + inc - v;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
         }
+        if (lane == 0) s_seg_ring[p.n_rings] = carry;
+    }
+    for (int k = tid; k < SEG_CELLS; k += SEGB_THREADS) s_hist[k] = 0;
+    __syncthreads();
+    const int nseg = min(s_seg_ring[p.n_rings], p.ss.max_seg[w]);
+    for (int r = tid; r <= VLO_MAX_RINGS; r += SEGB_THREADS) seg_ring[r] = min(s_seg_ring[min(r, p.n_rings)], nseg);
+    if (tid == 0) p.ss.nseg[w][b] = nseg;
+    // 2. fine boxes: one warp per segment; the CTA's bounding box of the box centres on the side
+    float blo[3] = { INF, INF, INF }, bhi[3] = { -INF, -INF, -INF };
+    for (int f = warp; f < nseg; f += SEGB_THREADS / 32) {
+        int lo = 0, hi = p.n_rings;                  // ring r with seg_ring[r] <= f < seg_ring[r + 1]
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_seg_ring[mid] <= f) lo = mid; else hi = mid; }
+        const int s0 = rs[lo] + 32 * (f - s_seg_ring[lo]), cnt = min(32, rs[lo + 1] - s0);
+        float x0 = INF, y0 = INF, z0 = INF, x1 = -INF, y1 = -INF, z1 = -INF;
+        if (lane < cnt) { const float4 q = pts[s0 + lane]; x0 = x1 = q.x; y0 = y1 = q.y; z0 = z1 = q.z; }
+        x0 = seg_warp_min(x0); y0 = seg_warp_min(y0); z0 = seg_warp_min(z0);
+        x1 = seg_warp_max(x1); y1 = seg_warp_max(y1); z1 = seg_warp_max(z1);
+        if (lane == 0) {
+            fbox[2 * f] = make_float4(x0, y0, z0, __int_as_float(s0));
+            fbox[2 * f + 1] = make_float4(x1, y1, z1, __int_as_float((lo << 8) | cnt));
+            const float c[3] = { 0.5f * (x0 + x1), 0.5f * (y0 + y1), 0.5f * (z0 + z1) };
+            #pragma unroll
+            for (int a = 0; a < 3; a++) { blo[a] = fminf(blo[a], c[a]); bhi[a] = fmaxf(bhi[a], c[a]); }
+        }
+    }
+    if (lane == 0) {
+        #pragma unroll
+        for (int a = 0; a < 3; a++) { s_red[a][warp] = blo[a]; s_red[3 + a][warp] = bhi[a]; }
+    }
+    __syncthreads();
+    if (tid < 3) {
+        float lo = INF, hi = -INF;
+        for (int k = 0; k < SEGB_THREADS / 32; k++) { lo = fminf(lo, s_red[tid][k]); hi = fmaxf(hi, s_red[3 + tid][k]); }
+        const float ext = hi - lo;
+        s_glo[tid] = lo;
+        s_gsc[tid] = (ext > 1e-6f) ? (tid == 1 ? 4.0f : 16.0f) / ext : 0.0f;
+    }
+    __syncthreads();
+    // 3. counting sort of the segments by the cell of their box centre -> perm
+    for (int f = tid; f < nseg; f += SEGB_THREADS) atomicAdd(&s_hist[seg_cell_of(fbox[2 * f], fbox[2 * f + 1], s_glo, s_gsc)], 1);
+    __syncthreads();
+    {
+        const int k0 = tid * (SEG_CELLS / SEGB_THREADS);         // consecutive cells per thread
+        int loc[SEG_CELLS / SEGB_THREADS], sum = 0;
+        #pragma unroll
+        for (int e = 0; e < SEG_CELLS / SEGB_THREADS; e++) { loc[e] = s_hist[k0 + e]; sum += loc[e]; }
+        int inc = sum;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+        if (lane == 31) s_wsum[warp] = inc;
+        __syncthreads();
+        int off = 0;
+        for (int k = 0; k < warp; k++) off += s_wsum[k];
+        int run = off + inc - sum;
+        #pragma unroll
+        for (int e = 0; e < SEG_CELLS / SEGB_THREADS; e++) { s_hist[k0 + e] = run; run += loc[e]; }
+    }
+    __syncthreads();
+    for (int f = tid; f < nseg; f += SEGB_THREADS)
+        perm[atomicAdd(&s_hist[seg_cell_of(fbox[2 * f], fbox[2 * f + 1], s_glo, s_gsc)], 1)] = f;
+    __syncthreads();
+    // 4. coarse boxes: group c = perm[32 c .. 32 c + 32)
+    const int ncoarse = (nseg + 31) >> 5;
+    for (int c = warp; c < ncoarse; c += SEGB_THREADS / 32) {
+        const int nmem = min(32, nseg - 32 * c);
+        float x0 = INF, y0 = INF, z0 = INF, x1 = -INF, y1 = -INF, z1 = -INF;
+        if (lane < nmem) {
+            const int f = perm[32 * c + lane];
+            const float4 lo = fbox[2 * f], hi = fbox[2 * f + 1];
+            x0 = lo.x; y0 = lo.y; z0 = lo.z; x1 = hi.x; y1 = hi.y; z1 = hi.z;
+        }
+        x0 = seg_warp_min(x0); y0 = seg_warp_min(y0); z0 = seg_warp_min(z0);
+        x1 = seg_warp_max(x1); y1 = seg_warp_max(y1); z1 = seg_warp_max(z1);
+        if (lane == 0) { cbox[2 * c] = make_float4(x0, y0, z0, __int_as_float(nmem)); cbox[2 * c + 1] = make_float4(x1, y1, z1, 0.0f); }
     }
 }
 
-// Batch variant of k3_assoc (whole-bag mode): ONE THREAD per feature point.  The warp-per-query search above spends
-// ~540 warp-instructions per query on its cooperative machinery (27 probes, prefix scan, merge rounds) -- fine for
-// the latency of a single pair, wasteful when thousands of queries are waiting.  Here a thread runs the per-lane
-// 27-cell search of grid.cuh for its own point, once per stage (nearest neighbour, partner(s)) through ONE inlined
-// copy of the search.  Exactness: the 27-cell block around the query's cell contains every point closer than one cell
-// edge, so a hit with d2 < (cell - slack)^2 is the global (d2, tie) minimum; a stage without such a hit (sparse
-// regions, far partners) is redone with the exact warp-cooperative search, one such lane at a time.
-struct FilterOdom {          // mode 0: plain nearest neighbour (tie = dense index); mode 1: FilterPartner's rules
-    int mode, ind, ring_lo, ring_hi, skip_ring, fwd_bound;
-    __device__ __forceinline__ bool operator()(unsigned tag, unsigned &tie) const
-    {
-        const int ring = (int)(tag >> 24), idx = (int)(tag & 0xFFFFFFu);
-        if (mode == 0) { tie = (unsigned)idx; return true; }
-        if (ring < ring_lo || ring > ring_hi || ring == skip_ring || idx == ind) return false;
-        if (idx > ind) { if (idx >= fwd_bound) return false; tie = (unsigned)(idx - ind); }
-        else tie = 0x40000000u + (unsigned)(ind - idx);
-        return true;
-    }
-};
-
-#define K3T_THREADS 128
-#define K3_THREAD_PAIRS 4        // up to this many pairs per call keep the warp-per-query kernel (latency of the online tick)
-__global__ void __launch_bounds__(K3T_THREADS) k3_assoc_thread(OdomParams p, int n_pairs)
+__device__ __forceinline__ SegCloud seg_cloud_of(const OdomParams &p, int w, int scan)
 {
-    __shared__ int scratch[K3T_THREADS / 32][GRID_SCRATCH_INTS];
-    const int pair = blockIdx.y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SegCloud c;
+    c.pts = (w == 0 ? p.lsharp_pts + (size_t)scan * p.cap_lsharp : p.lflat_pts + (size_t)scan * p.N);
+    c.fbox = p.ss.fbox[w] + (size_t)scan * p.ss.max_seg[w] * 2;
+    c.cbox = p.ss.cbox[w] + (size_t)scan * p.ss.max_coarse[w] * 2;
+    c.perm = p.ss.perm[w] + (size_t)scan * p.ss.max_seg[w];
+    c.seg_ring = p.ss.seg_ring[w] + scan * (VLO_MAX_RINGS + 1);
+    c.nseg = p.ss.nseg[w][scan]; c.ncoarse = (c.nseg + 31) >> 5;
+    return c;
+}
+
+// Association: one WARP per feature point of the current sweep -- transformToStart, exact nearest neighbour in the
+// previous sweep's cloud (d2 < 25), ring-constrained partner search(es) with upstream's forward / backward tie order.
+// CTA `chunk` of a pair owns a contiguous share of the pair's queries: its threads transform them once into shared
+// memory (one thread per point), then its warps take them one at a time.
+#define K3A_THREADS 256
+#define K3A_MAXQ 512             // queries per CTA share
+__global__ void __launch_bounds__(K3A_THREADS) k3_assoc(OdomParams p, int n_pairs)
+{
+    __shared__ float4 s_q[K3A_MAXQ];
+    const int pair = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (p.pair_state[pair * 4 + 0]) return;                          // converged
     const int last = p.pair_last[pair], cur = p.pair_cur[pair];
     const int n_sharp = p.counts[cur * 8 + 1], n_flat = p.counts[cur * 8 + 3];
@@ -130,54 +200,45 @@ __global__ void __launch_bounds__(K3T_THREADS) k3_assoc_thread(OdomParams p, int
     float T[6];
     #pragma unroll
     for (int a = 0; a < 6; a++) T[a] = p.pair_T[pair * 6 + a];
-    const int total = n_sharp + n_flat, n_warps = gridDim.x * (K3T_THREADS / 32);
-    for (int base = (blockIdx.x * (K3T_THREADS / 32) + warp) * 32; base < total; base += n_warps * 32) {   // warp-uniform
-        const int w = base + lane;
-        const bool valid = w < total, sharp = w < n_sharp;
-        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) q = vlo_to_start(T, sharp ? p.sharp_pts[(size_t)cur * p.cap_sharp + w] : p.flat_pts[(size_t)cur * p.cap_flat + (w - n_sharp)],
-                                    p.deskew, p.inv_period);
-        const GridSet gs = sharp ? p.gc : p.gsf;
-        const float edge = gs.cell - 2e-3f * gs.cell;
-        const float dfast = fminf(25.0f, edge * edge);
-        const int fb_bound = sharp ? (p.fwd_quirk ? min(n_sharp, n_lc) : n_lc) : (p.fwd_quirk ? min(n_flat, n_ls) : n_ls);
-        int i1 = -1, i2 = -1, i3 = -1, ring = 0;
-        #pragma unroll 1
-        for (int stage = 0; stage < 3; stage++) {
-            const bool act = valid && (stage == 0 || i1 >= 0) && (stage < 2 || !sharp);
-            FilterOdom f;
-            f.mode = stage == 0 ? 0 : 1; f.ind = i1; f.fwd_bound = fb_bound;
-            if (stage == 1 && !sharp) { f.ring_lo = ring; f.ring_hi = ring; f.skip_ring = -1; }      // same-ring partner of a flat point
-            else { f.ring_lo = ring - 2; f.ring_hi = ring + 2; f.skip_ring = ring; }
-            unsigned tag = GRID_NOTAG;
-            if (act) {
-                TopKT<1> best;
-                grid_search_thread27(gs, last, q.x, q.y, q.z, dfast, f, best);
-                tag = best.tag[0];
-            }
-            // stages the 27-cell block could not settle: exact warp-cooperative search, one lane's query at a time
-            unsigned redo = __ballot_sync(0xffffffffu, act && tag == GRID_NOTAG && dfast < 25.0f);
-            while (redo) {
-                const int src = __ffs(redo) - 1;
-                redo &= redo - 1u;
-                FilterOdom g;
-                g.mode = __shfl_sync(0xffffffffu, f.mode, src); g.ind = __shfl_sync(0xffffffffu, f.ind, src);
-                g.ring_lo = __shfl_sync(0xffffffffu, f.ring_lo, src); g.ring_hi = __shfl_sync(0xffffffffu, f.ring_hi, src);
-                g.skip_ring = __shfl_sync(0xffffffffu, f.skip_ring, src); g.fwd_bound = __shfl_sync(0xffffffffu, f.fwd_bound, src);
-                const float bx = __shfl_sync(0xffffffffu, q.x, src), by = __shfl_sync(0xffffffffu, q.y, src), bz = __shfl_sync(0xffffffffu, q.z, src);
-                const bool bsharp = __shfl_sync(0xffffffffu, (int)sharp, src) != 0;
-                TopK<1> r;
-                grid_search<1>(bsharp ? p.gc : p.gsf, last, bx, by, bz, 25.0f, g, r, lane, scratch[warp]);
-                if (lane == src) tag = r.tag[0];
-            }
-            const int idx = (act && tag != GRID_NOTAG) ? (int)(tag & 0xFFFFFFu) : -1;
-            if (stage == 0) { i1 = idx; ring = (int)(tag >> 24); }
-            else if (stage == 1) i2 = idx;
-            else i3 = idx;
+    const SegCloud cc = seg_cloud_of(p, 0, last), cs = seg_cloud_of(p, 1, last);
+    const int total = n_sharp + n_flat;
+    const int R = p.n_rings;
+    for (int base = blockIdx.x * K3A_MAXQ; base < total; base += gridDim.x * K3A_MAXQ) {       // CTA-uniform
+        const int nq = min(K3A_MAXQ, total - base);
+        __syncthreads();
+        for (int k = tid; k < nq; k += K3A_THREADS) {
+            const int wq = base + k;
+            s_q[k] = vlo_to_start(T, wq < n_sharp ? p.sharp_pts[(size_t)cur * p.cap_sharp + wq] : p.flat_pts[(size_t)cur * p.cap_flat + (wq - n_sharp)],
+                                  p.deskew, p.inv_period);
         }
-        if (valid) {
-            if (sharp) { int *o = p.cidx + ((size_t)pair * p.cap_sharp + w) * 2; o[0] = i1; o[1] = i2; }
-            else { int *o = p.sidx + ((size_t)pair * p.cap_flat + (w - n_sharp)) * 3; o[0] = i1; o[1] = i2; o[2] = i3; }
+        __syncthreads();
+        for (int k = warp; k < nq; k += K3A_THREADS / 32) {
+            const int wq = base + k;
+            const float4 q = s_q[k];
+            const bool sharp = wq < n_sharp;
+            const SegCloud &c = sharp ? cc : cs;
+            SegFilter f; f.mode = 0; f.ind = -1; f.ring_lo = 0; f.ring_hi = 0; f.skip_ring = -1; f.fwd_bound = 0;
+            int ring = 0;
+            const int i1 = seg_search(c, -1, -1, -1, q.x, q.y, q.z, 25.0f, f, lane, &ring);
+            int i2 = -1, i3 = -1;
+            if (i1 >= 0) {
+                f.mode = 1; f.ind = i1;
+                f.fwd_bound = sharp ? (p.fwd_quirk ? min(n_sharp, n_lc) : n_lc) : (p.fwd_quirk ? min(n_flat, n_ls) : n_ls);
+                const int rlo = max(ring - 2, 0), rhi = min(ring + 2, R - 1);
+                if (sharp) {
+                    f.ring_lo = ring - 2; f.ring_hi = ring + 2; f.skip_ring = ring;
+                    i2 = seg_search(c, rlo, rhi, ring, q.x, q.y, q.z, 25.0f, f, lane, nullptr);
+                } else {
+                    f.ring_lo = ring; f.ring_hi = ring; f.skip_ring = -1;                     // same-ring partner
+                    i2 = seg_search(c, ring, ring, -1, q.x, q.y, q.z, 25.0f, f, lane, nullptr);
+                    f.ring_lo = ring - 2; f.ring_hi = ring + 2; f.skip_ring = ring;
+                    i3 = seg_search(c, rlo, rhi, ring, q.x, q.y, q.z, 25.0f, f, lane, nullptr);
+                }
+            }
+            if (lane == 0) {
+                if (sharp) { int *o = p.cidx + ((size_t)pair * p.cap_sharp + wq) * 2; o[0] = i1; o[1] = i2; }
+                else { int *o = p.sidx + ((size_t)pair * p.cap_flat + (wq - n_sharp)) * 3; o[0] = i1; o[1] = i2; o[2] = i3; }
+            }
         }
     }
 }
@@ -382,27 +443,25 @@ static OdomParams make_params(vlo_handle *h)
     p.lflat_ring_start = sb.lflat_ring_start; p.counts = sb.counts; p.n_rings = c.n_rings;
     p.pair_last = h->pair_last; p.pair_cur = h->pair_cur; p.pair_T = h->pair_T; p.pair_state = h->pair_state;
     p.cidx = h->pair_cidx; p.sidx = h->pair_sidx; p.result = h->pair_result;
-    p.gc = h->gs_corner; p.gsf = h->gs_surf;
+    p.ss = h->segs;
     p.deskew = c.deskew; p.inv_period = 1.0f / c.scan_period; p.fwd_quirk = c.odom_forward_bound_quirk;
     p.max_iter = c.odom_max_iterations; p.degen_thr = c.odom_degen_eig; p.dT_abort = c.odom_delta_t_abort;
     p.dR_abort = c.odom_delta_r_abort; p.rot_thr = c.dopt_rot_threshold; p.trans_thr = c.dopt_trans_threshold;
     return p;
 }
 
-// builds the corner / surf grids of resident scans [first, first + count) (grid index = scan index)
+// builds the ring-segment box indices of the target clouds of resident scans [first, first + count)
 int vlo_build_scan_grids(vlo_handle *h, int first, int count)
 {
+    if (count <= 0) return VLO_OK;
     ScanBatchDev &sb = h->sb; const vlo_config &c = h->cfg;
-    GridSource sc = {};
-    sc.pts = sb.lsharp_pts; sc.pts_stride = (size_t)h->cap_lsharp; sc.ring_off = nullptr; sc.ring_off_stride = 0;
-    sc.ring_cnt = nullptr; sc.ring_cnt_stride = 0; sc.dense_start = nullptr; sc.dense_start_stride = 0;
-    sc.n_dense = sb.counts; sc.n_dense_stride = 8; sc.n_dense_field = 2; sc.n_rings = c.n_rings; sc.grid_scan = nullptr;
-    int rc = vlo_grid_build(h, h->gs_corner, sc, first, count, h->cap_lsharp); if (rc) return rc;
-    GridSource ss = {};
-    ss.pts = sb.lflat_pts; ss.pts_stride = (size_t)c.max_points; ss.ring_off = nullptr; ss.ring_off_stride = 0;
-    ss.ring_cnt = nullptr; ss.ring_cnt_stride = 0; ss.dense_start = nullptr; ss.dense_start_stride = 0;
-    ss.n_dense = sb.counts; ss.n_dense_stride = 8; ss.n_dense_field = 4; ss.n_rings = c.n_rings; ss.grid_scan = nullptr;
-    rc = vlo_grid_build(h, h->gs_surf, ss, first, count, c.max_points); if (rc) return rc;
+    SegBuildParams q;
+    q.pts[0] = sb.lsharp_pts; q.stride[0] = (size_t)h->cap_lsharp; q.ring_start[0] = sb.lsharp_ring_start;
+    q.pts[1] = sb.lflat_pts; q.stride[1] = (size_t)c.max_points; q.ring_start[1] = sb.lflat_ring_start;
+    q.n_rings = c.n_rings; q.scan_first = first; q.ss = h->segs;
+    VLO_PROF(h, ST_GRID_BUILD, (k3_seg_build<<<dim3(count, 2), SEGB_THREADS, 0, h->stream>>>(q)));
+    h->launches += 1;
+    VLO_CUDA(cudaGetLastError());
     return VLO_OK;
 }
 
@@ -438,17 +497,14 @@ int vlo_launch_register_pairs(vlo_handle *h, int n_pairs, const float *d_seeds, 
     }
     if (only_grid_scan >= 0) { int rc = vlo_build_scan_grids(h, only_grid_scan, 1); if (rc) return rc; h->grids_valid = 1; }
     if (!h->grids_valid) { int rc = vlo_build_scan_grids(h, 0, h->sb.n_scans); if (rc) return rc; h->grids_valid = 1; }
-    // persistent association grid: enough CTAs to fill the machine, warps stride over the queries
-    int n_warps = h->cap_sharp + h->cap_flat;
-    int ctas = (n_warps * 32 + 255) / 256;
-    int fill = (148 * 8 + n_pairs - 1) / n_pairs;
-    dim3 ga(std::max(1, std::min(ctas, fill)), n_pairs);
-    // batches: one thread per query (k3_assoc_thread), never more threads than queries
-    dim3 gt(std::max(1, (h->cap_sharp + h->cap_flat + K3T_THREADS - 1) / K3T_THREADS), n_pairs);
+    // association grid: every CTA owns a contiguous share of its pair's queries, one warp per query; a single pair (the
+    // online tick) is spread over the whole machine, a batch gets a few CTAs per pair
+    const int n_q = h->cap_sharp + h->cap_flat;
+    const int fill = std::max(1, (148 * 4 + n_pairs - 1) / n_pairs);
+    dim3 ga(std::max(1, std::min((n_q + 7) / 8, fill)), n_pairs);
     size_t trace_stride = (size_t)n_pairs * (h->cap_sharp * 2 + h->cap_flat * 3);
     for (int base = 0, round = 0; base < c.odom_max_iterations; base += 5, round++) {
-        if (n_pairs > K3_THREAD_PAIRS) VLO_PROF(h, ST_ASSOC, (k3_assoc_thread<<<gt, K3T_THREADS, 0, h->stream>>>(p, n_pairs)));
-        else VLO_PROF(h, ST_ASSOC, (k3_assoc<<<ga, 256, 0, h->stream>>>(p, n_pairs)));
+        VLO_PROF(h, ST_ASSOC, (k3_assoc<<<ga, K3A_THREADS, 0, h->stream>>>(p, n_pairs)));
         if (h->trace && round < 5) {
             int *dst = h->pair_trace + (size_t)round * trace_stride;
             VLO_CUDA(cudaMemcpyAsync(dst, h->pair_cidx, sizeof(int) * (size_t)n_pairs * h->cap_sharp * 2, cudaMemcpyDeviceToDevice, h->stream));

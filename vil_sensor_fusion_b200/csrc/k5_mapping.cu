@@ -513,7 +513,7 @@ int vlo_launch_register_map(vlo_handle *h, const int *d_scans, int n, const floa
     } else {
         // throughput path: two launches per Gauss-Newton iteration (association, then linearisation + solve), each a
         // persistent grid over the flat tile list of the unconverged slots, never more warps than tiles
-        static int sms = 0, occ_a = 0, occ_l = 0;
+        int &sms = h->dev_sms, &occ_a = h->k5_occ_assoc, &occ_l = h->k5_occ_lin;      // per handle = per device
         if (!sms) {
             VLO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device));
             VLO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a, k5_assoc, KNN_THREADS, 2048));

@@ -761,11 +761,14 @@ extern "C" int vlo_map_process(vlo_handle *h, int scan, const float *seed6, vlo_
     VLO_CUDA(cudaMemcpyAsync(pinfo + 8, lm.sub_n, sizeof(int) * 8, cudaMemcpyDeviceToHost, h->stream));
     VLO_CUDA(cudaMemcpyAsync(pinfo + 16, h->map_n, sizeof(int) * 8, cudaMemcpyDeviceToHost, h->stream));
     rc = vlo_synchronize(h);
+    if (rc && rc != VLO_ERR_CAPACITY) return rc;
+    // a capacity report (map full: new voxels were dropped) leaves the registration result and the map valid: the record
+    // is delivered and the code returned beside it
     h->map_n_host[0] = pinfo[18]; h->map_n_host[1] = pinfo[20];
-    if (rc) { if (rc == VLO_ERR_CAPACITY && h->err.empty()) h->err = "capacity"; return rc; }
     *out = *pres;
     vlo_finish_cov_host(out, &h->cfg);
     h->last_n_map = 1;
     if (info) { info[0] = pinfo[2]; info[1] = pinfo[4]; info[2] = pinfo[10]; info[3] = pinfo[12]; info[4] = pinfo[18]; info[5] = pinfo[20]; }
+    if (rc) return rc;
     return out->status == VLO_SOFT_TOO_FEW_CORR ? VLO_SOFT_TOO_FEW_CORR : VLO_OK;
 }

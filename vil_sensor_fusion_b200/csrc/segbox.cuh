@@ -1,0 +1,174 @@
+// Ring-segment box index: the spatial index of the scan-to-scan association (LaserOdometry, k3_odometry.cu).
+// Replaces pcl::KdTreeFLANN::nearestKSearch + the ring-constrained partner loops of BasicLaserOdometry::process in the
+// `loam` nodelet laserOdometry (gtsam_fusion/launch/loam.launch:40-45).
+//
+// The target clouds of a sweep (less-sharp corners, less-flat surface points) are ring-major arrays: ring r owns the
+// dense indices [ring_start[r], ring_start[r + 1]), consecutive points of a ring are neighbours in space.  The index
+// keeps that order (no sorted copy, the dense index IS the position) and adds two levels of axis-aligned boxes:
+//   fine   segment f = up to 32 consecutive points of ONE ring (an arc); ring r owns segments [seg_ring[r], seg_ring[r + 1])
+//   coarse group c   = 32 fine segments that are close in space: the fine segments are counting-sorted by the cell of
+//                      their box centre on a 16 x 4 x 16 grid over the cloud's bounding box (Morton order), `perm` is
+//                      that order, group c = perm[32 c .. 32 c + 32)
+// A query is answered by ONE WARP: every level is one box test per lane, a ballot, and a 32-wide coalesced scan of
+// the surviving segments -- no divergence, no hash probes, no data-dependent shell expansion (round-1 ncu of the
+// voxel-hash version: 8.9 of 32 lanes active, 13 % of the samples on the probe load, far partners falling back to a
+// cooperative search that walked thousands of empty cells).  Ring-constrained partner searches use the ring-major
+// numbering directly: the admissible rings' segments are one contiguous range.
+//
+// Exactness: a box is skipped only if its lower bound exceeds the best distance found so far.  The bound is computed
+// with the same rounded operations as the point distance -- per-axis gap g = max(lo - q, q - hi, 0) satisfies
+// fl(g) <= fl(|p - q|) for every p in the box because IEEE subtraction is monotone, and so do the squares and the
+// ((x + y) + z) sums -- so lb <= d2 holds in float32, ties included (boxes with lb == best are visited).  Candidates
+// compare by (d2 bits, tie) lexicographically like every arg-min of this library.
+#pragma once
+#include "vlo_internal.cuh"
+
+#define SEG_NONE 0xFFFFFFFFu
+#define SEG_CELLS 1024              // 16 x 4 x 16 cells of the coarse grouping
+
+struct SegCloud {                   // one target cloud of one scan
+    const float4 *pts;              // dense ring-major points, ring = int(w)
+    const float4 *fbox;             // [nseg][2]: lo.xyz | first dense index (int bits), hi.xyz | (ring << 8 | count) (int bits)
+    const float4 *cbox;             // [ncoarse][2]: lo.xyz | member count, hi.xyz
+    const int *perm;                // [nseg] fine segments in coarse-group order
+    const int *seg_ring;            // [R + 1]
+    int nseg, ncoarse;
+};
+
+__device__ __forceinline__ float seg_box_lb2(const float4 lo, const float4 hi, float qx, float qy, float qz)
+{
+    const float gx = fmaxf(fmaxf(lo.x - qx, qx - hi.x), 0.0f);
+    const float gy = fmaxf(fmaxf(lo.y - qy, qy - hi.y), 0.0f);
+    const float gz = fmaxf(fmaxf(lo.z - qz, qz - hi.z), 0.0f);
+    return (gx * gx + gy * gy) + gz * gz;
+}
+
+// candidate admission + tie rule.  mode 0: plain nearest neighbour (tie = dense index, lowest wins);
+// mode 1: upstream's partner loops: forward indices first (ascending), then backward (descending)
+struct SegFilter {
+    int mode, ind, ring_lo, ring_hi, skip_ring, fwd_bound;
+    __device__ __forceinline__ bool operator()(int ring, int idx, unsigned &tie) const
+    {
+        if (mode == 0) { tie = (unsigned)idx; return true; }
+        if (ring < ring_lo || ring > ring_hi || ring == skip_ring || idx == ind) return false;
+        if (idx > ind) { if (idx >= fwd_bound) return false; tie = (unsigned)(idx - ind); }
+        else tie = 0x40000000u + (unsigned)(ind - idx);
+        return true;
+    }
+};
+
+struct SegBest { unsigned d, t; int idx; };      // lane-local best: d = float bits of d2 (or of dmax: none yet)
+
+// the lanes of the warp look at the (up to 32) points of fine segment f
+__device__ __forceinline__ void seg_scan(const SegCloud &c, int f, float qx, float qy, float qz, float dmax, const SegFilter &flt,
+                                         SegBest &best, int lane)
+{
+    const float4 lo = c.fbox[2 * f], hi = c.fbox[2 * f + 1];
+    const int s0 = __float_as_int(lo.w), meta = __float_as_int(hi.w), cnt = meta & 0xff;
+    if (lane < cnt) {
+        const float4 p = c.pts[s0 + lane];
+        unsigned tie;
+        if (flt(meta >> 8, s0 + lane, tie)) {
+            const float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
+            const float d2 = (dx * dx + dy * dy) + dz * dz;
+            const unsigned db = __float_as_uint(d2);
+            if (d2 < dmax && (db < best.d || (db == best.d && tie < best.t))) { best.d = db; best.t = tie; best.idx = s0 + lane; }
+        }
+    }
+}
+
+// Exact warp-cooperative search.  ring_lo < 0: every ring (coarse groups first); otherwise only the fine segments of
+// rings ring_lo .. ring_hi (one contiguous range of the ring-major numbering), skip_ring's segments left out.
+// Returns the dense index of the (d2, tie) minimum among admissible points with d2 < dmax, or -1; every lane gets it.
+__device__ __forceinline__ int seg_search(const SegCloud &c, int ring_lo, int ring_hi, int skip_ring, float qx, float qy, float qz,
+                                          float dmax, const SegFilter &flt, int lane, int *ring_out)
+{
+    const unsigned dmaxb = __float_as_uint(dmax);
+    SegBest best; best.d = dmaxb; best.t = 0xFFFFFFFFu; best.idx = -1;
+    unsigned bound = dmaxb;                      // float bits of the best d2 any lane holds (dmax: none yet)
+    if (ring_lo < 0) {
+        // ---- phase A: the coarse group nearest to the query, its nearest fine segment -> a first bound
+        float my = __int_as_float(0x7f800000); int myc = -1;
+        for (int cb = lane; cb < c.ncoarse; cb += 32) {
+            const float lb = seg_box_lb2(c.cbox[2 * cb], c.cbox[2 * cb + 1], qx, qy, qz);
+            if (lb < my) { my = lb; myc = cb; }
+        }
+        const unsigned m = __reduce_min_sync(0xffffffffu, myc >= 0 ? __float_as_uint(my) : 0x7f800000u);
+        if (!(m < dmaxb)) { if (ring_out) *ring_out = 0; return -1; }      // nothing closer than dmax (also: empty cloud, NaN query)
+        {
+            const int src = __ffs(__ballot_sync(0xffffffffu, myc >= 0 && __float_as_uint(my) == m)) - 1;
+            const int cstar = __shfl_sync(0xffffffffu, myc, src);
+            const int nmem = __float_as_int(c.cbox[2 * cstar].w);
+            int f = -1; float lbf = __int_as_float(0x7f800000);
+            if (lane < nmem) { f = c.perm[32 * cstar + lane]; lbf = seg_box_lb2(c.fbox[2 * f], c.fbox[2 * f + 1], qx, qy, qz); }
+            const unsigned mf = __reduce_min_sync(0xffffffffu, __float_as_uint(lbf));
+            const int srcf = __ffs(__ballot_sync(0xffffffffu, f >= 0 && __float_as_uint(lbf) == mf)) - 1;
+            seg_scan(c, __shfl_sync(0xffffffffu, f, srcf), qx, qy, qz, dmax, flt, best, lane);
+            bound = __reduce_min_sync(0xffffffffu, best.d);
+        }
+        // ---- phase B: every coarse group / fine segment whose box can hold a point at least as close
+        for (int cb0 = 0; cb0 < c.ncoarse; cb0 += 32) {
+            const int cb = cb0 + lane;
+            float lbc = __int_as_float(0x7f800000);
+            if (cb < c.ncoarse) lbc = seg_box_lb2(c.cbox[2 * cb], c.cbox[2 * cb + 1], qx, qy, qz);
+            unsigned cmask = __ballot_sync(0xffffffffu, __float_as_uint(lbc) <= bound && lbc < dmax);
+            while (cmask) {
+                const int j = __ffs(cmask) - 1;
+                cmask &= cmask - 1u;
+                if (__float_as_uint(__shfl_sync(0xffffffffu, lbc, j)) > bound) continue;      // the bound has tightened since the ballot
+                const int cc = cb0 + j;
+                const int nmem = __float_as_int(c.cbox[2 * cc].w);
+                int f = -1; float lbf = __int_as_float(0x7f800000);
+                if (lane < nmem) { f = c.perm[32 * cc + lane]; lbf = seg_box_lb2(c.fbox[2 * f], c.fbox[2 * f + 1], qx, qy, qz); }
+                unsigned fmask = __ballot_sync(0xffffffffu, f >= 0 && __float_as_uint(lbf) <= bound && lbf < dmax);
+                while (fmask) {
+                    const int k = __ffs(fmask) - 1;
+                    fmask &= fmask - 1u;
+                    seg_scan(c, __shfl_sync(0xffffffffu, f, k), qx, qy, qz, dmax, flt, best, lane);
+                }
+                bound = __reduce_min_sync(0xffffffffu, best.d);
+            }
+        }
+    } else {
+        const int f0 = c.seg_ring[ring_lo], f1 = c.seg_ring[ring_hi + 1];
+        // ---- phase A: nearest admissible fine segment of the range -> a first bound
+        float my = __int_as_float(0x7f800000); int myf = -1;
+        for (int f = f0 + lane; f < f1; f += 32) {
+            const float4 hi = c.fbox[2 * f + 1];
+            if ((__float_as_int(hi.w) >> 8) == skip_ring) continue;
+            const float lb = seg_box_lb2(c.fbox[2 * f], hi, qx, qy, qz);
+            if (lb < my) { my = lb; myf = f; }
+        }
+        const unsigned m = __reduce_min_sync(0xffffffffu, myf >= 0 ? __float_as_uint(my) : 0x7f800000u);
+        if (!(m < dmaxb)) { if (ring_out) *ring_out = 0; return -1; }
+        {
+            const int src = __ffs(__ballot_sync(0xffffffffu, myf >= 0 && __float_as_uint(my) == m)) - 1;
+            seg_scan(c, __shfl_sync(0xffffffffu, myf, src), qx, qy, qz, dmax, flt, best, lane);
+            bound = __reduce_min_sync(0xffffffffu, best.d);
+        }
+        // ---- phase B
+        for (int fb0 = f0; fb0 < f1; fb0 += 32) {
+            const int f = fb0 + lane;
+            float lbf = __int_as_float(0x7f800000);
+            if (f < f1) {
+                const float4 hi = c.fbox[2 * f + 1];
+                if ((__float_as_int(hi.w) >> 8) != skip_ring) lbf = seg_box_lb2(c.fbox[2 * f], hi, qx, qy, qz);
+            }
+            unsigned fmask = __ballot_sync(0xffffffffu, __float_as_uint(lbf) <= bound && lbf < dmax);
+            while (fmask) {
+                const int k = __ffs(fmask) - 1;
+                fmask &= fmask - 1u;
+                seg_scan(c, fb0 + k, qx, qy, qz, dmax, flt, best, lane);
+            }
+            bound = __reduce_min_sync(0xffffffffu, best.d);
+        }
+    }
+    // ---- (d2, tie) minimum over the lanes
+    const unsigned md = __reduce_min_sync(0xffffffffu, best.idx >= 0 ? best.d : 0xFFFFFFFFu);
+    if (md == 0xFFFFFFFFu) { if (ring_out) *ring_out = 0; return -1; }
+    const unsigned mt = __reduce_min_sync(0xffffffffu, (best.idx >= 0 && best.d == md) ? best.t : 0xFFFFFFFFu);
+    const int src = __ffs(__ballot_sync(0xffffffffu, best.idx >= 0 && best.d == md && best.t == mt)) - 1;
+    const int idx = __shfl_sync(0xffffffffu, best.idx, src);
+    if (ring_out) *ring_out = (int)c.pts[idx].w;
+    return idx;
+}

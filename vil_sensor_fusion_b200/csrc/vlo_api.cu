@@ -97,12 +97,13 @@ extern "C" int vlo_create(const vlo_config *cfg, vlo_handle **out)
     vlo_handle *h = new vlo_handle();
     h->cfg = c; h->launches = 0; h->pinned = nullptr; h->pinned_bytes = 0; h->upload_pinned = nullptr;
     memset(&h->sb, 0, sizeof(h->sb)); memset(&h->lm, 0, sizeof(h->lm));
-    memset(&h->gs_corner, 0, sizeof(GridSet)); memset(&h->gs_surf, 0, sizeof(GridSet)); memset(h->gs_map, 0, sizeof(h->gs_map));
+    memset(&h->segs, 0, sizeof(SegSet)); memset(h->gs_map, 0, sizeof(h->gs_map));
     h->map_pts[0] = h->map_pts[1] = nullptr; h->map_n = nullptr; h->map_n_host[0] = h->map_n_host[1] = 0;
     h->grids_valid = 0; h->trace = 0; h->pair_last_T = nullptr;
     h->status_word = nullptr; h->pair_T = h->pair_seed = nullptr; h->pair_last = h->pair_cur = h->pair_state = nullptr;
     h->pair_cidx = h->pair_sidx = h->pair_trace = nullptr; h->pair_result = nullptr;
     h->map_partials = nullptr; h->map_idx5 = nullptr; h->map_T = h->map_seed = nullptr; h->map_state = h->map_ncorr = h->map_scans = h->map_done = nullptr;
+    h->k1_smem_configured = h->k1c_smem_configured = 0; h->dev_sms = h->k5_occ_assoc = h->k5_occ_lin = 0;
     h->map_result = nullptr; h->coop_resident = 0; h->map_qmax = 0; h->last_n_map = 0; h->last_n_pairs = 0;
     h->imu_buf = nullptr; h->imu_buf_bytes = 0; h->imu_out = nullptr; h->imu_out_cap = 0;
     h->online_have_last = 0; h->online_slot = 0; h->prof_enabled = 0; h->prof_used = 0;
@@ -141,8 +142,14 @@ extern "C" int vlo_create(const vlo_config *cfg, vlo_handle **out)
     HALLOC(h->pair_trace, (size_t)B * 5 * (h->cap_sharp * 2 + h->cap_flat * 3));
     HALLOC(h->pair_result, (size_t)B);
     HALLOC(h->pair_last_T, (size_t)B * 6);
-    { int rc = alloc_gridset(h, h->gs_corner, B, h->cap_lsharp, c.odom_corner_cell_size > 0.f ? c.odom_corner_cell_size : 5.0f); if (rc) { vlo_destroy(h); return rc; } }
-    { int rc = alloc_gridset(h, h->gs_surf, B, N, c.odom_cell_size); if (rc) { vlo_destroy(h); return rc; } }
+    // ring-segment box indices of the scan-to-scan target clouds (segbox.cuh): 32-point arcs, at most one partial arc per ring
+    for (int w = 0; w < 2; w++) {
+        SegSet &ss = h->segs;
+        ss.max_seg[w] = (w == 0 ? h->cap_lsharp : N) / 32 + R + 1;
+        ss.max_coarse[w] = ss.max_seg[w] / 32 + 1;
+        HALLOC(ss.fbox[w], (size_t)B * ss.max_seg[w] * 2); HALLOC(ss.cbox[w], (size_t)B * ss.max_coarse[w] * 2);
+        HALLOC(ss.perm[w], (size_t)B * ss.max_seg[w]); HALLOC(ss.seg_ring[w], (size_t)B * (VLO_MAX_RINGS + 1)); HALLOC(ss.nseg[w], (size_t)B);
+    }
     HALLOC(h->map_n, 8);
     cudaMemset(h->map_n, 0, 8 * sizeof(int));
     if (c.max_map_points > 0) {
@@ -177,7 +184,8 @@ extern "C" void vlo_destroy(vlo_handle *h)
                      h->map_scans, h->map_result, h->imu_buf, h->imu_out };
     for (void *p : ptrs) if (p) cudaFree(p);
     vlo_lm_free(h);
-    free_gridset(h->gs_corner); free_gridset(h->gs_surf); free_gridset(h->gs_map[0]); free_gridset(h->gs_map[1]);
+    for (int w = 0; w < 2; w++) { cudaFree(h->segs.fbox[w]); cudaFree(h->segs.cbox[w]); cudaFree(h->segs.perm[w]); cudaFree(h->segs.seg_ring[w]); cudaFree(h->segs.nseg[w]); }
+    free_gridset(h->gs_map[0]); free_gridset(h->gs_map[1]);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->upload_pinned) { cudaFreeHost(h->upload_pinned); cudaEventDestroy(h->upload_ev[0]); cudaEventDestroy(h->upload_ev[1]); }
     for (auto &e : h->prof_events) cudaEventDestroy(e);
@@ -194,13 +202,14 @@ extern "C" int vlo_synchronize(vlo_handle *h)
     VLO_CUDA(cudaStreamSynchronize(h->stream));
     int st = 0;
     VLO_CUDA(cudaMemcpy(&st, h->status_word, sizeof(int), cudaMemcpyDeviceToHost));
-    if (st & 1) { h->err = "a ring holds more points than max_ring_points"; return VLO_ERR_CAPACITY; }
-    if (st & 2) {       // reported once: the map keeps working with the voxels it has
-        int cleared = st & ~2;
-        cudaMemcpy(h->status_word, &cleared, sizeof(int), cudaMemcpyHostToDevice);
-        h->err = "the maintained map is full (max_map_points): new voxels were dropped"; return VLO_ERR_CAPACITY;
-    }
-    return VLO_OK;
+    if (!st) return VLO_OK;
+    // both conditions are reported ONCE and cleared: the oversized ring was skipped for that sweep only (the reference
+    // has no per-ring cap and carries on with the next sweep), the map keeps working with the voxels it has
+    const int zero = 0;
+    VLO_CUDA(cudaMemcpy(h->status_word, &zero, sizeof(int), cudaMemcpyHostToDevice));
+    if (st & 1) { h->err = "a ring holds more points than max_ring_points (that ring yielded no features)"; return VLO_ERR_CAPACITY; }
+    h->err = "the maintained map is full (max_map_points): new voxels were dropped";
+    return VLO_ERR_CAPACITY;
 }
 
 extern "C" int vlo_scans_upload_pc2(vlo_handle *h, const void *data, const int *offsets, int n_scans, int point_step,

@@ -278,6 +278,10 @@ extern "C" int vlo_process_scan(vlo_handle *h, const float *raw, int n_points, i
     h->map_qmax = 0;
     vlo_result *pres = (vlo_result *)h->pinned;
     int soft = VLO_OK;
+    // a capacity report (oversized ring, map full) concerns this sweep only: the tick's state (slots, transformSum, map pose)
+    // still advances, the code is returned at the end -- the next tick then registers against THIS sweep, as the
+    // reference's nodelets would
+    int deferred = VLO_OK;
     bool did_odom = false;
     if (h->online_have_last) {
         int *pl = poff + 2;                                      // pinned staging (after the offsets)
@@ -296,7 +300,8 @@ extern "C" int vlo_process_scan(vlo_handle *h, const float *raw, int n_points, i
         // transformToEnd of this sweep's target clouds with its own transform (device-resident, no host round trip):
         // they are the next tick's `last` clouds and the stack LaserMapping receives
         if (h->cfg.deskew) { rc = vlo_launch_to_end(h, h->pair_cur, h->pair_T, 1); if (rc) return rc; }
-        rc = vlo_synchronize(h); if (rc) return rc;
+        rc = vlo_synchronize(h);
+        if (rc == VLO_ERR_CAPACITY) deferred = rc; else if (rc) return rc;
         h->last_n_pairs = 1;
         vlo_finish_cov_host(pres, &h->cfg);
         if (pres->status == VLO_OK) memcpy(h->online_T, pres->transform, sizeof(float) * 6);
@@ -305,7 +310,8 @@ extern "C" int vlo_process_scan(vlo_handle *h, const float *raw, int n_points, i
         if (odom) *odom = *pres;
         did_odom = true;
     } else {
-        rc = vlo_synchronize(h); if (rc) return rc;
+        rc = vlo_synchronize(h);
+        if (rc == VLO_ERR_CAPACITY) deferred = rc; else if (rc) return rc;
     }
     if (!did_odom && odom) { memset(odom, 0, sizeof(*odom)); for (int a = 0; a < 6; a++) odom->P[a * 7] = 1.0f; odom->status = VLO_SOFT_TOO_FEW_CORR; }
     if (mapped) {
@@ -329,7 +335,8 @@ extern "C" int vlo_process_scan(vlo_handle *h, const float *raw, int n_points, i
                 // maintained map: the whole BasicLaserMapping::process (sub-map, optimisation, insertion)
                 mrc = vlo_map_process(h, cur, seed, mapped, nullptr);
             }
-            if (mrc < 0) return mrc;
+            if (mrc == VLO_ERR_CAPACITY) deferred = mrc;        // the record in `mapped` is valid (vlo_map_process fills it)
+            else if (mrc < 0) return mrc;
             if (mapped->status == VLO_OK || h->lm.mode != 1) {
                 // transformUpdate: upstream stores the pose whether or not the optimisation ran
                 memcpy(h->online_map_aft, mapped->transform, sizeof(float) * 6); memcpy(h->online_map_bef, h->online_sum, sizeof(float) * 6);
@@ -338,7 +345,7 @@ extern "C" int vlo_process_scan(vlo_handle *h, const float *raw, int n_points, i
         }
     }
     h->online_have_last = 1; h->online_slot = last; h->online_ticks++;
-    return soft;
+    return deferred ? deferred : soft;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -51,6 +51,12 @@ struct GridSource {
     int mask_lo[3], mask_side;                   // cube coordinates of mask bit (0,0,0); side = 2 nb + 1
 };
 
+// ring-segment box indices of the scan-to-scan target clouds (segbox.cuh): per resident scan, cloud 0 = less sharp, 1 = less flat
+struct SegSet {
+    float4 *fbox[2]; float4 *cbox[2]; int *perm[2]; int *seg_ring[2]; int *nseg[2];
+    int max_seg[2], max_coarse[2];
+};
+
 // Device-resident state of a batch of scans (capacities from vlo_config)
 struct ScanBatchDev {
     int    n_scans;
@@ -130,8 +136,8 @@ struct vlo_handle {
     vlo_result *pair_result;   // device results [P]
     float *pair_last_T;        // [P][6] staging of last_transforms
     int grids_valid, trace, last_n_pairs;
-    // grids for scan-to-scan targets (grid index = scan index) and the map (0 corner, 1 surf)
-    GridSet gs_corner, gs_surf;
+    // box indices of the scan-to-scan targets (per resident scan) and the voxel-hash grids of the map (0 corner, 1 surf)
+    SegSet segs;
     GridSet gs_map[2];
     float4 *map_pts[2];
     int *map_n;                // device [8]: [2] = n_corner, [4] = n_surf (same layout as counts rows)
@@ -142,6 +148,10 @@ struct vlo_handle {
     float *map_T; float *map_seed; int *map_state; int *map_ncorr; int *map_done; int *map_scans; vlo_result *map_result;
     int map_qmax, last_n_map;
     int coop_resident;
+    // per-device launch configuration, cached per HANDLE (function attributes and occupancy are per device; a process may
+    // hold handles on several devices)
+    size_t k1_smem_configured, k1c_smem_configured;
+    int dev_sms, k5_occ_assoc, k5_occ_lin;
     LaserMapDev lm;
     // IMU staging (grown on demand)
     double *imu_buf; size_t imu_buf_bytes; vlo_preint *imu_out; int imu_out_cap;
