@@ -8,7 +8,7 @@ pool = [synth.make_scan(scene, "HDL-64E", t0=0.1 * k, traj=traj, rolling=False, 
 B = 128
 order = list(range(8)) + list(range(6, 0, -1))
 raws = [pool[order[k % len(order)]] for k in range(B)]
-cfg = api.default_config("HDL-64E", deskew=0, max_scans=B, max_points=131072, odom_cell_size=0.7)
+cfg = api.default_config("HDL-64E", deskew=0, max_scans=B, max_points=131072)
 with api.Handle(cfg) as h:
     for rep in range(3):
         h.upload(raws); h.organise(); h.extract()

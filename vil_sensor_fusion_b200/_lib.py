@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libvlo.so")
+# VLO_LIB_PATH: load another build of the same library (tuning experiments: tools/build_variant.py)
+LIB_PATH = os.environ.get("VLO_LIB_PATH") or os.path.join(HERE, "lib", "libvlo.so")
 
 
 class Config(C.Structure):

@@ -11,7 +11,13 @@
 //              warp 0 solves (QR), iteration 0 also runs the single-warp Jacobi degeneracy test.
 // The host enqueues [k3_assoc, k3_gn] x ceil(maxIter/5) back to back; convergence is a device flag,
 // so control never returns to the host inside a registration.
+#include "grid.cuh"
 #include "segbox.cuh"
+#ifndef K3_ONLINE_GRID
+#define K3_ONLINE_GRID 1         // 1: a call of up to K3_THREAD_PAIRS pairs (the online tick) keeps round 1's voxel-hash warp kernel:
+                                 // with the whole machine on ONE pair its latency is lower (HDL-64 tick p50 0.90 vs 1.50 ms)
+#endif
+#define K3_THREAD_PAIRS 4
 #include "dense6.cuh"
 #include "odom_lin.cuh"
 #include <algorithm>
@@ -26,7 +32,8 @@ struct OdomParams {
     int n_rings;
     // pairs
     const int *pair_last, *pair_cur; float *pair_T; int *pair_state; int *cidx, *sidx; vlo_result *result;
-    SegSet ss;                                           // ring-segment box index of every resident scan's target clouds
+    GridSet gc, gsf;                                     // corner / surf voxel-hash grids, grid index = scan index
+    SegSet ss;                                           // ring-segment box index of every resident scan's target clouds (batches)
     int deskew; float inv_period; int fwd_quirk;
     int max_iter; float degen_thr, dT_abort, dR_abort, rot_thr, trans_thr;
 };
@@ -81,12 +88,12 @@ __global__ void __launch_bounds__(SEGB_THREADS) k3_seg_build(SegBuildParams p)
     int *perm = p.ss.perm[w] + (size_t)b * p.ss.max_seg[w];
     int *seg_ring = p.ss.seg_ring[w] + b * (VLO_MAX_RINGS + 1);
     const float INF = __int_as_float(0x7f800000);
-    // 1. segments per ring (ceil(n_r / 32)), exclusive prefix
+    // 1. segments per ring (ceil(n_r / SEG_PTS)), exclusive prefix
     if (warp == 0) {
         int carry = 0;
         for (int r0 = 0; r0 < p.n_rings; r0 += 32) {
             const int r = r0 + lane;
-            const int v = r < p.n_rings ? (rs[r + 1] - rs[r] + 31) >> 5 : 0;
+            const int v = r < p.n_rings ? (rs[r + 1] - rs[r] + SEG_PTS - 1) / SEG_PTS : 0;
             int inc = v;
             #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
@@ -100,27 +107,46 @@ __global__ void __launch_bounds__(SEGB_THREADS) k3_seg_build(SegBuildParams p)
     const int nseg = min(s_seg_ring[p.n_rings], p.ss.max_seg[w]);
     for (int r = tid; r <= VLO_MAX_RINGS; r += SEGB_THREADS) seg_ring[r] = min(s_seg_ring[min(r, p.n_rings)], nseg);
     if (tid == 0) p.ss.nseg[w][b] = nseg;
-    // 2. fine boxes: one warp per segment; the CTA's bounding box of the box centres on the side
-    float blo[3] = { INF, INF, INF }, bhi[3] = { -INF, -INF, -INF };
-    for (int f = warp; f < nseg; f += SEGB_THREADS / 32) {
-        int lo = 0, hi = p.n_rings;                  // ring r with seg_ring[r] <= f < seg_ring[r + 1]
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_seg_ring[mid] <= f) lo = mid; else hi = mid; }
-        const int s0 = rs[lo] + 32 * (f - s_seg_ring[lo]), cnt = min(32, rs[lo + 1] - s0);
-        float x0 = INF, y0 = INF, z0 = INF, x1 = -INF, y1 = -INF, z1 = -INF;
-        if (lane < cnt) { const float4 q = pts[s0 + lane]; x0 = x1 = q.x; y0 = y1 = q.y; z0 = z1 = q.z; }
-        x0 = seg_warp_min(x0); y0 = seg_warp_min(y0); z0 = seg_warp_min(z0);
-        x1 = seg_warp_max(x1); y1 = seg_warp_max(y1); z1 = seg_warp_max(z1);
-        if (lane == 0) {
-            fbox[2 * f] = make_float4(x0, y0, z0, __int_as_float(s0));
-            fbox[2 * f + 1] = make_float4(x1, y1, z1, __int_as_float((lo << 8) | cnt));
-            const float c[3] = { 0.5f * (x0 + x1), 0.5f * (y0 + y1), 0.5f * (z0 + z1) };
+    // 2. fine boxes: a lane group of SEG_PTS lanes per segment
+    {
+        const int g = lane >> SEG_SHIFT, l = lane & (SEG_PTS - 1);
+        for (int fb = warp * SEG_GROUPS; fb < nseg; fb += (SEGB_THREADS / 32) * SEG_GROUPS) {       // warp-uniform
+            const int f = fb + g;
+            int lo = 0, hi = p.n_rings, s0 = 0, cnt = 0;
+            if (f < nseg) {
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_seg_ring[mid] <= f) lo = mid; else hi = mid; }   // ring of segment f
+                s0 = rs[lo] + SEG_PTS * (f - s_seg_ring[lo]); cnt = min(SEG_PTS, rs[lo + 1] - s0);
+            }
+            float x0 = INF, y0 = INF, z0 = INF, x1 = -INF, y1 = -INF, z1 = -INF;
+            if (l < cnt) { const float4 q = pts[s0 + l]; x0 = x1 = q.x; y0 = y1 = q.y; z0 = z1 = q.z; }
+            #pragma unroll
+            for (int d = SEG_PTS / 2; d >= 1; d >>= 1) {       // the group's lane 0 ends up with the group's extrema
+                x0 = fminf(x0, __shfl_down_sync(0xffffffffu, x0, d)); y0 = fminf(y0, __shfl_down_sync(0xffffffffu, y0, d));
+                z0 = fminf(z0, __shfl_down_sync(0xffffffffu, z0, d)); x1 = fmaxf(x1, __shfl_down_sync(0xffffffffu, x1, d));
+                y1 = fmaxf(y1, __shfl_down_sync(0xffffffffu, y1, d)); z1 = fmaxf(z1, __shfl_down_sync(0xffffffffu, z1, d));
+            }
+            if (l == 0 && f < nseg) {
+                fbox[2 * f] = make_float4(x0, y0, z0, __int_as_float(s0));
+                fbox[2 * f + 1] = make_float4(x1, y1, z1, __int_as_float((lo << 8) | cnt));
+            }
+        }
+    }
+    __syncthreads();
+    // bounding box of the box centres
+    {
+        float blo[3] = { INF, INF, INF }, bhi[3] = { -INF, -INF, -INF };
+        for (int f = tid; f < nseg; f += SEGB_THREADS) {
+            const float4 lo = fbox[2 * f], hi = fbox[2 * f + 1];
+            const float c[3] = { 0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z) };
             #pragma unroll
             for (int a = 0; a < 3; a++) { blo[a] = fminf(blo[a], c[a]); bhi[a] = fmaxf(bhi[a], c[a]); }
         }
-    }
-    if (lane == 0) {
         #pragma unroll
-        for (int a = 0; a < 3; a++) { s_red[a][warp] = blo[a]; s_red[3 + a][warp] = bhi[a]; }
+        for (int a = 0; a < 3; a++) { blo[a] = seg_warp_min(blo[a]); bhi[a] = seg_warp_max(bhi[a]); }
+        if (lane == 0) {
+            #pragma unroll
+            for (int a = 0; a < 3; a++) { s_red[a][warp] = blo[a]; s_red[3 + a][warp] = bhi[a]; }
+        }
     }
     __syncthreads();
     if (tid < 3) {
@@ -182,13 +208,83 @@ __device__ __forceinline__ SegCloud seg_cloud_of(const OdomParams &p, int w, int
     return c;
 }
 
-// Association: one WARP per feature point of the current sweep -- transformToStart, exact nearest neighbour in the
-// previous sweep's cloud (d2 < 25), ring-constrained partner search(es) with upstream's forward / backward tie order.
-// CTA `chunk` of a pair owns a contiguous share of the pair's queries: its threads transform them once into shared
-// memory (one thread per point), then its warps take them one at a time.
-#define K3A_THREADS 256
-#define K3A_MAXQ 512             // queries per CTA share
-__global__ void __launch_bounds__(K3A_THREADS) k3_assoc(OdomParams p, int n_pairs)
+#if K3_ONLINE_GRID
+// Online tick (a few pairs): one warp per feature point on the voxel-hash grids (grid.cuh grid_search: shells of cells
+// resolved cooperatively), the whole machine on one pair.
+__global__ void __launch_bounds__(256) k3_assoc_warp(OdomParams p, int n_pairs)
+{
+    __shared__ int scratch[8][GRID_SCRATCH_INTS];
+    const int pair = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    if (p.pair_state[pair * 4 + 0]) return;                          // converged
+    const int last = p.pair_last[pair], cur = p.pair_cur[pair];
+    const int n_sharp = p.counts[cur * 8 + 1], n_flat = p.counts[cur * 8 + 3];
+    const int n_lc = p.counts[last * 8 + 2], n_ls = p.counts[last * 8 + 4];
+    if (!(n_lc > 10 && n_ls > 100)) return;
+    float T[6];
+    #pragma unroll
+    for (int a = 0; a < 6; a++) T[a] = p.pair_T[pair * 6 + a];
+    // persistent warps stride over the compact query index space [sharp..., flat...]
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_sharp + n_flat; w += n_warps) {
+        if (w < n_sharp) {
+            float4 q = vlo_to_start(T, p.sharp_pts[(size_t)cur * p.cap_sharp + w], p.deskew, p.inv_period);
+            TopK<1> nn;
+            grid_search<1>(p.gc, last, q.x, q.y, q.z, 25.0f, FilterAll(), nn, lane, scratch[warp]);
+            int i1 = -1, i2 = -1;
+            if (nn.tag[0] != GRID_NOTAG) {
+                i1 = (int)(nn.tag[0] & 0xFFFFFFu);
+                int ring = (int)(nn.tag[0] >> 24);
+                FilterPartner f; f.ind = i1; f.ring_lo = ring - 2; f.ring_hi = ring + 2; f.skip_ring = ring;
+                f.fwd_bound = p.fwd_quirk ? min(n_sharp, n_lc) : n_lc;
+                TopK<1> pr;
+                grid_search<1>(p.gc, last, q.x, q.y, q.z, 25.0f, f, pr, lane, scratch[warp]);
+                if (pr.tag[0] != GRID_NOTAG) i2 = (int)(pr.tag[0] & 0xFFFFFFu);
+            }
+            if (lane == 0) {
+                int *o = p.cidx + ((size_t)pair * p.cap_sharp + w) * 2;
+                o[0] = i1; o[1] = i2;
+            }
+        } else {
+            int f_i = w - n_sharp;
+            float4 q = vlo_to_start(T, p.flat_pts[(size_t)cur * p.cap_flat + f_i], p.deskew, p.inv_period);
+            TopK<1> nn;
+            grid_search<1>(p.gsf, last, q.x, q.y, q.z, 25.0f, FilterAll(), nn, lane, scratch[warp]);
+            int i1 = -1, i2 = -1, i3 = -1;
+            if (nn.tag[0] != GRID_NOTAG) {
+                i1 = (int)(nn.tag[0] & 0xFFFFFFu);
+                int ring = (int)(nn.tag[0] >> 24);
+                int fb = p.fwd_quirk ? min(n_flat, n_ls) : n_ls;
+                FilterPartner f2; f2.ind = i1; f2.ring_lo = ring; f2.ring_hi = ring; f2.skip_ring = -1; f2.fwd_bound = fb;
+                FilterPartner f3; f3.ind = i1; f3.ring_lo = ring - 2; f3.ring_hi = ring + 2; f3.skip_ring = ring; f3.fwd_bound = fb;
+                TopK<1> p2, p3;
+                grid_search<1>(p.gsf, last, q.x, q.y, q.z, 25.0f, f2, p2, lane, scratch[warp]);
+                grid_search<1>(p.gsf, last, q.x, q.y, q.z, 25.0f, f3, p3, lane, scratch[warp]);
+                if (p2.tag[0] != GRID_NOTAG) i2 = (int)(p2.tag[0] & 0xFFFFFFu);
+                if (p3.tag[0] != GRID_NOTAG) i3 = (int)(p3.tag[0] & 0xFFFFFFu);
+            }
+            if (lane == 0) {
+                int *o = p.sidx + ((size_t)pair * p.cap_flat + f_i) * 3;
+                o[0] = i1; o[1] = i2; o[2] = i3;
+            }
+        }
+    }
+}
+
+#endif
+
+// Association on the ring-segment box index: one WARP per feature point of the current sweep -- transformToStart, exact
+// nearest neighbour in the previous sweep's cloud (d2 < 25), ring-constrained partner search(es) with upstream's forward /
+// backward tie order.  CTA `chunk` of a pair owns a contiguous share of the pair's queries: its threads transform them once
+// into shared memory (one thread per point), then its warps take them one at a time.  From the second association round
+// on, the previous round's answers (same pair, pose a few Gauss-Newton steps older) seed the searches: they are candidates
+// like any other, and their distances prune nearly every box at once.
+// Measured against round 1's voxel-hash kernels on the whole-bag workload (127 HDL-64 pairs, 5 rounds, profiles/r02*):
+// 4.9 ms vs 11.2 / 22.8 ms (1.0 / 0.7 m cells) -- the hash version fell back to walking cell shells whenever a partner was
+// more than one cell edge away -- with bit-identical results.
+#define K3A_THREADS 128
+#define K3A_MAXQ 128             // queries per CTA share
+__global__ void __launch_bounds__(K3A_THREADS) k3_assoc(OdomParams p, int n_pairs, int round)
 {
     __shared__ float4 s_q[K3A_MAXQ];
     const int pair = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -217,9 +313,13 @@ __global__ void __launch_bounds__(K3A_THREADS) k3_assoc(OdomParams p, int n_pair
             const float4 q = s_q[k];
             const bool sharp = wq < n_sharp;
             const SegCloud &c = sharp ? cc : cs;
+            int *o = sharp ? p.cidx + ((size_t)pair * p.cap_sharp + wq) * 2 : p.sidx + ((size_t)pair * p.cap_flat + (wq - n_sharp)) * 3;
+            int s1 = -1, s2 = -1, s3 = -1;
+            if (round > 0) { s1 = o[0]; s2 = o[1]; if (!sharp) s3 = o[2]; }
+            const int n_tgt = sharp ? n_lc : n_ls;
             SegFilter f; f.mode = 0; f.ind = -1; f.ring_lo = 0; f.ring_hi = 0; f.skip_ring = -1; f.fwd_bound = 0;
             int ring = 0;
-            const int i1 = seg_search(c, -1, -1, -1, q.x, q.y, q.z, 25.0f, f, lane, &ring);
+            const int i1 = seg_search(c, -1, -1, -1, q.x, q.y, q.z, 25.0f, f, (s1 >= 0 && s1 < n_tgt) ? s1 : -1, lane, &ring);
             int i2 = -1, i3 = -1;
             if (i1 >= 0) {
                 f.mode = 1; f.ind = i1;
@@ -227,18 +327,15 @@ __global__ void __launch_bounds__(K3A_THREADS) k3_assoc(OdomParams p, int n_pair
                 const int rlo = max(ring - 2, 0), rhi = min(ring + 2, R - 1);
                 if (sharp) {
                     f.ring_lo = ring - 2; f.ring_hi = ring + 2; f.skip_ring = ring;
-                    i2 = seg_search(c, rlo, rhi, ring, q.x, q.y, q.z, 25.0f, f, lane, nullptr);
+                    i2 = seg_search(c, rlo, rhi, ring, q.x, q.y, q.z, 25.0f, f, (s2 >= 0 && s2 < n_tgt) ? s2 : -1, lane, nullptr);
                 } else {
                     f.ring_lo = ring; f.ring_hi = ring; f.skip_ring = -1;                     // same-ring partner
-                    i2 = seg_search(c, ring, ring, -1, q.x, q.y, q.z, 25.0f, f, lane, nullptr);
+                    i2 = seg_search(c, ring, ring, -1, q.x, q.y, q.z, 25.0f, f, (s2 >= 0 && s2 < n_tgt) ? s2 : -1, lane, nullptr);
                     f.ring_lo = ring - 2; f.ring_hi = ring + 2; f.skip_ring = ring;
-                    i3 = seg_search(c, rlo, rhi, ring, q.x, q.y, q.z, 25.0f, f, lane, nullptr);
+                    i3 = seg_search(c, rlo, rhi, ring, q.x, q.y, q.z, 25.0f, f, (s3 >= 0 && s3 < n_tgt) ? s3 : -1, lane, nullptr);
                 }
             }
-            if (lane == 0) {
-                if (sharp) { int *o = p.cidx + ((size_t)pair * p.cap_sharp + wq) * 2; o[0] = i1; o[1] = i2; }
-                else { int *o = p.sidx + ((size_t)pair * p.cap_flat + (wq - n_sharp)) * 3; o[0] = i1; o[1] = i2; o[2] = i3; }
-            }
+            if (lane == 0) { o[0] = i1; o[1] = i2; if (!sharp) o[2] = i3; }
         }
     }
 }
@@ -443,18 +540,31 @@ static OdomParams make_params(vlo_handle *h)
     p.lflat_ring_start = sb.lflat_ring_start; p.counts = sb.counts; p.n_rings = c.n_rings;
     p.pair_last = h->pair_last; p.pair_cur = h->pair_cur; p.pair_T = h->pair_T; p.pair_state = h->pair_state;
     p.cidx = h->pair_cidx; p.sidx = h->pair_sidx; p.result = h->pair_result;
-    p.ss = h->segs;
+    p.gc = h->gs_corner; p.gsf = h->gs_surf; p.ss = h->segs;
     p.deskew = c.deskew; p.inv_period = 1.0f / c.scan_period; p.fwd_quirk = c.odom_forward_bound_quirk;
     p.max_iter = c.odom_max_iterations; p.degen_thr = c.odom_degen_eig; p.dT_abort = c.odom_delta_t_abort;
     p.dR_abort = c.odom_delta_r_abort; p.rot_thr = c.dopt_rot_threshold; p.trans_thr = c.dopt_trans_threshold;
     return p;
 }
 
-// builds the ring-segment box indices of the target clouds of resident scans [first, first + count)
+// builds the search indices of the target clouds of resident scans [first, first + count)
 int vlo_build_scan_grids(vlo_handle *h, int first, int count)
 {
     if (count <= 0) return VLO_OK;
     ScanBatchDev &sb = h->sb; const vlo_config &c = h->cfg;
+#if K3_ONLINE_GRID
+    h->scan_index_grid = count <= K3_THREAD_PAIRS;       // what the association of these scans will search
+    if (h->scan_index_grid) {
+        GridSource sc = {};
+        sc.pts = sb.lsharp_pts; sc.pts_stride = (size_t)h->cap_lsharp;
+        sc.n_dense = sb.counts; sc.n_dense_stride = 8; sc.n_dense_field = 2; sc.n_rings = c.n_rings;
+        int rc = vlo_grid_build(h, h->gs_corner, sc, first, count, h->cap_lsharp); if (rc) return rc;
+        GridSource ss = {};
+        ss.pts = sb.lflat_pts; ss.pts_stride = (size_t)c.max_points;
+        ss.n_dense = sb.counts; ss.n_dense_stride = 8; ss.n_dense_field = 4; ss.n_rings = c.n_rings;
+        return vlo_grid_build(h, h->gs_surf, ss, first, count, c.max_points);
+    }
+#endif
     SegBuildParams q;
     q.pts[0] = sb.lsharp_pts; q.stride[0] = (size_t)h->cap_lsharp; q.ring_start[0] = sb.lsharp_ring_start;
     q.pts[1] = sb.lflat_pts; q.stride[1] = (size_t)c.max_points; q.ring_start[1] = sb.lflat_ring_start;
@@ -498,13 +608,20 @@ int vlo_launch_register_pairs(vlo_handle *h, int n_pairs, const float *d_seeds, 
     if (only_grid_scan >= 0) { int rc = vlo_build_scan_grids(h, only_grid_scan, 1); if (rc) return rc; h->grids_valid = 1; }
     if (!h->grids_valid) { int rc = vlo_build_scan_grids(h, 0, h->sb.n_scans); if (rc) return rc; h->grids_valid = 1; }
     // association grid: every CTA owns a contiguous share of its pair's queries, one warp per query; a single pair (the
-    // online tick) is spread over the whole machine, a batch gets a few CTAs per pair
+    // online tick) is spread over the whole machine, a batch gets as many CTAs per pair as keep every SM busy
     const int n_q = h->cap_sharp + h->cap_flat;
-    const int fill = std::max(1, (148 * 4 + n_pairs - 1) / n_pairs);
-    dim3 ga(std::max(1, std::min((n_q + 7) / 8, fill)), n_pairs);
+    const int fill = std::max(1, (148 * 16 + n_pairs - 1) / n_pairs);
+    dim3 ga(std::max(1, std::min((n_q + K3A_THREADS / 32 - 1) / (K3A_THREADS / 32), fill)), n_pairs);
+#if K3_ONLINE_GRID
+    dim3 gw(std::max(1, std::min(((h->cap_sharp + h->cap_flat) * 32 + 255) / 256, (148 * 8 + n_pairs - 1) / n_pairs)), n_pairs);
+#endif
     size_t trace_stride = (size_t)n_pairs * (h->cap_sharp * 2 + h->cap_flat * 3);
     for (int base = 0, round = 0; base < c.odom_max_iterations; base += 5, round++) {
-        VLO_PROF(h, ST_ASSOC, (k3_assoc<<<ga, K3A_THREADS, 0, h->stream>>>(p, n_pairs)));
+#if K3_ONLINE_GRID
+        if (h->scan_index_grid) VLO_PROF(h, ST_ASSOC, (k3_assoc_warp<<<gw, 256, 0, h->stream>>>(p, n_pairs)));
+        else
+#endif
+        VLO_PROF(h, ST_ASSOC, (k3_assoc<<<ga, K3A_THREADS, 0, h->stream>>>(p, n_pairs, round)));
         if (h->trace && round < 5) {
             int *dst = h->pair_trace + (size_t)round * trace_stride;
             VLO_CUDA(cudaMemcpyAsync(dst, h->pair_cidx, sizeof(int) * (size_t)n_pairs * h->cap_sharp * 2, cudaMemcpyDeviceToDevice, h->stream));

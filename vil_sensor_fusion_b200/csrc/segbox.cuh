@@ -5,7 +5,8 @@
 // The target clouds of a sweep (less-sharp corners, less-flat surface points) are ring-major arrays: ring r owns the
 // dense indices [ring_start[r], ring_start[r + 1]), consecutive points of a ring are neighbours in space.  The index
 // keeps that order (no sorted copy, the dense index IS the position) and adds two levels of axis-aligned boxes:
-//   fine   segment f = up to 32 consecutive points of ONE ring (an arc); ring r owns segments [seg_ring[r], seg_ring[r + 1])
+//   fine   segment f = up to SEG_PTS consecutive points of ONE ring (a short arc: its box is tight); ring r owns segments
+//                      [seg_ring[r], seg_ring[r + 1])
 //   coarse group c   = 32 fine segments that are close in space: the fine segments are counting-sorted by the cell of
 //                      their box centre on a 16 x 4 x 16 grid over the cloud's bounding box (Morton order), `perm` is
 //                      that order, group c = perm[32 c .. 32 c + 32)
@@ -23,7 +24,11 @@
 #pragma once
 #include "vlo_internal.cuh"
 
-#define SEG_NONE 0xFFFFFFFFu
+#ifndef SEG_PTS
+#define SEG_PTS 8                   // points per fine segment (arc): 8, 16 or 32
+#endif
+#define SEG_GROUPS (32 / SEG_PTS)   // arcs a warp looks at in one pass (lane group g takes the g-th surviving arc)
+#define SEG_SHIFT (SEG_PTS == 32 ? 5 : (SEG_PTS == 16 ? 4 : 3))
 #define SEG_CELLS 1024              // 16 x 4 x 16 cells of the coarse grouping
 
 struct SegCloud {                   // one target cloud of one scan
@@ -47,6 +52,7 @@ __device__ __forceinline__ float seg_box_lb2(const float4 lo, const float4 hi, f
 // mode 1: upstream's partner loops: forward indices first (ascending), then backward (descending)
 struct SegFilter {
     int mode, ind, ring_lo, ring_hi, skip_ring, fwd_bound;
+    __device__ __forceinline__ bool ring_ok(int ring) const { return mode == 0 || (ring >= ring_lo && ring <= ring_hi && ring != skip_ring); }
     __device__ __forceinline__ bool operator()(int ring, int idx, unsigned &tie) const
     {
         if (mode == 0) { tie = (unsigned)idx; return true; }
@@ -55,47 +61,70 @@ struct SegFilter {
         else tie = 0x40000000u + (unsigned)(ind - idx);
         return true;
     }
+    // the same rule on a voxel-hash tag (ring << 24 | dense index; grid.cuh)
+    __device__ __forceinline__ bool operator()(unsigned tag, unsigned &tie) const { return (*this)((int)(tag >> 24), (int)(tag & 0xFFFFFFu), tie); }
 };
 
 struct SegBest { unsigned d, t; int idx; };      // lane-local best: d = float bits of d2 (or of dmax: none yet)
 
-// the lanes of the warp look at the (up to 32) points of fine segment f
-__device__ __forceinline__ void seg_scan(const SegCloud &c, int f, float qx, float qy, float qz, float dmax, const SegFilter &flt,
-                                         SegBest &best, int lane)
+__device__ __forceinline__ void seg_consider(const SegCloud &c, int ring, int idx, float qx, float qy, float qz, float dmax,
+                                             const SegFilter &flt, SegBest &best)
 {
-    const float4 lo = c.fbox[2 * f], hi = c.fbox[2 * f + 1];
-    const int s0 = __float_as_int(lo.w), meta = __float_as_int(hi.w), cnt = meta & 0xff;
-    if (lane < cnt) {
-        const float4 p = c.pts[s0 + lane];
-        unsigned tie;
-        if (flt(meta >> 8, s0 + lane, tie)) {
-            const float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
-            const float d2 = (dx * dx + dy * dy) + dz * dz;
-            const unsigned db = __float_as_uint(d2);
-            if (d2 < dmax && (db < best.d || (db == best.d && tie < best.t))) { best.d = db; best.t = tie; best.idx = s0 + lane; }
+    unsigned tie;
+    if (flt(ring, idx, tie)) {
+        const float4 p = c.pts[idx];
+        const float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
+        const float d2 = (dx * dx + dy * dy) + dz * dz;
+        const unsigned db = __float_as_uint(d2);
+        if (d2 < dmax && (db < best.d || (db == best.d && tie < best.t))) { best.d = db; best.t = tie; best.idx = idx; }
+    }
+}
+
+// the surviving arcs of `fmask` (bit k = fine segment f_of_bit(k)), SEG_GROUPS of them per pass: lane group g looks at
+// the g-th set bit, one point per lane.  `f_mine`: this lane's segment id for ITS bit (lane k holds bit k's id).
+__device__ __forceinline__ void seg_scan_mask(const SegCloud &c, unsigned fmask, int f_mine, float qx, float qy, float qz, float dmax,
+                                              const SegFilter &flt, SegBest &best, int lane)
+{
+    const int g = lane >> SEG_SHIFT, l = lane & (SEG_PTS - 1);
+    while (fmask) {
+        // position of the (g + 1)-th set bit of fmask (-1: fewer bits than that)
+        unsigned m = fmask;
+        #pragma unroll
+        for (int k = 0; k < SEG_GROUPS - 1; k++) if (k < g) m &= m - 1u;
+        const int bit = m ? __ffs(m) - 1 : 0;
+        const int f = __shfl_sync(0xffffffffu, f_mine, bit);
+        if (m) {
+            const float4 lo = c.fbox[2 * f], hi = c.fbox[2 * f + 1];
+            const int s0 = __float_as_int(lo.w), meta = __float_as_int(hi.w);
+            if (l < (meta & 0xff)) seg_consider(c, meta >> 8, s0 + l, qx, qy, qz, dmax, flt, best);
         }
+        #pragma unroll
+        for (int k = 0; k < SEG_GROUPS; k++) fmask &= fmask - 1u;       // drop the SEG_GROUPS lowest set bits
     }
 }
 
 // Exact warp-cooperative search.  ring_lo < 0: every ring (coarse groups first); otherwise only the fine segments of
 // rings ring_lo .. ring_hi (one contiguous range of the ring-major numbering), skip_ring's segments left out.
+// seed >= 0: a point known to be a candidate (the previous association round's answer): the search starts from its
+// distance, so nearly every box is pruned at once.
 // Returns the dense index of the (d2, tie) minimum among admissible points with d2 < dmax, or -1; every lane gets it.
 __device__ __forceinline__ int seg_search(const SegCloud &c, int ring_lo, int ring_hi, int skip_ring, float qx, float qy, float qz,
-                                          float dmax, const SegFilter &flt, int lane, int *ring_out)
+                                          float dmax, const SegFilter &flt, int seed, int lane, int *ring_out)
 {
     const unsigned dmaxb = __float_as_uint(dmax);
     SegBest best; best.d = dmaxb; best.t = 0xFFFFFFFFu; best.idx = -1;
-    unsigned bound = dmaxb;                      // float bits of the best d2 any lane holds (dmax: none yet)
+    if (seed >= 0) seg_consider(c, (int)c.pts[seed].w, seed, qx, qy, qz, dmax, flt, best);      // same value in every lane
+    unsigned bound = best.d;                     // float bits of the best d2 any lane holds (dmax: none yet)
     if (ring_lo < 0) {
-        // ---- phase A: the coarse group nearest to the query, its nearest fine segment -> a first bound
-        float my = __int_as_float(0x7f800000); int myc = -1;
-        for (int cb = lane; cb < c.ncoarse; cb += 32) {
-            const float lb = seg_box_lb2(c.cbox[2 * cb], c.cbox[2 * cb + 1], qx, qy, qz);
-            if (lb < my) { my = lb; myc = cb; }
-        }
-        const unsigned m = __reduce_min_sync(0xffffffffu, myc >= 0 ? __float_as_uint(my) : 0x7f800000u);
-        if (!(m < dmaxb)) { if (ring_out) *ring_out = 0; return -1; }      // nothing closer than dmax (also: empty cloud, NaN query)
-        {
+        if (best.idx < 0) {
+            // ---- phase A: the coarse group nearest to the query, its nearest fine segment -> a first bound
+            float my = __int_as_float(0x7f800000); int myc = -1;
+            for (int cb = lane; cb < c.ncoarse; cb += 32) {
+                const float lb = seg_box_lb2(c.cbox[2 * cb], c.cbox[2 * cb + 1], qx, qy, qz);
+                if (lb < my) { my = lb; myc = cb; }
+            }
+            const unsigned m = __reduce_min_sync(0xffffffffu, myc >= 0 ? __float_as_uint(my) : 0x7f800000u);
+            if (!(m < dmaxb)) { if (ring_out) *ring_out = 0; return -1; }      // nothing closer than dmax (also: empty cloud, NaN query)
             const int src = __ffs(__ballot_sync(0xffffffffu, myc >= 0 && __float_as_uint(my) == m)) - 1;
             const int cstar = __shfl_sync(0xffffffffu, myc, src);
             const int nmem = __float_as_int(c.cbox[2 * cstar].w);
@@ -103,7 +132,7 @@ __device__ __forceinline__ int seg_search(const SegCloud &c, int ring_lo, int ri
             if (lane < nmem) { f = c.perm[32 * cstar + lane]; lbf = seg_box_lb2(c.fbox[2 * f], c.fbox[2 * f + 1], qx, qy, qz); }
             const unsigned mf = __reduce_min_sync(0xffffffffu, __float_as_uint(lbf));
             const int srcf = __ffs(__ballot_sync(0xffffffffu, f >= 0 && __float_as_uint(lbf) == mf)) - 1;
-            seg_scan(c, __shfl_sync(0xffffffffu, f, srcf), qx, qy, qz, dmax, flt, best, lane);
+            seg_scan_mask(c, 1u << srcf, f, qx, qy, qz, dmax, flt, best, lane);
             bound = __reduce_min_sync(0xffffffffu, best.d);
         }
         // ---- phase B: every coarse group / fine segment whose box can hold a point at least as close
@@ -119,31 +148,31 @@ __device__ __forceinline__ int seg_search(const SegCloud &c, int ring_lo, int ri
                 const int cc = cb0 + j;
                 const int nmem = __float_as_int(c.cbox[2 * cc].w);
                 int f = -1; float lbf = __int_as_float(0x7f800000);
-                if (lane < nmem) { f = c.perm[32 * cc + lane]; lbf = seg_box_lb2(c.fbox[2 * f], c.fbox[2 * f + 1], qx, qy, qz); }
-                unsigned fmask = __ballot_sync(0xffffffffu, f >= 0 && __float_as_uint(lbf) <= bound && lbf < dmax);
-                while (fmask) {
-                    const int k = __ffs(fmask) - 1;
-                    fmask &= fmask - 1u;
-                    seg_scan(c, __shfl_sync(0xffffffffu, f, k), qx, qy, qz, dmax, flt, best, lane);
+                if (lane < nmem) {
+                    f = c.perm[32 * cc + lane];
+                    const float4 hi = c.fbox[2 * f + 1];
+                    if (flt.ring_ok(__float_as_int(hi.w) >> 8)) lbf = seg_box_lb2(c.fbox[2 * f], hi, qx, qy, qz);
                 }
+                const unsigned fmask = __ballot_sync(0xffffffffu, f >= 0 && __float_as_uint(lbf) <= bound && lbf < dmax);
+                seg_scan_mask(c, fmask, f, qx, qy, qz, dmax, flt, best, lane);
                 bound = __reduce_min_sync(0xffffffffu, best.d);
             }
         }
     } else {
         const int f0 = c.seg_ring[ring_lo], f1 = c.seg_ring[ring_hi + 1];
-        // ---- phase A: nearest admissible fine segment of the range -> a first bound
-        float my = __int_as_float(0x7f800000); int myf = -1;
-        for (int f = f0 + lane; f < f1; f += 32) {
-            const float4 hi = c.fbox[2 * f + 1];
-            if ((__float_as_int(hi.w) >> 8) == skip_ring) continue;
-            const float lb = seg_box_lb2(c.fbox[2 * f], hi, qx, qy, qz);
-            if (lb < my) { my = lb; myf = f; }
-        }
-        const unsigned m = __reduce_min_sync(0xffffffffu, myf >= 0 ? __float_as_uint(my) : 0x7f800000u);
-        if (!(m < dmaxb)) { if (ring_out) *ring_out = 0; return -1; }
-        {
+        if (best.idx < 0) {
+            // ---- phase A: nearest admissible fine segment of the range -> a first bound
+            float my = __int_as_float(0x7f800000); int myf = -1;
+            for (int f = f0 + lane; f < f1; f += 32) {
+                const float4 hi = c.fbox[2 * f + 1];
+                if ((__float_as_int(hi.w) >> 8) == skip_ring) continue;
+                const float lb = seg_box_lb2(c.fbox[2 * f], hi, qx, qy, qz);
+                if (lb < my) { my = lb; myf = f; }
+            }
+            const unsigned m = __reduce_min_sync(0xffffffffu, myf >= 0 ? __float_as_uint(my) : 0x7f800000u);
+            if (!(m < dmaxb)) { if (ring_out) *ring_out = 0; return -1; }
             const int src = __ffs(__ballot_sync(0xffffffffu, myf >= 0 && __float_as_uint(my) == m)) - 1;
-            seg_scan(c, __shfl_sync(0xffffffffu, myf, src), qx, qy, qz, dmax, flt, best, lane);
+            seg_scan_mask(c, 1u << src, myf, qx, qy, qz, dmax, flt, best, lane);
             bound = __reduce_min_sync(0xffffffffu, best.d);
         }
         // ---- phase B
@@ -154,12 +183,8 @@ __device__ __forceinline__ int seg_search(const SegCloud &c, int ring_lo, int ri
                 const float4 hi = c.fbox[2 * f + 1];
                 if ((__float_as_int(hi.w) >> 8) != skip_ring) lbf = seg_box_lb2(c.fbox[2 * f], hi, qx, qy, qz);
             }
-            unsigned fmask = __ballot_sync(0xffffffffu, __float_as_uint(lbf) <= bound && lbf < dmax);
-            while (fmask) {
-                const int k = __ffs(fmask) - 1;
-                fmask &= fmask - 1u;
-                seg_scan(c, fb0 + k, qx, qy, qz, dmax, flt, best, lane);
-            }
+            const unsigned fmask = __ballot_sync(0xffffffffu, __float_as_uint(lbf) <= bound && lbf < dmax);
+            seg_scan_mask(c, fmask, f, qx, qy, qz, dmax, flt, best, lane);
             bound = __reduce_min_sync(0xffffffffu, best.d);
         }
     }

@@ -97,9 +97,9 @@ extern "C" int vlo_create(const vlo_config *cfg, vlo_handle **out)
     vlo_handle *h = new vlo_handle();
     h->cfg = c; h->launches = 0; h->pinned = nullptr; h->pinned_bytes = 0; h->upload_pinned = nullptr;
     memset(&h->sb, 0, sizeof(h->sb)); memset(&h->lm, 0, sizeof(h->lm));
-    memset(&h->segs, 0, sizeof(SegSet)); memset(h->gs_map, 0, sizeof(h->gs_map));
+    memset(&h->gs_corner, 0, sizeof(GridSet)); memset(&h->gs_surf, 0, sizeof(GridSet)); memset(&h->segs, 0, sizeof(SegSet)); memset(h->gs_map, 0, sizeof(h->gs_map));
     h->map_pts[0] = h->map_pts[1] = nullptr; h->map_n = nullptr; h->map_n_host[0] = h->map_n_host[1] = 0;
-    h->grids_valid = 0; h->trace = 0; h->pair_last_T = nullptr;
+    h->grids_valid = 0; h->scan_index_grid = 0; h->trace = 0; h->pair_last_T = nullptr;
     h->status_word = nullptr; h->pair_T = h->pair_seed = nullptr; h->pair_last = h->pair_cur = h->pair_state = nullptr;
     h->pair_cidx = h->pair_sidx = h->pair_trace = nullptr; h->pair_result = nullptr;
     h->map_partials = nullptr; h->map_idx5 = nullptr; h->map_T = h->map_seed = nullptr; h->map_state = h->map_ncorr = h->map_scans = h->map_done = nullptr;
@@ -142,10 +142,12 @@ extern "C" int vlo_create(const vlo_config *cfg, vlo_handle **out)
     HALLOC(h->pair_trace, (size_t)B * 5 * (h->cap_sharp * 2 + h->cap_flat * 3));
     HALLOC(h->pair_result, (size_t)B);
     HALLOC(h->pair_last_T, (size_t)B * 6);
-    // ring-segment box indices of the scan-to-scan target clouds (segbox.cuh): 32-point arcs, at most one partial arc per ring
+    { int rc = alloc_gridset(h, h->gs_corner, B, h->cap_lsharp, c.odom_corner_cell_size > 0.f ? c.odom_corner_cell_size : 5.0f); if (rc) { vlo_destroy(h); return rc; } }
+    { int rc = alloc_gridset(h, h->gs_surf, B, N, c.odom_cell_size); if (rc) { vlo_destroy(h); return rc; } }
+    // ring-segment box indices of the scan-to-scan target clouds (segbox.cuh): SEG_PTS-point arcs, at most one partial arc per ring
     for (int w = 0; w < 2; w++) {
         SegSet &ss = h->segs;
-        ss.max_seg[w] = (w == 0 ? h->cap_lsharp : N) / 32 + R + 1;
+        ss.max_seg[w] = (w == 0 ? h->cap_lsharp : N) / SEG_PTS + R + 1;
         ss.max_coarse[w] = ss.max_seg[w] / 32 + 1;
         HALLOC(ss.fbox[w], (size_t)B * ss.max_seg[w] * 2); HALLOC(ss.cbox[w], (size_t)B * ss.max_coarse[w] * 2);
         HALLOC(ss.perm[w], (size_t)B * ss.max_seg[w]); HALLOC(ss.seg_ring[w], (size_t)B * (VLO_MAX_RINGS + 1)); HALLOC(ss.nseg[w], (size_t)B);
@@ -185,7 +187,7 @@ extern "C" void vlo_destroy(vlo_handle *h)
     for (void *p : ptrs) if (p) cudaFree(p);
     vlo_lm_free(h);
     for (int w = 0; w < 2; w++) { cudaFree(h->segs.fbox[w]); cudaFree(h->segs.cbox[w]); cudaFree(h->segs.perm[w]); cudaFree(h->segs.seg_ring[w]); cudaFree(h->segs.nseg[w]); }
-    free_gridset(h->gs_map[0]); free_gridset(h->gs_map[1]);
+    free_gridset(h->gs_corner); free_gridset(h->gs_surf); free_gridset(h->gs_map[0]); free_gridset(h->gs_map[1]);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->upload_pinned) { cudaFreeHost(h->upload_pinned); cudaEventDestroy(h->upload_ev[0]); cudaEventDestroy(h->upload_ev[1]); }
     for (auto &e : h->prof_events) cudaEventDestroy(e);

@@ -51,6 +51,9 @@ struct GridSource {
     int mask_lo[3], mask_side;                   // cube coordinates of mask bit (0,0,0); side = 2 nb + 1
 };
 
+#ifndef SEG_PTS
+#define SEG_PTS 8          // points per fine segment of the ring-segment box index (segbox.cuh)
+#endif
 // ring-segment box indices of the scan-to-scan target clouds (segbox.cuh): per resident scan, cloud 0 = less sharp, 1 = less flat
 struct SegSet {
     float4 *fbox[2]; float4 *cbox[2]; int *perm[2]; int *seg_ring[2]; int *nseg[2];
@@ -136,7 +139,9 @@ struct vlo_handle {
     vlo_result *pair_result;   // device results [P]
     float *pair_last_T;        // [P][6] staging of last_transforms
     int grids_valid, trace, last_n_pairs;
+    int scan_index_grid;       // the resident scans' search index: 1 voxel-hash grids (a few scans: the online tick), 0 ring-segment boxes
     // box indices of the scan-to-scan targets (per resident scan) and the voxel-hash grids of the map (0 corner, 1 surf)
+    GridSet gs_corner, gs_surf;
     SegSet segs;
     GridSet gs_map[2];
     float4 *map_pts[2];
