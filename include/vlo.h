@@ -39,6 +39,7 @@ extern "C" {
 #define VLO_ERR_CAPACITY          -3   /* more scans / points / ring points than the handle was created for */
 #define VLO_ERR_NO_DEVICE         -4
 #define VLO_ERR_STATE             -5   /* call order violated (e.g. register before extract) */
+#define VLO_ERR_UNSUPPORTED       -6   /* the configuration asks for something this library does not implement (see vlo_config.undistort_input_cloud) */
 #define VLO_SOFT_TOO_FEW_CORR      1   /* < 10 (odometry) / < 50 (mapping) correspondences: no update */
 #define VLO_SOFT_DEGENERATE_DROP   2   /* D-optimality gate would drop this odometry message */
 
@@ -105,6 +106,12 @@ typedef struct vlo_config {
                                           ring_field_type 0: index in float32 units of a FLOAT32 field; 1 / 2: BYTE offset of a
                                           UINT16 / UINT8 field (PointCloud2 fields[].offset of the usual uint16 `ring`) */
     int   ring_field_type;
+    /* undistortInputCloud (34): the fork's ego-motion compensation of the INPUT cloud inside MultiScanRegistration from an
+     * external prior / motion model / the IMU topic the nodelet subscribes to (loam.launch:38, imuHistorySize :24).  Its
+     * code is not in the reference and it is NOT implemented here: vlo_create refuses a non-zero value with
+     * VLO_ERR_UNSUPPORTED instead of silently doing something else.  (`deskew` above is a different thing: LaserOdometry's own
+     * per-point interpolation of the sweep motion, upstream's transformToStart, which is always on upstream.) */
+    int   undistort_input_cloud;
 } vlo_config;
 
 /* One registration result = one nav_msgs/Odometry + loam/OptStatus pair of the reference. */
@@ -223,6 +230,10 @@ int vlo_scans_stack_counts(vlo_handle *h, int *n_corner, int *n_surf);
  * previous transform) [+ scan-to-map when a map is resident]; `odom` / `mapped` may be NULL. */
 int vlo_process_scan(vlo_handle *h, const float *raw, int n_points, int stride_floats, double stamp,
                      vlo_result *odom, vlo_result *mapped);
+/* the same tick for a sensor_msgs/PointCloud2 payload as it arrives: point_step bytes per point, FLOAT32 x / y / z at the byte
+ * offsets of fields[] (multiples of 4); ring ids per vlo_config.ring_field */
+int vlo_process_scan_pc2(vlo_handle *h, const void *data, int n_points, int point_step, int x_offset, int y_offset, int z_offset,
+                         double stamp, vlo_result *odom, vlo_result *mapped);
 int vlo_online_reset(vlo_handle *h);
 /* accumulated odometry pose (transformSum) and last mapped pose (transformAftMapped), LOAM order/axes */
 int vlo_online_pose(vlo_handle *h, float *sum6, float *mapped6);

@@ -152,3 +152,55 @@ def test_host_helpers_vs_oracle(orc):
     H[3, 3] = -1.0
     ok, lr, lt = api.dopt_gate(H, 11.5, -1.0)
     assert np.isnan(lr) and ok
+
+
+def test_online_tick_from_a_pointcloud2_layout_equals_the_plain_tick():
+    """vlo_process_scan_pc2: the tick fed with a PointCloud2 payload whose x / y / z sit at other byte offsets (intensity first,
+    a ring column last: point_step 20) gives bit for bit what vlo_process_scan gives on the plain x y z i layout."""
+    from vil_sensor_fusion_b200 import api
+    raws = [scenes.vlp16_scan(0.1 * k) for k in range(3)]
+    gcfg = api.default_config("VLP-16", deskew=1, max_scans=2, max_points=65536)      # staging: 4 floats per point slot, the payload has 5
+    with api.Handle(gcfg) as h:
+        plain = [h.process_scan(r, 0.1 * k)[1] for k, r in enumerate(raws)]
+    with api.Handle(gcfg) as h:
+        for k, r in enumerate(raws):
+            blob = np.zeros((r.shape[0], 5), np.float32)
+            blob[:, 0] = 7.0                       # intensity
+            blob[:, 1:4] = r[:, :3][:, [1, 0, 2]]  # y x z
+            msg = {"data": blob.tobytes(), "point_step": 20, "fields": {"x": 8, "y": 4, "z": 12}}
+            rc, o, _ = h.process_pointcloud2(msg, 0.1 * k)
+            np.testing.assert_array_equal(o["transform"].view(np.uint32), plain[k]["transform"].view(np.uint32))
+            np.testing.assert_array_equal(o["hessian"].view(np.uint32), plain[k]["hessian"].view(np.uint32))
+
+
+def test_online_state_advances_through_a_map_full_report():
+    """a one-shot capacity report of the mapping side (map full) must not freeze the odometry state: the tick
+    that reports it still delivers its records and advances, so every later odometry result equals the run with a map that
+    never fills."""
+    from vil_sensor_fusion_b200 import api
+    raws = [scenes.vlp16_scan(0.1 * k) for k in range(6)]
+    big = api.default_config("VLP-16", deskew=1, max_scans=2, max_points=32768, max_map_points=1 << 18, io_ratio=1)
+    tiny = api.default_config("VLP-16", deskew=1, max_scans=2, max_points=32768, max_map_points=2000, io_ratio=1)
+    with api.Handle(big) as h:
+        h.map_reset()
+        ref = [h.process_scan(r, 0.1 * k, want_map=True)[1] for k, r in enumerate(raws)]
+        ref_sum, _ = h.online_pose()
+    reports = 0
+    with api.Handle(tiny) as h:
+        h.map_reset()
+        got = []
+        for k, r in enumerate(raws):
+            # the record pointers are filled even when the call reports the capacity condition
+            odom = api.Result()
+            mapped = api.Result()
+            r32 = np.ascontiguousarray(r, np.float32)
+            import ctypes as C
+            rc = h.lib.vlo_process_scan(h._h, r32.ctypes.data_as(C.c_void_p), r32.shape[0], r32.shape[1], 0.1 * k, C.byref(odom), C.byref(mapped))
+            assert rc >= 0 or rc == -3, (rc, h.lib.vlo_last_error(h._h))
+            reports += int(rc == -3)
+            got.append(np.frombuffer(bytes(odom), api.RESULT_DTYPE)[0])
+        got_sum, _ = h.online_pose()
+    assert reports >= 1, "the 2000-voxel map should have filled up"
+    for k in range(1, len(raws)):
+        np.testing.assert_array_equal(got[k]["transform"].view(np.uint32), ref[k]["transform"].view(np.uint32), err_msg="tick %d" % k)
+    np.testing.assert_array_equal(got_sum, ref_sum)

@@ -29,6 +29,7 @@ class Config(C.Structure):
         ("map_dims", C.c_int * 3), ("map_start_cubes", C.c_int * 3), ("n_neighbor_cubes", C.c_int), ("io_ratio", C.c_int),
         ("hessian_order", C.c_int),
         ("rotate_input", C.c_int), ("input_rotation", C.c_float * 3), ("ring_field", C.c_int), ("ring_field_type", C.c_int),
+        ("undistort_input_cloud", C.c_int),
     ]
 
 
@@ -100,6 +101,7 @@ SYMBOLS = {
     "vlo_online_pose": (C.c_int, [_VP, _VP, _VP]),
     "vlo_online_set_map_pose": (C.c_int, [_VP, _VP]),
     "vlo_process_scan": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_double, C.POINTER(Result), C.POINTER(Result)]),
+    "vlo_process_scan_pc2": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.POINTER(Result), C.POINTER(Result)]),
     "vlo_bag_register_map": (C.c_int, [_VP, C.POINTER(BagBatch), C.c_int, C.c_int, _VP]),
     "vlo_bag_register_pairs": (C.c_int, [_VP, C.POINTER(BagBatch), C.c_int, C.c_int, _VP]),
     "vlo_imu_preintegrate_batch": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, _VP, _VP, _VP, C.c_int, _VP]),

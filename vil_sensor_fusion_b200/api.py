@@ -292,6 +292,19 @@ class Handle:
         m = np.frombuffer(bytes(mapped), RESULT_DTYPE)[0] if want_map else None
         return rc, o, m
 
+    def process_pointcloud2(self, msg, stamp: float = 0.0, want_map: bool = False):
+        """One online tick for a PointCloud2-shaped dict {data, point_step, fields: {name: byte offset}} (see upload_pointcloud2)."""
+        data = np.frombuffer(msg["data"], np.uint8) if not isinstance(msg["data"], np.ndarray) else msg["data"].view(np.uint8).ravel()
+        data = np.ascontiguousarray(data)
+        step, f = int(msg["point_step"]), msg["fields"]
+        odom = Result()
+        mapped = Result() if want_map else None
+        rc = self._check(self.lib.vlo_process_scan_pc2(self._h, _ptr(data), data.size // step, step, int(f["x"]), int(f["y"]), int(f["z"]), stamp,
+                                                       C.byref(odom), C.byref(mapped) if want_map else None))
+        o = np.frombuffer(bytes(odom), RESULT_DTYPE)[0]
+        m = np.frombuffer(bytes(mapped), RESULT_DTYPE)[0] if want_map else None
+        return rc, o, m
+
     # ---- whole-bag streaming (copy of batch k+1 overlaps the kernels of batch k)
     def _bag(self, fn, batches, stride, pairs: bool) -> np.ndarray:
         """batches: list of (raw, offsets, seeds); raw = host float32 array or an int address of pinned memory."""

@@ -30,6 +30,7 @@ extern "C" void vlo_default_config(vlo_config *c)
     c->map_dims[0] = 101; c->map_dims[1] = 51; c->map_dims[2] = 101;
     c->map_start_cubes[0] = 50; c->map_start_cubes[1] = 25; c->map_start_cubes[2] = 50;
     c->n_neighbor_cubes = 5; c->io_ratio = 2; c->hessian_order = 0;
+    c->undistort_input_cloud = 0;
     c->rotate_input = 0; c->input_rotation[0] = c->input_rotation[1] = c->input_rotation[2] = 0.0f; c->ring_field = -1; c->ring_field_type = 0;
 }
 
@@ -91,6 +92,7 @@ extern "C" int vlo_create(const vlo_config *cfg, vlo_handle **out)
         c.max_corner_less_sharp > 255 || c.max_surface_flat < 0 || c.max_surface_flat > 255 || !(c.upper_deg > c.lower_deg) ||
         !(c.less_flat_filter_size > 0.f) || !(c.scan_period > 0.f))
         return VLO_ERR_INVALID_ARG;
+    if (c.undistort_input_cloud) return VLO_ERR_UNSUPPORTED;      // see vlo.h: not implemented, never silently mapped onto something else
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || c.device >= ndev) return VLO_ERR_NO_DEVICE;
     if (cudaSetDevice(c.device) != cudaSuccess) return VLO_ERR_NO_DEVICE;

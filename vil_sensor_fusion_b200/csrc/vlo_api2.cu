@@ -254,9 +254,31 @@ extern "C" int vlo_online_set_map_pose(vlo_handle *h, const float *pose6)
     return VLO_OK;
 }
 
+static int process_scan_impl(vlo_handle *h, const float *raw, int n_points, int stride, const int *xyz_off, vlo_result *odom, vlo_result *mapped);
+
 extern "C" int vlo_process_scan(vlo_handle *h, const float *raw, int n_points, int stride, double stamp, vlo_result *odom, vlo_result *mapped)
 {
     (void)stamp;
+    const int off[3] = { 0, 1, 2 };
+    return process_scan_impl(h, raw, n_points, stride, off, odom, mapped);
+}
+
+extern "C" int vlo_process_scan_pc2(vlo_handle *h, const void *data, int n_points, int point_step, int x_offset, int y_offset, int z_offset,
+                                    double stamp, vlo_result *odom, vlo_result *mapped)
+{
+    (void)stamp;
+    if (!h || point_step < 12 || (point_step & 3) || (x_offset & 3) || (y_offset & 3) || (z_offset & 3) || x_offset < 0 || y_offset < 0 ||
+        z_offset < 0 || x_offset + 4 > point_step || y_offset + 4 > point_step || z_offset + 4 > point_step ||
+        x_offset == y_offset || x_offset == z_offset || y_offset == z_offset) {
+        if (h) h->err = "PointCloud2 layout: point_step and the x/y/z offsets must be multiples of 4 inside the point (FLOAT32 fields)";
+        return VLO_ERR_INVALID_ARG;
+    }
+    const int off[3] = { x_offset / 4, y_offset / 4, z_offset / 4 };
+    return process_scan_impl(h, (const float *)data, n_points, point_step / 4, off, odom, mapped);
+}
+
+static int process_scan_impl(vlo_handle *h, const float *raw, int n_points, int stride, const int *xyz_off, vlo_result *odom, vlo_result *mapped)
+{
     if (!h || !raw || n_points < 0 || stride < 3) return VLO_ERR_INVALID_ARG;
     if (h->cfg.max_scans < 2) { h->err = "online mode needs max_scans >= 2"; return VLO_ERR_STATE; }
     if (n_points > h->cfg.max_points || (size_t)n_points * stride > (size_t)h->cfg.max_points * 4) { h->err = "scan exceeds max_points"; return VLO_ERR_CAPACITY; }
@@ -272,7 +294,7 @@ extern "C" int vlo_process_scan(vlo_handle *h, const float *raw, int n_points, i
     VLO_CUDA(cudaMemcpyAsync(dst, raw, sizeof(float) * (size_t)n_points * stride, cudaMemcpyHostToDevice, h->stream));
     VLO_CUDA(cudaMemcpyAsync(sb.raw_offset + 2 * cur, poff, sizeof(int) * 2, cudaMemcpyHostToDevice, h->stream));
     sb.raw = sb.raw_owned; sb.stride = stride; sb.n_scans = 2; sb.scan_first = cur; sb.scan_count = 1;
-    sb.xyz_off[0] = 0; sb.xyz_off[1] = 1; sb.xyz_off[2] = 2;
+    sb.xyz_off[0] = xyz_off[0]; sb.xyz_off[1] = xyz_off[1]; sb.xyz_off[2] = xyz_off[2];
     rc = vlo_launch_organise(h); if (rc) return rc;
     rc = vlo_launch_extract(h); if (rc) return rc;
     h->map_qmax = 0;
