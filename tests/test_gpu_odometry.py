@@ -93,29 +93,44 @@ def test_hdl64_pairs_batch(orc):
             _compare(ro, res[p], "hdl64 pair %d" % p)
 
 
-def test_degenerate_corridor_and_plane(orc):
-    """C3: corridor -> one eigenvalue below odomDegenEigVal along the axis, projection removes it;
-    single plane -> three; D-opt gate drops both."""
+@pytest.mark.parametrize("lidar,max_points", [("VLP-16", 32768), ("HDL-64E", 131072)])
+def test_degenerate_corridor_and_plane(orc, lidar, max_points):
+    """C3, VLP-16 and HDL-64.  Corridor along x with no end caps: the registration runs (status 0), is flagged
+    degenerate with two eigenvalues of AtA under odomDegenEigVal (translation along the axis and its coupled rotation), the
+    update is remapped (pose, eigenvalues, projection compared with the oracle: pose and P bit for bit, eigenvalues 1e-4),
+    the along-axis motion is NOT recovered, and the D-opt gate drops the message (logdet_trans < 28.9).  Single ground plane:
+    no corner features at all, so upstream's precondition (more than 10 corner / 100 surface points in the last sweep) refuses
+    to optimise -- the soft status, identically on both sides; three dropped dimensions cannot arise through a registration."""
     from vil_sensor_fusion_b200 import api, synth
-    ocfg = orc.default_config("VLP-16", deskew=0)
-    gcfg = api.default_config("VLP-16", deskew=0, max_scans=2, max_points=32768)
-    for scene, n_deg in ((synth.scene_corridor(), 1), (synth.scene_plane(), 3)):
-        raw0 = synth.make_scan(scene, "VLP-16", pose=(np.eye(3), np.zeros(3)), rolling=False)
-        raw1 = synth.make_scan(scene, "VLP-16", pose=(np.eye(3), np.array([0.1, 0.02, 0.0])), rolling=False)
+    ocfg = orc.default_config(lidar, deskew=0)
+    gcfg = api.default_config(lidar, deskew=0, max_scans=2, max_points=max_points)
+    motion = np.array([0.1, 0.02, 0.0])                      # ROS frame: 10 cm along the corridor, 2 cm across
+    out = {}
+    for scene in (synth.scene_corridor(), synth.scene_plane()):
+        raw0 = synth.make_scan(scene, lidar, pose=(np.eye(3), np.zeros(3)), rolling=False)
+        raw1 = synth.make_scan(scene, lidar, pose=(np.eye(3), motion), rolling=False)
         ro, _, _ = _oracle_pair(orc, ocfg, raw0, raw1, None, None)
         with api.Handle(gcfg) as h:
             h.upload([raw0, raw1])
             h.organise()
             h.extract()
             rg = h.register_pairs([0], [1])[0]
-        if ro["status"] == 0:
-            _compare(ro, rg, scene.name)
-            assert ro["is_degenerate"]
-            assert int(np.sum(ro["eig"] < ocfg.odom_degen_eig)) >= n_deg
-            # the remapped update has no component along the dropped eigen-directions
-            assert not ro["pass_dopt"] or scene.name == "corridor"
-        else:
-            assert rg["status"] == 1
+        out[scene.name] = (ro, rg)
+    ro, rg = out["corridor"]
+    assert ro["status"] == 0 and rg["status"] == 0
+    _compare(ro, rg, "corridor")
+    assert rg["is_degenerate"] == 1
+    assert int(np.sum(rg["eig"] < ocfg.odom_degen_eig)) == 2 and int(np.sum(ro["eig"] < ocfg.odom_degen_eig)) == 2
+    assert rg["pass_dopt"] == 0 and rg["logdet_trans"] < 28.9          # degerate_odometry_filter.cpp:39-42 drops it
+    # LOAM axes: x = ROS y (across), z = ROS x (along).  Across-corridor motion is observed, along-axis motion is projected out
+    assert abs(rg["transform"][5]) < 1e-3 and 0.005 < abs(rg["transform"][3]) < 0.025, rg["transform"]
+    # the projection really removes the dropped eigen-directions: P is idempotent and of rank 4
+    P = rg["P"].reshape(6, 6).astype(np.float64)
+    np.testing.assert_allclose(P @ P, P, atol=1e-5)
+    assert abs(np.trace(P) - 4.0) < 1e-4
+    ro, rg = out["plane"]
+    assert ro["status"] == 1 and rg["status"] == 1 and rg["iterations"] == 0 and ro["iterations"] == 0
+    assert np.all(rg["transform"] == 0) and rg["is_degenerate"] == 0
 
 
 def test_too_few_features_soft_status(orc):
