@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(SEGB_THREADS) k3_seg_build(SegBuildParams p)
     float4 *fbox = p.ss.fbox[w] + (size_t)b * p.ss.max_seg[w] * 2;
     float4 *cbox = p.ss.cbox[w] + (size_t)b * p.ss.max_coarse[w] * 2;
     int *perm = p.ss.perm[w] + (size_t)b * p.ss.max_seg[w];
+    float4 *mbox = p.ss.mbox[w] + (size_t)b * p.ss.max_seg[w] * 2;
     int *seg_ring = p.ss.seg_ring[w] + b * (VLO_MAX_RINGS + 1);
     const float INF = __int_as_float(0x7f800000);
     // 1. segments per ring (ceil(n_r / SEG_PTS)), exclusive prefix
@@ -188,6 +189,7 @@ __global__ void __launch_bounds__(SEGB_THREADS) k3_seg_build(SegBuildParams p)
         if (lane < nmem) {
             const int f = perm[32 * c + lane];
             const float4 lo = fbox[2 * f], hi = fbox[2 * f + 1];
+            mbox[2 * (32 * c + lane)] = lo; mbox[2 * (32 * c + lane) + 1] = hi;       // the group's members, side by side
             x0 = lo.x; y0 = lo.y; z0 = lo.z; x1 = hi.x; y1 = hi.y; z1 = hi.z;
         }
         x0 = seg_warp_min(x0); y0 = seg_warp_min(y0); z0 = seg_warp_min(z0);
@@ -202,7 +204,7 @@ __device__ __forceinline__ SegCloud seg_cloud_of(const OdomParams &p, int w, int
     c.pts = (w == 0 ? p.lsharp_pts + (size_t)scan * p.cap_lsharp : p.lflat_pts + (size_t)scan * p.N);
     c.fbox = p.ss.fbox[w] + (size_t)scan * p.ss.max_seg[w] * 2;
     c.cbox = p.ss.cbox[w] + (size_t)scan * p.ss.max_coarse[w] * 2;
-    c.perm = p.ss.perm[w] + (size_t)scan * p.ss.max_seg[w];
+    c.mbox = p.ss.mbox[w] + (size_t)scan * p.ss.max_seg[w] * 2;
     c.seg_ring = p.ss.seg_ring[w] + scan * (VLO_MAX_RINGS + 1);
     c.nseg = p.ss.nseg[w][scan]; c.ncoarse = (c.nseg + 31) >> 5;
     return c;
@@ -284,7 +286,10 @@ __global__ void __launch_bounds__(256) k3_assoc_warp(OdomParams p, int n_pairs)
 // more than one cell edge away -- with bit-identical results.
 #define K3A_THREADS 128
 #define K3A_MAXQ 128             // queries per CTA share
-__global__ void __launch_bounds__(K3A_THREADS) k3_assoc(OdomParams p, int n_pairs, int round)
+#ifndef K3A_MINB
+#define K3A_MINB 1
+#endif
+__global__ void __launch_bounds__(K3A_THREADS, K3A_MINB) k3_assoc(OdomParams p, int n_pairs, int round)
 {
     __shared__ float4 s_q[K3A_MAXQ];
     const int pair = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -329,10 +334,10 @@ __global__ void __launch_bounds__(K3A_THREADS) k3_assoc(OdomParams p, int n_pair
                     f.ring_lo = ring - 2; f.ring_hi = ring + 2; f.skip_ring = ring;
                     i2 = seg_search(c, rlo, rhi, ring, q.x, q.y, q.z, 25.0f, f, (s2 >= 0 && s2 < n_tgt) ? s2 : -1, lane, nullptr);
                 } else {
-                    f.ring_lo = ring; f.ring_hi = ring; f.skip_ring = -1;                     // same-ring partner
-                    i2 = seg_search(c, ring, ring, -1, q.x, q.y, q.z, 25.0f, f, (s2 >= 0 && s2 < n_tgt) ? s2 : -1, lane, nullptr);
-                    f.ring_lo = ring - 2; f.ring_hi = ring + 2; f.skip_ring = ring;
-                    i3 = seg_search(c, rlo, rhi, ring, q.x, q.y, q.z, 25.0f, f, (s3 >= 0 && s3 < n_tgt) ? s3 : -1, lane, nullptr);
+                    SegFilter f2 = f; f2.ring_lo = ring; f2.ring_hi = ring; f2.skip_ring = -1;             // same-ring partner
+                    f.ring_lo = ring - 2; f.ring_hi = ring + 2; f.skip_ring = ring;                         // other-ring partner
+                    seg_search_partners(c, ring, R, q.x, q.y, q.z, 25.0f, f2, f, (s2 >= 0 && s2 < n_tgt) ? s2 : -1,
+                                        (s3 >= 0 && s3 < n_tgt) ? s3 : -1, lane, i2, i3);
                 }
             }
             if (lane == 0) { o[0] = i1; o[1] = i2; if (!sharp) o[2] = i3; }
@@ -340,17 +345,20 @@ __global__ void __launch_bounds__(K3A_THREADS) k3_assoc(OdomParams p, int n_pair
     }
 }
 
-#define GN_THREADS 256
+#ifndef GN_THREADS
+#define GN_THREADS 512     // one CTA per pair: the pair's 2304 correspondences in 5 chunks (8 warps / 9 chunks before: 26 us per iteration on one SM)
+#endif
+#define GN_GROUPS (GN_THREADS / 32)
 #define TSTRIDE 29     // padded row of the transposed term buffer
 
-// R1 block reduction of one chunk of 256 queries held in smem terms[256][TSTRIDE]:
+// R1 block reduction of one chunk of GN_THREADS queries held in smem terms[GN_THREADS][TSTRIDE] (the comments count for 256):
 // 224 threads sum 32 consecutive queries each (level 1), then 28 threads fold the 8 level-1 sums into
 // the running level-2 accumulator; level 2 closes into level 3 every 1024 queries.
 __device__ __forceinline__ void r1_chunk(float *terms, float *l1buf, float *l2acc, float *l3acc, int chunk, int n_chunks, int q_total, int tid)
 {
     __syncthreads();
-    if (tid < 8 * VLO_NTERM) {
-        int g = tid / VLO_NTERM, e = tid % VLO_NTERM;
+    for (int task = tid; task < GN_GROUPS * VLO_NTERM; task += GN_THREADS) {
+        int g = task / VLO_NTERM, e = task % VLO_NTERM;
         float l1 = 0.0f;
         const float *src = terms + (size_t)(g * 32) * TSTRIDE + e;
         #pragma unroll 8
@@ -360,16 +368,23 @@ __device__ __forceinline__ void r1_chunk(float *terms, float *l1buf, float *l2ac
     __syncthreads();
     if (tid < VLO_NTERM) {
         float l2 = l2acc[tid];
-        for (int g = 0; g < 8; g++) if (chunk * 256 + g * 32 < q_total) l2 = l2 + l1buf[g * VLO_NTERM + tid];
-        if ((chunk & 3) == 3 || chunk == n_chunks - 1) { l3acc[tid] = l3acc[tid] + l2; l2 = 0.0f; }
+        for (int g = 0; g < GN_GROUPS; g++) {
+            const int q0 = chunk * GN_THREADS + g * 32;          // level 1 block = 32 queries, level 2 closes every 1024 queries
+            if (q0 < q_total) l2 = l2 + l1buf[g * VLO_NTERM + tid];
+            if (q0 < q_total && ((q0 & 1023) == 992 || q0 + 32 >= q_total)) { l3acc[tid] = l3acc[tid] + l2; l2 = 0.0f; }
+        }
         l2acc[tid] = l2;
     }
 }
 
 __global__ void __launch_bounds__(GN_THREADS) k3_gn(OdomParams p, int iter_base, int n_iters)
 {
-    __shared__ float terms[GN_THREADS * TSTRIDE];
-    __shared__ float l1buf[8 * VLO_NTERM];
+#ifdef VLO_HOST_EMULATION
+    static float terms[GN_THREADS * TSTRIDE];
+#else
+    extern __shared__ float terms[];             // [GN_THREADS][TSTRIDE]: 58 KB at 512 threads (dynamic, opted in per handle)
+#endif
+    __shared__ float l1buf[GN_GROUPS * VLO_NTERM];
     __shared__ float l2acc[VLO_NTERM], l3acc[VLO_NTERM];
     __shared__ float trig[6];
     __shared__ GnScratch S;
@@ -394,7 +409,7 @@ __global__ void __launch_bounds__(GN_THREADS) k3_gn(OdomParams p, int iter_base,
     if (tid < VLO_NTERM) S.total[tid] = 0.0f;
     __syncthreads();
     const int q_total = n_sharp + n_flat;
-    const int n_chunks = (q_total + 255) / 256;
+    const int n_chunks = (q_total + GN_THREADS - 1) / GN_THREADS;
     bool have_total = false, did_eig = false;
     for (int it = iter_base; it < iter_base + n_iters && it < p.max_iter; it++) {
         if (tid == 0) {
@@ -410,7 +425,7 @@ __global__ void __launch_bounds__(GN_THREADS) k3_gn(OdomParams p, int iter_base,
         for (int a = 0; a < 6; a++) T[a] = S.T[a];
         int my_edge = 0, my_plane = 0;
         for (int chunk = 0; chunk < n_chunks; chunk++) {
-            int i = chunk * 256 + tid;
+            int i = chunk * GN_THREADS + tid;
             float t[VLO_NTERM];
             #pragma unroll
             for (int e = 0; e < VLO_NTERM; e++) t[e] = 0.0f;
@@ -596,6 +611,11 @@ int vlo_launch_register_pairs(vlo_handle *h, int n_pairs, const float *d_seeds, 
     const vlo_config &c = h->cfg;
     k3_init_pairs<<<(n_pairs + 127) / 128, 128, 0, h->stream>>>(p, d_seeds, n_pairs);
     h->launches += 1;
+    const size_t gn_smem = sizeof(float) * GN_THREADS * TSTRIDE;
+    if (!h->k3_gn_configured) {                    // per handle = per device
+        VLO_CUDA(cudaFuncSetAttribute(k3_gn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gn_smem));
+        h->k3_gn_configured = 1;
+    }
     if (d_last_T) {
         dim3 g0((h->cap_lsharp + 255) / 256, n_pairs), g1((c.max_points + 255) / 256, n_pairs);
         vlo_prof_begin(h, ST_TO_END);
@@ -627,7 +647,7 @@ int vlo_launch_register_pairs(vlo_handle *h, int n_pairs, const float *d_seeds, 
             VLO_CUDA(cudaMemcpyAsync(dst, h->pair_cidx, sizeof(int) * (size_t)n_pairs * h->cap_sharp * 2, cudaMemcpyDeviceToDevice, h->stream));
             VLO_CUDA(cudaMemcpyAsync(dst + (size_t)n_pairs * h->cap_sharp * 2, h->pair_sidx, sizeof(int) * (size_t)n_pairs * h->cap_flat * 3, cudaMemcpyDeviceToDevice, h->stream));
         }
-        VLO_PROF(h, ST_GN, (k3_gn<<<n_pairs, GN_THREADS, 0, h->stream>>>(p, base, 5)));
+        VLO_PROF(h, ST_GN, (k3_gn<<<n_pairs, GN_THREADS, gn_smem, h->stream>>>(p, base, 5)));
         h->launches += 2;
     }
     VLO_CUDA(cudaGetLastError());

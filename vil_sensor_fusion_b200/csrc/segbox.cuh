@@ -8,8 +8,8 @@
 //   fine   segment f = up to SEG_PTS consecutive points of ONE ring (a short arc: its box is tight); ring r owns segments
 //                      [seg_ring[r], seg_ring[r + 1])
 //   coarse group c   = 32 fine segments that are close in space: the fine segments are counting-sorted by the cell of
-//                      their box centre on a 16 x 4 x 16 grid over the cloud's bounding box (Morton order), `perm` is
-//                      that order, group c = perm[32 c .. 32 c + 32)
+//                      their box centre on a 16 x 4 x 16 grid over the cloud's bounding box (Morton order); `mbox`
+//                      holds the fine boxes in that order, group c = mbox[32 c .. 32 c + 32)
 // A query is answered by ONE WARP: every level is one box test per lane, a ballot, and a 32-wide coalesced scan of
 // the surviving segments -- no divergence, no hash probes, no data-dependent shell expansion (round-1 ncu of the
 // voxel-hash version: 8.9 of 32 lanes active, 13 % of the samples on the probe load, far partners falling back to a
@@ -35,7 +35,7 @@ struct SegCloud {                   // one target cloud of one scan
     const float4 *pts;              // dense ring-major points, ring = int(w)
     const float4 *fbox;             // [nseg][2]: lo.xyz | first dense index (int bits), hi.xyz | (ring << 8 | count) (int bits)
     const float4 *cbox;             // [ncoarse][2]: lo.xyz | member count, hi.xyz
-    const int *perm;                // [nseg] fine segments in coarse-group order
+    const float4 *mbox;             // [nseg][2]: the fine boxes again, in coarse-group order (group c = entries 32 c .. 32 c + 31): one trip, no indirection
     const int *seg_ring;            // [R + 1]
     int nseg, ncoarse;
 };
@@ -80,24 +80,21 @@ __device__ __forceinline__ void seg_consider(const SegCloud &c, int ring, int id
     }
 }
 
-// the surviving arcs of `fmask` (bit k = fine segment f_of_bit(k)), SEG_GROUPS of them per pass: lane group g looks at
-// the g-th set bit, one point per lane.  `f_mine`: this lane's segment id for ITS bit (lane k holds bit k's id).
-__device__ __forceinline__ void seg_scan_mask(const SegCloud &c, unsigned fmask, int f_mine, float qx, float qy, float qz, float dmax,
-                                              const SegFilter &flt, SegBest &best, int lane)
+// the surviving arcs of `fmask` (bit k = the arc whose box lane k has just tested), SEG_GROUPS of them per pass: lane
+// group g looks at the g-th set bit, one point per lane.  `s0_mine` / `meta_mine`: first dense index and (ring << 8 | count)
+// of this lane's arc, broadcast from the registers of the lane that tested it (no second trip to the box arrays).
+__device__ __forceinline__ void seg_scan_mask(const SegCloud &c, unsigned fmask, int s0_mine, int meta_mine, float qx, float qy, float qz,
+                                              float dmax, const SegFilter &flt, SegBest &best, int lane)
 {
     const int g = lane >> SEG_SHIFT, l = lane & (SEG_PTS - 1);
     while (fmask) {
-        // position of the (g + 1)-th set bit of fmask (-1: fewer bits than that)
+        // position of the (g + 1)-th set bit of fmask (none: fewer bits than that)
         unsigned m = fmask;
         #pragma unroll
         for (int k = 0; k < SEG_GROUPS - 1; k++) if (k < g) m &= m - 1u;
         const int bit = m ? __ffs(m) - 1 : 0;
-        const int f = __shfl_sync(0xffffffffu, f_mine, bit);
-        if (m) {
-            const float4 lo = c.fbox[2 * f], hi = c.fbox[2 * f + 1];
-            const int s0 = __float_as_int(lo.w), meta = __float_as_int(hi.w);
-            if (l < (meta & 0xff)) seg_consider(c, meta >> 8, s0 + l, qx, qy, qz, dmax, flt, best);
-        }
+        const int s0 = __shfl_sync(0xffffffffu, s0_mine, bit), meta = __shfl_sync(0xffffffffu, meta_mine, bit);
+        if (m && l < (meta & 0xff)) seg_consider(c, meta >> 8, s0 + l, qx, qy, qz, dmax, flt, best);
         #pragma unroll
         for (int k = 0; k < SEG_GROUPS; k++) fmask &= fmask - 1u;       // drop the SEG_GROUPS lowest set bits
     }
@@ -128,11 +125,15 @@ __device__ __forceinline__ int seg_search(const SegCloud &c, int ring_lo, int ri
             const int src = __ffs(__ballot_sync(0xffffffffu, myc >= 0 && __float_as_uint(my) == m)) - 1;
             const int cstar = __shfl_sync(0xffffffffu, myc, src);
             const int nmem = __float_as_int(c.cbox[2 * cstar].w);
-            int f = -1; float lbf = __int_as_float(0x7f800000);
-            if (lane < nmem) { f = c.perm[32 * cstar + lane]; lbf = seg_box_lb2(c.fbox[2 * f], c.fbox[2 * f + 1], qx, qy, qz); }
+            int s0 = 0, meta = 0; float lbf = __int_as_float(0x7f800000);
+            if (lane < nmem) {
+                const float4 lo = c.mbox[2 * (32 * cstar + lane)], hi = c.mbox[2 * (32 * cstar + lane) + 1];
+                s0 = __float_as_int(lo.w); meta = __float_as_int(hi.w);
+                lbf = seg_box_lb2(lo, hi, qx, qy, qz);
+            }
             const unsigned mf = __reduce_min_sync(0xffffffffu, __float_as_uint(lbf));
-            const int srcf = __ffs(__ballot_sync(0xffffffffu, f >= 0 && __float_as_uint(lbf) == mf)) - 1;
-            seg_scan_mask(c, 1u << srcf, f, qx, qy, qz, dmax, flt, best, lane);
+            const int srcf = __ffs(__ballot_sync(0xffffffffu, lane < nmem && __float_as_uint(lbf) == mf)) - 1;
+            seg_scan_mask(c, 1u << srcf, s0, meta, qx, qy, qz, dmax, flt, best, lane);
             bound = __reduce_min_sync(0xffffffffu, best.d);
         }
         // ---- phase B: every coarse group / fine segment whose box can hold a point at least as close
@@ -147,14 +148,14 @@ __device__ __forceinline__ int seg_search(const SegCloud &c, int ring_lo, int ri
                 if (__float_as_uint(__shfl_sync(0xffffffffu, lbc, j)) > bound) continue;      // the bound has tightened since the ballot
                 const int cc = cb0 + j;
                 const int nmem = __float_as_int(c.cbox[2 * cc].w);
-                int f = -1; float lbf = __int_as_float(0x7f800000);
+                int s0 = 0, meta = 0; float lbf = __int_as_float(0x7f800000);
                 if (lane < nmem) {
-                    f = c.perm[32 * cc + lane];
-                    const float4 hi = c.fbox[2 * f + 1];
-                    if (flt.ring_ok(__float_as_int(hi.w) >> 8)) lbf = seg_box_lb2(c.fbox[2 * f], hi, qx, qy, qz);
+                    const float4 lo = c.mbox[2 * (32 * cc + lane)], hi = c.mbox[2 * (32 * cc + lane) + 1];
+                    s0 = __float_as_int(lo.w); meta = __float_as_int(hi.w);
+                    if (flt.ring_ok(meta >> 8)) lbf = seg_box_lb2(lo, hi, qx, qy, qz);
                 }
-                const unsigned fmask = __ballot_sync(0xffffffffu, f >= 0 && __float_as_uint(lbf) <= bound && lbf < dmax);
-                seg_scan_mask(c, fmask, f, qx, qy, qz, dmax, flt, best, lane);
+                const unsigned fmask = __ballot_sync(0xffffffffu, __float_as_uint(lbf) <= bound && lbf < dmax);
+                seg_scan_mask(c, fmask, s0, meta, qx, qy, qz, dmax, flt, best, lane);
                 bound = __reduce_min_sync(0xffffffffu, best.d);
             }
         }
@@ -162,29 +163,30 @@ __device__ __forceinline__ int seg_search(const SegCloud &c, int ring_lo, int ri
         const int f0 = c.seg_ring[ring_lo], f1 = c.seg_ring[ring_hi + 1];
         if (best.idx < 0) {
             // ---- phase A: nearest admissible fine segment of the range -> a first bound
-            float my = __int_as_float(0x7f800000); int myf = -1;
+            float my = __int_as_float(0x7f800000); int mys0 = 0, mymeta = -1;
             for (int f = f0 + lane; f < f1; f += 32) {
-                const float4 hi = c.fbox[2 * f + 1];
+                const float4 lo = c.fbox[2 * f], hi = c.fbox[2 * f + 1];
                 if ((__float_as_int(hi.w) >> 8) == skip_ring) continue;
-                const float lb = seg_box_lb2(c.fbox[2 * f], hi, qx, qy, qz);
-                if (lb < my) { my = lb; myf = f; }
+                const float lb = seg_box_lb2(lo, hi, qx, qy, qz);
+                if (lb < my) { my = lb; mys0 = __float_as_int(lo.w); mymeta = __float_as_int(hi.w); }
             }
-            const unsigned m = __reduce_min_sync(0xffffffffu, myf >= 0 ? __float_as_uint(my) : 0x7f800000u);
+            const unsigned m = __reduce_min_sync(0xffffffffu, mymeta >= 0 ? __float_as_uint(my) : 0x7f800000u);
             if (!(m < dmaxb)) { if (ring_out) *ring_out = 0; return -1; }
-            const int src = __ffs(__ballot_sync(0xffffffffu, myf >= 0 && __float_as_uint(my) == m)) - 1;
-            seg_scan_mask(c, 1u << src, myf, qx, qy, qz, dmax, flt, best, lane);
+            const int src = __ffs(__ballot_sync(0xffffffffu, mymeta >= 0 && __float_as_uint(my) == m)) - 1;
+            seg_scan_mask(c, 1u << src, mys0, mymeta, qx, qy, qz, dmax, flt, best, lane);
             bound = __reduce_min_sync(0xffffffffu, best.d);
         }
         // ---- phase B
         for (int fb0 = f0; fb0 < f1; fb0 += 32) {
             const int f = fb0 + lane;
-            float lbf = __int_as_float(0x7f800000);
+            float lbf = __int_as_float(0x7f800000); int s0 = 0, meta = 0;
             if (f < f1) {
-                const float4 hi = c.fbox[2 * f + 1];
-                if ((__float_as_int(hi.w) >> 8) != skip_ring) lbf = seg_box_lb2(c.fbox[2 * f], hi, qx, qy, qz);
+                const float4 lo = c.fbox[2 * f], hi = c.fbox[2 * f + 1];
+                s0 = __float_as_int(lo.w); meta = __float_as_int(hi.w);
+                if ((meta >> 8) != skip_ring) lbf = seg_box_lb2(lo, hi, qx, qy, qz);
             }
             const unsigned fmask = __ballot_sync(0xffffffffu, __float_as_uint(lbf) <= bound && lbf < dmax);
-            seg_scan_mask(c, fmask, f, qx, qy, qz, dmax, flt, best, lane);
+            seg_scan_mask(c, fmask, s0, meta, qx, qy, qz, dmax, flt, best, lane);
             bound = __reduce_min_sync(0xffffffffu, best.d);
         }
     }
@@ -196,4 +198,75 @@ __device__ __forceinline__ int seg_search(const SegCloud &c, int ring_lo, int ri
     const int idx = __shfl_sync(0xffffffffu, best.idx, src);
     if (ring_out) *ring_out = (int)c.pts[idx].w;
     return idx;
+}
+
+// The two partner searches of a surface point in ONE walk over the arcs of rings ring - 2 .. ring + 2: arcs of `ring` feed the
+// same-ring partner (filter f2), the others the other-ring partner (filter f3); each class keeps its own bound.  Same results
+// as two seg_search calls on (ring, ring) and (ring - 2, ring + 2 without ring).
+__device__ __forceinline__ void seg_search_partners(const SegCloud &c, int ring, int n_rings, float qx, float qy, float qz, float dmax,
+                                                    const SegFilter &f2, const SegFilter &f3, int seed2, int seed3, int lane, int &i2, int &i3)
+{
+    const unsigned dmaxb = __float_as_uint(dmax);
+    const float INF = __int_as_float(0x7f800000);
+    SegBest b2, b3;
+    b2.d = b3.d = dmaxb; b2.t = b3.t = 0xFFFFFFFFu; b2.idx = b3.idx = -1;
+    if (seed2 >= 0) seg_consider(c, (int)c.pts[seed2].w, seed2, qx, qy, qz, dmax, f2, b2);
+    if (seed3 >= 0) seg_consider(c, (int)c.pts[seed3].w, seed3, qx, qy, qz, dmax, f3, b3);
+    const int f0 = c.seg_ring[max(ring - 2, 0)], f1 = c.seg_ring[min(ring + 2, n_rings - 1) + 1];
+    const bool need2 = b2.idx < 0, need3 = b3.idx < 0;          // warp-uniform (the seeds are)
+    if (need2 || need3) {
+        // ---- phase A: the nearest arc of each class that has no seed -> first bounds
+        float my2 = INF, my3 = INF; int s2 = 0, m2 = -1, s3 = 0, m3 = -1;
+        for (int f = f0 + lane; f < f1; f += 32) {
+            const float4 lo = c.fbox[2 * f], hi = c.fbox[2 * f + 1];
+            const int meta = __float_as_int(hi.w);
+            const float lb = seg_box_lb2(lo, hi, qx, qy, qz);
+            if ((meta >> 8) == ring) { if (lb < my2) { my2 = lb; s2 = __float_as_int(lo.w); m2 = meta; } }
+            else if (lb < my3) { my3 = lb; s3 = __float_as_int(lo.w); m3 = meta; }
+        }
+        if (need2) {
+            const unsigned m = __reduce_min_sync(0xffffffffu, m2 >= 0 ? __float_as_uint(my2) : 0x7f800000u);
+            if (m < dmaxb) {
+                const int src = __ffs(__ballot_sync(0xffffffffu, m2 >= 0 && __float_as_uint(my2) == m)) - 1;
+                seg_scan_mask(c, 1u << src, s2, m2, qx, qy, qz, dmax, f2, b2, lane);
+            }
+        }
+        if (need3) {
+            const unsigned m = __reduce_min_sync(0xffffffffu, m3 >= 0 ? __float_as_uint(my3) : 0x7f800000u);
+            if (m < dmaxb) {
+                const int src = __ffs(__ballot_sync(0xffffffffu, m3 >= 0 && __float_as_uint(my3) == m)) - 1;
+                seg_scan_mask(c, 1u << src, s3, m3, qx, qy, qz, dmax, f3, b3, lane);
+            }
+        }
+    }
+    unsigned bound2 = __reduce_min_sync(0xffffffffu, b2.d), bound3 = __reduce_min_sync(0xffffffffu, b3.d);
+    // ---- phase B
+    for (int fb0 = f0; fb0 < f1; fb0 += 32) {
+        const int f = fb0 + lane;
+        float lbf = INF; int s0 = 0, meta = 0; bool same = false;
+        if (f < f1) {
+            const float4 lo = c.fbox[2 * f], hi = c.fbox[2 * f + 1];
+            s0 = __float_as_int(lo.w); meta = __float_as_int(hi.w);
+            same = (meta >> 8) == ring;
+            lbf = seg_box_lb2(lo, hi, qx, qy, qz);
+        }
+        const bool in = lbf < dmax;
+        const unsigned k2 = __ballot_sync(0xffffffffu, in && same && __float_as_uint(lbf) <= bound2);
+        const unsigned k3 = __ballot_sync(0xffffffffu, in && !same && __float_as_uint(lbf) <= bound3);
+        if (k2) { seg_scan_mask(c, k2, s0, meta, qx, qy, qz, dmax, f2, b2, lane); bound2 = __reduce_min_sync(0xffffffffu, b2.d); }
+        if (k3) { seg_scan_mask(c, k3, s0, meta, qx, qy, qz, dmax, f3, b3, lane); bound3 = __reduce_min_sync(0xffffffffu, b3.d); }
+    }
+    // ---- (d2, tie) minima
+    {
+        const unsigned md = __reduce_min_sync(0xffffffffu, b2.idx >= 0 ? b2.d : 0xFFFFFFFFu);
+        const unsigned mt = __reduce_min_sync(0xffffffffu, (b2.idx >= 0 && b2.d == md) ? b2.t : 0xFFFFFFFFu);
+        const unsigned who = __ballot_sync(0xffffffffu, b2.idx >= 0 && b2.d == md && b2.t == mt);
+        i2 = who ? __shfl_sync(0xffffffffu, b2.idx, __ffs(who) - 1) : -1;
+    }
+    {
+        const unsigned md = __reduce_min_sync(0xffffffffu, b3.idx >= 0 ? b3.d : 0xFFFFFFFFu);
+        const unsigned mt = __reduce_min_sync(0xffffffffu, (b3.idx >= 0 && b3.d == md) ? b3.t : 0xFFFFFFFFu);
+        const unsigned who = __ballot_sync(0xffffffffu, b3.idx >= 0 && b3.d == md && b3.t == mt);
+        i3 = who ? __shfl_sync(0xffffffffu, b3.idx, __ffs(who) - 1) : -1;
+    }
 }
