@@ -207,3 +207,48 @@ def test_pairs_batch_thread_search_equals_oracle_and_single_pair_path(orc, lidar
                                           err_msg="pair %d field %s: batch vs single-pair path" % (p, f))
         for f in ("iterations", "n_corr_edge", "n_corr_plane", "status", "is_degenerate"):
             assert res[f][p] == singles[p][f], (p, f)
+
+
+def _late_first_column(raw, rings, k):
+    """the sweep as a driver delivers it when the packet that opens the message is not the one with the smallest azimuth:
+    column k of the (column-major) cloud first, then columns 0 .. k-1, then the rest.  startOri is taken from the first point,
+    so the k moved columns get a slightly NEGATIVE relTime and their intensity ring + relTime reads as ring - 1 through
+    upstream's int(intensity)"""
+    cols = raw.reshape(-1, rings, raw.shape[1])
+    return np.concatenate([cols[k:k + 1], cols[:k], cols[k + 1:]]).reshape(raw.shape).copy()
+
+
+@pytest.mark.parametrize("lidar,rings,max_points", [("VLP-16", 16, 32768), ("HDL-64E", 64, 131072)])
+def test_scan_ids_read_from_intensity_like_upstream(orc, lidar, rings, max_points):
+    """Upstream's partner loops take a target point's scan id from int(intensity), not from the ring it was filed
+    under; the two differ for points with negative relTime (and for less-flat centroids whose first member is one): they read as
+    the ring below, move between the same-scan / other-scan classes and decide where the loops break.  Found on frame 17072 of
+    the whole-bag workload (returns at ~2 cm range, random azimuth).  Every association round of the single-pair path
+    (voxel-hash search) and of the batch path (box index) must equal the oracle's, and so must the converged result."""
+    from vil_sensor_fusion_b200 import api
+    mk = scenes.vlp16_scan if lidar == "VLP-16" else scenes.hdl64_scan
+    raws = [_late_first_column(mk(0.1 * k, noise=0.01, seed=k, rolling=False), rings, 40 + 7 * k) for k in range(6)]
+    ocfg = orc.default_config(lidar, deskew=0)
+    c0, rs0, _ = orc.organise(ocfg, raws[0])
+    f0 = orc.extract(ocfg, c0, rs0)
+    slot = np.searchsorted(f0["less_flat_ring_start"], np.arange(len(f0["less_flat"])), side="right") - 1
+    assert np.count_nonzero(f0["less_flat"][:, 3].astype(int) != slot) > 20, "the input does not exercise the case"
+    gcfg = api.default_config(lidar, deskew=0, max_scans=6, max_points=max_points)
+    check = (0, 3) if lidar == "VLP-16" else (2,)
+    with api.Handle(gcfg) as h:
+        h.lib.vlo_set_trace(h._h, 1)
+        h.upload(raws)
+        h.organise()
+        h.extract()
+        for p in check:
+            ro, n_sharp, n_flat = _oracle_pair(orc, ocfg, raws[p], raws[p + 1], None, None)
+            per = 2 * n_sharp + 3 * n_flat
+            n_rounds = min(5, (ro["iterations"] + 4) // 5)
+            for path in ("batch", "single"):
+                res = h.register_pairs(np.arange(5), np.arange(1, 6))[p] if path == "batch" else h.register_pairs([p], [p + 1])[0]
+                for rnd in range(n_rounds):
+                    ci, si = h.pair_correspondences(p if path == "batch" else 0, rnd, n_sharp, n_flat)
+                    tr = ro["trace_idx"][rnd * per:(rnd + 1) * per]
+                    np.testing.assert_array_equal(ci.ravel(), tr[:2 * n_sharp], err_msg="%s corner idx, pair %d round %d" % (path, p, rnd))
+                    np.testing.assert_array_equal(si.ravel(), tr[2 * n_sharp:], err_msg="%s surf idx, pair %d round %d" % (path, p, rnd))
+                _compare(ro, res, "%s %s pair %d" % (lidar, path, p))

@@ -125,6 +125,8 @@ def load(path: str | None = None):
             "there is no CPU fallback" % p)
     lib = C.CDLL(p)
     for name, (res, args) in SYMBOLS.items():
+        if os.environ.get("VLO_LIB_PATH") and not hasattr(lib, name):
+            continue                     # an older build loaded for a tuning comparison: it may predate a symbol
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args

@@ -67,6 +67,23 @@ struct FilterPartner {
     }
 };
 
+// upstream's partner loops in full (oracle/laser_odometry.c partners_corner / partners_surf; the same rule as SegFilter mode 1,
+// segbox.cuh): around the nearest neighbour `ind` whose scan id is `scan` the forward loop visits the dense indices (ind, hi),
+// the backward loop (lo, ind) -- lo / hi from k3_partner_ranges -- and a forward point is in the same-scan class (want 2) if
+// its scan id (tag >> 24 = int(w)) is <= scan, a backward point if it is >= scan, otherwise in the other-scan class (want 3)
+struct FilterPartnerRange {
+    int ind, scan, lo, hi, want;
+    __device__ __forceinline__ bool operator()(unsigned tag, unsigned &tie) const
+    {
+        const int e = (int)(tag >> 24), idx = (int)(tag & 0xFFFFFFu);
+        if (idx <= lo || idx >= hi || idx == ind) return false;
+        int cls;
+        if (idx > ind) { cls = e > scan ? 3 : 2; tie = (unsigned)(idx - ind); }
+        else { cls = e < scan ? 3 : 2; tie = 0x40000000u + (unsigned)(ind - idx); }
+        return cls == want;
+    }
+};
+
 // K-best list kept sorted ascending by (d2 bits, tie) in registers.  Entries whose tag is
 // GRID_NOTAG are placeholders carrying the admission threshold; they always sit behind real ones.
 #define GRID_NOTAG 0xFFFFFFFFu

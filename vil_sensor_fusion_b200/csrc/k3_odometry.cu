@@ -73,8 +73,72 @@ __device__ __forceinline__ float seg_warp_max(float v) {
     return v;
 }
 
+// Where upstream's partner loops break (oracle/laser_odometry.c partners_corner / partners_surf): started at target
+// point j whose scan id is e = int(w_j), the forward loop stops at the first k > j with int(w_k) > e + 2.5 and the backward loop
+// at the first k < j with int(w_k) < e - 2.5; out[j] = (that backward k or -1, that forward k or n).  Scan ids follow the
+// ring-major order except where relTime is negative (segbox.cuh), so the answer is nearly always the start of ring e + 3 / the
+// end of ring e - 3: rings whose min / max scan id (s_emin / s_emax, filled by the caller) cannot stop the loop are skipped
+// whole, the stopping ring is walked.  No assumption on the scan ids beyond that; CTA-wide, no barrier inside.
+__device__ __forceinline__ void partner_ranges_cta(const float4 *pts, const int *rs, int R, int2 *out, const int *s_emin, const int *s_emax,
+                                                   int tid, int n_threads)
+{
+    const int n = rs[R];
+    for (int j = tid; j < n; j += n_threads) {
+        int lo = 0, hi = R;                      // ring slot of j
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (rs[mid] <= j) lo = mid; else hi = mid; }
+        const int e = (int)pts[j].w;
+        int F = n, B = -1;
+        {
+            const int t = e + 3; int k = j + 1; bool found = false;
+            for (int r = lo; r < R && !found; r++) {
+                if (s_emax[r] >= t) {
+                    const int end = rs[r + 1];
+                    for (k = max(k, rs[r]); k < end; k++) if ((int)pts[k].w >= t) { F = k; found = true; break; }
+                }
+            }
+        }
+        {
+            const int t = e - 3; int k = j - 1; bool found = false;
+            for (int r = lo; r >= 0 && !found; r--) {
+                if (s_emin[r] <= t) {
+                    const int beg = rs[r];
+                    for (k = min(k, rs[r + 1] - 1); k >= beg; k--) if ((int)pts[k].w <= t) { B = k; found = true; break; }
+                }
+            }
+        }
+        out[j] = make_int2(B, F);
+    }
+}
+
+// min / max scan id of every ring slot into shared memory (the caller barriers before and after)
+__device__ __forceinline__ void ring_scan_extrema_cta(const float4 *pts, const int *rs, int R, int *s_emin, int *s_emax, int tid, int n_threads)
+{
+    const int lane = tid & 31;
+    for (int r = tid >> 5; r < R; r += n_threads >> 5) {        // a warp per ring
+        int mn = 0x7fffffff, mx = (int)0x80000000;
+        for (int k = rs[r] + lane; k < rs[r + 1]; k += 32) { const int e = (int)pts[k].w; mn = min(mn, e); mx = max(mx, e); }
+        mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
+        if (lane == 0) { s_emin[r] = mn; s_emax[r] = mx; }
+    }
+}
+
+#if K3_ONLINE_GRID
+// the partner-loop ranges alone (the online tick searches voxel-hash grids, not the box index): one CTA per (scan, cloud)
+__global__ void __launch_bounds__(SEGB_THREADS) k3_partner_ranges(SegBuildParams p)
+{
+    __shared__ int s_emin[VLO_MAX_RINGS], s_emax[VLO_MAX_RINGS];
+    const int b = p.scan_first + blockIdx.x, w = blockIdx.y, tid = threadIdx.x;
+    const float4 *pts = p.pts[w] + (size_t)b * p.stride[w];
+    const int *rs = p.ring_start[w] + b * (VLO_MAX_RINGS + 1);
+    ring_scan_extrema_cta(pts, rs, p.n_rings, s_emin, s_emax, tid, SEGB_THREADS);
+    __syncthreads();
+    partner_ranges_cta(pts, rs, p.n_rings, p.ss.prange[w] + (size_t)b * p.stride[w], s_emin, s_emax, tid, SEGB_THREADS);
+}
+#endif
+
 __global__ void __launch_bounds__(SEGB_THREADS) k3_seg_build(SegBuildParams p)
 {
+    __shared__ int s_emin[VLO_MAX_RINGS], s_emax[VLO_MAX_RINGS];
     __shared__ int s_seg_ring[VLO_MAX_RINGS + 1];
     __shared__ int s_hist[SEG_CELLS];
     __shared__ int s_wsum[SEGB_THREADS / 32];
@@ -119,16 +183,18 @@ __global__ void __launch_bounds__(SEGB_THREADS) k3_seg_build(SegBuildParams p)
                 s0 = rs[lo] + SEG_PTS * (f - s_seg_ring[lo]); cnt = min(SEG_PTS, rs[lo + 1] - s0);
             }
             float x0 = INF, y0 = INF, z0 = INF, x1 = -INF, y1 = -INF, z1 = -INF;
-            if (l < cnt) { const float4 q = pts[s0 + l]; x0 = x1 = q.x; y0 = y1 = q.y; z0 = z1 = q.z; }
+            int e0 = 0x7fffffff, e1 = (int)0x80000000;           // min / max scan id (int(w), segbox.cuh) of the arc
+            if (l < cnt) { const float4 q = pts[s0 + l]; x0 = x1 = q.x; y0 = y1 = q.y; z0 = z1 = q.z; e0 = e1 = (int)q.w; }
             #pragma unroll
             for (int d = SEG_PTS / 2; d >= 1; d >>= 1) {       // the group's lane 0 ends up with the group's extrema
                 x0 = fminf(x0, __shfl_down_sync(0xffffffffu, x0, d)); y0 = fminf(y0, __shfl_down_sync(0xffffffffu, y0, d));
                 z0 = fminf(z0, __shfl_down_sync(0xffffffffu, z0, d)); x1 = fmaxf(x1, __shfl_down_sync(0xffffffffu, x1, d));
                 y1 = fmaxf(y1, __shfl_down_sync(0xffffffffu, y1, d)); z1 = fmaxf(z1, __shfl_down_sync(0xffffffffu, z1, d));
+                e0 = min(e0, __shfl_down_sync(0xffffffffu, e0, d)); e1 = max(e1, __shfl_down_sync(0xffffffffu, e1, d));
             }
             if (l == 0 && f < nseg) {
                 fbox[2 * f] = make_float4(x0, y0, z0, __int_as_float(s0));
-                fbox[2 * f + 1] = make_float4(x1, y1, z1, __int_as_float((lo << 8) | cnt));
+                fbox[2 * f + 1] = make_float4(x1, y1, z1, __int_as_float(SEG_META(e0, e1, cnt)));
             }
         }
     }
@@ -196,6 +262,10 @@ __global__ void __launch_bounds__(SEGB_THREADS) k3_seg_build(SegBuildParams p)
         x1 = seg_warp_max(x1); y1 = seg_warp_max(y1); z1 = seg_warp_max(z1);
         if (lane == 0) { cbox[2 * c] = make_float4(x0, y0, z0, __int_as_float(nmem)); cbox[2 * c + 1] = make_float4(x1, y1, z1, 0.0f); }
     }
+    // 5. where the partner loops started at each point break
+    ring_scan_extrema_cta(pts, rs, p.n_rings, s_emin, s_emax, tid, SEGB_THREADS);
+    __syncthreads();
+    partner_ranges_cta(pts, rs, p.n_rings, p.ss.prange[w] + (size_t)b * p.stride[w], s_emin, s_emax, tid, SEGB_THREADS);
 }
 
 __device__ __forceinline__ SegCloud seg_cloud_of(const OdomParams &p, int w, int scan)
@@ -206,7 +276,9 @@ __device__ __forceinline__ SegCloud seg_cloud_of(const OdomParams &p, int w, int
     c.cbox = p.ss.cbox[w] + (size_t)scan * p.ss.max_coarse[w] * 2;
     c.mbox = p.ss.mbox[w] + (size_t)scan * p.ss.max_seg[w] * 2;
     c.seg_ring = p.ss.seg_ring[w] + scan * (VLO_MAX_RINGS + 1);
-    c.nseg = p.ss.nseg[w][scan]; c.ncoarse = (c.nseg + 31) >> 5;
+    c.ring_start = (w == 0 ? p.lsharp_ring_start : p.lflat_ring_start) + scan * (VLO_MAX_RINGS + 1);
+    c.prange = p.ss.prange[w] + (size_t)scan * (w == 0 ? p.cap_lsharp : p.N);
+    c.nseg = p.ss.nseg[w][scan]; c.ncoarse = (c.nseg + 31) >> 5; c.n_rings = p.n_rings;
     return c;
 }
 
@@ -236,9 +308,9 @@ __global__ void __launch_bounds__(256) k3_assoc_warp(OdomParams p, int n_pairs)
             int i1 = -1, i2 = -1;
             if (nn.tag[0] != GRID_NOTAG) {
                 i1 = (int)(nn.tag[0] & 0xFFFFFFu);
-                int ring = (int)(nn.tag[0] >> 24);
-                FilterPartner f; f.ind = i1; f.ring_lo = ring - 2; f.ring_hi = ring + 2; f.skip_ring = ring;
-                f.fwd_bound = p.fwd_quirk ? min(n_sharp, n_lc) : n_lc;
+                const int2 rg = p.ss.prange[0][(size_t)last * p.cap_lsharp + i1];
+                FilterPartnerRange f; f.ind = i1; f.scan = (int)(nn.tag[0] >> 24); f.lo = rg.x; f.want = 3;
+                f.hi = min(rg.y, p.fwd_quirk ? min(n_sharp, n_lc) : n_lc);
                 TopK<1> pr;
                 grid_search<1>(p.gc, last, q.x, q.y, q.z, 25.0f, f, pr, lane, scratch[warp]);
                 if (pr.tag[0] != GRID_NOTAG) i2 = (int)(pr.tag[0] & 0xFFFFFFu);
@@ -255,10 +327,10 @@ __global__ void __launch_bounds__(256) k3_assoc_warp(OdomParams p, int n_pairs)
             int i1 = -1, i2 = -1, i3 = -1;
             if (nn.tag[0] != GRID_NOTAG) {
                 i1 = (int)(nn.tag[0] & 0xFFFFFFu);
-                int ring = (int)(nn.tag[0] >> 24);
-                int fb = p.fwd_quirk ? min(n_flat, n_ls) : n_ls;
-                FilterPartner f2; f2.ind = i1; f2.ring_lo = ring; f2.ring_hi = ring; f2.skip_ring = -1; f2.fwd_bound = fb;
-                FilterPartner f3; f3.ind = i1; f3.ring_lo = ring - 2; f3.ring_hi = ring + 2; f3.skip_ring = ring; f3.fwd_bound = fb;
+                const int2 rg = p.ss.prange[1][(size_t)last * p.N + i1];
+                FilterPartnerRange f2; f2.ind = i1; f2.scan = (int)(nn.tag[0] >> 24); f2.lo = rg.x; f2.want = 2;
+                f2.hi = min(rg.y, p.fwd_quirk ? min(n_flat, n_ls) : n_ls);
+                FilterPartnerRange f3 = f2; f3.want = 3;
                 TopK<1> p2, p3;
                 grid_search<1>(p.gsf, last, q.x, q.y, q.z, 25.0f, f2, p2, lane, scratch[warp]);
                 grid_search<1>(p.gsf, last, q.x, q.y, q.z, 25.0f, f3, p3, lane, scratch[warp]);
@@ -303,7 +375,6 @@ __global__ void __launch_bounds__(K3A_THREADS, K3A_MINB) k3_assoc(OdomParams p, 
     for (int a = 0; a < 6; a++) T[a] = p.pair_T[pair * 6 + a];
     const SegCloud cc = seg_cloud_of(p, 0, last), cs = seg_cloud_of(p, 1, last);
     const int total = n_sharp + n_flat;
-    const int R = p.n_rings;
     for (int base = blockIdx.x * K3A_MAXQ; base < total; base += gridDim.x * K3A_MAXQ) {       // CTA-uniform
         const int nq = min(K3A_MAXQ, total - base);
         __syncthreads();
@@ -322,21 +393,19 @@ __global__ void __launch_bounds__(K3A_THREADS, K3A_MINB) k3_assoc(OdomParams p, 
             int s1 = -1, s2 = -1, s3 = -1;
             if (round > 0) { s1 = o[0]; s2 = o[1]; if (!sharp) s3 = o[2]; }
             const int n_tgt = sharp ? n_lc : n_ls;
-            SegFilter f; f.mode = 0; f.ind = -1; f.ring_lo = 0; f.ring_hi = 0; f.skip_ring = -1; f.fwd_bound = 0;
-            int ring = 0;
-            const int i1 = seg_search(c, -1, -1, -1, q.x, q.y, q.z, 25.0f, f, (s1 >= 0 && s1 < n_tgt) ? s1 : -1, lane, &ring);
+            SegFilter f; f.mode = 0; f.ind = -1; f.scan = 0; f.lo = 0; f.hi = 0; f.want = 0;
+            int scan = 0;
+            const int i1 = seg_search(c, q.x, q.y, q.z, 25.0f, f, (s1 >= 0 && s1 < n_tgt) ? s1 : -1, lane, &scan);
             int i2 = -1, i3 = -1;
             if (i1 >= 0) {
-                f.mode = 1; f.ind = i1;
-                f.fwd_bound = sharp ? (p.fwd_quirk ? min(n_sharp, n_lc) : n_lc) : (p.fwd_quirk ? min(n_flat, n_ls) : n_ls);
-                const int rlo = max(ring - 2, 0), rhi = min(ring + 2, R - 1);
+                const int2 pr = c.prange[i1];                                // where the loops started at i1 break
+                f.mode = 1; f.ind = i1; f.scan = scan; f.lo = pr.x; f.want = 3;
+                f.hi = min(pr.y, sharp ? (p.fwd_quirk ? min(n_sharp, n_lc) : n_lc) : (p.fwd_quirk ? min(n_flat, n_ls) : n_ls));
                 if (sharp) {
-                    f.ring_lo = ring - 2; f.ring_hi = ring + 2; f.skip_ring = ring;
-                    i2 = seg_search(c, rlo, rhi, ring, q.x, q.y, q.z, 25.0f, f, (s2 >= 0 && s2 < n_tgt) ? s2 : -1, lane, nullptr);
+                    i2 = seg_search(c, q.x, q.y, q.z, 25.0f, f, (s2 >= 0 && s2 < n_tgt) ? s2 : -1, lane, nullptr);
                 } else {
-                    SegFilter f2 = f; f2.ring_lo = ring; f2.ring_hi = ring; f2.skip_ring = -1;             // same-ring partner
-                    f.ring_lo = ring - 2; f.ring_hi = ring + 2; f.skip_ring = ring;                         // other-ring partner
-                    seg_search_partners(c, ring, R, q.x, q.y, q.z, 25.0f, f2, f, (s2 >= 0 && s2 < n_tgt) ? s2 : -1,
+                    SegFilter f2 = f; f2.want = 2;                           // same-scan partner; f: other-scan partner
+                    seg_search_partners(c, q.x, q.y, q.z, 25.0f, f2, f, (s2 >= 0 && s2 < n_tgt) ? s2 : -1,
                                         (s3 >= 0 && s3 < n_tgt) ? s3 : -1, lane, i2, i3);
                 }
             }
@@ -577,13 +646,21 @@ int vlo_build_scan_grids(vlo_handle *h, int first, int count)
         GridSource ss = {};
         ss.pts = sb.lflat_pts; ss.pts_stride = (size_t)c.max_points;
         ss.n_dense = sb.counts; ss.n_dense_stride = 8; ss.n_dense_field = 4; ss.n_rings = c.n_rings;
-        return vlo_grid_build(h, h->gs_surf, ss, first, count, c.max_points);
+        rc = vlo_grid_build(h, h->gs_surf, ss, first, count, c.max_points); if (rc) return rc;
     }
 #endif
     SegBuildParams q;
     q.pts[0] = sb.lsharp_pts; q.stride[0] = (size_t)h->cap_lsharp; q.ring_start[0] = sb.lsharp_ring_start;
     q.pts[1] = sb.lflat_pts; q.stride[1] = (size_t)c.max_points; q.ring_start[1] = sb.lflat_ring_start;
     q.n_rings = c.n_rings; q.scan_first = first; q.ss = h->segs;
+#if K3_ONLINE_GRID
+    if (h->scan_index_grid) {
+        VLO_PROF(h, ST_GRID_BUILD, (k3_partner_ranges<<<dim3(count, 2), SEGB_THREADS, 0, h->stream>>>(q)));
+        h->launches += 1;
+        VLO_CUDA(cudaGetLastError());
+        return VLO_OK;
+    }
+#endif
     VLO_PROF(h, ST_GRID_BUILD, (k3_seg_build<<<dim3(count, 2), SEGB_THREADS, 0, h->stream>>>(q)));
     h->launches += 1;
     VLO_CUDA(cudaGetLastError());

@@ -32,13 +32,25 @@
 #define SEG_CELLS 1024              // 16 x 4 x 16 cells of the coarse grouping
 
 struct SegCloud {                   // one target cloud of one scan
-    const float4 *pts;              // dense ring-major points, ring = int(w)
-    const float4 *fbox;             // [nseg][2]: lo.xyz | first dense index (int bits), hi.xyz | (ring << 8 | count) (int bits)
+    const float4 *pts;              // dense ring-major points; the scan id upstream's partner loops read is int(w)
+    const float4 *fbox;             // [nseg][2]: lo.xyz | first dense index (int bits), hi.xyz | SEG_META(min scan id, max scan id, count) (int bits)
     const float4 *cbox;             // [ncoarse][2]: lo.xyz | member count, hi.xyz
     const float4 *mbox;             // [nseg][2]: the fine boxes again, in coarse-group order (group c = entries 32 c .. 32 c + 31): one trip, no indirection
     const int *seg_ring;            // [R + 1]
-    int nseg, ncoarse;
+    const int *ring_start;          // [R + 1] dense index of ring r's first point
+    const int2 *prange;             // [n] per target point: where upstream's backward / forward partner loops started at it break
+    int nseg, ncoarse, n_rings;
 };
+
+// Scan ids.  Upstream's partner loops read the scan id of a target point as int(intensity) (oracle/laser_odometry.c
+// partners_*), NOT the ring the point was filed under: intensity = ring + relTime and relTime is slightly negative for points
+// whose azimuth precedes the sweep's first point, so such a point (or a less-flat centroid whose first member is one) reads as
+// ring - 1.  The index therefore classifies by int(w) per point, keeps the min / max scan id of every arc for pruning, and
+// takes the loops' break positions from k3_partner_ranges.
+#define SEG_EBIAS 256
+#define SEG_META(emin, emax, cnt) ((min(max((emin) + SEG_EBIAS, 0), 1023) << 18) | (min(max((emax) + SEG_EBIAS, 0), 1023) << 8) | (cnt))
+#define SEG_META_EMIN(meta) ((int)(((unsigned)(meta)) >> 18) - SEG_EBIAS)
+#define SEG_META_EMAX(meta) ((int)((((unsigned)(meta)) >> 8) & 1023u) - SEG_EBIAS)
 
 __device__ __forceinline__ float seg_box_lb2(const float4 lo, const float4 hi, float qx, float qy, float qz)
 {
@@ -49,30 +61,42 @@ __device__ __forceinline__ float seg_box_lb2(const float4 lo, const float4 hi, f
 }
 
 // candidate admission + tie rule.  mode 0: plain nearest neighbour (tie = dense index, lowest wins);
-// mode 1: upstream's partner loops: forward indices first (ascending), then backward (descending)
+// mode 1: upstream's partner loops (oracle/laser_odometry.c partners_corner / partners_surf) around the nearest
+// neighbour `ind` whose scan id is `scan`: the forward loop visits the dense indices (ind, hi), the backward loop (lo, ind)
+// (lo / hi: where the loops break, k3_partner_ranges; hi also carries the forward-bound quirk); a forward point belongs to
+// the same-scan class (want 2) if its scan id is <= scan, a backward point if it is >= scan, everything else to the
+// other-scan class (want 3).  Ties: forward indices first (ascending), then backward (descending), as the loops visit them.
 struct SegFilter {
-    int mode, ind, ring_lo, ring_hi, skip_ring, fwd_bound;
-    __device__ __forceinline__ bool ring_ok(int ring) const { return mode == 0 || (ring >= ring_lo && ring <= ring_hi && ring != skip_ring); }
-    __device__ __forceinline__ bool operator()(int ring, int idx, unsigned &tie) const
+    int mode, ind, scan, lo, hi, want;
+    // can an arc (dense indices [s0, s0 + cnt), scan ids within [emin, emax]) hold a point of class `cls`?
+    __device__ __forceinline__ bool arc_may(int s0, int meta, int cls) const
+    {
+        const int cnt = meta & 0xff;
+        if (s0 + cnt - 1 <= lo || s0 >= hi) return false;
+        if ((unsigned)(scan + SEG_EBIAS - 1) >= 1021u) return true;                  // scan id outside what the arc summaries can express
+        const int emin = SEG_META_EMIN(meta), emax = SEG_META_EMAX(meta);
+        const bool fwd = s0 + cnt - 1 > ind, bwd = s0 < ind;                          // the arc holds forward / backward points
+        return cls == 2 ? ((fwd && emin <= scan) || (bwd && emax >= scan)) : ((fwd && emax > scan) || (bwd && emin < scan));
+    }
+    __device__ __forceinline__ bool operator()(int e, int idx, unsigned &tie) const
     {
         if (mode == 0) { tie = (unsigned)idx; return true; }
-        if (ring < ring_lo || ring > ring_hi || ring == skip_ring || idx == ind) return false;
-        if (idx > ind) { if (idx >= fwd_bound) return false; tie = (unsigned)(idx - ind); }
-        else tie = 0x40000000u + (unsigned)(ind - idx);
-        return true;
+        if (idx <= lo || idx >= hi || idx == ind) return false;
+        int cls;
+        if (idx > ind) { cls = e > scan ? 3 : 2; tie = (unsigned)(idx - ind); }
+        else { cls = e < scan ? 3 : 2; tie = 0x40000000u + (unsigned)(ind - idx); }
+        return cls == want;
     }
-    // the same rule on a voxel-hash tag (ring << 24 | dense index; grid.cuh)
-    __device__ __forceinline__ bool operator()(unsigned tag, unsigned &tie) const { return (*this)((int)(tag >> 24), (int)(tag & 0xFFFFFFu), tie); }
 };
 
 struct SegBest { unsigned d, t; int idx; };      // lane-local best: d = float bits of d2 (or of dmax: none yet)
 
-__device__ __forceinline__ void seg_consider(const SegCloud &c, int ring, int idx, float qx, float qy, float qz, float dmax,
+__device__ __forceinline__ void seg_consider(const SegCloud &c, int idx, float qx, float qy, float qz, float dmax,
                                              const SegFilter &flt, SegBest &best)
 {
     unsigned tie;
-    if (flt(ring, idx, tie)) {
-        const float4 p = c.pts[idx];
+    const float4 p = c.pts[idx];
+    if (flt((int)p.w, idx, tie)) {
         const float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
         const float d2 = (dx * dx + dy * dy) + dz * dz;
         const unsigned db = __float_as_uint(d2);
@@ -81,7 +105,7 @@ __device__ __forceinline__ void seg_consider(const SegCloud &c, int ring, int id
 }
 
 // the surviving arcs of `fmask` (bit k = the arc whose box lane k has just tested), SEG_GROUPS of them per pass: lane
-// group g looks at the g-th set bit, one point per lane.  `s0_mine` / `meta_mine`: first dense index and (ring << 8 | count)
+// group g looks at the g-th set bit, one point per lane.  `s0_mine` / `meta_mine`: first dense index and SEG_META (count in the low byte)
 // of this lane's arc, broadcast from the registers of the lane that tested it (no second trip to the box arrays).
 __device__ __forceinline__ void seg_scan_mask(const SegCloud &c, unsigned fmask, int s0_mine, int meta_mine, float qx, float qy, float qz,
                                               float dmax, const SegFilter &flt, SegBest &best, int lane)
@@ -94,25 +118,37 @@ __device__ __forceinline__ void seg_scan_mask(const SegCloud &c, unsigned fmask,
         for (int k = 0; k < SEG_GROUPS - 1; k++) if (k < g) m &= m - 1u;
         const int bit = m ? __ffs(m) - 1 : 0;
         const int s0 = __shfl_sync(0xffffffffu, s0_mine, bit), meta = __shfl_sync(0xffffffffu, meta_mine, bit);
-        if (m && l < (meta & 0xff)) seg_consider(c, meta >> 8, s0 + l, qx, qy, qz, dmax, flt, best);
+        if (m && l < (meta & 0xff)) seg_consider(c, s0 + l, qx, qy, qz, dmax, flt, best);
         #pragma unroll
         for (int k = 0; k < SEG_GROUPS; k++) fmask &= fmask - 1u;       // drop the SEG_GROUPS lowest set bits
     }
 }
 
-// Exact warp-cooperative search.  ring_lo < 0: every ring (coarse groups first); otherwise only the fine segments of
-// rings ring_lo .. ring_hi (one contiguous range of the ring-major numbering), skip_ring's segments left out.
+// arc (fine segment) that holds dense index k (0 <= k < number of points); warp-cooperative, every lane gets it
+__device__ __forceinline__ int seg_arc_of(const SegCloud &c, int k, int lane)
+{
+    int slot = -1;                               // the largest r with ring_start[r] <= k (ring_start is non-decreasing)
+    for (int r0 = 0; r0 <= c.n_rings; r0 += 32) {
+        const int r = r0 + lane;
+        slot += __popc(__ballot_sync(0xffffffffu, r <= c.n_rings && c.ring_start[r] <= k));
+    }
+    return c.seg_ring[slot] + ((k - c.ring_start[slot]) >> SEG_SHIFT);
+}
+
+// Exact warp-cooperative search.  flt.mode 0: every point (coarse groups first); mode 1: only the arcs that overlap the
+// dense-index range (flt.lo, flt.hi) of upstream's partner loops -- one contiguous range of the ring-major numbering --
+// and can hold a point of class flt.want.
 // seed >= 0: a point known to be a candidate (the previous association round's answer): the search starts from its
 // distance, so nearly every box is pruned at once.
 // Returns the dense index of the (d2, tie) minimum among admissible points with d2 < dmax, or -1; every lane gets it.
-__device__ __forceinline__ int seg_search(const SegCloud &c, int ring_lo, int ring_hi, int skip_ring, float qx, float qy, float qz,
+__device__ __forceinline__ int seg_search(const SegCloud &c, float qx, float qy, float qz,
                                           float dmax, const SegFilter &flt, int seed, int lane, int *ring_out)
 {
     const unsigned dmaxb = __float_as_uint(dmax);
     SegBest best; best.d = dmaxb; best.t = 0xFFFFFFFFu; best.idx = -1;
-    if (seed >= 0) seg_consider(c, (int)c.pts[seed].w, seed, qx, qy, qz, dmax, flt, best);      // same value in every lane
+    if (seed >= 0) seg_consider(c, seed, qx, qy, qz, dmax, flt, best);      // same value in every lane
     unsigned bound = best.d;                     // float bits of the best d2 any lane holds (dmax: none yet)
-    if (ring_lo < 0) {
+    if (flt.mode == 0) {
         if (best.idx < 0) {
             // ---- phase A: the coarse group nearest to the query, its nearest fine segment -> a first bound
             float my = __int_as_float(0x7f800000); int myc = -1;
@@ -152,21 +188,21 @@ __device__ __forceinline__ int seg_search(const SegCloud &c, int ring_lo, int ri
                 if (lane < nmem) {
                     const float4 lo = c.mbox[2 * (32 * cc + lane)], hi = c.mbox[2 * (32 * cc + lane) + 1];
                     s0 = __float_as_int(lo.w); meta = __float_as_int(hi.w);
-                    if (flt.ring_ok(meta >> 8)) lbf = seg_box_lb2(lo, hi, qx, qy, qz);
+                    lbf = seg_box_lb2(lo, hi, qx, qy, qz);
                 }
                 const unsigned fmask = __ballot_sync(0xffffffffu, __float_as_uint(lbf) <= bound && lbf < dmax);
                 seg_scan_mask(c, fmask, s0, meta, qx, qy, qz, dmax, flt, best, lane);
                 bound = __reduce_min_sync(0xffffffffu, best.d);
             }
         }
-    } else {
-        const int f0 = c.seg_ring[ring_lo], f1 = c.seg_ring[ring_hi + 1];
+    } else if (flt.hi - flt.lo > 1) {
+        const int f0 = seg_arc_of(c, flt.lo + 1, lane), f1 = seg_arc_of(c, flt.hi - 1, lane) + 1;
         if (best.idx < 0) {
             // ---- phase A: nearest admissible fine segment of the range -> a first bound
             float my = __int_as_float(0x7f800000); int mys0 = 0, mymeta = -1;
             for (int f = f0 + lane; f < f1; f += 32) {
                 const float4 lo = c.fbox[2 * f], hi = c.fbox[2 * f + 1];
-                if ((__float_as_int(hi.w) >> 8) == skip_ring) continue;
+                if (!flt.arc_may(__float_as_int(lo.w), __float_as_int(hi.w), flt.want)) continue;
                 const float lb = seg_box_lb2(lo, hi, qx, qy, qz);
                 if (lb < my) { my = lb; mys0 = __float_as_int(lo.w); mymeta = __float_as_int(hi.w); }
             }
@@ -183,7 +219,7 @@ __device__ __forceinline__ int seg_search(const SegCloud &c, int ring_lo, int ri
             if (f < f1) {
                 const float4 lo = c.fbox[2 * f], hi = c.fbox[2 * f + 1];
                 s0 = __float_as_int(lo.w); meta = __float_as_int(hi.w);
-                if ((meta >> 8) != skip_ring) lbf = seg_box_lb2(lo, hi, qx, qy, qz);
+                if (flt.arc_may(s0, meta, flt.want)) lbf = seg_box_lb2(lo, hi, qx, qy, qz);
             }
             const unsigned fmask = __ballot_sync(0xffffffffu, __float_as_uint(lbf) <= bound && lbf < dmax);
             seg_scan_mask(c, fmask, s0, meta, qx, qy, qz, dmax, flt, best, lane);
@@ -200,29 +236,31 @@ __device__ __forceinline__ int seg_search(const SegCloud &c, int ring_lo, int ri
     return idx;
 }
 
-// The two partner searches of a surface point in ONE walk over the arcs of rings ring - 2 .. ring + 2: arcs of `ring` feed the
-// same-ring partner (filter f2), the others the other-ring partner (filter f3); each class keeps its own bound.  Same results
-// as two seg_search calls on (ring, ring) and (ring - 2, ring + 2 without ring).
-__device__ __forceinline__ void seg_search_partners(const SegCloud &c, int ring, int n_rings, float qx, float qy, float qz, float dmax,
+// The two partner searches of a surface point in ONE walk over the arcs of the loops' dense-index range: arcs that can hold
+// same-scan points feed the same-scan partner (filter f2, want 2), arcs that can hold other-scan points the other-scan partner
+// (filter f3, want 3; nearly always an arc is one or the other); each class keeps its own bound.  f2 and f3 share ind / scan /
+// lo / hi.  Same results as two seg_search calls.
+__device__ __forceinline__ void seg_search_partners(const SegCloud &c, float qx, float qy, float qz, float dmax,
                                                     const SegFilter &f2, const SegFilter &f3, int seed2, int seed3, int lane, int &i2, int &i3)
 {
     const unsigned dmaxb = __float_as_uint(dmax);
     const float INF = __int_as_float(0x7f800000);
     SegBest b2, b3;
     b2.d = b3.d = dmaxb; b2.t = b3.t = 0xFFFFFFFFu; b2.idx = b3.idx = -1;
-    if (seed2 >= 0) seg_consider(c, (int)c.pts[seed2].w, seed2, qx, qy, qz, dmax, f2, b2);
-    if (seed3 >= 0) seg_consider(c, (int)c.pts[seed3].w, seed3, qx, qy, qz, dmax, f3, b3);
-    const int f0 = c.seg_ring[max(ring - 2, 0)], f1 = c.seg_ring[min(ring + 2, n_rings - 1) + 1];
+    if (seed2 >= 0) seg_consider(c, seed2, qx, qy, qz, dmax, f2, b2);
+    if (seed3 >= 0) seg_consider(c, seed3, qx, qy, qz, dmax, f3, b3);
+    int f0 = 0, f1 = 0;
+    if (f2.hi - f2.lo > 1) { f0 = seg_arc_of(c, f2.lo + 1, lane); f1 = seg_arc_of(c, f2.hi - 1, lane) + 1; }
     const bool need2 = b2.idx < 0, need3 = b3.idx < 0;          // warp-uniform (the seeds are)
     if (need2 || need3) {
         // ---- phase A: the nearest arc of each class that has no seed -> first bounds
         float my2 = INF, my3 = INF; int s2 = 0, m2 = -1, s3 = 0, m3 = -1;
         for (int f = f0 + lane; f < f1; f += 32) {
             const float4 lo = c.fbox[2 * f], hi = c.fbox[2 * f + 1];
-            const int meta = __float_as_int(hi.w);
+            const int s0 = __float_as_int(lo.w), meta = __float_as_int(hi.w);
             const float lb = seg_box_lb2(lo, hi, qx, qy, qz);
-            if ((meta >> 8) == ring) { if (lb < my2) { my2 = lb; s2 = __float_as_int(lo.w); m2 = meta; } }
-            else if (lb < my3) { my3 = lb; s3 = __float_as_int(lo.w); m3 = meta; }
+            if (f2.arc_may(s0, meta, 2) && lb < my2) { my2 = lb; s2 = s0; m2 = meta; }
+            if (f3.arc_may(s0, meta, 3) && lb < my3) { my3 = lb; s3 = s0; m3 = meta; }
         }
         if (need2) {
             const unsigned m = __reduce_min_sync(0xffffffffu, m2 >= 0 ? __float_as_uint(my2) : 0x7f800000u);
@@ -243,16 +281,16 @@ __device__ __forceinline__ void seg_search_partners(const SegCloud &c, int ring,
     // ---- phase B
     for (int fb0 = f0; fb0 < f1; fb0 += 32) {
         const int f = fb0 + lane;
-        float lbf = INF; int s0 = 0, meta = 0; bool same = false;
+        float lbf = INF; int s0 = 0, meta = 0; bool may2 = false, may3 = false;
         if (f < f1) {
             const float4 lo = c.fbox[2 * f], hi = c.fbox[2 * f + 1];
             s0 = __float_as_int(lo.w); meta = __float_as_int(hi.w);
-            same = (meta >> 8) == ring;
+            may2 = f2.arc_may(s0, meta, 2); may3 = f3.arc_may(s0, meta, 3);
             lbf = seg_box_lb2(lo, hi, qx, qy, qz);
         }
         const bool in = lbf < dmax;
-        const unsigned k2 = __ballot_sync(0xffffffffu, in && same && __float_as_uint(lbf) <= bound2);
-        const unsigned k3 = __ballot_sync(0xffffffffu, in && !same && __float_as_uint(lbf) <= bound3);
+        const unsigned k2 = __ballot_sync(0xffffffffu, in && may2 && __float_as_uint(lbf) <= bound2);
+        const unsigned k3 = __ballot_sync(0xffffffffu, in && may3 && __float_as_uint(lbf) <= bound3);
         if (k2) { seg_scan_mask(c, k2, s0, meta, qx, qy, qz, dmax, f2, b2, lane); bound2 = __reduce_min_sync(0xffffffffu, b2.d); }
         if (k3) { seg_scan_mask(c, k3, s0, meta, qx, qy, qz, dmax, f3, b3, lane); bound3 = __reduce_min_sync(0xffffffffu, b3.d); }
     }

@@ -153,6 +153,7 @@ extern "C" int vlo_create(const vlo_config *cfg, vlo_handle **out)
         ss.max_coarse[w] = ss.max_seg[w] / 32 + 1;
         HALLOC(ss.fbox[w], (size_t)B * ss.max_seg[w] * 2); HALLOC(ss.mbox[w], (size_t)B * ss.max_seg[w] * 2); HALLOC(ss.cbox[w], (size_t)B * ss.max_coarse[w] * 2);
         HALLOC(ss.perm[w], (size_t)B * ss.max_seg[w]); HALLOC(ss.seg_ring[w], (size_t)B * (VLO_MAX_RINGS + 1)); HALLOC(ss.nseg[w], (size_t)B);
+        HALLOC(ss.prange[w], (size_t)B * (w == 0 ? h->cap_lsharp : N));
     }
     HALLOC(h->map_n, 8);
     cudaMemset(h->map_n, 0, 8 * sizeof(int));
@@ -188,7 +189,7 @@ extern "C" void vlo_destroy(vlo_handle *h)
                      h->map_scans, h->map_result, h->imu_buf, h->imu_out };
     for (void *p : ptrs) if (p) cudaFree(p);
     vlo_lm_free(h);
-    for (int w = 0; w < 2; w++) { cudaFree(h->segs.fbox[w]); cudaFree(h->segs.mbox[w]); cudaFree(h->segs.cbox[w]); cudaFree(h->segs.perm[w]); cudaFree(h->segs.seg_ring[w]); cudaFree(h->segs.nseg[w]); }
+    for (int w = 0; w < 2; w++) { cudaFree(h->segs.fbox[w]); cudaFree(h->segs.mbox[w]); cudaFree(h->segs.cbox[w]); cudaFree(h->segs.perm[w]); cudaFree(h->segs.seg_ring[w]); cudaFree(h->segs.nseg[w]); cudaFree(h->segs.prange[w]); }
     free_gridset(h->gs_corner); free_gridset(h->gs_surf); free_gridset(h->gs_map[0]); free_gridset(h->gs_map[1]);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->upload_pinned) { cudaFreeHost(h->upload_pinned); cudaEventDestroy(h->upload_ev[0]); cudaEventDestroy(h->upload_ev[1]); }

@@ -57,6 +57,7 @@ struct GridSource {
 // ring-segment box indices of the scan-to-scan target clouds (segbox.cuh): per resident scan, cloud 0 = less sharp, 1 = less flat
 struct SegSet {
     float4 *fbox[2]; float4 *mbox[2]; float4 *cbox[2]; int *perm[2]; int *seg_ring[2]; int *nseg[2];
+    int2 *prange[2];          // [B][cap_lsharp] / [B][max_points]: where upstream's partner loops started at a target point break (k3_odometry.cu)
     int max_seg[2], max_coarse[2];
 };
 
