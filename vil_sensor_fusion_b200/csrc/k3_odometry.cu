@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(256) k3_assoc_warp(OdomParams p, int n_pairs)
 #define K3A_THREADS 128
 #define K3A_MAXQ 128             // queries per CTA share
 #ifndef K3A_MINB
-#define K3A_MINB 1
+#define K3A_MINB 10           // 48 registers: 10 CTAs per SM (left to itself ptxas takes 128 registers and halves the occupancy)
 #endif
 __global__ void __launch_bounds__(K3A_THREADS, K3A_MINB) k3_assoc(OdomParams p, int n_pairs, int round)
 {
