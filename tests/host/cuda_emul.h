@@ -206,12 +206,14 @@ static inline unsigned __ballot_sync(unsigned, int pred)
 { return emu_collective(pred ? 1ull : 0ull, [&](const unsigned long long *s, const bool *a) { unsigned m = 0; for (int l = 0; l < 32; l++) if (a[l] && s[l]) m |= 1u << l; return m; }); }
 static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0u; }
 static inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, !pred) == 0u; }
-template <class T, class Op> static inline T emu_reduce(T v, Op op)
-{ return emu_collective(emu_bits(v), [&](const unsigned long long *s, const bool *a) { T r = v; for (int l = 0; l < 32; l++) if (a[l]) r = op(r, emu_from<T>(s[l])); return r; }); }
-static inline unsigned __reduce_max_sync(unsigned, unsigned v) { return emu_reduce(v, [](unsigned a, unsigned b) { return a > b ? a : b; }); }
-static inline unsigned __reduce_min_sync(unsigned, unsigned v) { return emu_reduce(v, [](unsigned a, unsigned b) { return a < b ? a : b; }); }
-static inline int __reduce_max_sync(unsigned, int v) { return emu_reduce(v, [](int a, int b) { return a > b ? a : b; }); }
-static inline int __reduce_min_sync(unsigned, int v) { return emu_reduce(v, [](int a, int b) { return a < b ? a : b; }); }
+// reductions honour the member mask: sub-warp groups (the octets of csrc/octbox.cuh) reduce among themselves, provided every
+// live lane of the warp reaches the same call (each with its own group's mask) -- which is how the kernels use them
+template <class T, class Op> static inline T emu_reduce(unsigned mask, T v, Op op)
+{ return emu_collective(emu_bits(v), [&](const unsigned long long *s, const bool *a) { T r = v; for (int l = 0; l < 32; l++) if (a[l] && ((mask >> l) & 1u)) r = op(r, emu_from<T>(s[l])); return r; }); }
+static inline unsigned __reduce_max_sync(unsigned m, unsigned v) { return emu_reduce(m, v, [](unsigned a, unsigned b) { return a > b ? a : b; }); }
+static inline unsigned __reduce_min_sync(unsigned m, unsigned v) { return emu_reduce(m, v, [](unsigned a, unsigned b) { return a < b ? a : b; }); }
+static inline int __reduce_max_sync(unsigned m, int v) { return emu_reduce(m, v, [](int a, int b) { return a > b ? a : b; }); }
+static inline int __reduce_min_sync(unsigned m, int v) { return emu_reduce(m, v, [](int a, int b) { return a < b ? a : b; }); }
 static inline int __reduce_add_sync(unsigned, int v)
 { return emu_collective(emu_bits(v), [&](const unsigned long long *s, const bool *a) { int r = 0; for (int l = 0; l < 32; l++) if (a[l]) r += emu_from<int>(s[l]); return r; }); }
 template <class T> static inline unsigned __match_any_sync(unsigned, T v)

@@ -31,7 +31,7 @@ struct OdomParams {
     const int *counts;                                   // [B][8]
     int n_rings;
     // pairs
-    const int *pair_last, *pair_cur; float *pair_T; int *pair_state; int *cidx, *sidx; vlo_result *result;
+    const int *pair_last, *pair_cur; float *pair_T; int *pair_state; int *cidx, *sidx; vlo_result *result; int max_pairs;
     GridSet gc, gsf;                                     // corner / surf voxel-hash grids, grid index = scan index
     SegSet ss;                                           // ring-segment box index of every resident scan's target clouds (batches)
     int deskew; float inv_period; int fwd_quirk;
@@ -75,12 +75,13 @@ __device__ __forceinline__ float seg_warp_max(float v) {
 
 // Where upstream's partner loops break (oracle/laser_odometry.c partners_corner / partners_surf): started at target
 // point j whose scan id is e = int(w_j), the forward loop stops at the first k > j with int(w_k) > e + 2.5 and the backward loop
-// at the first k < j with int(w_k) < e - 2.5; out[j] = (that backward k or -1, that forward k or n).  Scan ids follow the
+// at the first k < j with int(w_k) < e - 2.5; out[j] = (that backward k or -1, that forward k or n, and -- with the box index -- the arcs
+// [f0, f1) that hold the points in between).  Scan ids follow the
 // ring-major order except where relTime is negative (segbox.cuh), so the answer is nearly always the start of ring e + 3 / the
 // end of ring e - 3: rings whose min / max scan id (s_emin / s_emax, filled by the caller) cannot stop the loop are skipped
 // whole, the stopping ring is walked.  No assumption on the scan ids beyond that; CTA-wide, no barrier inside.
-__device__ __forceinline__ void partner_ranges_cta(const float4 *pts, const int *rs, int R, int2 *out, const int *s_emin, const int *s_emax,
-                                                   int tid, int n_threads)
+__device__ __forceinline__ void partner_ranges_cta(const float4 *pts, const int *rs, int R, int4 *out, const int *s_emin, const int *s_emax,
+                                                   const int *seg_ring, int tid, int n_threads)
 {
     const int n = rs[R];
     for (int j = tid; j < n; j += n_threads) {
@@ -106,7 +107,17 @@ __device__ __forceinline__ void partner_ranges_cta(const float4 *pts, const int 
                 }
             }
         }
-        out[j] = make_int2(B, F);
+        // the arcs [f0, f1) of the box index that hold the points between the two break positions
+        int f0 = 0, f1 = 0;
+        if (seg_ring && F - B > 1) {
+            int a = 0, b = R;
+            while (b - a > 1) { const int mid = (a + b) >> 1; if (rs[mid] <= B + 1) a = mid; else b = mid; }
+            f0 = seg_ring[a] + ((B + 1 - rs[a]) >> SEG_SHIFT);
+            a = 0; b = R;
+            while (b - a > 1) { const int mid = (a + b) >> 1; if (rs[mid] <= F - 1) a = mid; else b = mid; }
+            f1 = seg_ring[a] + ((F - 1 - rs[a]) >> SEG_SHIFT) + 1;
+        }
+        out[j] = make_int4(B, F, f0, f1);
     }
 }
 
@@ -132,7 +143,7 @@ __global__ void __launch_bounds__(SEGB_THREADS) k3_partner_ranges(SegBuildParams
     const int *rs = p.ring_start[w] + b * (VLO_MAX_RINGS + 1);
     ring_scan_extrema_cta(pts, rs, p.n_rings, s_emin, s_emax, tid, SEGB_THREADS);
     __syncthreads();
-    partner_ranges_cta(pts, rs, p.n_rings, p.ss.prange[w] + (size_t)b * p.stride[w], s_emin, s_emax, tid, SEGB_THREADS);
+    partner_ranges_cta(pts, rs, p.n_rings, p.ss.prange[w] + (size_t)b * p.stride[w], s_emin, s_emax, nullptr, tid, SEGB_THREADS);
 }
 #endif
 
@@ -265,7 +276,7 @@ __global__ void __launch_bounds__(SEGB_THREADS) k3_seg_build(SegBuildParams p)
     // 5. where the partner loops started at each point break
     ring_scan_extrema_cta(pts, rs, p.n_rings, s_emin, s_emax, tid, SEGB_THREADS);
     __syncthreads();
-    partner_ranges_cta(pts, rs, p.n_rings, p.ss.prange[w] + (size_t)b * p.stride[w], s_emin, s_emax, tid, SEGB_THREADS);
+    partner_ranges_cta(pts, rs, p.n_rings, p.ss.prange[w] + (size_t)b * p.stride[w], s_emin, s_emax, s_seg_ring, tid, SEGB_THREADS);
 }
 
 __device__ __forceinline__ SegCloud seg_cloud_of(const OdomParams &p, int w, int scan)
@@ -308,7 +319,7 @@ __global__ void __launch_bounds__(256) k3_assoc_warp(OdomParams p, int n_pairs)
             int i1 = -1, i2 = -1;
             if (nn.tag[0] != GRID_NOTAG) {
                 i1 = (int)(nn.tag[0] & 0xFFFFFFu);
-                const int2 rg = p.ss.prange[0][(size_t)last * p.cap_lsharp + i1];
+                const int4 rg = p.ss.prange[0][(size_t)last * p.cap_lsharp + i1];
                 FilterPartnerRange f; f.ind = i1; f.scan = (int)(nn.tag[0] >> 24); f.lo = rg.x; f.want = 3;
                 f.hi = min(rg.y, p.fwd_quirk ? min(n_sharp, n_lc) : n_lc);
                 TopK<1> pr;
@@ -327,7 +338,7 @@ __global__ void __launch_bounds__(256) k3_assoc_warp(OdomParams p, int n_pairs)
             int i1 = -1, i2 = -1, i3 = -1;
             if (nn.tag[0] != GRID_NOTAG) {
                 i1 = (int)(nn.tag[0] & 0xFFFFFFu);
-                const int2 rg = p.ss.prange[1][(size_t)last * p.N + i1];
+                const int4 rg = p.ss.prange[1][(size_t)last * p.N + i1];
                 FilterPartnerRange f2; f2.ind = i1; f2.scan = (int)(nn.tag[0] >> 24); f2.lo = rg.x; f2.want = 2;
                 f2.hi = min(rg.y, p.fwd_quirk ? min(n_flat, n_ls) : n_ls);
                 FilterPartnerRange f3 = f2; f3.want = 3;
@@ -357,27 +368,37 @@ __global__ void __launch_bounds__(256) k3_assoc_warp(OdomParams p, int n_pairs)
 // 4.9 ms vs 11.2 / 22.8 ms (1.0 / 0.7 m cells) -- the hash version fell back to walking cell shells whenever a partner was
 // more than one cell edge away -- with bit-identical results.
 #define K3A_THREADS 128
-#define K3A_MAXQ 128             // queries per CTA share
+#define K3A_MAXQ 256             // queries per ticket
 #ifndef K3A_MINB
 #define K3A_MINB 10           // 48 registers: 10 CTAs per SM (left to itself ptxas takes 128 registers and halves the occupancy)
 #endif
-__global__ void __launch_bounds__(K3A_THREADS, K3A_MINB) k3_assoc(OdomParams p, int n_pairs, int round)
+__global__ void __launch_bounds__(K3A_THREADS, K3A_MINB) k3_assoc(OdomParams p, int n_pairs, int round, int shares_per_pair)
 {
     __shared__ float4 s_q[K3A_MAXQ];
-    const int pair = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (p.pair_state[pair * 4 + 0]) return;                          // converged
-    const int last = p.pair_last[pair], cur = p.pair_cur[pair];
-    const int n_sharp = p.counts[cur * 8 + 1], n_flat = p.counts[cur * 8 + 3];
-    const int n_lc = p.counts[last * 8 + 2], n_ls = p.counts[last * 8 + 4];
-    if (!(n_lc > 10 && n_ls > 100)) return;
-    float T[6];
-    #pragma unroll
-    for (int a = 0; a < 6; a++) T[a] = p.pair_T[pair * 6 + a];
-    const SegCloud cc = seg_cloud_of(p, 0, last), cs = seg_cloud_of(p, 1, last);
-    const int total = n_sharp + n_flat;
-    for (int base = blockIdx.x * K3A_MAXQ; base < total; base += gridDim.x * K3A_MAXQ) {       // CTA-uniform
-        const int nq = min(K3A_MAXQ, total - base);
+    __shared__ int s_ticket;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int *tickets = p.pair_state + (size_t)p.max_pairs * 4;           // one work counter per association round (zeroed by k3_init_pairs)
+    // persistent CTAs draw (pair, share of K3A_MAXQ queries) tickets: every CTA slot of the device stays busy until the round's
+    // work is gone (a (share, pair) grid ran 1.6 waves: the second one left a third of the machine idle)
+    while (true) {
+        __syncthreads();                                             // the previous share is done with s_q / s_ticket
+        if (tid == 0) s_ticket = atomicAdd(&tickets[round], 1);
         __syncthreads();
+        const int ticket = s_ticket;
+        if (ticket >= n_pairs * shares_per_pair) break;
+        const int pair = ticket / shares_per_pair, base = (ticket - pair * shares_per_pair) * K3A_MAXQ;
+        if (p.pair_state[pair * 4 + 0]) continue;                    // converged
+        const int last = p.pair_last[pair], cur = p.pair_cur[pair];
+        const int n_sharp = p.counts[cur * 8 + 1], n_flat = p.counts[cur * 8 + 3];
+        const int n_lc = p.counts[last * 8 + 2], n_ls = p.counts[last * 8 + 4];
+        if (!(n_lc > 10 && n_ls > 100)) continue;
+        const int total = n_sharp + n_flat;
+        if (base >= total) continue;
+        float T[6];
+        #pragma unroll
+        for (int a = 0; a < 6; a++) T[a] = p.pair_T[pair * 6 + a];
+        const SegCloud cc = seg_cloud_of(p, 0, last), cs = seg_cloud_of(p, 1, last);
+        const int nq = min(K3A_MAXQ, total - base);
         for (int k = tid; k < nq; k += K3A_THREADS) {
             const int wq = base + k;
             s_q[k] = vlo_to_start(T, wq < n_sharp ? p.sharp_pts[(size_t)cur * p.cap_sharp + wq] : p.flat_pts[(size_t)cur * p.cap_flat + (wq - n_sharp)],
@@ -393,13 +414,13 @@ __global__ void __launch_bounds__(K3A_THREADS, K3A_MINB) k3_assoc(OdomParams p, 
             int s1 = -1, s2 = -1, s3 = -1;
             if (round > 0) { s1 = o[0]; s2 = o[1]; if (!sharp) s3 = o[2]; }
             const int n_tgt = sharp ? n_lc : n_ls;
-            SegFilter f; f.mode = 0; f.ind = -1; f.scan = 0; f.lo = 0; f.hi = 0; f.want = 0;
+            SegFilter f; f.mode = 0; f.ind = -1; f.scan = 0; f.lo = 0; f.hi = 0; f.want = 0; f.f0 = f.f1 = 0;
             int scan = 0;
             const int i1 = seg_search(c, q.x, q.y, q.z, 25.0f, f, (s1 >= 0 && s1 < n_tgt) ? s1 : -1, lane, &scan);
             int i2 = -1, i3 = -1;
             if (i1 >= 0) {
-                const int2 pr = c.prange[i1];                                // where the loops started at i1 break
-                f.mode = 1; f.ind = i1; f.scan = scan; f.lo = pr.x; f.want = 3;
+                const int4 pr = c.prange[i1];                                // where the loops started at i1 break, the arcs in between
+                f.mode = 1; f.ind = i1; f.scan = scan; f.lo = pr.x; f.want = 3; f.f0 = pr.z; f.f1 = pr.w;
                 f.hi = min(pr.y, sharp ? (p.fwd_quirk ? min(n_sharp, n_lc) : n_lc) : (p.fwd_quirk ? min(n_flat, n_ls) : n_ls));
                 if (sharp) {
                     i2 = seg_search(c, q.x, q.y, q.z, 25.0f, f, (s2 >= 0 && s2 < n_tgt) ? s2 : -1, lane, nullptr);
@@ -576,6 +597,7 @@ __global__ void __launch_bounds__(GN_THREADS) k3_gn(OdomParams p, int iter_base,
 __global__ void k3_init_pairs(OdomParams p, const float *seeds, int n_pairs)
 {
     int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair < 64) p.pair_state[(size_t)p.max_pairs * 4 + pair] = 0;            // the association rounds' work tickets
     if (pair >= n_pairs) return;
     for (int a = 0; a < 6; a++) p.pair_T[pair * 6 + a] = seeds ? seeds[pair * 6 + a] : 0.0f;
     int *st = p.pair_state + pair * 4;
@@ -622,7 +644,7 @@ static OdomParams make_params(vlo_handle *h)
     p.lsharp_pts = sb.lsharp_pts; p.cap_lsharp = h->cap_lsharp; p.lflat_pts = sb.lflat_pts; p.N = c.max_points;
     p.lsharp_ring_start = sb.lsharp_ring_start;
     p.lflat_ring_start = sb.lflat_ring_start; p.counts = sb.counts; p.n_rings = c.n_rings;
-    p.pair_last = h->pair_last; p.pair_cur = h->pair_cur; p.pair_T = h->pair_T; p.pair_state = h->pair_state;
+    p.pair_last = h->pair_last; p.pair_cur = h->pair_cur; p.pair_T = h->pair_T; p.pair_state = h->pair_state; p.max_pairs = h->max_pairs;
     p.cidx = h->pair_cidx; p.sidx = h->pair_sidx; p.result = h->pair_result;
     p.gc = h->gs_corner; p.gsf = h->gs_surf; p.ss = h->segs;
     p.deskew = c.deskew; p.inv_period = 1.0f / c.scan_period; p.fwd_quirk = c.odom_forward_bound_quirk;
@@ -706,9 +728,15 @@ int vlo_launch_register_pairs(vlo_handle *h, int n_pairs, const float *d_seeds, 
     if (!h->grids_valid) { int rc = vlo_build_scan_grids(h, 0, h->sb.n_scans); if (rc) return rc; h->grids_valid = 1; }
     // association grid: every CTA owns a contiguous share of its pair's queries, one warp per query; a single pair (the
     // online tick) is spread over the whole machine, a batch gets as many CTAs per pair as keep every SM busy
-    const int n_q = h->cap_sharp + h->cap_flat;
-    const int fill = std::max(1, (148 * 16 + n_pairs - 1) / n_pairs);
-    dim3 ga(std::max(1, std::min((n_q + K3A_THREADS / 32 - 1) / (K3A_THREADS / 32), fill)), n_pairs);
+    const int shares = (h->cap_sharp + h->cap_flat + K3A_MAXQ - 1) / K3A_MAXQ;
+    if (c.odom_max_iterations > 5 * 64) { h->err = "odomMaxIterations: at most 320"; return VLO_ERR_INVALID_ARG; }
+    if (!h->k3a_ctas) {                                  // persistent grid: every CTA slot of the device (per handle = per device)
+        int occ = 0, sms = 0;
+        VLO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_assoc, K3A_THREADS, 0));
+        VLO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device));
+        h->k3a_ctas = std::max(1, occ * sms);
+    }
+    const int ga = std::max(1, std::min(h->k3a_ctas, n_pairs * shares));
 #if K3_ONLINE_GRID
     dim3 gw(std::max(1, std::min(((h->cap_sharp + h->cap_flat) * 32 + 255) / 256, (148 * 8 + n_pairs - 1) / n_pairs)), n_pairs);
 #endif
@@ -718,7 +746,7 @@ int vlo_launch_register_pairs(vlo_handle *h, int n_pairs, const float *d_seeds, 
         if (h->scan_index_grid) VLO_PROF(h, ST_ASSOC, (k3_assoc_warp<<<gw, 256, 0, h->stream>>>(p, n_pairs)));
         else
 #endif
-        VLO_PROF(h, ST_ASSOC, (k3_assoc<<<ga, K3A_THREADS, 0, h->stream>>>(p, n_pairs, round)));
+        VLO_PROF(h, ST_ASSOC, (k3_assoc<<<ga, K3A_THREADS, 0, h->stream>>>(p, n_pairs, round, shares)));
         if (h->trace && round < 5) {
             int *dst = h->pair_trace + (size_t)round * trace_stride;
             VLO_CUDA(cudaMemcpyAsync(dst, h->pair_cidx, sizeof(int) * (size_t)n_pairs * h->cap_sharp * 2, cudaMemcpyDeviceToDevice, h->stream));

@@ -38,7 +38,7 @@ struct SegCloud {                   // one target cloud of one scan
     const float4 *mbox;             // [nseg][2]: the fine boxes again, in coarse-group order (group c = entries 32 c .. 32 c + 31): one trip, no indirection
     const int *seg_ring;            // [R + 1]
     const int *ring_start;          // [R + 1] dense index of ring r's first point
-    const int2 *prange;             // [n] per target point: where upstream's backward / forward partner loops started at it break
+    const int4 *prange;             // [n] per target point: where upstream's backward / forward partner loops started at it break (.x, .y) and the arcs [.z, .w) in between
     int nseg, ncoarse, n_rings;
 };
 
@@ -68,6 +68,7 @@ __device__ __forceinline__ float seg_box_lb2(const float4 lo, const float4 hi, f
 // other-scan class (want 3).  Ties: forward indices first (ascending), then backward (descending), as the loops visit them.
 struct SegFilter {
     int mode, ind, scan, lo, hi, want;
+    int f0, f1;                 // the arcs that hold the dense indices (lo, hi)  (k3_partner_ranges)
     // can an arc (dense indices [s0, s0 + cnt), scan ids within [emin, emax]) hold a point of class `cls`?
     __device__ __forceinline__ bool arc_may(int s0, int meta, int cls) const
     {
@@ -122,17 +123,6 @@ __device__ __forceinline__ void seg_scan_mask(const SegCloud &c, unsigned fmask,
         #pragma unroll
         for (int k = 0; k < SEG_GROUPS; k++) fmask &= fmask - 1u;       // drop the SEG_GROUPS lowest set bits
     }
-}
-
-// arc (fine segment) that holds dense index k (0 <= k < number of points); warp-cooperative, every lane gets it
-__device__ __forceinline__ int seg_arc_of(const SegCloud &c, int k, int lane)
-{
-    int slot = -1;                               // the largest r with ring_start[r] <= k (ring_start is non-decreasing)
-    for (int r0 = 0; r0 <= c.n_rings; r0 += 32) {
-        const int r = r0 + lane;
-        slot += __popc(__ballot_sync(0xffffffffu, r <= c.n_rings && c.ring_start[r] <= k));
-    }
-    return c.seg_ring[slot] + ((k - c.ring_start[slot]) >> SEG_SHIFT);
 }
 
 // Exact warp-cooperative search.  flt.mode 0: every point (coarse groups first); mode 1: only the arcs that overlap the
@@ -196,7 +186,7 @@ __device__ __forceinline__ int seg_search(const SegCloud &c, float qx, float qy,
             }
         }
     } else if (flt.hi - flt.lo > 1) {
-        const int f0 = seg_arc_of(c, flt.lo + 1, lane), f1 = seg_arc_of(c, flt.hi - 1, lane) + 1;
+        const int f0 = flt.f0, f1 = flt.f1;
         if (best.idx < 0) {
             // ---- phase A: nearest admissible fine segment of the range -> a first bound
             float my = __int_as_float(0x7f800000); int mys0 = 0, mymeta = -1;
@@ -250,7 +240,7 @@ __device__ __forceinline__ void seg_search_partners(const SegCloud &c, float qx,
     if (seed2 >= 0) seg_consider(c, seed2, qx, qy, qz, dmax, f2, b2);
     if (seed3 >= 0) seg_consider(c, seed3, qx, qy, qz, dmax, f3, b3);
     int f0 = 0, f1 = 0;
-    if (f2.hi - f2.lo > 1) { f0 = seg_arc_of(c, f2.lo + 1, lane); f1 = seg_arc_of(c, f2.hi - 1, lane) + 1; }
+    if (f2.hi - f2.lo > 1) { f0 = f2.f0; f1 = f2.f1; }
     const bool need2 = b2.idx < 0, need3 = b3.idx < 0;          // warp-uniform (the seeds are)
     if (need2 || need3) {
         // ---- phase A: the nearest arc of each class that has no seed -> first bounds

@@ -105,7 +105,7 @@ extern "C" int vlo_create(const vlo_config *cfg, vlo_handle **out)
     h->status_word = nullptr; h->pair_T = h->pair_seed = nullptr; h->pair_last = h->pair_cur = h->pair_state = nullptr;
     h->pair_cidx = h->pair_sidx = h->pair_trace = nullptr; h->pair_result = nullptr;
     h->map_partials = nullptr; h->map_idx5 = nullptr; h->map_T = h->map_seed = nullptr; h->map_state = h->map_ncorr = h->map_scans = h->map_done = nullptr;
-    h->k1_smem_configured = h->k1c_smem_configured = 0; h->dev_sms = h->k5_occ_assoc = h->k5_occ_lin = h->k3_gn_configured = 0;
+    h->k1_smem_configured = h->k1c_smem_configured = 0; h->dev_sms = h->k5_occ_assoc = h->k5_occ_lin = h->k3_gn_configured = h->k3a_ctas = 0;
     h->map_result = nullptr; h->coop_resident = 0; h->map_qmax = 0; h->last_n_map = 0; h->last_n_pairs = 0;
     h->imu_buf = nullptr; h->imu_buf_bytes = 0; h->imu_out = nullptr; h->imu_out_cap = 0;
     h->online_have_last = 0; h->online_slot = 0; h->prof_enabled = 0; h->prof_used = 0;
@@ -139,7 +139,7 @@ extern "C" int vlo_create(const vlo_config *cfg, vlo_handle **out)
     // registration workspace: at most one pair per resident scan
     h->max_pairs = B;
     HALLOC(h->pair_T, (size_t)B * 6); HALLOC(h->pair_seed, (size_t)B * 6);
-    HALLOC(h->pair_last, (size_t)B); HALLOC(h->pair_cur, (size_t)B); HALLOC(h->pair_state, (size_t)B * 4);
+    HALLOC(h->pair_last, (size_t)B); HALLOC(h->pair_cur, (size_t)B); HALLOC(h->pair_state, (size_t)B * 4 + 64);       // + one work counter per association round
     HALLOC(h->pair_cidx, (size_t)B * h->cap_sharp * 2); HALLOC(h->pair_sidx, (size_t)B * h->cap_flat * 3);
     HALLOC(h->pair_trace, (size_t)B * 5 * (h->cap_sharp * 2 + h->cap_flat * 3));
     HALLOC(h->pair_result, (size_t)B);

@@ -57,7 +57,8 @@ struct GridSource {
 // ring-segment box indices of the scan-to-scan target clouds (segbox.cuh): per resident scan, cloud 0 = less sharp, 1 = less flat
 struct SegSet {
     float4 *fbox[2]; float4 *mbox[2]; float4 *cbox[2]; int *perm[2]; int *seg_ring[2]; int *nseg[2];
-    int2 *prange[2];          // [B][cap_lsharp] / [B][max_points]: where upstream's partner loops started at a target point break (k3_odometry.cu)
+    int4 *prange[2];          // [B][cap_lsharp] / [B][max_points] per target point: where upstream's partner loops started there break (.x backward,
+                              // .y forward) and the arcs [.z, .w) of the box index in between (k3_odometry.cu)
     int max_seg[2], max_coarse[2];
 };
 
@@ -157,7 +158,7 @@ struct vlo_handle {
     // per-device launch configuration, cached per HANDLE (function attributes and occupancy are per device; a process may
     // hold handles on several devices)
     size_t k1_smem_configured, k1c_smem_configured;
-    int dev_sms, k5_occ_assoc, k5_occ_lin, k3_gn_configured;
+    int dev_sms, k5_occ_assoc, k5_occ_lin, k3_gn_configured, k3a_ctas;
     LaserMapDev lm;
     // IMU staging (grown on demand)
     double *imu_buf; size_t imu_buf_bytes; vlo_preint *imu_out; int imu_out_cap;
