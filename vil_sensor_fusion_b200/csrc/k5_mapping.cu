@@ -368,6 +368,7 @@ __global__ void __launch_bounds__(KNN_THREADS) k5_assoc(MapParams p, int it, int
 }
 
 // linearisation + level-1 sums of every unconverged slot; the warp that completes a slot's last tile solves the slot
+// (8 CTAs per SM at 64 registers measured the same as 6 at 80: 0.1528 vs 0.1529 ms per launch -- not occupancy-bound)
 __global__ void __launch_bounds__(KNN_THREADS, 6) k5_lin(MapParams p, int it, int n)
 {
     VLO_DYN_SMEM_INT(s_dyn);

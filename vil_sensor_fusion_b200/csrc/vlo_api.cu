@@ -106,6 +106,7 @@ extern "C" int vlo_create(const vlo_config *cfg, vlo_handle **out)
     h->pair_cidx = h->pair_sidx = h->pair_trace = nullptr; h->pair_result = nullptr;
     h->map_partials = nullptr; h->map_idx5 = nullptr; h->map_T = h->map_seed = nullptr; h->map_state = h->map_ncorr = h->map_scans = h->map_done = nullptr;
     h->k1_smem_configured = h->k1c_smem_configured = 0; h->dev_sms = h->k5_occ_assoc = h->k5_occ_lin = h->k3_gn_configured = h->k3a_ctas = 0;
+    { const char *e0 = getenv("VLO_K0_SUB"), *e1 = getenv("VLO_K1_SUB"); h->k0_sub = e0 ? atoi(e0) : 0; h->k1_sub = e1 ? atoi(e1) : 0; }
     h->map_result = nullptr; h->coop_resident = 0; h->map_qmax = 0; h->last_n_map = 0; h->last_n_pairs = 0;
     h->imu_buf = nullptr; h->imu_buf_bytes = 0; h->imu_out = nullptr; h->imu_out_cap = 0;
     h->online_have_last = 0; h->online_slot = 0; h->prof_enabled = 0; h->prof_used = 0;

@@ -159,6 +159,7 @@ struct vlo_handle {
     // hold handles on several devices)
     size_t k1_smem_configured, k1c_smem_configured;
     int dev_sms, k5_occ_assoc, k5_occ_lin, k3_gn_configured, k3a_ctas;
+    int k0_sub, k1_sub;        // tuning (VLO_K0_SUB / VLO_K1_SUB): scans per sub-batch of K0 / K1; 0 = the whole batch in one pass
     LaserMapDev lm;
     // IMU staging (grown on demand)
     double *imu_buf; size_t imu_buf_bytes; vlo_preint *imu_out; int imu_out_cap;
