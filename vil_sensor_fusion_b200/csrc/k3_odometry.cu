@@ -360,33 +360,32 @@ __global__ void __launch_bounds__(256) k3_assoc_warp(OdomParams p, int n_pairs)
 
 // Association on the ring-segment box index: one WARP per feature point of the current sweep -- transformToStart, exact
 // nearest neighbour in the previous sweep's cloud (d2 < 25), ring-constrained partner search(es) with upstream's forward /
-// backward tie order.  CTA `chunk` of a pair owns a contiguous share of the pair's queries: its threads transform them once
-// into shared memory (one thread per point), then its warps take them one at a time.  From the second association round
-// on, the previous round's answers (same pair, pose a few Gauss-Newton steps older) seed the searches: they are candidates
-// like any other, and their distances prune nearly every box at once.
+// backward tie order.  From the second association round on, the previous round's answers (same pair, pose a few Gauss-Newton
+// steps older) seed the searches: they are candidates like any other, and their distances prune nearly every box at once.
 // Measured against round 1's voxel-hash kernels on the whole-bag workload (127 HDL-64 pairs, 5 rounds, profiles/r02*):
 // 4.9 ms vs 11.2 / 22.8 ms (1.0 / 0.7 m cells) -- the hash version fell back to walking cell shells whenever a partner was
 // more than one cell edge away -- with bit-identical results.
 #define K3A_THREADS 128
-#define K3A_MAXQ 256             // queries per ticket
-#ifndef K3A_MINB
-#define K3A_MINB 10           // 48 registers: 10 CTAs per SM (left to itself ptxas takes 128 registers and halves the occupancy)
+#ifndef K3A_WQ
+#define K3A_WQ 4                 // queries per ticket: a WARP draws (pair, 4 consecutive queries) tickets (3.35 ms per 127-pair step; 8: 3.46, 16: 3.80, 1: 3.57)
 #endif
+#ifndef K3A_MINB
+#define K3A_MINB 10          // 48 registers: 10 CTAs per SM (left to itself ptxas takes 128 registers and halves the occupancy)
+#endif
+// Persistent warps, no CTA-level step: a ticket is (pair, K3A_WQ queries); the warp's first lanes transform the ticket's queries
+// (transformToStart, one query per lane), then the warp answers them one after the other.  Measured on the 127-pair step: a
+// (share, pair) grid with the share's queries dealt to the CTA's warps in turn and a barrier per share took 4.49 ms at 128
+// queries per share, 3.71 at 64, 3.40 at 16 -- the barrier waited for the warp with the expensive queries; warp tickets remove it.
 __global__ void __launch_bounds__(K3A_THREADS, K3A_MINB) k3_assoc(OdomParams p, int n_pairs, int round, int shares_per_pair)
 {
-    __shared__ float4 s_q[K3A_MAXQ];
-    __shared__ int s_ticket;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = threadIdx.x & 31;
     int *tickets = p.pair_state + (size_t)p.max_pairs * 4;           // one work counter per association round (zeroed by k3_init_pairs)
-    // persistent CTAs draw (pair, share of K3A_MAXQ queries) tickets: every CTA slot of the device stays busy until the round's
-    // work is gone (a (share, pair) grid ran 1.6 waves: the second one left a third of the machine idle)
     while (true) {
-        __syncthreads();                                             // the previous share is done with s_q / s_ticket
-        if (tid == 0) s_ticket = atomicAdd(&tickets[round], 1);
-        __syncthreads();
-        const int ticket = s_ticket;
+        int ticket = 0;
+        if (lane == 0) ticket = atomicAdd(&tickets[round], 1);
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
         if (ticket >= n_pairs * shares_per_pair) break;
-        const int pair = ticket / shares_per_pair, base = (ticket - pair * shares_per_pair) * K3A_MAXQ;
+        const int pair = ticket / shares_per_pair, base = (ticket - pair * shares_per_pair) * K3A_WQ;
         if (p.pair_state[pair * 4 + 0]) continue;                    // converged
         const int last = p.pair_last[pair], cur = p.pair_cur[pair];
         const int n_sharp = p.counts[cur * 8 + 1], n_flat = p.counts[cur * 8 + 3];
@@ -394,20 +393,21 @@ __global__ void __launch_bounds__(K3A_THREADS, K3A_MINB) k3_assoc(OdomParams p, 
         if (!(n_lc > 10 && n_ls > 100)) continue;
         const int total = n_sharp + n_flat;
         if (base >= total) continue;
-        float T[6];
-        #pragma unroll
-        for (int a = 0; a < 6; a++) T[a] = p.pair_T[pair * 6 + a];
-        const SegCloud cc = seg_cloud_of(p, 0, last), cs = seg_cloud_of(p, 1, last);
-        const int nq = min(K3A_MAXQ, total - base);
-        for (int k = tid; k < nq; k += K3A_THREADS) {
-            const int wq = base + k;
-            s_q[k] = vlo_to_start(T, wq < n_sharp ? p.sharp_pts[(size_t)cur * p.cap_sharp + wq] : p.flat_pts[(size_t)cur * p.cap_flat + (wq - n_sharp)],
-                                  p.deskew, p.inv_period);
+        const int nq = min(K3A_WQ, total - base);
+        float4 myq = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < nq) {
+            float T[6];
+            #pragma unroll
+            for (int a = 0; a < 6; a++) T[a] = p.pair_T[pair * 6 + a];
+            const int wq = base + lane;
+            myq = vlo_to_start(T, wq < n_sharp ? p.sharp_pts[(size_t)cur * p.cap_sharp + wq] : p.flat_pts[(size_t)cur * p.cap_flat + (wq - n_sharp)],
+                               p.deskew, p.inv_period);
         }
-        __syncthreads();
-        for (int k = warp; k < nq; k += K3A_THREADS / 32) {
+        const SegCloud cc = seg_cloud_of(p, 0, last), cs = seg_cloud_of(p, 1, last);
+        for (int k = 0; k < nq; k++) {
             const int wq = base + k;
-            const float4 q = s_q[k];
+            float4 q;
+            q.x = __shfl_sync(0xffffffffu, myq.x, k); q.y = __shfl_sync(0xffffffffu, myq.y, k); q.z = __shfl_sync(0xffffffffu, myq.z, k);
             const bool sharp = wq < n_sharp;
             const SegCloud &c = sharp ? cc : cs;
             int *o = sharp ? p.cidx + ((size_t)pair * p.cap_sharp + wq) * 2 : p.sidx + ((size_t)pair * p.cap_flat + (wq - n_sharp)) * 3;
@@ -728,7 +728,7 @@ int vlo_launch_register_pairs(vlo_handle *h, int n_pairs, const float *d_seeds, 
     if (!h->grids_valid) { int rc = vlo_build_scan_grids(h, 0, h->sb.n_scans); if (rc) return rc; h->grids_valid = 1; }
     // association grid: every CTA owns a contiguous share of its pair's queries, one warp per query; a single pair (the
     // online tick) is spread over the whole machine, a batch gets as many CTAs per pair as keep every SM busy
-    const int shares = (h->cap_sharp + h->cap_flat + K3A_MAXQ - 1) / K3A_MAXQ;
+    const int shares = (h->cap_sharp + h->cap_flat + K3A_WQ - 1) / K3A_WQ;
     if (c.odom_max_iterations > 5 * 64) { h->err = "odomMaxIterations: at most 320"; return VLO_ERR_INVALID_ARG; }
     if (!h->k3a_ctas) {                                  // persistent grid: every CTA slot of the device (per handle = per device)
         int occ = 0, sms = 0;
@@ -736,7 +736,7 @@ int vlo_launch_register_pairs(vlo_handle *h, int n_pairs, const float *d_seeds, 
         VLO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device));
         h->k3a_ctas = std::max(1, occ * sms);
     }
-    const int ga = std::max(1, std::min(h->k3a_ctas, n_pairs * shares));
+    const int ga = std::max(1, std::min(h->k3a_ctas, (n_pairs * shares + K3A_THREADS / 32 - 1) / (K3A_THREADS / 32)));
 #if K3_ONLINE_GRID
     dim3 gw(std::max(1, std::min(((h->cap_sharp + h->cap_flat) * 32 + 255) / 256, (148 * 8 + n_pairs - 1) / n_pairs)), n_pairs);
 #endif

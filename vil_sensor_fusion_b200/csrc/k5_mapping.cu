@@ -344,7 +344,11 @@ __device__ __forceinline__ int k5_build_list(const MapParams &p, int it, int n, 
 }
 
 // association of every unconverged slot's feature points (exact 5-NN, indices to idx5)
+#ifdef K5A_MINB
+__global__ void __launch_bounds__(KNN_THREADS, K5A_MINB) k5_assoc(MapParams p, int it, int n)
+#else
 __global__ void __launch_bounds__(KNN_THREADS) k5_assoc(MapParams p, int it, int n)
+#endif
 {
     VLO_DYN_SMEM_INT(s_dyn);                       // [n] active slots, [n + 1] tile prefix
     __shared__ ListSmem L;

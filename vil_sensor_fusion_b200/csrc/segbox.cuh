@@ -92,17 +92,25 @@ struct SegFilter {
 
 struct SegBest { unsigned d, t; int idx; };      // lane-local best: d = float bits of d2 (or of dmax: none yet)
 
-__device__ __forceinline__ void seg_consider(const SegCloud &c, int idx, float qx, float qy, float qz, float dmax,
+// `meta`: the SEG_META of the arc that holds `idx`, or 0 (unknown).  An arc whose points all carry one scan id (min == max:
+// every arc of a sweep without negative relTime) is filtered on that id, before the point is loaded; otherwise on int(w).
+__device__ __forceinline__ void seg_consider(const SegCloud &c, int idx, int meta, float qx, float qy, float qz, float dmax,
                                              const SegFilter &flt, SegBest &best)
 {
     unsigned tie;
-    const float4 p = c.pts[idx];
-    if (flt((int)p.w, idx, tie)) {
-        const float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
-        const float d2 = (dx * dx + dy * dy) + dz * dz;
-        const unsigned db = __float_as_uint(d2);
-        if (d2 < dmax && (db < best.d || (db == best.d && tie < best.t))) { best.d = db; best.t = tie; best.idx = idx; }
+    float4 p;
+    const int emin = SEG_META_EMIN(meta);
+    if (meta != 0 && emin == SEG_META_EMAX(meta) && (unsigned)(emin + SEG_EBIAS - 1) < 1022u) {      // (not a clamped summary)
+        if (!flt(emin, idx, tie)) return;
+        p = c.pts[idx];
+    } else {
+        p = c.pts[idx];
+        if (!flt((int)p.w, idx, tie)) return;
     }
+    const float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
+    const float d2 = (dx * dx + dy * dy) + dz * dz;
+    const unsigned db = __float_as_uint(d2);
+    if (d2 < dmax && (db < best.d || (db == best.d && tie < best.t))) { best.d = db; best.t = tie; best.idx = idx; }
 }
 
 // the surviving arcs of `fmask` (bit k = the arc whose box lane k has just tested), SEG_GROUPS of them per pass: lane
@@ -119,7 +127,7 @@ __device__ __forceinline__ void seg_scan_mask(const SegCloud &c, unsigned fmask,
         for (int k = 0; k < SEG_GROUPS - 1; k++) if (k < g) m &= m - 1u;
         const int bit = m ? __ffs(m) - 1 : 0;
         const int s0 = __shfl_sync(0xffffffffu, s0_mine, bit), meta = __shfl_sync(0xffffffffu, meta_mine, bit);
-        if (m && l < (meta & 0xff)) seg_consider(c, s0 + l, qx, qy, qz, dmax, flt, best);
+        if (m && l < (meta & 0xff)) seg_consider(c, s0 + l, meta, qx, qy, qz, dmax, flt, best);
         #pragma unroll
         for (int k = 0; k < SEG_GROUPS; k++) fmask &= fmask - 1u;       // drop the SEG_GROUPS lowest set bits
     }
@@ -136,7 +144,7 @@ __device__ __forceinline__ int seg_search(const SegCloud &c, float qx, float qy,
 {
     const unsigned dmaxb = __float_as_uint(dmax);
     SegBest best; best.d = dmaxb; best.t = 0xFFFFFFFFu; best.idx = -1;
-    if (seed >= 0) seg_consider(c, seed, qx, qy, qz, dmax, flt, best);      // same value in every lane
+    if (seed >= 0) seg_consider(c, seed, 0, qx, qy, qz, dmax, flt, best);      // same value in every lane
     unsigned bound = best.d;                     // float bits of the best d2 any lane holds (dmax: none yet)
     if (flt.mode == 0) {
         if (best.idx < 0) {
@@ -237,8 +245,8 @@ __device__ __forceinline__ void seg_search_partners(const SegCloud &c, float qx,
     const float INF = __int_as_float(0x7f800000);
     SegBest b2, b3;
     b2.d = b3.d = dmaxb; b2.t = b3.t = 0xFFFFFFFFu; b2.idx = b3.idx = -1;
-    if (seed2 >= 0) seg_consider(c, seed2, qx, qy, qz, dmax, f2, b2);
-    if (seed3 >= 0) seg_consider(c, seed3, qx, qy, qz, dmax, f3, b3);
+    if (seed2 >= 0) seg_consider(c, seed2, 0, qx, qy, qz, dmax, f2, b2);
+    if (seed3 >= 0) seg_consider(c, seed3, 0, qx, qy, qz, dmax, f3, b3);
     int f0 = 0, f1 = 0;
     if (f2.hi - f2.lo > 1) { f0 = f2.f0; f1 = f2.f1; }
     const bool need2 = b2.idx < 0, need3 = b3.idx < 0;          // warp-uniform (the seeds are)
