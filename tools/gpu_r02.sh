@@ -20,15 +20,21 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --
 python tools/launch_shares.py $OUT/launches.csv | tee $OUT/launch_shares.txt
 echo "== ncu launch list (whole-bag pairs step)"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_pairs.csv \
-    python tools/pairs_profile.py > $OUT/pairs_under_ncu.log 2>&1
+    python tools/pairs_time.py > $OUT/pairs_under_ncu.log 2>&1
 python tools/launch_shares.py $OUT/launches_pairs.csv | tee $OUT/launch_shares_pairs.txt
 for K in $BK; do
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:^$K -s 2 -c 1 -f -o $OUT/full_$K \
-      python bench.py --steps 1 --warmup 3 --batch 128 --no-cpu-baseline --legs none > $OUT/ncu_$K.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -s 2 -c 1 -f -o $OUT/full_$K \
+      python bench.py --steps 1 --warmup 3 --batch 128 --no-cpu-baseline --no-latency --legs none > $OUT/ncu_$K.log 2>&1
   ls -la $OUT/full_$K.ncu-rep
 done
 for K in $PK; do
-  timeout 400 ncu --set full --clock-control none --import-source on -k regex:^$K -s 1 -c 1 -f -o $OUT/full_$K \
-      python tools/pairs_profile.py > $OUT/ncu_$K.log 2>&1
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:$K -s 1 -c 1 -f -o $OUT/full_$K \
+      python tools/pairs_time.py > $OUT/ncu_$K.log 2>&1
   ls -la $OUT/full_$K.ncu-rep
 done
+echo "== ncu: batched IMU preintegration (C4)"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k6_imu -s 1 -c 1 -f -o $OUT/full_k6_imu \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-latency --legs c4 > $OUT/ncu_k6_imu.log 2>&1
+ls -la $OUT/full_k6_imu.ncu-rep
+echo "== reference arm"
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; cut -c1-300 $OUT/bench_ref.json

@@ -80,44 +80,70 @@ __device__ __forceinline__ float seg_warp_max(float v) {
 // ring-major order except where relTime is negative (segbox.cuh), so the answer is nearly always the start of ring e + 3 / the
 // end of ring e - 3: rings whose min / max scan id (s_emin / s_emax, filled by the caller) cannot stop the loop are skipped
 // whole, the stopping ring is walked.  No assumption on the scan ids beyond that; CTA-wide, no barrier inside.
+// the two break positions for loops started at point j of ring slot `lo` whose scan id is e
+__device__ __forceinline__ void partner_breaks(const float4 *pts, const int *rs, int R, const int *s_emin, const int *s_emax,
+                                               int j_fwd, int j_bwd, int lo, int e, int &B, int &F)
+{
+    F = rs[R]; B = -1;
+    {
+        const int t = e + 3; int k = j_fwd + 1; bool found = false;
+        for (int r = lo; r < R && !found; r++) {
+            if (s_emax[r] >= t) {
+                const int end = rs[r + 1];
+                for (k = max(k, rs[r]); k < end; k++) if ((int)pts[k].w >= t) { F = k; found = true; break; }
+            }
+        }
+    }
+    {
+        const int t = e - 3; int k = j_bwd - 1; bool found = false;
+        for (int r = lo; r >= 0 && !found; r--) {
+            if (s_emin[r] <= t) {
+                const int beg = rs[r];
+                for (k = min(k, rs[r + 1] - 1); k >= beg; k--) if ((int)pts[k].w <= t) { B = k; found = true; break; }
+            }
+        }
+    }
+}
+// the arcs [f0, f1) of the box index that hold the points between the two break positions
+__device__ __forceinline__ int4 partner_range_record(const int *rs, int R, const int *seg_ring, int B, int F)
+{
+    int f0 = 0, f1 = 0;
+    if (seg_ring && F - B > 1) {
+        int a = 0, b = R;
+        while (b - a > 1) { const int mid = (a + b) >> 1; if (rs[mid] <= B + 1) a = mid; else b = mid; }
+        f0 = seg_ring[a] + ((B + 1 - rs[a]) >> SEG_SHIFT);
+        a = 0; b = R;
+        while (b - a > 1) { const int mid = (a + b) >> 1; if (rs[mid] <= F - 1) a = mid; else b = mid; }
+        f1 = seg_ring[a] + ((F - 1 - rs[a]) >> SEG_SHIFT) + 1;
+    }
+    return make_int4(B, F, f0, f1);
+}
+// A warp per ring.  All points of a ring whose scan ids agree (min == max: every ring of a sweep without negative relTime) share
+// one record -- no point of the ring itself can stop a loop started in it -- computed once; otherwise point by point.
 __device__ __forceinline__ void partner_ranges_cta(const float4 *pts, const int *rs, int R, int4 *out, const int *s_emin, const int *s_emax,
                                                    const int *seg_ring, int tid, int n_threads)
 {
-    const int n = rs[R];
-    for (int j = tid; j < n; j += n_threads) {
-        int lo = 0, hi = R;                      // ring slot of j
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (rs[mid] <= j) lo = mid; else hi = mid; }
-        const int e = (int)pts[j].w;
-        int F = n, B = -1;
-        {
-            const int t = e + 3; int k = j + 1; bool found = false;
-            for (int r = lo; r < R && !found; r++) {
-                if (s_emax[r] >= t) {
-                    const int end = rs[r + 1];
-                    for (k = max(k, rs[r]); k < end; k++) if ((int)pts[k].w >= t) { F = k; found = true; break; }
-                }
+    const int lane = tid & 31;
+    for (int r = tid >> 5; r < R; r += n_threads >> 5) {
+        const int j0 = rs[r], j1 = rs[r + 1];
+        if (j1 <= j0) continue;
+        if (s_emin[r] == s_emax[r]) {
+            int4 rec = make_int4(0, 0, 0, 0);
+            if (lane == 0) {
+                int B, F;
+                partner_breaks(pts, rs, R, s_emin, s_emax, j1 - 1, j0, r, s_emin[r], B, F);
+                rec = partner_range_record(rs, R, seg_ring, B, F);
+            }
+            rec.x = __shfl_sync(0xffffffffu, rec.x, 0); rec.y = __shfl_sync(0xffffffffu, rec.y, 0);
+            rec.z = __shfl_sync(0xffffffffu, rec.z, 0); rec.w = __shfl_sync(0xffffffffu, rec.w, 0);
+            for (int j = j0 + lane; j < j1; j += 32) out[j] = rec;
+        } else {
+            for (int j = j0 + lane; j < j1; j += 32) {
+                int B, F;
+                partner_breaks(pts, rs, R, s_emin, s_emax, j, j, r, (int)pts[j].w, B, F);
+                out[j] = partner_range_record(rs, R, seg_ring, B, F);
             }
         }
-        {
-            const int t = e - 3; int k = j - 1; bool found = false;
-            for (int r = lo; r >= 0 && !found; r--) {
-                if (s_emin[r] <= t) {
-                    const int beg = rs[r];
-                    for (k = min(k, rs[r + 1] - 1); k >= beg; k--) if ((int)pts[k].w <= t) { B = k; found = true; break; }
-                }
-            }
-        }
-        // the arcs [f0, f1) of the box index that hold the points between the two break positions
-        int f0 = 0, f1 = 0;
-        if (seg_ring && F - B > 1) {
-            int a = 0, b = R;
-            while (b - a > 1) { const int mid = (a + b) >> 1; if (rs[mid] <= B + 1) a = mid; else b = mid; }
-            f0 = seg_ring[a] + ((B + 1 - rs[a]) >> SEG_SHIFT);
-            a = 0; b = R;
-            while (b - a > 1) { const int mid = (a + b) >> 1; if (rs[mid] <= F - 1) a = mid; else b = mid; }
-            f1 = seg_ring[a] + ((F - 1 - rs[a]) >> SEG_SHIFT) + 1;
-        }
-        out[j] = make_int4(B, F, f0, f1);
     }
 }
 
