@@ -134,6 +134,9 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+RAW_BYTES = 12           # bytes per raw point of the headline workload (set from --point-floats)
+
+
 def algorithmic_bytes(stage: str, counts, n_map_pts, iters_done, q_stack=None):
     """ALGORITHMIC bytes one launch of `stage` moves for the batch (SURVEY.md 8d formulas).
     q_stack = total size of the down-sampled corner + surface stacks (the scan-to-map queries)."""
@@ -142,7 +145,7 @@ def algorithmic_bytes(stage: str, counts, n_map_pts, iters_done, q_stack=None):
     q_in = sum(c["n_less_sharp"] + c["n_less_flat"] for c in counts)
     q = q_in if q_stack is None else q_stack
     if stage == "k0_organise":
-        return nv * (16 + 16)                                # raw xyz(i) in, ring-major float4 out
+        return nv * (RAW_BYTES + 16)                         # raw point in (12 B xyz / 16 B xyzi), ring-major float4 out
     if stage == "k1_extract":
         return nv * 21 + 4 * nfeat                           # 16 in + 4 curvature + 1 label, + index lists
     if stage == "k1b_compact":
@@ -484,10 +487,15 @@ def run_gpu(args):
     sizes = np.array([raws_pool[k % pool_n].shape[0] for k in range(n_buf)], np.int64)
     offs_all = np.zeros(n_buf + 1, np.int64)
     offs_all[1:] = np.cumsum(sizes)
-    host = torch.empty((int(offs_all[-1]), 4), dtype=torch.float32).pin_memory()
+    # the PointCloud2 payload as the reference's /lidar topic carries it: CARLA publishes x, y, z float32 only (point_step 12;
+    # carla_tools/src/carla_to_ros_transforms.py:69-70 reshapes the data to [-1, 3]); --point-floats 4 gives velodyne-style xyzi
+    PF = args.point_floats
+    global RAW_BYTES
+    RAW_BYTES = 4 * PF
+    host = torch.empty((int(offs_all[-1]), PF), dtype=torch.float32).pin_memory()
     hv = host.numpy()
     for k in range(n_buf):
-        hv[offs_all[k]:offs_all[k + 1]] = raws_pool[k % pool_n]
+        hv[offs_all[k]:offs_all[k + 1]] = raws_pool[k % pool_n][:, :PF]
     dev = host.to("cuda", non_blocking=False)
     seeds_all = np.stack([seeds_pool[k % pool_n] for k in range(n_buf)])
     scans_idx = np.arange(B, dtype=np.int32)
@@ -497,7 +505,7 @@ def run_gpu(args):
         return w0, (offs_all[w0:w0 + B + 1] - offs_all[w0]).astype(np.int32), seeds_all[w0:w0 + B]
 
     n_pts = int(np.mean([offs_all[w + B] - offs_all[w] for w in range(pool_n)]))       # points per step (mean over windows)
-    h2d_bytes = n_pts * 16
+    h2d_bytes = n_pts * 4 * PF
     d2h_bytes = B * api.RESULT_DTYPE.itemsize
 
     cfg = api.default_config("HDL-64E", deskew=0, max_scans=B, max_points=131072,
@@ -510,8 +518,8 @@ def run_gpu(args):
 
     def step(on_device: bool, k: int):
         w0, offs, seeds = window(k)
-        base = (dev if on_device else host).data_ptr() + int(offs_all[w0]) * 16
-        h.upload_raw(base, offs, 4, on_device)
+        base = (dev if on_device else host).data_ptr() + int(offs_all[w0]) * 4 * PF
+        h.upload_raw(base, offs, PF, on_device)
         h.organise()
         h.extract()
         return h.register_map(scans_idx, seeds)
@@ -576,13 +584,13 @@ def run_gpu(args):
         out = []
         for k in range(n_steps):
             w0, offs, seeds = window(k)
-            base = host.data_ptr() + int(offs_all[w0]) * 16
+            base = host.data_ptr() + int(offs_all[w0]) * 4 * PF
             out.append((base, offs[:HBn + 1], seeds[:HBn]))
-            out.append((base + int(offs[HBn]) * 16, offs[HBn:] - offs[HBn], seeds[HBn:]))
+            out.append((base + int(offs[HBn]) * 4 * PF, offs[HBn:] - offs[HBn], seeds[HBn:]))
         return out
 
     def e2e_pass(n_steps):
-        r = h.bag_register_map(e2e_batches(n_steps), stride=4)
+        r = h.bag_register_map(e2e_batches(n_steps), stride=PF)
         if world > 1:
             bag.gather_results(r, counts=[B * n_steps] * world)      # the job's single exchange step, inside the timed region
         return r
@@ -750,6 +758,7 @@ def run_gpu(args):
             "config": {"workload": "hdl64_scan_to_map_1M: HDL-64-shaped scans (64x1800) -> organise + feature extraction + "
                                    "scan-to-map registration (<=10 GN iterations, 5-NN on a 1M-point voxel-hash map) + eigen-degeneracy "
                                    "+ D-opt gate", "scans_per_step_per_gpu": B, "points_per_scan": int(n_pts // B),
+                       "point_step": 4 * PF, "payload": "x y z float32 (CARLA /lidar clouds, carla_to_ros_transforms.py:69-70)" if PF == 3 else "x y z intensity float32",
                        "map_points": int(n_map_pts), "parallelism": "frame-range dp%d" % world,
                        "l2": "inputs %.0f MB per step > 126 MB L2" % (h2d_bytes / 1e6), "mean_gn_iterations": round(mean_iters, 2),
                        "gn_iterations_hist": np.bincount(res_all["iterations"], minlength=cfg.map_max_iterations + 1).tolist(),
@@ -763,7 +772,7 @@ def run_gpu(args):
                     "pcie_h2d_gbs_all_ranks_concurrently": None if pcie_gbs is None else round(pcie_gbs, 2),
                     "h2d_gbs_achieved": round(h2d_bytes / (e2e_ms / args.steps * 1e-3) / 1e9, 2),
                     "frac_of_pcie": None if not pcie_gbs else round(h2d_bytes / (e2e_ms / args.steps * 1e-3) / 1e9 / pcie_gbs, 4),
-                    "bound": "PCIe host->device copy of the 16 B/point PointCloud2 payload (kernels overlap it); the ceiling is measured with "
+                    "bound": "PCIe host->device copy of the %d B/point PointCloud2 payload (kernels overlap it); the ceiling is measured with " % (4 * PF) +
                              "every rank copying at the same time"},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
@@ -874,6 +883,9 @@ def main():
     ap.add_argument("--bag-seconds", type=float, default=1.0, help="minimum length of the whole-bag timed region (the job is repeated)")
     ap.add_argument("--imu-factors", type=int, default=10000)
     ap.add_argument("--vlp16-scans", type=int, default=600)
+    ap.add_argument("--point-floats", type=int, default=3, choices=[3, 4],
+                    help="float32 fields per raw point of the headline workload: 3 = x y z (point_step 12, the CARLA clouds the reference's "
+                         "/lidar topic carries), 4 = x y z intensity (point_step 16, velodyne-style; round 1's payload)")
     ap.add_argument("--r01-workload", action="store_true", help="round 1's pool (8 scans, one fixed seed offset) instead of SURVEY C2's 200 perturbed poses")
     args = ap.parse_args()
     if args.legs is None:
