@@ -558,6 +558,8 @@ def run_gpu(args):
     all_res = []
     for k in range(args.steps):
         all_res.append(step(True, k))
+    ev_mid = torch.cuda.Event(enable_timing=True)
+    ev_mid.record(stream)
     if world > 1:
         # the ONE exchange step of the whole job: every rank's result records, gathered once over NVLink (one fixed-size
         # all_gather_into_tensor of K * B 480-byte records per rank); nothing collective happens per scan or per batch
@@ -566,6 +568,7 @@ def run_gpu(args):
     ev1.record(stream)
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
+    steps_only_ms = ev0.elapsed_time(ev_mid)
     launches = h.launch_count() - launches0
     stages = h.stage_times()
     h.set_profiling(False)
@@ -765,6 +768,7 @@ def run_gpu(args):
                        "pool": ("%d distinct scans at poses perturbed by N(0, 0.1 m) / N(0, 0.5 deg), seeds 1..%d; a step takes %d consecutive pool "
                                 "entries from a start that moves by 61 per step" % (pool_n, pool_n, B)) if not args.r01_workload else "round-1 pool: 8 scans, one fixed offset",
                        "exchange": "one all_gather_into_tensor of the result records per job" if world > 1 else "none",
+                       "timed_region_ms": {"steps": round(steps_only_ms, 3), "exchange_and_wait_for_slowest_rank": round(dev_ms - steps_only_ms, 3)},
                        "numa_node": numa},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                     "ms_per_step": round(e2e_ms / args.steps, 4), "wall_ms": round(e2e_wall_ms, 3), "device_ms": round(e2e_dev_ms, 3),
