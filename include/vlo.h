@@ -248,7 +248,7 @@ int vlo_online_set_map_pose(vlo_handle *h, const float *pose6);
  *   vlo_bag_register_pairs: scan-to-scan of the consecutive pairs (i, i+1) inside each batch from seeds[(n_scans-1)*6]
  *                           (NULL = zero seed); out = sum(n_scans - 1) records; overlap batches by one frame to chain */
 typedef struct vlo_bag_batch {
-    const float *raw;          /* concatenated clouds of this batch (host) */
+    const float *raw;          /* concatenated clouds of this batch: host memory (pinned, for the copy to overlap) or device memory */
     const int   *offsets;      /* n_scans + 1 point offsets into raw */
     int          n_scans;
     const float *seeds;

@@ -74,6 +74,22 @@ def test_bag_map_equals_resident_map():
             batches.append((raw, offs, seeds[lo:hi]))
         got = h.bag_register_map(batches)
         _same(got, ref)
+        # a second call on the same handle (staging kept between calls), clouds of 3 floats per point (CARLA's /lidar layout)
+        got3 = h.bag_register_map([(np.ascontiguousarray(r[:, :3]), o, s_) for r, o, s_ in batches], stride=3)
+        _same(got3, ref)
+        # clouds already resident in device memory: the same call, the same records
+        try:
+            import torch
+            on_gpu = torch.cuda.is_available()
+        except ImportError:
+            on_gpu = False
+        if on_gpu:
+            keep = [torch.from_numpy(np.ascontiguousarray(r)).cuda() for r, _, _ in batches]
+            got_d = h.bag_register_map([(int(t.data_ptr()), o, s_) for t, (_, o, s_) in zip(keep, batches)])
+        else:       # the CPU-emulated library: "device" memory is host memory
+            keep = [np.ascontiguousarray(r, np.float32) for r, _, _ in batches]
+            got_d = h.bag_register_map([(int(a.ctypes.data), o, s_) for a, (_, o, s_) in zip(keep, batches)])
+        _same(got_d, ref)
 
 
 def test_bag_capacity_errors():

@@ -105,7 +105,7 @@ extern "C" int vlo_create(const vlo_config *cfg, vlo_handle **out)
     h->status_word = nullptr; h->pair_T = h->pair_seed = nullptr; h->pair_last = h->pair_cur = h->pair_state = nullptr;
     h->pair_cidx = h->pair_sidx = h->pair_trace = nullptr; h->pair_result = nullptr;
     h->map_partials = nullptr; h->map_idx5 = nullptr; h->map_T = h->map_seed = nullptr; h->map_state = h->map_ncorr = h->map_scans = h->map_done = nullptr;
-    h->k1_smem_configured = h->k1c_smem_configured = 0; h->dev_sms = h->k5_occ_assoc = h->k5_occ_lin = h->k3_gn_configured = h->k3a_ctas = 0;
+    h->k1_smem_configured = h->k1c_smem_configured = 0; h->dev_sms = h->k5_occ_assoc = h->k5_occ_lin = h->k3_gn_configured = h->k3a_ctas = 0; h->bag_ctx = nullptr;
     { const char *e0 = getenv("VLO_K0_SUB"), *e1 = getenv("VLO_K1_SUB"); h->k0_sub = e0 ? atoi(e0) : 0; h->k1_sub = e1 ? atoi(e1) : 0; }
     h->map_result = nullptr; h->coop_resident = 0; h->map_qmax = 0; h->last_n_map = 0; h->last_n_pairs = 0;
     h->imu_buf = nullptr; h->imu_buf_bytes = 0; h->imu_out = nullptr; h->imu_out_cap = 0;
@@ -190,6 +190,7 @@ extern "C" void vlo_destroy(vlo_handle *h)
                      h->map_scans, h->map_result, h->imu_buf, h->imu_out };
     for (void *p : ptrs) if (p) cudaFree(p);
     vlo_lm_free(h);
+    vlo_bag_free(h);
     for (int w = 0; w < 2; w++) { cudaFree(h->segs.fbox[w]); cudaFree(h->segs.mbox[w]); cudaFree(h->segs.cbox[w]); cudaFree(h->segs.perm[w]); cudaFree(h->segs.seg_ring[w]); cudaFree(h->segs.nseg[w]); cudaFree(h->segs.prange[w]); }
     free_gridset(h->gs_corner); free_gridset(h->gs_surf); free_gridset(h->gs_map[0]); free_gridset(h->gs_map[1]);
     if (h->pinned) cudaFreeHost(h->pinned);

@@ -9,14 +9,15 @@
 
 namespace {
 
+// Kept in the handle between calls: a pinned allocation and a stream creation cost more than a millisecond, a streaming call
+// over ten 128-scan batches lasts 35.
 struct BagCtx {
     cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
     cudaEvent_t copied[2] = { nullptr, nullptr }, raw_free[2] = { nullptr, nullptr };
-    char *pinned = nullptr;
+    char *pinned = nullptr; size_t pinned_bytes = 0;
     char *d_par = nullptr;          // per half: slot indices (2 arrays) + seeds, uploaded on the COPY stream
     ~BagCtx()
     {
-        // error paths leave work in flight: drain both streams before the staging they use goes away
         if (copy_stream) cudaStreamSynchronize(copy_stream);
         if (compute_stream) cudaStreamSynchronize(compute_stream);
         for (int i = 0; i < 2; i++) { if (copied[i]) cudaEventDestroy(copied[i]); if (raw_free[i]) cudaEventDestroy(raw_free[i]); }
@@ -24,6 +25,11 @@ struct BagCtx {
         if (pinned) cudaFreeHost(pinned);
         if (d_par) cudaFree(d_par);
     }
+};
+// error paths leave work in flight: drain both streams before the caller touches the staging again
+struct BagDrain {
+    BagCtx &c;
+    ~BagDrain() { if (c.copy_stream) cudaStreamSynchronize(c.copy_stream); if (c.compute_stream) cudaStreamSynchronize(c.compute_stream); }
 };
 
 // mode 0: scan-to-map of every scan; mode 1: scan-to-scan of the consecutive pairs inside each batch
@@ -50,20 +56,30 @@ int bag_run(vlo_handle *h, const vlo_bag_batch *batches, int n_batches, int stri
     }
     cudaSetDevice(h->cfg.device);
     ScanBatchDev &sb = h->sb;
-    BagCtx ctx;
+    if (!h->bag_ctx) h->bag_ctx = new BagCtx();
+    BagCtx &ctx = *(BagCtx *)h->bag_ctx;
+    BagDrain drain{ ctx };
     ctx.compute_stream = h->stream;
-    VLO_CUDA(cudaStreamCreateWithFlags(&ctx.copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) {
-        VLO_CUDA(cudaEventCreateWithFlags(&ctx.copied[i], cudaEventDisableTiming));
-        VLO_CUDA(cudaEventCreateWithFlags(&ctx.raw_free[i], cudaEventDisableTiming));
+    const size_t par_bytes = sizeof(int) * 2 * (size_t)HB + sizeof(float) * 6 * (size_t)HB;
+    if (!ctx.copy_stream) {
+        VLO_CUDA(cudaStreamCreateWithFlags(&ctx.copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            VLO_CUDA(cudaEventCreateWithFlags(&ctx.copied[i], cudaEventDisableTiming));
+            VLO_CUDA(cudaEventCreateWithFlags(&ctx.raw_free[i], cudaEventDisableTiming));
+        }
+        VLO_CUDA(cudaMalloc((void **)&ctx.d_par, par_bytes * 2));
     }
     // pinned staging for the whole bag: per batch {offset pairs, slot indices (2 arrays), seeds} + the result records
     const size_t per_batch = sizeof(int) * 4 * (size_t)HB + sizeof(float) * 6 * (size_t)HB;
     const size_t res_off = per_batch * (size_t)n_batches;
-    VLO_CUDA(cudaMallocHost((void **)&ctx.pinned, res_off + sizeof(vlo_result) * std::max<size_t>(n_out, 1)));
+    const size_t pin_need = res_off + sizeof(vlo_result) * std::max<size_t>(n_out, 1);
+    if (pin_need > ctx.pinned_bytes) {
+        if (ctx.pinned) cudaFreeHost(ctx.pinned);
+        ctx.pinned = nullptr; ctx.pinned_bytes = 0;
+        VLO_CUDA(cudaMallocHost((void **)&ctx.pinned, pin_need + pin_need / 4));
+        ctx.pinned_bytes = pin_need + pin_need / 4;
+    }
     vlo_result *pres = (vlo_result *)(ctx.pinned + res_off);
-    const size_t par_bytes = sizeof(int) * 2 * (size_t)HB + sizeof(float) * 6 * (size_t)HB;
-    VLO_CUDA(cudaMalloc((void **)&ctx.d_par, par_bytes * 2));
 
     VLO_CUDA(cudaStreamSynchronize(h->stream));
     sb.raw = sb.raw_owned; sb.stride = stride; sb.n_scans = 2 * HB;
@@ -92,8 +108,9 @@ int bag_run(vlo_handle *h, const vlo_bag_batch *batches, int n_batches, int stri
         if (b >= 2) VLO_CUDA(cudaStreamWaitEvent(ctx.copy_stream, ctx.raw_free[half], 0));
         VLO_CUDA(cudaMemcpyAsync(dpar, pidx, par_bytes, cudaMemcpyHostToDevice, ctx.copy_stream));
         VLO_CUDA(cudaMemcpyAsync(sb.raw_offset + 2 * first, poff, sizeof(int) * 2 * (size_t)n, cudaMemcpyHostToDevice, ctx.copy_stream));
+        // (cudaMemcpyDefault: the clouds may live in host memory -- pinned for the copy to overlap -- or already on the device)
         VLO_CUDA(cudaMemcpyAsync(sb.raw_owned + base_pt * stride, bb.raw + (size_t)bb.offsets[0] * stride, sizeof(float) * total * stride,
-                                 cudaMemcpyHostToDevice, ctx.copy_stream));
+                                 cudaMemcpyDefault, ctx.copy_stream));
         VLO_CUDA(cudaEventRecord(ctx.copied[half], ctx.copy_stream));
         // ---- compute stream
         VLO_CUDA(cudaStreamWaitEvent(h->stream, ctx.copied[half], 0));
@@ -130,6 +147,11 @@ int bag_run(vlo_handle *h, const vlo_bag_batch *batches, int n_batches, int stri
 }
 
 }  // namespace
+
+void vlo_bag_free(vlo_handle *h)
+{
+    if (h && h->bag_ctx) { delete (BagCtx *)h->bag_ctx; h->bag_ctx = nullptr; }
+}
 
 extern "C" int vlo_bag_register_map(vlo_handle *h, const vlo_bag_batch *batches, int n_batches, int stride_floats, vlo_result *out)
 {

@@ -168,6 +168,7 @@ struct vlo_handle {
     // pinned staging
     void *pinned; size_t pinned_bytes;
     void *upload_pinned; cudaEvent_t upload_ev[2]; int upload_parity, upload_used[2];   // vlo_scans_upload's offsets staging
+    void *bag_ctx;             // whole-bag streaming: copy stream, events, staging (vlo_bag.cu), created on first use
     // online state
     int online_have_last; float online_T[6]; float online_sum[6]; float online_map_bef[6], online_map_aft[6];
     int online_slot; long long online_ticks;
@@ -295,5 +296,6 @@ int vlo_launch_register_map(vlo_handle *h, const int *d_scans, int n, const floa
 int vlo_launch_stack_ds(vlo_handle *h, int first, int count);
 int vlo_lm_alloc(vlo_handle *h);
 void vlo_lm_free(vlo_handle *h);
+void vlo_bag_free(vlo_handle *h);
 int vlo_launch_imu(vlo_handle *h, const double *d_t, const double *d_acc, const double *d_gyro, int n_samples,
                    const double *d_t0, const double *d_t1, const double *d_bias, int n_factors, vlo_preint *d_out);
