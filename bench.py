@@ -542,6 +542,7 @@ def run_gpu(args):
 
     for k in range(max(args.warmup - 1, 0)):
         step(True, k + 1)
+    res_pin = torch.empty(args.steps * B * api.RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
     all_counts = [B * args.steps] * world
     if world > 1:
         # warm-up of the exchange step with the timed region's shapes (NCCL connects lazily on the first collective)
@@ -558,9 +559,17 @@ def run_gpu(args):
     # one call sequence per step over the whole 128-scan batch.  (The streaming call over device-resident clouds -- no host round
     # trip between steps -- was measured and is slower: it works on 64-scan half-batches, on which the persistent per-iteration
     # kernels of the scan-to-map registration lose 1.75x: 3.55 ms against 2.72 ms per step.)
-    all_res = []
+    # every step is only ENQUEUED (vlo_register_map_enqueue: the step's result records land in pinned memory when the stream gets
+    # there); the host synchronises once after the last step, so no step waits for the host to turn around
     for k in range(args.steps):
-        all_res.append(step(True, k))
+        w0, offs, seeds = window(k)
+        h.upload_raw(dev.data_ptr() + int(offs_all[w0]) * 4 * PF, offs, PF, True)
+        h.organise()
+        h.extract()
+        h.register_map_enqueue(scans_idx, seeds, res_pin.data_ptr() + k * B * api.RESULT_DTYPE.itemsize)
+    h.synchronize()
+    res_all_steps = h.results_finish(np.frombuffer(res_pin.numpy(), api.RESULT_DTYPE).copy())
+    all_res = [res_all_steps[k * B:(k + 1) * B] for k in range(args.steps)]
     ev_mid = torch.cuda.Event(enable_timing=True)
     ev_mid.record(stream)
     if world > 1:

@@ -198,6 +198,12 @@ int vlo_pair_get_correspondences(vlo_handle *h, int pair, int round, int *corner
 int vlo_map_build(vlo_handle *h, const float *corner_xyzi, int n_corner, const float *surf_xyzi, int n_surf, int on_device);
 /* registers the down-sampled corner (less sharp) / surface (less flat) stacks of resident scans against the map */
 int vlo_register_map(vlo_handle *h, const int *scans, int n, const float *seeds /* n*6 transformTobeMapped */, vlo_result *out);
+/* the same without the host synchronisation: everything, including the copy of the n result records into `out`, is only
+ * ENQUEUED on the handle's stream (`out`: pinned host memory that stays valid until vlo_synchronize; the next batch can be
+ * uploaded and registered meanwhile).  After vlo_synchronize: vlo_results_finish(h, out, n) completes the records on the host
+ * (the float64 covariance) and returns the soft status vlo_register_map would have returned. */
+int vlo_register_map_enqueue(vlo_handle *h, const int *scans, int n, const float *seeds, vlo_result *out_pinned);
+int vlo_results_finish(vlo_handle *h, vlo_result *out, int n);
 int vlo_map_get_correspondences(vlo_handle *h, int slot, int *corner_idx5, int *surf_idx5);
 /* exact k-NN service on the map grids (k = 1 or 5, neighbours with d2 < max_d2): which = 0 corner, 1 surf;
  * queries host xyzi; missing neighbours are idx -1 / d2 +inf */

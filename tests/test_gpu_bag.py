@@ -126,3 +126,33 @@ def test_reprocess_pairs_from_a_ros_bag(tmp_path):
     np.testing.assert_allclose(stamps, 100.0 + 0.1 * np.arange(5), atol=1e-9)
     np.testing.assert_array_equal(res_bag["transform"].view(np.uint32), res_arr["transform"].view(np.uint32))
     np.testing.assert_array_equal(res_bag["hessian"].view(np.uint32), res_arr["hessian"].view(np.uint32))
+
+
+def test_register_map_enqueue_equals_register_map():
+    """vlo_register_map_enqueue + vlo_synchronize + vlo_results_finish (no host synchronisation between batches) gives the records
+    vlo_register_map gives, also when a second batch is enqueued before the first one's records are read"""
+    from vil_sensor_fusion_b200 import api, synth
+    scene = synth.scene_room(0)
+    traj = synth.Trajectory()
+    cm, sm = synth.sample_map_points(scene, 150000, seed=1)
+    raws, seeds = [], []
+    for k in range(4):
+        t = 0.1 * k
+        raws.append(synth.make_scan(scene, "VLP-16", t0=t, traj=traj, rolling=False, n_az=900))
+        gt = synth.loam_map_pose(traj.rotation(t), traj.position(t)).astype(np.float32)
+        seeds.append(gt + np.array([0.004, -0.006, 0.003, 0.06, -0.04, 0.08], np.float32))
+    seeds = np.stack(seeds)
+    cfg = api.default_config("VLP-16", deskew=0, max_scans=2, max_points=16384, max_map_points=int(max(len(cm), len(sm))))
+    with api.Handle(cfg) as h:
+        h.map_build(cm, sm)
+        ref = []
+        for lo in (0, 2):
+            h.upload(raws[lo:lo + 2]); h.organise(); h.extract()
+            ref.append(h.register_map(np.arange(2), seeds[lo:lo + 2]))
+        ref = np.concatenate(ref)
+        out = np.zeros(4, api.RESULT_DTYPE)
+        for i, lo in enumerate((0, 2)):
+            h.upload(raws[lo:lo + 2]); h.organise(); h.extract()
+            h.register_map_enqueue(np.arange(2), seeds[lo:lo + 2], out.ctypes.data + i * 2 * api.RESULT_DTYPE.itemsize)
+        h.synchronize()
+        _same(h.results_finish(out), ref)

@@ -214,6 +214,21 @@ class Handle:
         self._check(self.lib.vlo_register_map(self._h, _ptr(scans), len(scans), _ptr(seeds), _ptr(out)))
         return out
 
+    def register_map_enqueue(self, scans, seeds, out_address: int) -> None:
+        """vlo_register_map without the host synchronisation: the result records land at `out_address` (pinned host memory,
+        len(scans) * RESULT_DTYPE.itemsize bytes) once the handle's stream reaches them; see results_finish."""
+        scans = np.ascontiguousarray(scans, np.int32)
+        seeds = np.ascontiguousarray(seeds, np.float32).reshape(len(scans), 6)
+        self._check(self.lib.vlo_register_map_enqueue(self._h, _ptr(scans), len(scans), _ptr(seeds), C.c_void_p(out_address)))
+
+    def results_finish(self, records: np.ndarray) -> np.ndarray:
+        """after synchronize(): completes records written by register_map_enqueue (in place) and returns them"""
+        assert records.dtype == RESULT_DTYPE and records.flags["C_CONTIGUOUS"]
+        rc = self.lib.vlo_results_finish(self._h, _ptr(records), len(records))
+        if rc < 0:
+            self._check(rc)
+        return records
+
     def map_correspondences(self, slot: int, n_corner: int, n_surf: int):
         ci = np.zeros((max(n_corner, 1), 5), np.int32)
         si = np.zeros((max(n_surf, 1), 5), np.int32)

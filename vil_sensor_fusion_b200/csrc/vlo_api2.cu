@@ -125,6 +125,33 @@ extern "C" int vlo_register_map(vlo_handle *h, const int *scans, int n, const fl
     return soft;
 }
 
+extern "C" int vlo_register_map_enqueue(vlo_handle *h, const int *scans, int n, const float *seeds, vlo_result *out_pinned)
+{
+    if (!h || !scans || !seeds || !out_pinned || n < 1) return VLO_ERR_INVALID_ARG;
+    if (h->cfg.max_map_points <= 0) { h->err = "handle created with max_map_points = 0"; return VLO_ERR_STATE; }
+    if (n > h->cfg.max_scans) { h->err = "n exceeds max_scans"; return VLO_ERR_CAPACITY; }
+    for (int k = 0; k < n; k++) if (scans[k] < 0 || scans[k] >= h->sb.n_scans) { h->err = "scan index outside the resident batch"; return VLO_ERR_INVALID_ARG; }
+    cudaSetDevice(h->cfg.device);
+    // the slot indices and seeds are small: a copy from pageable memory is staged by the runtime before the call returns, so
+    // the caller's arrays may be reused at once and no staging of ours is in flight between calls
+    VLO_CUDA(cudaMemcpyAsync(h->map_scans, scans, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    VLO_CUDA(cudaMemcpyAsync(h->map_seed, seeds, sizeof(float) * 6 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    int rc;
+    if (!h->lm.ds_valid) { rc = vlo_launch_stack_ds(h, 0, h->sb.n_scans); if (rc) return rc; h->lm.ds_valid = 1; }
+    rc = vlo_launch_register_map(h, h->map_scans, n, h->map_seed); if (rc) return rc;
+    VLO_CUDA(cudaMemcpyAsync(out_pinned, h->map_result, sizeof(vlo_result) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    h->last_n_map = n;
+    return VLO_OK;
+}
+
+extern "C" int vlo_results_finish(vlo_handle *h, vlo_result *out, int n)
+{
+    if (!h || !out || n < 0) return VLO_ERR_INVALID_ARG;
+    int soft = VLO_OK;
+    for (int k = 0; k < n; k++) { vlo_finish_cov_host(&out[k], &h->cfg); if (out[k].status == VLO_SOFT_TOO_FEW_CORR) soft = VLO_SOFT_TOO_FEW_CORR; }
+    return soft;
+}
+
 extern "C" int vlo_map_get_correspondences(vlo_handle *h, int slot, int *corner_idx5, int *surf_idx5)
 {
     // neighbour indices of the LAST executed association of slot `slot`
