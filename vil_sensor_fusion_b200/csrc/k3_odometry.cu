@@ -396,7 +396,8 @@ __global__ void __launch_bounds__(256) k3_assoc_warp(OdomParams p, int n_pairs)
 #define K3A_WQ 4                 // queries per ticket: a WARP draws (pair, 4 consecutive queries) tickets (3.35 ms per 127-pair step; 8: 3.46, 16: 3.80, 1: 3.57)
 #endif
 #ifndef K3A_MINB
-#define K3A_MINB 10          // 48 registers: 10 CTAs per SM (left to itself ptxas takes 128 registers and halves the occupancy)
+#define K3A_MINB 16          // 32 registers (148 B of spills): all 64 warp slots of an SM.  255-pair step: 6.89 ms at 8 CTAs per SM (64 registers),
+                             // 6.51 at 10, 6.19 at 12 (40 registers, no spill), 6.06 at 16; left to itself ptxas takes 128 registers: 1.6x slower
 #endif
 // Persistent warps, no CTA-level step: a ticket is (pair, K3A_WQ queries); the warp's first lanes transform the ticket's queries
 // (transformToStart, one query per lane), then the warp answers them one after the other.  Measured on the 127-pair step: a
@@ -493,7 +494,10 @@ __device__ __forceinline__ void r1_chunk(float *terms, float *l1buf, float *l2ac
     }
 }
 
-__global__ void __launch_bounds__(GN_THREADS) k3_gn(OdomParams p, int iter_base, int n_iters)
+#ifndef GN_MINB
+#define GN_MINB 2          // 64 registers, two CTAs per SM: the 255 pairs of a 256-frame batch run in one wave (k3_gn 1.17 -> 0.82 ms; 127 pairs: 0.60 -> 0.63)
+#endif
+__global__ void __launch_bounds__(GN_THREADS, GN_MINB) k3_gn(OdomParams p, int iter_base, int n_iters)
 {
 #ifdef VLO_HOST_EMULATION
     static float terms[GN_THREADS * TSTRIDE];
