@@ -38,3 +38,9 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:k6_i
 ls -la $OUT/full_k6_imu.ncu-rep
 echo "== reference arm"
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; cut -c1-300 $OUT/bench_ref.json
+echo "== ncu: map maintenance kernels of the online tick (maintained map)"
+for K in k7_ins_probe k7_ins_assign k7_ins_accum k7_ins_final; do
+  MAINTAINED=1 timeout 300 ncu --set full --clock-control none --import-source on -k regex:$K -s 30 -c 1 -f -o $OUT/full_$K \
+      python tools/online_time.py > $OUT/ncu_$K.log 2>&1
+  ls -la $OUT/full_$K.ncu-rep
+done
