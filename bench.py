@@ -578,6 +578,7 @@ def run_gpu(args):
         gathered = bag.gather_results(np.concatenate(all_res), counts=all_counts)
         assert len(gathered) == world * args.steps * B
     ev1.record(stream)
+    gather_split = dict(bag.LAST_GATHER_MS) if world > 1 else {}
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
     steps_only_ms = ev0.elapsed_time(ev_mid)
@@ -653,6 +654,11 @@ def run_gpu(args):
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         dev_ms, e2e_ms = float(tmax[0]), float(tmax[1])
         launches = int(tsum[2])
+        ts = torch.tensor([steps_only_ms, -steps_only_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        steps_ms_ranks = (float(-ts[1]), float(ts[0]))          # fastest and slowest rank's own steps (before the exchange)
+    else:
+        steps_ms_ranks = (steps_only_ms, steps_only_ms)
     ms_per_step = dev_ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
     e2e_value = world * B / (e2e_ms / args.steps * 1e-3)
@@ -783,7 +789,9 @@ def run_gpu(args):
                        "pool": ("%d distinct scans at poses perturbed by N(0, 0.1 m) / N(0, 0.5 deg), seeds 1..%d; a step takes %d consecutive pool "
                                 "entries from a start that moves by 61 per step" % (pool_n, pool_n, B)) if not args.r01_workload else "round-1 pool: 8 scans, one fixed offset",
                        "exchange": "one all_gather_into_tensor of the result records per job" if world > 1 else "none",
-                       "timed_region_ms": {"steps": round(steps_only_ms, 3), "exchange_and_wait_for_slowest_rank": round(dev_ms - steps_only_ms, 3)},
+                       "timed_region_ms": {"steps": round(steps_only_ms, 3), "exchange_and_wait_for_slowest_rank": round(dev_ms - steps_only_ms, 3),
+                                           "steps_fastest_rank": round(steps_ms_ranks[0], 3), "steps_slowest_rank": round(steps_ms_ranks[1], 3),
+                                           "exchange_rank0_wall_ms": {k: round(v, 3) for k, v in gather_split.items()}},
                        "numa_node": numa},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                     "ms_per_step": round(e2e_ms / args.steps, 4), "wall_ms": round(e2e_wall_ms, 3), "device_ms": round(e2e_dev_ms, 3),

@@ -89,11 +89,14 @@ def reprocess_pairs_from_bag(h: Handle, path: str, cloud_topic: str = "/lidar", 
 
 
 _GATHER_BUFFERS: dict = {}
+LAST_GATHER_MS: dict = {}          # wall-clock split of the last gather_results call on this rank (bench.py reports it)
 
 
 def gather_results(local: np.ndarray, group=None, device=None, counts=None) -> np.ndarray:
     """The single exchange step: all ranks contribute their result records, every rank receives the
     concatenation in rank (= frame) order.  Works on NCCL (device tensors over NVLink) and gloo (CPU).
+
+    With equal shares the result is a view of a staging buffer that the next call with the same shapes overwrites (copy it to keep it).
 
     counts: records per rank when every rank can derive them (e.g. from pair_range) -- the exchange is then ONE
     fixed-size all_gather_into_tensor of the padded record blocks with no count round trip and no host
@@ -123,18 +126,29 @@ def gather_results(local: np.ndarray, group=None, device=None, counts=None) -> n
                 torch.empty(world * nmax * item, dtype=torch.uint8, device=dev), torch.empty(world * nmax * item, dtype=torch.uint8, pin_memory=pin))
         _GATHER_BUFFERS.clear()
         _GATHER_BUFFERS[key] = bufs
+    import time
     mine_host, mine, everything, all_host = bufs
+    t0 = time.perf_counter()
     mine_host.numpy()[:local.shape[0] * item] = np.frombuffer(np.ascontiguousarray(local).data, np.uint8)
     mine.copy_(mine_host, non_blocking=True)
+    t1 = time.perf_counter()
     dist.all_gather_into_tensor(everything, mine, group=group)
     all_host.copy_(everything, non_blocking=True)
     if dev.type == "cuda":
         torch.cuda.current_stream(dev).synchronize()
+    t2 = time.perf_counter()
     flat = all_host.numpy()
-    out = np.empty(sum(counts), RESULT_DTYPE)
-    ob = out.view(np.uint8).reshape(-1)
-    pos = 0
-    for r, c in enumerate(counts):
-        ob[pos * item:(pos + c) * item] = flat[r * nmax * item:r * nmax * item + c * item]
-        pos += c
+    total = sum(counts)
+    if all(c == nmax for c in counts):
+        # equal shares: the gathered block IS the record array (a view of the pinned staging buffer, valid until the next call with
+        # these shapes -- copying 8 x 1280 records into fresh pages costs more than the collective)
+        out = flat[:total * item].view(RESULT_DTYPE)
+    else:
+        out = np.empty(total, RESULT_DTYPE)
+        ob = out.view(np.uint8).reshape(-1)
+        pos = 0
+        for r, c in enumerate(counts):
+            ob[pos * item:(pos + c) * item] = flat[r * nmax * item:r * nmax * item + c * item]
+            pos += c
+    LAST_GATHER_MS.update(stage_in=(t1 - t0) * 1e3, collective_and_copy_back=(t2 - t1) * 1e3, unpack=(time.perf_counter() - t2) * 1e3)
     return out
