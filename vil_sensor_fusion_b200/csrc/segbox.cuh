@@ -217,7 +217,8 @@ __device__ __forceinline__ int seg_search(const SegCloud &c, float qx, float qy,
             if (f < f1) {
                 const float4 lo = c.fbox[2 * f], hi = c.fbox[2 * f + 1];
                 s0 = __float_as_int(lo.w); meta = __float_as_int(hi.w);
-                if (flt.arc_may(s0, meta, flt.want)) lbf = seg_box_lb2(lo, hi, qx, qy, qz);
+                lbf = seg_box_lb2(lo, hi, qx, qy, qz);
+                if (__float_as_uint(lbf) <= bound && lbf < dmax && !flt.arc_may(s0, meta, flt.want)) lbf = __int_as_float(0x7f800000);
             }
             const unsigned fmask = __ballot_sync(0xffffffffu, __float_as_uint(lbf) <= bound && lbf < dmax);
             seg_scan_mask(c, fmask, s0, meta, qx, qy, qz, dmax, flt, best, lane);
@@ -283,12 +284,15 @@ __device__ __forceinline__ void seg_search_partners(const SegCloud &c, float qx,
         if (f < f1) {
             const float4 lo = c.fbox[2 * f], hi = c.fbox[2 * f + 1];
             s0 = __float_as_int(lo.w); meta = __float_as_int(hi.w);
-            may2 = f2.arc_may(s0, meta, 2); may3 = f3.arc_may(s0, meta, 3);
             lbf = seg_box_lb2(lo, hi, qx, qy, qz);
+            // the class tests only for the few arcs whose box survives a bound (nearly every arc of the range is admissible for one
+            // class or the other: testing them first cost 30 instructions per arc)
+            const bool c2 = lbf < dmax && __float_as_uint(lbf) <= bound2, c3 = lbf < dmax && __float_as_uint(lbf) <= bound3;
+            if (c2) may2 = f2.arc_may(s0, meta, 2);
+            if (c3) may3 = f3.arc_may(s0, meta, 3);
         }
-        const bool in = lbf < dmax;
-        const unsigned k2 = __ballot_sync(0xffffffffu, in && may2 && __float_as_uint(lbf) <= bound2);
-        const unsigned k3 = __ballot_sync(0xffffffffu, in && may3 && __float_as_uint(lbf) <= bound3);
+        const unsigned k2 = __ballot_sync(0xffffffffu, may2);
+        const unsigned k3 = __ballot_sync(0xffffffffu, may3);
         if (k2) { seg_scan_mask(c, k2, s0, meta, qx, qy, qz, dmax, f2, b2, lane); bound2 = __reduce_min_sync(0xffffffffu, b2.d); }
         if (k3) { seg_scan_mask(c, k3, s0, meta, qx, qy, qz, dmax, f3, b3, lane); bound3 = __reduce_min_sync(0xffffffffu, b3.d); }
     }
