@@ -430,13 +430,12 @@ __global__ void __launch_bounds__(K3A_THREADS, K3A_MINB) k3_assoc(OdomParams p, 
             myq = vlo_to_start(T, wq < n_sharp ? p.sharp_pts[(size_t)cur * p.cap_sharp + wq] : p.flat_pts[(size_t)cur * p.cap_flat + (wq - n_sharp)],
                                p.deskew, p.inv_period);
         }
-        const SegCloud cc = seg_cloud_of(p, 0, last), cs = seg_cloud_of(p, 1, last);
         for (int k = 0; k < nq; k++) {
             const int wq = base + k;
             float4 q;
             q.x = __shfl_sync(0xffffffffu, myq.x, k); q.y = __shfl_sync(0xffffffffu, myq.y, k); q.z = __shfl_sync(0xffffffffu, myq.z, k);
             const bool sharp = wq < n_sharp;
-            const SegCloud &c = sharp ? cc : cs;
+            const SegCloud c = seg_cloud_of(p, sharp ? 0 : 1, last);
             int *o = sharp ? p.cidx + ((size_t)pair * p.cap_sharp + wq) * 2 : p.sidx + ((size_t)pair * p.cap_flat + (wq - n_sharp)) * 3;
             int s1 = -1, s2 = -1, s3 = -1;
             if (round > 0) { s1 = o[0]; s2 = o[1]; if (!sharp) s3 = o[2]; }
