@@ -451,8 +451,7 @@ __global__ void __launch_bounds__(K3A_THREADS, K3A_MINB) k3_assoc(OdomParams p, 
                 if (sharp) {
                     i2 = seg_search(c, q.x, q.y, q.z, 25.0f, f, (s2 >= 0 && s2 < n_tgt) ? s2 : -1, lane, nullptr);
                 } else {
-                    SegFilter f2 = f; f2.want = 2;                           // same-scan partner; f: other-scan partner
-                    seg_search_partners(c, q.x, q.y, q.z, 25.0f, f2, f, (s2 >= 0 && s2 < n_tgt) ? s2 : -1,
+                    seg_search_partners(c, q.x, q.y, q.z, 25.0f, f, (s2 >= 0 && s2 < n_tgt) ? s2 : -1,          // same-scan and other-scan partner
                                         (s3 >= 0 && s3 < n_tgt) ? s3 : -1, lane, i2, i3);
                 }
             }

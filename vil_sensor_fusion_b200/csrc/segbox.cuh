@@ -79,14 +79,15 @@ struct SegFilter {
         const bool fwd = s0 + cnt - 1 > ind, bwd = s0 < ind;                          // the arc holds forward / backward points
         return cls == 2 ? ((fwd && emin <= scan) || (bwd && emax >= scan)) : ((fwd && emax > scan) || (bwd && emin < scan));
     }
-    __device__ __forceinline__ bool operator()(int e, int idx, unsigned &tie) const
+    // `cls`: the class asked for (the two partner searches of a surface point share one filter and differ only in it)
+    __device__ __forceinline__ bool admit(int e, int idx, unsigned &tie, int cls_wanted) const
     {
         if (mode == 0) { tie = (unsigned)idx; return true; }
         if (idx <= lo || idx >= hi || idx == ind) return false;
         int cls;
         if (idx > ind) { cls = e > scan ? 3 : 2; tie = (unsigned)(idx - ind); }
         else { cls = e < scan ? 3 : 2; tie = 0x40000000u + (unsigned)(ind - idx); }
-        return cls == want;
+        return cls == cls_wanted;
     }
 };
 
@@ -95,17 +96,17 @@ struct SegBest { unsigned d, t; int idx; };      // lane-local best: d = float b
 // `meta`: the SEG_META of the arc that holds `idx`, or 0 (unknown).  An arc whose points all carry one scan id (min == max:
 // every arc of a sweep without negative relTime) is filtered on that id, before the point is loaded; otherwise on int(w).
 __device__ __forceinline__ void seg_consider(const SegCloud &c, int idx, int meta, float qx, float qy, float qz, float dmax,
-                                             const SegFilter &flt, SegBest &best)
+                                             const SegFilter &flt, int want, SegBest &best)
 {
     unsigned tie;
     float4 p;
     const int emin = SEG_META_EMIN(meta);
     if (meta != 0 && emin == SEG_META_EMAX(meta) && (unsigned)(emin + SEG_EBIAS - 1) < 1022u) {      // (not a clamped summary)
-        if (!flt(emin, idx, tie)) return;
+        if (!flt.admit(emin, idx, tie, want)) return;
         p = c.pts[idx];
     } else {
         p = c.pts[idx];
-        if (!flt((int)p.w, idx, tie)) return;
+        if (!flt.admit((int)p.w, idx, tie, want)) return;
     }
     const float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
     const float d2 = (dx * dx + dy * dy) + dz * dz;
@@ -117,7 +118,7 @@ __device__ __forceinline__ void seg_consider(const SegCloud &c, int idx, int met
 // group g looks at the g-th set bit, one point per lane.  `s0_mine` / `meta_mine`: first dense index and SEG_META (count in the low byte)
 // of this lane's arc, broadcast from the registers of the lane that tested it (no second trip to the box arrays).
 __device__ __forceinline__ void seg_scan_mask(const SegCloud &c, unsigned fmask, int s0_mine, int meta_mine, float qx, float qy, float qz,
-                                              float dmax, const SegFilter &flt, SegBest &best, int lane)
+                                              float dmax, const SegFilter &flt, int want, SegBest &best, int lane)
 {
     const int g = lane >> SEG_SHIFT, l = lane & (SEG_PTS - 1);
     while (fmask) {
@@ -127,7 +128,7 @@ __device__ __forceinline__ void seg_scan_mask(const SegCloud &c, unsigned fmask,
         for (int k = 0; k < SEG_GROUPS - 1; k++) if (k < g) m &= m - 1u;
         const int bit = m ? __ffs(m) - 1 : 0;
         const int s0 = __shfl_sync(0xffffffffu, s0_mine, bit), meta = __shfl_sync(0xffffffffu, meta_mine, bit);
-        if (m && l < (meta & 0xff)) seg_consider(c, s0 + l, meta, qx, qy, qz, dmax, flt, best);
+        if (m && l < (meta & 0xff)) seg_consider(c, s0 + l, meta, qx, qy, qz, dmax, flt, want, best);
         #pragma unroll
         for (int k = 0; k < SEG_GROUPS; k++) fmask &= fmask - 1u;       // drop the SEG_GROUPS lowest set bits
     }
@@ -144,7 +145,7 @@ __device__ __forceinline__ int seg_search(const SegCloud &c, float qx, float qy,
 {
     const unsigned dmaxb = __float_as_uint(dmax);
     SegBest best; best.d = dmaxb; best.t = 0xFFFFFFFFu; best.idx = -1;
-    if (seed >= 0) seg_consider(c, seed, 0, qx, qy, qz, dmax, flt, best);      // same value in every lane
+    if (seed >= 0) seg_consider(c, seed, 0, qx, qy, qz, dmax, flt, flt.want, best);      // same value in every lane
     unsigned bound = best.d;                     // float bits of the best d2 any lane holds (dmax: none yet)
     if (flt.mode == 0) {
         if (best.idx < 0) {
@@ -167,7 +168,7 @@ __device__ __forceinline__ int seg_search(const SegCloud &c, float qx, float qy,
             }
             const unsigned mf = __reduce_min_sync(0xffffffffu, __float_as_uint(lbf));
             const int srcf = __ffs(__ballot_sync(0xffffffffu, lane < nmem && __float_as_uint(lbf) == mf)) - 1;
-            seg_scan_mask(c, 1u << srcf, s0, meta, qx, qy, qz, dmax, flt, best, lane);
+            seg_scan_mask(c, 1u << srcf, s0, meta, qx, qy, qz, dmax, flt, flt.want, best, lane);
             bound = __reduce_min_sync(0xffffffffu, best.d);
         }
         // ---- phase B: every coarse group / fine segment whose box can hold a point at least as close
@@ -189,7 +190,7 @@ __device__ __forceinline__ int seg_search(const SegCloud &c, float qx, float qy,
                     lbf = seg_box_lb2(lo, hi, qx, qy, qz);
                 }
                 const unsigned fmask = __ballot_sync(0xffffffffu, __float_as_uint(lbf) <= bound && lbf < dmax);
-                seg_scan_mask(c, fmask, s0, meta, qx, qy, qz, dmax, flt, best, lane);
+                seg_scan_mask(c, fmask, s0, meta, qx, qy, qz, dmax, flt, flt.want, best, lane);
                 bound = __reduce_min_sync(0xffffffffu, best.d);
             }
         }
@@ -207,7 +208,7 @@ __device__ __forceinline__ int seg_search(const SegCloud &c, float qx, float qy,
             const unsigned m = __reduce_min_sync(0xffffffffu, mymeta >= 0 ? __float_as_uint(my) : 0x7f800000u);
             if (!(m < dmaxb)) { if (ring_out) *ring_out = 0; return -1; }
             const int src = __ffs(__ballot_sync(0xffffffffu, mymeta >= 0 && __float_as_uint(my) == m)) - 1;
-            seg_scan_mask(c, 1u << src, mys0, mymeta, qx, qy, qz, dmax, flt, best, lane);
+            seg_scan_mask(c, 1u << src, mys0, mymeta, qx, qy, qz, dmax, flt, flt.want, best, lane);
             bound = __reduce_min_sync(0xffffffffu, best.d);
         }
         // ---- phase B
@@ -221,7 +222,7 @@ __device__ __forceinline__ int seg_search(const SegCloud &c, float qx, float qy,
                 if (__float_as_uint(lbf) <= bound && lbf < dmax && !flt.arc_may(s0, meta, flt.want)) lbf = __int_as_float(0x7f800000);
             }
             const unsigned fmask = __ballot_sync(0xffffffffu, __float_as_uint(lbf) <= bound && lbf < dmax);
-            seg_scan_mask(c, fmask, s0, meta, qx, qy, qz, dmax, flt, best, lane);
+            seg_scan_mask(c, fmask, s0, meta, qx, qy, qz, dmax, flt, flt.want, best, lane);
             bound = __reduce_min_sync(0xffffffffu, best.d);
         }
     }
@@ -236,18 +237,18 @@ __device__ __forceinline__ int seg_search(const SegCloud &c, float qx, float qy,
 }
 
 // The two partner searches of a surface point in ONE walk over the arcs of the loops' dense-index range: arcs that can hold
-// same-scan points feed the same-scan partner (filter f2, want 2), arcs that can hold other-scan points the other-scan partner
-// (filter f3, want 3; nearly always an arc is one or the other); each class keeps its own bound.  f2 and f3 share ind / scan /
+// same-scan points feed the same-scan partner (class 2), arcs that can hold other-scan points the other-scan partner
+// (class 3; nearly always an arc is one or the other); each class keeps its own bound.  One filter serves both: ind / scan /
 // lo / hi.  Same results as two seg_search calls.
 __device__ __forceinline__ void seg_search_partners(const SegCloud &c, float qx, float qy, float qz, float dmax,
-                                                    const SegFilter &f2, const SegFilter &f3, int seed2, int seed3, int lane, int &i2, int &i3)
+                                                    const SegFilter &f2, int seed2, int seed3, int lane, int &i2, int &i3)
 {
     const unsigned dmaxb = __float_as_uint(dmax);
     const float INF = __int_as_float(0x7f800000);
     SegBest b2, b3;
     b2.d = b3.d = dmaxb; b2.t = b3.t = 0xFFFFFFFFu; b2.idx = b3.idx = -1;
-    if (seed2 >= 0) seg_consider(c, seed2, 0, qx, qy, qz, dmax, f2, b2);
-    if (seed3 >= 0) seg_consider(c, seed3, 0, qx, qy, qz, dmax, f3, b3);
+    if (seed2 >= 0) seg_consider(c, seed2, 0, qx, qy, qz, dmax, f2, 2, b2);
+    if (seed3 >= 0) seg_consider(c, seed3, 0, qx, qy, qz, dmax, f2, 3, b3);
     int f0 = 0, f1 = 0;
     if (f2.hi - f2.lo > 1) { f0 = f2.f0; f1 = f2.f1; }
     const bool need2 = b2.idx < 0, need3 = b3.idx < 0;          // warp-uniform (the seeds are)
@@ -259,20 +260,20 @@ __device__ __forceinline__ void seg_search_partners(const SegCloud &c, float qx,
             const int s0 = __float_as_int(lo.w), meta = __float_as_int(hi.w);
             const float lb = seg_box_lb2(lo, hi, qx, qy, qz);
             if (f2.arc_may(s0, meta, 2) && lb < my2) { my2 = lb; s2 = s0; m2 = meta; }
-            if (f3.arc_may(s0, meta, 3) && lb < my3) { my3 = lb; s3 = s0; m3 = meta; }
+            if (f2.arc_may(s0, meta, 3) && lb < my3) { my3 = lb; s3 = s0; m3 = meta; }
         }
         if (need2) {
             const unsigned m = __reduce_min_sync(0xffffffffu, m2 >= 0 ? __float_as_uint(my2) : 0x7f800000u);
             if (m < dmaxb) {
                 const int src = __ffs(__ballot_sync(0xffffffffu, m2 >= 0 && __float_as_uint(my2) == m)) - 1;
-                seg_scan_mask(c, 1u << src, s2, m2, qx, qy, qz, dmax, f2, b2, lane);
+                seg_scan_mask(c, 1u << src, s2, m2, qx, qy, qz, dmax, f2, 2, b2, lane);
             }
         }
         if (need3) {
             const unsigned m = __reduce_min_sync(0xffffffffu, m3 >= 0 ? __float_as_uint(my3) : 0x7f800000u);
             if (m < dmaxb) {
                 const int src = __ffs(__ballot_sync(0xffffffffu, m3 >= 0 && __float_as_uint(my3) == m)) - 1;
-                seg_scan_mask(c, 1u << src, s3, m3, qx, qy, qz, dmax, f3, b3, lane);
+                seg_scan_mask(c, 1u << src, s3, m3, qx, qy, qz, dmax, f2, 3, b3, lane);
             }
         }
     }
@@ -289,12 +290,12 @@ __device__ __forceinline__ void seg_search_partners(const SegCloud &c, float qx,
             // class or the other: testing them first cost 30 instructions per arc)
             const bool c2 = lbf < dmax && __float_as_uint(lbf) <= bound2, c3 = lbf < dmax && __float_as_uint(lbf) <= bound3;
             if (c2) may2 = f2.arc_may(s0, meta, 2);
-            if (c3) may3 = f3.arc_may(s0, meta, 3);
+            if (c3) may3 = f2.arc_may(s0, meta, 3);
         }
         const unsigned k2 = __ballot_sync(0xffffffffu, may2);
         const unsigned k3 = __ballot_sync(0xffffffffu, may3);
-        if (k2) { seg_scan_mask(c, k2, s0, meta, qx, qy, qz, dmax, f2, b2, lane); bound2 = __reduce_min_sync(0xffffffffu, b2.d); }
-        if (k3) { seg_scan_mask(c, k3, s0, meta, qx, qy, qz, dmax, f3, b3, lane); bound3 = __reduce_min_sync(0xffffffffu, b3.d); }
+        if (k2) { seg_scan_mask(c, k2, s0, meta, qx, qy, qz, dmax, f2, 2, b2, lane); bound2 = __reduce_min_sync(0xffffffffu, b2.d); }
+        if (k3) { seg_scan_mask(c, k3, s0, meta, qx, qy, qz, dmax, f2, 3, b3, lane); bound3 = __reduce_min_sync(0xffffffffu, b3.d); }
     }
     // ---- (d2, tie) minima
     {
