@@ -189,6 +189,9 @@ int vlo_scan_get_features(vlo_handle *h, int scan, int8_t *label, float *curvatu
  * (transformToEnd).  Results are written to `out` (host). */
 int vlo_register_pairs(vlo_handle *h, const int *last, const int *cur, int n_pairs,
                        const float *seeds, const float *last_transforms, vlo_result *out);
+/* the same without the host synchronisation (rigid batches: no last_transforms): see vlo_register_map_enqueue below -- the records
+ * land in `out_pinned` when the stream gets there; vlo_synchronize, then vlo_results_finish(h, out, n_pairs) */
+int vlo_register_pairs_enqueue(vlo_handle *h, const int *last, const int *cur, int n_pairs, const float *seeds, vlo_result *out_pinned);
 /* parity hooks: with tracing enabled, the correspondence indices of association round `round`
  * (iterations 0,5,10,.. -> round 0,1,2,..) of pair `pair` of the last vlo_register_pairs call */
 int vlo_set_trace(vlo_handle *h, int enable);

@@ -156,3 +156,17 @@ def test_register_map_enqueue_equals_register_map():
             h.register_map_enqueue(np.arange(2), seeds[lo:lo + 2], out.ctypes.data + i * 2 * api.RESULT_DTYPE.itemsize)
         h.synchronize()
         _same(h.results_finish(out), ref)
+
+
+def test_register_pairs_enqueue_equals_register_pairs():
+    """vlo_register_pairs_enqueue + vlo_synchronize + vlo_results_finish = vlo_register_pairs, record for record"""
+    from vil_sensor_fusion_b200 import api
+    raws = [scenes.vlp16_scan(0.1 * k, noise=0.01, seed=k, rolling=False, n_az=900) for k in range(6)]
+    cfg = api.default_config("VLP-16", deskew=0, max_scans=6, max_points=16384)
+    with api.Handle(cfg) as h:
+        h.upload(raws); h.organise(); h.extract()
+        ref = h.register_pairs(np.arange(5), np.arange(1, 6))
+        out = np.zeros(5, api.RESULT_DTYPE)
+        h.register_pairs_enqueue(np.arange(5), np.arange(1, 6), out.ctypes.data)
+        h.synchronize()
+        _same(h.results_finish(out), ref)

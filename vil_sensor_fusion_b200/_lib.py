@@ -89,6 +89,7 @@ SYMBOLS = {
     "vlo_map_build": (C.c_int, [_VP, _VP, C.c_int, _VP, C.c_int, C.c_int]),
     "vlo_register_map": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP]),
     "vlo_register_map_enqueue": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP]),
+    "vlo_register_pairs_enqueue": (C.c_int, [_VP, _VP, _VP, C.c_int, _VP, _VP]),
     "vlo_results_finish": (C.c_int, [_VP, _VP, C.c_int]),
     "vlo_map_get_correspondences": (C.c_int, [_VP, C.c_int, _VP, _VP]),
     "vlo_map_knn": (C.c_int, [_VP, C.c_int, _VP, C.c_int, C.c_int, C.c_float, _VP, _VP]),

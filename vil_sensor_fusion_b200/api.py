@@ -221,6 +221,14 @@ class Handle:
         seeds = np.ascontiguousarray(seeds, np.float32).reshape(len(scans), 6)
         self._check(self.lib.vlo_register_map_enqueue(self._h, _ptr(scans), len(scans), _ptr(seeds), C.c_void_p(out_address)))
 
+    def register_pairs_enqueue(self, last, cur, out_address: int, seeds=None) -> None:
+        """vlo_register_pairs without the host synchronisation (rigid batches); see register_map_enqueue / results_finish"""
+        last = np.ascontiguousarray(last, np.int32)
+        cur = np.ascontiguousarray(cur, np.int32)
+        if seeds is not None:
+            seeds = np.ascontiguousarray(seeds, np.float32).reshape(len(last), 6)
+        self._check(self.lib.vlo_register_pairs_enqueue(self._h, _ptr(last), _ptr(cur), len(last), _ptr(seeds), C.c_void_p(out_address)))
+
     def results_finish(self, records: np.ndarray) -> np.ndarray:
         """after synchronize(): completes records written by register_map_enqueue (in place) and returns them"""
         assert records.dtype == RESULT_DTYPE and records.flags["C_CONTIGUOUS"]

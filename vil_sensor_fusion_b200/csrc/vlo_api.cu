@@ -382,6 +382,24 @@ extern "C" int vlo_register_pairs(vlo_handle *h, const int *last, const int *cur
     return soft;
 }
 
+extern "C" int vlo_register_pairs_enqueue(vlo_handle *h, const int *last, const int *cur, int n_pairs, const float *seeds, vlo_result *out_pinned)
+{
+    if (!h || !last || !cur || !out_pinned || n_pairs < 1) return VLO_ERR_INVALID_ARG;
+    if (n_pairs > h->max_pairs) { h->err = "n_pairs exceeds max_scans"; return VLO_ERR_CAPACITY; }
+    for (int p = 0; p < n_pairs; p++)
+        if (last[p] < 0 || last[p] >= h->sb.n_scans || cur[p] < 0 || cur[p] >= h->sb.n_scans) { h->err = "pair index outside the resident batch"; return VLO_ERR_INVALID_ARG; }
+    cudaSetDevice(h->cfg.device);
+    // (small copies from pageable memory are staged by the runtime before the call returns: see vlo_register_map_enqueue)
+    VLO_CUDA(cudaMemcpyAsync(h->pair_last, last, sizeof(int) * (size_t)n_pairs, cudaMemcpyHostToDevice, h->stream));
+    VLO_CUDA(cudaMemcpyAsync(h->pair_cur, cur, sizeof(int) * (size_t)n_pairs, cudaMemcpyHostToDevice, h->stream));
+    if (seeds) VLO_CUDA(cudaMemcpyAsync(h->pair_seed, seeds, sizeof(float) * 6 * (size_t)n_pairs, cudaMemcpyHostToDevice, h->stream));
+    int rc = vlo_launch_register_pairs(h, n_pairs, seeds ? h->pair_seed : nullptr, nullptr, -1);
+    if (rc) return rc;
+    VLO_CUDA(cudaMemcpyAsync(out_pinned, h->pair_result, sizeof(vlo_result) * (size_t)n_pairs, cudaMemcpyDeviceToHost, h->stream));
+    h->last_n_pairs = n_pairs;
+    return VLO_OK;
+}
+
 extern "C" int vlo_pair_get_correspondences(vlo_handle *h, int pair, int round, int *corner_idx, int *surf_idx)
 {
     if (!h || pair < 0 || pair >= h->last_n_pairs || round < 0 || round >= 5) return VLO_ERR_INVALID_ARG;
