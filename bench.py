@@ -527,9 +527,12 @@ def run_gpu(args):
     h = api.Handle(cfg)
     h.map_build(cm, sm)
     stream = torch.cuda.ExternalStream(h.stream_ptr(), device=torch.device("cuda", local_rank))
-    hB = api.Handle(cfg)                   # the second resident batch of the value loop (its own stream and workspace, the same map)
-    hB.map_build(cm, sm)
-    streamB = torch.cuda.ExternalStream(hB.stream_ptr(), device=torch.device("cuda", local_rank))
+    # further resident batches of the value loop (each its own stream and workspace, the same map): three batches in flight
+    extra_handles = [api.Handle(cfg) for _ in range(2)]
+    for hx in extra_handles:
+        hx.map_build(cm, sm)
+    extra_streams = [torch.cuda.ExternalStream(hx.stream_ptr(), device=torch.device("cuda", local_rank)) for hx in extra_handles]
+    value_handles = [h] + extra_handles
 
     def step(on_device: bool, k: int):
         w0, offs, seeds = window(k)
@@ -557,12 +560,13 @@ def run_gpu(args):
 
     for k in range(max(args.warmup - 1, 0)):
         step(True, k + 1)
-    for k in range(max(args.warmup, 1)):       # the second handle's warm-up
-        w0, offs_w, seeds_w = window(k)
-        hB.upload_raw(dev.data_ptr() + int(offs_all[w0]) * 4 * PF, offs_w, PF, True)
-        hB.organise()
-        hB.extract()
-        hB.register_map(scans_idx, seeds_w)
+    for hx in extra_handles:                   # the other handles' warm-up
+        for k in range(max(args.warmup, 1)):
+            w0, offs_w, seeds_w = window(k)
+            hx.upload_raw(dev.data_ptr() + int(offs_all[w0]) * 4 * PF, offs_w, PF, True)
+            hx.organise()
+            hx.extract()
+            hx.register_map(scans_idx, seeds_w)
     res_pin = torch.empty(args.steps * B * api.RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
     all_counts = [B * args.steps] * world
     if world > 1:
@@ -595,18 +599,20 @@ def run_gpu(args):
     serial_ms = evs0.elapsed_time(evs1)
     stages = h.stage_times()
     h.set_profiling(False)
-    # ---- timed region: the same K steps, alternating between TWO handles (two resident batches, two streams): the kernels of
-    # consecutive steps overlap -- each of them alone leaves issue slots and warp slots idle (profiles/SUMMARY.md) -- 2.0 ms
-    # against 2.5 ms per step on one stream.  Every step is only enqueued; the host synchronises once after the last one.
-    launches0 = h.launch_count() + hB.launch_count()
+    # ---- timed region: the same K steps, dealt in turn to THREE handles (three resident batches, three streams): the kernels of
+    # consecutive steps overlap -- each of them alone leaves issue slots and warp slots idle (profiles/SUMMARY.md) -- 10 steps:
+    # 2.48 ms per step on one stream, 2.02 on two, 1.93 on three, 1.90 on four.  Every step is only enqueued; the host synchronises
+    # once after the last one.
+    launches0 = sum(hx.launch_count() for hx in value_handles)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
-    streamB.wait_event(ev0)
+    for sx in extra_streams:
+        sx.wait_event(ev0)
     for k in range(args.steps):
-        enqueue_step(h if (k & 1) == 0 else hB, k)
-    h.synchronize()
-    hB.synchronize()
+        enqueue_step(value_handles[k % len(value_handles)], k)
+    for hx in value_handles:
+        hx.synchronize()
     res_all_steps = h.results_finish(np.frombuffer(res_pin.numpy(), api.RESULT_DTYPE).copy())
     all_res = [res_all_steps[k * B:(k + 1) * B] for k in range(args.steps)]
     ev_mid = torch.cuda.Event(enable_timing=True)
@@ -621,7 +627,7 @@ def run_gpu(args):
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
     steps_only_ms = ev0.elapsed_time(ev_mid)
-    launches = h.launch_count() + hB.launch_count() - launches0
+    launches = sum(hx.launch_count() for hx in value_handles) - launches0
     res_all = np.concatenate(all_res)
     ok = int(np.sum(res_all["status"] == 0))
     mean_iters = float(np.mean(res_all["iterations"]))
@@ -826,7 +832,7 @@ def run_gpu(args):
                        "pool": ("%d distinct scans at poses perturbed by N(0, 0.1 m) / N(0, 0.5 deg), seeds 1..%d; a step takes %d consecutive pool "
                                 "entries from a start that moves by 61 per step" % (pool_n, pool_n, B)) if not args.r01_workload else "round-1 pool: 8 scans, one fixed offset",
                        "exchange": "one all_gather_into_tensor of the result records per job" if world > 1 else "none",
-                       "value_loop": "K steps alternating between two handles (two resident batches on two streams, kernels of consecutive steps "
+                       "value_loop": "K steps dealt in turn to three handles (three resident batches on three streams, kernels of consecutive steps "
                                      "overlap), every step only enqueued, one host synchronisation after the last",
                        "serial_pass": {"ms_per_step": round(serial_ms / args.steps, 4), "what": "the same K steps on one handle / one stream with the stage "
                                        "timers on: `stages` and `roofline` are taken there, every kernel running alone"},
