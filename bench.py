@@ -213,7 +213,7 @@ def whole_bag_pairs_leg(args, rank, world, local_rank, barrier, peak):
     cfg = api.default_config("HDL-64E", deskew=0, max_scans=PB, max_points=npts, max_map_points=0, device=local_rank)
     # two handles (two resident batches, two streams) take alternate batches of the job: the kernels of consecutive batches overlap;
     # every batch is only enqueued (vlo_register_pairs_enqueue), the host synchronises once per job
-    hs = [api.Handle(cfg), api.Handle(cfg)]
+    hs = [api.Handle(cfg) for _ in range(int(os.environ.get("VLO_BAG_HANDLES", "2")))]
     h = hs[0]
     stream = torch.cuda.ExternalStream(h.stream_ptr(), device=torch.device("cuda", local_rank))
     raws = [torch.empty((PB, npts, 4), dtype=torch.float32, device="cuda") for _ in hs]
@@ -222,7 +222,7 @@ def whole_bag_pairs_leg(args, rank, world, local_rank, barrier, peak):
     item = api.RESULT_DTYPE.itemsize
     res_pin = torch.empty(max(hi - lo, 1) * item, dtype=torch.uint8).pin_memory()
 
-    def job(time_synth=False, n_handles=2):
+    def job(time_synth=False, n_handles=len(hs)):
         k, b, pos, synth_ms = lo, 0, 0, 0.0
         while k < hi:
             hh, raw = hs[b % n_handles], raws[b % n_handles]
